@@ -1,0 +1,223 @@
+/* pzb200.h -- C-ABI of libpzb200.so: a B200 (sm_100a) native replacement for the per-operator GPU
+ * backend of PuzzleLib (the cuDNN/cuBLAS/NVRTC layer under Cuda/Backend.py).
+ *
+ * Every function returns 0 on success or a PZ_ERR_* code; pz_last_error() gives the message of the last
+ * failure on the calling thread.  All pointers named x/y/dx/... are DEVICE pointers unless the name says
+ * "host".  `stream` is a cudaStream_t passed as void* (NULL = the library's default stream, which is the
+ * CUDA legacy default stream -- the reference enqueues everything there, SURVEY 8b "Threading / streams").
+ * Tensors are dense row-major NCHW / (rows, cols), as in the reference (CuDnn.c:137-158,202-204).
+ *
+ * Each entry names the reference interface it replaces (paths relative to the PuzzleLib tree).
+ */
+#ifndef PZB200_H
+#define PZB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---------------------------------------------------------------- status / dtypes / enums */
+enum { PZ_OK = 0, PZ_ERR_VALUE = 1, PZ_ERR_CUDA = 2, PZ_ERR_MEMORY = 3, PZ_ERR_NCCL = 4, PZ_ERR_UNSUPPORTED = 5 };
+
+/* dtype codes (reference: Cuda_DataType, Cuda/Source/Core/Driver.h:164-194; bf16 is new) */
+enum {
+	PZ_F32 = 0, PZ_F16 = 1, PZ_BF16 = 2, PZ_F64 = 3,
+	PZ_I8 = 4, PZ_U8 = 5, PZ_I16 = 6, PZ_U16 = 7, PZ_I32 = 8, PZ_U32 = 9, PZ_I64 = 10, PZ_U64 = 11
+};
+
+/* activation kinds (reference: Cuda/Kernels/ElementWise.py:9-492) */
+enum {
+	PZ_ACT_SIGMOID = 0, PZ_ACT_TANH = 1, PZ_ACT_RELU = 2, PZ_ACT_LEAKYRELU = 3, PZ_ACT_ELU = 4,
+	PZ_ACT_SOFTPLUS = 5, PZ_ACT_CLIP = 6, PZ_ACT_GELU = 7
+};
+
+/* pooling modes: values of cudnnPoolingMode_t, exported by the reference as CuDnn.POOL_MODE_*
+ * (Cuda/Backend.py:104-108) */
+enum { PZ_POOL_MAX = 0, PZ_POOL_AVG_WITH_PAD = 1, PZ_POOL_AVG_NO_PAD = 2, PZ_POOL_MAX_DETERMINISM = 3 };
+
+/* batch-norm modes: cudnnBatchNormMode_t (Cuda/Backend.py:122-125) */
+enum { PZ_BN_PER_ACTIVATION = 0, PZ_BN_SPATIAL = 1, PZ_BN_SPATIAL_PERSISTENT = 2 };
+
+/* softmax modes: cudnnSoftmaxMode_t (Cuda/Backend.py:111-113): per-activation = INSTANCE, spatial = CHANNEL */
+enum { PZ_SOFTMAX_PER_ACTIVATION = 0, PZ_SOFTMAX_SPATIAL = 1 };
+
+const char* pz_last_error(void);
+int pz_version(void);
+
+/* ---------------------------------------------------------------- device / memory / streams
+ * replaces Cuda/Source/Core/{Device,Buffer,Allocator,Stream}.c */
+int pz_device_count(int* count);                               /* Device.c  Device.count()        */
+int pz_device_set(int index);                                  /* Device.c  Device.set()          */
+int pz_device_get(int* index);
+int pz_device_name(int index, char* buf, int buflen);          /* Device.c  Device.name()         */
+int pz_device_sm_count(int* count);
+int pz_device_cc(int* major, int* minor);
+int pz_device_synchronize(void);                               /* Device.c  Device.synchronize()  */
+int pz_mem_info(size_t* free_bytes, size_t* total_bytes);      /* Driver.c  getMemoryInfo()       */
+
+int pz_malloc(void** ptr, size_t nbytes);                      /* Buffer.c  Cuda_Buffer_init      */
+int pz_free(void* ptr);
+int pz_host_alloc(void** ptr, size_t nbytes);                  /* pinned host staging             */
+int pz_host_free(void* ptr);
+
+/* caching allocator with the reference's bin function: sizes rounded up to (4..7)*2^e, i.e. two mantissa
+ * bits (Allocator.c:29-67); blocks return to their bin and go back to the driver only on free_held */
+int pz_pool_create(void** pool);                               /* Allocator.c MemoryPool()        */
+int pz_pool_destroy(void* pool);
+int pz_pool_alloc(void* pool, size_t nbytes, void** ptr, size_t* granted);
+int pz_pool_release(void* pool, void* ptr, size_t granted);    /* Allocator.c MemoryPool_hold     */
+int pz_pool_free_held(void* pool);                             /* Allocator.c freeHeld()          */
+int pz_pool_stats(void* pool, size_t* held_blocks, size_t* held_bytes, size_t* active_blocks, size_t* active_bytes);
+size_t pz_pool_alloc_size(size_t nbytes);                      /* bin -> block size, for tests    */
+
+int pz_memcpy_h2d(void* dst, const void* host_src, size_t nbytes, void* stream, int async);
+int pz_memcpy_d2h(void* host_dst, const void* src, size_t nbytes, void* stream, int async);
+int pz_memcpy_d2d(void* dst, const void* src, size_t nbytes, void* stream);
+/* kind: 0 = d2d, 1 = h2d, 2 = d2h (Driver.c memcpy2D, used by GPUArray slices and concatenate/split/tile) */
+int pz_memcpy2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height, int kind,
+				void* stream);
+int pz_memset8(void* ptr, uint8_t value, size_t count, void* stream);    /* Buffer.c fillD8  */
+int pz_memset16(void* ptr, uint16_t value, size_t count, void* stream);  /* Buffer.c fillD16 */
+int pz_memset32(void* ptr, uint32_t value, size_t count, void* stream);  /* Buffer.c fillD32 */
+
+int pz_stream_create(void** stream);
+int pz_stream_destroy(void* stream);
+int pz_stream_synchronize(void* stream);
+int pz_event_create(void** event);
+int pz_event_destroy(void* event);
+int pz_event_record(void* event, void* stream);
+int pz_event_synchronize(void* event);
+int pz_event_elapsed_ms(void* start, void* stop, float* ms);
+int pz_stream_wait_event(void* stream, void* event);
+
+/* number of kernels this library has launched on the calling process since load (bench "gpu_launches") */
+uint64_t pz_launch_count(void);
+
+/* ---------------------------------------------------------------- elementwise (bandwidth-bound)
+ * replaces the NVRTC-JIT kernels of Cuda/Kernels/ElementWise.py and Cuda/GPUArray.py */
+/* out = f(in);  a, b are the optional scalars (leakyRelu a, elu a, clip a,b). ElementWise.py:9-445 */
+int pz_act_fwd(int kind, int dtype, void* out, const void* in, int64_t n, float a, float b, void* stream);
+/* ingrad = f'(outgrad, ref) where ref = the activation's OUTPUT (its INPUT for gelu). ElementWise.py:36-492 */
+int pz_act_bwd(int kind, int dtype, void* ingrad, const void* outgrad, const void* ref, int64_t n, float a, float b,
+			   void* stream);
+int pz_axpy(int dtype, void* y, const void* x, float alpha, int64_t n, void* stream);       /* toVectorAddVectorKer :582-606  */
+int pz_axpby(int dtype, void* out, const void* x, float alpha, const void* y, float beta, int64_t n,
+			 void* stream);                                                                 /* addKer :1017-1045 (also Grid.py:133) */
+int pz_scale_shift(int dtype, void* out, const void* in, float a, float b, int64_t n, void* stream); /* linearKer :1073-1099 */
+int pz_mul(int dtype, void* out, const void* a, const void* b, int64_t n, void* stream);    /* mulKer :1047-1071 */
+int pz_add2(int dtype, void* out, const void* a, const void* b, int64_t n, void* stream);   /* Add.py:15-23 as one pass */
+int pz_cast(int dst_dtype, void* dst, int src_dtype, const void* src, int64_t n, void* stream); /* GPUArray.py astype */
+int pz_fill64(void* ptr, uint64_t value, int64_t count, void* stream);                      /* GPUArray.py:167-180 8-byte fill */
+/* mom = momRate*mom + learnRate*grad; param += mom  (ElementWise.py:771-800 classicMomSGD) */
+int pz_sgd_momentum(int dtype, void* param, const void* grad, void* mom, float learn_rate, float mom_rate,
+					int64_t n, void* stream);
+/* min / max reduction of a float tensor into a 1-element device buffer (GPUArray.py min/max) */
+int pz_reduce_minmax(int dtype, const void* in, int64_t n, int want_max, void* out, void* stream);
+
+/* ---------------------------------------------------------------- matrix-vector helpers
+ * replaces Cuda/Kernels/MatVec.py */
+/* out[z][y][x] = mat[z][y][x] + vec: axis=1, vecdim==cols: vec[z][x]; axis=1, vecdim<cols: vec[x % vecdim];
+ * axis=0: vec[z][y]   (MatVec.py:128-171,346-374) */
+int pz_addvec2mat(int dtype, void* out, const void* mat, const void* vec, int64_t z, int64_t rows, int64_t cols,
+				  int axis, int64_t vecdim, void* stream);
+/* tensor viewed as [z][h][w]: reduce_rows=1 -> out[z][h] = beta*out + alpha*sum_w ; else out[z][w] = beta*out +
+ * alpha*sum_h   (MatVec.py:60-91,273-308) */
+int pz_matsum(int dtype, void* out, const void* tensor, int64_t z, int64_t h, int64_t w, int reduce_rows,
+			  float alpha, float beta, void* stream);
+/* argmax/argmin along the middle axis of [z][h][w] (w=1 for the last-axis case after the caller's view)
+ * -> int32 idx[z][w]; first occurrence wins (MatVec.py:8-57,231-268) */
+int pz_argminmax(int dtype, int32_t* idx, const void* tensor, int64_t z, int64_t h, int64_t w, int want_max,
+				 void* stream);
+
+/* ---------------------------------------------------------------- batch normalisation
+ * replaces cudnnBatchNormalizationForwardTraining/Inference/Backward (CuDnnNorm.c:31-71,158-194).
+ * x, y: [N][C][S] of `dtype`; scale/bias/mean/var/saves: fp32 [C] (CuDnnNorm.c:118-121). */
+int pz_bn_fwd_train(int dtype, const void* x, void* y, int64_t N, int64_t C, int64_t S, const float* scale,
+					const float* bias, float* running_mean, float* running_var, float* save_mean,
+					float* save_invvar, double eps, double factor, void* stream);
+int pz_bn_fwd_infer(int dtype, const void* x, void* y, int64_t N, int64_t C, int64_t S, const float* scale,
+					const float* bias, const float* mean, const float* var, double eps, void* stream);
+int pz_bn_bwd(int dtype, const void* x, const void* dy, void* dx, int64_t N, int64_t C, int64_t S,
+			  const float* scale, const float* save_mean, const float* save_invvar, float* dscale, float* dbias,
+			  void* stream);
+
+/* ---------------------------------------------------------------- pooling
+ * replaces cudnnPoolingForward/Backward (CuDnnPool.c:81,171) -- 2-D; 1-D is H=1 */
+int pz_pool2d_fwd(int dtype, int mode, const void* x, void* y, int64_t planes, int H, int W, int OH, int OW,
+				  int fh, int fw, int sh, int sw, int ph, int pw, void* stream);
+int pz_pool2d_bwd(int dtype, int mode, const void* x, const void* y, const void* dy, void* dx, int64_t planes,
+				  int H, int W, int OH, int OW, int fh, int fw, int sh, int sw, int ph, int pw, void* stream);
+/* fp32 max-pool with int32 argmax mask, bit-exact with Cuda/Kernels/Pool.py:10-112 */
+int pz_maxpool2d_mask_fwd(const float* x, float* y, int32_t* mask, int64_t planes, int H, int W, int OH, int OW,
+						  int fh, int fw, int sh, int sw, int ph, int pw, void* stream);
+int pz_maxpool2d_mask_bwd(const float* dy, const int32_t* mask, float* dx, int64_t planes, int H, int W, int OH,
+						  int OW, int fh, int fw, int sh, int sw, int ph, int pw, void* stream);
+/* y must be zeroed by the caller (reference uses GPUArray.zeros, Pool.py:178) */
+int pz_maxunpool2d_fwd(const float* x, const int32_t* mask, float* y, int64_t planes, int inHW, int outHW,
+					   void* stream);
+int pz_maxunpool2d_bwd(const float* dy, const int32_t* mask, float* dx, int64_t planes, int inHW, int outHW,
+					   void* stream);
+
+/* ---------------------------------------------------------------- softmax
+ * replaces cudnnSoftmaxForward/Backward, SOFTMAX_ACCURATE (CuDnn.c:984,1063). Tensor [N][C][S]:
+ * spatial mode normalises over C for each (n, s); per-activation mode over C*S for each n. */
+int pz_softmax_fwd(int dtype, int mode, const void* x, void* y, int64_t N, int64_t C, int64_t S, void* stream);
+int pz_softmax_bwd(int dtype, int mode, const void* y, const void* dy, void* dx, int64_t N, int64_t C, int64_t S,
+				   void* stream);
+
+/* ---------------------------------------------------------------- GEMM (tcgen05 / TMEM)
+ * replaces cublasGemmEx as called by CuBlas_Context_gemm (CuBlas.c:327-403): row-major
+ * C[M][N] = alpha * op(A) * op(B) + beta * C, fp32 storage computed as TF32 with fp32 accumulation in TMEM
+ * (the reference sets CUBLAS_GEMM_DEFAULT_TENSOR_OP, CuBlas.c:91-106).  op(A) is M x K, op(B) is K x N;
+ * lda/ldb/ldc are the row pitches (elements) of the STORED matrices.  bias (optional, length N) is added
+ * in the epilogue (Linear.py:36-40 addVecToMat folded in). */
+int pz_gemm(int dtype, const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, int64_t lda,
+			int64_t ldb, int64_t ldc, int transA, int transB, float alpha, float beta, const void* bias,
+			void* stream);
+
+/* ---------------------------------------------------------------- convolution (implicit GEMM on tcgen05)
+ * replaces cudnnConvolutionForward / BackwardData / BackwardFilter / BackwardBias
+ * (CuDnn.c:397-449,517-571,652-712,375-394).  Cross-correlation, NCHW, filter [K][C/G][R][S].
+ * P,Q: output spatial size.  All three passes accept stride / pad / dilation / groups. */
+typedef struct pz_conv2d_desc {
+	int N, C, H, W;        /* input  (data)  tensor */
+	int K, R, S;           /* filter: K output maps, R x S taps, C/groups input maps per filter */
+	int P, Q;              /* output (grad)  spatial size */
+	int stride_h, stride_w, pad_h, pad_w, dil_h, dil_w, groups;
+} pz_conv2d_desc;
+
+/* y = conv(x, w) (+ bias[K]) */
+int pz_conv2d_fprop(int dtype, const pz_conv2d_desc* d, const void* x, const void* w, const void* bias, void* y,
+					void* stream);
+/* dx = conv_transpose(dy, w) (+ bias[C], used when this is a Deconv forward, Dnn.py:211-215).
+ * workspace: pz_conv2d_dgrad_workspace() bytes of device scratch (re-packed filter). */
+size_t pz_conv2d_dgrad_workspace(int dtype, const pz_conv2d_desc* d);
+int pz_conv2d_dgrad(int dtype, const pz_conv2d_desc* d, const void* dy, const void* w, const void* bias, void* dx,
+					void* workspace, size_t workspace_bytes, void* stream);
+/* dw = alpha * sum_{n,p,q} x (*) dy + beta * dw   (in place; CuDnn.c:682-685 scale/momentum) */
+int pz_conv2d_wgrad(int dtype, const pz_conv2d_desc* d, const void* x, const void* dy, void* dw, float alpha,
+					float beta, void* stream);
+/* db[c] = alpha * sum_{n,s} t[n][c][s] + beta * db[c]   (cudnnConvolutionBackwardBias, CuDnn.c:375-394) */
+int pz_bias_grad(int dtype, const void* t, void* db, int64_t N, int64_t C, int64_t S, float alpha, float beta,
+				 void* stream);
+
+/* ---------------------------------------------------------------- data-parallel gradient sync (NCCL over NVLink)
+ * replaces Grid.py's CUDA-IPC parent/child star (Grid.py:66-157; Buffer.c:411-424) */
+int pz_nccl_unique_id(void* id128);                                  /* 128-byte ncclUniqueId, host memory */
+int pz_nccl_comm_init(void** comm, int nranks, int rank, const void* id128);
+int pz_nccl_comm_destroy(void* comm);
+/* in-place sum all-reduce then scale by `scale` (1/P for Grid.sumTensor's mean, Grid.py:126-133) */
+int pz_nccl_allreduce_mean(void* comm, int dtype, void* buf, int64_t count, float scale, void* stream);
+int pz_nccl_broadcast(void* comm, int dtype, void* buf, int64_t count, int root, void* stream); /* Grid.py:114-121 */
+/* fused: all-reduce(sum) the flat gradient, then mom = mr*mom + lr*(grad/P); param += mom in one pass
+ * (Optimizer.py:166-170 + MomentumSGD.py:24-27) */
+int pz_nccl_allreduce_sgd_momentum(void* comm, int dtype, void* param, void* grad, void* mom, int64_t count,
+								   float scale, float learn_rate, float mom_rate, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PZB200_H */

@@ -1,0 +1,62 @@
+// pz_common.h -- shared helpers for the libpzb200 C-ABI library (sm_100a only).
+//
+// Error model: every exported entry point returns an int status (0 = OK) and
+// leaves a thread-local message retrievable through pz_last_error(); the
+// ctypes shim raises the reference's exception classes from it
+// (reference: Cuda/Source/Core/Common.h:119-139, Libs/Libs.h:30-44).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/pzb200.h"
+
+void pz_set_error(int code, const char* fmt, ...);
+
+#define PZ_CHECK_CUDA(expr)                                                                      \
+	do {                                                                                         \
+		cudaError_t _e = (expr);                                                                 \
+		if (_e != cudaSuccess) {                                                                 \
+			pz_set_error(PZ_ERR_CUDA, "%s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+			return PZ_ERR_CUDA;                                                                  \
+		}                                                                                        \
+	} while (0)
+
+#define PZ_REQUIRE(cond, ...)                     \
+	do {                                          \
+		if (!(cond)) {                            \
+			pz_set_error(PZ_ERR_VALUE, __VA_ARGS__); \
+			return PZ_ERR_VALUE;                  \
+		}                                         \
+	} while (0)
+
+#define PZ_LAUNCH_CHECK()                                                                        \
+	do {                                                                                         \
+		cudaError_t _e = cudaGetLastError();                                                     \
+		if (_e != cudaSuccess) {                                                                 \
+			pz_set_error(PZ_ERR_CUDA, "%s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+			return PZ_ERR_CUDA;                                                                  \
+		}                                                                                        \
+	} while (0)
+
+static inline cudaStream_t pz_stream(void* s) { return (cudaStream_t)s; }
+
+int pz_num_sms();
+void pz_count_launch(int n);
+
+static inline int64_t pz_cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+static inline size_t pz_dtype_size(int dtype)
+{
+	switch (dtype) {
+		case PZ_F32: case PZ_I32: case PZ_U32: return 4;
+		case PZ_F16: case PZ_BF16: case PZ_I16: case PZ_U16: return 2;
+		case PZ_I8: case PZ_U8: return 1;
+		case PZ_F64: case PZ_I64: case PZ_U64: return 8;
+		default: return 0;
+	}
+}

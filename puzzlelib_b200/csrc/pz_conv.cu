@@ -1,0 +1,326 @@
+// pz_conv.cu -- 2-D convolution forward / backward-data / backward-filter as implicit GEMMs on the
+// tcgen05 engine of pz_umma.cuh, operating directly on the reference's NCHW tensors.
+//
+// Replaces cudnnConvolutionForward / BackwardData / BackwardFilter / BackwardBias as driven by
+// CuDnn_Context_convNd, _convNdBackwardData, _convNdBackwardParams (reference
+// Cuda/Source/Libs/CuDnn.c:397-449, 517-571, 652-712, 375-394).
+//
+// GEMM mapping (TMEM lanes = the contiguous dimension of the output, so epilogue stores coalesce):
+//   fprop : D[(n,p,q)][k]     = sum_{c,r,s}  x[n,c,p*s-pad+r*dil,...] * w[k,c,r,s]        -> y   NCHW
+//   dgrad : D[(n,h,w)][c]     = sum_{k,r,s}  dy[n,k,(h+pad-r*dil)/s,...] * w[k,c,r,s]     -> dx  NCHW
+//   wgrad : D[(c,r,s)][k]     = sum_{n,p,q}  x[n,c,p*s-pad+r*dil,...] * dy[n,k,p,q]       -> dw  KCRS
+// The activations are gathered by the producer warps with the index algebra of pzumma::Operand, so no
+// im2col matrix, NHWC copy or zero-inserted gradient is ever materialised in HBM.
+#include "pz_umma.cuh"
+
+using namespace pzumma;
+
+namespace {
+
+struct Geo {
+	int N, C, H, W, K, R, S, P, Q, sh, sw, ph, pw, dh, dw, G, Cg, Kg;
+};
+
+int check_desc(int dtype, const pz_conv2d_desc* d, Geo& g)
+{
+	PZ_REQUIRE(dtype == PZ_F32, "conv2d: only float32 storage is implemented (got dtype %d)", dtype);
+	PZ_REQUIRE(d != nullptr, "conv2d: null descriptor");
+	g = Geo{d->N, d->C, d->H, d->W, d->K, d->R, d->S, d->P, d->Q, d->stride_h, d->stride_w, d->pad_h, d->pad_w,
+			d->dil_h, d->dil_w, d->groups, 0, 0};
+	PZ_REQUIRE(g.N > 0 && g.C > 0 && g.H > 0 && g.W > 0 && g.K > 0 && g.R > 0 && g.S > 0, "conv2d: invalid tensor dims");
+	PZ_REQUIRE(g.sh > 0 && g.sw > 0 && g.dh > 0 && g.dw > 0 && g.ph >= 0 && g.pw >= 0 && g.G > 0, "conv2d: invalid conv params");
+	PZ_REQUIRE(g.C % g.G == 0 && g.K % g.G == 0, "conv2d: maps not divisible by groups");
+	PZ_REQUIRE(g.P > 0 && g.Q > 0, "conv2d: empty output");
+	// output size as the reference computes it (CuDnn.c:242-266); a deconv "postpad" < stride keeps it exact
+	PZ_REQUIRE(g.H + 2 * g.ph - g.dh * (g.R - 1) - 1 >= 0 && g.W + 2 * g.pw - g.dw * (g.S - 1) - 1 >= 0,
+			   "conv2d: filter does not fit the padded input");
+	PZ_REQUIRE(g.P == (g.H + 2 * g.ph - g.dh * (g.R - 1) - 1) / g.sh + 1 &&
+			   g.Q == (g.W + 2 * g.pw - g.dw * (g.S - 1) - 1) / g.sw + 1,
+			   "conv2d: output size %dx%d inconsistent with input %dx%d", g.P, g.Q, g.H, g.W);
+	g.Cg = g.C / g.G;
+	g.Kg = g.K / g.G;
+	long long xin = (long long)g.N * g.C * g.H * g.W, yout = (long long)g.N * g.K * g.P * g.Q;
+	PZ_REQUIRE(xin < (1ll << 31) && yout < (1ll << 31), "conv2d: tensor exceeds 2^31 elements");
+	return PZ_OK;
+}
+
+// true when no tap of any output position can fall outside the un-padded input
+bool taps_in_bounds(const Geo& g)
+{
+	return g.ph == 0 && g.pw == 0 && (long long)(g.P - 1) * g.sh + (long long)g.dh * (g.R - 1) < g.H &&
+		   (long long)(g.Q - 1) * g.sw + (long long)g.dw * (g.S - 1) < g.W;
+}
+
+void set_splits(GemmParams& p, long long tiles, int min_kb_per_split)
+{
+	int splits = 1;
+	if (tiles < 2ll * pz_num_sms()) {
+		splits = (int)((3ll * pz_num_sms()) / (tiles > 0 ? tiles : 1));
+		if (splits > p.kblocks / min_kb_per_split) splits = p.kblocks / min_kb_per_split;
+		if (splits < 1) splits = 1;
+	}
+	p.kb_per_split = (int)pz_cdiv(p.kblocks, splits);
+	p.splits = (int)pz_cdiv(p.kblocks, p.kb_per_split);
+}
+
+// wt[g][c][ko][rs] = w[g*Kg + ko][c][rs] : the filter with the reduction index (ko, r, s) contiguous
+__global__ void repack_filter_dgrad(const float* __restrict__ w, float* __restrict__ wt, int Kg, int Cg, int RS, long long total)
+{
+	long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= total) return;
+	int rs = (int)(i % RS);
+	long long t = i / RS;
+	int ko = (int)(t % Kg);
+	t /= Kg;
+	int c = (int)(t % Cg);
+	int g = (int)(t / Cg);
+	wt[i] = w[(((long long)g * Kg + ko) * Cg + c) * RS + rs];
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) bias_grad_kernel(const float* __restrict__ t, float* __restrict__ db, long long N,
+															 long long C, long long S, float alpha, int nsplit)
+{
+	// grid = (C, nsplit): each CTA reduces a slice of the images of one channel, then one red.add
+	const long long c = blockIdx.x;
+	float acc = 0.0f;
+	for (long long n = blockIdx.y; n < N; n += nsplit) {
+		const float* plane = t + (n * C + c) * S;
+		for (long long s = threadIdx.x; s < S; s += THREADS) acc += plane[s];
+	}
+	__shared__ float part[THREADS / 32];
+	#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+	if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+	__syncthreads();
+	if (threadIdx.x < 32) {
+		acc = threadIdx.x < THREADS / 32 ? part[threadIdx.x] : 0.0f;
+		#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+		if (threadIdx.x == 0) atomicAdd(db + c, alpha * acc);
+	}
+}
+
+int prescale(float* buf, long long n, float beta, void* stream)
+{
+	if (beta == 0.0f) return pz_memset8(buf, 0, (size_t)n * 4, stream);
+	if (beta == 1.0f) return PZ_OK;
+	return pz_scale_shift(PZ_F32, buf, buf, beta, 0.0f, n, stream);
+}
+
+}  // namespace
+
+extern "C" {
+
+int pz_conv2d_fprop(int dtype, const pz_conv2d_desc* d, const void* x, const void* w, const void* bias, void* y, void* stream)
+{
+	Geo g;
+	int st = check_desc(dtype, d, g);
+	if (st != PZ_OK) return st;
+	const int RS = g.R * g.S, PQ = g.P * g.Q, HW = g.H * g.W;
+
+	GemmParams p{};
+	Operand& A = p.A;   // im2col view of x: rows (n,p,q), k (c,r,s)
+	A.ptr = (const float*)x;
+	A.rd12 = make_fastdiv(PQ); A.rd2 = make_fastdiv(g.Q);
+	A.kd12 = make_fastdiv(RS); A.kd2 = make_fastdiv(g.S);
+	A.rs0 = g.C * HW; A.ks0 = HW;
+	A.ah = g.sh; A.bh = g.dh; A.ch = -g.ph;
+	A.aw = g.sw; A.bw = g.dw; A.cw = -g.pw;
+	A.H = g.H; A.W = g.W; A.Wd = g.W;
+	A.cdh = A.cdw = 1;
+	A.rows = g.N * PQ; A.kdim = g.Cg * RS;
+	A.group_stride = (long long)g.Cg * HW;
+
+	p.B = dense_k((const float*)w, g.Kg, g.Cg * RS, (long long)g.Cg * RS);
+	p.B.group_stride = (long long)g.Kg * g.Cg * RS;
+
+	Epilogue& E = p.E;
+	E.out = (float*)y;
+	E.bias = (const float*)bias;
+	E.md12 = make_fastdiv(PQ); E.md2 = make_fastdiv(0);
+	E.ms0 = g.K * PQ; E.ms1 = 0; E.ms2 = 1;
+	E.ncs = PQ;
+	E.M = g.N * PQ; E.N = g.Kg;
+	E.alpha = 1.0f; E.beta = 0.0f;
+	E.bias_mode = bias ? 1 : 0;
+	E.atomic = 0;
+	E.group_stride = (long long)g.Kg * PQ;
+	E.bias_group_stride = g.Kg;
+
+	p.kblocks = (int)pz_cdiv(A.kdim, BK);
+	p.splits = 1;
+	p.kb_per_split = p.kblocks;
+	const int amode = taps_in_bounds(g) ? MODE_MN_SIMPLE : MODE_MN_GENERAL;
+	return launch(p, pick_bn(g.Kg), amode, MODE_K_SIMPLE, false, g.G, pz_stream(stream));
+}
+
+size_t pz_conv2d_dgrad_workspace(int dtype, const pz_conv2d_desc* d)
+{
+	(void)dtype;
+	if (!d) return 0;
+	if (d->R == 1 && d->S == 1 && d->pad_h == 0 && d->pad_w == 0 && d->stride_h == 1 && d->stride_w == 1) return 0;
+	return (size_t)d->K * (d->C / (d->groups > 0 ? d->groups : 1)) * d->R * d->S * sizeof(float);
+}
+
+int pz_conv2d_dgrad(int dtype, const pz_conv2d_desc* d, const void* dy, const void* w, const void* bias, void* dx,
+					void* workspace, size_t workspace_bytes, void* stream)
+{
+	Geo g;
+	int st = check_desc(dtype, d, g);
+	if (st != PZ_OK) return st;
+	const int RS = g.R * g.S, PQ = g.P * g.Q, HW = g.H * g.W;
+	const bool is1x1 = g.R == 1 && g.S == 1;
+	const bool strided = g.sh > 1 || g.sw > 1;
+
+	GemmParams p{};
+	Operand& A = p.A;
+	Epilogue& E = p.E;
+	E.out = (float*)dx;
+	E.bias = (const float*)bias;
+	E.alpha = 1.0f; E.beta = 0.0f;
+	E.bias_mode = bias ? 1 : 0;
+	E.atomic = 0;
+	E.ncs = HW;
+	E.N = g.Cg;
+	E.group_stride = (long long)g.Cg * HW;
+	E.bias_group_stride = g.Cg;
+	p.splits = 1;
+
+	if (is1x1 && g.ph == 0 && g.pw == 0 && !(strided && bias)) {
+		// 1x1: dx[n,c,p*sh,q*sw] = sum_k dy[n,k,p,q] * w[k,c]; other positions of dx are zero.
+		if (strided) {
+			st = pz_memset8(dx, 0, (size_t)g.N * g.C * HW * 4, stream);
+			if (st != PZ_OK) return st;
+		}
+		A.ptr = (const float*)dy;                 // rows (n, pq), k = ko
+		A.rd12 = make_fastdiv(PQ); A.rd2 = make_fastdiv(0);
+		A.kd12 = make_fastdiv(1); A.kd2 = make_fastdiv(0);
+		A.rs0 = g.K * PQ; A.ks0 = PQ;
+		A.ah = A.bh = A.ch = 0;
+		A.aw = 1; A.bw = 0; A.cw = 0;
+		A.H = 1; A.W = PQ; A.Wd = 0;
+		A.cdh = A.cdw = 1;
+		A.rows = g.N * PQ; A.kdim = g.Kg;
+		A.group_stride = (long long)g.Kg * PQ;
+
+		// filter element (row = c, k = ko) at w[(g*Kg + ko)*Cg + c]
+		p.B = dense_mn((const float*)w, g.Cg, g.Kg, g.Cg);
+		p.B.group_stride = (long long)g.Kg * g.Cg;
+
+		E.md12 = make_fastdiv(PQ); E.md2 = make_fastdiv(g.Q);
+		E.ms0 = g.C * HW; E.ms1 = g.sh * g.W; E.ms2 = g.sw;
+		E.M = g.N * PQ;
+		p.kblocks = (int)pz_cdiv(A.kdim, BK);
+		p.kb_per_split = p.kblocks;
+		return launch(p, pick_bn(g.Cg), MODE_MN_SIMPLE, MODE_MN_SIMPLE, false, g.G, pz_stream(stream));
+	}
+
+	// general case: gather dy through the transposed-convolution index map
+	const size_t need = (size_t)g.K * g.Cg * RS * sizeof(float);
+	PZ_REQUIRE(workspace != nullptr && workspace_bytes >= need, "conv2d dgrad: workspace too small (%zu < %zu)", workspace_bytes, need);
+	{
+		long long total = (long long)g.K * g.Cg * RS;
+		repack_filter_dgrad<<<(unsigned)pz_cdiv(total, 256), 256, 0, pz_stream(stream)>>>((const float*)w, (float*)workspace, g.Kg, g.Cg, RS, total);
+		pz_count_launch(1);
+		PZ_LAUNCH_CHECK();
+	}
+
+	A.ptr = (const float*)dy;                     // rows (n,h,w), k (ko,r,s)
+	A.rd12 = make_fastdiv(HW); A.rd2 = make_fastdiv(g.W);
+	A.kd12 = make_fastdiv(RS); A.kd2 = make_fastdiv(g.S);
+	A.rs0 = g.K * PQ; A.ks0 = PQ;
+	A.ah = 1; A.bh = -g.dh; A.ch = g.ph;
+	A.aw = 1; A.bw = -g.dw; A.cw = g.pw;
+	A.H = g.P; A.W = g.Q; A.Wd = g.Q;
+	A.cdh = g.sh; A.cdw = g.sw;
+	A.rows = g.N * HW; A.kdim = g.Kg * RS;
+	A.group_stride = (long long)g.Kg * PQ;
+
+	p.B = dense_k((const float*)workspace, g.Cg, g.Kg * RS, (long long)g.Kg * RS);
+	p.B.group_stride = (long long)g.Cg * g.Kg * RS;
+
+	E.md12 = make_fastdiv(HW); E.md2 = make_fastdiv(0);
+	E.ms0 = g.C * HW; E.ms1 = 0; E.ms2 = 1;
+	E.M = g.N * HW;
+	p.kblocks = (int)pz_cdiv(A.kdim, BK);
+	p.kb_per_split = p.kblocks;
+	return launch(p, pick_bn(g.Cg), MODE_MN_GENERAL, MODE_K_SIMPLE, strided, g.G, pz_stream(stream));
+}
+
+int pz_conv2d_wgrad(int dtype, const pz_conv2d_desc* d, const void* x, const void* dy, void* dw, float alpha, float beta,
+					void* stream)
+{
+	Geo g;
+	int st = check_desc(dtype, d, g);
+	if (st != PZ_OK) return st;
+	const int RS = g.R * g.S, PQ = g.P * g.Q, HW = g.H * g.W;
+	PZ_REQUIRE((long long)g.N * PQ < (1ll << 31), "conv2d wgrad: reduction too long");
+
+	GemmParams p{};
+	Operand& A = p.A;   // im2col view of x: rows (c,r,s), k (n,p,q)
+	A.ptr = (const float*)x;
+	A.rd12 = make_fastdiv(RS); A.rd2 = make_fastdiv(g.S);
+	A.kd12 = make_fastdiv(PQ); A.kd2 = make_fastdiv(g.Q);
+	A.rs0 = HW; A.ks0 = g.C * HW;
+	A.ah = g.dh; A.bh = g.sh; A.ch = -g.ph;
+	A.aw = g.dw; A.bw = g.sw; A.cw = -g.pw;
+	A.H = g.H; A.W = g.W; A.Wd = g.W;
+	A.cdh = A.cdw = 1;
+	A.rows = g.Cg * RS; A.kdim = g.N * PQ;
+	A.group_stride = (long long)g.Cg * HW;
+
+	Operand& B = p.B;   // dy: rows ko, k (n, pq)
+	B.ptr = (const float*)dy;
+	B.rd12 = make_fastdiv(1); B.rd2 = make_fastdiv(0);
+	B.kd12 = make_fastdiv(PQ); B.kd2 = make_fastdiv(0);
+	B.rs0 = PQ; B.ks0 = g.K * PQ;
+	B.ah = B.bh = B.ch = 0;
+	B.aw = 0; B.bw = 1; B.cw = 0;
+	B.H = 1; B.W = PQ; B.Wd = 0;
+	B.cdh = B.cdw = 1;
+	B.rows = g.Kg; B.kdim = g.N * PQ;
+	B.group_stride = (long long)g.Kg * PQ;
+
+	Epilogue& E = p.E;
+	E.out = (float*)dw;
+	E.bias = nullptr;
+	E.md12 = make_fastdiv(0); E.md2 = make_fastdiv(0);
+	E.ms0 = 0; E.ms1 = 0; E.ms2 = 1;
+	E.ncs = g.Cg * RS;
+	E.M = g.Cg * RS; E.N = g.Kg;
+	E.alpha = alpha; E.beta = beta;
+	E.bias_mode = 0;
+	E.group_stride = (long long)g.Kg * g.Cg * RS;
+	E.bias_group_stride = 0;
+
+	p.kblocks = (int)pz_cdiv(A.kdim, BK);
+	const int bn = pick_bn(g.Kg);
+	set_splits(p, pz_cdiv(E.M, BM) * pz_cdiv(E.N, bn) * g.G, 8);
+	E.atomic = p.splits > 1;
+	if (E.atomic) {
+		st = prescale((float*)dw, (long long)g.K * g.Cg * RS, beta, stream);
+		if (st != PZ_OK) return st;
+	}
+	const int amode = taps_in_bounds(g) ? MODE_K_SIMPLE : MODE_K_GENERAL;
+	return launch(p, bn, amode, MODE_K_SIMPLE, false, g.G, pz_stream(stream));
+}
+
+int pz_bias_grad(int dtype, const void* t, void* db, int64_t N, int64_t C, int64_t S, float alpha, float beta, void* stream)
+{
+	PZ_REQUIRE(dtype == PZ_F32, "bias_grad: only float32 is implemented (got dtype %d)", dtype);
+	if (C <= 0) return PZ_OK;
+	int st = prescale((float*)db, C, beta, stream);
+	if (st != PZ_OK) return st;
+	if (N <= 0 || S <= 0) return PZ_OK;
+	int nsplit = (int)(pz_cdiv(4ll * pz_num_sms(), C));
+	if (nsplit > N) nsplit = (int)N;
+	if (nsplit < 1) nsplit = 1;
+	dim3 grid((unsigned)C, (unsigned)nsplit);
+	bias_grad_kernel<256><<<grid, 256, 0, pz_stream(stream)>>>((const float*)t, (float*)db, N, C, S, alpha, nsplit);
+	pz_count_launch(1);
+	PZ_LAUNCH_CHECK();
+	return PZ_OK;
+}
+
+}  // extern "C"

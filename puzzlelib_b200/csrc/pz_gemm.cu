@@ -1,0 +1,156 @@
+// pz_gemm.cu -- launcher of the tcgen05 GEMM engine (pz_umma.cuh) and the pz_gemm entry point.
+// Replaces cublasGemmEx as used by CuBlas_Context_gemm (reference Cuda/Source/Libs/CuBlas.c:327-403).
+#include "pz_umma.cuh"
+
+namespace pzumma {
+
+Operand dense_k(const float* ptr, int rows, int kdim, long long ld)
+{
+	Operand o{};
+	o.ptr = ptr;
+	o.rd12 = make_fastdiv(1);  // r0 = row
+	o.rd2 = make_fastdiv(0);
+	o.kd12 = make_fastdiv(0);  // k2 = k
+	o.kd2 = make_fastdiv(0);
+	o.rs0 = (int)ld;
+	o.ks0 = 0;
+	o.ah = o.bh = o.ch = 0;
+	o.aw = 0; o.bw = 1; o.cw = 0;
+	o.H = 1; o.W = kdim; o.Wd = 0;
+	o.cdh = o.cdw = 1;
+	o.rows = rows; o.kdim = kdim;
+	o.group_stride = 0;
+	return o;
+}
+
+Operand dense_mn(const float* ptr, int rows, int kdim, long long ld)
+{
+	Operand o{};
+	o.ptr = ptr;
+	o.rd12 = make_fastdiv(0);  // r2 = row
+	o.rd2 = make_fastdiv(0);
+	o.kd12 = make_fastdiv(1);  // k0 = k
+	o.kd2 = make_fastdiv(0);
+	o.rs0 = 0;
+	o.ks0 = (int)ld;
+	o.ah = o.bh = o.ch = 0;
+	o.aw = 1; o.bw = 0; o.cw = 0;
+	o.H = 1; o.W = rows; o.Wd = 0;
+	o.cdh = o.cdw = 1;
+	o.rows = rows; o.kdim = kdim;
+	o.group_stride = 0;
+	return o;
+}
+
+int pick_bn(int n) { return n <= 64 ? 64 : 128; }
+
+template <int BN, int AM, int BMODE, bool CDIV>
+static int launch_inst(const GemmParams& p, dim3 grid, cudaStream_t stream)
+{
+	auto kern = umma_gemm_kernel<BN, AM, BMODE, CDIV>;
+	static bool configured = false;
+	if (!configured) {
+		PZ_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES));
+		configured = true;
+	}
+	kern<<<grid, NTHREADS, Cfg<BN>::SMEM_BYTES, stream>>>(p);
+	pz_count_launch(1);
+	PZ_LAUNCH_CHECK();
+	return PZ_OK;
+}
+
+int launch(const GemmParams& p, int bn, int amode, int bmode, bool cdiv, int groups, cudaStream_t stream)
+{
+	const int M = p.E.M, N = p.E.N;
+	if (M <= 0 || N <= 0) return PZ_OK;
+	PZ_REQUIRE(p.kblocks > 0 && p.splits > 0 && p.kb_per_split > 0, "empty contraction");
+	PZ_REQUIRE((long long)(p.splits - 1) * p.kb_per_split < p.kblocks, "empty split");
+	dim3 grid((unsigned)pz_cdiv(N, bn), (unsigned)pz_cdiv(M, BM), (unsigned)(groups * p.splits));
+	PZ_REQUIRE(grid.y <= 65535 * 32 && grid.z <= 65535, "tile grid too large");
+
+#define PZ_INST(BNV, AMV, BMV, CD)                                             \
+	if (bn == BNV && amode == AMV && bmode == BMV && cdiv == CD)               \
+		return launch_inst<BNV, AMV, BMV, CD>(p, grid, stream);
+#define PZ_INST_BN(AMV, BMV, CD) PZ_INST(64, AMV, BMV, CD) PZ_INST(128, AMV, BMV, CD)
+	PZ_INST_BN(MODE_K_GENERAL, MODE_K_SIMPLE, false)
+	PZ_INST_BN(MODE_K_SIMPLE, MODE_K_SIMPLE, false)
+	PZ_INST_BN(MODE_K_SIMPLE, MODE_MN_SIMPLE, false)
+	PZ_INST_BN(MODE_MN_GENERAL, MODE_K_SIMPLE, false)
+	PZ_INST_BN(MODE_MN_GENERAL, MODE_K_SIMPLE, true)
+	PZ_INST_BN(MODE_MN_SIMPLE, MODE_K_SIMPLE, false)
+	PZ_INST_BN(MODE_MN_SIMPLE, MODE_MN_SIMPLE, false)
+#undef PZ_INST_BN
+#undef PZ_INST
+	pz_set_error(PZ_ERR_UNSUPPORTED, "no GEMM instantiation for bn=%d amode=%d bmode=%d cdiv=%d", bn, amode, bmode, (int)cdiv);
+	return PZ_ERR_UNSUPPORTED;
+}
+
+}  // namespace pzumma
+
+using namespace pzumma;
+
+extern "C" int pz_gemm(int dtype, const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, int64_t lda,
+					   int64_t ldb, int64_t ldc, int transA, int transB, float alpha, float beta, const void* bias,
+					   void* stream)
+{
+	PZ_REQUIRE(dtype == PZ_F32, "pz_gemm: only float32 storage is implemented (got dtype %d)", dtype);
+	PZ_REQUIRE(M >= 0 && N >= 0 && K > 0, "pz_gemm: invalid sizes M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)K);
+	PZ_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "pz_gemm: dimension too large");
+	PZ_REQUIRE(M * lda < (1ll << 31) && K * ldb < (1ll << 31) && K * lda < (1ll << 31) && N * ldb < (1ll << 31),
+			   "pz_gemm: operand exceeds 2^31 elements");
+	if (M == 0 || N == 0) return PZ_OK;
+
+	// TMEM lanes (engine rows) are mapped to C's contiguous dimension: D[n][m] = sum_k opB[k][n] * opA[m][k]
+	GemmParams p{};
+	int amode, bmode;
+	if (transB) { p.A = dense_k((const float*)B, (int)N, (int)K, ldb); amode = MODE_K_SIMPLE; }
+	else        { p.A = dense_mn((const float*)B, (int)N, (int)K, ldb); amode = MODE_MN_SIMPLE; }
+	if (transA) { p.B = dense_mn((const float*)A, (int)M, (int)K, lda); bmode = MODE_MN_SIMPLE; }
+	else        { p.B = dense_k((const float*)A, (int)M, (int)K, lda); bmode = MODE_K_SIMPLE; }
+
+	Epilogue& E = p.E;
+	E.out = (float*)C;
+	E.bias = (const float*)bias;
+	E.md12 = make_fastdiv(0);
+	E.md2 = make_fastdiv(0);
+	E.ms0 = 0; E.ms1 = 0; E.ms2 = 1;
+	E.ncs = (int)ldc;
+	E.M = (int)N;
+	E.N = (int)M;
+	E.alpha = alpha;
+	E.beta = beta;
+	E.bias_mode = bias ? 2 : 0;
+	E.atomic = 0;
+	E.group_stride = 0;
+	E.bias_group_stride = 0;
+
+	p.kblocks = (int)pz_cdiv(K, BK);
+	const int bn = pick_bn((int)M);
+	const long long tiles = pz_cdiv(N, BM) * pz_cdiv(M, bn);
+	int splits = 1;
+	if (tiles < pz_num_sms() && p.kblocks >= 16) {
+		splits = (int)((2ll * pz_num_sms()) / tiles);
+		if (splits > p.kblocks / 4) splits = p.kblocks / 4;
+		if (splits < 1) splits = 1;
+	}
+	p.kb_per_split = (int)pz_cdiv(p.kblocks, splits);
+	p.splits = (int)pz_cdiv(p.kblocks, p.kb_per_split);
+
+	if (p.splits > 1) {
+		// split-K accumulates with red.add: bring C to beta*C first (rows of C may be pitched)
+		E.atomic = 1;
+		if (ldc == N) {
+			int st = beta == 0.0f ? pz_memset8(C, 0, (size_t)M * N * 4, stream)
+								  : (beta == 1.0f ? PZ_OK : pz_scale_shift(PZ_F32, C, C, beta, 0.0f, M * N, stream));
+			if (st != PZ_OK) return st;
+		} else {
+			for (int64_t r = 0; r < M; r++) {
+				float* row = (float*)C + r * ldc;
+				int st = beta == 0.0f ? pz_memset8(row, 0, (size_t)N * 4, stream)
+									  : (beta == 1.0f ? PZ_OK : pz_scale_shift(PZ_F32, row, row, beta, 0.0f, N, stream));
+				if (st != PZ_OK) return st;
+			}
+		}
+	}
+	return launch(p, bn, amode, bmode, false, 1, pz_stream(stream));
+}

@@ -1,0 +1,192 @@
+// pz_matvec.cu -- bias add / axis sums / argmax on [z][h][w] tensors.
+// Replaces the NVRTC kernels of the reference's Cuda/Kernels/MatVec.py (opRowVecToMat, opColVecToMat,
+// opRowOneVecToMat :128-171; sumOnRow, sumOnCol :60-91; minMaxOnRow, minMaxOnCol :8-57).
+#include "pz_common.h"
+
+namespace {
+
+template <typename T> __device__ __forceinline__ float ldf(const T* p, int64_t i);
+template <> __device__ __forceinline__ float ldf<float>(const float* p, int64_t i) { return p[i]; }
+template <> __device__ __forceinline__ float ldf<__half>(const __half* p, int64_t i) { return __half2float(p[i]); }
+template <> __device__ __forceinline__ float ldf<__nv_bfloat16>(const __nv_bfloat16* p, int64_t i) { return __bfloat162float(p[i]); }
+template <typename T> __device__ __forceinline__ void stf(T* p, int64_t i, float v);
+template <> __device__ __forceinline__ void stf<float>(float* p, int64_t i, float v) { p[i] = v; }
+template <> __device__ __forceinline__ void stf<__half>(__half* p, int64_t i, float v) { p[i] = __float2half_rn(v); }
+template <> __device__ __forceinline__ void stf<__nv_bfloat16>(__nv_bfloat16* p, int64_t i, float v) { p[i] = __float2bfloat16_rn(v); }
+
+// mode 0: vec[z*cols + x]   1: vec[z*cols + x % vecdim] (reference indexes with tidz*m, MatVec.py:164)   2: vec[z*rows + y]
+template <typename T>
+__global__ void __launch_bounds__(256) addvec_kernel(T* __restrict__ out, const T* __restrict__ mat, const T* __restrict__ vec,
+													 int64_t rows, int64_t cols, int64_t total, int mode, int64_t vecdim)
+{
+	const int64_t step = (int64_t)gridDim.x * blockDim.x;
+	for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += step) {
+		int64_t x = i % cols, t = i / cols, y = t % rows, z = t / rows;
+		int64_t vi = mode == 0 ? z * cols + x : (mode == 1 ? z * cols + x % vecdim : z * rows + y);
+		stf<T>(out, i, ldf<T>(mat, i) + ldf<T>(vec, vi));
+	}
+}
+
+// one warp per row: out[row] = beta*out[row] + alpha*sum_w
+template <typename T>
+__global__ void __launch_bounds__(256) sum_row_kernel(T* __restrict__ out, const T* __restrict__ mat, int64_t nrows, int64_t w,
+													  float alpha, float beta)
+{
+	const int lane = threadIdx.x & 31;
+	const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+	if (row >= nrows) return;
+	float acc = 0.0f;
+	for (int64_t i = lane; i < w; i += 32) acc += ldf<T>(mat, row * w + i);
+	#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+	if (lane == 0) stf<T>(out, row, beta * ldf<T>(out, row) + alpha * acc);
+}
+
+// column sums of [z][h][w]: a CTA owns 32 columns; 8 warps stride over h, then combine through smem
+template <typename T>
+__global__ void __launch_bounds__(256) sum_col_kernel(T* __restrict__ out, const T* __restrict__ mat, int64_t h, int64_t w,
+													  float alpha, float beta)
+{
+	__shared__ float part[8][33];
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	const int64_t col = (int64_t)blockIdx.x * 32 + lane, z = blockIdx.z;
+	float acc = 0.0f;
+	if (col < w)
+		for (int64_t i = wid; i < h; i += 8) acc += ldf<T>(mat, (z * h + i) * w + col);
+	part[wid][lane] = acc;
+	__syncthreads();
+	if (wid == 0 && col < w) {
+		float s = 0.0f;
+		#pragma unroll
+		for (int k = 0; k < 8; k++) s += part[k][lane];
+		stf<T>(out, z * w + col, beta * ldf<T>(out, z * w + col) + alpha * s);
+	}
+}
+
+// arg-extremum along h of [z][h][w]; thread per (z, col) for w > 1, warp per z for w == 1; first occurrence wins
+template <typename T, bool MAX>
+__global__ void __launch_bounds__(256) argcol_kernel(int32_t* __restrict__ idx, const T* __restrict__ mat, int64_t z, int64_t h, int64_t w)
+{
+	const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (gid >= z * w) return;
+	const int64_t zi = gid / w, col = gid % w;
+	float best = MAX ? -3.402823466e+38f : 3.402823466e+38f;
+	int bi = -1;
+	for (int64_t i = 0; i < h; i++) {
+		float v = ldf<T>(mat, (zi * h + i) * w + col);
+		if (MAX ? (v > best) : (v < best)) { best = v; bi = (int)i; }
+	}
+	idx[gid] = bi;
+}
+
+template <typename T, bool MAX>
+__global__ void __launch_bounds__(256) argrow_kernel(int32_t* __restrict__ idx, const T* __restrict__ mat, int64_t nrows, int64_t h)
+{
+	const int lane = threadIdx.x & 31;
+	const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+	if (row >= nrows) return;
+	float best = MAX ? -3.402823466e+38f : 3.402823466e+38f;
+	int bi = 0x7fffffff;
+	for (int64_t i = lane; i < h; i += 32) {
+		float v = ldf<T>(mat, row * h + i);
+		if (MAX ? (v > best) : (v < best)) { best = v; bi = (int)i; }
+	}
+	#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) {
+		float ob = __shfl_xor_sync(0xffffffffu, best, o);
+		int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+		bool take = MAX ? (ob > best) : (ob < best);
+		if (take || (ob == best && oi < bi)) { best = ob; bi = oi; }
+	}
+	if (lane == 0) idx[row] = bi == 0x7fffffff ? -1 : bi;
+}
+
+template <typename T>
+int addvec_launch(void* out, const void* mat, const void* vec, int64_t z, int64_t rows, int64_t cols, int mode, int64_t vecdim, void* stream)
+{
+	int64_t total = z * rows * cols;
+	if (total <= 0) return PZ_OK;
+	int64_t blocks = pz_cdiv(total, 256);
+	if (blocks > (int64_t)pz_num_sms() * 16) blocks = (int64_t)pz_num_sms() * 16;
+	addvec_kernel<T><<<(unsigned)blocks, 256, 0, pz_stream(stream)>>>((T*)out, (const T*)mat, (const T*)vec, rows, cols, total, mode, vecdim);
+	pz_count_launch(1);
+	PZ_LAUNCH_CHECK();
+	return PZ_OK;
+}
+
+template <typename T>
+int matsum_launch(void* out, const void* t, int64_t z, int64_t h, int64_t w, int reduce_rows, float alpha, float beta, void* stream)
+{
+	if (reduce_rows) {
+		int64_t nrows = z * h;
+		if (nrows <= 0) return PZ_OK;
+		sum_row_kernel<T><<<(unsigned)pz_cdiv(nrows, 8), 256, 0, pz_stream(stream)>>>((T*)out, (const T*)t, nrows, w, alpha, beta);
+	} else {
+		if (z <= 0 || w <= 0) return PZ_OK;
+		dim3 grid((unsigned)pz_cdiv(w, 32), 1, (unsigned)z);
+		sum_col_kernel<T><<<grid, 256, 0, pz_stream(stream)>>>((T*)out, (const T*)t, h, w, alpha, beta);
+	}
+	pz_count_launch(1);
+	PZ_LAUNCH_CHECK();
+	return PZ_OK;
+}
+
+template <typename T>
+int arg_launch(int32_t* idx, const void* t, int64_t z, int64_t h, int64_t w, int want_max, void* stream)
+{
+	if (z * w <= 0) return PZ_OK;
+	if (w == 1) {
+		unsigned blocks = (unsigned)pz_cdiv(z, 8);
+		if (want_max) argrow_kernel<T, true><<<blocks, 256, 0, pz_stream(stream)>>>(idx, (const T*)t, z, h);
+		else argrow_kernel<T, false><<<blocks, 256, 0, pz_stream(stream)>>>(idx, (const T*)t, z, h);
+	} else {
+		unsigned blocks = (unsigned)pz_cdiv(z * w, 256);
+		if (want_max) argcol_kernel<T, true><<<blocks, 256, 0, pz_stream(stream)>>>(idx, (const T*)t, z, h, w);
+		else argcol_kernel<T, false><<<blocks, 256, 0, pz_stream(stream)>>>(idx, (const T*)t, z, h, w);
+	}
+	pz_count_launch(1);
+	PZ_LAUNCH_CHECK();
+	return PZ_OK;
+}
+
+#define PZ_DISPATCH_FLOAT(dtype, ...)                                                    \
+	switch (dtype) {                                                                     \
+		case PZ_F32: { using T = float; return __VA_ARGS__; }                            \
+		case PZ_F16: { using T = __half; return __VA_ARGS__; }                           \
+		case PZ_BF16: { using T = __nv_bfloat16; return __VA_ARGS__; }                   \
+		default: pz_set_error(PZ_ERR_UNSUPPORTED, "unsupported dtype %d", (int)(dtype)); \
+				 return PZ_ERR_UNSUPPORTED;                                              \
+	}
+
+}  // namespace
+
+extern "C" {
+
+int pz_addvec2mat(int dtype, void* out, const void* mat, const void* vec, int64_t z, int64_t rows, int64_t cols, int axis,
+				  int64_t vecdim, void* stream)
+{
+	PZ_REQUIRE(axis == 0 || axis == 1, "addvec2mat: axis must be 0 or 1");
+	int mode;
+	if (axis == 1) {
+		if (vecdim == cols) mode = 0;
+		else {
+			PZ_REQUIRE(vecdim > 0 && cols % vecdim == 0, "addvec2mat: matrix width %lld is not a multiple of the vector length %lld",
+					   (long long)cols, (long long)vecdim);
+			mode = 1;
+		}
+	} else mode = 2;
+	PZ_DISPATCH_FLOAT(dtype, addvec_launch<T>(out, mat, vec, z, rows, cols, mode, vecdim, stream));
+}
+
+int pz_matsum(int dtype, void* out, const void* tensor, int64_t z, int64_t h, int64_t w, int reduce_rows, float alpha,
+			  float beta, void* stream)
+{
+	PZ_DISPATCH_FLOAT(dtype, matsum_launch<T>(out, tensor, z, h, w, reduce_rows, alpha, beta, stream));
+}
+
+int pz_argminmax(int dtype, int32_t* idx, const void* tensor, int64_t z, int64_t h, int64_t w, int want_max, void* stream)
+{
+	PZ_DISPATCH_FLOAT(dtype, arg_launch<T>(idx, tensor, z, h, w, want_max, stream));
+}
+
+}  // extern "C"

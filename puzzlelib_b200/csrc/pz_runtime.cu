@@ -1,0 +1,302 @@
+// pz_runtime.cu -- device, memory pool, copies, streams/events.
+// B200-native replacement of the reference's Cuda/Source/Core/{Device,Buffer,Allocator,Stream}.c
+// surface, exposed as plain C entry points (no CPython objects; the ctypes shim owns lifetimes).
+#include "pz_common.h"
+
+#include <cstdarg>
+#include <atomic>
+#include <mutex>
+#include <unordered_map>
+#include <vector>
+
+static thread_local char g_err[1024] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+void pz_set_error(int code, const char* fmt, ...)
+{
+	(void)code;
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(g_err, sizeof(g_err), fmt, ap);
+	va_end(ap);
+}
+
+void pz_count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+int pz_num_sms()
+{
+	static int sms = 0;
+	if (sms == 0) {
+		int dev = 0;
+		if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+		if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+	}
+	return sms;
+}
+
+template <typename T>
+__global__ void pz_fill_kernel(T* __restrict__ p, T v, size_t n)
+{
+	size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	size_t step = (size_t)gridDim.x * blockDim.x;
+	for (; i < n; i += step) p[i] = v;
+}
+
+template <typename T>
+static int pz_fill_any(T* ptr, T value, size_t count, void* stream)
+{
+	if (count == 0) return PZ_OK;
+	// vector path: fill 16-byte words when aligned
+	constexpr int per = 16 / sizeof(T);
+	size_t head = 0;
+	uintptr_t addr = (uintptr_t)ptr;
+	if (addr % 16) head = ((16 - addr % 16) / sizeof(T));
+	if (head > count) head = count;
+	size_t body = (count - head) / per, tail = count - head - body * per;
+	int blocks;
+	if (head) { pz_fill_kernel<T><<<1, 32, 0, pz_stream(stream)>>>(ptr, value, head); pz_count_launch(1); }
+	if (body) {
+		uint4 v4;
+		T tmp[per];
+		for (int i = 0; i < per; i++) tmp[i] = value;
+		memcpy(&v4, tmp, 16);
+		blocks = (int)(pz_cdiv((int64_t)body, 256) < (int64_t)pz_num_sms() * 16 ? pz_cdiv((int64_t)body, 256) : (int64_t)pz_num_sms() * 16);
+		pz_fill_kernel<uint4><<<blocks, 256, 0, pz_stream(stream)>>>((uint4*)(ptr + head), v4, body);
+		pz_count_launch(1);
+	}
+	if (tail) { pz_fill_kernel<T><<<1, 32, 0, pz_stream(stream)>>>(ptr + head + body * per, value, tail); pz_count_launch(1); }
+	PZ_LAUNCH_CHECK();
+	return PZ_OK;
+}
+
+
+extern "C" {
+
+const char* pz_last_error(void) { return g_err; }
+int pz_version(void) { return 100; }
+uint64_t pz_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int pz_device_count(int* count) { PZ_CHECK_CUDA(cudaGetDeviceCount(count)); return PZ_OK; }
+int pz_device_set(int index) { PZ_CHECK_CUDA(cudaSetDevice(index)); return PZ_OK; }
+int pz_device_get(int* index) { PZ_CHECK_CUDA(cudaGetDevice(index)); return PZ_OK; }
+
+int pz_device_name(int index, char* buf, int buflen)
+{
+	cudaDeviceProp prop;
+	PZ_CHECK_CUDA(cudaGetDeviceProperties(&prop, index));
+	snprintf(buf, (size_t)buflen, "%s", prop.name);
+	return PZ_OK;
+}
+
+int pz_device_sm_count(int* count) { *count = pz_num_sms(); return PZ_OK; }
+
+int pz_device_cc(int* major, int* minor)
+{
+	int dev = 0;
+	PZ_CHECK_CUDA(cudaGetDevice(&dev));
+	PZ_CHECK_CUDA(cudaDeviceGetAttribute(major, cudaDevAttrComputeCapabilityMajor, dev));
+	PZ_CHECK_CUDA(cudaDeviceGetAttribute(minor, cudaDevAttrComputeCapabilityMinor, dev));
+	return PZ_OK;
+}
+
+int pz_device_synchronize(void) { PZ_CHECK_CUDA(cudaDeviceSynchronize()); return PZ_OK; }
+int pz_mem_info(size_t* f, size_t* t) { PZ_CHECK_CUDA(cudaMemGetInfo(f, t)); return PZ_OK; }
+
+int pz_malloc(void** ptr, size_t nbytes)
+{
+	cudaError_t e = cudaMalloc(ptr, nbytes ? nbytes : 1);
+	if (e == cudaErrorMemoryAllocation) {
+		cudaGetLastError();
+		pz_set_error(PZ_ERR_MEMORY, "out of device memory allocating %zu bytes", nbytes);
+		return PZ_ERR_MEMORY;
+	}
+	PZ_CHECK_CUDA(e);
+	return PZ_OK;
+}
+
+int pz_free(void* ptr) { PZ_CHECK_CUDA(cudaFree(ptr)); return PZ_OK; }
+int pz_host_alloc(void** ptr, size_t nbytes) { PZ_CHECK_CUDA(cudaMallocHost(ptr, nbytes ? nbytes : 1)); return PZ_OK; }
+int pz_host_free(void* ptr) { PZ_CHECK_CUDA(cudaFreeHost(ptr)); return PZ_OK; }
+
+// ---------------------------------------------------------------------------------------- memory pool
+// Size classes follow the reference's float-like binning with two mantissa bits (Allocator.c:29-67):
+// a request is rounded up to m * 2^e with m in {4,5,6,7}; the smallest block here is 256 B so that every
+// block keeps the 256-byte alignment cudaMalloc gives (128-bit vector access, TMA 16-byte rule).
+size_t pz_pool_alloc_size(size_t nbytes)
+{
+	const size_t minblock = 256;
+	if (nbytes <= minblock) return minblock;
+	int msb = 63 - __builtin_clzll((unsigned long long)nbytes);
+	int shift = msb - 2;
+	size_t mant = nbytes >> shift;                 // in [4, 8)
+	if (nbytes & (((size_t)1 << shift) - 1)) mant += 1;
+	return mant << shift;                           // mant == 8 rolls over to the next exponent, still exact
+}
+
+struct PzPool {
+	std::mutex mu;
+	std::unordered_map<size_t, std::vector<void*>> bins;
+	size_t held_blocks = 0, held_bytes = 0, active_blocks = 0, active_bytes = 0;
+};
+
+int pz_pool_create(void** pool) { *pool = new PzPool(); return PZ_OK; }
+
+int pz_pool_free_held(void* pool)
+{
+	PzPool* p = (PzPool*)pool;
+	std::lock_guard<std::mutex> lock(p->mu);
+	for (auto& kv : p->bins) {
+		for (void* ptr : kv.second) cudaFree(ptr);
+		kv.second.clear();
+	}
+	p->held_blocks = 0;
+	p->held_bytes = 0;
+	return PZ_OK;
+}
+
+int pz_pool_destroy(void* pool)
+{
+	if (!pool) return PZ_OK;
+	pz_pool_free_held(pool);
+	delete (PzPool*)pool;
+	return PZ_OK;
+}
+
+int pz_pool_alloc(void* pool, size_t nbytes, void** ptr, size_t* granted)
+{
+	PzPool* p = (PzPool*)pool;
+	size_t sz = pz_pool_alloc_size(nbytes);
+	*granted = sz;
+	{
+		std::lock_guard<std::mutex> lock(p->mu);
+		auto it = p->bins.find(sz);
+		if (it != p->bins.end() && !it->second.empty()) {
+			*ptr = it->second.back();
+			it->second.pop_back();
+			p->held_blocks -= 1;
+			p->held_bytes -= sz;
+			p->active_blocks += 1;
+			p->active_bytes += sz;
+			return PZ_OK;
+		}
+	}
+	int st = pz_malloc(ptr, sz);
+	if (st != PZ_OK) return st;      // like the reference, no retry after freeHeld
+	std::lock_guard<std::mutex> lock(p->mu);
+	p->active_blocks += 1;
+	p->active_bytes += sz;
+	return PZ_OK;
+}
+
+int pz_pool_release(void* pool, void* ptr, size_t granted)
+{
+	PzPool* p = (PzPool*)pool;
+	std::lock_guard<std::mutex> lock(p->mu);
+	p->bins[granted].push_back(ptr);
+	p->held_blocks += 1;
+	p->held_bytes += granted;
+	p->active_blocks -= 1;
+	p->active_bytes -= granted;
+	return PZ_OK;
+}
+
+int pz_pool_stats(void* pool, size_t* hb, size_t* hbytes, size_t* ab, size_t* abytes)
+{
+	PzPool* p = (PzPool*)pool;
+	std::lock_guard<std::mutex> lock(p->mu);
+	*hb = p->held_blocks; *hbytes = p->held_bytes; *ab = p->active_blocks; *abytes = p->active_bytes;
+	return PZ_OK;
+}
+
+// ---------------------------------------------------------------------------------------- copies
+int pz_memcpy_h2d(void* dst, const void* src, size_t n, void* stream, int async)
+{
+	if (n == 0) return PZ_OK;
+	PZ_CHECK_CUDA(cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, pz_stream(stream)));
+	if (!async) PZ_CHECK_CUDA(cudaStreamSynchronize(pz_stream(stream)));
+	return PZ_OK;
+}
+
+int pz_memcpy_d2h(void* dst, const void* src, size_t n, void* stream, int async)
+{
+	if (n == 0) return PZ_OK;
+	PZ_CHECK_CUDA(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, pz_stream(stream)));
+	if (!async) PZ_CHECK_CUDA(cudaStreamSynchronize(pz_stream(stream)));
+	return PZ_OK;
+}
+
+int pz_memcpy_d2d(void* dst, const void* src, size_t n, void* stream)
+{
+	if (n == 0) return PZ_OK;
+	PZ_CHECK_CUDA(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToDevice, pz_stream(stream)));
+	return PZ_OK;
+}
+
+int pz_memcpy2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height, int kind,
+				void* stream)
+{
+	if (width == 0 || height == 0) return PZ_OK;
+	cudaMemcpyKind k = kind == 0 ? cudaMemcpyDeviceToDevice : (kind == 1 ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost);
+	PZ_CHECK_CUDA(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, k, pz_stream(stream)));
+	if (kind != 0) PZ_CHECK_CUDA(cudaStreamSynchronize(pz_stream(stream)));
+	return PZ_OK;
+}
+
+int pz_memset8(void* ptr, uint8_t value, size_t count, void* stream)
+{
+	if (count == 0) return PZ_OK;
+	PZ_CHECK_CUDA(cudaMemsetAsync(ptr, value, count, pz_stream(stream)));
+	return PZ_OK;
+}
+
+int pz_memset16(void* ptr, uint16_t value, size_t count, void* stream)
+{
+	if (((value >> 8) & 0xff) == (value & 0xff)) return pz_memset8(ptr, (uint8_t)(value & 0xff), count * 2, stream);
+	return pz_fill_any<uint16_t>((uint16_t*)ptr, value, count, stream);
+}
+
+int pz_memset32(void* ptr, uint32_t value, size_t count, void* stream)
+{
+	uint8_t b = value & 0xff;
+	if (value == (uint32_t)b * 0x01010101u) return pz_memset8(ptr, b, count * 4, stream);
+	return pz_fill_any<uint32_t>((uint32_t*)ptr, value, count, stream);
+}
+
+int pz_fill64(void* ptr, uint64_t value, int64_t count, void* stream)
+{
+	return pz_fill_any<uint64_t>((uint64_t*)ptr, value, (size_t)count, stream);
+}
+
+// ---------------------------------------------------------------------------------------- streams / events
+int pz_stream_create(void** stream)
+{
+	cudaStream_t s;
+	PZ_CHECK_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+	*stream = (void*)s;
+	return PZ_OK;
+}
+int pz_stream_destroy(void* stream) { PZ_CHECK_CUDA(cudaStreamDestroy(pz_stream(stream))); return PZ_OK; }
+int pz_stream_synchronize(void* stream) { PZ_CHECK_CUDA(cudaStreamSynchronize(pz_stream(stream))); return PZ_OK; }
+
+int pz_event_create(void** event)
+{
+	cudaEvent_t e;
+	PZ_CHECK_CUDA(cudaEventCreate(&e));
+	*event = (void*)e;
+	return PZ_OK;
+}
+int pz_event_destroy(void* event) { PZ_CHECK_CUDA(cudaEventDestroy((cudaEvent_t)event)); return PZ_OK; }
+int pz_event_record(void* event, void* stream) { PZ_CHECK_CUDA(cudaEventRecord((cudaEvent_t)event, pz_stream(stream))); return PZ_OK; }
+int pz_event_synchronize(void* event) { PZ_CHECK_CUDA(cudaEventSynchronize((cudaEvent_t)event)); return PZ_OK; }
+int pz_event_elapsed_ms(void* start, void* stop, float* ms)
+{
+	PZ_CHECK_CUDA(cudaEventElapsedTime(ms, (cudaEvent_t)start, (cudaEvent_t)stop));
+	return PZ_OK;
+}
+int pz_stream_wait_event(void* stream, void* event)
+{
+	PZ_CHECK_CUDA(cudaStreamWaitEvent(pz_stream(stream), (cudaEvent_t)event, 0));
+	return PZ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,488 @@
+// pz_umma.cuh -- one tcgen05 / TMEM GEMM engine for every dense contraction of the backend
+// (Linear fwd/dgrad/wgrad, conv fprop/dgrad/wgrad, deconv).
+//
+// D[M x N] (+)= A[M x K] * B[N x K]^T with fp32 storage, TF32 tensor-core math, fp32 accumulation in TMEM.
+//
+// B200 design
+//   * one CTA = one 128 x BN output tile; accumulator lives in TMEM (BN fp32 columns x 128 lanes);
+//     tcgen05.mma.cta_group::1.kind::tf32, M=128, N=BN, K=8 per instruction, issued by ONE thread;
+//   * operands are staged in shared memory as K-major tiles of 32 floats (128-byte rows) in the canonical
+//     SWIZZLE_128B layout (8-row x 128-byte atoms, 16-byte chunk index XOR row%8) - the same layout a TMA
+//     SWIZZLE_128B box produces, so a TMA producer can replace a gather producer tile by tile;
+//   * 8 producer warps gather both operands straight from the reference's NCHW / row-major tensors
+//     (no im2col buffer, no NHWC shadow copy), round fp32 -> tf32 with cvt.rna (tcgen05 itself would
+//     truncate, which biases every product by ~ -2^-11) and write the swizzled tile; 1 warp issues MMAs;
+//     a ring of mbarriers (full: 8 warp arrivals, empty: tcgen05.commit) pipelines STAGES tiles;
+//   * the same 8 warps then run the epilogue: tcgen05.ld 32 lanes x 32 columns, alpha/beta/bias, coalesced
+//     stores (TMEM lanes are always mapped to the contiguous dimension of the output) or red.add for split-K.
+//
+// An operand is described by `Operand`: element (row, k) lives at
+//     ptr[ r0*rs0 + k0*ks0 + hh*Wd + ww ],  (r0,r1,r2) = split(row), (k0,k1,k2) = split(k),
+//     hh = (r1*ah + k1*bh + ch) / cdh,  ww = (r2*aw + k2*bw + cw) / cdw     (exact division required)
+// and is zero unless 0<=hh<H, 0<=ww<W, row<rows, k<kdim.  That one formula covers dense matrices in either
+// orientation, im2col views of NCHW tensors for fprop / wgrad, and the transposed-conv gather of dgrad with
+// any stride / padding / dilation.
+#pragma once
+
+#include "pz_common.h"
+
+namespace pzumma {
+
+constexpr int BM = 128;          // tile rows  = TMEM lanes
+constexpr int BK = 32;           // floats per k-block = one 128-byte swizzle row
+constexpr int NPROD_WARPS = 8;
+constexpr int NPROD = NPROD_WARPS * 32;
+constexpr int NTHREADS = NPROD + 32;
+constexpr int INVALID = -(1 << 28);
+
+struct FastDiv {
+	uint32_t d, m, sh;           // d == 0 encodes an "infinite" divisor (quotient 0); d == 1 is the identity
+};
+
+inline FastDiv make_fastdiv(uint32_t d)
+{
+	FastDiv f{d, 0, 0};
+	if (d <= 1) return f;
+	uint32_t s = 0;
+	while ((1ull << s) < d) s++;
+	uint32_t p = 31 + s;
+	f.m = (uint32_t)(((1ull << p) + d - 1) / d);
+	f.sh = p - 32;
+	return f;
+}
+
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f)
+{
+	return f.d == 1 ? n : (__umulhi(n, f.m) >> f.sh);
+}
+
+__device__ __forceinline__ void split3(uint32_t x, const FastDiv& d12, const FastDiv& d2, int& x0, int& x1, int& x2)
+{
+	uint32_t q0 = fdiv(x, d12);
+	uint32_t rem = x - q0 * d12.d;
+	uint32_t q1 = fdiv(rem, d2);
+	x0 = (int)q0;
+	x1 = (int)q1;
+	x2 = (int)(rem - q1 * d2.d);
+}
+
+enum { MODE_K_GENERAL = 0, MODE_K_SIMPLE = 1, MODE_MN_GENERAL = 2, MODE_MN_SIMPLE = 3 };
+
+struct Operand {
+	const float* ptr;
+	FastDiv rd12, rd2, kd12, kd2;
+	int rs0, ks0;
+	int ah, bh, ch, aw, bw, cw;
+	int H, W, Wd;
+	int cdh, cdw;
+	int rows, kdim;
+	long long group_stride;
+};
+
+struct Epilogue {
+	float* out;
+	const float* bias;
+	FastDiv md12, md2;
+	int ms0, ms1, ms2;           // row m -> m0*ms0 + m1*ms1 + m2*ms2
+	int ncs;                     // column n -> n*ncs
+	int M, N;
+	float alpha, beta;
+	int bias_mode;               // 0 none, 1 bias[n], 2 bias[m]
+	int atomic;                  // 1: out += alpha*acc with red.global.add (split-K)
+	long long group_stride;
+	int bias_group_stride;
+};
+
+struct GemmParams {
+	Operand A, B;
+	Epilogue E;
+	int kblocks;                 // ceil(K / 32)
+	int splits;                  // split-K factor (grid.z = groups * splits)
+	int kb_per_split;
+};
+
+// ------------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+	uint32_t ok;
+	do {
+		asm volatile(
+			"{\n\t.reg .pred p;\n\t"
+			"mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+			"selp.u32 %0, 1, 0, p;\n\t}"
+			: "=r"(ok)
+			: "r"(bar), "r"(parity)
+			: "memory");
+	} while (!ok);
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols)
+{
+	asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+	asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols)
+{
+	asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar)
+{
+	asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
+{
+	asm volatile(
+		"{\n\t.reg .pred p;\n\t"
+		"setp.ne.b32 p, %4, 0;\n\t"
+		"tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+		::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+		: "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
+{
+	asm volatile(
+		"tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+		"{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+		"%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+		: "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+		  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+		  "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+		  "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+		: "r"(taddr)
+		: "memory");
+	asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t to_tf32(float x)
+{
+	uint32_t r;
+	asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+	return r;
+}
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
+{
+	asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+// start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout=SWIZZLE_128B(2) [61,64)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr)
+{
+	uint64_t d = 0;
+	d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+	d |= (uint64_t)1 << 16;                 // LBO: unused for swizzled K-major, canonical value 1
+	d |= (uint64_t)(1024 >> 4) << 32;       // SBO: 8 rows x 128 B between 8-row groups
+	d |= (uint64_t)1 << 46;                 // descriptor version (Blackwell)
+	d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
+	return d;
+}
+
+// tcgen05 instruction descriptor (cute::UMMA::InstrDescriptor), kind::tf32, fp32 accumulate, both K-major
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int m, int n)
+{
+	return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------ operand producers
+struct RowInfo { int rbase, hr, wr, valid; };
+
+__device__ __forceinline__ RowInfo make_rowinfo(const Operand& op, int row)
+{
+	RowInfo ri;
+	int r0, r1, r2;
+	bool valid = row < op.rows;
+	split3((uint32_t)(valid ? row : 0), op.rd12, op.rd2, r0, r1, r2);
+	ri.rbase = r0 * op.rs0;
+	ri.hr = valid ? r1 * op.ah + op.ch : INVALID;
+	ri.wr = r2 * op.aw + op.cw;
+	ri.valid = valid;
+	return ri;
+}
+
+struct KInfo { int kbase, hk, wk, valid; };
+
+__device__ __forceinline__ KInfo make_kinfo(const Operand& op, int k)
+{
+	KInfo ki;
+	int k0, k1, k2;
+	bool valid = k < op.kdim;
+	split3((uint32_t)(valid ? k : 0), op.kd12, op.kd2, k0, k1, k2);
+	ki.kbase = k0 * op.ks0;
+	ki.hk = valid ? k1 * op.bh : INVALID;
+	ki.wk = k2 * op.bw;
+	ki.valid = valid;
+	return ki;
+}
+
+// fetch one element given row and k info; SIMPLE: no spatial bound checks (the host proved them unnecessary)
+template <bool SIMPLE, bool CDIV>
+__device__ __forceinline__ float fetch(const Operand& op, const float* __restrict__ base, const RowInfo& ri, const KInfo& ki)
+{
+	int hh = ri.hr + ki.hk;
+	int ww = ri.wr + ki.wk;
+	if (SIMPLE) {
+		bool ok = ri.valid && ki.valid;
+		int off = ri.rbase + ki.kbase + hh * op.Wd + ww;
+		return ok ? __ldg(base + off) : 0.0f;
+	}
+	bool ok = true;
+	if (CDIV) {
+		ok = (hh % op.cdh == 0) && (ww % op.cdw == 0);
+		hh /= op.cdh;
+		ww /= op.cdw;
+	}
+	ok = ok && ((unsigned)hh < (unsigned)op.H) && ((unsigned)ww < (unsigned)op.W);
+	int off = ri.rbase + ki.kbase + hh * op.Wd + ww;
+	return ok ? __ldg(base + off) : 0.0f;
+}
+
+// MN-contiguous producer: thread owns one tile row (kept in registers) and ROWS/32 16-byte chunks per stage.
+template <int ROWS, bool SIMPLE, bool CDIV>
+struct MnProducer {
+	static constexpr int NCH = ROWS / 32;            // chunks per thread per stage
+	static constexpr int CSTEP = NPROD / ROWS;       // chunk stride between a thread's chunks
+	RowInfo ri;
+	int row_local, chunk0;
+	float v[NCH][4];
+
+	__device__ __forceinline__ void init(const Operand& op, int tile_row0, int warp, int lane, uint32_t)
+	{
+		int t = warp * 32 + lane;
+		row_local = t % ROWS;
+		chunk0 = (warp * 32) / ROWS;                 // warp-uniform
+		ri = make_rowinfo(op, tile_row0 + row_local);
+	}
+	__device__ __forceinline__ void load(const Operand& op, const float* __restrict__ base, int kb)
+	{
+		#pragma unroll
+		for (int i = 0; i < NCH; i++) {
+			int kc = kb * BK + (chunk0 + i * CSTEP) * 4;   // warp-uniform
+			#pragma unroll
+			for (int e = 0; e < 4; e++) {
+				KInfo ki = make_kinfo(op, kc + e);
+				v[i][e] = fetch<SIMPLE, CDIV>(op, base, ri, ki);
+			}
+		}
+	}
+	__device__ __forceinline__ void store(uint32_t tile)
+	{
+		#pragma unroll
+		for (int i = 0; i < NCH; i++) {
+			int chunk = chunk0 + i * CSTEP;
+			uint32_t addr = tile + row_local * 128 + ((chunk ^ (row_local & 7)) << 4);
+			sts128(addr, to_tf32(v[i][0]), to_tf32(v[i][1]), to_tf32(v[i][2]), to_tf32(v[i][3]));
+		}
+	}
+};
+
+// K-contiguous producer: a warp reads one tile row x 32 consecutive k per request (lane = k), rows w, w+8, ...
+template <int ROWS, bool SIMPLE>
+struct KProducer {
+	static constexpr int NR = ROWS / NPROD_WARPS;    // rows per warp per stage
+	int warp, lane;
+	uint32_t rowinfo_smem;                           // smem table of RowInfo[ROWS]
+	float v[NR];
+
+	__device__ __forceinline__ void init(const Operand& op, int tile_row0, int warp_, int lane_, uint32_t table)
+	{
+		warp = warp_;
+		lane = lane_;
+		rowinfo_smem = table;
+		int t = warp * 32 + lane;
+		if (t < ROWS) {
+			RowInfo ri = make_rowinfo(op, tile_row0 + t);
+			sts128(table + t * 16, (uint32_t)ri.rbase, (uint32_t)ri.hr, (uint32_t)ri.wr, (uint32_t)ri.valid);
+		}
+	}
+	__device__ __forceinline__ void load(const Operand& op, const float* __restrict__ base, int kb)
+	{
+		KInfo ki = make_kinfo(op, kb * BK + lane);
+		#pragma unroll
+		for (int i = 0; i < NR; i++) {
+			RowInfo ri;
+			asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+						 : "=r"(ri.rbase), "=r"(ri.hr), "=r"(ri.wr), "=r"(ri.valid)
+						 : "r"(rowinfo_smem + (warp + i * NPROD_WARPS) * 16));
+			v[i] = fetch<SIMPLE, false>(op, base, ri, ki);
+		}
+	}
+	__device__ __forceinline__ void store(uint32_t tile)
+	{
+		// row & 7 == warp & 7 for every row of this warp, so the swizzled column offset is a thread constant
+		uint32_t col = ((((uint32_t)lane >> 2) ^ ((uint32_t)warp & 7)) << 4) | (((uint32_t)lane & 3) << 2);
+		#pragma unroll
+		for (int i = 0; i < NR; i++) sts32(tile + (warp + i * NPROD_WARPS) * 128 + col, to_tf32(v[i]));
+	}
+};
+
+template <int ROWS, int MODE, bool CDIV> struct ProducerSel;
+template <int ROWS, bool CDIV> struct ProducerSel<ROWS, MODE_K_GENERAL, CDIV> { using type = KProducer<ROWS, false>; };
+template <int ROWS, bool CDIV> struct ProducerSel<ROWS, MODE_K_SIMPLE, CDIV> { using type = KProducer<ROWS, true>; };
+template <int ROWS, bool CDIV> struct ProducerSel<ROWS, MODE_MN_GENERAL, CDIV> { using type = MnProducer<ROWS, false, CDIV>; };
+template <int ROWS, bool CDIV> struct ProducerSel<ROWS, MODE_MN_SIMPLE, CDIV> { using type = MnProducer<ROWS, true, false>; };
+
+template <int BN> struct Cfg {
+	static constexpr int STAGE_BYTES = (BM + BN) * 128;
+	static constexpr int STAGES = BN <= 64 ? 4 : 3;
+	static constexpr int TABLE_BYTES = (BM + BN) * 16;
+	static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + TABLE_BYTES + 256 + 1024;  // + barriers + align slack
+};
+
+// ------------------------------------------------------------------------------------------ the kernel
+template <int BN, int AMODE, int BMODE, bool CDIV>
+__global__ void __launch_bounds__(NTHREADS, 2) umma_gemm_kernel(const __grid_constant__ GemmParams p)
+{
+	using C = Cfg<BN>;
+	extern __shared__ uint8_t smem_raw[];
+	const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+	const uint32_t tables = smem0 + C::STAGES * C::STAGE_BYTES;
+	const uint32_t bars = tables + C::TABLE_BYTES;          // full[STAGES], empty[STAGES], accum, tmem ptr
+	const uint32_t bar_full = bars, bar_empty = bars + 8 * C::STAGES, bar_accum = bars + 16 * C::STAGES;
+	const uint32_t tmem_slot = bar_accum + 8;
+
+	const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+	const int lane = threadIdx.x & 31;
+
+	const int n_tile = blockIdx.x, m_tile = blockIdx.y;
+	const int group = blockIdx.z / p.splits, split = blockIdx.z % p.splits;
+	const int kb_begin = split * p.kb_per_split;
+	const int kb_end = min(p.kblocks, kb_begin + p.kb_per_split);
+
+	if (warp == NPROD_WARPS) {
+		if (lane == 0) {
+			for (int s = 0; s < C::STAGES; s++) {
+				mbar_init(bar_full + 8 * s, NPROD_WARPS);
+				mbar_init(bar_empty + 8 * s, 1);
+			}
+			mbar_init(bar_accum, 1);
+			fence_barrier_init();
+		}
+		__syncwarp();
+		tmem_alloc(tmem_slot, BN);
+	}
+
+	typename ProducerSel<BM, AMODE, CDIV>::type prodA;
+	typename ProducerSel<BN, BMODE, false>::type prodB;
+	const float* baseA = p.A.ptr + (long long)group * p.A.group_stride;
+	const float* baseB = p.B.ptr + (long long)group * p.B.group_stride;
+	if (warp < NPROD_WARPS) {
+		prodA.init(p.A, m_tile * BM, warp, lane, tables);
+		prodB.init(p.B, n_tile * BN, warp, lane, tables + BM * 16);
+	}
+
+	tc_fence_before();
+	__syncthreads();
+	tc_fence_after();
+
+	uint32_t tmem_base;
+	asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+	if (warp < NPROD_WARPS) {
+		// ===================== producers =====================
+		int stage = 0;
+		uint32_t phase = 0;
+		for (int kb = kb_begin; kb < kb_end; kb++) {
+			prodA.load(p.A, baseA, kb);
+			prodB.load(p.B, baseB, kb);
+			mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+			const uint32_t tileA = smem0 + stage * C::STAGE_BYTES;
+			prodA.store(tileA);
+			prodB.store(tileA + BM * 128);
+			fence_async_smem();
+			__syncwarp();
+			if (lane == 0) mbar_arrive(bar_full + 8 * stage);
+			if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+		}
+
+		// ===================== epilogue =====================
+		mbar_wait(bar_accum, 0);
+		tc_fence_after();
+
+		const Epilogue& E = p.E;
+		const int lg = warp & 3, half = warp >> 2;
+		const int m = m_tile * BM + lg * 32 + lane;
+		const bool mvalid = m < E.M;
+		int m0, m1, m2;
+		split3((uint32_t)(mvalid ? m : 0), E.md12, E.md2, m0, m1, m2);
+		float* outp = E.out + (long long)group * E.group_stride + ((long long)m0 * E.ms0 + (long long)m1 * E.ms1 + (long long)m2 * E.ms2);
+		const float* biasp = E.bias ? E.bias + (long long)group * E.bias_group_stride : nullptr;
+		const float bias_m = (E.bias_mode == 2 && mvalid) ? biasp[m] : 0.0f;
+
+		#pragma unroll 1
+		for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
+			uint32_t v[32];
+			tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)c0, v);
+			#pragma unroll
+			for (int j = 0; j < 32; j++) {
+				const int n = n_tile * BN + c0 + j;
+				if (mvalid && n < E.N && kb_end > kb_begin) {
+					float r = E.alpha * __uint_as_float(v[j]);
+					float* dst = outp + (long long)n * E.ncs;
+					if (!E.atomic || split == 0) {   // with split-K the bias is contributed once
+						if (E.bias_mode == 1) r += biasp[n];
+						else if (E.bias_mode == 2) r += bias_m;
+					}
+					if (E.atomic) {
+						atomicAdd(dst, r);           // out was pre-scaled by beta on the host side
+					} else {
+						if (E.beta != 0.0f) r += E.beta * *dst;
+						*dst = r;
+					}
+				}
+			}
+		}
+		tc_fence_before();
+	} else {
+		// ===================== MMA issuer (one thread) =====================
+		constexpr uint32_t idesc = make_idesc_tf32(BM, BN);
+		int stage = 0;
+		uint32_t phase = 0;
+		for (int kb = kb_begin; kb < kb_end; kb++) {
+			mbar_wait(bar_full + 8 * stage, phase);
+			tc_fence_after();
+			if (lane == 0) {
+				const uint32_t tileA = smem0 + stage * C::STAGE_BYTES;
+				const uint64_t da = make_smem_desc(tileA), db = make_smem_desc(tileA + BM * 128);
+				#pragma unroll
+				for (int kk = 0; kk < BK / 8; kk++)    // 8 tf32 = 32 bytes per MMA: +2 in the (addr >> 4) field
+					umma_tf32(tmem_base, da + 2 * kk, db + 2 * kk, idesc, (kb > kb_begin || kk > 0) ? 1u : 0u);
+				umma_commit(bar_empty + 8 * stage);
+			}
+			__syncwarp();
+			if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+		}
+		if (lane == 0) umma_commit(bar_accum);
+		__syncwarp();
+		tc_fence_before();
+	}
+
+	__syncthreads();
+	if (warp == NPROD_WARPS) {
+		tc_fence_after();
+		tmem_dealloc(tmem_base, BN);
+	}
+}
+
+// host-side launcher (defined in pz_gemm.cu)
+int launch(const GemmParams& p, int bn, int amode, int bmode, bool cdiv, int groups, cudaStream_t stream);
+int pick_bn(int n);
+
+// helpers to build operands
+Operand dense_k(const float* ptr, int rows, int kdim, long long ld);     // element (row,k) at ptr[row*ld + k]
+Operand dense_mn(const float* ptr, int rows, int kdim, long long ld);    // element (row,k) at ptr[k*ld + row]
+
+}  // namespace pzumma
