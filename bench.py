@@ -1,0 +1,308 @@
+"""bench.py -- ResNet-50 fp32 forward+backward images/s on synthetic Nx3x224x224 (BASELINE.json configs[1]).
+
+  python bench.py --gpus 1 --steps K --warmup W                      this repo's CUDA path (one JSON line)
+  python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...   data parallel, one rank per GPU
+  python bench.py --impl reference ...                               the CPU arm (oracle port on the host cores)
+
+One "step" = zeroGradParams + net(data) + net.backward(grad) + gradient sync (mean over ranks, NCCL) + momentum-SGD
+update, i.e. one Trainer.handleBatch of the reference with the cost replaced by a fixed synthetic output gradient
+(SURVEY 8d C2/C4).  `value` times K steps with the input batch already resident in HBM; `e2e` repeats the measurement
+with the batch copied from pinned host memory every step and the softmax output read back to the host every step.
+torch is used only as the rendezvous (gloo) between ranks; all device work goes through libpzb200.so.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+	sys.path.insert(0, ROOT)
+
+METRIC = "ResNet-50 fp32 fwd+bwd images/sec"
+BATCH = 64
+FLOP_PER_IMAGE = 23.01e9          # 3 x (490.53 GFLOP conv + 0.262 fc) / 64
+
+
+def loadPeaks():
+	path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+	if os.path.exists(path):
+		with open(path) as f:
+			peaks = json.load(f)
+		return {"hbm": float(peaks["hbm_gbs"]), "bf16": float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])), "src": "measured"}
+	return {"hbm": 6650.0, "bf16": 1400.0, "src": "fallback"}
+
+
+# ---------------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+	FIELDS = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+			 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+	def __init__(self, device):
+		self.device, self.samples, self.proc, self.thread = device, [], None, None
+
+	def start(self):
+		try:
+			self.proc = subprocess.Popen(
+				["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits", "-lms", "100"],
+				stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True
+			)
+		except OSError:
+			return
+		self.thread = threading.Thread(target=self._read, daemon=True)
+		self.thread.start()
+
+	def _read(self):
+		for line in self.proc.stdout:
+			parts = [p.strip() for p in line.split(",")]
+			if len(parts) >= 7:
+				self.samples.append(parts)
+
+	def stop(self):
+		if self.proc is None:
+			return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+		self.proc.terminate()
+		try:
+			self.proc.wait(timeout=5)
+		except Exception:
+			self.proc.kill()
+
+		sm, smmax, reasons = [], [], set()
+		for parts in self.samples:
+			try:
+				sm.append(float(parts[0]))
+				smmax.append(float(parts[1]))
+			except ValueError:
+				continue
+			for name, flag in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[3:7]):
+				if flag.lower().startswith("active"):
+					reasons.add(name)
+		return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smmax) if smmax else None,
+				"reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------- CPU arm
+def cpuThreads():
+	try:
+		from threadpoolctl import threadpool_info
+		return max([info.get("num_threads", 1) for info in threadpool_info()] or [os.cpu_count() or 1])
+	except Exception:
+		return os.cpu_count() or 1
+
+
+def cpuStep(net, x, gy):
+	from oracle import refnet      # the CPU baseline IS the oracle port (cpu_baseline.kind = "port")
+	for layer in net.leaves():
+		for name in ("dW", "db", "dscale", "dbias"):
+			if getattr(layer, name, None) is not None:
+				setattr(layer, name, np.zeros_like(getattr(layer, name)))
+	net.forward(x, np.float32)
+	net.backward(gy, np.float32, 1.0, 1.0)
+
+
+def cpuBaseline(images, steps, warmup):
+	from oracle import refnet
+	net = refnet.init_he(refnet.resnet50(), seed=1234)
+	rng = np.random.RandomState(1234)
+	x = rng.randn(images, 3, 224, 224).astype(np.float32)
+	gy = (rng.randn(images, 1000) * 1e-3).astype(np.float32)
+
+	for _ in range(warmup):
+		cpuStep(net, x, gy)
+	t0 = time.perf_counter()
+	for _ in range(steps):
+		cpuStep(net, x, gy)
+	dt = (time.perf_counter() - t0) / steps
+	return images / dt, dt
+
+
+def referenceArm(args):
+	rank = int(os.environ.get("RANK", "0"))
+	if rank != 0:
+		return
+
+	# bounded sample: calibrate the per-step image count so that (steps + warmup) steps stay within ~150 s
+	ips, dt = cpuBaseline(1, 1, 1)
+	budget = 150.0 / max(1, args.steps + args.warmup)
+	images = int(max(1, min(BATCH, budget * ips * 1.5)))
+	ips, dt = cpuBaseline(images, args.steps, args.warmup)
+	cores = cpuThreads()
+
+	line = {
+		"impl": "reference", "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
+		"warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+		"dtype": "f32", "data": "synthetic",
+		"config": {"workload": "ResNet-50 fp32 fwd+bwd, synthetic %dx3x224x224 (bounded sample of the 64-image batch)" % images,
+				   "images_per_step": images, "parallelism": "cpu"},
+		"cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
+						 "sample": "%d images/step, %d steps: numpy float32 restatement of the reference ops (oracle/refnet.py); "
+								   "the reference's own numpy CPU backend has no conv/pool/batch-norm backward (SURVEY F5)" % (images, args.steps)},
+		"e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+		"gpu_launches": 0,
+	}
+	print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------- GPU arm
+def gpuArm(args):
+	from puzzlelib_b200 import Config, driver
+	from puzzlelib_b200.grid import nodeFromEnvironment
+
+	node = nodeFromEnvironment()
+	if node.gridsize != args.gpus:
+		raise SystemExit("--gpus %d does not match WORLD_SIZE %d (launch with torch.distributed.run)" % (args.gpus, node.gridsize))
+
+	Config.deviceIdx = node.device
+	driver.Device(node.device).set()
+	node.attach()
+
+	from puzzlelib_b200 import modules as M
+	from puzzlelib_b200.nets import loadResNet
+	from puzzlelib_b200.optim import MomentumSGD
+	from puzzlelib_b200.shim import backend
+
+	bnd = backend()
+	np.random.seed(1234)                       # same initial weights on every rank (and broadcast from rank 0 anyway)
+	net = loadResNet(None, "50", initscheme="he")
+	optimizer = MomentumSGD(learnRate=1e-3, momRate=0.9, nodeinfo=node if node.gridsize > 1 else None)
+	optimizer.setupOn(net, useGlobalState=True)
+
+	rng = np.random.RandomState(1234 + node.index)      # every rank draws its own shard of the global batch
+	pinned = driver.PinnedBuffer((BATCH, 3, 224, 224), np.float32)
+	pinned.array[...] = rng.randn(BATCH, 3, 224, 224).astype(np.float32)
+	data = M.gpuarray.to_gpu(pinned.array)
+	grad = M.gpuarray.to_gpu((rng.randn(BATCH, 1000) * 1e-3).astype(np.float32))
+	hostOut = driver.PinnedBuffer((BATCH, 1000), np.float32)
+
+	def step(e2e=False):
+		if e2e:
+			data.set(pinned.array)                                   # H2D from pinned memory
+		optimizer.zeroGradParams()
+		out = net(data)
+		net.backward(grad)
+		optimizer.update()                                           # N > 1: all-reduce(mean) fused with the SGD update
+		if e2e:
+			driver.check(driver.lib.pz_memcpy_d2h(hostOut.ptr, out.ptr, out.nbytes, None, 0))      # D2H of the step's result
+		net.reset()                                                  # like Handler.handle: activations go back to the pool
+
+	def timed(nsteps, e2e=False):
+		node.barrier()
+		driver.Device.synchronize()
+		start, end = driver.Event(), driver.Event()
+		launches = driver.launchCount()
+		start.record()
+		for _ in range(nsteps):
+			step(e2e)
+		end.record()
+		end.synchronize()
+		driver.Device.synchronize()
+		ms = start.timeTill(end)
+		launches = driver.launchCount() - launches
+		node.barrier()
+		if node.gridsize > 1:
+			ms = node.rendezvous.maxValue(ms)                        # device time, max over ranks
+		return ms, launches
+
+	for _ in range(max(3, args.warmup)):
+		step()
+
+	sampler = ClockSampler(node.device) if node.index == 0 else None
+	if sampler:
+		sampler.start()
+	ms, launches = timed(args.steps)
+	clocks = sampler.stop() if sampler else None
+
+	msE2e, _ = timed(args.steps, e2e=True)
+
+	# roofline pass: the same K steps with CUDA events around every launch of each kernel family
+	driver.profileEnable(True)
+	msProf, _ = timed(args.steps)
+	driver.profileEnable(False)
+	families = {name: driver.profileCollect(name) for name in driver.PROF_FAMILIES}
+
+	if node.index != 0:
+		node.close()
+		return
+
+	peaks = loadPeaks()
+	images = BATCH * node.gridsize * args.steps
+	value = images / (ms * 1e-3)
+
+	total = sum(f["ms"] for f in families.values()) or 1.0
+	top = max(families, key=lambda name: families[name]["ms"])
+	fam = families[top]
+	if top == "gemm":
+		achieved = fam["flops"] / (fam["ms"] * 1e-3) / 1e12
+		peak = peaks["bf16"] / 2.0
+		roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+					"peak_note": "tf32 products: 0.5 x the %s bf16 sustained GEMM peak (no tf32 figure in MEASURED_PEAKS.json)" % peaks["src"]}
+	else:
+		achieved = fam["bytes"] / (fam["ms"] * 1e-3) / 1e9
+		roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm"], "unit": "GB/s", "frac": achieved / peaks["hbm"],
+					"traffic": None, "peak_note": "%s STREAM-style copy bandwidth" % peaks["src"]}
+	roofline.update({
+		"kernel": {"gemm": "umma_gemm_kernel (tcgen05 implicit-GEMM conv / GEMM)", "bn_fwd": "bn_fwd_train_kernel", "bn_bwd": "bn_bwd_kernel",
+				   "eltwise": "ew_kernel", "pool": "pool kernels", "other": "other"}[top],
+		"launches_per_step": fam["launches"] / args.steps, "avg_launch_us": fam["ms"] * 1e3 / max(1, fam["launches"]),
+		"share_of_profiled_kernel_time": fam["ms"] / total, "profiled_ms_per_step": msProf / args.steps,
+		"families_ms_per_step": {name: f["ms"] / args.steps for name, f in families.items()},
+		"families_achieved": {
+			name: ({"TFLOP/s": f["flops"] / (f["ms"] * 1e-3) / 1e12} if name == "gemm" else {"GB/s": f["bytes"] / (f["ms"] * 1e-3) / 1e9})
+			for name, f in families.items() if f["ms"] > 0
+		},
+	})
+
+	line = {
+		"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": node.gridsize, "steps": args.steps, "warmup": max(3, args.warmup),
+		"ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+		"dtype": "f32 (tensor-core contractions: tf32 products, f32 accumulation -- what cuDNN/cuBLAS TENSOR_OP_MATH give the reference here)",
+		"data": "synthetic",
+		"config": {
+			"workload": "ResNet-50 fp32 fwd+bwd, synthetic 64x3x224x224 per GPU (BASELINE.json configs[1])", "batch_per_gpu": BATCH,
+			"global_batch": BATCH * node.gridsize, "parallelism": "dp%d" % node.gridsize,
+			"step": "zeroGradParams + forward + backward (incl. conv1 dgrad) + grad mean over ranks + momentum-SGD update",
+			"l2": "no explicit flush: one step streams ~20 GB of activations through the 126 MB L2, every kernel's inputs exceed L2 between reuses",
+			"model_flops_per_image": FLOP_PER_IMAGE, "achieved_model_tflops_per_gpu": value / node.gridsize * FLOP_PER_IMAGE / 1e12,
+		},
+		"clocks": clocks,
+		"e2e": {"value": images / (msE2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": int(data.nbytes) * node.gridsize,
+				"d2h_bytes_per_step": BATCH * 1000 * 4 * node.gridsize},
+		"gpu_launches": launches,
+		"roofline": roofline,
+	}
+
+	if node.gridsize == 1 and not args.no_cpu:
+		ips, dt = cpuBaseline(args.cpu_images, 1, 1)
+		line["cpu_baseline"] = {
+			"value": ips, "unit": "images/s", "cores": cpuThreads(), "kind": "port",
+			"sample": "%d images, 1 warm-up + 1 timed fwd+bwd step of the numpy float32 oracle port (oracle/refnet.py), %.1f s; the "
+					  "reference's own numpy CPU backend cannot run conv/pool/batch-norm backward (SURVEY F5)" % (args.cpu_images, dt)
+		}
+
+	print(json.dumps(line), flush=True)
+	node.close()
+
+
+def main():
+	parser = argparse.ArgumentParser()
+	parser.add_argument("--gpus", type=int, default=1)
+	parser.add_argument("--steps", type=int, default=20)
+	parser.add_argument("--warmup", type=int, default=5)
+	parser.add_argument("--impl", default="ours", choices=["ours", "reference"])
+	parser.add_argument("--cpu-images", type=int, default=8, help="bounded CPU-baseline sample (images per step)")
+	parser.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+	args = parser.parse_args()
+
+	if args.impl == "reference":
+		referenceArm(args)
+	else:
+		gpuArm(args)
+
+
+if __name__ == "__main__":
+	main()

@@ -96,6 +96,12 @@ int pz_stream_wait_event(void* stream, void* event);
 /* number of kernels this library has launched on the calling process since load (bench "gpu_launches") */
 uint64_t pz_launch_count(void);
 
+/* per-launch CUDA-event profiling of one kernel family (bench.py roofline numbers). family: 0 tcgen05 GEMM/conv engine,
+ * 1 batch-norm forward, 2 batch-norm backward, 3 elementwise, 4 pooling, 5 other; -1 = all. flops / bytes are the
+ * ALGORITHMIC ones of the recorded launches (operands read once, results written once). */
+int pz_profile_enable(int on);
+int pz_profile_collect(int family, double* total_ms, double* flops, double* bytes, uint64_t* launches);
+
 /* ---------------------------------------------------------------- elementwise (bandwidth-bound)
  * replaces the NVRTC-JIT kernels of Cuda/Kernels/ElementWise.py and Cuda/GPUArray.py */
 /* out = f(in);  a, b are the optional scalars (leakyRelu a, elu a, clip a,b). ElementWise.py:9-445 */
@@ -206,6 +212,7 @@ int pz_bias_grad(int dtype, const void* t, void* db, int64_t N, int64_t C, int64
 
 /* ---------------------------------------------------------------- data-parallel gradient sync (NCCL over NVLink)
  * replaces Grid.py's CUDA-IPC parent/child star (Grid.py:66-157; Buffer.c:411-424) */
+int pz_nccl_version(int* version);                                   /* ncclGetVersion of the loaded libnccl */
 int pz_nccl_unique_id(void* id128);                                  /* 128-byte ncclUniqueId, host memory */
 int pz_nccl_comm_init(void** comm, int nranks, int rank, const void* id128);
 int pz_nccl_comm_destroy(void* comm);
@@ -214,6 +221,9 @@ int pz_nccl_allreduce_mean(void* comm, int dtype, void* buf, int64_t count, floa
 int pz_nccl_broadcast(void* comm, int dtype, void* buf, int64_t count, int root, void* stream); /* Grid.py:114-121 */
 /* fused: all-reduce(sum) the flat gradient, then mom = mr*mom + lr*(grad/P); param += mom in one pass
  * (Optimizer.py:166-170 + MomentumSGD.py:24-27) */
+/* the local half of the fused call: grad *= scale; mom = mr*mom + lr*grad; param += mom (single pass) */
+int pz_mean_sgd_momentum(int dtype, void* param, void* grad, void* mom, int64_t count, float scale, float learn_rate,
+						 float mom_rate, void* stream);
 int pz_nccl_allreduce_sgd_momentum(void* comm, int dtype, void* param, void* grad, void* mom, int64_t count,
 								   float scale, float learn_rate, float mom_rate, void* stream);
 

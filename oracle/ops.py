@@ -1,0 +1,442 @@
+"""CPU oracle of the hot path -- numpy restatement of what the reference's GPU backend computes, op by op.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under puzzlelib_b200/ imports this package; only tests/, __graft_entry__.smoke()
+and bench.py's cpu_baseline / `--impl reference` legs do, and there only as the checker or the timed CPU baseline.
+
+Where the arithmetic lives.  In the reference these ops are calls into closed third-party libraries that are NOT in
+/root/reference and are not version-pinned by it (no version file; requirements.txt lists Python deps only):
+cuDNN (conv / pool / batch-norm / softmax; this image: 9.10.2) and cuBLAS (GEMM; this image: 12.9), plus the
+reference's own NVRTC-JIT kernels (activations, axpy-style updates, max-pool with mask, mat-vec helpers) whose source
+IS in the tree.  Each function below therefore follows either
+  * the JIT kernel source itself (cited file:line), or
+  * the host recomputation the reference's own unit test holds for the library call (cited file:line) -- those test
+    loops are the reference's specification of the cuDNN / cuBLAS result.
+
+Pinning.  (a) tests/golden/ref_cpu_*.npz hold outputs of the REFERENCE ITSELF (its numpy CPU backend, imported from
+/root/reference by tools/gen_golden.py in the build container) for conv2d / pool2d / batch-norm-inference forward,
+Linear forward+backward and every activation forward+backward; tests/test_oracle.py checks this oracle against them.
+(b) The backward conv / pool / batch-norm / softmax formulas cannot be produced by the reference without a GPU (its
+CPU backend is inference-only) -- they are pinned by finite-difference gradient checks of this oracle in
+fp64 (the reference's own TestLib/GradientCheck.py:25-52 method) and by adjoint identities.
+(c) cuDNN's max-pool-backward tie routing, the biased-vs-unbiased running variance and TF32 rounding are asserted by
+no reference test: "parity unpinned" for exactly those three behaviours ("Oracle").
+
+All functions take and return numpy arrays; `dtype` selects the accumulation type (float64 for parity checks,
+float32 for the timed CPU baseline).
+"""
+import numpy as np
+from numpy.lib.stride_tricks import as_strided
+
+FLT_MAX = np.finfo(np.float32).max
+
+
+def _pair(v):
+	return (int(v), int(v)) if isinstance(v, (int, np.integer)) else (int(v[0]), int(v[1]))
+
+
+# ================================================================================================ convolution
+def conv_out_size(insize, fsize, stride, pad, dilation):
+	"""reference: CuDnn.c:242-266"""
+	return (insize + 2 * pad - dilation * (fsize - 1) - 1) // stride + 1
+
+
+def _im2col(xp, R, S, P, Q, stride, dilation):
+	"""(N, C, Hp, Wp) padded input -> view (N, C, R, S, P, Q) without copying"""
+	sN, sC, sH, sW = xp.strides
+	N, C = xp.shape[:2]
+	return as_strided(
+		xp, shape=(N, C, R, S, P, Q),
+		strides=(sN, sC, dilation[0] * sH, dilation[1] * sW, stride[0] * sH, stride[1] * sW), writeable=False
+	)
+
+
+def _padded(x, pad, dtype):
+	N, C, H, W = x.shape
+	if pad == (0, 0) and x.dtype == dtype:
+		return x
+	xp = np.zeros((N, C, H + 2 * pad[0], W + 2 * pad[1]), dtype=dtype)
+	xp[:, :, pad[0]:pad[0] + H, pad[1]:pad[1] + W] = x
+	return xp
+
+
+def conv2d(x, w, bias=None, stride=1, pad=0, dilation=1, groups=1, dtype=np.float64):
+	"""y[n,k,p,q] = sum_{c,r,s} x[n, g*Cg+c, p*sh-ph+r*dh, q*sw-pw+s*dw] * w[k,c,r,s] (+ b[k]) -- cross-correlation.
+	reference: cudnnConvolutionForward call site CuDnn.c:397-449; host loops of the unit tests
+	Cuda/Wrappers/CuDnn.py:29-80 (conv2dTest), :137-201 (convGroupTest); Modules/Conv2D.py:92-327."""
+	stride, pad, dilation = _pair(stride), _pair(pad), _pair(dilation)
+	N, C, H, W = x.shape
+	K, Cg, R, S = w.shape
+	assert C == Cg * groups and K % groups == 0
+	Kg = K // groups
+	P, Q = conv_out_size(H, R, stride[0], pad[0], dilation[0]), conv_out_size(W, S, stride[1], pad[1], dilation[1])
+
+	xp = _padded(x, pad, dtype)
+	y = np.empty((N, K, P, Q), dtype=dtype)
+	wm = w.astype(dtype, copy=False)
+
+	for g in range(groups):
+		cols = _im2col(xp[:, g * Cg:(g + 1) * Cg], R, S, P, Q, stride, dilation).reshape(N, Cg * R * S, P * Q)
+		y[:, g * Kg:(g + 1) * Kg] = np.matmul(wm[g * Kg:(g + 1) * Kg].reshape(Kg, Cg * R * S), cols).reshape(N, Kg, P, Q)
+
+	if bias is not None:
+		y += bias.astype(dtype).reshape(1, K, 1, 1)
+	return y
+
+
+def conv2d_bwd_data(dy, w, inshape=None, bias=None, stride=1, pad=0, dilation=1, postpad=0, groups=1, dtype=np.float64):
+	"""dx = transposed convolution of dy with w; also IS the Deconv forward (+bias over the produced maps).
+	reference: cudnnConvolutionBackwardData call site CuDnn.c:517-571; in-shape with `postpad` :269-284;
+	host loops Cuda/Wrappers/CuDnn.py:29-80 (conv2dTest, bwd data), :204-252 (deconv2dTest)."""
+	stride, pad, dilation, postpad = _pair(stride), _pair(pad), _pair(dilation), _pair(postpad)
+	N, K, P, Q = dy.shape
+	Kw, Cg, R, S = w.shape
+	assert K == Kw
+	C, Kg = Cg * groups, K // groups
+
+	if inshape is None:
+		H = (P - 1) * stride[0] + dilation[0] * (R - 1) - 2 * pad[0] + 1 + postpad[0]
+		W = (Q - 1) * stride[1] + dilation[1] * (S - 1) - 2 * pad[1] + 1 + postpad[1]
+	else:
+		H, W = inshape[2], inshape[3]
+
+	Hp, Wp = H + 2 * pad[0], W + 2 * pad[1]
+	dxp = np.zeros((N, C, Hp, Wp), dtype=dtype)
+	wm = w.astype(dtype, copy=False)
+	dym = dy.astype(dtype, copy=False).reshape(N, K, P * Q)
+
+	for g in range(groups):
+		wg = wm[g * Kg:(g + 1) * Kg].reshape(Kg, Cg * R * S)
+		dcols = np.matmul(wg.T, dym[:, g * Kg:(g + 1) * Kg]).reshape(N, Cg, R, S, P, Q)
+		for r in range(R):
+			for s in range(S):
+				h0, w0 = r * dilation[0], s * dilation[1]
+				dxp[:, g * Cg:(g + 1) * Cg, h0:h0 + (P - 1) * stride[0] + 1:stride[0], w0:w0 + (Q - 1) * stride[1] + 1:stride[1]] += \
+					dcols[:, :, r, s]
+
+	dx = dxp[:, :, pad[0]:pad[0] + H, pad[1]:pad[1] + W]
+	if bias is not None:
+		dx = dx + bias.astype(dtype).reshape(1, C, 1, 1)
+	return np.ascontiguousarray(dx)
+
+
+def conv2d_bwd_params(x, dy, wshape, stride=1, pad=0, dilation=1, groups=1, withbias=False, deconv=False, wgrad=None,
+					  bgrad=None, scale=1.0, momentum=0.0, dtype=np.float64):
+	"""dW = scale * sum_{n,p,q} x (*) dy + momentum * dW_old;  db = scale * sum dy + momentum * db_old, where the
+	bias side is `dy` for a conv and `x` for a deconv.
+	reference: cudnnConvolutionBackwardFilter alpha/beta CuDnn.c:682-685, BackwardBias :375-394, deconv side :689-690,774;
+	host loops Cuda/Wrappers/CuDnn.py:29-80 (conv2dTest, wgrad / bgrad), :204-252 (deconv side)."""
+	stride, pad, dilation = _pair(stride), _pair(pad), _pair(dilation)
+	N, C, H, W = x.shape
+	K, Cg, R, S = wshape
+	Kg = K // groups
+	P, Q = dy.shape[2:]
+
+	xp = _padded(x, pad, dtype)
+	dym = dy.astype(dtype, copy=False).reshape(N, K, P * Q)
+	dw = np.empty(wshape, dtype=dtype)
+
+	for g in range(groups):
+		cols = _im2col(xp[:, g * Cg:(g + 1) * Cg], R, S, P, Q, stride, dilation).reshape(N, Cg * R * S, P * Q)
+		acc = np.matmul(dym[:, g * Kg:(g + 1) * Kg], cols.transpose(0, 2, 1)).sum(axis=0)
+		dw[g * Kg:(g + 1) * Kg] = acc.reshape(Kg, Cg, R, S)
+
+	dw = scale * dw + (momentum * wgrad.astype(dtype) if wgrad is not None and momentum != 0.0 else 0.0)
+	if not withbias:
+		return dw
+
+	side = x if deconv else dy
+	db = scale * side.astype(dtype).sum(axis=(0, 2, 3))
+	if bgrad is not None and momentum != 0.0:
+		db = db + momentum * bgrad.astype(dtype).ravel()
+	return dw, db
+
+
+# ================================================================================================ GEMM / mat-vec
+def gemm(A, B, out=None, transpA=False, transpB=False, alpha=1.0, beta=0.0, dtype=np.float64):
+	"""reference: cublasGemmEx call site CuBlas.c:327-403; unit test Cuda/Wrappers/CuBlas.py:32-47 (matrixTest)"""
+	a = A.astype(dtype, copy=False)
+	b = B.astype(dtype, copy=False)
+	r = alpha * np.matmul(a.T if transpA else a, b.T if transpB else b)
+	if out is not None and beta != 0.0:
+		r = r + beta * out.astype(dtype)
+	return r
+
+
+def add_vec_to_mat(vec, mat, axis=1):
+	"""reference: Cuda/Kernels/MatVec.py:128-171 (opRowVecToMat / opRowOneVecToMat / opColVecToMat)"""
+	if axis == 1:
+		if vec.shape[-1] == mat.shape[-1]:
+			return mat + vec[..., None, :]
+		reps = mat.shape[-1] // vec.shape[-1]
+		return mat + np.tile(vec, reps)[..., None, :]
+	return mat + vec[..., :, None]
+
+
+def matsum(tensor, axis, out=None, alpha=1.0, beta=0.0, dtype=np.float64):
+	"""reference: Cuda/Kernels/MatVec.py:60-91 (out = beta * out + alpha * sum)"""
+	r = alpha * tensor.astype(dtype).sum(axis=axis)
+	if out is not None:
+		r = r + beta * out.astype(dtype)
+	return r
+
+
+def argmax(tensor, axis):
+	"""first occurrence wins (reference: Cuda/Kernels/MatVec.py:8-57)"""
+	return np.argmax(tensor, axis=axis).astype(np.int32)
+
+
+# ================================================================================================ batch norm
+def batchnorm_train(x, scale, bias, mean, var, epsilon=1e-5, factor=1.0, dtype=np.float64):
+	"""Spatial batch norm, training.  Returns (y, savemean, saveinvvar, new_running_mean, new_running_var).
+	reference: cudnnBatchNormalizationForwardTraining call site CuDnnNorm.c:31-71; unit test formulas
+	Cuda/Wrappers/CuDnnNorm.py:36-48 (y, saveinvvar = 1/sqrt(biased var + eps), running mean at factor 1).
+	The running VARIANCE follows cuDNN's documented behaviour (unbiased estimate) -- not asserted by the reference."""
+	axes = (0, ) + tuple(range(2, x.ndim))
+	shape = (1, -1) + (1, ) * (x.ndim - 2)
+	xd = x.astype(dtype)
+	m = xd.size // xd.shape[1]
+
+	mu = xd.mean(axis=axes)
+	varb = xd.var(axis=axes)
+	invstd = 1.0 / np.sqrt(varb + epsilon)
+
+	y = (xd - mu.reshape(shape)) * invstd.reshape(shape) * scale.astype(dtype).reshape(shape) + bias.astype(dtype).reshape(shape)
+
+	varu = varb * m / (m - 1) if m > 1 else varb
+	newmean = (1.0 - factor) * mean.astype(dtype).ravel() + factor * mu
+	newvar = (1.0 - factor) * var.astype(dtype).ravel() + factor * varu
+	return y, mu, invstd, newmean, newvar
+
+
+def batchnorm_infer(x, scale, bias, mean, var, epsilon=1e-5, dtype=np.float64):
+	"""reference: cudnnBatchNormalizationForwardInference CuDnnNorm.c:55; test Cuda/Wrappers/CuDnnNorm.py:70-77;
+	CPU backend CPU/Wrappers/NumpyDnn.py:115-129"""
+	shape = (1, -1) + (1, ) * (x.ndim - 2)
+	a = scale.astype(dtype).ravel() / np.sqrt(var.astype(dtype).ravel() + epsilon)
+	b = bias.astype(dtype).ravel() - mean.astype(dtype).ravel() * a
+	return x.astype(dtype) * a.reshape(shape) + b.reshape(shape)
+
+
+def batchnorm_bwd(x, dy, scale, savemean, saveinvvar, dtype=np.float64):
+	"""dbias = sum dy; dscale = sum dy * xhat; dx = scale * invstd * (dy - dbias/m - xhat * dscale/m)
+	reference: cudnnBatchNormalizationBackward CuDnnNorm.c:158-194; test formulas Cuda/Wrappers/CuDnnNorm.py:50-68"""
+	axes = (0, ) + tuple(range(2, x.ndim))
+	shape = (1, -1) + (1, ) * (x.ndim - 2)
+	xd, g = x.astype(dtype), dy.astype(dtype)
+	m = xd.size // xd.shape[1]
+
+	invstd = saveinvvar.astype(dtype).reshape(shape)
+	xhat = (xd - savemean.astype(dtype).reshape(shape)) * invstd
+	dbias = g.sum(axis=axes)
+	dscale = (g * xhat).sum(axis=axes)
+	dx = scale.astype(dtype).reshape(shape) * invstd * (g - dbias.reshape(shape) / m - xhat * dscale.reshape(shape) / m)
+	return dx, dscale, dbias
+
+
+# ================================================================================================ pooling
+def pool_out_size(insize, fsize, stride, pad):
+	"""reference: CuDnnPool.c:24-41; Cuda/Kernels/Pool.py:131-132"""
+	return (insize + 2 * pad - fsize) // stride + 1
+
+
+def _windows(H, W, size, stride, pad):
+	OH, OW = pool_out_size(H, size[0], stride[0], pad[0]), pool_out_size(W, size[1], stride[1], pad[1])
+	for oh in range(OH):
+		h0 = oh * stride[0] - pad[0]
+		h1 = min(h0 + size[0], H)
+		h0 = max(h0, 0)
+		for ow in range(OW):
+			w0 = ow * stride[1] - pad[1]
+			w1 = min(w0 + size[1], W)
+			w0 = max(w0, 0)
+			yield oh, ow, h0, h1, w0, w1
+
+
+def maxpool2d_mask(x, size=2, stride=2, pad=0):
+	"""Max pool returning (y, int32 mask): mask = h*W + w of the FIRST strict maximum of a row-major scan of the
+	window clipped to the plane, starting from -FLT_MAX; -1 for an empty window.
+	reference: kernel Cuda/Kernels/Pool.py:10-46; unit test :229-263 (exact mask equality)."""
+	size, stride, pad = _pair(size), _pair(stride), _pair(pad)
+	N, C, H, W = x.shape
+	OH, OW = pool_out_size(H, size[0], stride[0], pad[0]), pool_out_size(W, size[1], stride[1], pad[1])
+	y = np.full((N, C, OH, OW), -FLT_MAX, dtype=np.float32)
+	mask = np.full((N, C, OH, OW), -1, dtype=np.int32)
+
+	for oh, ow, h0, h1, w0, w1 in _windows(H, W, size, stride, pad):
+		if h1 <= h0 or w1 <= w0:
+			continue
+		win = x[:, :, h0:h1, w0:w1].reshape(N, C, -1)
+		valid = win > -FLT_MAX                      # NaN and -FLT_MAX never win the strict '>' test
+		cand = np.where(valid, win, -np.inf)
+		idx = np.argmax(cand, axis=2)               # first occurrence of the maximum
+		has = valid.any(axis=2)
+		hh, ww = h0 + idx // (w1 - w0), w0 + idx % (w1 - w0)
+		y[:, :, oh, ow] = np.where(has, np.take_along_axis(win, idx[..., None], axis=2)[..., 0], -FLT_MAX)
+		mask[:, :, oh, ow] = np.where(has, hh * W + ww, -1)
+	return y, mask
+
+
+def maxpool2d_mask_bwd(dy, inshape, mask, size=2, stride=2, pad=0):
+	"""dx[h,w] = sum over the candidate windows, in (ph, pw) order, of dy where mask == h*W + w (fp32 adds).
+	reference: kernel Cuda/Kernels/Pool.py:66-96; unit test :265-281."""
+	size, stride, pad = _pair(size), _pair(stride), _pair(pad)
+	N, C, H, W = inshape
+	dx = np.zeros((N, C, H * W), dtype=np.float32)
+	OH, OW = dy.shape[2:]
+	n_idx, c_idx = np.meshgrid(np.arange(N), np.arange(C), indexing="ij")
+
+	for oh in range(OH):                            # (ph, pw) ascending = the kernel's accumulation order per element
+		for ow in range(OW):
+			m = mask[:, :, oh, ow]
+			ok = m >= 0
+			np.add.at(dx, (n_idx[ok], c_idx[ok], m[ok]), dy[:, :, oh, ow][ok].astype(np.float32))
+	return dx.reshape(N, C, H, W)
+
+
+def maxunpool2d(x, outshape, mask):
+	"""reference: kernel Cuda/Kernels/Pool.py:48-63"""
+	N, C = x.shape[:2]
+	y = np.zeros((N, C, outshape[2] * outshape[3]), dtype=x.dtype)
+	np.put_along_axis(y, mask.reshape(N, C, -1).astype(np.int64), x.reshape(N, C, -1), axis=2)
+	return y.reshape(N, C, outshape[2], outshape[3])
+
+
+def maxunpool2d_bwd(dy, poolshape, mask):
+	"""reference: kernel Cuda/Kernels/Pool.py:98-112"""
+	N, C = dy.shape[:2]
+	dx = np.take_along_axis(dy.reshape(N, C, -1), mask.reshape(N, C, -1).astype(np.int64), axis=2)
+	return dx.reshape(N, C, poolshape[2], poolshape[3])
+
+
+def pool2d(x, size=2, stride=2, pad=0, mode="max", dtype=np.float64):
+	"""cuDNN-style pooling forward.  mode: max | avgWithPad (divide by fh*fw) | avgNoPad (divide by the valid count).
+	reference: cudnnPoolingForward call site CuDnnPool.c:64-96 (NOT_PROPAGATE_NAN); host loops of the unit test
+	Cuda/Wrappers/CuDnn.py:376-393 (maxpool2dTest); CPU backend CPU/Wrappers/NumpyDnn.py:83-112 (max, avg-with-pad)."""
+	size, stride, pad = _pair(size), _pair(stride), _pair(pad)
+	N, C, H, W = x.shape
+	OH, OW = pool_out_size(H, size[0], stride[0], pad[0]), pool_out_size(W, size[1], stride[1], pad[1])
+	xd = x.astype(dtype)
+	y = np.empty((N, C, OH, OW), dtype=dtype)
+
+	for oh, ow, h0, h1, w0, w1 in _windows(H, W, size, stride, pad):
+		win = xd[:, :, h0:h1, w0:w1]
+		if mode == "max":
+			y[:, :, oh, ow] = np.fmax.reduce(win.reshape(N, C, -1), axis=2)
+		else:
+			cnt = size[0] * size[1] if mode == "avgWithPad" else (h1 - h0) * (w1 - w0)
+			y[:, :, oh, ow] = win.sum(axis=(2, 3)) / cnt
+	return y
+
+
+def pool2d_bwd(x, y, dy, size=2, stride=2, pad=0, mode="max", dtype=np.float64):
+	"""cuDNN-style pooling backward.  max: the window's dy goes to the FIRST element equal to the window maximum
+	(row-major); with no ties this is the reference test's expectation (Cuda/Wrappers/CuDnn.py:395-410).  Tie routing
+	itself is not asserted by any reference test -- "parity unpinned" for ties.
+	reference: cudnnPoolingBackward call site CuDnnPool.c:155-190."""
+	size, stride, pad = _pair(size), _pair(stride), _pair(pad)
+	N, C, H, W = x.shape
+	dx = np.zeros((N, C, H, W), dtype=dtype)
+	g = dy.astype(dtype)
+	n_idx, c_idx = np.meshgrid(np.arange(N), np.arange(C), indexing="ij")
+
+	for oh, ow, h0, h1, w0, w1 in _windows(H, W, size, stride, pad):
+		if mode == "max":
+			win = x[:, :, h0:h1, w0:w1].reshape(N, C, -1)
+			idx = np.argmax(win == y[:, :, oh, ow][..., None].astype(x.dtype), axis=2)
+			hh, ww = h0 + idx // (w1 - w0), w0 + idx % (w1 - w0)
+			np.add.at(dx, (n_idx, c_idx, hh, ww), g[:, :, oh, ow])
+		else:
+			cnt = size[0] * size[1] if mode == "avgWithPad" else (h1 - h0) * (w1 - w0)
+			dx[:, :, h0:h1, w0:w1] += (g[:, :, oh, ow] / cnt)[..., None, None]
+	return dx
+
+
+# ================================================================================================ softmax
+def softmax(x, mode="spatial", dtype=np.float64):
+	"""SOFTMAX_ACCURATE: exp(x - max) / sum.  spatial = over axis 1 for every (n, spatial...) position
+	(CUDNN_SOFTMAX_MODE_CHANNEL); perActivation = over all non-batch axes (MODE_INSTANCE).
+	reference: cudnnSoftmaxForward call site CuDnn.c:974-997; unit test Cuda/Wrappers/CuDnn.py:454-470 (softmax2dTest)"""
+	xd = x.astype(dtype)
+	axes = 1 if mode == "spatial" else tuple(range(1, x.ndim))
+	e = np.exp(xd - xd.max(axis=axes, keepdims=True))
+	return e / e.sum(axis=axes, keepdims=True)
+
+
+def softmax_bwd(y, dy, mode="spatial", dtype=np.float64):
+	"""dx = y * (dy - sum(y * dy)).  reference: cudnnSoftmaxBackward CuDnn.c:1053-1079; test Cuda/Wrappers/CuDnn.py:472-485"""
+	yd, g = y.astype(dtype), dy.astype(dtype)
+	axes = 1 if mode == "spatial" else tuple(range(1, y.ndim))
+	return yd * (g - (yd * g).sum(axis=axes, keepdims=True))
+
+
+# ================================================================================================ elementwise
+def _erf(x):
+	from math import erf
+	return np.vectorize(erf, otypes=[np.float64])(x)
+
+
+def activation(kind, x, a=None, b=None, dtype=np.float64):
+	"""reference formulas: Cuda/Kernels/ElementWise.py:18 (sigmoid), :73 (tanh), :128 (relu), :184-188 (leakyRelu),
+	:249-254 (elu), :313 (softPlus), :369-373 (clip), :436-441 (gelu); same in CPU/Kernels/ElementWise.py"""
+	x = x.astype(dtype)
+	if kind == "sigmoid":
+		return 1.0 / (1.0 + np.exp(-x))
+	if kind == "tanh":
+		return np.tanh(x)
+	if kind == "relu":
+		return x * (x > 0)
+	if kind == "leakyRelu":
+		a = 0.01 if a is None else a
+		return x * ((x > 0) + a * (x <= 0))
+	if kind == "elu":
+		a = 1.0 if a is None else a
+		return x * (x > 0) + a * (np.exp(x) - 1.0) * (x <= 0)
+	if kind == "softPlus":
+		return np.log(1.0 + np.exp(x))
+	if kind == "clip":
+		a, b = (0.0 if a is None else a), (6.0 if b is None else b)
+		return np.minimum(b, np.maximum(a, x))
+	if kind == "gelu":
+		return 0.5 * x * (1.0 + _erf(x / np.sqrt(2.0)))
+	raise ValueError(kind)
+
+
+def activation_bwd(kind, g, ref, a=None, b=None, dtype=np.float64):
+	"""`ref` is the activation OUTPUT (the INPUT for gelu, whose Gaussian term uses 1/sqrt(pi), sic).
+	reference: Cuda/Kernels/ElementWise.py:45, :100, :156, :215-220, :281-286, :341, :403-407, :468-477"""
+	g, d = g.astype(dtype), ref.astype(dtype)
+	if kind == "sigmoid":
+		return g * d * (1.0 - d)
+	if kind == "tanh":
+		return g * (1.0 - d * d)
+	if kind == "relu":
+		return g * (d > 0)
+	if kind == "leakyRelu":
+		a = 0.01 if a is None else a
+		return g * ((d > 0) + a * (d <= 0))
+	if kind == "elu":
+		a = 1.0 if a is None else a
+		return g * ((d > 0) + (d + a) * (d <= 0))
+	if kind == "softPlus":
+		return g * (1.0 - np.exp(-d))
+	if kind == "clip":
+		a, b = (0.0 if a is None else a), (6.0 if b is None else b)
+		return g * ((d > a) & (d < b))
+	if kind == "gelu":
+		return g * (0.5 * (1.0 + _erf(d / np.sqrt(2.0))) + d / np.sqrt(np.pi) * np.exp(-0.5 * d * d))
+	raise ValueError(kind)
+
+
+def sgd_momentum(param, grad, mom, learnRate, momRate, dtype=np.float64):
+	"""mom = momRate * mom + learnRate * grad; param += mom (gradients are ascent direction).
+	reference: Cuda/Kernels/ElementWise.py:771-800; Optimizers/MomentumSGD.py:24-27"""
+	mom = momRate * mom.astype(dtype) + learnRate * grad.astype(dtype)
+	return param.astype(dtype) + mom, mom
+
+
+def grid_mean(tensors, dtype=np.float64):
+	"""Grid.sumTensor: the mean of the per-rank buffers (reference: Grid.py:123-135, beta = 1/P)"""
+	acc = np.zeros_like(tensors[0], dtype=dtype)
+	for t in tensors:
+		acc += t.astype(dtype)
+	return acc / len(tensors)

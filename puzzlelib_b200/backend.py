@@ -1,0 +1,887 @@
+"""The `CudaBackend`-shaped object of the B200 backend -- the drop-in seam.
+
+The reference reaches the GPU only through `PuzzleLib.Cuda.Backend.getBackend(deviceIdx, initmode)` and the
+attributes of the object it returns (reference: Cuda/Backend.py:50-66,353-370; Cuda/GPUBackend.py:17-215;
+consumers: Backend/gpuarray.py:60-113, Backend/Dnn.py:159-338, Backend/Blas.py:43-102, Backend/Kernels/*.py).
+This module provides the same function and an object with the same attribute names and call signatures, where
+every operation is one call into the C-ABI of libpzb200.so (hand-written sm_100a kernels).  There is no cuDNN,
+cuBLAS, NVRTC or CPU fallback behind it.
+
+`dnn`      mirrors CuDnn.DnnContext    (Cuda/Source/Libs/CuDnn.c, CuDnnPool.c, CuDnnNorm.c)
+`blas`     mirrors CuBlas.BlasContext  (Cuda/Source/Libs/CuBlas.c)
+`matmod`   mirrors MatModule           (Cuda/Kernels/MatVec.py)
+`poolmod`  mirrors PoolModule          (Cuda/Kernels/Pool.py)
+`*Ker`     mirror the kernel factories of Cuda/Kernels/ElementWise.py
+"""
+from enum import Enum
+from collections import OrderedDict
+from ctypes import byref
+
+import numpy as np
+
+from . import driver
+from .driver import lib, check, dtypeCode, Conv2dDesc, CuDnnError, CuBlasError
+from .gpuarray import GPUArray
+
+_f32 = np.dtype(np.float32)
+_i32 = np.dtype(np.int32)
+
+
+def prod(seq):
+	n = 1
+	for d in seq:
+		n *= int(d)
+	return n
+
+
+def _seq(val, nd, default, name):
+	"""int / sequence / None -> tuple of nd ints (reference: Libs.h:91-119 CuDnn_unpackIntSequence)."""
+	if val is None:
+		return (default, ) * nd
+	if isinstance(val, (int, np.integer)):
+		return (int(val), ) * nd
+	val = tuple(int(v) for v in val)
+	if len(val) != nd:
+		raise ValueError("%s must be int or %d-elem tuple" % (name, nd))
+	return val
+
+
+def _requireArray(ary, name):
+	if not isinstance(ary, GPUArray):
+		raise TypeError("%s must be a GPUArray (got %s)" % (name, type(ary).__name__))
+	if not ary.contiguous:
+		raise ValueError("invalid %s gpuarray data layout" % name)
+
+
+def _checkOut(out, shape, dtype):
+	# reference: CuDnn.c:77-134 -- an `out` array must match shape and dtype exactly
+	_requireArray(out, "output")
+	if out.shape != tuple(shape) or out.dtype != dtype:
+		raise ValueError("invalid output gpuarray data layout")
+	return out
+
+
+# ============================================================================================================ dnn
+class DnnContext:
+	"""Hand-written sm_100a replacements of the cuDNN entry points the reference uses."""
+
+	def __init__(self, backend):
+		self.backend = backend
+		self.tensorOps = True
+
+	@staticmethod
+	def getVersion():
+		return int(lib.pz_version())
+
+	def enableTensorOps(self, enable):
+		# the tcgen05 path is the only one; fp32 storage always computes as TF32 like cuDNN's TENSOR_OP_MATH
+		self.tensorOps = bool(enable)
+
+	# ------------------------------------------------------------------------------------------ convolution
+	@staticmethod
+	def _convDesc(datashape, Wshape, outshape, stride, pad, dilation, groups):
+		N, C, H, W = datashape
+		K, _, R, S = Wshape
+		return Conv2dDesc(N, C, H, W, K, R, S, outshape[2], outshape[3], stride[0], stride[1], pad[0], pad[1],
+						  dilation[0], dilation[1], groups)
+
+	@staticmethod
+	def _check4d(ary, name):
+		_requireArray(ary, name)
+		if ary.ndim == 5:
+			raise NotImplementedError("3-d convolution / pooling is not implemented in the B200 backend yet")
+		if ary.ndim != 4:
+			raise ValueError("invalid %s gpuarray dims" % name)
+
+	def convNd(self, data, W, bias=None, stride=1, pad=0, dilation=1, groups=1, algo=0, out=None, allocator=None):
+		"""reference: CuDnn_Context_pyConvNd, CuDnn.c:457-514 (out shape :242-266)"""
+		self._check4d(data, "data")
+		self._check4d(W, "W")
+		stride, pad, dilation = _seq(stride, 2, 1, "stride"), _seq(pad, 2, 0, "pad"), _seq(dilation, 2, 1, "dilation")
+
+		if data.dtype != W.dtype:
+			raise ValueError("invalid W gpuarray data layout")
+		if data.shape[1] != W.shape[1] * groups:
+			raise ValueError("invalid number of input maps")
+		if W.shape[0] % groups != 0:
+			raise ValueError("invalid number of output maps")
+
+		outshape = [data.shape[0], W.shape[0]]
+		for i in range(2):
+			ext = data.shape[2 + i] + 2 * pad[i] - dilation[i] * (W.shape[2 + i] - 1) - 1
+			if ext < 0:
+				raise ValueError("invalid input map size on dim #%d" % (i + 1))
+			outshape.append(ext // stride[i] + 1)
+		outshape = tuple(outshape)
+
+		if bias is not None:
+			_requireArray(bias, "bias")
+			if bias.ndim != 1 or bias.shape[0] != W.shape[0] or bias.dtype != data.dtype:
+				raise ValueError("invalid bias gpuarray data layout")
+
+		out = GPUArray(outshape, data.dtype, allocator=allocator) if out is None else _checkOut(out, outshape, data.dtype)
+		desc = self._convDesc(data.shape, W.shape, outshape, stride, pad, dilation, groups)
+
+		check(lib.pz_conv2d_fprop(dtypeCode(data.dtype), byref(desc), data.ptr, W.ptr, bias.ptr if bias is not None else None,
+								  out.ptr, None))
+		return out
+
+	def convNdBackwardData(self, grad, W, bias=None, data=None, stride=1, pad=0, dilation=1, postpad=0, groups=1,
+						   algo=0, out=None, allocator=None):
+		"""reference: CuDnn_Context_pyConvNdBackwardData, CuDnn.c:579-649 (in shape :269-322)"""
+		self._check4d(grad, "grad")
+		self._check4d(W, "W")
+		stride, pad, dilation = _seq(stride, 2, 1, "stride"), _seq(pad, 2, 0, "pad"), _seq(dilation, 2, 1, "dilation")
+		postpad = _seq(postpad, 2, 0, "postpad")
+
+		if grad.dtype != W.dtype:
+			raise ValueError("invalid W gpuarray data layout")
+		if grad.shape[1] != W.shape[0]:
+			raise ValueError("invalid number of output maps")
+
+		inmaps = W.shape[1] * groups
+		if data is not None:
+			self._check4d(data, "data")
+			inshape = data.shape
+			if inshape[0] != grad.shape[0] or inshape[1] != inmaps:
+				raise ValueError("invalid data gpuarray dims")
+		else:
+			inshape = (grad.shape[0], inmaps) + tuple(
+				(grad.shape[2 + i] - 1) * stride[i] + dilation[i] * (W.shape[2 + i] - 1) - 2 * pad[i] + 1 + postpad[i]
+				for i in range(2)
+			)
+
+		if bias is not None:
+			_requireArray(bias, "bias")
+			if bias.ndim != 1 or bias.shape[0] != inmaps or bias.dtype != grad.dtype:
+				raise ValueError("invalid bias gpuarray data layout")
+
+		out = GPUArray(inshape, grad.dtype, allocator=allocator) if out is None else _checkOut(out, inshape, grad.dtype)
+		desc = self._convDesc(inshape, W.shape, grad.shape, stride, pad, dilation, groups)
+
+		code = dtypeCode(grad.dtype)
+		wsbytes = int(lib.pz_conv2d_dgrad_workspace(code, byref(desc)))
+		workspace = GPUArray((max(wsbytes, 1), ), np.uint8, allocator=allocator) if wsbytes > 0 else None
+
+		check(lib.pz_conv2d_dgrad(code, byref(desc), grad.ptr, W.ptr, bias.ptr if bias is not None else None, out.ptr,
+								  workspace.ptr if workspace is not None else None, wsbytes, None))
+		return out
+
+	def convNdBackwardParams(self, data, grad, W, stride=1, pad=0, dilation=1, groups=1, withbias=False, deconv=False,
+							 wgrad=None, bgrad=None, scale=1.0, momentum=0.0, algo=0, allocator=None):
+		"""reference: CuDnn_Context_pyConvNdBackwardParams, CuDnn.c:722-800; wgrad / bgrad accumulate IN PLACE with
+		alpha = scale, beta = momentum (:682-685, :388)"""
+		self._check4d(data, "data")
+		self._check4d(grad, "grad")
+		self._check4d(W, "W")
+		stride, pad, dilation = _seq(stride, 2, 1, "stride"), _seq(pad, 2, 0, "pad"), _seq(dilation, 2, 1, "dilation")
+
+		if data.dtype != grad.dtype or data.dtype != W.dtype:
+			raise ValueError("invalid gpuarray data layout")
+		if data.shape[1] != W.shape[1] * groups or grad.shape[1] != W.shape[0] or data.shape[0] != grad.shape[0]:
+			raise ValueError("invalid number of maps")
+
+		if wgrad is None:
+			wgrad = GPUArray.zeros(W.shape, W.dtype, allocator=allocator)
+		else:
+			_checkOut(wgrad, W.shape, W.dtype)
+
+		desc = self._convDesc(data.shape, W.shape, grad.shape, stride, pad, dilation, groups)
+		code = dtypeCode(data.dtype)
+		check(lib.pz_conv2d_wgrad(code, byref(desc), data.ptr, grad.ptr, wgrad.ptr, scale, momentum, None))
+
+		if not withbias:
+			return wgrad
+
+		# the bias belongs to the OUTPUT side of the layer: `grad` for a conv, `data` for a deconv (CuDnn.c:689-690,774)
+		side = data if deconv else grad
+		if bgrad is None:
+			bgrad = GPUArray.zeros((side.shape[1], ), side.dtype, allocator=allocator)
+		else:
+			_checkOut(bgrad, (side.shape[1], ), side.dtype)
+
+		check(lib.pz_bias_grad(code, side.ptr, bgrad.ptr, side.shape[0], side.shape[1], prod(side.shape[2:]), scale,
+							   momentum, None))
+		return wgrad, bgrad
+
+	# ------------------------------------------------------------------------------------------ pooling
+	def poolNd(self, data, size=2, stride=2, pad=0, mode=0, out=None, allocator=None):
+		"""reference: CuDnn_Context_pyPoolNd, CuDnnPool.c:102-152"""
+		self._check4d(data, "data")
+		size, stride, pad = _seq(size, 2, 2, "size"), _seq(stride, 2, 2, "stride"), _seq(pad, 2, 0, "pad")
+
+		outshape = [data.shape[0], data.shape[1]]
+		for i in range(2):
+			ext = data.shape[2 + i] + 2 * pad[i]
+			if ext < size[i]:
+				raise ValueError("invalid input map size on dim #%d" % (i + 1))
+			outshape.append((ext - size[i]) // stride[i] + 1)
+		outshape = tuple(outshape)
+
+		out = GPUArray(outshape, data.dtype, allocator=allocator) if out is None else _checkOut(out, outshape, data.dtype)
+		check(lib.pz_pool2d_fwd(dtypeCode(data.dtype), int(mode), data.ptr, out.ptr, data.shape[0] * data.shape[1],
+								data.shape[2], data.shape[3], outshape[2], outshape[3], size[0], size[1], stride[0], stride[1],
+								pad[0], pad[1], None))
+		return out
+
+	def poolNdBackward(self, grad, indata, outdata, size=2, stride=2, pad=0, mode=0, out=None, allocator=None):
+		"""reference: CuDnn_Context_pyPoolNdBackward, CuDnnPool.c:197-245"""
+		self._check4d(grad, "grad")
+		self._check4d(indata, "indata")
+		self._check4d(outdata, "outdata")
+		size, stride, pad = _seq(size, 2, 2, "size"), _seq(stride, 2, 2, "stride"), _seq(pad, 2, 0, "pad")
+
+		if grad.shape != outdata.shape or grad.dtype != indata.dtype or outdata.dtype != indata.dtype:
+			raise ValueError("invalid grad gpuarray data layout")
+
+		out = GPUArray(indata.shape, indata.dtype, allocator=allocator) if out is None else \
+			_checkOut(out, indata.shape, indata.dtype)
+		check(lib.pz_pool2d_bwd(dtypeCode(indata.dtype), int(mode), indata.ptr, outdata.ptr, grad.ptr, out.ptr,
+								indata.shape[0] * indata.shape[1], indata.shape[2], indata.shape[3], outdata.shape[2],
+								outdata.shape[3], size[0], size[1], stride[0], stride[1], pad[0], pad[1], None))
+		return out
+
+	# ------------------------------------------------------------------------------------------ softmax
+	@staticmethod
+	def _ncs(ary):
+		if ary.ndim < 2:
+			raise ValueError("invalid data gpuarray dims")
+		return ary.shape[0], ary.shape[1], prod(ary.shape[2:])
+
+	def softmaxNd(self, data, mode=1, algo=1, out=None, allocator=None):
+		"""reference: CuDnn_Context_pySoftmaxNd, CuDnn.c:1005-1048 (SOFTMAX_ACCURATE)"""
+		_requireArray(data, "data")
+		N, C, S = self._ncs(data)
+		out = GPUArray(data.shape, data.dtype, allocator=allocator) if out is None else _checkOut(out, data.shape, data.dtype)
+		check(lib.pz_softmax_fwd(dtypeCode(data.dtype), int(mode), data.ptr, out.ptr, N, C, S, None))
+		return out
+
+	def softmaxNdBackward(self, grad, outdata, mode=1, algo=1, out=None, allocator=None):
+		"""reference: CuDnn_Context_pySoftmaxNdBackward, CuDnn.c:1087-1131"""
+		_requireArray(grad, "grad")
+		_requireArray(outdata, "outdata")
+		if grad.shape != outdata.shape or grad.dtype != outdata.dtype:
+			raise ValueError("invalid grad gpuarray data layout")
+		N, C, S = self._ncs(grad)
+		out = GPUArray(grad.shape, grad.dtype, allocator=allocator) if out is None else _checkOut(out, grad.shape, grad.dtype)
+		check(lib.pz_softmax_bwd(dtypeCode(grad.dtype), int(mode), outdata.ptr, grad.ptr, out.ptr, N, C, S, None))
+		return out
+
+	# ------------------------------------------------------------------------------------------ batch norm
+	@staticmethod
+	def _bnGeometry(data, mode):
+		if data.ndim < 2:
+			raise ValueError("invalid data gpuarray dims")
+		if mode == 0:   # per activation: one statistic per (c, spatial...) position over the batch
+			return data.shape[0], prod(data.shape[1:]), 1
+		return data.shape[0], data.shape[1], prod(data.shape[2:])
+
+	@staticmethod
+	def _checkBnParam(ary, C, name):
+		_requireArray(ary, name)
+		if ary.dtype != _f32 or ary.size != C:
+			raise ValueError("invalid %s gpuarray data layout" % name)
+
+	def batchNormNd(self, data, mean, var, scale, bias, epsilon=1e-5, factor=1.0, test=False, mode=1, out=None,
+					allocator=None):
+		"""reference: CuDnn_Context_pyBatchNormNd, CuDnnNorm.c:80-155; params and statistics are always fp32 (:118-121)"""
+		_requireArray(data, "data")
+		N, C, S = self._bnGeometry(data, mode)
+		for ary, name in ((mean, "mean"), (var, "var"), (scale, "scale"), (bias, "bias")):
+			self._checkBnParam(ary, C, name)
+
+		out = GPUArray(data.shape, data.dtype, allocator=allocator) if out is None else _checkOut(out, data.shape, data.dtype)
+		code = dtypeCode(data.dtype)
+
+		if test:
+			check(lib.pz_bn_fwd_infer(code, data.ptr, out.ptr, N, C, S, scale.ptr, bias.ptr, mean.ptr, var.ptr, epsilon, None))
+			return out
+
+		savemean = GPUArray(scale.shape, _f32, allocator=allocator)
+		saveinvvar = GPUArray(scale.shape, _f32, allocator=allocator)
+		check(lib.pz_bn_fwd_train(code, data.ptr, out.ptr, N, C, S, scale.ptr, bias.ptr, mean.ptr, var.ptr, savemean.ptr,
+								  saveinvvar.ptr, epsilon, factor, None))
+		return out, savemean, saveinvvar
+
+	def batchNormNdBackward(self, grad, data, scale, savemean=None, saveinvvar=None, epsilon=1e-5, mode=1,
+							scalegrad=None, bgrad=None, out=None, allocator=None):
+		"""reference: CuDnn_Context_pyBatchNormNdBackward, CuDnnNorm.c:201-293"""
+		_requireArray(grad, "grad")
+		_requireArray(data, "data")
+		if grad.shape != data.shape or grad.dtype != data.dtype:
+			raise ValueError("invalid grad gpuarray data layout")
+		N, C, S = self._bnGeometry(data, mode)
+		self._checkBnParam(scale, C, "scale")
+
+		if savemean is None or saveinvvar is None:
+			# cuDNN recomputes the batch statistics when no saved ones are given (CuDnnNorm.c:176-190)
+			tmpmean, tmpvar = GPUArray.zeros(scale.shape, _f32, allocator=allocator), GPUArray.zeros(scale.shape, _f32, allocator=allocator)
+			tmpbias = GPUArray.zeros(scale.shape, _f32, allocator=allocator)
+			_, savemean, saveinvvar = self.batchNormNd(data, tmpmean, tmpvar, scale, tmpbias, epsilon, 1.0, False, mode,
+													   allocator=allocator)
+		else:
+			self._checkBnParam(savemean, C, "savemean")
+			self._checkBnParam(saveinvvar, C, "saveinvvar")
+
+		out = GPUArray(data.shape, data.dtype, allocator=allocator) if out is None else _checkOut(out, data.shape, data.dtype)
+		scalegrad = GPUArray(scale.shape, _f32, allocator=allocator) if scalegrad is None else _checkOut(scalegrad, scale.shape, _f32)
+		bgrad = GPUArray(scale.shape, _f32, allocator=allocator) if bgrad is None else _checkOut(bgrad, scale.shape, _f32)
+
+		check(lib.pz_bn_bwd(dtypeCode(data.dtype), data.ptr, grad.ptr, out.ptr, N, C, S, scale.ptr, savemean.ptr, saveinvvar.ptr,
+							scalegrad.ptr, bgrad.ptr, None))
+		return out, scalegrad, bgrad
+
+
+# ============================================================================================================ blas
+class BlasContext:
+	def __init__(self, backend):
+		self.backend = backend
+
+	def enableTensorOps(self, enable):
+		pass
+
+	def gemm(self, A, B, out=None, transpA=False, transpB=False, alpha=1.0, beta=0.0, allocator=None):
+		"""Row-major out = alpha * op(A) op(B) + beta * out; at most one operand transposed (reference:
+		CuBlas_Context_gemm, CuBlas.c:327-403, shape rules :168-203)"""
+		_requireArray(A, "A")
+		_requireArray(B, "B")
+		if A.ndim != 2 or B.ndim != 2 or A.dtype != B.dtype:
+			raise ValueError("invalid gemm operands")
+		if transpA and transpB:
+			raise ValueError("only one of the gemm operands can be transposed")
+
+		M, K = (A.shape[1], A.shape[0]) if transpA else A.shape
+		Kb, N = (B.shape[1], B.shape[0]) if transpB else B.shape
+		if K != Kb:
+			raise ValueError("gemm operand shapes %s and %s do not match" % (A.shape, B.shape))
+
+		if out is None:
+			out = GPUArray((M, N), A.dtype, allocator=allocator)
+			if beta != 0.0:
+				out.fill(0)
+		else:
+			_checkOut(out, (M, N), A.dtype)
+
+		check(lib.pz_gemm(dtypeCode(A.dtype), A.ptr, B.ptr, out.ptr, M, N, K, A.shape[1], B.shape[1], N, int(transpA),
+						  int(transpB), alpha, beta, None, None))
+		return out
+
+	def gemmBias(self, A, B, bias, out=None, transpB=False, allocator=None):
+		"""Linear forward with the bias add folded into the GEMM epilogue (Linear.py:36-40 as one kernel)."""
+		M, K = A.shape
+		N = B.shape[0] if transpB else B.shape[1]
+		out = GPUArray((M, N), A.dtype, allocator=allocator) if out is None else _checkOut(out, (M, N), A.dtype)
+		check(lib.pz_gemm(dtypeCode(A.dtype), A.ptr, B.ptr, out.ptr, M, N, K, A.shape[1], B.shape[1], N, 0, int(transpB),
+						  1.0, 0.0, bias.ptr, None))
+		return out
+
+
+# ============================================================================================================ matmod
+class MatModule:
+	"""reference: Cuda/Kernels/MatVec.py:216-374"""
+
+	def __init__(self, backend):
+		self.backend = backend
+
+	def addVecToMat(self, vec, mat, axis=0, out=None, allocator=None):
+		assert vec.dtype == mat.dtype
+		assert vec.ndim == mat.ndim - 1 and 0 <= axis < 2
+		assert mat.shape[:-2] == vec.shape[:-1]
+
+		out = GPUArray(mat.shape, mat.dtype, allocator=allocator) if out is None else out
+		z = prod(mat.shape[:-2])
+		n, m = mat.shape[-2:]
+
+		if axis == 1:
+			assert m % vec.shape[-1] == 0
+		else:
+			assert vec.shape[-1] == n
+
+		check(lib.pz_addvec2mat(dtypeCode(mat.dtype), out.ptr, mat.ptr, vec.ptr, z, n, m, axis, vec.shape[-1], None))
+		return out
+
+	def matsum(self, tensor, axis=0, out=None, alpha=1.0, beta=0.0, allocator=None):
+		assert 0 <= axis < tensor.ndim
+		outshape = tensor.shape[:axis] + tensor.shape[axis + 1:]
+
+		if out is None:
+			out = GPUArray.zeros(outshape, tensor.dtype, allocator=allocator)
+		else:
+			assert out.shape == outshape
+
+		if axis == tensor.ndim - 1:
+			z, h, w, rows = 1, prod(tensor.shape[:-1]), tensor.shape[-1], 1
+		else:
+			z, h, w, rows = prod(tensor.shape[:axis]), tensor.shape[axis], prod(tensor.shape[axis + 1:]), 0
+
+		check(lib.pz_matsum(dtypeCode(tensor.dtype), out.ptr, tensor.ptr, z, h, w, rows, alpha, beta, None))
+		return out
+
+	def argminmax(self, tensor, axis, mode, allocator=None):
+		assert 0 <= axis < tensor.ndim
+		idx = GPUArray(tensor.shape[:axis] + tensor.shape[axis + 1:], _i32, allocator=allocator)
+		z, h, w = prod(tensor.shape[:axis]), tensor.shape[axis], prod(tensor.shape[axis + 1:])
+		check(lib.pz_argminmax(dtypeCode(tensor.dtype), idx.ptr, tensor.ptr, z, h, w, 1 if mode == "max" else 0, None))
+		return idx
+
+	def argmax(self, tensor, axis=0, allocator=None):
+		return self.argminmax(tensor, axis, "max", allocator)
+
+	def argmin(self, tensor, axis=0, allocator=None):
+		return self.argminmax(tensor, axis, "min", allocator)
+
+
+# ============================================================================================================ poolmod
+class PoolModule:
+	"""reference: Cuda/Kernels/Pool.py:115-213 (bit-exact int32 argmax masks)"""
+
+	def __init__(self, backend):
+		self.backend = backend
+
+	def maxpool2d(self, data, size, stride, pad, allocator=None):
+		assert data.dtype == _f32
+		batchsize, maps, inh, inw = data.shape
+		(fh, fw), (hstride, wstride), (hpad, wpad) = size, stride, pad
+
+		outh = (inh - fh + 2 * hpad) // hstride + 1
+		outw = (inw - fw + 2 * wpad) // wstride + 1
+
+		outdata = GPUArray((batchsize, maps, outh, outw), _f32, allocator=allocator)
+		mask = GPUArray((batchsize, maps, outh, outw), _i32, allocator=allocator)
+
+		check(lib.pz_maxpool2d_mask_fwd(data.ptr, outdata.ptr, mask.ptr, batchsize * maps, inh, inw, outh, outw, fh, fw,
+										hstride, wstride, hpad, wpad, None))
+		return outdata, mask
+
+	def maxpool2dBackward(self, grad, origshape, mask, size, stride, pad, allocator=None):
+		assert grad.dtype == _f32 and mask.dtype == _i32
+		batchsize, maps, outh, outw = grad.shape
+		(fh, fw), (hstride, wstride), (hpad, wpad) = size, stride, pad
+		inh, inw = origshape[2], origshape[3]
+
+		ingrad = GPUArray((batchsize, maps, inh, inw), _f32, allocator=allocator)
+		check(lib.pz_maxpool2d_mask_bwd(grad.ptr, mask.ptr, ingrad.ptr, batchsize * maps, inh, inw, outh, outw, fh, fw,
+										hstride, wstride, hpad, wpad, None))
+		return ingrad
+
+	def maxunpool2d(self, data, origshape, mask, allocator=None):
+		assert data.dtype == _f32
+		batchsize, maps, inh, inw = data.shape
+		outh, outw = origshape[2], origshape[3]
+
+		outdata = GPUArray.zeros((batchsize, maps, outh, outw), _f32, allocator=allocator)
+		check(lib.pz_maxunpool2d_fwd(data.ptr, mask.ptr, outdata.ptr, batchsize * maps, inh * inw, outh * outw, None))
+		return outdata
+
+	def maxunpool2dBackward(self, grad, poolshape, mask, allocator=None):
+		assert grad.dtype == _f32 and mask.dtype == _i32
+		batchsize, maps, outh, outw = grad.shape
+		inh, inw = poolshape[2], poolshape[3]
+
+		ingrad = GPUArray((batchsize, maps, inh, inw), _f32, allocator=allocator)
+		check(lib.pz_maxunpool2d_bwd(grad.ptr, mask.ptr, ingrad.ptr, batchsize * maps, inh * inw, outh * outw, None))
+		return ingrad
+
+
+# ============================================================================================================ SharedArray
+class SharedArray:
+	"""One flat buffer with 16-byte aligned named views (reference: Cuda/Utils.py:19-64); the per-dtype flat
+	parameter / gradient buffers of Optimizer.setupGlobalState and the payload of the DP all-reduce."""
+	alignment = 16
+
+	def __init__(self, dtype=np.float32, allocator=None):
+		self.ary = None
+		self.blocks = OrderedDict()
+		self.dtype = np.dtype(dtype)
+		self.allocator = allocator
+
+	def register(self, shape, dtype, name):
+		assert name not in self.blocks
+		assert dtype == self.dtype
+		self.blocks[name] = (shape, prod(shape) * self.dtype.itemsize)
+
+	def build(self):
+		totalbytes = sum(self.align(nbytes) for _, nbytes in self.blocks.values())
+		self.ary = GPUArray((totalbytes // self.dtype.itemsize, ), self.dtype, allocator=self.allocator)
+
+		blocks, offset = OrderedDict(), 0
+		for name, (shape, nbytes) in self.blocks.items():
+			blocks[name] = GPUArray(shape, self.dtype, gpudata=self.ary.gpudata[offset:offset + nbytes])
+			offset += self.align(nbytes)
+		self.blocks = blocks
+
+	def __getitem__(self, item):
+		return self.blocks[item]
+
+	@classmethod
+	def align(cls, nbytes):
+		return (nbytes + cls.alignment - 1) // cls.alignment * cls.alignment
+
+
+class QueueManager:
+	"""Borrow / give pool of streams or events (reference: Cuda/Utils.py:67-94)."""
+
+	def __init__(self, objtype):
+		self.objtype = objtype
+		self.items = []
+
+	def reserve(self, nitems):
+		self.items.extend(self.objtype() for _ in range(nitems))
+
+	def borrow(self, nitems):
+		if len(self.items) < nitems:
+			self.reserve(nitems - len(self.items))
+		borrowed, self.items = self.items[:nitems], self.items[nitems:]
+		return borrowed
+
+	def give(self, items):
+		self.items.extend(items)
+
+	def clear(self):
+		self.items = []
+
+
+# ============================================================================================================ kernels
+_ACT_KINDS = {"sigmoid": 0, "tanh": 1, "relu": 2, "leakyRelu": 3, "elu": 4, "softPlus": 5, "clip": 6, "gelu": 7}
+
+
+def _noSlice(kwargs):
+	if kwargs.get("slice") is not None:
+		raise NotImplementedError("strided `slice=` elementwise launches are not implemented in the B200 backend")
+
+
+def _actFactory(kind, nscalars):
+	code = _ACT_KINDS[kind]
+
+	def factory(dtype):
+		dt = dtypeCode(dtype)
+
+		def fwd(out, inp, *scalars, **kwargs):
+			_noSlice(kwargs)
+			a = float(scalars[0]) if nscalars > 0 else 0.0
+			b = float(scalars[1]) if nscalars > 1 else 0.0
+			check(lib.pz_act_fwd(code, dt, out.ptr, inp.ptr, out.size, a, b, None))
+
+		return fwd
+
+	def derFactory(dtype):
+		dt = dtypeCode(dtype)
+
+		def bwd(ingrad, outgrad, ref, *scalars, **kwargs):
+			_noSlice(kwargs)
+			a = float(scalars[0]) if nscalars > 0 else 0.0
+			b = float(scalars[1]) if nscalars > 1 else 0.0
+			check(lib.pz_act_bwd(code, dt, ingrad.ptr, outgrad.ptr, ref.ptr, ingrad.size, a, b, None))
+
+		return bwd
+
+	return factory, derFactory
+
+
+class ConvPerf:
+	def __init__(self, algo, tm, memory):
+		self.algo, self.time, self.memory = algo, tm, memory
+		self.determinism = True
+
+	def __repr__(self):
+		return "Algo %s time %.6f secs memory %.6f mbytes" % (self.algo, self.time, self.memory / 1024 ** 2)
+
+
+# ============================================================================================================ backend
+class B200Backend:
+	BackendName = "B200"
+	warpSize, nthreads = 32, 1024
+
+	GPUArray = GPUArray
+	Driver = driver
+	SharedArray = SharedArray
+
+	class GroupFormat(Enum):
+		gbp = 0
+		bgp = 1
+
+	class ConvFwdAlgo(Enum):
+		implicitGemm = 0
+		implicitPrecompGemm = 1
+		gemm = 2
+		direct = 3
+		fft = 4
+		fftTiling = 5
+		winograd = 6
+		winogradNonfused = 7
+
+	class ConvBwdDataAlgo(Enum):
+		algo0 = 0
+		algo1 = 1
+		fft = 2
+		fftTiling = 3
+		winograd = 4
+		winogradNonfused = 5
+
+	class ConvBwdFilterAlgo(Enum):
+		algo0 = 0
+		algo1 = 1
+		fft = 2
+		algo3 = 3
+		winograd = 4
+		winogradNonfused = 5
+		fftTiling = 6
+
+	class PoolMode(Enum):
+		max = 0
+		avgWithPad = 1
+		avgNoPad = 2
+		maxDeterminism = 3
+
+	class SoftMaxMode(Enum):
+		perActivation = 0
+		spatial = 1
+
+	class BatchNormMode(Enum):
+		perActivation = 0
+		spatial = 1
+		spatialPersistent = 2
+
+	def __init__(self, deviceIdx, initmode=0, logger=None):
+		self.deviceIdx = deviceIdx
+		self.logger = logger
+
+		ndevices = driver.Device.count()
+		if ndevices == 0:
+			raise driver.CudaError("no CUDA device is visible")
+
+		self.device = driver.Device(deviceIdx % ndevices).set()
+		major, minor = self.device.computeCapability()
+		if major != 10:
+			raise driver.CudaError(
+				"libpzb200 holds sm_100a code only; device %s is sm_%d%d" % (self.device.name(), major, minor)
+			)
+
+		if logger is not None:
+			logger.debug("Using device #%s (%s), %d SMs", deviceIdx, self.device.name(), driver.Device.smCount())
+
+		self.memoryPool = driver.MemoryPool()
+		self.streamManager = QueueManager(driver.Stream)
+		self.eventManager = QueueManager(driver.Event)
+		self.globalRng = None
+
+		self.initmode = 0
+		self.blas, self.dnn = None, None
+		self.matmod, self.poolmod = None, None
+		self.updateBackend(initmode)
+
+	def updateBackend(self, initmode):
+		if initmode >= 1 and self.dnn is None:
+			self.blas, self.dnn = BlasContext(self), DnnContext(self)
+		if initmode >= 2 and self.matmod is None:
+			self.matmod, self.poolmod = MatModule(self), PoolModule(self)
+		self.initmode = max(self.initmode, initmode)
+
+	# ---- kernel factories (reference attribute names: Cuda/GPUBackend.py:85-131)
+	sigmoidKer, sigmoidDerKer = (staticmethod(f) for f in _actFactory("sigmoid", 0))
+	tanhKer, tanhDerKer = (staticmethod(f) for f in _actFactory("tanh", 0))
+	reluKer, reluDerKer = (staticmethod(f) for f in _actFactory("relu", 0))
+	leakyReluKer, leakyReluDerKer = (staticmethod(f) for f in _actFactory("leakyRelu", 1))
+	eluKer, eluDerKer = (staticmethod(f) for f in _actFactory("elu", 1))
+	softPlusKer, softPlusDerKer = (staticmethod(f) for f in _actFactory("softPlus", 0))
+	clipKer, clipDerKer = (staticmethod(f) for f in _actFactory("clip", 2))
+	geluKer, geluDerKer = (staticmethod(f) for f in _actFactory("gelu", 0))
+
+	@staticmethod
+	def toVectorAddVectorKer(dtype):
+		dt = dtypeCode(dtype)
+
+		def ker(y, x, alpha, **kwargs):
+			_noSlice(kwargs)
+			check(lib.pz_axpy(dt, y.ptr, x.ptr, float(alpha), y.size, None))
+
+		return ker
+
+	@staticmethod
+	def addKer(dtype):
+		dt = dtypeCode(dtype)
+
+		def ker(out, x, alpha, y, beta, **kwargs):
+			_noSlice(kwargs)
+			check(lib.pz_axpby(dt, out.ptr, x.ptr, float(alpha), y.ptr, float(beta), out.size, None))
+
+		return ker
+
+	@staticmethod
+	def mulKer(dtype):
+		dt = dtypeCode(dtype)
+
+		def ker(out, a, b, **kwargs):
+			_noSlice(kwargs)
+			check(lib.pz_mul(dt, out.ptr, a.ptr, b.ptr, out.size, None))
+
+		return ker
+
+	@staticmethod
+	def linearKer(dtype):
+		dt = dtypeCode(dtype)
+
+		def ker(out, inp, a, b, **kwargs):
+			_noSlice(kwargs)
+			check(lib.pz_scale_shift(dt, out.ptr, inp.ptr, float(a), float(b), out.size, None))
+
+		return ker
+
+	@staticmethod
+	def classicMomSGDKer(dtype):
+		dt = dtypeCode(dtype)
+
+		def ker(param, grad, mom, learnRate, momRate, **kwargs):
+			check(lib.pz_sgd_momentum(dt, param.ptr, grad.ptr, mom.ptr, float(learnRate), float(momRate), param.size, None))
+
+		return ker
+
+	@staticmethod
+	def add2Ker(dtype):
+		"""out = a + b in one pass: the value Add.updateData / Replicate.updateGrad build with fill(0) + 2 axpy
+		(reference Modules/Add.py:15-23), 3 tensor passes instead of 5"""
+		dt = dtypeCode(dtype)
+
+		def ker(out, a, b):
+			check(lib.pz_add2(dt, out.ptr, a.ptr, b.ptr, out.size, None))
+
+		return ker
+
+	# ---- misc surface used by Backend/gpuarray.py
+	@staticmethod
+	def dtypesSupported():
+		supported = [(np.float32, 1e-5), (np.float16, 1e-2)]
+		if driver.bfloat16 is not None:
+			supported.append((driver.bfloat16, 5e-2))
+		return supported
+
+	@staticmethod
+	def copy(dest, source, allocator=None):
+		if dest is None:
+			return source.copy(allocator=allocator)
+		dest.set(source)
+		return dest
+
+	def concatenate(self, tup, axis, out=None, allocator=None):
+		ary = tup[0]
+		reduced = ary.shape[:axis] + ary.shape[axis + 1:]
+		assert all(a.dtype == ary.dtype and a.shape[:axis] + a.shape[axis + 1:] == reduced for a in tup[1:])
+
+		shape = ary.shape[:axis] + (sum(a.shape[axis] for a in tup), ) + ary.shape[axis + 1:]
+		if out is None:
+			out = GPUArray(shape, ary.dtype, allocator=allocator)
+		else:
+			assert out.shape == shape and out.dtype == ary.dtype
+
+		dstPitch = out.strides[axis - 1] if axis > 0 else out.nbytes
+		height, offset = prod(shape[:axis]), 0
+
+		for a in tup:
+			width = a.strides[axis - 1] if axis > 0 else a.nbytes
+			check(lib.pz_memcpy2d(out.ptr + offset, dstPitch, a.ptr, width, width, height, 0, None))
+			offset += width
+		return out
+
+	def split(self, ary, sections, axis, allocator=None):
+		assert sum(sections) == ary.shape[axis]
+		outs = [GPUArray(ary.shape[:axis] + (sec, ) + ary.shape[axis + 1:], ary.dtype, allocator=allocator) for sec in sections]
+
+		srcPitch = ary.strides[axis - 1] if axis > 0 else ary.nbytes
+		height, offset = prod(ary.shape[:axis]), 0
+
+		for out in outs:
+			width = out.strides[axis - 1] if axis > 0 else out.nbytes
+			check(lib.pz_memcpy2d(out.ptr, width, ary.ptr + offset, srcPitch, width, height, 0, None))
+			offset += width
+		return outs
+
+	def tile(self, ary, times, axis, allocator=None):
+		return self.concatenate([ary] * times, axis, allocator=allocator)
+
+	def timeKernel(self, func, args, kwargs=None, looplength=1000, log=True, logname=None, normalize=False, hotpass=True):
+		"""CUDA-event timing of a python-side launch loop (reference: Cuda/GPUBackend.py:332-368)"""
+		kwargs = {} if kwargs is None else kwargs
+		if hotpass:
+			func(*args, **kwargs)
+
+		start, end = driver.Event(), driver.Event()
+		start.record()
+		for _ in range(looplength):
+			func(*args, **kwargs)
+		end.record()
+		end.synchronize()
+
+		secs = start.timeTill(end) * 1e-3
+		if normalize:
+			secs /= looplength
+		if log and self.logger is not None:
+			self.logger.info("%s time: %s secs", logname or func.__name__, secs)
+		return secs
+
+	def convNdbenchmark(self, datashape, Wshape, dtype, stride=1, pad=0, dilation=1, groups=1, algoCount=10):
+		"""One implementation per pass, so each list holds one timed entry (reference: GPUBackend.py:371-378)."""
+		stride, pad, dilation = _seq(stride, 2, 1, "stride"), _seq(pad, 2, 0, "pad"), _seq(dilation, 2, 1, "dilation")
+		data, W = GPUArray.zeros(datashape, dtype, allocator=self.memoryPool), GPUArray.zeros(Wshape, dtype, allocator=self.memoryPool)
+		out = self.dnn.convNd(data, W, None, stride, pad, dilation, groups, allocator=self.memoryPool)
+		wgrad = GPUArray.zeros(Wshape, dtype, allocator=self.memoryPool)
+
+		def bench(fn):
+			return self.timeKernel(fn, (), looplength=5, log=False, normalize=True)
+
+		fwd = bench(lambda: self.dnn.convNd(data, W, None, stride, pad, dilation, groups, out=out))
+		bwdData = bench(lambda: self.dnn.convNdBackwardData(out, W, None, data, stride, pad, dilation, None, groups,
+															allocator=self.memoryPool))
+		bwdParam = bench(lambda: self.dnn.convNdBackwardParams(data, out, W, stride, pad, dilation, groups, wgrad=wgrad))
+		return [ConvPerf(0, fwd, 0)], [ConvPerf(0, bwdData, 0)], [ConvPerf(0, bwdParam, 0)]
+
+	def instanceNorm2d(self, data, scale, bias, epsilon, allocator=None):
+		"""BN over a (1, N*C, H, W) view with the affine parameters tiled N times (reference: GPUBackend.py:381-398)"""
+		batchsize, maps, height, width = data.shape
+		extmaps = batchsize * maps
+
+		indata = data.reshape(1, extmaps, height, width)
+		mean, var = GPUArray.zeros((extmaps, ), _f32, allocator=allocator), GPUArray.zeros((extmaps, ), _f32, allocator=allocator)
+
+		if batchsize > 1:
+			scale, bias = self.tile(scale, batchsize, axis=0, allocator=allocator), self.tile(bias, batchsize, axis=0, allocator=allocator)
+
+		outdata, savemean, saveinvvar = self.dnn.batchNormNd(indata, mean, var, scale, bias, epsilon, 1.0, False, 1,
+															 allocator=allocator)
+		return outdata.reshape(data.shape), savemean, saveinvvar, scale
+
+	def instanceNorm2dBackward(self, grad, data, extscale, savemean, saveinvvar, epsilon, affine, allocator=None):
+		"""reference: GPUBackend.py:401-416"""
+		batchsize, maps, height, width = grad.shape
+		extmaps = batchsize * maps
+
+		outgrad, scalegrad, biasgrad = self.dnn.batchNormNdBackward(
+			grad.reshape(1, extmaps, height, width), data.reshape(1, extmaps, height, width), extscale, savemean, saveinvvar,
+			epsilon, 1, allocator=allocator
+		)
+		outgrad = outgrad.reshape(grad.shape)
+
+		if not affine:
+			return outgrad
+
+		if batchsize > 1:
+			scalegrad = self.matmod.matsum(scalegrad.reshape(batchsize, -1), axis=0, allocator=allocator)
+			biasgrad = self.matmod.matsum(biasgrad.reshape(batchsize, -1), axis=0, allocator=allocator)
+		return outgrad, scalegrad, biasgrad
+
+
+_backends = {}
+
+
+def getDeviceCount():
+	return driver.Device.count()
+
+
+def getBackend(deviceIdx=0, initmode=0, logger=None):
+	"""reference: Cuda/Backend.py:360-370 -- one cached backend object per device, upgraded in place by initmode"""
+	bnd = _backends.get(deviceIdx)
+	if bnd is None:
+		bnd = B200Backend(deviceIdx, initmode, logger)
+		_backends[deviceIdx] = bnd
+	else:
+		bnd.updateBackend(initmode)
+	return bnd

@@ -48,6 +48,26 @@ static inline cudaStream_t pz_stream(void* s) { return (cudaStream_t)s; }
 int pz_num_sms();
 void pz_count_launch(int n);
 
+// ---- optional per-launch profiling (bench.py roofline): CUDA events around the launches of one kernel family
+enum { PZ_PROF_GEMM = 0, PZ_PROF_BN_FWD = 1, PZ_PROF_BN_BWD = 2, PZ_PROF_ELTWISE = 3, PZ_PROF_POOL = 4, PZ_PROF_OTHER = 5,
+	   PZ_PROF_FAMILIES = 6 };
+bool pz_prof_on();
+void pz_prof_begin(int family, cudaStream_t stream, double flops, double bytes);
+void pz_prof_end(cudaStream_t stream);
+
+struct PzProfScope {
+	cudaStream_t stream;
+	bool on;
+	PzProfScope(int family, cudaStream_t s, double flops, double bytes) : stream(s), on(pz_prof_on())
+	{
+		if (on) pz_prof_begin(family, s, flops, bytes);
+	}
+	~PzProfScope()
+	{
+		if (on) pz_prof_end(stream);
+	}
+};
+
 static inline int64_t pz_cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 static inline size_t pz_dtype_size(int dtype)

@@ -63,6 +63,14 @@ void set_splits(GemmParams& p, long long tiles, int min_kb_per_split)
 	p.splits = (int)pz_cdiv(p.kblocks, p.kb_per_split);
 }
 
+// algorithmic work of one conv pass: 2*MACs; every operand read once + the result written once
+void set_alg(GemmParams& p, const Geo& g)
+{
+	const double x = (double)g.N * g.C * g.H * g.W, y = (double)g.N * g.K * g.P * g.Q, w = (double)g.K * g.Cg * g.R * g.S;
+	p.alg_flops = 2.0 * y * g.Cg * g.R * g.S;
+	p.alg_bytes = 4.0 * (x + y + w);
+}
+
 // wt[g][c][ko][rs] = w[g*Kg + ko][c][rs] : the filter with the reduction index (ko, r, s) contiguous
 __global__ void repack_filter_dgrad(const float* __restrict__ w, float* __restrict__ wt, int Kg, int Cg, int RS, long long total)
 {
@@ -151,6 +159,7 @@ int pz_conv2d_fprop(int dtype, const pz_conv2d_desc* d, const void* x, const voi
 	p.kblocks = (int)pz_cdiv(A.kdim, BK);
 	p.splits = 1;
 	p.kb_per_split = p.kblocks;
+	set_alg(p, g);
 	const int amode = taps_in_bounds(g) ? MODE_MN_SIMPLE : MODE_MN_GENERAL;
 	return launch(p, pick_bn(g.Kg), amode, MODE_K_SIMPLE, false, g.G, pz_stream(stream));
 }
@@ -213,6 +222,7 @@ int pz_conv2d_dgrad(int dtype, const pz_conv2d_desc* d, const void* dy, const vo
 		E.M = g.N * PQ;
 		p.kblocks = (int)pz_cdiv(A.kdim, BK);
 		p.kb_per_split = p.kblocks;
+		set_alg(p, g);
 		return launch(p, pick_bn(g.Cg), MODE_MN_SIMPLE, MODE_MN_SIMPLE, false, g.G, pz_stream(stream));
 	}
 
@@ -245,6 +255,7 @@ int pz_conv2d_dgrad(int dtype, const pz_conv2d_desc* d, const void* dy, const vo
 	E.M = g.N * HW;
 	p.kblocks = (int)pz_cdiv(A.kdim, BK);
 	p.kb_per_split = p.kblocks;
+	set_alg(p, g);
 	return launch(p, pick_bn(g.Cg), MODE_MN_GENERAL, MODE_K_SIMPLE, strided, g.G, pz_stream(stream));
 }
 
@@ -302,6 +313,7 @@ int pz_conv2d_wgrad(int dtype, const pz_conv2d_desc* d, const void* x, const voi
 		st = prescale((float*)dw, (long long)g.K * g.Cg * RS, beta, stream);
 		if (st != PZ_OK) return st;
 	}
+	set_alg(p, g);
 	const int amode = taps_in_bounds(g) ? MODE_K_SIMPLE : MODE_K_GENERAL;
 	return launch(p, bn, amode, MODE_K_SIMPLE, false, g.G, pz_stream(stream));
 }

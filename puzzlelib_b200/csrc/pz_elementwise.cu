@@ -123,6 +123,7 @@ int ew_launch(void* io0, void* io1, const void* in0, const void* in1, const void
 	if (blocks > maxblocks) blocks = maxblocks;
 	if (blocks < 1) blocks = 1;
 
+	PzProfScope prof(PZ_PROF_ELTWISE, pz_stream(stream), 0.0, (double)n * sizeof(T) * (NIN + NIO * (READ_IO ? 2 : 1)));
 	ew_kernel<T, NIO, NIN, READ_IO, Op><<<(unsigned)blocks, kThreads, 0, pz_stream(stream)>>>(
 		(T*)io0, (T*)io1, (const T*)in0, (const T*)in1, (const T*)in2, n, head, nvec, op);
 	pz_count_launch(1);

@@ -53,7 +53,10 @@ static int launch_inst(const GemmParams& p, dim3 grid, cudaStream_t stream)
 		PZ_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES));
 		configured = true;
 	}
-	kern<<<grid, NTHREADS, Cfg<BN>::SMEM_BYTES, stream>>>(p);
+	{
+		PzProfScope prof(PZ_PROF_GEMM, stream, p.alg_flops, p.alg_bytes);
+		kern<<<grid, NTHREADS, Cfg<BN>::SMEM_BYTES, stream>>>(p);
+	}
 	pz_count_launch(1);
 	PZ_LAUNCH_CHECK();
 	return PZ_OK;
@@ -125,6 +128,8 @@ extern "C" int pz_gemm(int dtype, const void* A, const void* B, void* C, int64_t
 	E.bias_group_stride = 0;
 
 	p.kblocks = (int)pz_cdiv(K, BK);
+	p.alg_flops = 2.0 * (double)M * (double)N * (double)K;
+	p.alg_bytes = 4.0 * ((double)M * K + (double)K * N + (double)M * N * (beta != 0.0f ? 2.0 : 1.0));
 	const int bn = pick_bn((int)M);
 	const long long tiles = pz_cdiv(N, BM) * pz_cdiv(M, bn);
 	int splits = 1;

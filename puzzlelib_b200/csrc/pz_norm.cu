@@ -347,6 +347,7 @@ int fwd_train(const void* x, void* y, int64_t N, int64_t C, int64_t S, const flo
 	const int cs = pick_cluster(N, C);
 	const int vec_ok = same_misalignment({x, y}) && ((uintptr_t)x % sizeof(T) == 0);
 	const int warp_planes = S < 2048;
+	PzProfScope prof(PZ_PROF_BN_FWD, pz_stream(stream), 0.0, 2.0 * (double)N * C * S * sizeof(T));
 	return launch_cluster(bn_fwd_train_kernel<T>, dim3((unsigned)cs, (unsigned)C), kThreads, cs, pz_stream(stream), (const T*)x,
 						  (T*)y, N, C, S, scale, bias, rm, rv, sm, siv, (float)eps, (float)factor, vec_ok, warp_planes);
 }
@@ -372,6 +373,7 @@ int bwd(const void* x, const void* dy, void* dx, int64_t N, int64_t C, int64_t S
 	const int cs = pick_cluster(N, C);
 	const int vec_ok = same_misalignment({x, dy, dx}) && ((uintptr_t)x % sizeof(T) == 0);
 	const int warp_planes = S < 2048;
+	PzProfScope prof(PZ_PROF_BN_BWD, pz_stream(stream), 0.0, 3.0 * (double)N * C * S * sizeof(T));
 	return launch_cluster(bn_bwd_kernel<T>, dim3((unsigned)cs, (unsigned)C), kThreads, cs, pz_stream(stream), (const T*)x,
 						  (const T*)dy, (T*)dx, N, C, S, scale, sm, siv, dscale, dbias, vec_ok, warp_planes);
 }

@@ -219,6 +219,7 @@ int fwd_dispatch(int mode, const void* x, void* y, int64_t planes, const PoolGeo
 	const int64_t total = planes * g.OH * g.OW;
 	const unsigned grid = grid_for(total);
 	cudaStream_t s = pz_stream(stream);
+	PzProfScope prof(PZ_PROF_POOL, s, 0.0, (double)sizeof(T) * planes * ((double)g.H * g.W + (double)g.OH * g.OW));
 	switch (mode) {
 		case PZ_POOL_MAX:
 		case PZ_POOL_MAX_DETERMINISM:
@@ -242,6 +243,7 @@ int bwd_dispatch(int mode, const void* x, const void* y, const void* dy, void* d
 	const int64_t total = planes * g.H * g.W;
 	const unsigned grid = grid_for(total);
 	cudaStream_t s = pz_stream(stream);
+	PzProfScope prof(PZ_PROF_POOL, s, 0.0, (double)sizeof(T) * planes * (2.0 * g.H * g.W + 2.0 * g.OH * g.OW));
 	switch (mode) {
 		case PZ_POOL_MAX:
 		case PZ_POOL_MAX_DETERMINISM:

@@ -34,6 +34,36 @@ int pz_num_sms()
 	return sms;
 }
 
+// ---------------------------------------------------------------------------------------- launch profiling
+namespace {
+struct ProfRecord { cudaEvent_t start, stop; int family; double flops, bytes; };
+std::vector<ProfRecord> g_prof;
+std::vector<cudaEvent_t> g_prof_free;
+bool g_prof_enabled = false;
+
+cudaEvent_t prof_event()
+{
+	if (!g_prof_free.empty()) { cudaEvent_t e = g_prof_free.back(); g_prof_free.pop_back(); return e; }
+	cudaEvent_t e;
+	cudaEventCreate(&e);
+	return e;
+}
+}  // namespace
+
+bool pz_prof_on() { return g_prof_enabled; }
+
+void pz_prof_begin(int family, cudaStream_t stream, double flops, double bytes)
+{
+	ProfRecord r{prof_event(), prof_event(), family, flops, bytes};
+	cudaEventRecord(r.start, stream);
+	g_prof.push_back(r);
+}
+
+void pz_prof_end(cudaStream_t stream)
+{
+	if (!g_prof.empty()) cudaEventRecord(g_prof.back().stop, stream);
+}
+
 template <typename T>
 __global__ void pz_fill_kernel(T* __restrict__ p, T v, size_t n)
 {
@@ -75,6 +105,32 @@ extern "C" {
 const char* pz_last_error(void) { return g_err; }
 int pz_version(void) { return 100; }
 uint64_t pz_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int pz_profile_enable(int on)
+{
+	g_prof_enabled = on != 0;
+	return PZ_OK;
+}
+
+// Sums the recorded launches of one family since the last call and clears them (synchronises the device).
+int pz_profile_collect(int family, double* total_ms, double* flops, double* bytes, uint64_t* launches)
+{
+	PZ_CHECK_CUDA(cudaDeviceSynchronize());
+	*total_ms = 0.0; *flops = 0.0; *bytes = 0.0; *launches = 0;
+	std::vector<ProfRecord> keep;
+	for (const ProfRecord& r : g_prof) {
+		if (r.family != family && family >= 0) { keep.push_back(r); continue; }
+		float ms = 0.0f;
+		if (cudaEventElapsedTime(&ms, r.start, r.stop) == cudaSuccess) {
+			*total_ms += ms; *flops += r.flops; *bytes += r.bytes; *launches += 1;
+		}
+		g_prof_free.push_back(r.start);
+		g_prof_free.push_back(r.stop);
+	}
+	g_prof.swap(keep);
+	cudaGetLastError();
+	return PZ_OK;
+}
 
 int pz_device_count(int* count) { PZ_CHECK_CUDA(cudaGetDeviceCount(count)); return PZ_OK; }
 int pz_device_set(int index) { PZ_CHECK_CUDA(cudaSetDevice(index)); return PZ_OK; }

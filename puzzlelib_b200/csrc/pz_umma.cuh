@@ -99,6 +99,7 @@ struct GemmParams {
 	int kblocks;                 // ceil(K / 32)
 	int splits;                  // split-K factor (grid.z = groups * splits)
 	int kb_per_split;
+	double alg_flops, alg_bytes; // host-side bookkeeping for the profiler (algorithmic work of this launch)
 };
 
 // ------------------------------------------------------------------------------------------ PTX helpers

@@ -101,6 +101,8 @@ _SIGNATURES = {
 	"pz_event_synchronize": [_P],
 	"pz_event_elapsed_ms": [_P, _P, POINTER(c_float)],
 	"pz_stream_wait_event": [_P, _P],
+	"pz_profile_enable": [c_int],
+	"pz_profile_collect": [c_int, POINTER(c_double), POINTER(c_double), POINTER(c_double), POINTER(c_uint64)],
 	"pz_act_fwd": [c_int, c_int, _P, _P, c_int64, c_float, c_float, _P],
 	"pz_act_bwd": [c_int, c_int, _P, _P, _P, c_int64, c_float, c_float, _P],
 	"pz_axpy": [c_int, _P, _P, c_float, c_int64, _P],
@@ -132,7 +134,9 @@ _SIGNATURES = {
 	"pz_conv2d_dgrad": [c_int, POINTER(Conv2dDesc), _P, _P, _P, _P, _P, c_size_t, _P],
 	"pz_conv2d_wgrad": [c_int, POINTER(Conv2dDesc), _P, _P, _P, c_float, c_float, _P],
 	"pz_bias_grad": [c_int, _P, _P, c_int64, c_int64, c_int64, c_float, c_float, _P],
+	"pz_nccl_version": [POINTER(c_int)],
 	"pz_nccl_unique_id": [_P],
+	"pz_mean_sgd_momentum": [c_int, _P, _P, _P, c_int64, c_float, c_float, c_float, _P],
 	"pz_nccl_comm_init": [POINTER(_P), c_int, c_int, _P],
 	"pz_nccl_comm_destroy": [_P],
 	"pz_nccl_allreduce_mean": [_P, c_int, _P, c_int64, c_float, _P],
@@ -257,6 +261,20 @@ def getMemoryInfo():
 
 def launchCount():
 	return int(lib.pz_launch_count())
+
+
+PROF_FAMILIES = {"gemm": 0, "bn_fwd": 1, "bn_bwd": 2, "eltwise": 3, "pool": 4, "other": 5}
+
+
+def profileEnable(on):
+	check(lib.pz_profile_enable(1 if on else 0))
+
+
+def profileCollect(family):
+	ms, flops, nbytes, launches = c_double(0), c_double(0), c_double(0), c_uint64(0)
+	check(lib.pz_profile_collect(PROF_FAMILIES[family] if isinstance(family, str) else family, byref(ms), byref(flops),
+								 byref(nbytes), byref(launches)))
+	return {"ms": ms.value, "flops": flops.value, "bytes": nbytes.value, "launches": launches.value}
 
 
 # --------------------------------------------------------------------------------------------------------- memory

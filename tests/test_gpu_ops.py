@@ -1,0 +1,469 @@
+"""GPU tier: every operator of the hot path, called through the backend object (i.e. through the C-ABI of
+libpzb200.so), against the CPU oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): bit-exact for max-pool argmax masks and index ops; fp32 tensors within 1e-3
+relative (the tcgen05 path computes fp32 storage as TF32 products with fp32 accumulation, like cuDNN/cuBLAS with
+TENSOR_OP_MATH on this GPU generation); elementwise / reduction kernels are held to the reference's own
+fp32 bar of 1e-5 (Cuda/GPUBackend.py:218-220).
+"""
+import numpy as np
+import pytest
+
+from oracle import ops
+
+pytestmark = pytest.mark.gpu
+
+REL_TC = 1e-3      # tensor-core (TF32) contractions
+ATOL32 = 1e-5      # fp32 CUDA-core kernels
+
+
+def relerr(got, want):
+	want = np.asarray(want, dtype=np.float64)
+	return float(np.abs(np.asarray(got, dtype=np.float64) - want).max() / (np.abs(want).max() + 1e-30))
+
+
+def G(bnd, ary):
+	return bnd.GPUArray.toGpu(np.ascontiguousarray(ary))
+
+
+# ================================================================================================ convolution
+CONV_CASES = [
+	# N, C, H, W, K, R, S, stride, pad, dil, groups, bias
+	(2, 8, 12, 12, 16, 1, 1, 1, 0, 1, 1, False),
+	(2, 8, 12, 12, 16, 3, 3, 1, 1, 1, 1, True),
+	(2, 3, 20, 20, 8, 7, 7, 2, 3, 1, 1, False),       # ResNet conv1 geometry
+	(2, 16, 11, 11, 32, 1, 1, 2, 0, 1, 1, False),     # strided 1x1 (first conv of a ResNet stage)
+	(3, 6, 9, 10, 4, 2, 3, 1, 0, 1, 2, True),         # groups, non-square
+	(2, 4, 13, 13, 6, 3, 3, 2, 1, 2, 1, False),       # dilation + stride
+	(1, 1, 28, 28, 16, 3, 3, 1, 0, 1, 1, True),       # LeNet conv1
+	(2, 16, 13, 13, 32, 4, 4, 1, 0, 1, 1, True),      # LeNet conv2
+	(4, 64, 14, 14, 64, 3, 3, 1, 1, 1, 1, False),
+	(2, 256, 7, 7, 512, 1, 1, 1, 0, 1, 1, False),
+	(1, 130, 5, 5, 200, 3, 3, 1, 1, 1, 1, True),      # ragged: nothing a multiple of the tile sizes
+	(2, 12, 9, 9, 12, 3, 3, 1, 1, 1, 4, False),       # 4 groups
+	(1, 5, 1, 40, 7, 1, 5, 1, (0, 2), 1, 1, True),    # 1-d conv geometry (H = 1)
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv2d_fwd_bwd(bnd, case):
+	N, C, H, W, K, R, S, stride, pad, dil, groups, bias = case
+	rng = np.random.RandomState(hash(case) % (2 ** 31))
+	x = rng.randn(N, C, H, W).astype(np.float32)
+	w = rng.randn(K, C // groups, R, S).astype(np.float32)
+	b = rng.randn(K).astype(np.float32) if bias else None
+
+	y = ops.conv2d(x, w, b, stride, pad, dil, groups)
+	dy = rng.randn(*y.shape).astype(np.float32)
+
+	dx_, dw_ = G(bnd, x), G(bnd, w)
+	out = bnd.dnn.convNd(dx_, dw_, G(bnd, b) if bias else None, stride, pad, dil, groups, allocator=bnd.memoryPool)
+	assert out.shape == y.shape
+	assert relerr(out.get(), y) < REL_TC
+
+	dgrad = bnd.dnn.convNdBackwardData(G(bnd, dy), dw_, None, dx_, stride, pad, dil, None, groups, allocator=bnd.memoryPool)
+	assert relerr(dgrad.get(), ops.conv2d_bwd_data(dy, w, x.shape, None, stride, pad, dil, 0, groups)) < REL_TC
+
+	w0 = rng.randn(*w.shape).astype(np.float32)
+	b0 = rng.randn(K).astype(np.float32)
+	wgrad, bgrad = G(bnd, w0), G(bnd, b0)
+	res = bnd.dnn.convNdBackwardParams(dx_, G(bnd, dy), dw_, stride, pad, dil, groups, bias, False, wgrad, bgrad if bias else None,
+									   0.5, 0.25, allocator=bnd.memoryPool)
+	want = ops.conv2d_bwd_params(x, dy, w.shape, stride, pad, dil, groups, True, False, w0, b0, 0.5, 0.25)
+	assert relerr(wgrad.get(), want[0]) < REL_TC
+	if bias:
+		assert res[1] is bgrad
+		assert relerr(bgrad.get(), want[1]) < 1e-5
+
+
+def test_conv2d_wgrad_overwrite_and_accumulate(bnd):
+	# Module.backward default momentum = 0 overwrites, Sequential.backward default momentum = 1 accumulates
+	rng = np.random.RandomState(11)
+	x, dy = rng.randn(8, 32, 28, 28).astype(np.float32), rng.randn(8, 48, 28, 28).astype(np.float32)
+	w = rng.randn(48, 32, 3, 3).astype(np.float32)
+	want = ops.conv2d_bwd_params(x, dy, w.shape, 1, 1)
+	wgrad = G(bnd, np.full(w.shape, np.nan, np.float32))
+	bnd.dnn.convNdBackwardParams(G(bnd, x), G(bnd, dy), G(bnd, w), 1, 1, 1, 1, False, False, wgrad, None, 1.0, 0.0)
+	assert relerr(wgrad.get(), want) < REL_TC          # NaNs in the old buffer must not leak at momentum = 0
+	bnd.dnn.convNdBackwardParams(G(bnd, x), G(bnd, dy), G(bnd, w), 1, 1, 1, 1, False, False, wgrad, None, 1.0, 1.0)
+	assert relerr(wgrad.get(), 2 * want) < REL_TC
+
+
+@pytest.mark.parametrize("case", [(2, 6, 5, 5, 4, 3, 2, 1, 1, 1), (2, 4, 6, 7, 6, 4, 2, 1, 0, 2), (1, 8, 4, 4, 8, 2, 2, 0, 0, 1)])
+def test_deconv2d(bnd, case):
+	# Deconv forward = conv backward-data + bias, incl. postpad (Backend/Dnn.py:211-231; CuDnn.c:269-284)
+	N, inmaps, H, W, outmaps, size, stride, pad, postpad, groups = case
+	rng = np.random.RandomState(7)
+	x = rng.randn(N, inmaps, H, W).astype(np.float32)
+	w = rng.randn(inmaps, outmaps // groups, size, size).astype(np.float32)
+	b = rng.randn(outmaps).astype(np.float32)
+
+	y = ops.conv2d_bwd_data(x, w, None, b, stride, pad, 1, postpad, groups)
+	out = bnd.dnn.convNdBackwardData(G(bnd, x), G(bnd, w), G(bnd, b), None, stride, pad, 1, postpad, groups, allocator=bnd.memoryPool)
+	assert out.shape == y.shape
+	assert relerr(out.get(), y) < REL_TC
+
+	g = rng.randn(*y.shape).astype(np.float32)
+	dx = bnd.dnn.convNd(G(bnd, g), G(bnd, w), None, stride, pad, 1, groups)
+	assert relerr(dx.get(), ops.conv2d(g, w, None, stride, pad, 1, groups)) < REL_TC
+
+	wgrad, bgrad = bnd.dnn.convNdBackwardParams(G(bnd, g), G(bnd, x), G(bnd, w), stride, pad, 1, groups, True, True)
+	want = ops.conv2d_bwd_params(g, x, w.shape, stride, pad, 1, groups, True, True)
+	assert relerr(wgrad.get(), want[0]) < REL_TC and relerr(bgrad.get(), want[1]) < 1e-5
+
+
+def test_conv2d_argument_errors(bnd):
+	x = bnd.GPUArray.zeros((2, 4, 8, 8), np.float32)
+	w = bnd.GPUArray.zeros((6, 3, 3, 3), np.float32)
+	with pytest.raises(ValueError, match="input maps"):
+		bnd.dnn.convNd(x, w)
+	w = bnd.GPUArray.zeros((6, 4, 3, 3), np.float32)
+	with pytest.raises(ValueError, match="output gpuarray"):
+		bnd.dnn.convNd(x, w, out=bnd.GPUArray.zeros((2, 6, 5, 5), np.float32))
+	with pytest.raises(ValueError):
+		bnd.dnn.convNd(x, w, stride=(1, 2, 3))
+	with pytest.raises(ValueError, match="map size"):
+		bnd.dnn.convNd(bnd.GPUArray.zeros((2, 4, 2, 2), np.float32), w)
+
+
+# ================================================================================================ GEMM
+GEMM_CASES = [(128, 128, 32, 0, 0), (64, 1000, 2048, 0, 0), (64, 2048, 1000, 0, 1), (2048, 1000, 64, 1, 0), (100, 200, 77, 0, 0),
+			  (300, 70, 129, 1, 0), (33, 17, 5, 0, 1), (1, 10, 1024, 0, 0), (64, 1024, 800, 0, 0), (128, 4096, 4096, 0, 0)]
+
+
+@pytest.mark.parametrize("case", GEMM_CASES)
+def test_gemm(bnd, case):
+	M, N, K, ta, tb = case
+	rng = np.random.RandomState(M * 31 + N)
+	A = rng.randn(*((K, M) if ta else (M, K))).astype(np.float32)
+	B = rng.randn(*((N, K) if tb else (K, N))).astype(np.float32)
+	C0 = rng.randn(M, N).astype(np.float32)
+
+	out = bnd.blas.gemm(G(bnd, A), G(bnd, B), None, bool(ta), bool(tb), allocator=bnd.memoryPool)
+	assert relerr(out.get(), ops.gemm(A, B, None, ta, tb)) < REL_TC
+
+	acc = G(bnd, C0)
+	res = bnd.blas.gemm(G(bnd, A), G(bnd, B), acc, bool(ta), bool(tb), 0.5, 0.75)
+	assert res is acc
+	assert relerr(acc.get(), ops.gemm(A, B, C0, ta, tb, 0.5, 0.75)) < REL_TC
+
+
+def test_gemm_bias_epilogue_and_errors(bnd):
+	rng = np.random.RandomState(3)
+	A, B, b = rng.randn(64, 800).astype(np.float32), rng.randn(800, 1024).astype(np.float32), rng.randn(1024).astype(np.float32)
+	out = bnd.blas.gemmBias(G(bnd, A), G(bnd, B), G(bnd, b))
+	assert relerr(out.get(), ops.gemm(A, B) + b) < REL_TC
+	with pytest.raises(ValueError):
+		bnd.blas.gemm(G(bnd, A), G(bnd, A))
+	with pytest.raises(ValueError):
+		bnd.blas.gemm(G(bnd, A), G(bnd, B), transpA=True, transpB=True)
+
+
+# ================================================================================================ batch norm
+@pytest.mark.parametrize("shape", [(4, 5, 2, 3), (16, 64, 14, 14), (8, 3, 33, 35), (2, 7, 1, 1), (32, 256, 7, 7), (3, 2, 112, 112)])
+def test_batchnorm_train_bwd_infer(bnd, shape):
+	rng = np.random.RandomState(sum(shape))
+	N, C = shape[:2]
+	x = (rng.randn(*shape) * 2 + 0.5).astype(np.float32)
+	scale, bias = rng.randn(C).astype(np.float32), rng.randn(C).astype(np.float32)
+	mean0, var0 = rng.randn(C).astype(np.float32), (1 + rng.randn(C) ** 2).astype(np.float32)
+	factor = 0.3
+
+	y, mu, inv, newmean, newvar = ops.batchnorm_train(x, scale, bias, mean0, var0, 1e-5, factor)
+	mean, var = G(bnd, mean0), G(bnd, var0)
+	out, savemean, saveinvvar = bnd.dnn.batchNormNd(G(bnd, x), mean, var, G(bnd, scale), G(bnd, bias), 1e-5, factor, False,
+													allocator=bnd.memoryPool)
+	assert np.allclose(out.get(), y, atol=2e-5, rtol=1e-5)
+	assert np.allclose(savemean.get(), mu, atol=ATOL32) and np.allclose(saveinvvar.get(), inv, rtol=1e-5, atol=ATOL32)
+	assert np.allclose(mean.get(), newmean, atol=ATOL32)
+	assert np.allclose(var.get(), newvar, rtol=1e-5, atol=ATOL32)      # unbiased running variance (cuDNN), see oracle
+
+	dy = rng.randn(*shape).astype(np.float32)
+	dx, dscale, dbias = ops.batchnorm_bwd(x, dy, scale, mu, inv)
+	ingrad, scalegrad, bgrad = bnd.dnn.batchNormNdBackward(G(bnd, dy), G(bnd, x), G(bnd, scale), savemean, saveinvvar, 1e-5,
+														   allocator=bnd.memoryPool)
+	assert relerr(ingrad.get(), dx) < 1e-5
+	assert relerr(scalegrad.get(), dscale) < 1e-5 and relerr(bgrad.get(), dbias) < 1e-5
+
+	data = G(bnd, x)
+	res = bnd.dnn.batchNormNd(data, G(bnd, mean0), G(bnd, var0), G(bnd, scale), G(bnd, bias), 1e-5, 0, True, out=data)
+	assert res is data                                                   # in-place inference (BatchNormND inplace flag)
+	assert np.allclose(data.get(), ops.batchnorm_infer(x, scale, bias, mean0, var0), atol=2e-5, rtol=1e-5)
+
+
+def test_batchnorm_large_mean_is_stable(bnd):
+	# variance of data with mean >> std: a naive E[x^2] - E[x]^2 in fp32 loses all digits here
+	rng = np.random.RandomState(9)
+	x = (1000.0 + rng.randn(32, 4, 20, 20)).astype(np.float32)
+	one, zero = np.ones(4, np.float32), np.zeros(4, np.float32)
+	_, mu, inv, _, _ = ops.batchnorm_train(x, one, zero, zero, one)
+	_, savemean, saveinvvar = bnd.dnn.batchNormNd(G(bnd, x), G(bnd, zero), G(bnd, one), G(bnd, one), G(bnd, zero))
+	assert np.allclose(savemean.get(), mu, rtol=1e-6)
+	assert np.allclose(saveinvvar.get(), inv, rtol=2e-3)
+
+
+def test_instancenorm(bnd):
+	rng = np.random.RandomState(5)
+	x = rng.randn(3, 4, 6, 5).astype(np.float32)
+	scale, bias = rng.randn(4).astype(np.float32), rng.randn(4).astype(np.float32)
+	out, savemean, saveinvvar, extscale = bnd.instanceNorm2d(G(bnd, x), G(bnd, scale), G(bnd, bias), 1e-5)
+	mu, var = x.mean(axis=(2, 3), keepdims=True), x.var(axis=(2, 3), keepdims=True)
+	want = (x - mu) / np.sqrt(var + 1e-5) * scale.reshape(1, 4, 1, 1) + bias.reshape(1, 4, 1, 1)
+	assert np.allclose(out.get(), want, atol=2e-5)
+	g = rng.randn(*x.shape).astype(np.float32)
+	ingrad, scalegrad, biasgrad = bnd.instanceNorm2dBackward(G(bnd, g), G(bnd, x), extscale, savemean, saveinvvar, 1e-5, True)
+	xhat = (x - mu) / np.sqrt(var + 1e-5)
+	assert np.allclose(biasgrad.get(), g.sum(axis=(0, 2, 3)), atol=1e-4)
+	assert np.allclose(scalegrad.get(), (g * xhat).sum(axis=(0, 2, 3)), atol=1e-4)
+
+
+# ================================================================================================ pooling
+POOL_CASES = [(2, 3, 8, 8, 2, 2, 0), (2, 2, 9, 9, 3, 2, 0), (3, 2, 6, 6, 3, 2, 1), (2, 4, 112, 112, 3, 2, 0), (2, 5, 7, 7, 7, 1, 0),
+			  (1, 2, 10, 13, (2, 3), (2, 1), (1, 1)), (2, 3, 5, 5, 3, 1, 1)]
+
+
+@pytest.mark.parametrize("case", POOL_CASES)
+@pytest.mark.parametrize("mode", ["max", "avgWithPad", "avgNoPad"])
+def test_pool2d(bnd, case, mode):
+	N, C, H, W, size, stride, pad = case
+	rng = np.random.RandomState(H * 7 + W)
+	x = rng.randn(N, C, H, W).astype(np.float32)
+	code = {"max": bnd.PoolMode.max, "avgWithPad": bnd.PoolMode.avgWithPad, "avgNoPad": bnd.PoolMode.avgNoPad}[mode].value
+
+	y = ops.pool2d(x, size, stride, pad, mode)
+	out = bnd.dnn.poolNd(G(bnd, x), size, stride, pad, code, allocator=bnd.memoryPool)
+	assert out.shape == y.shape
+	if mode == "max":
+		assert np.array_equal(out.get(), y.astype(np.float32))
+	else:
+		assert np.allclose(out.get(), y, atol=ATOL32)
+
+	dy = rng.randn(*y.shape).astype(np.float32)
+	dx = bnd.dnn.poolNdBackward(G(bnd, dy), G(bnd, x), out, size, stride, pad, code, allocator=bnd.memoryPool)
+	assert np.allclose(dx.get(), ops.pool2d_bwd(x, out.get(), dy, size, stride, pad, mode), atol=ATOL32)
+
+
+def test_pool2d_max_backward_ties_go_to_the_first_maximum(bnd):
+	# post-ReLU windows full of zeros: route like the mask kernel does (first maximum), deterministically
+	x = np.zeros((1, 2, 6, 6), np.float32)
+	x[0, 1, 2, 2] = x[0, 1, 2, 3] = 3.0
+	dy = np.arange(1, 19, dtype=np.float32).reshape(1, 2, 3, 3)
+	out = bnd.dnn.poolNd(G(bnd, x), 2, 2, 0, 0)
+	dx = bnd.dnn.poolNdBackward(G(bnd, dy), G(bnd, x), out, 2, 2, 0, 0).get()
+	assert np.array_equal(dx, ops.pool2d_bwd(x, out.get(), dy, 2, 2, 0, "max").astype(np.float32))
+	assert dx[0, 0, 0, 0] == 1.0 and dx[0, 0, 0, 1] == 0.0 and dx[0, 1, 2, 2] == 14.0 and dx[0, 1, 2, 3] == 0.0
+
+
+@pytest.mark.parametrize("case", POOL_CASES)
+def test_maxpool2d_mask_is_bit_exact(bnd, case):
+	N, C, H, W, size, stride, pad = case
+	size, stride, pad = ops._pair(size), ops._pair(stride), ops._pair(pad)
+	rng = np.random.RandomState(H + W)
+	x = rng.randn(N, C, H, W).astype(np.float32)
+	x[rng.rand(*x.shape) < 0.4] = 0.0                 # many exact ties, as after a ReLU
+	x = np.maximum(x, 0.0)
+
+	y, mask = ops.maxpool2d_mask(x, size, stride, pad)
+	out, gmask = bnd.poolmod.maxpool2d(G(bnd, x), size, stride, pad, allocator=bnd.memoryPool)
+	assert gmask.dtype == np.int32
+	assert (mask == gmask.get()).all()                # the reference's own assertion, Cuda/Kernels/Pool.py:263
+	assert np.array_equal(out.get(), y)
+
+	dy = rng.randn(*y.shape).astype(np.float32)
+	dx = bnd.poolmod.maxpool2dBackward(G(bnd, dy), x.shape, gmask, size, stride, pad, allocator=bnd.memoryPool)
+	assert np.array_equal(dx.get(), ops.maxpool2d_mask_bwd(dy, x.shape, mask, size, stride, pad))
+
+	if stride[0] >= size[0] and stride[1] >= size[1] and pad == (0, 0):              # unpool needs non-overlapping windows to be a function
+		up = bnd.poolmod.maxunpool2d(out, x.shape, gmask)
+		assert np.array_equal(up.get(), ops.maxunpool2d(y, x.shape, mask))
+		back = bnd.poolmod.maxunpool2dBackward(up, y.shape, gmask)
+		assert np.array_equal(back.get(), y)
+
+
+# ================================================================================================ softmax
+@pytest.mark.parametrize("shape", [(5, 8, 2, 3), (64, 1000, 1, 1), (3, 1500, 1, 1), (7, 10, 1, 1), (2, 21, 17, 9), (1, 1, 1, 1)])
+def test_softmax(bnd, shape):
+	rng = np.random.RandomState(shape[1])
+	x = (rng.randn(*shape) * 3).astype(np.float32)
+	y = ops.softmax(x)
+	out = bnd.dnn.softmaxNd(G(bnd, x), bnd.SoftMaxMode.spatial.value, allocator=bnd.memoryPool)
+	assert np.allclose(out.get(), y, atol=1e-6, rtol=1e-5)
+	dy = rng.randn(*shape).astype(np.float32)
+	dx = bnd.dnn.softmaxNdBackward(G(bnd, dy), out, allocator=bnd.memoryPool)
+	assert np.allclose(dx.get(), ops.softmax_bwd(out.get(), dy), atol=1e-6, rtol=1e-5)
+
+	out = bnd.dnn.softmaxNd(G(bnd, x), bnd.SoftMaxMode.perActivation.value)
+	assert np.allclose(out.get(), ops.softmax(x, "perActivation"), atol=1e-6, rtol=1e-5)
+
+
+def test_softmax_is_max_subtracted(bnd):
+	x = np.array([[1000.0, 1001.0, 999.0], [-1e4, 0.0, -1e4]], np.float32).reshape(2, 3, 1, 1)
+	out = bnd.dnn.softmaxNd(G(bnd, x)).get()
+	assert np.isfinite(out).all() and np.allclose(out, ops.softmax(x), atol=1e-6)
+
+
+# ================================================================================================ elementwise
+ACTS = [("sigmoid", ()), ("tanh", ()), ("relu", ()), ("leakyRelu", (0.01, )), ("elu", (1.0, )), ("softPlus", ()), ("clip", (0.0, 6.0)),
+		("gelu", ())]
+
+
+@pytest.mark.parametrize("kind,args", ACTS)
+@pytest.mark.parametrize("n", [1, 7, 1000, 4099, 1 << 20])
+def test_activations(bnd, kind, args, n):
+	rng = np.random.RandomState(n % 1000)
+	x = (rng.randn(n) * 3).astype(np.float32)
+	x[::5] = 0.0
+	g = rng.randn(n).astype(np.float32)
+
+	out = bnd.GPUArray.empty((n, ), np.float32)
+	getattr(bnd, "%sKer" % kind)(np.float32)(out, G(bnd, x), *args)
+	y = ops.activation(kind, x, *args)
+	# the reference compiles these kernels with -use_fast_math (fast expf / logf / division): 1e-5 absolute is ITS bar
+	tol = {"tanh": 1e-3, "gelu": 1e-4}.get(kind, 2e-5)      # fast-math tanhf is the MUFU.TANH approximation (2^-11)
+	assert np.allclose(out.get(), y, atol=tol, rtol=tol)
+
+	ref = x if kind == "gelu" else out.get()
+	ingrad = bnd.GPUArray.empty((n, ), np.float32)
+	getattr(bnd, "%sDerKer" % kind)(np.float32)(ingrad, G(bnd, g), G(bnd, ref), *args)
+	assert np.allclose(ingrad.get(), ops.activation_bwd(kind, g, ref, *args), atol=tol, rtol=tol)
+
+
+def test_relu_is_exact_and_works_in_place_and_on_unaligned_views(bnd):
+	rng = np.random.RandomState(1)
+	x = rng.randn(3, 1001).astype(np.float32)
+	d = G(bnd, x)
+	bnd.reluKer(np.float32)(d, d)
+	assert np.array_equal(d.get(), x * (x > 0))
+	flat = G(bnd, x).ravel()
+	view = flat[3:2002]                              # 12-byte offset: exercises the head / tail peeling
+	out = bnd.GPUArray.zeros((2000, ), np.float32)[1:]
+	bnd.reluKer(np.float32)(out, view)
+	xs = x.ravel()[3:2002]
+	assert np.array_equal(out.get(), xs * (xs > 0))
+
+
+@pytest.mark.parametrize("dtype", ["float16", "bfloat16"])
+def test_16bit_elementwise(bnd, dtype):
+	from puzzlelib_b200.driver import bfloat16
+	dt = np.dtype(np.float16) if dtype == "float16" else bfloat16
+	rng = np.random.RandomState(2)
+	x32 = rng.randn(5000).astype(np.float32)
+	x = x32.astype(dt)
+	d = G(bnd, x)
+	out = bnd.GPUArray.empty(x.shape, dt)
+	bnd.reluKer(dt)(out, d)
+	xf = x.astype(np.float32)
+	assert np.array_equal(out.get().astype(np.float32), xf * (xf > 0))
+	back = G(bnd, x32).astype(dt)
+	assert np.array_equal(back.get().view(np.uint16), x.view(np.uint16))      # round-to-nearest-even like numpy
+	assert np.array_equal(back.astype(np.float32).get(), xf)
+
+
+def test_blas1_kernels(bnd):
+	rng = np.random.RandomState(4)
+	n = 100003
+	x, y = rng.randn(n).astype(np.float32), rng.randn(n).astype(np.float32)
+	dy = G(bnd, y)
+	bnd.toVectorAddVectorKer(np.float32)(dy, G(bnd, x), 0.3)
+	assert np.allclose(dy.get(), y + np.float32(0.3) * x, atol=1e-6)
+	out = bnd.GPUArray.empty((n, ), np.float32)
+	bnd.addKer(np.float32)(out, G(bnd, x), 0.25, G(bnd, y), -1.5)
+	assert np.allclose(out.get(), 0.25 * x - 1.5 * y, atol=1e-6)
+	bnd.linearKer(np.float32)(out, G(bnd, x), 2.0, -1.0)
+	assert np.allclose(out.get(), 2 * x - 1, atol=1e-6)
+	bnd.mulKer(np.float32)(out, G(bnd, x), G(bnd, y))
+	assert np.array_equal(out.get(), x * y)
+	bnd.add2Ker(np.float32)(out, G(bnd, x), G(bnd, y))
+	assert np.array_equal(out.get(), (np.float32(0) + x) + y)                # same bits as fill(0) + 2 axpy (Add.py:15-23)
+	p, m = rng.randn(n).astype(np.float32), rng.randn(n).astype(np.float32)
+	dp, dm = G(bnd, p), G(bnd, m)
+	bnd.classicMomSGDKer(np.float32)(dp, G(bnd, x), dm, 0.1, 0.9)
+	wp, wm = ops.sgd_momentum(p, x, m, 0.1, 0.9)
+	assert np.allclose(dp.get(), wp, atol=1e-6) and np.allclose(dm.get(), wm, atol=1e-6)
+
+
+def test_matvec_helpers(bnd):
+	rng = np.random.RandomState(6)
+	mat, vec = rng.randn(37, 130).astype(np.float32), rng.randn(130).astype(np.float32)
+	out = bnd.matmod.addVecToMat(G(bnd, vec), G(bnd, mat), axis=1)
+	assert np.array_equal(out.get(), mat + vec)
+	col = rng.randn(37).astype(np.float32)
+	assert np.array_equal(bnd.matmod.addVecToMat(G(bnd, col), G(bnd, mat), axis=0).get(), mat + col[:, None])
+	small = rng.randn(13).astype(np.float32)
+	assert np.array_equal(bnd.matmod.addVecToMat(G(bnd, small), G(bnd, mat), axis=1).get(), mat + np.tile(small, 10))
+
+	assert np.allclose(bnd.matmod.matsum(G(bnd, mat), 0).get(), mat.sum(0), atol=1e-4)
+	assert np.allclose(bnd.matmod.matsum(G(bnd, mat), 1).get(), mat.sum(1), atol=1e-4)
+	acc = rng.randn(130).astype(np.float32)
+	dacc = G(bnd, acc)
+	bnd.matmod.matsum(G(bnd, mat), 0, dacc, 0.5, 2.0)
+	assert np.allclose(dacc.get(), 2 * acc + 0.5 * mat.sum(0), atol=1e-4)
+	t3 = rng.randn(4, 9, 11).astype(np.float32)
+	assert np.allclose(bnd.matmod.matsum(G(bnd, t3), 1).get(), t3.sum(1), atol=1e-4)
+
+	logits = rng.randn(64, 1000).astype(np.float32)
+	logits[3, 17] = logits[3, 900] = 50.0             # tie: first occurrence wins
+	assert np.array_equal(bnd.matmod.argmax(G(bnd, logits), 1).get(), ops.argmax(logits, 1))
+	assert np.array_equal(bnd.matmod.argmax(G(bnd, t3), 1).get(), ops.argmax(t3, 1))
+	assert np.array_equal(bnd.matmod.argmin(G(bnd, t3), 0).get(), np.argmin(t3, 0).astype(np.int32))
+
+
+# ================================================================================================ GPUArray / memory
+def test_gpuarray_roundtrip_views_fill_and_arith(bnd):
+	rng = np.random.RandomState(8)
+	h = rng.randn(4, 5, 6).astype(np.float32)
+	a = G(bnd, h)
+	assert np.array_equal(a.get(), h)
+	assert np.array_equal(a[1:3].get(), h[1:3]) and np.array_equal(a[:, 2].get(), h[:, 2])
+	assert np.array_equal(a[:, 1:4, 2:5].get(), h[:, 1:4, 2:5])       # 2 discontiguous axes -> pitched copies
+	a[:, 2] = np.zeros((4, 6), np.float32)
+	h[:, 2] = 0
+	assert np.array_equal(a.get(), h)
+	assert np.array_equal(a[:, 1:3].copy().get(), h[:, 1:3])
+	assert np.array_equal(a.reshape(20, 6).get(), h.reshape(20, 6))
+
+	for dtype, val in ((np.float32, 1.5), (np.float16, -2.0), (np.int32, 7), (np.int8, -3), (np.float64, 3.25), (np.int64, 1 << 40)):
+		f = bnd.GPUArray.empty((1003, ), dtype)
+		f.fill(val)
+		assert (f.get() == np.array(val, dtype)).all()
+	b = G(bnd, h)
+	assert np.array_equal((a + b).get(), h + h) and np.array_equal((a * b).get(), h * h)
+	a += b
+	assert np.array_equal(a.get(), h + h)
+	assert float(b.max().get()) == h.max() and float(b.min().get()) == h.min()
+	with pytest.raises(ValueError):
+		a + G(bnd, h[:2])
+
+
+def test_memory_pool_reuses_blocks(bnd):
+	pool = bnd.Driver.MemoryPool()
+	a = bnd.GPUArray.empty((1000, ), np.float32, allocator=pool)
+	ptr = a.ptr
+	del a
+	stats = pool.getStats()
+	assert stats["heldBlocks"] == 1 and stats["activeBlocks"] == 0 and stats["heldBytes"] == pool.allocSize(4000)
+	b = bnd.GPUArray.empty((1001, ), np.float32, allocator=pool)      # same size class -> same block, no cudaMalloc
+	assert b.ptr == ptr
+	del b
+	pool.freeHeld()
+	assert pool.getStats()["heldBlocks"] == 0
+
+
+def test_concatenate_split_tile_sharedarray(bnd):
+	rng = np.random.RandomState(10)
+	a, b = rng.randn(3, 4, 5).astype(np.float32), rng.randn(3, 2, 5).astype(np.float32)
+	cat = bnd.concatenate([G(bnd, a), G(bnd, b)], axis=1)
+	assert np.array_equal(cat.get(), np.concatenate([a, b], axis=1))
+	parts = bnd.split(cat, [4, 2], axis=1)
+	assert np.array_equal(parts[0].get(), a) and np.array_equal(parts[1].get(), b)
+	assert np.array_equal(bnd.tile(G(bnd, a), 3, axis=0).get(), np.tile(a, (3, 1, 1)))
+
+	shared = bnd.SharedArray(np.float32, allocator=bnd.memoryPool)
+	shared.register((3, 5), np.float32, "w")
+	shared.register((7, ), np.float32, "b")
+	shared.build()
+	assert shared.ary.size == 16 + 8 and shared["b"].ptr - shared["w"].ptr == 64      # 16-byte aligned blocks
+	shared["w"].set(np.ones((3, 5), np.float32))
+	shared["b"].fill(2.0)
+	flat = shared.ary.get()
+	assert flat[:15].sum() == 15 and (flat[16:23] == 2).all()

@@ -1,0 +1,215 @@
+"""CPU tier: the oracle against (a) golden vectors produced by the reference itself (tools/gen_golden.py, reference
+numpy CPU backend) and (b) finite-difference / adjoint identities for the backward ops the reference cannot run on
+CPU (the method of the reference's TestLib/GradientCheck.py:25-52)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import ops, refnet
+
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_cpu_ops.npz"))
+
+
+@pytest.mark.parametrize("i", range(5))
+def test_conv_fwd_matches_reference_cpu(i):
+	size, stride, pad, dil, hasbias = (int(v) for v in GOLD["conv%d_cfg" % i])
+	b = GOLD["conv%d_b" % i].ravel() if hasbias else None
+	y = ops.conv2d(GOLD["conv%d_x" % i], GOLD["conv%d_w" % i], b, stride, pad, dil)
+	assert y.shape == GOLD["conv%d_y" % i].shape
+	assert np.allclose(y, GOLD["conv%d_y" % i], atol=1e-4, rtol=1e-5)
+
+
+@pytest.mark.parametrize("i", range(5))
+def test_pool_fwd_matches_reference_cpu(i):
+	size, stride, pad, kind = (int(v) for v in GOLD["pool%d_cfg" % i])
+	y = ops.pool2d(GOLD["pool%d_x" % i], size, stride, pad, "max" if kind == 0 else "avgWithPad")
+	assert np.allclose(y, GOLD["pool%d_y" % i], atol=1e-6)
+	if kind == 0:
+		ym, mask = ops.maxpool2d_mask(GOLD["pool%d_x" % i], size, stride, pad)
+		assert np.array_equal(ym, GOLD["pool%d_y" % i])
+		x = GOLD["pool%d_x" % i]
+		flat = x.reshape(x.shape[0], x.shape[1], -1)
+		assert np.array_equal(np.take_along_axis(flat, mask.reshape(*mask.shape[:2], -1).astype(np.int64), 2).reshape(ym.shape), ym)
+
+
+@pytest.mark.parametrize("i", range(2))
+def test_batchnorm_infer_matches_reference_cpu(i):
+	g = lambda key: GOLD["bn%d_%s" % (i, key)]
+	y = ops.batchnorm_infer(g("x"), g("scale"), g("bias"), g("mean"), g("var"))
+	assert np.allclose(y, g("y"), atol=1e-5)
+
+
+@pytest.mark.parametrize("i", range(2))
+def test_linear_matches_reference_cpu(i):
+	g = lambda key: GOLD["lin%d_%s" % (i, key)]
+	transpose = bool(g("transpose")[0])
+	y = ops.gemm(g("x"), g("w"), transpB=transpose) + g("b")
+	assert np.allclose(y, g("y"), atol=1e-5)
+	assert np.allclose(ops.gemm(g("g"), g("w"), transpB=not transpose), g("dx"), atol=1e-5)
+	dw = ops.gemm(g("x"), g("g"), transpA=True) if not transpose else ops.gemm(g("g"), g("x"), transpA=True)
+	assert np.allclose(dw, g("dw"), atol=1e-5)
+	if not transpose:
+		assert np.allclose(ops.matsum(g("g"), 0), g("db"), atol=1e-5)
+
+
+@pytest.mark.parametrize("kind", ["sigmoid", "tanh", "relu", "leakyRelu", "elu", "softPlus", "clip"])
+def test_activation_matches_reference_cpu(kind):
+	y = ops.activation(kind, GOLD["act_x"])
+	assert np.allclose(y, GOLD["act_%s_y" % kind], atol=1e-6)
+	dx = ops.activation_bwd(kind, GOLD["act_g"], GOLD["act_%s_y" % kind])
+	assert np.allclose(dx, GOLD["act_%s_dx" % kind], atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------ backward ops: gradient checks
+def numgrad(f, x, eps=1e-6):
+	g = np.zeros_like(x)
+	it = np.nditer(x, flags=["multi_index"])
+	while not it.finished:
+		idx = it.multi_index
+		old = x[idx]
+		x[idx] = old + eps
+		fp = f()
+		x[idx] = old - eps
+		fm = f()
+		x[idx] = old
+		g[idx] = (fp - fm) / (2 * eps)
+		it.iternext()
+	return g
+
+
+@pytest.mark.parametrize("cfg", [(1, 1, 0, 1), (2, 1, 1, 1), (1, 2, 2, 1), (2, 0, 1, 2), (1, 1, 1, 3)])
+def test_conv_backward_gradcheck(cfg):
+	stride, pad, dil, groups = cfg
+	rng = np.random.RandomState(0)
+	x = rng.randn(2, 2 * groups, 6, 5)
+	w = rng.randn(3 * groups, 2, 3, 2)
+	y = ops.conv2d(x, w, None, stride, pad, dil, groups)
+	gy = rng.randn(*y.shape)
+
+	loss = lambda: float((ops.conv2d(x, w, None, stride, pad, dil, groups) * gy).sum())
+	dx = ops.conv2d_bwd_data(gy, w, x.shape, stride=stride, pad=pad, dilation=dil, groups=groups)
+	dw, db = ops.conv2d_bwd_params(x, gy, w.shape, stride, pad, dil, groups, withbias=True)
+	assert np.allclose(dx, numgrad(loss, x), atol=1e-5)
+	assert np.allclose(dw, numgrad(loss, w), atol=1e-5)
+	assert np.allclose(db, gy.sum(axis=(0, 2, 3)))
+
+	old = rng.randn(*w.shape)
+	dw2 = ops.conv2d_bwd_params(x, gy, w.shape, stride, pad, dil, groups, wgrad=old, scale=0.5, momentum=0.25)
+	assert np.allclose(dw2, 0.5 * dw + 0.25 * old)
+
+
+def test_deconv_is_conv_transpose():
+	# <deconv(x), y> == <x, conv(y)>: Deconv forward is conv backward-data (Backend/Dnn.py:211-215)
+	rng = np.random.RandomState(1)
+	w = rng.randn(4, 3, 3, 3)
+	x = rng.randn(2, 4, 5, 5)
+	out = ops.conv2d_bwd_data(x, w, None, stride=2, pad=1, postpad=1)
+	assert out.shape == (2, 3, 10, 10)
+	y = rng.randn(*out.shape)
+	assert np.isclose((out * y).sum(), (x * ops.conv2d(y, w, None, 2, 1)).sum())
+
+
+def test_batchnorm_backward_gradcheck():
+	rng = np.random.RandomState(2)
+	x, scale, bias = rng.randn(3, 4, 2, 3), rng.randn(4), rng.randn(4)
+	gy = rng.randn(*x.shape)
+	zero, one = np.zeros(4), np.ones(4)
+	y, mu, inv, newmean, newvar = ops.batchnorm_train(x, scale, bias, zero, one, 1e-5, 1.0)
+	assert np.allclose(newmean, x.mean(axis=(0, 2, 3)))
+	assert np.allclose(newvar, x.var(axis=(0, 2, 3), ddof=1))
+
+	# the reference test's own closed form (Cuda/Wrappers/CuDnnNorm.py:50-64)
+	norm = 3 * 2 * 3
+	hm, hi, hs = mu.reshape(1, 4, 1, 1), inv.reshape(1, 4, 1, 1), scale.reshape(1, 4, 1, 1)
+	bg = gy.sum(axis=(0, 2, 3), keepdims=True)
+	vg = -0.5 * (gy * (x - hm)).sum(axis=(0, 2, 3), keepdims=True) * hs * hi ** 3
+	want = gy * hs * hi + (2 * vg * (x - hm) + (-hi * bg * hs)) / norm
+
+	dx, dscale, dbias = ops.batchnorm_bwd(x, gy, scale, mu, inv)
+	assert np.allclose(dx, want)
+	loss = lambda: float((ops.batchnorm_train(x, scale, bias, zero, one, 1e-5, 1.0)[0] * gy).sum())
+	assert np.allclose(dx, numgrad(loss, x), atol=1e-5)
+	assert np.allclose(dscale, numgrad(loss, scale), atol=1e-5)
+	assert np.allclose(dbias, numgrad(loss, bias), atol=1e-5)
+
+
+@pytest.mark.parametrize("mode", ["max", "avgWithPad", "avgNoPad"])
+def test_pool_backward_gradcheck(mode):
+	rng = np.random.RandomState(3)
+	x = rng.randn(2, 2, 7, 6)
+	y = ops.pool2d(x, 3, 2, 1, mode)
+	gy = rng.randn(*y.shape)
+	loss = lambda: float((ops.pool2d(x, 3, 2, 1, mode) * gy).sum())
+	assert np.allclose(ops.pool2d_bwd(x, y, gy, 3, 2, 1, mode), numgrad(loss, x), atol=1e-5)
+
+
+def test_maxpool_mask_semantics():
+	# ties: first strict maximum of the row-major scan wins (Cuda/Kernels/Pool.py:34-42); backward gathers by mask
+	x = np.zeros((1, 1, 4, 4), np.float32)
+	y, mask = ops.maxpool2d_mask(x, 2, 2, 0)
+	assert np.array_equal(mask[0, 0], np.array([[0, 2], [8, 10]], np.int32))
+	x[0, 0, 1, 1] = 1.0
+	y, mask = ops.maxpool2d_mask(x, 3, 1, 1)
+	assert mask[0, 0, 0, 0] == 5 and y[0, 0, 0, 0] == 1.0 and mask[0, 0, 3, 3] == 10
+	gy = np.arange(16, dtype=np.float32).reshape(1, 1, 4, 4)
+	dx = ops.maxpool2d_mask_bwd(gy, x.shape, mask, 3, 1, 1)
+	assert dx.sum() == gy.sum() and dx[0, 0, 1, 1] == gy[0, 0, :3, :3].sum()
+	up = ops.maxunpool2d(y, x.shape, mask)
+	assert up[0, 0, 1, 1] == 1.0
+	assert np.array_equal(ops.maxunpool2d_bwd(up, y.shape, mask), y)
+
+
+def test_softmax_backward_gradcheck():
+	rng = np.random.RandomState(4)
+	for mode in ("spatial", "perActivation"):
+		x = rng.randn(3, 5, 2, 2)
+		y = ops.softmax(x, mode)
+		axes = 1 if mode == "spatial" else (1, 2, 3)
+		assert np.allclose(y.sum(axis=axes), 1.0)
+		gy = rng.randn(*x.shape)
+		loss = lambda: float((ops.softmax(x, mode) * gy).sum())
+		assert np.allclose(ops.softmax_bwd(y, gy, mode), numgrad(loss, x), atol=1e-6)
+
+
+def test_gelu_derivative_is_the_reference_formula_not_the_true_one():
+	x = np.linspace(-2, 2, 9)
+	d = ops.activation_bwd("gelu", np.ones_like(x), x)
+	true = 0.5 * (1 + ops._erf(x / np.sqrt(2))) + x / np.sqrt(2 * np.pi) * np.exp(-0.5 * x * x)
+	assert not np.allclose(d, true)          # 1/sqrt(pi), sic (ElementWise.py:469-475)
+	assert np.allclose(d[4], true[4])
+
+
+def test_refnet_lenet_gradcheck_and_accumulate():
+	rng = np.random.RandomState(5)
+	net = refnet.init_he(refnet.lenet(), seed=7)
+	x = rng.randn(2, 1, 28, 28)
+	gy = rng.randn(2, 10)
+	net.forward(x, np.float64)
+	net.backward(gy, np.float64, scale=1.0, momentum=0.0)
+	first = net.layers[0]
+	W = first.W.astype(np.float64)
+	first.W = W
+	idxs = [(0, 0, 0, 0), (3, 0, 1, 2), (15, 0, 2, 2)]
+	for idx in idxs:
+		old = W[idx]
+		W[idx] = old + 1e-5
+		fp = float((net.forward(x, np.float64) * gy).sum())
+		W[idx] = old - 1e-5
+		fm = float((net.forward(x, np.float64) * gy).sum())
+		W[idx] = old
+		assert np.isclose(first.dW[idx], (fp - fm) / 2e-5, rtol=1e-4, atol=1e-7)
+	# Sequential.backward semantics: momentum = 1 accumulates into the existing gradient
+	before = first.dW.copy()
+	net.forward(x, np.float64)
+	net.backward(gy, np.float64, scale=1.0, momentum=1.0)
+	assert np.allclose(first.dW, 2 * before)
+
+
+def test_refnet_resnet50_shapes():
+	net = refnet.resnet50()
+	convs = [l for l in net.leaves() if isinstance(l, refnet.Conv)]
+	bns = [l for l in net.leaves() if isinstance(l, refnet.BatchNorm)]
+	assert len(convs) == 53 and len(bns) == 53
+	nparams = sum(l.W.size for l in convs) + sum(2 * l.scale.size for l in bns) + 2048 * 1000 + 1000
+	assert nparams == 25557032      # 25.56 M parameters
