@@ -44,6 +44,14 @@ int check_desc(int dtype, const pz_conv2d_desc* d, Geo& g)
 	return PZ_OK;
 }
 
+// the fast producers pack (offset << 6 | tap) into 32 bits: `span` elements of channel / row offsets plus the tap
+// offsets of one filter window must stay below 2^26, and a filter may have at most 63 taps
+bool tap_entries_fit(long long span, const Geo& g)
+{
+	const long long taps = (long long)(g.R - 1) * g.dh * (g.W > g.Q ? g.W : g.Q) + (long long)(g.S - 1) * g.dw;
+	return span + 2 * taps < (1ll << 26) && g.R * g.S <= 63;
+}
+
 // true when no tap of any output position can fall outside the un-padded input
 bool taps_in_bounds(const Geo& g)
 {
@@ -138,6 +146,7 @@ int pz_conv2d_fprop(int dtype, const pz_conv2d_desc* d, const void* x, const voi
 	A.H = g.H; A.W = g.W; A.Wd = g.W;
 	A.cdh = A.cdw = 1;
 	A.rows = g.N * PQ; A.kdim = g.Cg * RS;
+	A.R = g.R; A.S = g.S;
 	A.group_stride = (long long)g.Cg * HW;
 
 	p.B = dense_k((const float*)w, g.Kg, g.Cg * RS, (long long)g.Cg * RS);
@@ -160,8 +169,8 @@ int pz_conv2d_fprop(int dtype, const pz_conv2d_desc* d, const void* x, const voi
 	p.splits = 1;
 	p.kb_per_split = p.kblocks;
 	set_alg(p, g);
-	const int amode = taps_in_bounds(g) ? MODE_MN_SIMPLE : MODE_MN_GENERAL;
-	return launch(p, pick_bn(g.Kg), amode, MODE_K_SIMPLE, false, g.G, pz_stream(stream));
+	const bool fast = tap_entries_fit(34ll * HW, g);
+	return launch(p, pick_bn(g.Kg), fast ? MODE_MN_TAP : MODE_MN_GENERAL, MODE_K_DENSE, fast && RS > 31, g.G, pz_stream(stream));
 }
 
 size_t pz_conv2d_dgrad_workspace(int dtype, const pz_conv2d_desc* d)
@@ -211,6 +220,7 @@ int pz_conv2d_dgrad(int dtype, const pz_conv2d_desc* d, const void* dy, const vo
 		A.H = 1; A.W = PQ; A.Wd = 0;
 		A.cdh = A.cdw = 1;
 		A.rows = g.N * PQ; A.kdim = g.Kg;
+		A.R = A.S = 1;
 		A.group_stride = (long long)g.Kg * PQ;
 
 		// filter element (row = c, k = ko) at w[(g*Kg + ko)*Cg + c]
@@ -223,7 +233,8 @@ int pz_conv2d_dgrad(int dtype, const pz_conv2d_desc* d, const void* dy, const vo
 		p.kblocks = (int)pz_cdiv(A.kdim, BK);
 		p.kb_per_split = p.kblocks;
 		set_alg(p, g);
-		return launch(p, pick_bn(g.Cg), MODE_MN_SIMPLE, MODE_MN_SIMPLE, false, g.G, pz_stream(stream));
+		PZ_REQUIRE(34ll * PQ < (1ll << 26) && 34ll * g.Cg < (1ll << 26), "conv2d dgrad: tensor too large");
+		return launch(p, pick_bn(g.Cg), MODE_MN_TAP, MODE_MN_TAP, false, g.G, pz_stream(stream));
 	}
 
 	// general case: gather dy through the transposed-convolution index map
@@ -245,6 +256,7 @@ int pz_conv2d_dgrad(int dtype, const pz_conv2d_desc* d, const void* dy, const vo
 	A.H = g.P; A.W = g.Q; A.Wd = g.Q;
 	A.cdh = g.sh; A.cdw = g.sw;
 	A.rows = g.N * HW; A.kdim = g.Kg * RS;
+	A.R = g.R; A.S = g.S;
 	A.group_stride = (long long)g.Kg * PQ;
 
 	p.B = dense_k((const float*)workspace, g.Cg, g.Kg * RS, (long long)g.Kg * RS);
@@ -256,7 +268,9 @@ int pz_conv2d_dgrad(int dtype, const pz_conv2d_desc* d, const void* dy, const vo
 	p.kblocks = (int)pz_cdiv(A.kdim, BK);
 	p.kb_per_split = p.kblocks;
 	set_alg(p, g);
-	return launch(p, pick_bn(g.Cg), MODE_MN_GENERAL, MODE_K_SIMPLE, strided, g.G, pz_stream(stream));
+	if (!strided && tap_entries_fit(34ll * PQ, g))
+		return launch(p, pick_bn(g.Cg), MODE_MN_TAP, MODE_K_DENSE, RS > 31, g.G, pz_stream(stream));
+	return launch(p, pick_bn(g.Cg), MODE_MN_GENERAL, MODE_K_DENSE, strided, g.G, pz_stream(stream));
 }
 
 int pz_conv2d_wgrad(int dtype, const pz_conv2d_desc* d, const void* x, const void* dy, void* dw, float alpha, float beta,
@@ -279,6 +293,7 @@ int pz_conv2d_wgrad(int dtype, const pz_conv2d_desc* d, const void* x, const voi
 	A.H = g.H; A.W = g.W; A.Wd = g.W;
 	A.cdh = A.cdw = 1;
 	A.rows = g.Cg * RS; A.kdim = g.N * PQ;
+	A.R = g.R; A.S = g.S;
 	A.group_stride = (long long)g.Cg * HW;
 
 	Operand& B = p.B;   // dy: rows ko, k (n, pq)
@@ -290,6 +305,7 @@ int pz_conv2d_wgrad(int dtype, const pz_conv2d_desc* d, const void* x, const voi
 	B.aw = 0; B.bw = 1; B.cw = 0;
 	B.H = 1; B.W = PQ; B.Wd = 0;
 	B.cdh = B.cdw = 1;
+	B.R = B.S = 1;
 	B.rows = g.Kg; B.kdim = g.N * PQ;
 	B.group_stride = (long long)g.Kg * PQ;
 
@@ -314,8 +330,8 @@ int pz_conv2d_wgrad(int dtype, const pz_conv2d_desc* d, const void* x, const voi
 		if (st != PZ_OK) return st;
 	}
 	set_alg(p, g);
-	const int amode = taps_in_bounds(g) ? MODE_K_SIMPLE : MODE_K_GENERAL;
-	return launch(p, bn, amode, MODE_K_SIMPLE, false, g.G, pz_stream(stream));
+	const bool fast = tap_entries_fit((long long)g.Cg * HW, g);
+	return launch(p, bn, fast ? MODE_K_TAP : MODE_K_GENERAL, MODE_K_DENSE, fast && RS > 31, g.G, pz_stream(stream));
 }
 
 int pz_bias_grad(int dtype, const void* t, void* db, int64_t N, int64_t C, int64_t S, float alpha, float beta, void* stream)

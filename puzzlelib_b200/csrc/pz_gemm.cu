@@ -19,6 +19,7 @@ Operand dense_k(const float* ptr, int rows, int kdim, long long ld)
 	o.H = 1; o.W = kdim; o.Wd = 0;
 	o.cdh = o.cdw = 1;
 	o.rows = rows; o.kdim = kdim;
+	o.R = o.S = 1;
 	o.group_stride = 0;
 	return o;
 }
@@ -38,6 +39,7 @@ Operand dense_mn(const float* ptr, int rows, int kdim, long long ld)
 	o.H = 1; o.W = rows; o.Wd = 0;
 	o.cdh = o.cdw = 1;
 	o.rows = rows; o.kdim = kdim;
+	o.R = o.S = 1;
 	o.group_stride = 0;
 	return o;
 }
@@ -75,13 +77,15 @@ int launch(const GemmParams& p, int bn, int amode, int bmode, bool cdiv, int gro
 	if (bn == BNV && amode == AMV && bmode == BMV && cdiv == CD)               \
 		return launch_inst<BNV, AMV, BMV, CD>(p, grid, stream);
 #define PZ_INST_BN(AMV, BMV, CD) PZ_INST(64, AMV, BMV, CD) PZ_INST(128, AMV, BMV, CD)
-	PZ_INST_BN(MODE_K_GENERAL, MODE_K_SIMPLE, false)
-	PZ_INST_BN(MODE_K_SIMPLE, MODE_K_SIMPLE, false)
-	PZ_INST_BN(MODE_K_SIMPLE, MODE_MN_SIMPLE, false)
-	PZ_INST_BN(MODE_MN_GENERAL, MODE_K_SIMPLE, false)
-	PZ_INST_BN(MODE_MN_GENERAL, MODE_K_SIMPLE, true)
-	PZ_INST_BN(MODE_MN_SIMPLE, MODE_K_SIMPLE, false)
-	PZ_INST_BN(MODE_MN_SIMPLE, MODE_MN_SIMPLE, false)
+	PZ_INST_BN(MODE_MN_TAP, MODE_K_DENSE, false)       // fprop, stride-1 dgrad, GEMM NN
+	PZ_INST_BN(MODE_MN_TAP, MODE_K_DENSE, true)        //   ... with more than 31 taps (7x7)
+	PZ_INST_BN(MODE_MN_TAP, MODE_MN_TAP, false)        // 1x1 dgrad, GEMM TN
+	PZ_INST_BN(MODE_K_DENSE, MODE_K_DENSE, false)      // GEMM NT
+	PZ_INST_BN(MODE_K_TAP, MODE_K_DENSE, false)        // wgrad
+	PZ_INST_BN(MODE_K_TAP, MODE_K_DENSE, true)         //   ... with more than 31 taps
+	PZ_INST_BN(MODE_MN_GENERAL, MODE_K_DENSE, false)   // fallback: offsets too large for the packed tap entries
+	PZ_INST_BN(MODE_MN_GENERAL, MODE_K_DENSE, true)    // strided dgrad (exact-division gather)
+	PZ_INST_BN(MODE_K_GENERAL, MODE_K_DENSE, false)    // fallback for wgrad
 #undef PZ_INST_BN
 #undef PZ_INST
 	pz_set_error(PZ_ERR_UNSUPPORTED, "no GEMM instantiation for bn=%d amode=%d bmode=%d cdiv=%d", bn, amode, bmode, (int)cdiv);
@@ -91,6 +95,30 @@ int launch(const GemmParams& p, int bn, int amode, int bmode, bool cdiv, int gro
 }  // namespace pzumma
 
 using namespace pzumma;
+
+// Contractions with a tiny K (e.g. Linear wgrad at batch 2) gain nothing from tensor cores and would expose the raw
+// 2^-11 tf32 rounding of single products; they run in exact fp32 FMAs on the CUDA cores instead.
+__global__ void __launch_bounds__(256) gemm_smallk_kernel(const float* __restrict__ A, const float* __restrict__ B, float* C, int64_t M,
+														  int64_t N, int K, int64_t lda, int64_t ldb, int64_t ldc, int transA, int transB,
+														  float alpha, float beta, const float* __restrict__ bias)
+{
+	const int64_t total = M * N;
+	for (int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * 256) {
+		const int64_t m = idx / N, n = idx - m * N;
+		float acc = 0.0f;
+		for (int k = 0; k < K; k++) {
+			const float a = transA ? A[k * lda + m] : A[m * lda + k];
+			const float b = transB ? B[n * ldb + k] : B[k * ldb + n];
+			acc = fmaf(a, b, acc);
+		}
+		float r = alpha * acc;
+		if (bias) r += bias[n];
+		if (beta != 0.0f) r += beta * C[m * ldc + n];
+		C[m * ldc + n] = r;
+	}
+}
+
+constexpr int kSmallK = 8;
 
 extern "C" int pz_gemm(int dtype, const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, int64_t lda,
 					   int64_t ldb, int64_t ldc, int transA, int transB, float alpha, float beta, const void* bias,
@@ -103,13 +131,25 @@ extern "C" int pz_gemm(int dtype, const void* A, const void* B, void* C, int64_t
 			   "pz_gemm: operand exceeds 2^31 elements");
 	if (M == 0 || N == 0) return PZ_OK;
 
+	if (K <= kSmallK) {
+		int64_t blocks = pz_cdiv(M * N, 256);
+		if (blocks > (int64_t)pz_num_sms() * 16) blocks = (int64_t)pz_num_sms() * 16;
+		gemm_smallk_kernel<<<(unsigned)blocks, 256, 0, pz_stream(stream)>>>((const float*)A, (const float*)B, (float*)C, M, N, (int)K, lda,
+																			 ldb, ldc, transA, transB, alpha, beta, (const float*)bias);
+		pz_count_launch(1);
+		PZ_LAUNCH_CHECK();
+		return PZ_OK;
+	}
+
 	// TMEM lanes (engine rows) are mapped to C's contiguous dimension: D[n][m] = sum_k opB[k][n] * opA[m][k]
 	GemmParams p{};
 	int amode, bmode;
-	if (transB) { p.A = dense_k((const float*)B, (int)N, (int)K, ldb); amode = MODE_K_SIMPLE; }
-	else        { p.A = dense_mn((const float*)B, (int)N, (int)K, ldb); amode = MODE_MN_SIMPLE; }
-	if (transA) { p.B = dense_mn((const float*)A, (int)M, (int)K, lda); bmode = MODE_MN_SIMPLE; }
-	else        { p.B = dense_k((const float*)A, (int)M, (int)K, lda); bmode = MODE_K_SIMPLE; }
+	PZ_REQUIRE(!(transA && transB), "pz_gemm: at most one operand may be transposed");
+	PZ_REQUIRE(ldb < (1ll << 20) && lda < (1ll << 20), "pz_gemm: row pitch too large");
+	if (transB) { p.A = dense_k((const float*)B, (int)N, (int)K, ldb); amode = MODE_K_DENSE; }
+	else        { p.A = dense_mn((const float*)B, (int)N, (int)K, ldb); amode = MODE_MN_TAP; }
+	if (transA) { p.B = dense_mn((const float*)A, (int)M, (int)K, lda); bmode = MODE_MN_TAP; }
+	else        { p.B = dense_k((const float*)A, (int)M, (int)K, lda); bmode = MODE_K_DENSE; }
 
 	Epilogue& E = p.E;
 	E.out = (float*)C;

@@ -49,7 +49,8 @@ __device__ __forceinline__ void plane_visit(const T* plane, int64_t S, int gi, i
 		if (head > S) head = S;
 		nvec = (S - head) / V;
 	}
-	for (int64_t v = gi; v < nvec; v += gsize) body(head + v * V);
+	#pragma unroll 4
+	for (int64_t v = gi; v < nvec; v += gsize) body(head + v * V);      // unrolled: 4 independent 128-bit loads in flight
 	const int64_t tailstart = head + nvec * V;
 	const int64_t nscalar = head + (S - tailstart);
 	for (int64_t s = gi; s < nscalar; s += gsize) tail(s < head ? s : tailstart + (s - head));
@@ -127,37 +128,43 @@ __global__ void __launch_bounds__(kThreads) bn_fwd_train_kernel(const T* __restr
 	__shared__ Moments cta_part;       // read by the other CTAs of the cluster through DSMEM
 	__shared__ float coef[2];
 
-	// pass 1: per-thread sum / sum of squares, converted to (n, mean, M2) before any cross-thread combination
-	float s1 = 0.0f, s2 = 0.0f, cnt = 0.0f;
+	// pass 1: sums of d = x - pivot and d^2 with a per-channel pivot (the channel's first element, identical for
+	// every thread of the cluster), so that E[d^2] - E[d]^2 does not cancel when |mean| >> std; plain sums combine
+	// associatively in a fixed order -> bit-identical statistics in every CTA of the cluster
+	const float pivot = to_f<T>(x[c * S]);
+	float s1 = 0.0f, s2 = 0.0f;
 	for (int64_t pl = group; pl < ps.count; pl += ngroups) {
 		const T* plane = x + ((ps.first + pl) * C + c) * S;
 		plane_visit<T>(plane, S, gi, gsize, vec_ok,
 			[&](int64_t i) {
 				Pack<T> p = *reinterpret_cast<const Pack<T>*>(plane + i);
 				#pragma unroll
-				for (int e = 0; e < VecOf<T>::N; e++) { float v = to_f<T>(p.v[e]); s1 += v; s2 += v * v; }
-				cnt += (float)VecOf<T>::N;
+				for (int e = 0; e < VecOf<T>::N; e++) { float d = to_f<T>(p.v[e]) - pivot; s1 += d; s2 = fmaf(d, d, s2); }
 			},
-			[&](int64_t i) { float v = to_f<T>(plane[i]); s1 += v; s2 += v * v; cnt += 1.0f; });
+			[&](int64_t i) { float d = to_f<T>(plane[i]) - pivot; s1 += d; s2 = fmaf(d, d, s2); });
 	}
-	Moments m;
-	m.n = cnt;
-	m.mean = cnt > 0.0f ? s1 / cnt : 0.0f;
-	m.m2 = cnt > 0.0f ? fmaxf(s2 - s1 * m.mean, 0.0f) : 0.0f;
-	m = warp_combine(m);
-	if ((threadIdx.x & 31) == 0) warp_part[threadIdx.x >> 5] = m;
+	s1 = warp_sum(s1);
+	s2 = warp_sum(s2);
+	if ((threadIdx.x & 31) == 0) { warp_part[threadIdx.x >> 5].mean = s1; warp_part[threadIdx.x >> 5].m2 = s2; }
 	__syncthreads();
 	if (threadIdx.x == 0) {
-		Moments acc = warp_part[0];
-		for (int w = 1; w < kThreads / 32; w++) acc = combine(acc, warp_part[w]);
-		cta_part = acc;
+		float a = 0.0f, b = 0.0f;
+		for (int w = 0; w < kThreads / 32; w++) { a += warp_part[w].mean; b += warp_part[w].m2; }
+		cta_part.mean = a;
+		cta_part.m2 = b;
 	}
 	cluster.sync();
 	if (threadIdx.x == 0) {
-		Moments acc = *cluster.map_shared_rank(&cta_part, 0);
-		for (unsigned r = 1; r < csize; r++) acc = combine(acc, *cluster.map_shared_rank(&cta_part, r));
-		const float mean = acc.mean;
-		const float var = acc.n > 0.0f ? acc.m2 / acc.n : 0.0f;            // biased, used for normalisation
+		float t1 = 0.0f, t2 = 0.0f;
+		for (unsigned r = 0; r < csize; r++) {
+			const Moments* remote = cluster.map_shared_rank(&cta_part, r);
+			t1 += remote->mean;
+			t2 += remote->m2;
+		}
+		const float cnt = (float)(N * S);
+		const float dmean = t1 / cnt;
+		const float mean = pivot + dmean;
+		const float var = fmaxf(t2 / cnt - dmean * dmean, 0.0f);            // biased, used for normalisation
 		const float invstd = 1.0f / sqrtf(var + eps);
 		const float a = scale[c] * invstd;
 		coef[0] = a;
@@ -166,7 +173,7 @@ __global__ void __launch_bounds__(kThreads) bn_fwd_train_kernel(const T* __restr
 			save_mean[c] = mean;
 			save_invvar[c] = invstd;
 			// cuDNN keeps the UNBIASED variance in the running estimate
-			const float uvar = acc.n > 1.0f ? acc.m2 / (acc.n - 1.0f) : var;
+			const float uvar = cnt > 1.0f ? var * (cnt / (cnt - 1.0f)) : var;
 			running_mean[c] = (1.0f - factor) * running_mean[c] + factor * mean;
 			running_var[c] = (1.0f - factor) * running_var[c] + factor * uvar;
 		}

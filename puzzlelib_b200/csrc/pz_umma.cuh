@@ -66,7 +66,11 @@ __device__ __forceinline__ void split3(uint32_t x, const FastDiv& d12, const Fas
 	x2 = (int)(rem - q1 * d2.d);
 }
 
-enum { MODE_K_GENERAL = 0, MODE_K_SIMPLE = 1, MODE_MN_GENERAL = 2, MODE_MN_SIMPLE = 3 };
+// producer kinds.  The *_GENERAL / *_SIMPLE ones evaluate the full index formula per element (any geometry);
+// MN_TAP / K_TAP / K_DENSE are the fast paths: per-row (or per-k) base offsets and tap-validity bit masks are
+// computed once, the per-element work is one predicated load + one tf32 rounding.
+enum { MODE_K_GENERAL = 0, MODE_K_SIMPLE = 1, MODE_MN_GENERAL = 2, MODE_MN_SIMPLE = 3, MODE_MN_TAP = 4, MODE_K_TAP = 5,
+	   MODE_K_DENSE = 6 };
 
 struct Operand {
 	const float* ptr;
@@ -76,6 +80,7 @@ struct Operand {
 	int H, W, Wd;
 	int cdh, cdw;
 	int rows, kdim;
+	int R, S;                    // taps of the (r, s) sub-index (1, 1 for dense operands); used by the *_TAP producers
 	long long group_stride;
 };
 
@@ -330,11 +335,211 @@ struct KProducer {
 	}
 };
 
+
+// ------------------------------------------------------------------------------------------ fast producers
+// An element is addressed as  base[ rowpart + kpart ]  with
+//   "spatial" index (the side that holds (n, y, x)):  off = i0*s0 + (i1*a_h + c_h)*Wd + (i2*a_w + c_w)
+//   "tap" index     (the side that holds (c, r, s)):  off = c*cs + r*b_h*Wd + s*b_w,   tap t = r*S + s
+// and is valid iff the tap t is in bounds for that spatial position -- one bit of a per-position mask.
+// Tap entries are packed as (offset - tapmin) << 6 | t; t == INVALID_TAP marks an out-of-range index (its mask bit is
+// never set: the host picks the 64-bit mask whenever a filter has more than 31 taps).
+template <bool WIDE> struct TapMask;
+template <> struct TapMask<false> {
+	static constexpr uint32_t INVALID_TAP = 31u;    // narrow masks serve filters with at most 31 taps
+	uint32_t m;
+	__device__ __forceinline__ void clear() { m = 0; }
+	__device__ __forceinline__ void set(int t) { m |= 1u << t; }
+	__device__ __forceinline__ bool test(uint32_t t) const { return (m >> t) & 1u; }
+};
+template <> struct TapMask<true> {
+	static constexpr uint32_t INVALID_TAP = 63u;
+	unsigned long long m;
+	__device__ __forceinline__ void clear() { m = 0; }
+	__device__ __forceinline__ void set(int t) { m |= 1ull << t; }
+	__device__ __forceinline__ bool test(uint32_t t) const { return (m >> t) & 1ull; }
+};
+
+__device__ __forceinline__ int tap_min(int nR, int nS, int bhW, int bw)
+{
+	return min(0, (nR - 1) * bhW) + min(0, (nS - 1) * bw);
+}
+
+// rows = spatial positions (MN-contiguous in memory), k = (c, r, s).  fprop, stride-1 dgrad, MN-contiguous dense.
+// Thread owns one tile row and ROWS/32 16-byte chunks (4 consecutive k) per stage; loads coalesce across lanes.
+template <int ROWS, bool WIDE>
+struct MnTapProducer {
+	static constexpr int NCH = ROWS / 32;
+	static constexpr int CSTEP = NPROD / ROWS;
+	TapMask<WIDE> mask;
+	int poff, row_local, chunk0, lane;
+	float v[NCH][4];
+
+	__device__ __forceinline__ void init(const Operand& op, int tile_row0, int warp, int lane_, uint32_t)
+	{
+		const int t = warp * 32 + lane_;
+		lane = lane_;
+		row_local = t % ROWS;
+		chunk0 = (warp * 32) / ROWS;
+		const int row = tile_row0 + row_local;
+		mask.clear();
+		int r0, r1, r2;
+		split3((uint32_t)(row < op.rows ? row : 0), op.rd12, op.rd2, r0, r1, r2);
+		const int hr = r1 * op.ah + op.ch, wr = r2 * op.aw + op.cw;
+		poff = r0 * op.rs0 + hr * op.Wd + wr + tap_min(op.R, op.S, op.bh * op.Wd, op.bw);
+		if (row < op.rows) {
+			for (int r = 0; r < op.R; r++) {
+				const bool okh = (unsigned)(hr + r * op.bh) < (unsigned)op.H;
+				for (int s = 0; s < op.S; s++)
+					if (okh && (unsigned)(wr + s * op.bw) < (unsigned)op.W) mask.set(r * op.S + s);
+			}
+		}
+	}
+	__device__ __forceinline__ void load(const Operand& op, const float* __restrict__ base, int kb)
+	{
+		// lane l decodes k = kb*32 + l once; the 4 k of a chunk are then fetched from the owning lanes by shuffle.
+		// Offsets are kept relative to the first channel of the stage so that they fit the 26-bit entry field.
+		const int k = kb * BK + lane;
+		const uint32_t cfirst = fdiv((uint32_t)(kb * BK), op.kd12);
+		const float* __restrict__ sbase = base + (long long)cfirst * op.ks0 + poff;
+		uint32_t entry = TapMask<WIDE>::INVALID_TAP;
+		if (k < op.kdim) {
+			const uint32_t c = fdiv((uint32_t)k, op.kd12);
+			const uint32_t t = (uint32_t)k - c * op.kd12.d;
+			const uint32_t r = fdiv(t, op.kd2);
+			const uint32_t s = t - r * op.kd2.d;
+			const int koff = (int)(c - cfirst) * op.ks0 + (int)r * op.bh * op.Wd + (int)s * op.bw - tap_min(op.R, op.S, op.bh * op.Wd, op.bw);
+			entry = ((uint32_t)koff << 6) | t;
+		}
+		#pragma unroll
+		for (int i = 0; i < NCH; i++) {
+			const int chunk = chunk0 + i * CSTEP;
+			#pragma unroll
+			for (int e = 0; e < 4; e++) {
+				const uint32_t ent = __shfl_sync(0xffffffffu, entry, chunk * 4 + e);
+				const bool ok = mask.test(ent & 63u);
+				v[i][e] = ok ? __ldg(sbase + (ent >> 6)) : 0.0f;
+			}
+		}
+	}
+	__device__ __forceinline__ void store(uint32_t tile)
+	{
+		#pragma unroll
+		for (int i = 0; i < NCH; i++) {
+			const int chunk = chunk0 + i * CSTEP;
+			const uint32_t addr = tile + row_local * 128 + ((chunk ^ (row_local & 7)) << 4);
+			sts128(addr, to_tf32(v[i][0]), to_tf32(v[i][1]), to_tf32(v[i][2]), to_tf32(v[i][3]));
+		}
+	}
+};
+
+// rows = (c, r, s) taps, k = spatial positions (K-contiguous in memory).  wgrad's activation operand.
+// lane = k; warp w covers tile rows w, w+8, ...; the per-row tap entries live in a small smem table.
+template <int ROWS, bool WIDE>
+struct KTapProducer {
+	static constexpr int NR = ROWS / NPROD_WARPS;
+	int warp, lane;
+	uint32_t table;
+	float v[NR];
+
+	__device__ __forceinline__ void init(const Operand& op, int tile_row0, int warp_, int lane_, uint32_t table_)
+	{
+		warp = warp_;
+		lane = lane_;
+		table = table_;
+		const int t = warp * 32 + lane;
+		if (t < ROWS) {
+			const int row = tile_row0 + t;
+			uint32_t entry = TapMask<WIDE>::INVALID_TAP;
+			if (row < op.rows) {
+				const uint32_t c = fdiv((uint32_t)row, op.rd12);
+				const uint32_t tp = (uint32_t)row - c * op.rd12.d;
+				const uint32_t r = fdiv(tp, op.rd2);
+				const uint32_t s = tp - r * op.rd2.d;
+				const int roff = (int)c * op.rs0 + (int)r * op.ah * op.Wd + (int)s * op.aw - tap_min(op.R, op.S, op.ah * op.Wd, op.aw);
+				entry = ((uint32_t)roff << 6) | tp;
+			}
+			sts32(table + t * 4, entry);
+		}
+	}
+	__device__ __forceinline__ void load(const Operand& op, const float* __restrict__ base, int kb)
+	{
+		const int k = kb * BK + lane;
+		TapMask<WIDE> mask;
+		mask.clear();
+		int k0, k1, k2;
+		split3((uint32_t)(k < op.kdim ? k : 0), op.kd12, op.kd2, k0, k1, k2);
+		const int hk = k1 * op.bh + op.ch, wk = k2 * op.bw + op.cw;
+		const int poff = k0 * op.ks0 + hk * op.Wd + wk + tap_min(op.R, op.S, op.ah * op.Wd, op.aw);
+		if (k < op.kdim) {
+			for (int r = 0; r < op.R; r++) {
+				const bool okh = (unsigned)(hk + r * op.ah) < (unsigned)op.H;
+				for (int s = 0; s < op.S; s++)
+					if (okh && (unsigned)(wk + s * op.aw) < (unsigned)op.W) mask.set(r * op.S + s);
+			}
+		}
+		#pragma unroll
+		for (int i = 0; i < NR; i++) {
+			uint32_t ent;
+			asm volatile("ld.shared.b32 %0, [%1];" : "=r"(ent) : "r"(table + (warp + i * NPROD_WARPS) * 4));
+			const bool ok = mask.test(ent & 63u);
+			v[i] = ok ? __ldg(base + poff + (int)(ent >> 6)) : 0.0f;
+		}
+	}
+	__device__ __forceinline__ void store(uint32_t tile)
+	{
+		const uint32_t col = ((((uint32_t)lane >> 2) ^ ((uint32_t)warp & 7)) << 4) | (((uint32_t)lane & 3) << 2);
+		#pragma unroll
+		for (int i = 0; i < NR; i++) sts32(tile + (warp + i * NPROD_WARPS) * 128 + col, to_tf32(v[i]));
+	}
+};
+
+// dense K-contiguous rows: element (row, k) at base[row*rs0 + (k / D)*ks0 + k % D]  (D = kd12.d, 0 = no batch split).
+// weights [K][C*R*S], transposed-B GEMM operands, and wgrad's dy operand ([ko][(n, pq)], D = PQ).
+template <int ROWS>
+struct KDenseProducer {
+	static constexpr int NR = ROWS / NPROD_WARPS;
+	int warp, lane, row0;
+	float v[NR];
+
+	__device__ __forceinline__ void init(const Operand&, int tile_row0, int warp_, int lane_, uint32_t)
+	{
+		warp = warp_;
+		lane = lane_;
+		row0 = tile_row0 + warp_;
+	}
+	__device__ __forceinline__ void load(const Operand& op, const float* __restrict__ base, int kb)
+	{
+		const int k = kb * BK + lane;
+		const bool kvalid = k < op.kdim;
+		int koff = k;
+		if (op.kd12.d > 1) {
+			const uint32_t k0 = fdiv((uint32_t)k, op.kd12);
+			koff = (int)k0 * op.ks0 + (int)((uint32_t)k - k0 * op.kd12.d);
+		}
+		const float* p = base + koff;
+		#pragma unroll
+		for (int i = 0; i < NR; i++) {
+			const int row = row0 + i * NPROD_WARPS;
+			v[i] = (kvalid && row < op.rows) ? __ldg(p + (long long)row * op.rs0) : 0.0f;
+		}
+	}
+	__device__ __forceinline__ void store(uint32_t tile)
+	{
+		const uint32_t col = ((((uint32_t)lane >> 2) ^ ((uint32_t)warp & 7)) << 4) | (((uint32_t)lane & 3) << 2);
+		#pragma unroll
+		for (int i = 0; i < NR; i++) sts32(tile + (warp + i * NPROD_WARPS) * 128 + col, to_tf32(v[i]));
+	}
+};
+
 template <int ROWS, int MODE, bool CDIV> struct ProducerSel;
 template <int ROWS, bool CDIV> struct ProducerSel<ROWS, MODE_K_GENERAL, CDIV> { using type = KProducer<ROWS, false>; };
 template <int ROWS, bool CDIV> struct ProducerSel<ROWS, MODE_K_SIMPLE, CDIV> { using type = KProducer<ROWS, true>; };
 template <int ROWS, bool CDIV> struct ProducerSel<ROWS, MODE_MN_GENERAL, CDIV> { using type = MnProducer<ROWS, false, CDIV>; };
 template <int ROWS, bool CDIV> struct ProducerSel<ROWS, MODE_MN_SIMPLE, CDIV> { using type = MnProducer<ROWS, true, false>; };
+// for the fast producers the CDIV slot selects the 64-bit tap mask (more than 32 taps, e.g. a 7x7 filter)
+template <int ROWS, bool WIDE> struct ProducerSel<ROWS, MODE_MN_TAP, WIDE> { using type = MnTapProducer<ROWS, WIDE>; };
+template <int ROWS, bool WIDE> struct ProducerSel<ROWS, MODE_K_TAP, WIDE> { using type = KTapProducer<ROWS, WIDE>; };
+template <int ROWS, bool WIDE> struct ProducerSel<ROWS, MODE_K_DENSE, WIDE> { using type = KDenseProducer<ROWS>; };
 
 template <int BN> struct Cfg {
 	static constexpr int STAGE_BYTES = (BM + BN) * 128;

@@ -182,7 +182,10 @@ def test_batchnorm_train_bwd_infer(bnd, shape):
 	dx, dscale, dbias = ops.batchnorm_bwd(x, dy, scale, mu, inv)
 	ingrad, scalegrad, bgrad = bnd.dnn.batchNormNdBackward(G(bnd, dy), G(bnd, x), G(bnd, scale), savemean, saveinvvar, 1e-5,
 														   allocator=bnd.memoryPool)
-	assert relerr(ingrad.get(), dx) < 1e-5
+	# dx is a difference of O(|dy| * |scale| * invstd) terms: hold it to 1e-5 of that scale (with 2 samples per channel it
+	# cancels to ~0 and a bound relative to max|dx| would be meaningless)
+	bar = 1e-5 * max(1.0, float(np.abs(dy).max() * np.abs(scale).max() * inv.max()))
+	assert np.abs(ingrad.get() - dx).max() < bar
 	assert relerr(scalegrad.get(), dscale) < 1e-5 and relerr(bgrad.get(), dbias) < 1e-5
 
 	data = G(bnd, x)
