@@ -93,6 +93,24 @@ __global__ void repack_filter_dgrad(const float* __restrict__ w, float* __restri
 	wt[i] = w[(((long long)g * Kg + ko) * Cg + c) * RS + rs];
 }
 
+// sub-filter of one output-parity class of a strided transposed convolution:
+// wt[g][c][ko][r'][s'] = w[g*Kg + ko][c][r0 + sh*r'][s0 + sw*s']
+__global__ void repack_filter_dgrad_class(const float* __restrict__ w, float* __restrict__ wt, int Kg, int Cg, int R, int S, int r0, int s0,
+										   int sh, int sw, int Rc, int Sc, long long total)
+{
+	long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= total) return;
+	int sc = (int)(i % Sc);
+	long long t = i / Sc;
+	int rc = (int)(t % Rc);
+	t /= Rc;
+	int ko = (int)(t % Kg);
+	t /= Kg;
+	int c = (int)(t % Cg);
+	int g = (int)(t / Cg);
+	wt[i] = w[((((long long)g * Kg + ko) * Cg + c) * R + (r0 + sh * rc)) * S + (s0 + sw * sc)];
+}
+
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) bias_grad_kernel(const float* __restrict__ t, float* __restrict__ db, long long N,
 															 long long C, long long S, float alpha, int nsplit)
@@ -240,6 +258,68 @@ int pz_conv2d_dgrad(int dtype, const pz_conv2d_desc* d, const void* dy, const vo
 	// general case: gather dy through the transposed-convolution index map
 	const size_t need = (size_t)g.K * g.Cg * RS * sizeof(float);
 	PZ_REQUIRE(workspace != nullptr && workspace_bytes >= need, "conv2d dgrad: workspace too small (%zu < %zu)", workspace_bytes, need);
+
+	if (strided && g.dh == 1 && g.dw == 1 && tap_entries_fit(34ll * PQ, g)) {
+		// A strided transposed convolution splits into sh*sw independent STRIDE-1 problems, one per parity class
+		// (h mod sh, w mod sw) of the input-gradient positions: only the taps r = r0 + sh*r' with r0 = (a_h + pad_h) mod sh
+		// can reach such a position.  No tap is ever evaluated on a zero, and each class runs on the fast tap producer.
+		float* wsp = (float*)workspace;
+		bool zeroed = false;
+		for (int a_h = 0; a_h < g.sh && a_h < g.H; a_h++)
+			for (int a_w = 0; a_w < g.sw && a_w < g.W; a_w++) {
+				const int r0 = (a_h + g.ph) % g.sh, s0 = (a_w + g.pw) % g.sw;
+				const int Rc = r0 < g.R ? (g.R - r0 + g.sh - 1) / g.sh : 0, Sc = s0 < g.S ? (g.S - s0 + g.sw - 1) / g.sw : 0;
+				const int Hc = (g.H - a_h + g.sh - 1) / g.sh, Wc = (g.W - a_w + g.sw - 1) / g.sw;
+				if (Rc == 0 || Sc == 0) {
+					// no tap reaches this class (stride larger than the filter): those gradients are zero (+ bias)
+					if (!zeroed) {
+						PZ_REQUIRE(bias == nullptr, "conv2d dgrad: bias with stride > filter size is not supported");
+						st = pz_memset8(dx, 0, (size_t)g.N * g.C * HW * 4, stream);
+						if (st != PZ_OK) return st;
+						zeroed = true;      // the memset precedes every class launch in stream order: classes only overwrite their own positions
+					}
+					continue;
+				}
+				const long long total = (long long)g.K * g.Cg * Rc * Sc;
+				repack_filter_dgrad_class<<<(unsigned)pz_cdiv(total, 256), 256, 0, pz_stream(stream)>>>(
+					(const float*)w, wsp, g.Kg, g.Cg, g.R, g.S, r0, s0, g.sh, g.sw, Rc, Sc, total);
+				pz_count_launch(1);
+				PZ_LAUNCH_CHECK();
+
+				GemmParams q{};
+				Operand& QA = q.A;                 // rows (n, h', w') of the class, k (ko, r', s')
+				QA.ptr = (const float*)dy;
+				QA.rd12 = make_fastdiv(Hc * Wc); QA.rd2 = make_fastdiv(Wc);
+				QA.kd12 = make_fastdiv(Rc * Sc); QA.kd2 = make_fastdiv(Sc);
+				QA.rs0 = g.K * PQ; QA.ks0 = PQ;
+				QA.ah = 1; QA.bh = -1; QA.ch = (a_h + g.ph - r0) / g.sh;
+				QA.aw = 1; QA.bw = -1; QA.cw = (a_w + g.pw - s0) / g.sw;
+				QA.H = g.P; QA.W = g.Q; QA.Wd = g.Q;
+				QA.cdh = QA.cdw = 1;
+				QA.rows = g.N * Hc * Wc; QA.kdim = g.Kg * Rc * Sc;
+				QA.R = Rc; QA.S = Sc;
+				QA.group_stride = (long long)g.Kg * PQ;
+
+				q.B = dense_k(wsp, g.Cg, g.Kg * Rc * Sc, (long long)g.Kg * Rc * Sc);
+				q.B.group_stride = (long long)g.Cg * g.Kg * Rc * Sc;
+
+				q.E = E;
+				q.E.out = (float*)dx + (long long)a_h * g.W + a_w;
+				q.E.md12 = make_fastdiv(Hc * Wc); q.E.md2 = make_fastdiv(Wc);
+				q.E.ms0 = g.C * HW; q.E.ms1 = g.sh * g.W; q.E.ms2 = g.sw;
+				q.E.M = g.N * Hc * Wc;
+				q.splits = 1;
+				q.kblocks = (int)pz_cdiv(QA.kdim, BK);
+				q.kb_per_split = q.kblocks;
+				q.alg_flops = 2.0 * (double)q.E.M * g.K * g.Cg * Rc * Sc / g.G * g.G;
+				q.alg_bytes = 4.0 * ((double)g.N * g.K * PQ / (g.sh * g.sw) + (double)total + (double)q.E.M * g.C);
+				st = launch(q, pick_bn(g.Cg), MODE_MN_TAP, MODE_K_DENSE, Rc * Sc > 31, g.G, pz_stream(stream));
+				if (st != PZ_OK) return st;
+				wsp += total;
+			}
+		return PZ_OK;
+	}
+
 	{
 		long long total = (long long)g.K * g.Cg * RS;
 		repack_filter_dgrad<<<(unsigned)pz_cdiv(total, 256), 256, 0, pz_stream(stream)>>>((const float*)w, (float*)workspace, g.Kg, g.Cg, RS, total);

@@ -172,11 +172,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
 		: "memory");
 	asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// fp32 -> tf32, round to nearest (ties away): the tensor core reads only the upper 19 bits of each 32-bit operand word, so
+// adding half a tf32 ulp is all that is needed (2 instructions; cvt.rna.tf32 is emulated with 3 on sm_100).  Inf / NaN
+// are left untouched.
 __device__ __forceinline__ uint32_t to_tf32(float x)
 {
-	uint32_t r;
-	asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-	return r;
+	const uint32_t u = __float_as_uint(x);
+	return fabsf(x) < INFINITY ? u + 0x1000u : u;
 }
 __device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
@@ -340,23 +342,24 @@ struct KProducer {
 // An element is addressed as  base[ rowpart + kpart ]  with
 //   "spatial" index (the side that holds (n, y, x)):  off = i0*s0 + (i1*a_h + c_h)*Wd + (i2*a_w + c_w)
 //   "tap" index     (the side that holds (c, r, s)):  off = c*cs + r*b_h*Wd + s*b_w,   tap t = r*S + s
-// and is valid iff the tap t is in bounds for that spatial position -- one bit of a per-position mask.
-// Tap entries are packed as (offset - tapmin) << 6 | t; t == INVALID_TAP marks an out-of-range index (its mask bit is
-// never set: the host picks the 64-bit mask whenever a filter has more than 31 taps).
+// and is valid iff tap t is in bounds for that spatial position -- one bit of a per-position mask.
+// Tap entries are packed as  (offset - tapmin) << SH | (TOP - t) : the validity test is then a left shift of the mask by
+// the low bits followed by a sign test (2 instructions).  t == TOP marks an out-of-range index: that mask bit is never
+// set because the host picks the 64-bit mask whenever a filter has more than 31 taps (63 at most).
 template <bool WIDE> struct TapMask;
 template <> struct TapMask<false> {
-	static constexpr uint32_t INVALID_TAP = 31u;    // narrow masks serve filters with at most 31 taps
+	static constexpr uint32_t TOP = 31u, SH = 5u;
 	uint32_t m;
 	__device__ __forceinline__ void clear() { m = 0; }
 	__device__ __forceinline__ void set(int t) { m |= 1u << t; }
-	__device__ __forceinline__ bool test(uint32_t t) const { return (m >> t) & 1u; }
+	__device__ __forceinline__ bool test(uint32_t ent) const { return (int)(m << (ent & 31u)) < 0; }
 };
 template <> struct TapMask<true> {
-	static constexpr uint32_t INVALID_TAP = 63u;
+	static constexpr uint32_t TOP = 63u, SH = 6u;
 	unsigned long long m;
 	__device__ __forceinline__ void clear() { m = 0; }
 	__device__ __forceinline__ void set(int t) { m |= 1ull << t; }
-	__device__ __forceinline__ bool test(uint32_t t) const { return (m >> t) & 1ull; }
+	__device__ __forceinline__ bool test(uint32_t ent) const { return (long long)(m << (ent & 63u)) < 0; }
 };
 
 __device__ __forceinline__ int tap_min(int nR, int nS, int bhW, int bw)
@@ -364,20 +367,29 @@ __device__ __forceinline__ int tap_min(int nR, int nS, int bhW, int bw)
 	return min(0, (nR - 1) * bhW) + min(0, (nS - 1) * bw);
 }
 
+__device__ __forceinline__ float ldg_off(const char* __restrict__ sb, uint32_t elem)
+{
+	return __ldg(reinterpret_cast<const float*>(sb + ((unsigned long long)elem << 2)));
+}
+
 // rows = spatial positions (MN-contiguous in memory), k = (c, r, s).  fprop, stride-1 dgrad, MN-contiguous dense.
 // Thread owns one tile row and ROWS/32 16-byte chunks (4 consecutive k) per stage; loads coalesce across lanes.
+// Each stage, lane l decodes k = kb*32 + l once into a 128-byte per-warp smem table that all lanes read back as uint4.
 template <int ROWS, bool WIDE>
 struct MnTapProducer {
+	using TM = TapMask<WIDE>;
 	static constexpr int NCH = ROWS / 32;
 	static constexpr int CSTEP = NPROD / ROWS;
-	TapMask<WIDE> mask;
+	TM mask;
 	int poff, row_local, chunk0, lane;
+	uint32_t tab;
 	float v[NCH][4];
 
-	__device__ __forceinline__ void init(const Operand& op, int tile_row0, int warp, int lane_, uint32_t)
+	__device__ __forceinline__ void init(const Operand& op, int tile_row0, int warp, int lane_, uint32_t table)
 	{
 		const int t = warp * 32 + lane_;
 		lane = lane_;
+		tab = table + warp * 128;
 		row_local = t % ROWS;
 		chunk0 = (warp * 32) / ROWS;
 		const int row = tile_row0 + row_local;
@@ -396,29 +408,29 @@ struct MnTapProducer {
 	}
 	__device__ __forceinline__ void load(const Operand& op, const float* __restrict__ base, int kb)
 	{
-		// lane l decodes k = kb*32 + l once; the 4 k of a chunk are then fetched from the owning lanes by shuffle.
-		// Offsets are kept relative to the first channel of the stage so that they fit the 26-bit entry field.
+		// offsets are kept relative to the first channel of the stage so that they fit the entry's offset field
 		const int k = kb * BK + lane;
 		const uint32_t cfirst = fdiv((uint32_t)(kb * BK), op.kd12);
-		const float* __restrict__ sbase = base + (long long)cfirst * op.ks0 + poff;
-		uint32_t entry = TapMask<WIDE>::INVALID_TAP;
+		const char* __restrict__ sb = reinterpret_cast<const char*>(base + (long long)cfirst * op.ks0 + poff);
+		uint32_t entry = 0u;                         // tap TOP, never valid
 		if (k < op.kdim) {
 			const uint32_t c = fdiv((uint32_t)k, op.kd12);
 			const uint32_t t = (uint32_t)k - c * op.kd12.d;
 			const uint32_t r = fdiv(t, op.kd2);
 			const uint32_t s = t - r * op.kd2.d;
 			const int koff = (int)(c - cfirst) * op.ks0 + (int)r * op.bh * op.Wd + (int)s * op.bw - tap_min(op.R, op.S, op.bh * op.Wd, op.bw);
-			entry = ((uint32_t)koff << 6) | t;
+			entry = ((uint32_t)koff << TM::SH) | (TM::TOP - t);
 		}
+		__syncwarp();
+		sts32(tab + lane * 4, entry);
+		__syncwarp();
 		#pragma unroll
 		for (int i = 0; i < NCH; i++) {
-			const int chunk = chunk0 + i * CSTEP;
+			uint32_t e4[4];
+			asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+						 : "=r"(e4[0]), "=r"(e4[1]), "=r"(e4[2]), "=r"(e4[3]) : "r"(tab + (chunk0 + i * CSTEP) * 16));
 			#pragma unroll
-			for (int e = 0; e < 4; e++) {
-				const uint32_t ent = __shfl_sync(0xffffffffu, entry, chunk * 4 + e);
-				const bool ok = mask.test(ent & 63u);
-				v[i][e] = ok ? __ldg(sbase + (ent >> 6)) : 0.0f;
-			}
+			for (int e = 0; e < 4; e++) v[i][e] = mask.test(e4[e]) ? ldg_off(sb, e4[e] >> TM::SH) : 0.0f;
 		}
 	}
 	__device__ __forceinline__ void store(uint32_t tile)
@@ -436,6 +448,7 @@ struct MnTapProducer {
 // lane = k; warp w covers tile rows w, w+8, ...; the per-row tap entries live in a small smem table.
 template <int ROWS, bool WIDE>
 struct KTapProducer {
+	using TM = TapMask<WIDE>;
 	static constexpr int NR = ROWS / NPROD_WARPS;
 	int warp, lane;
 	uint32_t table;
@@ -449,14 +462,14 @@ struct KTapProducer {
 		const int t = warp * 32 + lane;
 		if (t < ROWS) {
 			const int row = tile_row0 + t;
-			uint32_t entry = TapMask<WIDE>::INVALID_TAP;
+			uint32_t entry = 0u;
 			if (row < op.rows) {
 				const uint32_t c = fdiv((uint32_t)row, op.rd12);
 				const uint32_t tp = (uint32_t)row - c * op.rd12.d;
 				const uint32_t r = fdiv(tp, op.rd2);
 				const uint32_t s = tp - r * op.rd2.d;
 				const int roff = (int)c * op.rs0 + (int)r * op.ah * op.Wd + (int)s * op.aw - tap_min(op.R, op.S, op.ah * op.Wd, op.aw);
-				entry = ((uint32_t)roff << 6) | tp;
+				entry = ((uint32_t)roff << TM::SH) | (TM::TOP - tp);
 			}
 			sts32(table + t * 4, entry);
 		}
@@ -464,12 +477,13 @@ struct KTapProducer {
 	__device__ __forceinline__ void load(const Operand& op, const float* __restrict__ base, int kb)
 	{
 		const int k = kb * BK + lane;
-		TapMask<WIDE> mask;
+		TM mask;
 		mask.clear();
 		int k0, k1, k2;
 		split3((uint32_t)(k < op.kdim ? k : 0), op.kd12, op.kd2, k0, k1, k2);
 		const int hk = k1 * op.bh + op.ch, wk = k2 * op.bw + op.cw;
-		const int poff = k0 * op.ks0 + hk * op.Wd + wk + tap_min(op.R, op.S, op.ah * op.Wd, op.aw);
+		const char* __restrict__ sb = reinterpret_cast<const char*>(
+			base + ((long long)k0 * op.ks0 + hk * op.Wd + wk + tap_min(op.R, op.S, op.ah * op.Wd, op.aw)));
 		if (k < op.kdim) {
 			for (int r = 0; r < op.R; r++) {
 				const bool okh = (unsigned)(hk + r * op.ah) < (unsigned)op.H;
@@ -481,8 +495,7 @@ struct KTapProducer {
 		for (int i = 0; i < NR; i++) {
 			uint32_t ent;
 			asm volatile("ld.shared.b32 %0, [%1];" : "=r"(ent) : "r"(table + (warp + i * NPROD_WARPS) * 4));
-			const bool ok = mask.test(ent & 63u);
-			v[i] = ok ? __ldg(base + poff + (int)(ent >> 6)) : 0.0f;
+			v[i] = mask.test(ent) ? ldg_off(sb, ent >> TM::SH) : 0.0f;
 		}
 	}
 	__device__ __forceinline__ void store(uint32_t tile)
@@ -495,32 +508,38 @@ struct KTapProducer {
 
 // dense K-contiguous rows: element (row, k) at base[row*rs0 + (k / D)*ks0 + k % D]  (D = kd12.d, 0 = no batch split).
 // weights [K][C*R*S], transposed-B GEMM operands, and wgrad's dy operand ([ko][(n, pq)], D = PQ).
+// lane = k; warp w covers tile rows w, w+8, ... by stepping one 64-bit pointer.
 template <int ROWS>
 struct KDenseProducer {
 	static constexpr int NR = ROWS / NPROD_WARPS;
-	int warp, lane, row0;
+	int warp, lane, nvalid;
+	long long rowoff0, step;
 	float v[NR];
 
-	__device__ __forceinline__ void init(const Operand&, int tile_row0, int warp_, int lane_, uint32_t)
+	__device__ __forceinline__ void init(const Operand& op, int tile_row0, int warp_, int lane_, uint32_t)
 	{
 		warp = warp_;
 		lane = lane_;
-		row0 = tile_row0 + warp_;
+		const int row0 = tile_row0 + warp_;
+		rowoff0 = (long long)row0 * op.rs0;
+		step = (long long)NPROD_WARPS * op.rs0 * 4;
+		const int left = op.rows - row0;
+		nvalid = left <= 0 ? 0 : min(NR, (left + NPROD_WARPS - 1) / NPROD_WARPS);
 	}
 	__device__ __forceinline__ void load(const Operand& op, const float* __restrict__ base, int kb)
 	{
 		const int k = kb * BK + lane;
-		const bool kvalid = k < op.kdim;
 		int koff = k;
 		if (op.kd12.d > 1) {
 			const uint32_t k0 = fdiv((uint32_t)k, op.kd12);
 			koff = (int)k0 * op.ks0 + (int)((uint32_t)k - k0 * op.kd12.d);
 		}
-		const float* p = base + koff;
+		const int n = k < op.kdim ? nvalid : 0;
+		const char* __restrict__ p = reinterpret_cast<const char*>(base + rowoff0 + koff);
 		#pragma unroll
 		for (int i = 0; i < NR; i++) {
-			const int row = row0 + i * NPROD_WARPS;
-			v[i] = (kvalid && row < op.rows) ? __ldg(p + (long long)row * op.rs0) : 0.0f;
+			v[i] = i < n ? __ldg(reinterpret_cast<const float*>(p)) : 0.0f;
+			p += step;
 		}
 	}
 	__device__ __forceinline__ void store(uint32_t tile)

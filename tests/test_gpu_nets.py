@@ -62,7 +62,9 @@ def check_leaf(M, mod, failures, tol_tc=1e-3, tol=1e-5):
 		y, mu, inv, _, _ = ops.batchnorm_train(x, mod.scale.get().ravel(), mod.bias.get().ravel(), np.zeros(mod.maps), np.ones(mod.maps),
 											   mod.epsilon, 1.0)
 		expect("fwd", mod.data.get(), y, 2e-5)
-		expect("savemean", mod.savemean.get().ravel(), mu, tol)
+		# the mean is accurate relative to the channel's spread (fp32 accumulation), not relative to max |mean| (which is ~0)
+		if not float(np.abs((mod.savemean.get().ravel() - mu) * inv).max()) < 2e-5:
+			failures.append("%s savemean off by more than 2e-5 std" % name)
 		expect("saveinvvar", mod.saveinvvar.get().ravel(), inv, tol)
 		if g is not None:
 			dx, dscale, dbias = ops.batchnorm_bwd(x, g.get(), mod.scale.get().ravel(), mu, inv)
