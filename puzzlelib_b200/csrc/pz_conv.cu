@@ -79,37 +79,41 @@ void set_alg(GemmParams& p, const Geo& g)
 	p.alg_bytes = 4.0 * (x + y + w);
 }
 
-// wt[g][c][ko][rs] = w[g*Kg + ko][c][rs] : the filter with the reduction index (ko, r, s) contiguous
-__global__ void repack_filter_dgrad(const float* __restrict__ w, float* __restrict__ wt, int Kg, int Cg, int RS, long long total)
+// Prepared filters (the TMA-fetched operand of fprop / dgrad): fp32 rows of `kpad` (multiple of 32) elements, K-major,
+// rounded to tf32 (the tensor core would otherwise truncate) and zero-padded, in the library scratch.
+
+// fprop: wp[ko_total][k] = w[ko_total][k], k = (c, r, s) < kdim
+__global__ void prep_filter_fprop(const float* __restrict__ w, float* __restrict__ wp, int kdim, int kpad, long long total)
 {
 	long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= total) return;
-	int rs = (int)(i % RS);
-	long long t = i / RS;
-	int ko = (int)(t % Kg);
-	t /= Kg;
-	int c = (int)(t % Cg);
-	int g = (int)(t / Cg);
-	wt[i] = w[(((long long)g * Kg + ko) * Cg + c) * RS + rs];
+	const int k = (int)(i % kpad);
+	const long long row = i / kpad;
+	wp[i] = k < kdim ? __uint_as_float(to_tf32(w[row * kdim + k])) : 0.0f;
 }
 
-// sub-filter of one output-parity class of a strided transposed convolution:
-// wt[g][c][ko][r'][s'] = w[g*Kg + ko][c][r0 + sh*r'][s0 + sw*s']
-__global__ void repack_filter_dgrad_class(const float* __restrict__ w, float* __restrict__ wt, int Kg, int Cg, int R, int S, int r0, int s0,
-										   int sh, int sw, int Rc, int Sc, long long total)
+// dgrad: wt[g*Cg + c][(ko, r', s')] = w[g*Kg + ko][c][r0 + sh*r'][s0 + sw*s'] -- the sub-filter of one output-parity class of
+// a strided transposed convolution (r0 = s0 = 0, sh = sw = 1, Rc = R, Sc = S: the whole filter, stride-1 dgrad)
+__global__ void prep_filter_dgrad(const float* __restrict__ w, float* __restrict__ wt, int Kg, int Cg, int R, int S, int r0, int s0,
+								   int sh, int sw, int Rc, int Sc, int kpad, long long total)
 {
 	long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= total) return;
-	int sc = (int)(i % Sc);
-	long long t = i / Sc;
-	int rc = (int)(t % Rc);
-	t /= Rc;
-	int ko = (int)(t % Kg);
-	t /= Kg;
-	int c = (int)(t % Cg);
-	int g = (int)(t / Cg);
-	wt[i] = w[((((long long)g * Kg + ko) * Cg + c) * R + (r0 + sh * rc)) * S + (s0 + sw * sc)];
+	int k = (int)(i % kpad);
+	const int row = (int)(i / kpad);
+	float v = 0.0f;
+	if (k < Kg * Rc * Sc) {
+		const int sc = k % Sc;
+		k /= Sc;
+		const int rc = k % Rc;
+		const int ko = k / Rc;
+		const int c = row % Cg, g = row / Cg;
+		v = __uint_as_float(to_tf32(w[((((long long)g * Kg + ko) * Cg + c) * R + (r0 + sh * rc)) * S + (s0 + sw * sc)]));
+	}
+	wt[i] = v;
 }
+
+inline int round_up32(int v) { return (v + 31) & ~31; }
 
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) bias_grad_kernel(const float* __restrict__ t, float* __restrict__ db, long long N,
@@ -167,8 +171,16 @@ int pz_conv2d_fprop(int dtype, const pz_conv2d_desc* d, const void* x, const voi
 	A.R = g.R; A.S = g.S;
 	A.group_stride = (long long)g.Cg * HW;
 
-	p.B = dense_k((const float*)w, g.Kg, g.Cg * RS, (long long)g.Cg * RS);
-	p.B.group_stride = (long long)g.Kg * g.Cg * RS;
+	// filter: prepared copy [K][kpad], fetched by TMA
+	const int kdim = g.Cg * RS, kpad = round_up32(kdim);
+	const long long wtotal = (long long)g.K * kpad;
+	float* wp = scratch((size_t)wtotal * sizeof(float));
+	if (!wp) { pz_set_error(PZ_ERR_MEMORY, "conv2d fprop: cannot allocate %lld bytes of filter scratch", wtotal * 4); return PZ_ERR_MEMORY; }
+	prep_filter_fprop<<<(unsigned)pz_cdiv(wtotal, 256), 256, 0, pz_stream(stream)>>>((const float*)w, wp, kdim, kpad, wtotal);
+	pz_count_launch(1);
+	PZ_LAUNCH_CHECK();
+	const TmaSource tsrc{wp, g.K, kpad};
+	p.tma_rows_per_group = g.Kg;
 
 	Epilogue& E = p.E;
 	E.out = (float*)y;
@@ -188,15 +200,16 @@ int pz_conv2d_fprop(int dtype, const pz_conv2d_desc* d, const void* x, const voi
 	p.kb_per_split = p.kblocks;
 	set_alg(p, g);
 	const bool fast = tap_entries_fit(34ll * HW, g);
-	return launch(p, pick_bn(g.Kg), fast ? MODE_MN_TAP : MODE_MN_GENERAL, MODE_K_DENSE, fast && RS > 31, g.G, pz_stream(stream));
+	const int bn = pick_bn(g.Kg, (long long)g.N * PQ, p.kblocks, g.G, 256);
+	return launch(p, bn, fast ? MODE_MN_TAP : MODE_MN_GENERAL, MODE_TMA, fast && RS > 31, g.G, &tsrc, pz_stream(stream));
 }
 
+// the dgrad filter repack lives in the library's own scratch; callers need not supply a workspace any more
 size_t pz_conv2d_dgrad_workspace(int dtype, const pz_conv2d_desc* d)
 {
 	(void)dtype;
-	if (!d) return 0;
-	if (d->R == 1 && d->S == 1 && d->pad_h == 0 && d->pad_w == 0 && d->stride_h == 1 && d->stride_w == 1) return 0;
-	return (size_t)d->K * (d->C / (d->groups > 0 ? d->groups : 1)) * d->R * d->S * sizeof(float);
+	(void)d;
+	return 0;
 }
 
 int pz_conv2d_dgrad(int dtype, const pz_conv2d_desc* d, const void* dy, const void* w, const void* bias, void* dx,
@@ -209,9 +222,7 @@ int pz_conv2d_dgrad(int dtype, const pz_conv2d_desc* d, const void* dy, const vo
 	const bool is1x1 = g.R == 1 && g.S == 1;
 	const bool strided = g.sh > 1 || g.sw > 1;
 
-	GemmParams p{};
-	Operand& A = p.A;
-	Epilogue& E = p.E;
+	Epilogue E{};
 	E.out = (float*)dx;
 	E.bias = (const float*)bias;
 	E.alpha = 1.0f; E.beta = 0.0f;
@@ -221,49 +232,84 @@ int pz_conv2d_dgrad(int dtype, const pz_conv2d_desc* d, const void* dy, const vo
 	E.N = g.Cg;
 	E.group_stride = (long long)g.Cg * HW;
 	E.bias_group_stride = g.Cg;
-	p.splits = 1;
 
-	if (is1x1 && g.ph == 0 && g.pw == 0 && !(strided && bias)) {
-		// 1x1: dx[n,c,p*sh,q*sw] = sum_k dy[n,k,p,q] * w[k,c]; other positions of dx are zero.
-		if (strided) {
-			st = pz_memset8(dx, 0, (size_t)g.N * g.C * HW * 4, stream);
-			if (st != PZ_OK) return st;
+	(void)workspace;
+	(void)workspace_bytes;
+
+	// launches one stride-1 transposed-convolution problem over the sub-filter (r0 + sh*r', s0 + sw*s') whose outputs are the
+	// input-gradient positions (a_h + sh*h', a_w + sw*w'); the whole tensor for stride 1 (a = 0, sh = sw = 1).
+	// mode 0: parity class of a strided, un-dilated filter (fast tap producer); mode 1: stride 1, any dilation (fast tap
+	// producer); mode 2: any stride and dilation through the exact-division gather (csh = csw = 1, whole filter).
+	auto run_class = [&](float* wt, int a_h, int a_w, int r0, int s0, int csh, int csw, int Rc, int Sc, int Hc, int Wc, int mode) -> int {
+		const int kdim = g.Kg * Rc * Sc, kpad = round_up32(kdim);
+		const long long total = (long long)g.C * kpad;
+		prep_filter_dgrad<<<(unsigned)pz_cdiv(total, 256), 256, 0, pz_stream(stream)>>>((const float*)w, wt, g.Kg, g.Cg, g.R, g.S, r0, s0,
+																						csh, csw, Rc, Sc, kpad, total);
+		pz_count_launch(1);
+		PZ_LAUNCH_CHECK();
+
+		GemmParams q{};
+		Operand& QA = q.A;                 // rows (n, h', w') of the class, k (ko, r', s')
+		QA.ptr = (const float*)dy;
+		QA.rd12 = make_fastdiv(Hc * Wc); QA.rd2 = make_fastdiv(Wc);
+		QA.kd12 = make_fastdiv(Rc * Sc); QA.kd2 = make_fastdiv(Sc);
+		QA.rs0 = g.K * PQ; QA.ks0 = PQ;
+		QA.H = g.P; QA.W = g.Q; QA.Wd = g.Q;
+		if (mode == 0) {
+			QA.ah = 1; QA.bh = -1; QA.ch = (a_h + g.ph - r0) / csh;
+			QA.aw = 1; QA.bw = -1; QA.cw = (a_w + g.pw - s0) / csw;
+			QA.cdh = QA.cdw = 1;
+		} else {
+			// hh = (h + pad - r*dil) / stride when divisible (mode 1: stride 1)
+			QA.ah = 1; QA.bh = -g.dh; QA.ch = g.ph;
+			QA.aw = 1; QA.bw = -g.dw; QA.cw = g.pw;
+			QA.cdh = g.sh; QA.cdw = g.sw;
 		}
-		A.ptr = (const float*)dy;                 // rows (n, pq), k = ko
-		A.rd12 = make_fastdiv(PQ); A.rd2 = make_fastdiv(0);
-		A.kd12 = make_fastdiv(1); A.kd2 = make_fastdiv(0);
-		A.rs0 = g.K * PQ; A.ks0 = PQ;
-		A.ah = A.bh = A.ch = 0;
-		A.aw = 1; A.bw = 0; A.cw = 0;
-		A.H = 1; A.W = PQ; A.Wd = 0;
-		A.cdh = A.cdw = 1;
-		A.rows = g.N * PQ; A.kdim = g.Kg;
-		A.R = A.S = 1;
-		A.group_stride = (long long)g.Kg * PQ;
+		QA.rows = g.N * Hc * Wc; QA.kdim = kdim;
+		QA.R = Rc; QA.S = Sc;
+		QA.group_stride = (long long)g.Kg * PQ;
 
-		// filter element (row = c, k = ko) at w[(g*Kg + ko)*Cg + c]
-		p.B = dense_mn((const float*)w, g.Cg, g.Kg, g.Cg);
-		p.B.group_stride = (long long)g.Kg * g.Cg;
+		q.E = E;
+		q.E.out = (float*)dx + (long long)a_h * g.W + a_w;
+		q.E.md12 = make_fastdiv(Hc * Wc); q.E.md2 = make_fastdiv(Wc);
+		q.E.ms0 = g.C * HW; q.E.ms1 = csh * g.W; q.E.ms2 = csw;
+		q.E.M = g.N * Hc * Wc;
+		q.splits = 1;
+		q.kblocks = (int)pz_cdiv(kdim, BK);
+		q.kb_per_split = q.kblocks;
+		q.tma_rows_per_group = g.Cg;
+		q.alg_flops = 2.0 * (double)q.E.M * g.K * g.Cg * Rc * Sc / g.G;
+		q.alg_bytes = 4.0 * ((double)g.N * g.K * PQ / (csh * csw) + (double)g.K * g.Cg * Rc * Sc + (double)q.E.M * g.C);
+		const TmaSource tsrc{wt, g.C, kpad};
+		const int bn = pick_bn(g.Cg, q.E.M, q.kblocks, g.G, 256);
+		const bool cdiv = mode == 2 ? strided : Rc * Sc > 31;
+		return launch(q, bn, mode == 2 ? MODE_MN_GENERAL : MODE_MN_TAP, MODE_TMA, cdiv, g.G, &tsrc, pz_stream(stream));
+	};
 
-		E.md12 = make_fastdiv(PQ); E.md2 = make_fastdiv(g.Q);
-		E.ms0 = g.C * HW; E.ms1 = g.sh * g.W; E.ms2 = g.sw;
-		E.M = g.N * PQ;
-		p.kblocks = (int)pz_cdiv(A.kdim, BK);
-		p.kb_per_split = p.kblocks;
-		set_alg(p, g);
-		PZ_REQUIRE(34ll * PQ < (1ll << 26) && 34ll * g.Cg < (1ll << 26), "conv2d dgrad: tensor too large");
-		return launch(p, pick_bn(g.Cg), MODE_MN_TAP, MODE_MN_TAP, false, g.G, pz_stream(stream));
+	if (is1x1 && g.ph == 0 && g.pw == 0 && strided) {
+		// 1x1 strided: dx[n,c,p*sh,q*sw] = sum_k dy[n,k,p,q] * w[k,c]; all other positions of dx are zero (+ bias)
+		PZ_REQUIRE(bias == nullptr, "conv2d dgrad: bias with a strided 1x1 filter is not supported");
+		st = pz_memset8(dx, 0, (size_t)g.N * g.C * HW * 4, stream);
+		if (st != PZ_OK) return st;
+		float* wt = scratch((size_t)g.C * round_up32(g.Kg) * sizeof(float));
+		if (!wt) { pz_set_error(PZ_ERR_MEMORY, "conv2d dgrad: cannot allocate filter scratch"); return PZ_ERR_MEMORY; }
+		PZ_REQUIRE(tap_entries_fit(34ll * PQ, g), "conv2d dgrad: tensor too large");
+		return run_class(wt, 0, 0, 0, 0, g.sh, g.sw, 1, 1, g.P, g.Q, 0);
 	}
-
-	// general case: gather dy through the transposed-convolution index map
-	const size_t need = (size_t)g.K * g.Cg * RS * sizeof(float);
-	PZ_REQUIRE(workspace != nullptr && workspace_bytes >= need, "conv2d dgrad: workspace too small (%zu < %zu)", workspace_bytes, need);
 
 	if (strided && g.dh == 1 && g.dw == 1 && tap_entries_fit(34ll * PQ, g)) {
 		// A strided transposed convolution splits into sh*sw independent STRIDE-1 problems, one per parity class
 		// (h mod sh, w mod sw) of the input-gradient positions: only the taps r = r0 + sh*r' with r0 = (a_h + pad_h) mod sh
 		// can reach such a position.  No tap is ever evaluated on a zero, and each class runs on the fast tap producer.
-		float* wsp = (float*)workspace;
+		size_t need = 0;
+		for (int a_h = 0; a_h < g.sh && a_h < g.H; a_h++)
+			for (int a_w = 0; a_w < g.sw && a_w < g.W; a_w++) {
+				const int r0 = (a_h + g.ph) % g.sh, s0 = (a_w + g.pw) % g.sw;
+				const int Rc = r0 < g.R ? (g.R - r0 + g.sh - 1) / g.sh : 0, Sc = s0 < g.S ? (g.S - s0 + g.sw - 1) / g.sw : 0;
+				need += (size_t)g.C * round_up32(g.Kg * Rc * Sc) * sizeof(float);
+			}
+		float* wsp = scratch(need);
+		if (!wsp) { pz_set_error(PZ_ERR_MEMORY, "conv2d dgrad: cannot allocate %zu bytes of filter scratch", need); return PZ_ERR_MEMORY; }
 		bool zeroed = false;
 		for (int a_h = 0; a_h < g.sh && a_h < g.H; a_h++)
 			for (int a_w = 0; a_w < g.sw && a_w < g.W; a_w++) {
@@ -280,77 +326,19 @@ int pz_conv2d_dgrad(int dtype, const pz_conv2d_desc* d, const void* dy, const vo
 					}
 					continue;
 				}
-				const long long total = (long long)g.K * g.Cg * Rc * Sc;
-				repack_filter_dgrad_class<<<(unsigned)pz_cdiv(total, 256), 256, 0, pz_stream(stream)>>>(
-					(const float*)w, wsp, g.Kg, g.Cg, g.R, g.S, r0, s0, g.sh, g.sw, Rc, Sc, total);
-				pz_count_launch(1);
-				PZ_LAUNCH_CHECK();
-
-				GemmParams q{};
-				Operand& QA = q.A;                 // rows (n, h', w') of the class, k (ko, r', s')
-				QA.ptr = (const float*)dy;
-				QA.rd12 = make_fastdiv(Hc * Wc); QA.rd2 = make_fastdiv(Wc);
-				QA.kd12 = make_fastdiv(Rc * Sc); QA.kd2 = make_fastdiv(Sc);
-				QA.rs0 = g.K * PQ; QA.ks0 = PQ;
-				QA.ah = 1; QA.bh = -1; QA.ch = (a_h + g.ph - r0) / g.sh;
-				QA.aw = 1; QA.bw = -1; QA.cw = (a_w + g.pw - s0) / g.sw;
-				QA.H = g.P; QA.W = g.Q; QA.Wd = g.Q;
-				QA.cdh = QA.cdw = 1;
-				QA.rows = g.N * Hc * Wc; QA.kdim = g.Kg * Rc * Sc;
-				QA.R = Rc; QA.S = Sc;
-				QA.group_stride = (long long)g.Kg * PQ;
-
-				q.B = dense_k(wsp, g.Cg, g.Kg * Rc * Sc, (long long)g.Kg * Rc * Sc);
-				q.B.group_stride = (long long)g.Cg * g.Kg * Rc * Sc;
-
-				q.E = E;
-				q.E.out = (float*)dx + (long long)a_h * g.W + a_w;
-				q.E.md12 = make_fastdiv(Hc * Wc); q.E.md2 = make_fastdiv(Wc);
-				q.E.ms0 = g.C * HW; q.E.ms1 = g.sh * g.W; q.E.ms2 = g.sw;
-				q.E.M = g.N * Hc * Wc;
-				q.splits = 1;
-				q.kblocks = (int)pz_cdiv(QA.kdim, BK);
-				q.kb_per_split = q.kblocks;
-				q.alg_flops = 2.0 * (double)q.E.M * g.K * g.Cg * Rc * Sc / g.G * g.G;
-				q.alg_bytes = 4.0 * ((double)g.N * g.K * PQ / (g.sh * g.sw) + (double)total + (double)q.E.M * g.C);
-				st = launch(q, pick_bn(g.Cg), MODE_MN_TAP, MODE_K_DENSE, Rc * Sc > 31, g.G, pz_stream(stream));
+				st = run_class(wsp, a_h, a_w, r0, s0, g.sh, g.sw, Rc, Sc, Hc, Wc, 0);
 				if (st != PZ_OK) return st;
-				wsp += total;
+				wsp += (size_t)g.C * round_up32(g.Kg * Rc * Sc);
 			}
 		return PZ_OK;
 	}
 
 	{
-		long long total = (long long)g.K * g.Cg * RS;
-		repack_filter_dgrad<<<(unsigned)pz_cdiv(total, 256), 256, 0, pz_stream(stream)>>>((const float*)w, (float*)workspace, g.Kg, g.Cg, RS, total);
-		pz_count_launch(1);
-		PZ_LAUNCH_CHECK();
+		float* wt = scratch((size_t)g.C * round_up32(g.Kg * RS) * sizeof(float));
+		if (!wt) { pz_set_error(PZ_ERR_MEMORY, "conv2d dgrad: cannot allocate filter scratch"); return PZ_ERR_MEMORY; }
+		const bool tapmode = !strided && tap_entries_fit(34ll * PQ, g);
+		return run_class(wt, 0, 0, 0, 0, 1, 1, g.R, g.S, g.H, g.W, tapmode ? 1 : 2);
 	}
-
-	A.ptr = (const float*)dy;                     // rows (n,h,w), k (ko,r,s)
-	A.rd12 = make_fastdiv(HW); A.rd2 = make_fastdiv(g.W);
-	A.kd12 = make_fastdiv(RS); A.kd2 = make_fastdiv(g.S);
-	A.rs0 = g.K * PQ; A.ks0 = PQ;
-	A.ah = 1; A.bh = -g.dh; A.ch = g.ph;
-	A.aw = 1; A.bw = -g.dw; A.cw = g.pw;
-	A.H = g.P; A.W = g.Q; A.Wd = g.Q;
-	A.cdh = g.sh; A.cdw = g.sw;
-	A.rows = g.N * HW; A.kdim = g.Kg * RS;
-	A.R = g.R; A.S = g.S;
-	A.group_stride = (long long)g.Kg * PQ;
-
-	p.B = dense_k((const float*)workspace, g.Cg, g.Kg * RS, (long long)g.Kg * RS);
-	p.B.group_stride = (long long)g.Cg * g.Kg * RS;
-
-	E.md12 = make_fastdiv(HW); E.md2 = make_fastdiv(0);
-	E.ms0 = g.C * HW; E.ms1 = 0; E.ms2 = 1;
-	E.M = g.N * HW;
-	p.kblocks = (int)pz_cdiv(A.kdim, BK);
-	p.kb_per_split = p.kblocks;
-	set_alg(p, g);
-	if (!strided && tap_entries_fit(34ll * PQ, g))
-		return launch(p, pick_bn(g.Cg), MODE_MN_TAP, MODE_K_DENSE, RS > 31, g.G, pz_stream(stream));
-	return launch(p, pick_bn(g.Cg), MODE_MN_GENERAL, MODE_K_DENSE, strided, g.G, pz_stream(stream));
 }
 
 int pz_conv2d_wgrad(int dtype, const pz_conv2d_desc* d, const void* x, const void* dy, void* dw, float alpha, float beta,
@@ -402,7 +390,7 @@ int pz_conv2d_wgrad(int dtype, const pz_conv2d_desc* d, const void* x, const voi
 	E.bias_group_stride = 0;
 
 	p.kblocks = (int)pz_cdiv(A.kdim, BK);
-	const int bn = pick_bn(g.Kg);
+	const int bn = pick_bn(g.Kg, E.M, 8, g.G, 128);
 	set_splits(p, pz_cdiv(E.M, BM) * pz_cdiv(E.N, bn) * g.G, 8);
 	E.atomic = p.splits > 1;
 	if (E.atomic) {
@@ -411,7 +399,7 @@ int pz_conv2d_wgrad(int dtype, const pz_conv2d_desc* d, const void* x, const voi
 	}
 	set_alg(p, g);
 	const bool fast = tap_entries_fit((long long)g.Cg * HW, g);
-	return launch(p, bn, fast ? MODE_K_TAP : MODE_K_GENERAL, MODE_K_DENSE, fast && RS > 31, g.G, pz_stream(stream));
+	return launch(p, bn, fast ? MODE_K_TAP : MODE_K_GENERAL, MODE_K_DENSE, fast && RS > 31, g.G, nullptr, pz_stream(stream));
 }
 
 int pz_bias_grad(int dtype, const void* t, void* db, int64_t N, int64_t C, int64_t S, float alpha, float beta, void* stream)

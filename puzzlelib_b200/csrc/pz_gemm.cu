@@ -2,6 +2,8 @@
 // Replaces cublasGemmEx as used by CuBlas_Context_gemm (reference Cuda/Source/Libs/CuBlas.c:327-403).
 #include "pz_umma.cuh"
 
+#include <cstdlib>
+
 namespace pzumma {
 
 Operand dense_k(const float* ptr, int rows, int kdim, long long ld)
@@ -44,10 +46,44 @@ Operand dense_mn(const float* ptr, int rows, int kdim, long long ld)
 	return o;
 }
 
-int pick_bn(int n) { return n <= 64 ? 64 : 128; }
+// Tile width: the widest tile reads the gathered operand the fewest times, but few wide tiles leave SMs idle in the last
+// round of the persistent schedule.  Cost model (clock cycles per SM, rough): a k-block costs max(MMA, gather) and a tile
+// ends with a TMEM drain + stores; the launch takes ceil(units / SMs) rounds.
+int pick_bn(int n, long long m_rows, int kblocks, int groups, int max_bn)
+{
+	static const int forced = [] { const char* e = getenv("PZ_FORCE_BN"); return e ? atoi(e) : 0; }();
+	if (forced == 64 || forced == 128 || forced == 256) return forced <= max_bn ? forced : max_bn;
+	const long long sms = pz_num_sms();
+	int best = 64;
+	double best_cost = 1e300;
+	for (int bn = 64; bn <= max_bn; bn *= 2) {
+		const long long units = pz_cdiv(m_rows, BM) * pz_cdiv(n, bn) * groups;
+		const long long rounds = pz_cdiv(units, sms);
+		const double per_kb = 2.0 * bn > 320.0 ? 2.0 * bn : 320.0;
+		const double cost = (double)rounds * ((double)kblocks * per_kb + 10.0 * bn + 1500.0);
+		if (cost < best_cost * 0.97) { best_cost = cost; best = bn; }
+		if (bn >= n) break;
+	}
+	return best;
+}
+
+// library-owned scratch for prepared filters.  Use is stream-ordered: the prep kernel that writes it and the GEMM that reads
+// it are enqueued back to back on the caller's stream (the reference runs everything on the legacy default stream).
+float* scratch(size_t bytes)
+{
+	static float* buf = nullptr;
+	static size_t cap = 0;
+	if (bytes > cap) {
+		if (buf) { cudaDeviceSynchronize(); cudaFree(buf); buf = nullptr; cap = 0; }
+		size_t want = bytes < ((size_t)64 << 20) ? ((size_t)64 << 20) : bytes + (bytes >> 2);
+		if (cudaMalloc((void**)&buf, want) != cudaSuccess) { buf = nullptr; return nullptr; }
+		cap = want;
+	}
+	return buf;
+}
 
 template <int BN, int AM, int BMODE, bool CDIV>
-static int launch_inst(const GemmParams& p, dim3 grid, cudaStream_t stream)
+static int launch_inst(const GemmParams& p, const CUtensorMap& tmap, int grid, cudaStream_t stream)
 {
 	auto kern = umma_gemm_kernel<BN, AM, BMODE, CDIV>;
 	static bool configured = false;
@@ -57,35 +93,72 @@ static int launch_inst(const GemmParams& p, dim3 grid, cudaStream_t stream)
 	}
 	{
 		PzProfScope prof(PZ_PROF_GEMM, stream, p.alg_flops, p.alg_bytes);
-		kern<<<grid, NTHREADS, Cfg<BN>::SMEM_BYTES, stream>>>(p);
+		kern<<<grid, NTHREADS, Cfg<BN>::SMEM_BYTES, stream>>>(p, tmap);
 	}
 	pz_count_launch(1);
 	PZ_LAUNCH_CHECK();
 	return PZ_OK;
 }
 
-int launch(const GemmParams& p, int bn, int amode, int bmode, bool cdiv, int groups, cudaStream_t stream)
+int launch(GemmParams& p, int bn, int amode, int bmode, bool cdiv, int groups, const TmaSource* tma, cudaStream_t stream)
 {
 	const int M = p.E.M, N = p.E.N;
 	if (M <= 0 || N <= 0) return PZ_OK;
 	PZ_REQUIRE(p.kblocks > 0 && p.splits > 0 && p.kb_per_split > 0, "empty contraction");
 	PZ_REQUIRE((long long)(p.splits - 1) * p.kb_per_split < p.kblocks, "empty split");
-	dim3 grid((unsigned)pz_cdiv(N, bn), (unsigned)pz_cdiv(M, BM), (unsigned)(groups * p.splits));
-	PZ_REQUIRE(grid.y <= 65535 * 32 && grid.z <= 65535, "tile grid too large");
+	p.tiles_m = (int)pz_cdiv(M, BM);
+	p.tiles_n = (int)pz_cdiv(N, bn);
+	p.groups = groups;
+	const long long units = (long long)p.tiles_m * p.tiles_n * groups * p.splits;
+	PZ_REQUIRE(units < (1ll << 31), "tile grid too large");
+	const int grid = (int)(units < pz_num_sms() ? units : pz_num_sms());
+
+	alignas(64) CUtensorMap tmap;
+	memset(&tmap, 0, sizeof(tmap));
+	if (bmode == MODE_TMA) {
+		PZ_REQUIRE(tma != nullptr && tma->ptr != nullptr && ((uintptr_t)tma->ptr & 15) == 0 && tma->kpad % 4 == 0, "bad TMA source");
+		cuuint64_t dims[2] = {(cuuint64_t)tma->kpad, (cuuint64_t)tma->rows};
+		cuuint64_t strides[1] = {(cuuint64_t)tma->kpad * sizeof(float)};
+		cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)bn};
+		cuuint32_t estr[2] = {1, 1};
+		// resolved through the runtime so that the library has no link-time dependency on libcuda.so (it must load, and
+		// export its symbols, on a machine without a driver)
+		typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+									 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+									 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+		static EncodeFn encode = nullptr;
+		if (!encode) {
+			void* fn = nullptr;
+			cudaDriverEntryPointQueryResult qres;
+			PZ_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+			PZ_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled is not available in this driver");
+			encode = (EncodeFn)fn;
+		}
+		CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)tma->ptr, dims, strides, box, estr,
+											CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+											CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+		if (r != CUDA_SUCCESS) {
+			pz_set_error(PZ_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+			return PZ_ERR_CUDA;
+		}
+	}
 
 #define PZ_INST(BNV, AMV, BMV, CD)                                             \
 	if (bn == BNV && amode == AMV && bmode == BMV && cdiv == CD)               \
-		return launch_inst<BNV, AMV, BMV, CD>(p, grid, stream);
+		return launch_inst<BNV, AMV, BMV, CD>(p, tmap, grid, stream);
 #define PZ_INST_BN(AMV, BMV, CD) PZ_INST(64, AMV, BMV, CD) PZ_INST(128, AMV, BMV, CD)
-	PZ_INST_BN(MODE_MN_TAP, MODE_K_DENSE, false)       // fprop, stride-1 dgrad, GEMM NN
-	PZ_INST_BN(MODE_MN_TAP, MODE_K_DENSE, true)        //   ... with more than 31 taps (7x7)
-	PZ_INST_BN(MODE_MN_TAP, MODE_MN_TAP, false)        // 1x1 dgrad, GEMM TN
+#define PZ_INST_BN3(AMV, BMV, CD) PZ_INST_BN(AMV, BMV, CD) PZ_INST(256, AMV, BMV, CD)
+	PZ_INST_BN3(MODE_MN_TAP, MODE_TMA, false)          // fprop, dgrad (filter by TMA)
+	PZ_INST_BN3(MODE_MN_TAP, MODE_TMA, true)           //   ... with more than 31 taps (7x7)
+	PZ_INST_BN3(MODE_MN_GENERAL, MODE_TMA, false)      // fallback: offsets too large for the packed tap entries
+	PZ_INST_BN3(MODE_MN_GENERAL, MODE_TMA, true)       // strided dgrad with dilation (exact-division gather)
+	PZ_INST_BN(MODE_MN_TAP, MODE_K_DENSE, false)       // GEMM NN
+	PZ_INST_BN(MODE_MN_TAP, MODE_MN_TAP, false)        // GEMM TN
 	PZ_INST_BN(MODE_K_DENSE, MODE_K_DENSE, false)      // GEMM NT
 	PZ_INST_BN(MODE_K_TAP, MODE_K_DENSE, false)        // wgrad
 	PZ_INST_BN(MODE_K_TAP, MODE_K_DENSE, true)         //   ... with more than 31 taps
-	PZ_INST_BN(MODE_MN_GENERAL, MODE_K_DENSE, false)   // fallback: offsets too large for the packed tap entries
-	PZ_INST_BN(MODE_MN_GENERAL, MODE_K_DENSE, true)    // strided dgrad (exact-division gather)
 	PZ_INST_BN(MODE_K_GENERAL, MODE_K_DENSE, false)    // fallback for wgrad
+#undef PZ_INST_BN3
 #undef PZ_INST_BN
 #undef PZ_INST
 	pz_set_error(PZ_ERR_UNSUPPORTED, "no GEMM instantiation for bn=%d amode=%d bmode=%d cdiv=%d", bn, amode, bmode, (int)cdiv);
@@ -170,7 +243,7 @@ extern "C" int pz_gemm(int dtype, const void* A, const void* B, void* C, int64_t
 	p.kblocks = (int)pz_cdiv(K, BK);
 	p.alg_flops = 2.0 * (double)M * (double)N * (double)K;
 	p.alg_bytes = 4.0 * ((double)M * K + (double)K * N + (double)M * N * (beta != 0.0f ? 2.0 : 1.0));
-	const int bn = pick_bn((int)M);
+	const int bn = pick_bn((int)M, N, p.kblocks, 1, 128);
 	const long long tiles = pz_cdiv(N, BM) * pz_cdiv(M, bn);
 	int splits = 1;
 	if (tiles < pz_num_sms() && p.kblocks >= 16) {
@@ -197,5 +270,5 @@ extern "C" int pz_gemm(int dtype, const void* A, const void* B, void* C, int64_t
 			}
 		}
 	}
-	return launch(p, bn, amode, bmode, false, 1, pz_stream(stream));
+	return launch(p, bn, amode, bmode, false, 1, nullptr, pz_stream(stream));
 }

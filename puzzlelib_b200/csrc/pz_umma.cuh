@@ -4,17 +4,24 @@
 // D[M x N] (+)= A[M x K] * B[N x K]^T with fp32 storage, TF32 tensor-core math, fp32 accumulation in TMEM.
 //
 // B200 design
-//   * one CTA = one 128 x BN output tile; accumulator lives in TMEM (BN fp32 columns x 128 lanes);
-//     tcgen05.mma.cta_group::1.kind::tf32, M=128, N=BN, K=8 per instruction, issued by ONE thread;
+//   * PERSISTENT kernel, one CTA per SM, static round-robin schedule over 128 x BN output tiles (BN = 64 / 128 / 256);
+//     accumulators live in TMEM, DOUBLE-BUFFERED (2 x BN fp32 columns x 128 lanes) so that the epilogue of tile i
+//     overlaps the mainloop of tile i+1; tcgen05.mma.cta_group::1.kind::tf32, M=128, N=BN, K=8 per instruction,
+//     issued by ONE thread;
 //   * operands are staged in shared memory as K-major tiles of 32 floats (128-byte rows) in the canonical
 //     SWIZZLE_128B layout (8-row x 128-byte atoms, 16-byte chunk index XOR row%8) - the same layout a TMA
 //     SWIZZLE_128B box produces, so a TMA producer can replace a gather producer tile by tile;
-//   * 8 producer warps gather both operands straight from the reference's NCHW / row-major tensors
-//     (no im2col buffer, no NHWC shadow copy), round fp32 -> tf32 with cvt.rna (tcgen05 itself would
-//     truncate, which biases every product by ~ -2^-11) and write the swizzled tile; 1 warp issues MMAs;
-//     a ring of mbarriers (full: 8 warp arrivals, empty: tcgen05.commit) pipelines STAGES tiles;
-//   * the same 8 warps then run the epilogue: tcgen05.ld 32 lanes x 32 columns, alpha/beta/bias, coalesced
-//     stores (TMEM lanes are always mapped to the contiguous dimension of the output) or red.add for split-K.
+//   * warp roles: 16 producer warps | 1 MMA-issuer warp | 4 epilogue warps (672 threads, <= 96 registers each);
+//   * the producer warps gather the activation operand straight from the reference's NCHW / row-major tensors
+//     (no im2col buffer, no NHWC shadow copy), round fp32 -> tf32 (tcgen05 itself would truncate, which biases
+//     every product by ~ -2^-11) and write the swizzled tile.  Loads are software-pipelined through a ring of
+//     PF register buffers, so PF k-blocks of global loads are in flight per thread while older ones are stored;
+//   * the filter operand of fprop / dgrad is pre-rounded + zero-padded by a tiny prep kernel and then fetched by
+//     TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B box of 32 floats x BN rows) - no thread instructions at all;
+//   * a ring of mbarriers (full: 16 warp arrivals [+ TMA transaction bytes], empty: tcgen05.commit) pipelines
+//     4 - 8 smem stages (192 KB); accum-full / accum-empty barriers hand TMEM buffers to the epilogue warps;
+//   * epilogue warps: tcgen05.ld 32 lanes x 32 columns, alpha/beta/bias, coalesced stores (TMEM lanes are always
+//     mapped to the contiguous dimension of the output) or red.add for split-K.
 //
 // An operand is described by `Operand`: element (row, k) lives at
 //     ptr[ r0*rs0 + k0*ks0 + hh*Wd + ww ],  (r0,r1,r2) = split(row), (k0,k1,k2) = split(k),
@@ -26,13 +33,16 @@
 
 #include "pz_common.h"
 
+#include <cuda.h>
+
 namespace pzumma {
 
 constexpr int BM = 128;          // tile rows  = TMEM lanes
 constexpr int BK = 32;           // floats per k-block = one 128-byte swizzle row
-constexpr int NPROD_WARPS = 8;
+constexpr int NPROD_WARPS = 16;
 constexpr int NPROD = NPROD_WARPS * 32;
-constexpr int NTHREADS = NPROD + 32;
+constexpr int NEPI_WARPS = 4;
+constexpr int NTHREADS = NPROD + 32 + NEPI_WARPS * 32;
 constexpr int INVALID = -(1 << 28);
 
 struct FastDiv {
@@ -70,7 +80,7 @@ __device__ __forceinline__ void split3(uint32_t x, const FastDiv& d12, const Fas
 // MN_TAP / K_TAP / K_DENSE are the fast paths: per-row (or per-k) base offsets and tap-validity bit masks are
 // computed once, the per-element work is one predicated load + one tf32 rounding.
 enum { MODE_K_GENERAL = 0, MODE_K_SIMPLE = 1, MODE_MN_GENERAL = 2, MODE_MN_SIMPLE = 3, MODE_MN_TAP = 4, MODE_K_TAP = 5,
-	   MODE_K_DENSE = 6 };
+	   MODE_K_DENSE = 6, MODE_TMA = 7 };
 
 struct Operand {
 	const float* ptr;
@@ -102,8 +112,10 @@ struct GemmParams {
 	Operand A, B;
 	Epilogue E;
 	int kblocks;                 // ceil(K / 32)
-	int splits;                  // split-K factor (grid.z = groups * splits)
+	int splits;                  // split-K factor
 	int kb_per_split;
+	int tiles_m, tiles_n, groups; // tile grid; total work units = tiles_m * tiles_n * groups * splits
+	int tma_rows_per_group;      // MODE_TMA: row offset of group g in the prepared filter = g * tma_rows_per_group
 	double alg_flops, alg_bytes; // host-side bookkeeping for the profiler (algorithmic work of this launch)
 };
 
@@ -158,27 +170,33 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
 		::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
 		: "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
+constexpr int EPI_COLS = 16;     // accumulator columns per tcgen05.ld (two loads in flight: 32 registers)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16])
 {
 	asm volatile(
-		"tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-		"{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-		"%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+		"tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+		"{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
 		: "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-		  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-		  "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-		  "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+		  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
 		: "r"(taddr)
 		: "memory");
-	asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// tcgen05.wait::ld with the destination registers as in/out operands, so that no use of them can be scheduled above the wait
+__device__ __forceinline__ void tmem_wait_ld(uint32_t (&v)[16])
+{
+	asm volatile(
+		"tcgen05.wait::ld.sync.aligned;"
+		: "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+		  "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+		:
+		: "memory");
 }
 // fp32 -> tf32, round to nearest (ties away): the tensor core reads only the upper 19 bits of each 32-bit operand word, so
-// adding half a tf32 ulp is all that is needed (2 instructions; cvt.rna.tf32 is emulated with 3 on sm_100).  Inf / NaN
-// are left untouched.
+// adding half a tf32 ulp is all that is needed (1 instruction; cvt.rna.tf32 is emulated with 3 on sm_100).  Finite values
+// round correctly (including overflow to Inf); an Inf input becomes a NaN (its result would be Inf or NaN anyway).
 __device__ __forceinline__ uint32_t to_tf32(float x)
 {
-	const uint32_t u = __float_as_uint(x);
-	return fabsf(x) < INFINITY ? u + 0x1000u : u;
+	return __float_as_uint(x) + 0x1000u;
 }
 __device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
@@ -261,11 +279,11 @@ __device__ __forceinline__ float fetch(const Operand& op, const float* __restric
 // MN-contiguous producer: thread owns one tile row (kept in registers) and ROWS/32 16-byte chunks per stage.
 template <int ROWS, bool SIMPLE, bool CDIV>
 struct MnProducer {
-	static constexpr int NCH = ROWS / 32;            // chunks per thread per stage
+	static constexpr int NCH = 8 * ROWS / NPROD;     // 16-byte chunks per thread per stage (8 chunks per 128-byte row)
 	static constexpr int CSTEP = NPROD / ROWS;       // chunk stride between a thread's chunks
+	static constexpr int NV = NCH * 4;               // values per thread per stage
 	RowInfo ri;
 	int row_local, chunk0;
-	float v[NCH][4];
 
 	__device__ __forceinline__ void init(const Operand& op, int tile_row0, int warp, int lane, uint32_t)
 	{
@@ -274,7 +292,7 @@ struct MnProducer {
 		chunk0 = (warp * 32) / ROWS;                 // warp-uniform
 		ri = make_rowinfo(op, tile_row0 + row_local);
 	}
-	__device__ __forceinline__ void load(const Operand& op, const float* __restrict__ base, int kb)
+	__device__ __forceinline__ void load(const Operand& op, const float* __restrict__ base, int kb, float (&v)[NV])
 	{
 		#pragma unroll
 		for (int i = 0; i < NCH; i++) {
@@ -282,17 +300,17 @@ struct MnProducer {
 			#pragma unroll
 			for (int e = 0; e < 4; e++) {
 				KInfo ki = make_kinfo(op, kc + e);
-				v[i][e] = fetch<SIMPLE, CDIV>(op, base, ri, ki);
+				v[i * 4 + e] = fetch<SIMPLE, CDIV>(op, base, ri, ki);
 			}
 		}
 	}
-	__device__ __forceinline__ void store(uint32_t tile)
+	__device__ __forceinline__ void store(uint32_t tile, const float (&v)[NV])
 	{
 		#pragma unroll
 		for (int i = 0; i < NCH; i++) {
 			int chunk = chunk0 + i * CSTEP;
 			uint32_t addr = tile + row_local * 128 + ((chunk ^ (row_local & 7)) << 4);
-			sts128(addr, to_tf32(v[i][0]), to_tf32(v[i][1]), to_tf32(v[i][2]), to_tf32(v[i][3]));
+			sts128(addr, to_tf32(v[i * 4]), to_tf32(v[i * 4 + 1]), to_tf32(v[i * 4 + 2]), to_tf32(v[i * 4 + 3]));
 		}
 	}
 };
@@ -301,9 +319,9 @@ struct MnProducer {
 template <int ROWS, bool SIMPLE>
 struct KProducer {
 	static constexpr int NR = ROWS / NPROD_WARPS;    // rows per warp per stage
+	static constexpr int NV = NR;
 	int warp, lane;
 	uint32_t rowinfo_smem;                           // smem table of RowInfo[ROWS]
-	float v[NR];
 
 	__device__ __forceinline__ void init(const Operand& op, int tile_row0, int warp_, int lane_, uint32_t table)
 	{
@@ -316,7 +334,7 @@ struct KProducer {
 			sts128(table + t * 16, (uint32_t)ri.rbase, (uint32_t)ri.hr, (uint32_t)ri.wr, (uint32_t)ri.valid);
 		}
 	}
-	__device__ __forceinline__ void load(const Operand& op, const float* __restrict__ base, int kb)
+	__device__ __forceinline__ void load(const Operand& op, const float* __restrict__ base, int kb, float (&v)[NV])
 	{
 		KInfo ki = make_kinfo(op, kb * BK + lane);
 		#pragma unroll
@@ -328,7 +346,7 @@ struct KProducer {
 			v[i] = fetch<SIMPLE, false>(op, base, ri, ki);
 		}
 	}
-	__device__ __forceinline__ void store(uint32_t tile)
+	__device__ __forceinline__ void store(uint32_t tile, const float (&v)[NV])
 	{
 		// row & 7 == warp & 7 for every row of this warp, so the swizzled column offset is a thread constant
 		uint32_t col = ((((uint32_t)lane >> 2) ^ ((uint32_t)warp & 7)) << 4) | (((uint32_t)lane & 3) << 2);
@@ -378,12 +396,12 @@ __device__ __forceinline__ float ldg_off(const char* __restrict__ sb, uint32_t e
 template <int ROWS, bool WIDE>
 struct MnTapProducer {
 	using TM = TapMask<WIDE>;
-	static constexpr int NCH = ROWS / 32;
+	static constexpr int NCH = 8 * ROWS / NPROD;
 	static constexpr int CSTEP = NPROD / ROWS;
+	static constexpr int NV = NCH * 4;
 	TM mask;
 	int poff, row_local, chunk0, lane;
 	uint32_t tab;
-	float v[NCH][4];
 
 	__device__ __forceinline__ void init(const Operand& op, int tile_row0, int warp, int lane_, uint32_t table)
 	{
@@ -406,7 +424,7 @@ struct MnTapProducer {
 			}
 		}
 	}
-	__device__ __forceinline__ void load(const Operand& op, const float* __restrict__ base, int kb)
+	__device__ __forceinline__ void load(const Operand& op, const float* __restrict__ base, int kb, float (&v)[NV])
 	{
 		// offsets are kept relative to the first channel of the stage so that they fit the entry's offset field
 		const int k = kb * BK + lane;
@@ -430,16 +448,16 @@ struct MnTapProducer {
 			asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
 						 : "=r"(e4[0]), "=r"(e4[1]), "=r"(e4[2]), "=r"(e4[3]) : "r"(tab + (chunk0 + i * CSTEP) * 16));
 			#pragma unroll
-			for (int e = 0; e < 4; e++) v[i][e] = mask.test(e4[e]) ? ldg_off(sb, e4[e] >> TM::SH) : 0.0f;
+			for (int e = 0; e < 4; e++) v[i * 4 + e] = mask.test(e4[e]) ? ldg_off(sb, e4[e] >> TM::SH) : 0.0f;
 		}
 	}
-	__device__ __forceinline__ void store(uint32_t tile)
+	__device__ __forceinline__ void store(uint32_t tile, const float (&v)[NV])
 	{
 		#pragma unroll
 		for (int i = 0; i < NCH; i++) {
 			const int chunk = chunk0 + i * CSTEP;
 			const uint32_t addr = tile + row_local * 128 + ((chunk ^ (row_local & 7)) << 4);
-			sts128(addr, to_tf32(v[i][0]), to_tf32(v[i][1]), to_tf32(v[i][2]), to_tf32(v[i][3]));
+			sts128(addr, to_tf32(v[i * 4]), to_tf32(v[i * 4 + 1]), to_tf32(v[i * 4 + 2]), to_tf32(v[i * 4 + 3]));
 		}
 	}
 };
@@ -450,9 +468,9 @@ template <int ROWS, bool WIDE>
 struct KTapProducer {
 	using TM = TapMask<WIDE>;
 	static constexpr int NR = ROWS / NPROD_WARPS;
+	static constexpr int NV = NR;
 	int warp, lane;
 	uint32_t table;
-	float v[NR];
 
 	__device__ __forceinline__ void init(const Operand& op, int tile_row0, int warp_, int lane_, uint32_t table_)
 	{
@@ -474,7 +492,7 @@ struct KTapProducer {
 			sts32(table + t * 4, entry);
 		}
 	}
-	__device__ __forceinline__ void load(const Operand& op, const float* __restrict__ base, int kb)
+	__device__ __forceinline__ void load(const Operand& op, const float* __restrict__ base, int kb, float (&v)[NV])
 	{
 		const int k = kb * BK + lane;
 		TM mask;
@@ -498,7 +516,7 @@ struct KTapProducer {
 			v[i] = mask.test(ent) ? ldg_off(sb, ent >> TM::SH) : 0.0f;
 		}
 	}
-	__device__ __forceinline__ void store(uint32_t tile)
+	__device__ __forceinline__ void store(uint32_t tile, const float (&v)[NV])
 	{
 		const uint32_t col = ((((uint32_t)lane >> 2) ^ ((uint32_t)warp & 7)) << 4) | (((uint32_t)lane & 3) << 2);
 		#pragma unroll
@@ -512,9 +530,9 @@ struct KTapProducer {
 template <int ROWS>
 struct KDenseProducer {
 	static constexpr int NR = ROWS / NPROD_WARPS;
+	static constexpr int NV = NR;
 	int warp, lane, nvalid;
 	long long rowoff0, step;
-	float v[NR];
 
 	__device__ __forceinline__ void init(const Operand& op, int tile_row0, int warp_, int lane_, uint32_t)
 	{
@@ -526,7 +544,7 @@ struct KDenseProducer {
 		const int left = op.rows - row0;
 		nvalid = left <= 0 ? 0 : min(NR, (left + NPROD_WARPS - 1) / NPROD_WARPS);
 	}
-	__device__ __forceinline__ void load(const Operand& op, const float* __restrict__ base, int kb)
+	__device__ __forceinline__ void load(const Operand& op, const float* __restrict__ base, int kb, float (&v)[NV])
 	{
 		const int k = kb * BK + lane;
 		int koff = k;
@@ -542,12 +560,21 @@ struct KDenseProducer {
 			p += step;
 		}
 	}
-	__device__ __forceinline__ void store(uint32_t tile)
+	__device__ __forceinline__ void store(uint32_t tile, const float (&v)[NV])
 	{
 		const uint32_t col = ((((uint32_t)lane >> 2) ^ ((uint32_t)warp & 7)) << 4) | (((uint32_t)lane & 3) << 2);
 		#pragma unroll
 		for (int i = 0; i < NR; i++) sts32(tile + (warp + i * NPROD_WARPS) * 128 + col, to_tf32(v[i]));
 	}
+};
+
+// filter operand fetched by TMA from the prepared (tf32-rounded, zero-padded, K-major) copy: no per-thread state
+template <int ROWS>
+struct TmaProducer {
+	static constexpr int NV = 1;
+	__device__ __forceinline__ void init(const Operand&, int, int, int, uint32_t) {}
+	__device__ __forceinline__ void load(const Operand&, const float* __restrict__, int, float (&)[NV]) {}
+	__device__ __forceinline__ void store(uint32_t, const float (&)[NV]) {}
 };
 
 template <int ROWS, int MODE, bool CDIV> struct ProducerSel;
@@ -559,54 +586,128 @@ template <int ROWS, bool CDIV> struct ProducerSel<ROWS, MODE_MN_SIMPLE, CDIV> { 
 template <int ROWS, bool WIDE> struct ProducerSel<ROWS, MODE_MN_TAP, WIDE> { using type = MnTapProducer<ROWS, WIDE>; };
 template <int ROWS, bool WIDE> struct ProducerSel<ROWS, MODE_K_TAP, WIDE> { using type = KTapProducer<ROWS, WIDE>; };
 template <int ROWS, bool WIDE> struct ProducerSel<ROWS, MODE_K_DENSE, WIDE> { using type = KDenseProducer<ROWS>; };
+template <int ROWS, bool WIDE> struct ProducerSel<ROWS, MODE_TMA, WIDE> { using type = TmaProducer<ROWS>; };
 
 template <int BN> struct Cfg {
 	static constexpr int STAGE_BYTES = (BM + BN) * 128;
-	static constexpr int STAGES = BN <= 64 ? 4 : 3;
-	static constexpr int TABLE_BYTES = (BM + BN) * 16;
-	static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + TABLE_BYTES + 256 + 1024;  // + barriers + align slack
+	static constexpr int STAGES = (192 * 1024) / STAGE_BYTES;          // 8 / 6 / 4 stages for BN = 64 / 128 / 256
+	static constexpr int TABLE_BYTES = (BM + (BN > 128 ? BN : 128)) * 16;  // one set of producer tables (two sets: per-tile ping-pong)
+	static constexpr int BAR_BYTES = 256;
+	static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * TABLE_BYTES + BAR_BYTES + 1024;  // + align slack
+	static constexpr int TMEM_COLS = 2 * BN;                           // double-buffered accumulator (power of two >= 32)
 };
+
+// one unit of work of the persistent schedule
+struct Work {
+	int m_tile, n_tile, group, split, kb_begin, kb_end;
+};
+
+__device__ __forceinline__ Work decode_work(const GemmParams& p, int t)
+{
+	Work w;
+	w.n_tile = t % p.tiles_n;           // n fastest: CTAs running together share the activation tile through L2
+	t /= p.tiles_n;
+	w.m_tile = t % p.tiles_m;
+	t /= p.tiles_m;
+	w.split = t % p.splits;
+	w.group = t / p.splits;
+	w.kb_begin = w.split * p.kb_per_split;
+	w.kb_end = min(p.kblocks, w.kb_begin + p.kb_per_split);
+	return w;
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads)
+{
+	asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, int c0, int c1, uint32_t bar)
+{
+	asm volatile(
+		"cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+		::"r"(dst), "l"((unsigned long long)tmap), "r"(c0), "r"(c1), "r"(bar)
+		: "memory");
+}
+
+// one 32-lane x 16-column chunk of the accumulator -> global memory.  `fast`: 1 = store alpha*acc + bias[m], 2 = store
+// alpha*acc + bias[n], 3 = red.add alpha*acc, 0 = generic (beta, bias with split-K, ...).  Lanes are the contiguous output
+// dimension, so every store instruction of a warp writes 128 consecutive bytes.
+__device__ __forceinline__ void epilogue_chunk(const Epilogue& E, const uint32_t (&v)[EPI_COLS], float* outp, const float* biasp, float bias_m,
+											   bool mvalid, bool addbias, int n0, int fast)
+{
+	if (!mvalid) return;
+	float* dst = outp + (size_t)n0 * (unsigned)E.ncs;
+	const unsigned ncs = (unsigned)E.ncs;
+	const float alpha = E.alpha;
+	if (fast != 0 && n0 + EPI_COLS <= E.N) {
+		if (fast == 1) {
+			#pragma unroll
+			for (int j = 0; j < EPI_COLS; j++) dst[(size_t)j * ncs] = fmaf(alpha, __uint_as_float(v[j]), bias_m);
+		} else if (fast == 2) {
+			const float* bn = biasp + n0;
+			#pragma unroll
+			for (int j = 0; j < EPI_COLS; j++) dst[(size_t)j * ncs] = fmaf(alpha, __uint_as_float(v[j]), __ldg(bn + j));
+		} else {
+			#pragma unroll
+			for (int j = 0; j < EPI_COLS; j++) atomicAdd(dst + (size_t)j * ncs, alpha * __uint_as_float(v[j]));
+		}
+		return;
+	}
+	#pragma unroll
+	for (int j = 0; j < EPI_COLS; j++) {
+		if (n0 + j < E.N) {
+			float r = alpha * __uint_as_float(v[j]);
+			if (addbias) {
+				if (E.bias_mode == 1) r += biasp[n0 + j];
+				else if (E.bias_mode == 2) r += bias_m;
+			}
+			float* d = dst + (size_t)j * ncs;
+			if (E.atomic) {
+				atomicAdd(d, r);                             // out was pre-scaled by beta on the host side
+			} else {
+				if (E.beta != 0.0f) r += E.beta * *d;
+				*d = r;
+			}
+		}
+	}
+}
 
 // ------------------------------------------------------------------------------------------ the kernel
 template <int BN, int AMODE, int BMODE, bool CDIV>
-__global__ void __launch_bounds__(NTHREADS, 2) umma_gemm_kernel(const __grid_constant__ GemmParams p)
+__global__ void __launch_bounds__(NTHREADS, 1) umma_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ CUtensorMap tmapB)
 {
 	using C = Cfg<BN>;
+	constexpr bool B_TMA = BMODE == MODE_TMA;
+	constexpr int PF = B_TMA ? 3 : 2;                        // k-blocks of global loads in flight per producer thread
 	extern __shared__ uint8_t smem_raw[];
 	const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
 	const uint32_t tables = smem0 + C::STAGES * C::STAGE_BYTES;
-	const uint32_t bars = tables + C::TABLE_BYTES;          // full[STAGES], empty[STAGES], accum, tmem ptr
-	const uint32_t bar_full = bars, bar_empty = bars + 8 * C::STAGES, bar_accum = bars + 16 * C::STAGES;
-	const uint32_t tmem_slot = bar_accum + 8;
+	const uint32_t bars = tables + 2 * C::TABLE_BYTES;      // full[STAGES], empty[STAGES], acc_full[2], acc_empty[2], tmem ptr
+	const uint32_t bar_full = bars, bar_empty = bars + 8 * C::STAGES;
+	const uint32_t bar_accfull = bars + 16 * C::STAGES, bar_accempty = bar_accfull + 16;
+	const uint32_t tmem_slot = bar_accempty + 16;
 
 	const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
 	const int lane = threadIdx.x & 31;
-
-	const int n_tile = blockIdx.x, m_tile = blockIdx.y;
-	const int group = blockIdx.z / p.splits, split = blockIdx.z % p.splits;
-	const int kb_begin = split * p.kb_per_split;
-	const int kb_end = min(p.kblocks, kb_begin + p.kb_per_split);
+	const int total_work = p.tiles_m * p.tiles_n * p.groups * p.splits;
 
 	if (warp == NPROD_WARPS) {
 		if (lane == 0) {
 			for (int s = 0; s < C::STAGES; s++) {
-				mbar_init(bar_full + 8 * s, NPROD_WARPS);
+				mbar_init(bar_full + 8 * s, NPROD_WARPS + (B_TMA ? 1 : 0));
 				mbar_init(bar_empty + 8 * s, 1);
 			}
-			mbar_init(bar_accum, 1);
+			for (int a = 0; a < 2; a++) {
+				mbar_init(bar_accfull + 8 * a, 1);
+				mbar_init(bar_accempty + 8 * a, NEPI_WARPS);
+			}
 			fence_barrier_init();
 		}
 		__syncwarp();
-		tmem_alloc(tmem_slot, BN);
-	}
-
-	typename ProducerSel<BM, AMODE, CDIV>::type prodA;
-	typename ProducerSel<BN, BMODE, false>::type prodB;
-	const float* baseA = p.A.ptr + (long long)group * p.A.group_stride;
-	const float* baseB = p.B.ptr + (long long)group * p.B.group_stride;
-	if (warp < NPROD_WARPS) {
-		prodA.init(p.A, m_tile * BM, warp, lane, tables);
-		prodB.init(p.B, n_tile * BN, warp, lane, tables + BM * 16);
+		tmem_alloc(tmem_slot, C::TMEM_COLS);
 	}
 
 	tc_fence_before();
@@ -618,93 +719,167 @@ __global__ void __launch_bounds__(NTHREADS, 2) umma_gemm_kernel(const __grid_con
 
 	if (warp < NPROD_WARPS) {
 		// ===================== producers =====================
+		typename ProducerSel<BM, AMODE, CDIV>::type prodA;
+		typename ProducerSel<BN, BMODE, false>::type prodB;
+		using PA = decltype(prodA);
+		using PB = decltype(prodB);
+		float va[PF][PA::NV];
+		float vb[PF][PB::NV];
+		int tk[PF], tr[PF];                                  // TMA coordinates of the slot (k element, filter row)
+
+		// load cursor (runs PF-1 k-blocks ahead of the store cursor)
+		int lwork = blockIdx.x, lkb = 0, lseq = 0;
+		Work lw{};
+		bool lvalid = lwork < total_work;
+		if (lvalid) { lw = decode_work(p, lwork); lkb = lw.kb_begin; }
+		const float* baseA = p.A.ptr;
+		const float* baseB = p.B.ptr;
+		int issued = 0, done = 0;
 		int stage = 0;
 		uint32_t phase = 0;
-		for (int kb = kb_begin; kb < kb_end; kb++) {
-			prodA.load(p.A, baseA, kb);
-			prodB.load(p.B, baseB, kb);
-			mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-			const uint32_t tileA = smem0 + stage * C::STAGE_BYTES;
-			prodA.store(tileA);
-			prodB.store(tileA + BM * 128);
-			fence_async_smem();
-			__syncwarp();
-			if (lane == 0) mbar_arrive(bar_full + 8 * stage);
-			if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
-		}
 
-		// ===================== epilogue =====================
-		mbar_wait(bar_accum, 0);
-		tc_fence_after();
+		auto issue_load = [&](float (&a)[PA::NV], float (&b)[PB::NV], int& k_elem, int& b_row) {
+			if (lkb == lw.kb_begin) {
+				// first k-block of a work unit: per-tile producer state + smem tables (ping-pong sets, one named barrier)
+				const uint32_t tset = tables + (uint32_t)(lseq & 1) * C::TABLE_BYTES;
+				prodA.init(p.A, lw.m_tile * BM, warp, lane, tset);
+				prodB.init(p.B, lw.n_tile * BN, warp, lane, tset + BM * 16);
+				baseA = p.A.ptr + (long long)lw.group * p.A.group_stride;
+				baseB = p.B.ptr + (long long)lw.group * p.B.group_stride;
+				named_bar_sync(1, NPROD);
+				lseq++;
+			}
+			prodA.load(p.A, baseA, lkb, a);
+			prodB.load(p.B, baseB, lkb, b);
+			k_elem = lkb * BK;
+			b_row = lw.group * p.tma_rows_per_group + lw.n_tile * BN;
+			issued++;
+			if (++lkb == lw.kb_end) {
+				lwork += gridDim.x;
+				lvalid = lwork < total_work;
+				if (lvalid) { lw = decode_work(p, lwork); lkb = lw.kb_begin; }
+			}
+		};
 
-		const Epilogue& E = p.E;
-		const int lg = warp & 3, half = warp >> 2;
-		const int m = m_tile * BM + lg * 32 + lane;
-		const bool mvalid = m < E.M;
-		int m0, m1, m2;
-		split3((uint32_t)(mvalid ? m : 0), E.md12, E.md2, m0, m1, m2);
-		float* outp = E.out + (long long)group * E.group_stride + ((long long)m0 * E.ms0 + (long long)m1 * E.ms1 + (long long)m2 * E.ms2);
-		const float* biasp = E.bias ? E.bias + (long long)group * E.bias_group_stride : nullptr;
-		const float bias_m = (E.bias_mode == 2 && mvalid) ? biasp[m] : 0.0f;
+		#pragma unroll
+		for (int b = 0; b < PF - 1; b++)
+			if (lvalid) issue_load(va[b], vb[b], tk[b], tr[b]);
 
-		#pragma unroll 1
-		for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
-			uint32_t v[32];
-			tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)c0, v);
+		bool more = issued > 0;
+		while (more) {
 			#pragma unroll
-			for (int j = 0; j < 32; j++) {
-				const int n = n_tile * BN + c0 + j;
-				if (mvalid && n < E.N && kb_end > kb_begin) {
-					float r = E.alpha * __uint_as_float(v[j]);
-					float* dst = outp + (long long)n * E.ncs;
-					if (!E.atomic || split == 0) {   // with split-K the bias is contributed once
-						if (E.bias_mode == 1) r += biasp[n];
-						else if (E.bias_mode == 2) r += bias_m;
-					}
-					if (E.atomic) {
-						atomicAdd(dst, r);           // out was pre-scaled by beta on the host side
-					} else {
-						if (E.beta != 0.0f) r += E.beta * *dst;
-						*dst = r;
+			for (int b = 0; b < PF; b++) {
+				if (lvalid) issue_load(va[(b + PF - 1) % PF], vb[(b + PF - 1) % PF], tk[(b + PF - 1) % PF], tr[(b + PF - 1) % PF]);
+				if (done == issued) { more = false; break; }
+				mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+				const uint32_t tileA = smem0 + stage * C::STAGE_BYTES;
+				if (B_TMA) {
+					if (warp == 0 && lane == 0) {
+						mbar_arrive_expect_tx(bar_full + 8 * stage, BN * 128);
+						tma_load_2d(tileA + BM * 128, &tmapB, tk[b], tr[b], bar_full + 8 * stage);
 					}
 				}
+				prodA.store(tileA, va[b]);
+				prodB.store(tileA + BM * 128, vb[b]);
+				fence_async_smem();
+				__syncwarp();
+				if (lane == 0) mbar_arrive(bar_full + 8 * stage);
+				if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+				done++;
 			}
 		}
-		tc_fence_before();
-	} else {
+	} else if (warp == NPROD_WARPS) {
 		// ===================== MMA issuer (one thread) =====================
 		constexpr uint32_t idesc = make_idesc_tf32(BM, BN);
 		int stage = 0;
 		uint32_t phase = 0;
-		for (int kb = kb_begin; kb < kb_end; kb++) {
-			mbar_wait(bar_full + 8 * stage, phase);
+		int as = 0;
+		uint32_t aphase = 0;
+		for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
+			const Work w = decode_work(p, work);
+			mbar_wait(bar_accempty + 8 * as, aphase ^ 1);        // epilogue has drained this accumulator buffer
 			tc_fence_after();
-			if (lane == 0) {
-				const uint32_t tileA = smem0 + stage * C::STAGE_BYTES;
-				const uint64_t da = make_smem_desc(tileA), db = make_smem_desc(tileA + BM * 128);
-				#pragma unroll
-				for (int kk = 0; kk < BK / 8; kk++)    // 8 tf32 = 32 bytes per MMA: +2 in the (addr >> 4) field
-					umma_tf32(tmem_base, da + 2 * kk, db + 2 * kk, idesc, (kb > kb_begin || kk > 0) ? 1u : 0u);
-				umma_commit(bar_empty + 8 * stage);
+			const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+			for (int kb = w.kb_begin; kb < w.kb_end; kb++) {
+				mbar_wait(bar_full + 8 * stage, phase);
+				tc_fence_after();
+				if (lane == 0) {
+					const uint32_t tileA = smem0 + stage * C::STAGE_BYTES;
+					const uint64_t da = make_smem_desc(tileA), db = make_smem_desc(tileA + BM * 128);
+					#pragma unroll
+					for (int kk = 0; kk < BK / 8; kk++)    // 8 tf32 = 32 bytes per MMA: +2 in the (addr >> 4) field
+						umma_tf32(tmem_d, da + 2 * kk, db + 2 * kk, idesc, (kb > w.kb_begin || kk > 0) ? 1u : 0u);
+					umma_commit(bar_empty + 8 * stage);
+				}
+				__syncwarp();
+				if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
 			}
+			if (lane == 0) umma_commit(bar_accfull + 8 * as);
 			__syncwarp();
-			if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+			if (++as == 2) { as = 0; aphase ^= 1; }
 		}
-		if (lane == 0) umma_commit(bar_accum);
-		__syncwarp();
 		tc_fence_before();
+	} else {
+		// ===================== epilogue (4 warps; warp w may touch TMEM lanes 32*(w%4) .. +31) =====================
+		const Epilogue& E = p.E;
+		const int lg = warp & 3;
+		int as = 0;
+		uint32_t aphase = 0;
+		for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
+			const Work w = decode_work(p, work);
+			const int m = w.m_tile * BM + lg * 32 + lane;
+			const bool mvalid = m < E.M;
+			int m0, m1, m2;
+			split3((uint32_t)(mvalid ? m : 0), E.md12, E.md2, m0, m1, m2);
+			float* outp = E.out + (long long)w.group * E.group_stride + ((long long)m0 * E.ms0 + (long long)m1 * E.ms1 + (long long)m2 * E.ms2);
+			const float* biasp = E.bias ? E.bias + (long long)w.group * E.bias_group_stride : nullptr;
+			const bool addbias = !E.atomic || w.split == 0;      // with split-K the bias is contributed once
+			const float bias_m = (E.bias_mode == 2 && mvalid && addbias) ? biasp[m] : 0.0f;
+
+			mbar_wait(bar_accfull + 8 * as, aphase);
+			tc_fence_after();
+			const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN) + ((uint32_t)(lg * 32) << 16);
+			const int ncols = min(BN, E.N - w.n_tile * BN);       // valid columns of this tile (> 0)
+			// fast paths (straight-line, 2 - 3 instructions per element): plain store and split-K red.add
+			const int fast = E.atomic ? ((addbias && E.bias_mode) ? 0 : 3) : (E.beta != 0.0f ? 0 : (E.bias_mode == 1 ? 2 : 1));
+
+			uint32_t v0[EPI_COLS], v1[EPI_COLS];
+			tmem_ld16(tmem_d, v0);
+			#pragma unroll 1
+			for (int c0 = 0; c0 < ncols; c0 += 2 * EPI_COLS) {
+				tmem_wait_ld(v0);
+				if (c0 + EPI_COLS < ncols) tmem_ld16(tmem_d + (uint32_t)(c0 + EPI_COLS), v1);
+				epilogue_chunk(E, v0, outp, biasp, bias_m, mvalid, addbias, w.n_tile * BN + c0, fast);
+				if (c0 + EPI_COLS < ncols) {
+					tmem_wait_ld(v1);
+					if (c0 + 2 * EPI_COLS < ncols) tmem_ld16(tmem_d + (uint32_t)(c0 + 2 * EPI_COLS), v0);
+					epilogue_chunk(E, v1, outp, biasp, bias_m, mvalid, addbias, w.n_tile * BN + c0 + EPI_COLS, fast);
+				}
+			}
+			tc_fence_before();
+			__syncwarp();
+			if (lane == 0) mbar_arrive(bar_accempty + 8 * as);
+			if (++as == 2) { as = 0; aphase ^= 1; }
+		}
 	}
 
+	tc_fence_before();
 	__syncthreads();
 	if (warp == NPROD_WARPS) {
 		tc_fence_after();
-		tmem_dealloc(tmem_base, BN);
+		tmem_dealloc(tmem_base, C::TMEM_COLS);
 	}
 }
 
-// host-side launcher (defined in pz_gemm.cu)
-int launch(const GemmParams& p, int bn, int amode, int bmode, bool cdiv, int groups, cudaStream_t stream);
-int pick_bn(int n);
+// host-side launcher (defined in pz_gemm.cu).  `bn` = 0 lets the launcher pick the tile width; tmap_src (MODE_TMA only) is
+// the prepared filter: fp32 [tma_rows][tma_kpad], tf32-rounded, zero-padded, 16-byte aligned.
+struct TmaSource {
+	const float* ptr;
+	long long rows, kpad;
+};
+int launch(GemmParams& p, int bn, int amode, int bmode, bool cdiv, int groups, const TmaSource* tma, cudaStream_t stream);
+int pick_bn(int n, long long m_rows, int kblocks, int groups, int max_bn);
+float* scratch(size_t bytes);                   // library-owned, stream-ordered scratch (prepared filters)
 
 // helpers to build operands
 Operand dense_k(const float* ptr, int rows, int kdim, long long ld);     // element (row,k) at ptr[row*ld + k]
