@@ -79,41 +79,73 @@ void set_alg(GemmParams& p, const Geo& g)
 	p.alg_bytes = 4.0 * (x + y + w);
 }
 
+inline int round_up32(int v) { return (v + 31) & ~31; }
+inline int round_up32_c(int v) { return (v + 31) & ~31; }
+
 // Prepared filters (the TMA-fetched operand of fprop / dgrad): fp32 rows of `kpad` (multiple of 32) elements, K-major,
 // rounded to tf32 (the tensor core would otherwise truncate) and zero-padded, in the library scratch.
 
 // fprop: wp[ko_total][k] = w[ko_total][k], k = (c, r, s) < kdim
-__global__ void prep_filter_fprop(const float* __restrict__ w, float* __restrict__ wp, int kdim, int kpad, long long total)
+// chan != 0: k ordered (tap, channel block, 32 channels) for MnChanProducer, kpad = RS * ceil(Cg / 32) * 32
+__global__ void prep_filter_fprop(const float* __restrict__ w, float* __restrict__ wp, int kdim, int kpad, long long total, int chan, int Cg,
+								   int RS)
 {
 	long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= total) return;
 	const int k = (int)(i % kpad);
 	const long long row = i / kpad;
-	wp[i] = k < kdim ? __uint_as_float(to_tf32(w[row * kdim + k])) : 0.0f;
+	float v = 0.0f;
+	if (chan) {
+		const int cpad = kpad / RS;
+		const int t = k / cpad, c = k % cpad;
+		if (c < Cg) v = w[row * kdim + (long long)c * RS + t];
+	} else if (k < kdim) {
+		v = w[row * kdim + k];
+	}
+	wp[i] = __uint_as_float(to_tf32(v));
 }
 
 // dgrad: wt[g*Cg + c][(ko, r', s')] = w[g*Kg + ko][c][r0 + sh*r'][s0 + sw*s'] -- the sub-filter of one output-parity class of
 // a strided transposed convolution (r0 = s0 = 0, sh = sw = 1, Rc = R, Sc = S: the whole filter, stride-1 dgrad)
+// chan != 0: k ordered (tap (r', s'), ko block, 32 ko) for MnChanProducer, kpad = Rc * Sc * ceil(Kg / 32) * 32
 __global__ void prep_filter_dgrad(const float* __restrict__ w, float* __restrict__ wt, int Kg, int Cg, int R, int S, int r0, int s0,
-								   int sh, int sw, int Rc, int Sc, int kpad, long long total)
+								   int sh, int sw, int Rc, int Sc, int kpad, long long total, int chan)
 {
 	long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= total) return;
 	int k = (int)(i % kpad);
 	const int row = (int)(i / kpad);
-	float v = 0.0f;
-	if (k < Kg * Rc * Sc) {
-		const int sc = k % Sc;
+	int ko = -1, rc = 0, sc = 0;
+	if (chan) {
+		const int kopad = kpad / (Rc * Sc);
+		const int t = k / kopad;
+		ko = k % kopad;
+		if (ko >= Kg) ko = -1;
+		rc = t / Sc;
+		sc = t % Sc;
+	} else if (k < Kg * Rc * Sc) {
+		sc = k % Sc;
 		k /= Sc;
-		const int rc = k % Rc;
-		const int ko = k / Rc;
+		rc = k % Rc;
+		ko = k / Rc;
+	}
+	float v = 0.0f;
+	if (ko >= 0) {
 		const int c = row % Cg, g = row / Cg;
 		v = __uint_as_float(to_tf32(w[((((long long)g * Kg + ko) * Cg + c) * R + (r0 + sh * rc)) * S + (s0 + sw * sc)]));
 	}
 	wt[i] = v;
 }
 
-inline int round_up32(int v) { return (v + 31) & ~31; }
+// the (tap, channel) k order pads the channels of every tap to a multiple of 32: worth it unless the channel count is tiny
+inline bool use_chan_order(int chans) { return round_up32_c(chans) * 3 <= chans * 4; }
+
+// row length of the prepared dgrad filter: `taps` taps of Kg output channels
+inline int dgrad_kpad(int Kg, int taps, bool may_chan)
+{
+	return may_chan && use_chan_order(Kg) ? taps * round_up32_c(Kg) : round_up32_c(Kg * taps);
+}
+
 
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) bias_grad_kernel(const float* __restrict__ t, float* __restrict__ db, long long N,
@@ -172,11 +204,14 @@ int pz_conv2d_fprop(int dtype, const pz_conv2d_desc* d, const void* x, const voi
 	A.group_stride = (long long)g.Cg * HW;
 
 	// filter: prepared copy [K][kpad], fetched by TMA
-	const int kdim = g.Cg * RS, kpad = round_up32(kdim);
+	const bool fast = tap_entries_fit(34ll * HW, g);
+	const bool chan = fast && use_chan_order(g.Cg);
+	const int kdim = g.Cg * RS, kpad = chan ? RS * round_up32(g.Cg) : round_up32(kdim);
 	const long long wtotal = (long long)g.K * kpad;
 	float* wp = scratch((size_t)wtotal * sizeof(float));
 	if (!wp) { pz_set_error(PZ_ERR_MEMORY, "conv2d fprop: cannot allocate %lld bytes of filter scratch", wtotal * 4); return PZ_ERR_MEMORY; }
-	prep_filter_fprop<<<(unsigned)pz_cdiv(wtotal, 256), 256, 0, pz_stream(stream)>>>((const float*)w, wp, kdim, kpad, wtotal);
+	prep_filter_fprop<<<(unsigned)pz_cdiv(wtotal, 256), 256, 0, pz_stream(stream)>>>((const float*)w, wp, kdim, kpad, wtotal, chan ? 1 : 0,
+																					 g.Cg, RS);
 	pz_count_launch(1);
 	PZ_LAUNCH_CHECK();
 	const TmaSource tsrc{wp, g.K, kpad};
@@ -195,13 +230,14 @@ int pz_conv2d_fprop(int dtype, const pz_conv2d_desc* d, const void* x, const voi
 	E.group_stride = (long long)g.Kg * PQ;
 	E.bias_group_stride = g.Kg;
 
-	p.kblocks = (int)pz_cdiv(A.kdim, BK);
+	A.chans = g.Cg;
+	A.kbdiv = make_fastdiv((uint32_t)(round_up32(g.Cg) / 32));
+	p.kblocks = kpad / BK;
 	p.splits = 1;
 	p.kb_per_split = p.kblocks;
 	set_alg(p, g);
-	const bool fast = tap_entries_fit(34ll * HW, g);
 	const int bn = pick_bn(g.Kg, (long long)g.N * PQ, p.kblocks, g.G, 256);
-	return launch(p, bn, fast ? MODE_MN_TAP : MODE_MN_GENERAL, MODE_TMA, fast && RS > 31, g.G, &tsrc, pz_stream(stream));
+	return launch(p, bn, chan ? MODE_MN_CHAN : (fast ? MODE_MN_TAP : MODE_MN_GENERAL), MODE_TMA, fast && RS > 31, g.G, &tsrc, pz_stream(stream));
 }
 
 // the dgrad filter repack lives in the library's own scratch; callers need not supply a workspace any more
@@ -241,10 +277,11 @@ int pz_conv2d_dgrad(int dtype, const pz_conv2d_desc* d, const void* dy, const vo
 	// mode 0: parity class of a strided, un-dilated filter (fast tap producer); mode 1: stride 1, any dilation (fast tap
 	// producer); mode 2: any stride and dilation through the exact-division gather (csh = csw = 1, whole filter).
 	auto run_class = [&](float* wt, int a_h, int a_w, int r0, int s0, int csh, int csw, int Rc, int Sc, int Hc, int Wc, int mode) -> int {
-		const int kdim = g.Kg * Rc * Sc, kpad = round_up32(kdim);
+		const bool chan = mode != 2 && use_chan_order(g.Kg);
+		const int kdim = g.Kg * Rc * Sc, kpad = dgrad_kpad(g.Kg, Rc * Sc, mode != 2);
 		const long long total = (long long)g.C * kpad;
 		prep_filter_dgrad<<<(unsigned)pz_cdiv(total, 256), 256, 0, pz_stream(stream)>>>((const float*)w, wt, g.Kg, g.Cg, g.R, g.S, r0, s0,
-																						csh, csw, Rc, Sc, kpad, total);
+																						csh, csw, Rc, Sc, kpad, total, chan ? 1 : 0);
 		pz_count_launch(1);
 		PZ_LAUNCH_CHECK();
 
@@ -267,6 +304,8 @@ int pz_conv2d_dgrad(int dtype, const pz_conv2d_desc* d, const void* dy, const vo
 		}
 		QA.rows = g.N * Hc * Wc; QA.kdim = kdim;
 		QA.R = Rc; QA.S = Sc;
+		QA.chans = g.Kg;
+		QA.kbdiv = make_fastdiv((uint32_t)(round_up32(g.Kg) / 32));
 		QA.group_stride = (long long)g.Kg * PQ;
 
 		q.E = E;
@@ -275,7 +314,7 @@ int pz_conv2d_dgrad(int dtype, const pz_conv2d_desc* d, const void* dy, const vo
 		q.E.ms0 = g.C * HW; q.E.ms1 = csh * g.W; q.E.ms2 = csw;
 		q.E.M = g.N * Hc * Wc;
 		q.splits = 1;
-		q.kblocks = (int)pz_cdiv(kdim, BK);
+		q.kblocks = kpad / BK;
 		q.kb_per_split = q.kblocks;
 		q.tma_rows_per_group = g.Cg;
 		q.alg_flops = 2.0 * (double)q.E.M * g.K * g.Cg * Rc * Sc / g.G;
@@ -283,7 +322,7 @@ int pz_conv2d_dgrad(int dtype, const pz_conv2d_desc* d, const void* dy, const vo
 		const TmaSource tsrc{wt, g.C, kpad};
 		const int bn = pick_bn(g.Cg, q.E.M, q.kblocks, g.G, 256);
 		const bool cdiv = mode == 2 ? strided : Rc * Sc > 31;
-		return launch(q, bn, mode == 2 ? MODE_MN_GENERAL : MODE_MN_TAP, MODE_TMA, cdiv, g.G, &tsrc, pz_stream(stream));
+		return launch(q, bn, mode == 2 ? MODE_MN_GENERAL : (chan ? MODE_MN_CHAN : MODE_MN_TAP), MODE_TMA, cdiv, g.G, &tsrc, pz_stream(stream));
 	};
 
 	if (is1x1 && g.ph == 0 && g.pw == 0 && strided) {
@@ -291,7 +330,7 @@ int pz_conv2d_dgrad(int dtype, const pz_conv2d_desc* d, const void* dy, const vo
 		PZ_REQUIRE(bias == nullptr, "conv2d dgrad: bias with a strided 1x1 filter is not supported");
 		st = pz_memset8(dx, 0, (size_t)g.N * g.C * HW * 4, stream);
 		if (st != PZ_OK) return st;
-		float* wt = scratch((size_t)g.C * round_up32(g.Kg) * sizeof(float));
+		float* wt = scratch((size_t)g.C * dgrad_kpad(g.Kg, 1, true) * sizeof(float));
 		if (!wt) { pz_set_error(PZ_ERR_MEMORY, "conv2d dgrad: cannot allocate filter scratch"); return PZ_ERR_MEMORY; }
 		PZ_REQUIRE(tap_entries_fit(34ll * PQ, g), "conv2d dgrad: tensor too large");
 		return run_class(wt, 0, 0, 0, 0, g.sh, g.sw, 1, 1, g.P, g.Q, 0);
@@ -306,7 +345,7 @@ int pz_conv2d_dgrad(int dtype, const pz_conv2d_desc* d, const void* dy, const vo
 			for (int a_w = 0; a_w < g.sw && a_w < g.W; a_w++) {
 				const int r0 = (a_h + g.ph) % g.sh, s0 = (a_w + g.pw) % g.sw;
 				const int Rc = r0 < g.R ? (g.R - r0 + g.sh - 1) / g.sh : 0, Sc = s0 < g.S ? (g.S - s0 + g.sw - 1) / g.sw : 0;
-				need += (size_t)g.C * round_up32(g.Kg * Rc * Sc) * sizeof(float);
+				need += (size_t)g.C * dgrad_kpad(g.Kg, Rc * Sc, true) * sizeof(float);
 			}
 		float* wsp = scratch(need);
 		if (!wsp) { pz_set_error(PZ_ERR_MEMORY, "conv2d dgrad: cannot allocate %zu bytes of filter scratch", need); return PZ_ERR_MEMORY; }
@@ -328,15 +367,15 @@ int pz_conv2d_dgrad(int dtype, const pz_conv2d_desc* d, const void* dy, const vo
 				}
 				st = run_class(wsp, a_h, a_w, r0, s0, g.sh, g.sw, Rc, Sc, Hc, Wc, 0);
 				if (st != PZ_OK) return st;
-				wsp += (size_t)g.C * round_up32(g.Kg * Rc * Sc);
+				wsp += (size_t)g.C * dgrad_kpad(g.Kg, Rc * Sc, true);
 			}
 		return PZ_OK;
 	}
 
 	{
-		float* wt = scratch((size_t)g.C * round_up32(g.Kg * RS) * sizeof(float));
-		if (!wt) { pz_set_error(PZ_ERR_MEMORY, "conv2d dgrad: cannot allocate filter scratch"); return PZ_ERR_MEMORY; }
 		const bool tapmode = !strided && tap_entries_fit(34ll * PQ, g);
+		float* wt = scratch((size_t)g.C * dgrad_kpad(g.Kg, RS, tapmode) * sizeof(float));
+		if (!wt) { pz_set_error(PZ_ERR_MEMORY, "conv2d dgrad: cannot allocate filter scratch"); return PZ_ERR_MEMORY; }
 		return run_class(wt, 0, 0, 0, 0, 1, 1, g.R, g.S, g.H, g.W, tapmode ? 1 : 2);
 	}
 }
@@ -349,6 +388,11 @@ int pz_conv2d_wgrad(int dtype, const pz_conv2d_desc* d, const void* x, const voi
 	if (st != PZ_OK) return st;
 	const int RS = g.R * g.S, PQ = g.P * g.Q, HW = g.H * g.W;
 	PZ_REQUIRE((long long)g.N * PQ < (1ll << 31), "conv2d wgrad: reduction too long");
+
+	// reduction index k ordered (image, block of 32 positions): k-block kb = n * kbpi + pb (positions past PQ are zero)
+	const int kbpi = (int)pz_cdiv(PQ, BK);
+	const bool dense_x = RS == 1 && g.sh == 1 && g.sw == 1 && g.ph == 0 && g.pw == 0;
+	const bool fast = tap_entries_fit((long long)g.Cg * HW, g);
 
 	GemmParams p{};
 	Operand& A = p.A;   // im2col view of x: rows (c,r,s), k (n,p,q)
@@ -363,6 +407,8 @@ int pz_conv2d_wgrad(int dtype, const pz_conv2d_desc* d, const void* x, const voi
 	A.rows = g.Cg * RS; A.kdim = g.N * PQ;
 	A.R = g.R; A.S = g.S;
 	A.group_stride = (long long)g.Cg * HW;
+	A.kbdiv = make_fastdiv((uint32_t)kbpi);
+	A.plane = PQ;
 
 	Operand& B = p.B;   // dy: rows ko, k (n, pq)
 	B.ptr = (const float*)dy;
@@ -376,6 +422,8 @@ int pz_conv2d_wgrad(int dtype, const pz_conv2d_desc* d, const void* x, const voi
 	B.R = B.S = 1;
 	B.rows = g.Kg; B.kdim = g.N * PQ;
 	B.group_stride = (long long)g.Kg * PQ;
+	B.kbdiv = make_fastdiv((uint32_t)kbpi);
+	B.plane = PQ;
 
 	Epilogue& E = p.E;
 	E.out = (float*)dw;
@@ -389,8 +437,8 @@ int pz_conv2d_wgrad(int dtype, const pz_conv2d_desc* d, const void* x, const voi
 	E.group_stride = (long long)g.Kg * g.Cg * RS;
 	E.bias_group_stride = 0;
 
-	p.kblocks = (int)pz_cdiv(A.kdim, BK);
-	const int bn = pick_bn(g.Kg, E.M, 8, g.G, 128);
+	p.kblocks = fast ? g.N * kbpi : (int)pz_cdiv(A.kdim, BK);
+	const int bn = g.Kg > 64 ? 128 : 64;        // the x operand is re-read once per column tile: keep those few
 	set_splits(p, pz_cdiv(E.M, BM) * pz_cdiv(E.N, bn) * g.G, 8);
 	E.atomic = p.splits > 1;
 	if (E.atomic) {
@@ -398,8 +446,8 @@ int pz_conv2d_wgrad(int dtype, const pz_conv2d_desc* d, const void* x, const voi
 		if (st != PZ_OK) return st;
 	}
 	set_alg(p, g);
-	const bool fast = tap_entries_fit((long long)g.Cg * HW, g);
-	return launch(p, bn, fast ? MODE_K_TAP : MODE_K_GENERAL, MODE_K_DENSE, fast && RS > 31, g.G, nullptr, pz_stream(stream));
+	if (!fast) return launch(p, bn, MODE_K_GENERAL, MODE_K_DENSE, false, g.G, nullptr, pz_stream(stream));
+	return launch(p, bn, dense_x ? MODE_K_POS_DENSE : MODE_K_POS_TAP, MODE_K_POS_DENSE, !dense_x && RS > 31, g.G, nullptr, pz_stream(stream));
 }
 
 int pz_bias_grad(int dtype, const void* t, void* db, int64_t N, int64_t C, int64_t S, float alpha, float beta, void* stream)

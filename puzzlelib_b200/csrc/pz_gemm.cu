@@ -155,8 +155,11 @@ int launch(GemmParams& p, int bn, int amode, int bmode, bool cdiv, int groups, c
 	PZ_INST_BN(MODE_MN_TAP, MODE_K_DENSE, false)       // GEMM NN
 	PZ_INST_BN(MODE_MN_TAP, MODE_MN_TAP, false)        // GEMM TN
 	PZ_INST_BN(MODE_K_DENSE, MODE_K_DENSE, false)      // GEMM NT
-	PZ_INST_BN(MODE_K_TAP, MODE_K_DENSE, false)        // wgrad
-	PZ_INST_BN(MODE_K_TAP, MODE_K_DENSE, true)         //   ... with more than 31 taps
+	PZ_INST_BN3(MODE_MN_CHAN, MODE_TMA, false)         // fprop, dgrad with k ordered (tap, channel)
+	PZ_INST_BN3(MODE_MN_CHAN, MODE_TMA, true)          //   ... with more than 31 taps
+	PZ_INST_BN(MODE_K_POS_TAP, MODE_K_POS_DENSE, false)    // wgrad
+	PZ_INST_BN(MODE_K_POS_TAP, MODE_K_POS_DENSE, true)     //   ... with more than 31 taps
+	PZ_INST_BN(MODE_K_POS_DENSE, MODE_K_POS_DENSE, false)  // wgrad of a 1x1 / stride-1 / un-padded filter
 	PZ_INST_BN(MODE_K_GENERAL, MODE_K_DENSE, false)    // fallback for wgrad
 #undef PZ_INST_BN3
 #undef PZ_INST_BN

@@ -80,7 +80,7 @@ __device__ __forceinline__ void split3(uint32_t x, const FastDiv& d12, const Fas
 // MN_TAP / K_TAP / K_DENSE are the fast paths: per-row (or per-k) base offsets and tap-validity bit masks are
 // computed once, the per-element work is one predicated load + one tf32 rounding.
 enum { MODE_K_GENERAL = 0, MODE_K_SIMPLE = 1, MODE_MN_GENERAL = 2, MODE_MN_SIMPLE = 3, MODE_MN_TAP = 4, MODE_K_TAP = 5,
-	   MODE_K_DENSE = 6, MODE_TMA = 7 };
+	   MODE_K_DENSE = 6, MODE_TMA = 7, MODE_MN_CHAN = 8, MODE_K_POS_TAP = 9, MODE_K_POS_DENSE = 10 };
 
 struct Operand {
 	const float* ptr;
@@ -92,6 +92,10 @@ struct Operand {
 	int rows, kdim;
 	int R, S;                    // taps of the (r, s) sub-index (1, 1 for dense operands); used by the *_TAP producers
 	long long group_stride;
+	// MODE_MN_CHAN: k-block kb = tap * cblocks + channel block (32 channels per block, `chans` channels in all)
+	// MODE_K_POS*: k-block kb = image * kbpi + position block (32 positions per block, `plane` positions per image)
+	FastDiv kbdiv;               // divisor cblocks / kbpi
+	int chans, plane;
 };
 
 struct Epilogue {
@@ -568,6 +572,177 @@ struct KDenseProducer {
 	}
 };
 
+// rows = spatial positions (MN-contiguous in memory), k ordered (tap, channel): k-block kb = t * cblocks + cb covers channels
+// cb*32 .. cb*32+31 of ONE filter tap t = (r, s).  Tap validity is then a single per-thread predicate per stage and the 32
+// channel addresses are the tap address + j * channel-stride: 3 instructions per element (address, load, tf32 rounding)
+// instead of a table lookup + mask test per element.  fprop / dgrad whenever the channel count is not tiny; the prepared
+// filter (TMA operand) is laid out in the same k order by the prep kernels.
+template <int ROWS, bool WIDE>
+struct MnChanProducer {
+	using TM = TapMask<WIDE>;
+	static constexpr int NCH = 8 * ROWS / NPROD;
+	static constexpr int CSTEP = NPROD / ROWS;
+	static constexpr int NV = NCH * 4;
+	TM mask;
+	int poff, row_local, chunk0;
+
+	__device__ __forceinline__ void init(const Operand& op, int tile_row0, int warp, int lane, uint32_t)
+	{
+		const int t = warp * 32 + lane;
+		row_local = t % ROWS;
+		chunk0 = (warp * 32) / ROWS;
+		const int row = tile_row0 + row_local;
+		mask.clear();
+		int r0, r1, r2;
+		split3((uint32_t)(row < op.rows ? row : 0), op.rd12, op.rd2, r0, r1, r2);
+		const int hr = r1 * op.ah + op.ch, wr = r2 * op.aw + op.cw;
+		poff = r0 * op.rs0 + hr * op.Wd + wr;
+		if (row < op.rows) {
+			for (int r = 0; r < op.R; r++) {
+				const bool okh = (unsigned)(hr + r * op.bh) < (unsigned)op.H;
+				for (int s = 0; s < op.S; s++)
+					if (okh && (unsigned)(wr + s * op.bw) < (unsigned)op.W) mask.set((int)TM::TOP - (r * op.S + s));
+			}
+		}
+	}
+	__device__ __forceinline__ void load(const Operand& op, const float* __restrict__ base, int kb, float (&v)[NV])
+	{
+		const uint32_t t = fdiv((uint32_t)kb, op.kbdiv);             // warp-uniform
+		const uint32_t cb = (uint32_t)kb - t * op.kbdiv.d;
+		const uint32_t r = fdiv(t, op.kd2);
+		const uint32_t sx = t - r * op.kd2.d;
+		const int tapoff = (int)r * op.bh * op.Wd + (int)sx * op.bw;
+		const bool ok = mask.test(t);                                 // bit (TOP - t) of the mask, see init
+		const int c0 = (int)cb * 32 + chunk0 * 4;
+		const int cleft = op.chans - c0;
+		const float* __restrict__ ptr = base + ((long long)c0 * op.ks0 + (poff + tapoff));
+		#pragma unroll
+		for (int i = 0; i < NCH; i++) {
+			#pragma unroll
+			for (int e = 0; e < 4; e++) {
+				const int j = i * CSTEP * 4 + e;
+				v[i * 4 + e] = (ok && j < cleft) ? __ldg(ptr + (size_t)((unsigned)j * (unsigned)op.ks0)) : 0.0f;
+			}
+		}
+	}
+	__device__ __forceinline__ void store(uint32_t tile, const float (&v)[NV])
+	{
+		#pragma unroll
+		for (int i = 0; i < NCH; i++) {
+			const int chunk = chunk0 + i * CSTEP;
+			const uint32_t addr = tile + row_local * 128 + ((chunk ^ (row_local & 7)) << 4);
+			sts128(addr, to_tf32(v[i * 4]), to_tf32(v[i * 4 + 1]), to_tf32(v[i * 4 + 2]), to_tf32(v[i * 4 + 3]));
+		}
+	}
+};
+
+// K-contiguous operands of wgrad with the reduction index ordered (image, position block): k-block kb = n * kbpi + pb covers
+// positions pb*32 .. pb*32+31 of ONE image n (positions past the plane are zero), so the image / position decode is
+// warp-uniform and a lane only derives (p, q) from its position.  lane = position; warp w covers tile rows w, w+16, ...
+//
+// KPosDense: rows are channels with a constant stride (dy, or x of a 1x1 convolution with unit stride and no padding).
+template <int ROWS>
+struct KPosDenseProducer {
+	static constexpr int NR = ROWS / NPROD_WARPS;
+	static constexpr int NV = NR;
+	int warp, lane, nvalid;
+	long long rowoff0, step;
+
+	__device__ __forceinline__ void init(const Operand& op, int tile_row0, int warp_, int lane_, uint32_t)
+	{
+		warp = warp_;
+		lane = lane_;
+		const int row0 = tile_row0 + warp_;
+		rowoff0 = (long long)row0 * op.rs0;
+		step = (long long)NPROD_WARPS * op.rs0 * 4;
+		const int left = op.rows - row0;
+		nvalid = left <= 0 ? 0 : min(NR, (left + NPROD_WARPS - 1) / NPROD_WARPS);
+	}
+	__device__ __forceinline__ void load(const Operand& op, const float* __restrict__ base, int kb, float (&v)[NV])
+	{
+		const uint32_t n = fdiv((uint32_t)kb, op.kbdiv);              // warp-uniform
+		const int pos = (int)((uint32_t)kb - n * op.kbdiv.d) * BK + lane;
+		const int cnt = pos < op.plane ? nvalid : 0;
+		const char* __restrict__ p = reinterpret_cast<const char*>(base + (rowoff0 + (long long)n * op.ks0 + pos));
+		#pragma unroll
+		for (int i = 0; i < NR; i++) {
+			v[i] = i < cnt ? __ldg(reinterpret_cast<const float*>(p)) : 0.0f;
+			p += step;
+		}
+	}
+	__device__ __forceinline__ void store(uint32_t tile, const float (&v)[NV])
+	{
+		const uint32_t col = ((((uint32_t)lane >> 2) ^ ((uint32_t)warp & 7)) << 4) | (((uint32_t)lane & 3) << 2);
+		#pragma unroll
+		for (int i = 0; i < NR; i++) sts32(tile + (warp + i * NPROD_WARPS) * 128 + col, to_tf32(v[i]));
+	}
+};
+
+// KPosTap: rows = (c, r, s) filter taps of x (any stride / padding / dilation); per-row offsets + tap ids in a smem table.
+template <int ROWS, bool WIDE>
+struct KPosTapProducer {
+	using TM = TapMask<WIDE>;
+	static constexpr int NR = ROWS / NPROD_WARPS;
+	static constexpr int NV = NR;
+	int warp, lane;
+	uint32_t table;
+
+	__device__ __forceinline__ void init(const Operand& op, int tile_row0, int warp_, int lane_, uint32_t table_)
+	{
+		warp = warp_;
+		lane = lane_;
+		table = table_;
+		const int t = warp * 32 + lane;
+		if (t < ROWS) {
+			const int row = tile_row0 + t;
+			uint32_t entry = 0u;
+			if (row < op.rows) {
+				const uint32_t c = fdiv((uint32_t)row, op.rd12);
+				const uint32_t tp = (uint32_t)row - c * op.rd12.d;
+				const uint32_t r = fdiv(tp, op.rd2);
+				const uint32_t s = tp - r * op.rd2.d;
+				const int roff = (int)c * op.rs0 + (int)r * op.ah * op.Wd + (int)s * op.aw - tap_min(op.R, op.S, op.ah * op.Wd, op.aw);
+				entry = ((uint32_t)roff << TM::SH) | (TM::TOP - tp);
+			}
+			sts32(table + t * 4, entry);
+		}
+	}
+	__device__ __forceinline__ void load(const Operand& op, const float* __restrict__ base, int kb, float (&v)[NV])
+	{
+		const uint32_t n = fdiv((uint32_t)kb, op.kbdiv);              // warp-uniform
+		const int pos = (int)((uint32_t)kb - n * op.kbdiv.d) * BK + lane;
+		const bool pvalid = pos < op.plane;
+		const uint32_t pp = fdiv((uint32_t)(pvalid ? pos : 0), op.kd2);
+		const int qq = (pvalid ? pos : 0) - (int)pp * (int)op.kd2.d;
+		const int hk = (int)pp * op.bh + op.ch, wk = qq * op.bw + op.cw;
+		TM mask;
+		mask.clear();
+		if (pvalid) {
+			// valid(r, s) = vh(r) & vw(s): build the row of column bits once, then place it for every valid filter row
+			TM wm;
+			wm.clear();
+			for (int s = 0; s < op.S; s++)
+				if ((unsigned)(wk + s * op.aw) < (unsigned)op.W) wm.set(s);
+			for (int r = 0; r < op.R; r++)
+				if ((unsigned)(hk + r * op.ah) < (unsigned)op.H) mask.m |= wm.m << (r * op.S);
+		}
+		const char* __restrict__ sb = reinterpret_cast<const char*>(
+			base + ((long long)n * op.ks0 + hk * op.Wd + wk + tap_min(op.R, op.S, op.ah * op.Wd, op.aw)));
+		#pragma unroll
+		for (int i = 0; i < NR; i++) {
+			uint32_t ent;
+			asm volatile("ld.shared.b32 %0, [%1];" : "=r"(ent) : "r"(table + (warp + i * NPROD_WARPS) * 4));
+			v[i] = mask.test(ent) ? ldg_off(sb, ent >> TM::SH) : 0.0f;
+		}
+	}
+	__device__ __forceinline__ void store(uint32_t tile, const float (&v)[NV])
+	{
+		const uint32_t col = ((((uint32_t)lane >> 2) ^ ((uint32_t)warp & 7)) << 4) | (((uint32_t)lane & 3) << 2);
+		#pragma unroll
+		for (int i = 0; i < NR; i++) sts32(tile + (warp + i * NPROD_WARPS) * 128 + col, to_tf32(v[i]));
+	}
+};
+
 // filter operand fetched by TMA from the prepared (tf32-rounded, zero-padded, K-major) copy: no per-thread state
 template <int ROWS>
 struct TmaProducer {
@@ -587,6 +762,9 @@ template <int ROWS, bool WIDE> struct ProducerSel<ROWS, MODE_MN_TAP, WIDE> { usi
 template <int ROWS, bool WIDE> struct ProducerSel<ROWS, MODE_K_TAP, WIDE> { using type = KTapProducer<ROWS, WIDE>; };
 template <int ROWS, bool WIDE> struct ProducerSel<ROWS, MODE_K_DENSE, WIDE> { using type = KDenseProducer<ROWS>; };
 template <int ROWS, bool WIDE> struct ProducerSel<ROWS, MODE_TMA, WIDE> { using type = TmaProducer<ROWS>; };
+template <int ROWS, bool WIDE> struct ProducerSel<ROWS, MODE_MN_CHAN, WIDE> { using type = MnChanProducer<ROWS, WIDE>; };
+template <int ROWS, bool WIDE> struct ProducerSel<ROWS, MODE_K_POS_TAP, WIDE> { using type = KPosTapProducer<ROWS, WIDE>; };
+template <int ROWS, bool WIDE> struct ProducerSel<ROWS, MODE_K_POS_DENSE, WIDE> { using type = KPosDenseProducer<ROWS>; };
 
 template <int BN> struct Cfg {
 	static constexpr int STAGE_BYTES = (BM + BN) * 128;
