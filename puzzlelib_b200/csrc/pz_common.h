@@ -46,6 +46,9 @@ void pz_set_error(int code, const char* fmt, ...);
 static inline cudaStream_t pz_stream(void* s) { return (cudaStream_t)s; }
 
 int pz_num_sms();
+// library-owned device scratch, grown on demand and used in stream order (prepared conv filters, pooling winner maps);
+// nullptr when the allocation fails
+void* pz_scratch(size_t bytes);
 void pz_count_launch(int n);
 
 // ---- optional per-launch profiling (bench.py roofline): CUDA events around the launches of one kernel family

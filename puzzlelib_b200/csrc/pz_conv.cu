@@ -137,6 +137,16 @@ __global__ void prep_filter_dgrad(const float* __restrict__ w, float* __restrict
 	wt[i] = v;
 }
 
+// col2im dgrad: wt[(c, r, s)][ko] = w[ko][c][r][s] (the filter transposed), rows of kpad elements
+__global__ void prep_filter_col2im(const float* __restrict__ w, float* __restrict__ wt, int K, int CRS, int kpad, long long total)
+{
+	long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= total) return;
+	const int ko = (int)(i % kpad);
+	const long long row = i / kpad;
+	wt[i] = ko < K ? __uint_as_float(to_tf32(w[(long long)ko * CRS + row])) : 0.0f;
+}
+
 // the (tap, channel) k order pads the channels of every tap to a multiple of 32: worth it unless the channel count is tiny
 inline bool use_chan_order(int chans) { return round_up32_c(chans) * 3 <= chans * 4; }
 
@@ -324,6 +334,57 @@ int pz_conv2d_dgrad(int dtype, const pz_conv2d_desc* d, const void* dy, const vo
 		const bool cdiv = mode == 2 ? strided : Rc * Sc > 31;
 		return launch(q, bn, mode == 2 ? MODE_MN_GENERAL : (chan ? MODE_MN_CHAN : MODE_MN_TAP), MODE_TMA, cdiv, g.G, &tsrc, pz_stream(stream));
 	};
+
+	if (g.G == 1 && g.C <= 4 && g.C * RS <= 256 && RS > 1 && bias == nullptr && use_chan_order(g.K) && tap_entries_fit(34ll * PQ, g)) {
+		// Very few input channels (the first layer of a network): the implicit GEMM over (n, h, w) x c would gather every dy
+		// element R*S times for a handful of output columns.  Instead  D[(n,p,q)][(c,r,s)] = sum_k dy[n,k,p,q] * w[k,c,r,s]
+		// reads dy exactly once (a 1x1-convolution-shaped GEMM) and the epilogue scatters D into dx (col2im) with red.add.
+		st = pz_memset8(dx, 0, (size_t)g.N * g.C * HW * 4, stream);
+		if (st != PZ_OK) return st;
+		const int crs = g.C * RS, kpad = round_up32(g.K);
+		const long long total = (long long)crs * kpad;
+		float* wt = scratch((size_t)total * sizeof(float));
+		if (!wt) { pz_set_error(PZ_ERR_MEMORY, "conv2d dgrad: cannot allocate filter scratch"); return PZ_ERR_MEMORY; }
+		prep_filter_col2im<<<(unsigned)pz_cdiv(total, 256), 256, 0, pz_stream(stream)>>>((const float*)w, wt, g.K, crs, kpad, total);
+		pz_count_launch(1);
+		PZ_LAUNCH_CHECK();
+
+		GemmParams q{};
+		Operand& QA = q.A;                 // rows (n, p, q) of dy, k = ko: a 1x1 "convolution" over dy
+		QA.ptr = (const float*)dy;
+		QA.rd12 = make_fastdiv(PQ); QA.rd2 = make_fastdiv(g.Q);
+		QA.kd12 = make_fastdiv(1); QA.kd2 = make_fastdiv(1);
+		QA.rs0 = g.K * PQ; QA.ks0 = PQ;
+		QA.ah = 1; QA.bh = 1; QA.ch = 0;
+		QA.aw = 1; QA.bw = 1; QA.cw = 0;
+		QA.H = g.P; QA.W = g.Q; QA.Wd = g.Q;
+		QA.cdh = QA.cdw = 1;
+		QA.rows = g.N * PQ; QA.kdim = g.K;
+		QA.R = 1; QA.S = 1;
+		QA.chans = g.K;
+		QA.kbdiv = make_fastdiv((uint32_t)(kpad / 32));
+		QA.group_stride = 0;
+
+		q.E = E;
+		q.E.out = (float*)dx;
+		q.E.md12 = make_fastdiv(PQ); q.E.md2 = make_fastdiv(g.Q);
+		q.E.ms0 = g.C * HW; q.E.ms1 = 0; q.E.ms2 = 0;
+		q.E.ncs = 0;
+		q.E.M = g.N * PQ; q.E.N = crs;
+		q.E.c2i = 1;
+		q.E.c2i_sh = g.sh; q.E.c2i_sw = g.sw; q.E.c2i_ph = g.ph; q.E.c2i_pw = g.pw; q.E.c2i_dh = g.dh; q.E.c2i_dw = g.dw;
+		q.E.c2i_H = g.H; q.E.c2i_W = g.W;
+		q.E.c2i_rs = make_fastdiv((uint32_t)RS); q.E.c2i_s = make_fastdiv((uint32_t)g.S);
+		q.splits = 1;
+		q.kblocks = kpad / BK;
+		q.kb_per_split = q.kblocks;
+		q.tma_rows_per_group = crs;
+		q.alg_flops = 2.0 * (double)g.N * PQ * g.K * crs;
+		q.alg_bytes = 4.0 * ((double)g.N * g.K * PQ + (double)g.K * crs + (double)g.N * g.C * HW);
+		const TmaSource tsrc{wt, crs, kpad};
+		const int bn = crs <= 64 ? 64 : (crs <= 128 ? 128 : 256);
+		return launch(q, bn, MODE_MN_CHAN, MODE_TMA, false, 1, &tsrc, pz_stream(stream));
+	}
 
 	if (is1x1 && g.ph == 0 && g.pw == 0 && strided) {
 		// 1x1 strided: dx[n,c,p*sh,q*sw] = sum_k dy[n,k,p,q] * w[k,c]; all other positions of dx are zero (+ bias)

@@ -67,20 +67,7 @@ int pick_bn(int n, long long m_rows, int kblocks, int groups, int max_bn)
 	return best;
 }
 
-// library-owned scratch for prepared filters.  Use is stream-ordered: the prep kernel that writes it and the GEMM that reads
-// it are enqueued back to back on the caller's stream (the reference runs everything on the legacy default stream).
-float* scratch(size_t bytes)
-{
-	static float* buf = nullptr;
-	static size_t cap = 0;
-	if (bytes > cap) {
-		if (buf) { cudaDeviceSynchronize(); cudaFree(buf); buf = nullptr; cap = 0; }
-		size_t want = bytes < ((size_t)64 << 20) ? ((size_t)64 << 20) : bytes + (bytes >> 2);
-		if (cudaMalloc((void**)&buf, want) != cudaSuccess) { buf = nullptr; return nullptr; }
-		cap = want;
-	}
-	return buf;
-}
+float* scratch(size_t bytes) { return (float*)pz_scratch(bytes); }
 
 template <int BN, int AM, int BMODE, bool CDIV>
 static int launch_inst(const GemmParams& p, const CUtensorMap& tmap, int grid, cudaStream_t stream)

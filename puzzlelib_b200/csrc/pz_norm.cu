@@ -3,27 +3,35 @@
 // Replaces cudnnBatchNormalizationForwardTraining / ForwardInference / Backward as called from
 // CuDnn_Context_batchNormNd / _batchNormNdBackward (reference Cuda/Source/Libs/CuDnnNorm.c:31-71,158-194).
 //
-// B200 design: one thread-block CLUSTER per channel.  The N planes of a channel are dealt out to the CTAs
-// of the cluster; each CTA reduces its planes with 128-bit loads + warp shuffles, the per-CTA partials are
-// combined through distributed shared memory (every CTA reads all partials in rank order, so all CTAs hold
-// the same bits and no global atomics / second launch are needed), and the same CTA immediately re-reads
-// its planes - still resident in the 126 MB L2 - to write the normalised output.  DRAM traffic is therefore
-// the algorithmic one: read x once + write y once (forward), read x, dy once + write dx once (backward).
+// B200 design.  An NCHW tensor is the matrix [N rows][C*S columns]: row n is contiguous, column j belongs to channel
+// j / S.  A thread owns VEC consecutive columns (one 128-bit vector) and walks over rows, so
+//   * every load / store is a fully coalesced, 16-byte aligned vector whatever the plane size (7x7 planes are as
+//     efficient as 112x112 ones -- no per-plane head / tail handling),
+//   * the channels of a thread's columns never change: per-channel coefficients live in registers for the whole walk,
+//   * the row loop is unrolled, giving 8 independent 128-bit loads in flight per thread.
+// Two kernels per pass: `stats` (column sums over its rows -> shared-memory per-channel bins -> fp32 red.add into a
+// [C][2] buffer) and `apply` (normalise / input gradient, pure streaming).  Both are persistent: the work items
+// (column block x group of 8 rows) are dealt out evenly to SMs x 8 CTAs, consecutive items of a CTA share the column
+// block, so registers carry the partial sums / coefficients across them (measured on B200: splitting a tensor into
+// L2-sized channel slabs to save the second DRAM read costs more in launch ramps than it saves; PZ_BN_SLAB_MB).
+// Statistics are accumulated around a per-channel pivot (the channel's first element) so that E[d^2] - E[d]^2 does
+// not cancel when |mean| >> std.
 #include "pz_common.h"
 
-#include <cooperative_groups.h>
-
-namespace cg = cooperative_groups;
+#include <cstdlib>
+#include <initializer_list>
+#include <mutex>
 
 namespace {
 
-constexpr int kThreads = 512;
-constexpr int kMaxCluster = 8;
-
-template <typename T> struct VecOf;
-template <> struct VecOf<float> { static constexpr int N = 4; };
-template <> struct VecOf<__half> { static constexpr int N = 8; };
-template <> struct VecOf<__nv_bfloat16> { static constexpr int N = 8; };
+constexpr int kThreads = 256;
+constexpr int kRowUnroll = 8;
+// tensor bytes per slab that the apply kernel re-reads from L2 (PZ_BN_SLAB_MB overrides, for tuning)
+double slab_bytes()
+{
+	static const double v = [] { const char* e = getenv("PZ_BN_SLAB_MB"); return (e ? atof(e) : 1e9) * 1024 * 1024; }();
+	return v;
+}
 
 template <typename T> __device__ __forceinline__ float to_f(T v);
 template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
@@ -34,57 +42,23 @@ template <> __device__ __forceinline__ float from_f<float>(float v) { return v; 
 template <> __device__ __forceinline__ __half from_f<__half>(float v) { return __float2half_rn(v); }
 template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 
-template <typename T> struct alignas(16) Pack { T v[16 / sizeof(T)]; };
+template <typename T, int VEC> struct alignas(sizeof(T) * VEC) Pack { T v[VEC]; };
 
-// Visit every element of a plane of S elements with a group of `gsize` threads (rank `gi` in the group).
-// body(i, vec) is called for 16-byte aligned packs, tail(i) for the unaligned head / tail elements.
-template <typename T, typename FV, typename FS>
-__device__ __forceinline__ void plane_visit(const T* plane, int64_t S, int gi, int gsize, bool vec_ok, FV body, FS tail)
+struct FastDiv32 { uint32_t d, m, sh; };     // d == 1: identity
+
+inline FastDiv32 make_fastdiv32(uint32_t d)
 {
-	constexpr int V = VecOf<T>::N;
-	int64_t head = 0, nvec = 0;
-	if (vec_ok) {
-		uintptr_t mis = ((uintptr_t)plane % 16) / sizeof(T);
-		head = mis ? (int64_t)(V - mis) : 0;
-		if (head > S) head = S;
-		nvec = (S - head) / V;
-	}
-	#pragma unroll 4
-	for (int64_t v = gi; v < nvec; v += gsize) body(head + v * V);      // unrolled: 4 independent 128-bit loads in flight
-	const int64_t tailstart = head + nvec * V;
-	const int64_t nscalar = head + (S - tailstart);
-	for (int64_t s = gi; s < nscalar; s += gsize) tail(s < head ? s : tailstart + (s - head));
+	FastDiv32 f{d, 0, 0};
+	if (d <= 1) return f;
+	uint32_t s = 0;
+	while ((1ull << s) < d) s++;
+	const uint32_t p = 31 + s;
+	f.m = (uint32_t)(((1ull << p) + d - 1) / d);
+	f.sh = p - 32;
+	return f;
 }
-
-// ---- Chan et al. parallel (count, mean, M2) combination
-struct Moments { float n, mean, m2; };
-
-__device__ __forceinline__ Moments combine(const Moments& a, const Moments& b)
-{
-	Moments r;
-	r.n = a.n + b.n;
-	if (r.n == 0.0f) { r.mean = 0.0f; r.m2 = 0.0f; return r; }
-	float delta = b.mean - a.mean;
-	float frac = b.n / r.n;
-	r.mean = a.mean + delta * frac;
-	r.m2 = a.m2 + b.m2 + delta * delta * a.n * frac;
-	return r;
-}
-
-__device__ __forceinline__ Moments warp_combine(Moments m)
-{
-	#pragma unroll
-	for (int o = 16; o > 0; o >>= 1) {
-		Moments other;
-		other.n = __shfl_xor_sync(0xffffffffu, m.n, o);
-		other.mean = __shfl_xor_sync(0xffffffffu, m.mean, o);
-		other.m2 = __shfl_xor_sync(0xffffffffu, m.m2, o);
-		// order the pair by lane so that both lanes compute bit-identical results
-		bool lower = (threadIdx.x & o) == 0;
-		m = lower ? combine(m, other) : combine(other, m);
-	}
-	return m;
-}
+// exact for n < 2^31
+__device__ __forceinline__ uint32_t fdiv32(uint32_t n, const FastDiv32& f) { return f.d == 1 ? n : (__umulhi(n, f.m) >> f.sh); }
 
 __device__ __forceinline__ float warp_sum(float v)
 {
@@ -93,282 +67,464 @@ __device__ __forceinline__ float warp_sum(float v)
 	return v;
 }
 
-struct PlaneSplit {
-	int64_t first, count;  // this CTA handles planes n = first, first + 1, ... (count of them) of its channel
+// geometry of one launch: columns [col0, col0 + ncols) of the [N][C*S] matrix, rows split over gridDim.y
+struct Slab {
+	int64_t row_stride;      // C * S elements
+	int N, rows_per_block;
+	uint32_t col0, ncols;    // columns of this slab (col0 is a multiple of VEC and of S)
+	FastDiv32 sdiv;          // S
+	uint32_t S;
+	int row_groups, items, items_per_cta;   // persistent schedule: item = col_block * row_groups + row_group
 };
 
-__device__ __forceinline__ PlaneSplit split_planes(int64_t N, unsigned rank, unsigned csize)
+// the CTA's contiguous range of work items
+struct ItemRange { int begin, end; };
+__device__ __forceinline__ ItemRange my_items(const Slab& g)
 {
-	int64_t base = N / csize, rem = N % csize;
-	PlaneSplit p;
-	p.first = rank * base + (rank < rem ? rank : rem);
-	p.count = base + (rank < rem ? 1 : 0);
+	ItemRange r;
+	r.begin = blockIdx.x * g.items_per_cta;
+	r.end = min(g.items, r.begin + g.items_per_cta);
+	return r;
+}
+
+// adds the VEC per-column partial sums (a[e], b[e]) of a thread into the per-channel bins of the CTA and then into the global
+// [C][2] buffer.  ch[e] is non-decreasing in e and across the threads of the CTA.
+template <int VEC>
+__device__ __forceinline__ void reduce_to_channels(const float (&a)[VEC], const float (&b)[VEC], const int (&ch)[VEC], bool active,
+												   float* bins /* smem [nbins][2] */, int nbins, int ch_base, float* sums)
+{
+	for (int i = threadIdx.x; i < nbins * 2; i += kThreads) bins[i] = 0.0f;
+	__syncthreads();
+	// fast path: the whole warp works on one channel -> shuffle reduction, one shared-memory atomic per warp
+	const int first = __shfl_sync(0xffffffffu, active ? ch[0] : -1, 0);
+	const bool uniform = __all_sync(0xffffffffu, active && ch[0] == first && ch[VEC - 1] == first);
+	if (uniform) {
+		float sa = 0.0f, sb = 0.0f;
+		#pragma unroll
+		for (int e = 0; e < VEC; e++) { sa += a[e]; sb += b[e]; }
+		sa = warp_sum(sa);
+		sb = warp_sum(sb);
+		if ((threadIdx.x & 31) == 0) {
+			atomicAdd(&bins[(first - ch_base) * 2], sa);
+			atomicAdd(&bins[(first - ch_base) * 2 + 1], sb);
+		}
+	} else if (active) {
+		float sa = a[0], sb = b[0];
+		#pragma unroll
+		for (int e = 1; e < VEC; e++) {
+			if (ch[e] != ch[e - 1]) {
+				atomicAdd(&bins[(ch[e - 1] - ch_base) * 2], sa);
+				atomicAdd(&bins[(ch[e - 1] - ch_base) * 2 + 1], sb);
+				sa = 0.0f;
+				sb = 0.0f;
+			}
+			sa += a[e];
+			sb += b[e];
+		}
+		atomicAdd(&bins[(ch[VEC - 1] - ch_base) * 2], sa);
+		atomicAdd(&bins[(ch[VEC - 1] - ch_base) * 2 + 1], sb);
+	}
+	__syncthreads();
+	for (int i = threadIdx.x; i < nbins * 2; i += kThreads) {
+		const float v = bins[i];
+		if (v != 0.0f) atomicAdd(&sums[(size_t)ch_base * 2 + i], v);
+	}
+}
+
+// number of per-channel bins a CTA of kThreads * VEC consecutive columns can touch
+__host__ __device__ inline int bins_per_block(int vec, uint32_t S) { return (int)((uint32_t)(kThreads * vec - 1) / S) + 2; }
+
+// ------------------------------------------------------------------------------------------ forward statistics
+// sums[c] = { sum(x - pivot_c), sum((x - pivot_c)^2) } over the rows of this block
+template <typename T, int VEC>
+__global__ void __launch_bounds__(kThreads) bn_stats_kernel(const T* __restrict__ x, Slab g, float* __restrict__ sums)
+{
+	extern __shared__ float bins[];
+	const ItemRange ir = my_items(g);
+	int cur = -1, ch_base = 0;
+	uint32_t j = 0;
+	bool active = false;
+	int ch[VEC];
+	float pivot[VEC], s1[VEC], s2[VEC];
+	for (int it = ir.begin; it < ir.end; it++) {
+		const int cb = it / g.row_groups, rg = it - cb * g.row_groups;
+		if (cb != cur) {
+			if (cur >= 0) reduce_to_channels<VEC>(s1, s2, ch, active, bins, bins_per_block(VEC, g.S), ch_base, sums);
+			cur = cb;
+			j = g.col0 + ((uint32_t)cb * kThreads + threadIdx.x) * VEC;
+			active = j < g.col0 + g.ncols;
+			ch_base = (int)fdiv32(g.col0 + (uint32_t)cb * kThreads * VEC, g.sdiv);
+			#pragma unroll
+			for (int e = 0; e < VEC; e++) {
+				ch[e] = (int)fdiv32(active ? j + e : g.col0, g.sdiv);
+				pivot[e] = to_f<T>(x[(size_t)ch[e] * g.S]);
+				s1[e] = 0.0f;
+				s2[e] = 0.0f;
+			}
+		}
+		if (!active) continue;
+		const int r0 = rg * kRowUnroll, r1 = min(g.N, r0 + kRowUnroll);
+		const T* p = x + (size_t)r0 * g.row_stride + j;
+		if (r1 - r0 == kRowUnroll) {
+			Pack<T, VEC> v[kRowUnroll];
+			#pragma unroll
+			for (int u = 0; u < kRowUnroll; u++) v[u] = *reinterpret_cast<const Pack<T, VEC>*>(p + (size_t)u * g.row_stride);
+			#pragma unroll
+			for (int u = 0; u < kRowUnroll; u++) {
+				#pragma unroll
+				for (int e = 0; e < VEC; e++) { const float d = to_f<T>(v[u].v[e]) - pivot[e]; s1[e] += d; s2[e] = fmaf(d, d, s2[e]); }
+			}
+		} else {
+			for (int r = r0; r < r1; r++) {
+				const Pack<T, VEC> v = *reinterpret_cast<const Pack<T, VEC>*>(p);
+				#pragma unroll
+				for (int e = 0; e < VEC; e++) { const float d = to_f<T>(v.v[e]) - pivot[e]; s1[e] += d; s2[e] = fmaf(d, d, s2[e]); }
+				p += g.row_stride;
+			}
+		}
+	}
+	if (cur >= 0) reduce_to_channels<VEC>(s1, s2, ch, active, bins, bins_per_block(VEC, g.S), ch_base, sums);
+}
+
+// ------------------------------------------------------------------------------------------ forward apply
+// TRAIN: coefficients from the accumulated sums (+ writes the saved / running statistics once per channel);
+// otherwise from the given mean / var (inference).
+template <typename T, int VEC, bool TRAIN>
+__global__ void __launch_bounds__(kThreads) bn_apply_kernel(const T* __restrict__ x, T* __restrict__ y, Slab g,
+															const float* __restrict__ sums, const float* __restrict__ scale,
+															const float* __restrict__ bias, float* mean_io, float* var_io, float* save_mean,
+															float* save_invvar, float eps, float factor, float count)
+{
+	const ItemRange ir = my_items(g);
+	int cur = -1;
+	uint32_t j = 0;
+	bool active = false;
+	float a[VEC], b[VEC];
+	for (int it = ir.begin; it < ir.end; it++) {
+		const int cb = it / g.row_groups, rg = it - cb * g.row_groups;
+		if (cb != cur) {
+			cur = cb;
+			j = g.col0 + ((uint32_t)cb * kThreads + threadIdx.x) * VEC;
+			active = j < g.col0 + g.ncols;
+			if (active) {
+				#pragma unroll
+				for (int e = 0; e < VEC; e++) {
+					const int c = (int)fdiv32(j + e, g.sdiv);
+					float mean, invstd;
+					if (TRAIN) {
+						const float pivot = to_f<T>(x[(size_t)c * g.S]);
+						const float dmean = sums[2 * c] / count;
+						mean = pivot + dmean;
+						const float var = fmaxf(sums[2 * c + 1] / count - dmean * dmean, 0.0f);      // biased, used for normalisation
+						invstd = 1.0f / sqrtf(var + eps);
+						if (rg == 0 && j + e == (uint32_t)c * g.S) {
+							save_mean[c] = mean;
+							save_invvar[c] = invstd;
+							// cuDNN keeps the UNBIASED variance in the running estimate
+							const float uvar = count > 1.0f ? var * (count / (count - 1.0f)) : var;
+							mean_io[c] = (1.0f - factor) * mean_io[c] + factor * mean;
+							var_io[c] = (1.0f - factor) * var_io[c] + factor * uvar;
+						}
+					} else {
+						mean = mean_io[c];
+						invstd = 1.0f / sqrtf(var_io[c] + eps);
+					}
+					a[e] = scale[c] * invstd;
+					b[e] = bias[c] - mean * a[e];
+				}
+			}
+		}
+		if (!active) continue;
+		const int r0 = rg * kRowUnroll, r1 = min(g.N, r0 + kRowUnroll);
+		const T* p = x + (size_t)r0 * g.row_stride + j;
+		T* q = y + (size_t)r0 * g.row_stride + j;
+		if (r1 - r0 == kRowUnroll) {
+			Pack<T, VEC> v[kRowUnroll];
+			#pragma unroll
+			for (int u = 0; u < kRowUnroll; u++) v[u] = *reinterpret_cast<const Pack<T, VEC>*>(p + (size_t)u * g.row_stride);
+			#pragma unroll
+			for (int u = 0; u < kRowUnroll; u++) {
+				#pragma unroll
+				for (int e = 0; e < VEC; e++) v[u].v[e] = from_f<T>(fmaf(to_f<T>(v[u].v[e]), a[e], b[e]));
+				*reinterpret_cast<Pack<T, VEC>*>(q + (size_t)u * g.row_stride) = v[u];
+			}
+		} else {
+			for (int r = r0; r < r1; r++) {
+				Pack<T, VEC> v = *reinterpret_cast<const Pack<T, VEC>*>(p);
+				#pragma unroll
+				for (int e = 0; e < VEC; e++) v.v[e] = from_f<T>(fmaf(to_f<T>(v.v[e]), a[e], b[e]));
+				*reinterpret_cast<Pack<T, VEC>*>(q) = v;
+				p += g.row_stride;
+				q += g.row_stride;
+			}
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------ backward statistics
+// sums[c] = { sum(dy), sum(dy * (x - mean_c)) }
+template <typename T, int VEC>
+__global__ void __launch_bounds__(kThreads) bn_bwd_stats_kernel(const T* __restrict__ x, const T* __restrict__ dy, Slab g,
+																const float* __restrict__ save_mean, float* __restrict__ sums)
+{
+	extern __shared__ float bins[];
+	constexpr int UNR = kRowUnroll / 2;          // two tensors are read per row: 2 x 4 loads in flight
+	const ItemRange ir = my_items(g);
+	int cur = -1, ch_base = 0;
+	uint32_t j = 0;
+	bool active = false;
+	int ch[VEC];
+	float mean[VEC], s1[VEC], s2[VEC];
+	for (int it = ir.begin; it < ir.end; it++) {
+		const int cb = it / g.row_groups, rg = it - cb * g.row_groups;
+		if (cb != cur) {
+			if (cur >= 0) reduce_to_channels<VEC>(s1, s2, ch, active, bins, bins_per_block(VEC, g.S), ch_base, sums);
+			cur = cb;
+			j = g.col0 + ((uint32_t)cb * kThreads + threadIdx.x) * VEC;
+			active = j < g.col0 + g.ncols;
+			ch_base = (int)fdiv32(g.col0 + (uint32_t)cb * kThreads * VEC, g.sdiv);
+			#pragma unroll
+			for (int e = 0; e < VEC; e++) {
+				ch[e] = (int)fdiv32(active ? j + e : g.col0, g.sdiv);
+				mean[e] = save_mean[ch[e]];
+				s1[e] = 0.0f;
+				s2[e] = 0.0f;
+			}
+		}
+		if (!active) continue;
+		const int r0 = rg * kRowUnroll, r1 = min(g.N, r0 + kRowUnroll);
+		const size_t off = (size_t)r0 * g.row_stride + j;
+		const T* p = x + off;
+		const T* q = dy + off;
+		int r = r0;
+		for (; r + UNR <= r1; r += UNR) {
+			Pack<T, VEC> v[UNR], w[UNR];
+			#pragma unroll
+			for (int u = 0; u < UNR; u++) {
+				v[u] = *reinterpret_cast<const Pack<T, VEC>*>(p + (size_t)u * g.row_stride);
+				w[u] = *reinterpret_cast<const Pack<T, VEC>*>(q + (size_t)u * g.row_stride);
+			}
+			#pragma unroll
+			for (int u = 0; u < UNR; u++) {
+				#pragma unroll
+				for (int e = 0; e < VEC; e++) {
+					const float gv = to_f<T>(w[u].v[e]);
+					s1[e] += gv;
+					s2[e] = fmaf(gv, to_f<T>(v[u].v[e]) - mean[e], s2[e]);
+				}
+			}
+			p += (size_t)UNR * g.row_stride;
+			q += (size_t)UNR * g.row_stride;
+		}
+		for (; r < r1; r++) {
+			const Pack<T, VEC> v = *reinterpret_cast<const Pack<T, VEC>*>(p);
+			const Pack<T, VEC> w = *reinterpret_cast<const Pack<T, VEC>*>(q);
+			#pragma unroll
+			for (int e = 0; e < VEC; e++) {
+				const float gv = to_f<T>(w.v[e]);
+				s1[e] += gv;
+				s2[e] = fmaf(gv, to_f<T>(v.v[e]) - mean[e], s2[e]);
+			}
+			p += g.row_stride;
+			q += g.row_stride;
+		}
+	}
+	if (cur >= 0) reduce_to_channels<VEC>(s1, s2, ch, active, bins, bins_per_block(VEC, g.S), ch_base, sums);
+}
+
+// ------------------------------------------------------------------------------------------ backward apply
+// dx = c1*dy - c2 - (x - mean)*c3 with c1 = scale*invstd, c2 = c1*sum(dy)/m, c3 = c1*invstd^2*sum(dy*(x-mean))/m
+template <typename T, int VEC>
+__global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx,
+																Slab g, const float* __restrict__ sums, const float* __restrict__ scale,
+																const float* __restrict__ save_mean, const float* __restrict__ save_invvar,
+																float* dscale, float* dbias, float count)
+{
+	constexpr int UNR = kRowUnroll / 2;
+	const ItemRange ir = my_items(g);
+	int cur = -1;
+	uint32_t j = 0;
+	bool active = false;
+	float c1[VEC], c2[VEC], c3[VEC], mean[VEC];
+	for (int it = ir.begin; it < ir.end; it++) {
+		const int cb = it / g.row_groups, rg = it - cb * g.row_groups;
+		if (cb != cur) {
+			cur = cb;
+			j = g.col0 + ((uint32_t)cb * kThreads + threadIdx.x) * VEC;
+			active = j < g.col0 + g.ncols;
+			if (active) {
+				#pragma unroll
+				for (int e = 0; e < VEC; e++) {
+					const int c = (int)fdiv32(j + e, g.sdiv);
+					const float invstd = save_invvar[c];
+					const float tdy = sums[2 * c], tdyx = sums[2 * c + 1];
+					const float dsc = tdyx * invstd;        // sum(dy * xhat)
+					mean[e] = save_mean[c];
+					c1[e] = scale[c] * invstd;
+					c2[e] = c1[e] * tdy / count;
+					c3[e] = c1[e] * dsc / count * invstd;
+					if (rg == 0 && j + e == (uint32_t)c * g.S) { dscale[c] = dsc; dbias[c] = tdy; }
+				}
+			}
+		}
+		if (!active) continue;
+		const int r0 = rg * kRowUnroll, r1 = min(g.N, r0 + kRowUnroll);
+		const size_t off = (size_t)r0 * g.row_stride + j;
+		const T* p = x + off;
+		const T* q = dy + off;
+		T* o = dx + off;
+		int r = r0;
+		for (; r + UNR <= r1; r += UNR) {
+			Pack<T, VEC> v[UNR], w[UNR];
+			#pragma unroll
+			for (int u = 0; u < UNR; u++) {
+				v[u] = *reinterpret_cast<const Pack<T, VEC>*>(p + (size_t)u * g.row_stride);
+				w[u] = *reinterpret_cast<const Pack<T, VEC>*>(q + (size_t)u * g.row_stride);
+			}
+			#pragma unroll
+			for (int u = 0; u < UNR; u++) {
+				#pragma unroll
+				for (int e = 0; e < VEC; e++)
+					w[u].v[e] = from_f<T>(c1[e] * to_f<T>(w[u].v[e]) - c2[e] - (to_f<T>(v[u].v[e]) - mean[e]) * c3[e]);
+				*reinterpret_cast<Pack<T, VEC>*>(o + (size_t)u * g.row_stride) = w[u];
+			}
+			p += (size_t)UNR * g.row_stride;
+			q += (size_t)UNR * g.row_stride;
+			o += (size_t)UNR * g.row_stride;
+		}
+		for (; r < r1; r++) {
+			const Pack<T, VEC> v = *reinterpret_cast<const Pack<T, VEC>*>(p);
+			Pack<T, VEC> w = *reinterpret_cast<const Pack<T, VEC>*>(q);
+			#pragma unroll
+			for (int e = 0; e < VEC; e++) w.v[e] = from_f<T>(c1[e] * to_f<T>(w.v[e]) - c2[e] - (to_f<T>(v.v[e]) - mean[e]) * c3[e]);
+			*reinterpret_cast<Pack<T, VEC>*>(o) = w;
+			p += g.row_stride;
+			q += g.row_stride;
+			o += g.row_stride;
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------ host side
+// [C][2] fp32 accumulators, library-owned and used in stream order (zeroed by a memset before every pass)
+float* sums_buffer(int64_t C)
+{
+	static float* buf = nullptr;
+	static int64_t cap = 0;
+	static std::mutex mu;
+	std::lock_guard<std::mutex> lock(mu);
+	if (C > cap) {
+		if (buf) { cudaDeviceSynchronize(); cudaFree(buf); buf = nullptr; cap = 0; }
+		const int64_t want = C < 65536 ? 65536 : C + C / 2;
+		if (cudaMalloc((void**)&buf, (size_t)want * 2 * sizeof(float)) != cudaSuccess) return nullptr;
+		cap = want;
+	}
+	return buf;
+}
+
+struct Plan {
+	int vec;                 // columns per thread
+	int64_t slab_channels;   // channels per slab (all of them when the tensor fits)
+	int rows_per_block, row_blocks;
+};
+
+template <typename T>
+Plan make_plan(std::initializer_list<const void*> ptrs, int64_t N, int64_t C, int64_t S, int tensors)
+{
+	Plan p;
+	constexpr int V = 16 / sizeof(T);
+	bool aligned = (C * S) % V == 0;
+	for (const void* q : ptrs) aligned = aligned && ((uintptr_t)q % 16 == 0);
+	p.vec = aligned ? V : 1;
+
+	// slabs: whole channels, column start a multiple of the vector width, working set <= kSlabBytes
+	const double chan_bytes = (double)N * S * sizeof(T) * tensors;
+	int64_t sc = (int64_t)(slab_bytes() / chan_bytes);
+	if (sc >= C) sc = C;
+	else {
+		int64_t step = 1;                         // smallest channel count whose column count is a multiple of vec
+		while ((step * S) % p.vec != 0) step *= 2;
+		sc = sc / step * step;
+		if (sc < step) sc = step;
+		if (sc > C) sc = C;
+	}
+	p.slab_channels = sc;
+
+	p.rows_per_block = kRowUnroll;
+	p.row_blocks = (int)pz_cdiv(N, kRowUnroll);
 	return p;
 }
 
-// ------------------------------------------------------------------------------------------ forward, training
-template <typename T>
-__global__ void __launch_bounds__(kThreads) bn_fwd_train_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t N, int64_t C,
-																int64_t S, const float* __restrict__ scale,
-																const float* __restrict__ bias, float* running_mean,
-																float* running_var, float* save_mean, float* save_invvar,
-																float eps, float factor, int vec_ok, int warp_planes)
+Slab make_slab(const Plan& p, int64_t N, int64_t C, int64_t S, int64_t c0, int64_t c1)
 {
-	cg::cluster_group cluster = cg::this_cluster();
-	const unsigned rank = cluster.block_rank(), csize = cluster.num_blocks();
-	const int64_t c = blockIdx.y;
-	const PlaneSplit ps = split_planes(N, rank, csize);
-
-	const int gsize = warp_planes ? 32 : kThreads;
-	const int gi = warp_planes ? (threadIdx.x & 31) : threadIdx.x;
-	const int group = warp_planes ? (threadIdx.x >> 5) : 0;
-	const int ngroups = warp_planes ? kThreads / 32 : 1;
-
-	__shared__ Moments warp_part[kThreads / 32];
-	__shared__ Moments cta_part;       // read by the other CTAs of the cluster through DSMEM
-	__shared__ float coef[2];
-
-	// pass 1: sums of d = x - pivot and d^2 with a per-channel pivot (the channel's first element, identical for
-	// every thread of the cluster), so that E[d^2] - E[d]^2 does not cancel when |mean| >> std; plain sums combine
-	// associatively in a fixed order -> bit-identical statistics in every CTA of the cluster
-	const float pivot = to_f<T>(x[c * S]);
-	float s1 = 0.0f, s2 = 0.0f;
-	for (int64_t pl = group; pl < ps.count; pl += ngroups) {
-		const T* plane = x + ((ps.first + pl) * C + c) * S;
-		plane_visit<T>(plane, S, gi, gsize, vec_ok,
-			[&](int64_t i) {
-				Pack<T> p = *reinterpret_cast<const Pack<T>*>(plane + i);
-				#pragma unroll
-				for (int e = 0; e < VecOf<T>::N; e++) { float d = to_f<T>(p.v[e]) - pivot; s1 += d; s2 = fmaf(d, d, s2); }
-			},
-			[&](int64_t i) { float d = to_f<T>(plane[i]) - pivot; s1 += d; s2 = fmaf(d, d, s2); });
-	}
-	s1 = warp_sum(s1);
-	s2 = warp_sum(s2);
-	if ((threadIdx.x & 31) == 0) { warp_part[threadIdx.x >> 5].mean = s1; warp_part[threadIdx.x >> 5].m2 = s2; }
-	__syncthreads();
-	if (threadIdx.x == 0) {
-		float a = 0.0f, b = 0.0f;
-		for (int w = 0; w < kThreads / 32; w++) { a += warp_part[w].mean; b += warp_part[w].m2; }
-		cta_part.mean = a;
-		cta_part.m2 = b;
-	}
-	cluster.sync();
-	if (threadIdx.x == 0) {
-		float t1 = 0.0f, t2 = 0.0f;
-		for (unsigned r = 0; r < csize; r++) {
-			const Moments* remote = cluster.map_shared_rank(&cta_part, r);
-			t1 += remote->mean;
-			t2 += remote->m2;
-		}
-		const float cnt = (float)(N * S);
-		const float dmean = t1 / cnt;
-		const float mean = pivot + dmean;
-		const float var = fmaxf(t2 / cnt - dmean * dmean, 0.0f);            // biased, used for normalisation
-		const float invstd = 1.0f / sqrtf(var + eps);
-		const float a = scale[c] * invstd;
-		coef[0] = a;
-		coef[1] = bias[c] - mean * a;
-		if (rank == 0) {
-			save_mean[c] = mean;
-			save_invvar[c] = invstd;
-			// cuDNN keeps the UNBIASED variance in the running estimate
-			const float uvar = cnt > 1.0f ? var * (cnt / (cnt - 1.0f)) : var;
-			running_mean[c] = (1.0f - factor) * running_mean[c] + factor * mean;
-			running_var[c] = (1.0f - factor) * running_var[c] + factor * uvar;
-		}
-	}
-	cluster.sync();   // also keeps every cta_part alive until all remote reads are done
-	const float a = coef[0], b = coef[1];
-
-	// pass 2: the planes were just read by this CTA and are still in L2
-	for (int64_t pl = group; pl < ps.count; pl += ngroups) {
-		const int64_t off = ((ps.first + pl) * C + c) * S;
-		const T* plane = x + off;
-		T* out = y + off;
-		plane_visit<T>(plane, S, gi, gsize, vec_ok,
-			[&](int64_t i) {
-				Pack<T> p = *reinterpret_cast<const Pack<T>*>(plane + i);
-				#pragma unroll
-				for (int e = 0; e < VecOf<T>::N; e++) p.v[e] = from_f<T>(fmaf(to_f<T>(p.v[e]), a, b));
-				*reinterpret_cast<Pack<T>*>(out + i) = p;
-			},
-			[&](int64_t i) { out[i] = from_f<T>(fmaf(to_f<T>(plane[i]), a, b)); });
-	}
+	Slab g;
+	g.row_stride = C * S;
+	g.N = (int)N;
+	g.rows_per_block = p.rows_per_block;
+	g.col0 = (uint32_t)(c0 * S);
+	g.ncols = (uint32_t)((c1 - c0) * S);
+	g.sdiv = make_fastdiv32((uint32_t)S);
+	g.S = (uint32_t)S;
+	g.row_groups = p.row_blocks;
+	const int64_t col_blocks = pz_cdiv(g.ncols, (int64_t)kThreads * p.vec);
+	g.items = (int)(col_blocks * g.row_groups);
+	const int64_t ctas = (int64_t)pz_num_sms() * (2048 / kThreads);
+	g.items_per_cta = (int)pz_cdiv(g.items, ctas);
+	return g;
 }
 
-// ------------------------------------------------------------------------------------------ forward, inference
-template <typename T>
-__global__ void __launch_bounds__(256) bn_fwd_infer_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t planes, int64_t C,
-														   int64_t S, const float* __restrict__ scale,
-														   const float* __restrict__ bias, const float* __restrict__ mean,
-														   const float* __restrict__ var, float eps, int vec_ok)
-{
-	for (int64_t pl = blockIdx.x; pl < planes; pl += gridDim.x) {
-		const int64_t c = pl % C;
-		const float a = scale[c] / sqrtf(var[c] + eps);
-		const float b = bias[c] - mean[c] * a;
-		const T* plane = x + pl * S;
-		T* out = y + pl * S;
-		plane_visit<T>(plane, S, threadIdx.x, 256, vec_ok,
-			[&](int64_t i) {
-				Pack<T> p = *reinterpret_cast<const Pack<T>*>(plane + i);
-				#pragma unroll
-				for (int e = 0; e < VecOf<T>::N; e++) p.v[e] = from_f<T>(fmaf(to_f<T>(p.v[e]), a, b));
-				*reinterpret_cast<Pack<T>*>(out + i) = p;
-			},
-			[&](int64_t i) { out[i] = from_f<T>(fmaf(to_f<T>(plane[i]), a, b)); });
-	}
-}
-
-// ------------------------------------------------------------------------------------------ backward
-template <typename T>
-__global__ void __launch_bounds__(kThreads) bn_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx,
-														  int64_t N, int64_t C, int64_t S, const float* __restrict__ scale,
-														  const float* __restrict__ save_mean,
-														  const float* __restrict__ save_invvar, float* dscale, float* dbias,
-														  int vec_ok, int warp_planes)
-{
-	cg::cluster_group cluster = cg::this_cluster();
-	const unsigned rank = cluster.block_rank(), csize = cluster.num_blocks();
-	const int64_t c = blockIdx.y;
-	const PlaneSplit ps = split_planes(N, rank, csize);
-
-	const int gsize = warp_planes ? 32 : kThreads;
-	const int gi = warp_planes ? (threadIdx.x & 31) : threadIdx.x;
-	const int group = warp_planes ? (threadIdx.x >> 5) : 0;
-	const int ngroups = warp_planes ? kThreads / 32 : 1;
-
-	__shared__ float warp_part[2][kThreads / 32];
-	__shared__ float cta_part[2];
-	__shared__ float coef[3];
-
-	const float mean = save_mean[c], invstd = save_invvar[c];
-
-	// pass 1: sum(dy) and sum(dy * xhat)
-	float sdy = 0.0f, sdyx = 0.0f;
-	for (int64_t pl = group; pl < ps.count; pl += ngroups) {
-		const int64_t off = ((ps.first + pl) * C + c) * S;
-		const T* px = x + off;
-		const T* pg = dy + off;
-		plane_visit<T>(px, S, gi, gsize, vec_ok,
-			[&](int64_t i) {
-				Pack<T> a = *reinterpret_cast<const Pack<T>*>(px + i);
-				Pack<T> g = *reinterpret_cast<const Pack<T>*>(pg + i);
-				#pragma unroll
-				for (int e = 0; e < VecOf<T>::N; e++) {
-					float gv = to_f<T>(g.v[e]);
-					sdy += gv;
-					sdyx += gv * (to_f<T>(a.v[e]) - mean);
-				}
-			},
-			[&](int64_t i) { float gv = to_f<T>(pg[i]); sdy += gv; sdyx += gv * (to_f<T>(px[i]) - mean); });
-	}
-	sdy = warp_sum(sdy);
-	sdyx = warp_sum(sdyx);
-	if ((threadIdx.x & 31) == 0) { warp_part[0][threadIdx.x >> 5] = sdy; warp_part[1][threadIdx.x >> 5] = sdyx; }
-	__syncthreads();
-	if (threadIdx.x == 0) {
-		float a = 0.0f, b = 0.0f;
-		for (int w = 0; w < kThreads / 32; w++) { a += warp_part[0][w]; b += warp_part[1][w]; }
-		cta_part[0] = a;
-		cta_part[1] = b;
-	}
-	cluster.sync();
-	if (threadIdx.x == 0) {
-		float tdy = 0.0f, tdyx = 0.0f;
-		for (unsigned r = 0; r < csize; r++) {
-			const float* remote = cluster.map_shared_rank(&cta_part[0], r);
-			tdy += remote[0];
-			tdyx += remote[1];
-		}
-		const float dsc = tdyx * invstd;        // sum(dy * xhat)
-		const float m = (float)(N * S);
-		const float c1 = scale[c] * invstd;
-		coef[0] = c1;
-		coef[1] = c1 * tdy / m;
-		coef[2] = c1 * dsc / m * invstd;        // multiplies (x - mean)
-		if (rank == 0) { dscale[c] = dsc; dbias[c] = tdy; }
-	}
-	cluster.sync();
-	const float c1 = coef[0], c2 = coef[1], c3 = coef[2];
-
-	// pass 2: dx = c1*dy - c2 - (x - mean)*c3
-	for (int64_t pl = group; pl < ps.count; pl += ngroups) {
-		const int64_t off = ((ps.first + pl) * C + c) * S;
-		const T* px = x + off;
-		const T* pg = dy + off;
-		T* pd = dx + off;
-		plane_visit<T>(px, S, gi, gsize, vec_ok,
-			[&](int64_t i) {
-				Pack<T> a = *reinterpret_cast<const Pack<T>*>(px + i);
-				Pack<T> g = *reinterpret_cast<const Pack<T>*>(pg + i);
-				#pragma unroll
-				for (int e = 0; e < VecOf<T>::N; e++)
-					g.v[e] = from_f<T>(c1 * to_f<T>(g.v[e]) - c2 - (to_f<T>(a.v[e]) - mean) * c3);
-				*reinterpret_cast<Pack<T>*>(pd + i) = g;
-			},
-			[&](int64_t i) { pd[i] = from_f<T>(c1 * to_f<T>(pg[i]) - c2 - (to_f<T>(px[i]) - mean) * c3); });
-	}
-}
-
-int pick_cluster(int64_t N, int64_t C)
-{
-	int cs = 1;
-	while (cs < kMaxCluster && C * cs < 2ll * pz_num_sms() && cs * 2 <= N) cs *= 2;
-	return cs;
-}
-
-template <typename K, typename... Args>
-int launch_cluster(K kern, dim3 grid, int threads, int cs, cudaStream_t stream, Args... args)
-{
-	cudaLaunchConfig_t cfg{};
-	cfg.gridDim = grid;
-	cfg.blockDim = dim3((unsigned)threads);
-	cfg.dynamicSmemBytes = 0;
-	cfg.stream = stream;
-	cudaLaunchAttribute attr[1];
-	attr[0].id = cudaLaunchAttributeClusterDimension;
-	attr[0].val.clusterDim.x = (unsigned)cs;
-	attr[0].val.clusterDim.y = 1;
-	attr[0].val.clusterDim.z = 1;
-	cfg.attrs = attr;
-	cfg.numAttrs = 1;
-	PZ_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, args...));
-	pz_count_launch(1);
-	return PZ_OK;
-}
-
-bool same_misalignment(std::initializer_list<const void*> ptrs)
-{
-	uintptr_t m = (uintptr_t)(*ptrs.begin()) % 16;
-	for (const void* p : ptrs)
-		if ((uintptr_t)p % 16 != m) return false;
-	return true;
-}
+#define PZ_BN_LAUNCH(VECV, KERNEL, SMEM, ...)                                                                   \
+	do {                                                                                                        \
+		const dim3 grid((unsigned)pz_cdiv(g.items, g.items_per_cta));                                           \
+		KERNEL<<<grid, kThreads, SMEM, s>>>(__VA_ARGS__);                                                       \
+		pz_count_launch(1);                                                                                     \
+	} while (0)
 
 template <typename T>
 int fwd_train(const void* x, void* y, int64_t N, int64_t C, int64_t S, const float* scale, const float* bias, float* rm,
 			  float* rv, float* sm, float* siv, double eps, double factor, void* stream)
 {
-	const int cs = pick_cluster(N, C);
-	const int vec_ok = same_misalignment({x, y}) && ((uintptr_t)x % sizeof(T) == 0);
-	const int warp_planes = S < 2048;
-	PzProfScope prof(PZ_PROF_BN_FWD, pz_stream(stream), 0.0, 2.0 * (double)N * C * S * sizeof(T));
-	return launch_cluster(bn_fwd_train_kernel<T>, dim3((unsigned)cs, (unsigned)C), kThreads, cs, pz_stream(stream), (const T*)x,
-						  (T*)y, N, C, S, scale, bias, rm, rv, sm, siv, (float)eps, (float)factor, vec_ok, warp_planes);
+	constexpr int V = 16 / sizeof(T);
+	cudaStream_t s = pz_stream(stream);
+	float* sums = sums_buffer(C);
+	if (!sums) { pz_set_error(PZ_ERR_MEMORY, "batchnorm: cannot allocate the statistics buffer"); return PZ_ERR_MEMORY; }
+	const Plan plan = make_plan<T>({x, y}, N, C, S, 1);
+	const float count = (float)(N * S);
+	PzProfScope prof(PZ_PROF_BN_FWD, s, 0.0, 2.0 * (double)N * C * S * sizeof(T));
+	PZ_CHECK_CUDA(cudaMemsetAsync(sums, 0, (size_t)C * 2 * sizeof(float), s));
+	for (int64_t c0 = 0; c0 < C; c0 += plan.slab_channels) {
+		const int64_t c1 = c0 + plan.slab_channels < C ? c0 + plan.slab_channels : C;
+		const Slab g = make_slab(plan, N, C, S, c0, c1);
+		if (plan.vec == V) {
+			PZ_BN_LAUNCH(V, (bn_stats_kernel<T, V>), bins_per_block(V, g.S) * 2 * sizeof(float), (const T*)x, g, sums);
+			PZ_BN_LAUNCH(V, (bn_apply_kernel<T, V, true>), 0, (const T*)x, (T*)y, g, sums, scale, bias, rm, rv, sm, siv, (float)eps,
+						 (float)factor, count);
+		} else {
+			PZ_BN_LAUNCH(1, (bn_stats_kernel<T, 1>), bins_per_block(1, g.S) * 2 * sizeof(float), (const T*)x, g, sums);
+			PZ_BN_LAUNCH(1, (bn_apply_kernel<T, 1, true>), 0, (const T*)x, (T*)y, g, sums, scale, bias, rm, rv, sm, siv, (float)eps,
+						 (float)factor, count);
+		}
+	}
+	PZ_LAUNCH_CHECK();
+	return PZ_OK;
 }
 
 template <typename T>
 int fwd_infer(const void* x, void* y, int64_t N, int64_t C, int64_t S, const float* scale, const float* bias, const float* mean,
 			  const float* var, double eps, void* stream)
 {
-	const int64_t planes = N * C;
-	const int vec_ok = same_misalignment({x, y}) && ((uintptr_t)x % sizeof(T) == 0);
-	int64_t blocks = planes < (int64_t)pz_num_sms() * 8 ? planes : (int64_t)pz_num_sms() * 8;
-	bn_fwd_infer_kernel<T><<<(unsigned)blocks, 256, 0, pz_stream(stream)>>>((const T*)x, (T*)y, planes, C, S, scale, bias, mean, var,
-																			(float)eps, vec_ok);
-	pz_count_launch(1);
+	constexpr int V = 16 / sizeof(T);
+	cudaStream_t s = pz_stream(stream);
+	Plan plan = make_plan<T>({x, y}, N, C, S, 1);
+	plan.slab_channels = C;                       // nothing is re-read: one launch over the whole tensor
+	const Slab g = make_slab(plan, N, C, S, 0, C);
+	PzProfScope prof(PZ_PROF_BN_FWD, s, 0.0, 2.0 * (double)N * C * S * sizeof(T));
+	if (plan.vec == V)
+		PZ_BN_LAUNCH(V, (bn_apply_kernel<T, V, false>), 0, (const T*)x, (T*)y, g, nullptr, scale, bias, (float*)mean, (float*)var, nullptr,
+					 nullptr, (float)eps, 0.0f, 1.0f);
+	else
+		PZ_BN_LAUNCH(1, (bn_apply_kernel<T, 1, false>), 0, (const T*)x, (T*)y, g, nullptr, scale, bias, (float*)mean, (float*)var, nullptr,
+					 nullptr, (float)eps, 0.0f, 1.0f);
 	PZ_LAUNCH_CHECK();
 	return PZ_OK;
 }
@@ -377,12 +533,27 @@ template <typename T>
 int bwd(const void* x, const void* dy, void* dx, int64_t N, int64_t C, int64_t S, const float* scale, const float* sm,
 		const float* siv, float* dscale, float* dbias, void* stream)
 {
-	const int cs = pick_cluster(N, C);
-	const int vec_ok = same_misalignment({x, dy, dx}) && ((uintptr_t)x % sizeof(T) == 0);
-	const int warp_planes = S < 2048;
-	PzProfScope prof(PZ_PROF_BN_BWD, pz_stream(stream), 0.0, 3.0 * (double)N * C * S * sizeof(T));
-	return launch_cluster(bn_bwd_kernel<T>, dim3((unsigned)cs, (unsigned)C), kThreads, cs, pz_stream(stream), (const T*)x,
-						  (const T*)dy, (T*)dx, N, C, S, scale, sm, siv, dscale, dbias, vec_ok, warp_planes);
+	constexpr int V = 16 / sizeof(T);
+	cudaStream_t s = pz_stream(stream);
+	float* sums = sums_buffer(C);
+	if (!sums) { pz_set_error(PZ_ERR_MEMORY, "batchnorm: cannot allocate the statistics buffer"); return PZ_ERR_MEMORY; }
+	const Plan plan = make_plan<T>({x, dy, dx}, N, C, S, 2);
+	const float count = (float)(N * S);
+	PzProfScope prof(PZ_PROF_BN_BWD, s, 0.0, 3.0 * (double)N * C * S * sizeof(T));
+	PZ_CHECK_CUDA(cudaMemsetAsync(sums, 0, (size_t)C * 2 * sizeof(float), s));
+	for (int64_t c0 = 0; c0 < C; c0 += plan.slab_channels) {
+		const int64_t c1 = c0 + plan.slab_channels < C ? c0 + plan.slab_channels : C;
+		const Slab g = make_slab(plan, N, C, S, c0, c1);
+		if (plan.vec == V) {
+			PZ_BN_LAUNCH(V, (bn_bwd_stats_kernel<T, V>), bins_per_block(V, g.S) * 2 * sizeof(float), (const T*)x, (const T*)dy, g, sm, sums);
+			PZ_BN_LAUNCH(V, (bn_bwd_apply_kernel<T, V>), 0, (const T*)x, (const T*)dy, (T*)dx, g, sums, scale, sm, siv, dscale, dbias, count);
+		} else {
+			PZ_BN_LAUNCH(1, (bn_bwd_stats_kernel<T, 1>), bins_per_block(1, g.S) * 2 * sizeof(float), (const T*)x, (const T*)dy, g, sm, sums);
+			PZ_BN_LAUNCH(1, (bn_bwd_apply_kernel<T, 1>), 0, (const T*)x, (const T*)dy, (T*)dx, g, sums, scale, sm, siv, dscale, dbias, count);
+		}
+	}
+	PZ_LAUNCH_CHECK();
+	return PZ_OK;
 }
 
 #define PZ_DISPATCH_FLOAT(dtype, ...)                                                    \
@@ -394,6 +565,14 @@ int bwd(const void* x, const void* dy, void* dx, int64_t N, int64_t C, int64_t S
 				 return PZ_ERR_UNSUPPORTED;                                              \
 	}
 
+int check_dims(int64_t N, int64_t C, int64_t S)
+{
+	PZ_REQUIRE(N > 0 && C > 0 && S > 0, "batchnorm: empty tensor");
+	PZ_REQUIRE(N < (1ll << 31) && S < (1ll << 31) && C * S < (1ll << 31) - 4096 && pz_cdiv(C * S, kThreads) * pz_cdiv(N, kRowUnroll) < (1ll << 31),
+			   "batchnorm: tensor too large (N=%lld C=%lld S=%lld)", (long long)N, (long long)C, (long long)S);
+	return PZ_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -402,23 +581,24 @@ int pz_bn_fwd_train(int dtype, const void* x, void* y, int64_t N, int64_t C, int
 					float* running_mean, float* running_var, float* save_mean, float* save_invvar, double eps, double factor,
 					void* stream)
 {
-	PZ_REQUIRE(N > 0 && C > 0 && S > 0, "batchnorm: empty tensor");
-	PZ_REQUIRE(C <= 65535, "batchnorm: too many channels for one launch (%lld)", (long long)C);
+	int st = check_dims(N, C, S);
+	if (st != PZ_OK) return st;
 	PZ_DISPATCH_FLOAT(dtype, fwd_train<T>(x, y, N, C, S, scale, bias, running_mean, running_var, save_mean, save_invvar, eps, factor, stream));
 }
 
 int pz_bn_fwd_infer(int dtype, const void* x, void* y, int64_t N, int64_t C, int64_t S, const float* scale, const float* bias,
 					const float* mean, const float* var, double eps, void* stream)
 {
-	PZ_REQUIRE(N > 0 && C > 0 && S > 0, "batchnorm: empty tensor");
+	int st = check_dims(N, C, S);
+	if (st != PZ_OK) return st;
 	PZ_DISPATCH_FLOAT(dtype, fwd_infer<T>(x, y, N, C, S, scale, bias, mean, var, eps, stream));
 }
 
 int pz_bn_bwd(int dtype, const void* x, const void* dy, void* dx, int64_t N, int64_t C, int64_t S, const float* scale,
 			  const float* save_mean, const float* save_invvar, float* dscale, float* dbias, void* stream)
 {
-	PZ_REQUIRE(N > 0 && C > 0 && S > 0, "batchnorm: empty tensor");
-	PZ_REQUIRE(C <= 65535, "batchnorm: too many channels for one launch (%lld)", (long long)C);
+	int st = check_dims(N, C, S);
+	if (st != PZ_OK) return st;
 	PZ_DISPATCH_FLOAT(dtype, bwd<T>(x, dy, dx, N, C, S, scale, save_mean, save_invvar, dscale, dbias, stream));
 }
 

@@ -9,10 +9,13 @@
 //     row-major window scan starting from -FLT_MAX, -1 for an empty window; backward adds the candidate
 //     windows in (ph, pw) order.
 //
-// B200 design: one thread per output element with threadIdx.x running along the contiguous W axis, so each
+// B200 design: one thread per in-plane output position with threadIdx.x running along the contiguous W axis, so each
 // warp writes full 128-byte lines and its overlapping window reads are served from L1 (every input line is
-// fetched from HBM once).  The backward kernels are GATHERS (one thread per dx element) -- no atomics, so
-// results are deterministic run to run, which the reference's scatter-free mask kernel also guarantees.
+// fetched from HBM once).  A thread decodes its (h, w) and window bounds ONCE and then walks over planes
+// (blockIdx.y-strided), so the per-element work is loads + compares only -- no integer division in the loop.
+// Tiny planes (global average pooling) use flat-indexed variants instead.  The backward kernels are GATHERS (one
+// thread per dx element) -- no atomics, so results are deterministic run to run, which the reference's
+// scatter-free mask kernel also guarantees.
 #include "pz_common.h"
 
 #include <cfloat>
@@ -194,6 +197,201 @@ __global__ void __launch_bounds__(kThreads) maxunpool_bwd_kernel(const float* __
 	}
 }
 
+// ------------------------------------------------------------------------------------------ plane-walking variants
+// grid.x * blockDim.x covers the positions of one plane, grid.y strides over planes.
+template <typename T, int MODE>
+__global__ void __launch_bounds__(kThreads) pool_fwd_plane_kernel(const T* __restrict__ x, T* __restrict__ y, int planes, PoolGeo g)
+{
+	const int o = blockIdx.x * blockDim.x + threadIdx.x;
+	const int OHW = g.OH * g.OW, HW = g.H * g.W;
+	if (o >= OHW) return;
+	const int oh = o / g.OW, ow = o - oh * g.OW;
+	int h0 = oh * g.sh - g.ph, w0 = ow * g.sw - g.pw;
+	const int h1 = min(h0 + g.fh, g.H), w1 = min(w0 + g.fw, g.W);
+	h0 = max(h0, 0);
+	w0 = max(w0, 0);
+	for (int pl = blockIdx.y; pl < planes; pl += gridDim.y) {
+		const T* slice = x + (int64_t)pl * HW;
+		float r;
+		if (MODE == PZ_POOL_MAX || MODE == PZ_POOL_MAX_DETERMINISM) {
+			r = -FLT_MAX;
+			for (int h = h0; h < h1; h++)
+				for (int w = w0; w < w1; w++) r = fmaxf(r, to_f<T>(slice[h * g.W + w]));
+		} else {
+			float acc = 0.0f;
+			for (int h = h0; h < h1; h++)
+				for (int w = w0; w < w1; w++) acc += to_f<T>(slice[h * g.W + w]);
+			r = MODE == PZ_POOL_AVG_WITH_PAD ? acc / (float)(g.fh * g.fw) : acc / (float)((h1 - h0) * (w1 - w0));
+		}
+		y[(int64_t)pl * OHW + o] = from_f<T>(r);
+	}
+}
+
+template <typename T, int MODE>
+__global__ void __launch_bounds__(kThreads) pool_bwd_plane_kernel(const T* __restrict__ x, const T* __restrict__ y,
+																  const T* __restrict__ dy, T* __restrict__ dx, int planes, PoolGeo g)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	const int OHW = g.OH * g.OW, HW = g.H * g.W;
+	if (i >= HW) return;
+	const int h = i / g.W, w = i - h * g.W;
+	const int oh0 = (h + g.ph < g.fh) ? 0 : (h + g.ph - g.fh) / g.sh + 1;
+	const int oh1 = min((h + g.ph) / g.sh + 1, g.OH);
+	const int ow0 = (w + g.pw < g.fw) ? 0 : (w + g.pw - g.fw) / g.sw + 1;
+	const int ow1 = min((w + g.pw) / g.sw + 1, g.OW);
+
+	for (int pl = blockIdx.y; pl < planes; pl += gridDim.y) {
+		const T* xs = x + (int64_t)pl * HW;
+		const T* ys = y + (int64_t)pl * OHW;
+		const T* gs = dy + (int64_t)pl * OHW;
+		float grad = 0.0f;
+		if (MODE == PZ_POOL_MAX || MODE == PZ_POOL_MAX_DETERMINISM) {
+			const float xv = to_f<T>(xs[i]);
+			for (int oh = oh0; oh < oh1; oh++)
+				for (int ow = ow0; ow < ow1; ow++) {
+					const float yv = to_f<T>(ys[oh * g.OW + ow]);
+					if (xv != yv) continue;
+					// is (h, w) the first element of this window that equals the maximum?
+					const int hs = max(oh * g.sh - g.ph, 0), ws = max(ow * g.sw - g.pw, 0);
+					const int we = min(ow * g.sw - g.pw + g.fw, g.W);
+					bool first = true;
+					for (int hh = hs; hh <= h && first; hh++) {
+						const int wend = hh == h ? w : we;
+						for (int ww = ws; ww < wend; ww++)
+							if (to_f<T>(xs[hh * g.W + ww]) == yv) { first = false; break; }
+					}
+					if (first) grad += to_f<T>(gs[oh * g.OW + ow]);
+				}
+		} else {
+			for (int oh = oh0; oh < oh1; oh++)
+				for (int ow = ow0; ow < ow1; ow++) {
+					int cnt = g.fh * g.fw;
+					if (MODE == PZ_POOL_AVG_NO_PAD) {
+						const int hs = max(oh * g.sh - g.ph, 0), he = min(oh * g.sh - g.ph + g.fh, g.H);
+						const int ws = max(ow * g.sw - g.pw, 0), we = min(ow * g.sw - g.pw + g.fw, g.W);
+						cnt = (he - hs) * (we - ws);
+					}
+					grad += to_f<T>(gs[oh * g.OW + ow]) / (float)cnt;
+				}
+		}
+		dx[(int64_t)pl * HW + i] = from_f<T>(grad);
+	}
+}
+
+__global__ void __launch_bounds__(kThreads) maxpool_mask_fwd_plane_kernel(const float* __restrict__ x, float* __restrict__ y,
+																			   int32_t* __restrict__ mask, int planes, PoolGeo g)
+{
+	const int o = blockIdx.x * blockDim.x + threadIdx.x;
+	const int OHW = g.OH * g.OW, HW = g.H * g.W;
+	if (o >= OHW) return;
+	const int oh = o / g.OW, ow = o - oh * g.OW;
+	int h0 = oh * g.sh - g.ph, w0 = ow * g.sw - g.pw;
+	const int h1 = min(h0 + g.fh, g.H), w1 = min(w0 + g.fw, g.W);
+	h0 = max(h0, 0);
+	w0 = max(w0, 0);
+	for (int pl = blockIdx.y; pl < planes; pl += gridDim.y) {
+		const float* slice = x + (int64_t)pl * HW;
+		float maxval = -FLT_MAX;
+		int maxidx = -1;
+		for (int h = h0; h < h1; h++)
+			for (int w = w0; w < w1; w++) {
+				const float v = slice[h * g.W + w];
+				if (v > maxval) { maxidx = h * g.W + w; maxval = v; }
+			}
+		y[(int64_t)pl * OHW + o] = maxval;
+		mask[(int64_t)pl * OHW + o] = maxidx;
+	}
+}
+
+__global__ void __launch_bounds__(kThreads) maxpool_mask_bwd_plane_kernel(const float* __restrict__ dy, const int32_t* __restrict__ mask,
+																			   float* __restrict__ dx, int planes, PoolGeo g)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	const int OHW = g.OH * g.OW, HW = g.H * g.W;
+	if (i >= HW) return;
+	const int h = i / g.W, w = i - h * g.W;
+	const int oh0 = (h + g.ph < g.fh) ? 0 : (h + g.ph - g.fh) / g.sh + 1;
+	const int oh1 = min((h + g.ph) / g.sh + 1, g.OH);
+	const int ow0 = (w + g.pw < g.fw) ? 0 : (w + g.pw - g.fw) / g.sw + 1;
+	const int ow1 = min((w + g.pw) / g.sw + 1, g.OW);
+	for (int pl = blockIdx.y; pl < planes; pl += gridDim.y) {
+		const int32_t* ms = mask + (int64_t)pl * OHW;
+		const float* gs = dy + (int64_t)pl * OHW;
+		float grad = 0.0f;
+		for (int oh = oh0; oh < oh1; oh++)
+			for (int ow = ow0; ow < ow1; ow++)
+				if (ms[oh * g.OW + ow] == i) grad += gs[oh * g.OW + ow];
+		dx[(int64_t)pl * HW + i] = grad;
+	}
+}
+
+// cuDNN-style max backward (x, dy -> dx) in two passes through a library-owned int32 winner map: pass 1 finds the first
+// maximum of every window (exactly the forward scan), pass 2 gathers dy from the windows whose winner is this element.
+// Uniform work per thread -- the direct "am I the first maximum of this window?" test re-scans the window divergently.
+template <typename T>
+__global__ void __launch_bounds__(kThreads) pool_argmax_plane_kernel(const T* __restrict__ x, int32_t* __restrict__ winner, int planes,
+																		  PoolGeo g)
+{
+	const int o = blockIdx.x * blockDim.x + threadIdx.x;
+	const int OHW = g.OH * g.OW, HW = g.H * g.W;
+	if (o >= OHW) return;
+	const int oh = o / g.OW, ow = o - oh * g.OW;
+	int h0 = oh * g.sh - g.ph, w0 = ow * g.sw - g.pw;
+	const int h1 = min(h0 + g.fh, g.H), w1 = min(w0 + g.fw, g.W);
+	h0 = max(h0, 0);
+	w0 = max(w0, 0);
+	for (int pl = blockIdx.y; pl < planes; pl += gridDim.y) {
+		const T* slice = x + (int64_t)pl * HW;
+		float maxval = -FLT_MAX;
+		int maxidx = h0 * g.W + w0;          // a window of -FLT_MAX / NaN still routes its gradient somewhere (cuDNN does)
+		for (int h = h0; h < h1; h++)
+			for (int w = w0; w < w1; w++) {
+				const float v = to_f<T>(slice[h * g.W + w]);
+				if (v > maxval) { maxidx = h * g.W + w; maxval = v; }
+			}
+		winner[(int64_t)pl * OHW + o] = maxidx;
+	}
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) pool_gather_plane_kernel(const T* __restrict__ dy, const int32_t* __restrict__ winner,
+																		  T* __restrict__ dx, int planes, PoolGeo g)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	const int OHW = g.OH * g.OW, HW = g.H * g.W;
+	if (i >= HW) return;
+	const int h = i / g.W, w = i - h * g.W;
+	const int oh0 = (h + g.ph < g.fh) ? 0 : (h + g.ph - g.fh) / g.sh + 1;
+	const int oh1 = min((h + g.ph) / g.sh + 1, g.OH);
+	const int ow0 = (w + g.pw < g.fw) ? 0 : (w + g.pw - g.fw) / g.sw + 1;
+	const int ow1 = min((w + g.pw) / g.sw + 1, g.OW);
+	for (int pl = blockIdx.y; pl < planes; pl += gridDim.y) {
+		const int32_t* ms = winner + (int64_t)pl * OHW;
+		const T* gs = dy + (int64_t)pl * OHW;
+		float grad = 0.0f;
+		for (int oh = oh0; oh < oh1; oh++)
+			for (int ow = ow0; ow < ow1; ow++)
+				if (ms[oh * g.OW + ow] == i) grad += to_f<T>(gs[oh * g.OW + ow]);
+		dx[(int64_t)pl * HW + i] = from_f<T>(grad);
+	}
+}
+
+// launch geometry of the plane-walking kernels: `elems` positions per plane
+struct PlaneGrid { dim3 grid; unsigned threads; };
+PlaneGrid plane_grid(int elems, int64_t planes)
+{
+	PlaneGrid pg;
+	pg.threads = elems >= kThreads ? kThreads : (unsigned)((elems + 31) & ~31);
+	const unsigned gx = (unsigned)pz_cdiv(elems, pg.threads);
+	int64_t gy = pz_cdiv((int64_t)pz_num_sms() * 16, gx);
+	if (gy > planes) gy = planes;
+	if (gy > 65535) gy = 65535;
+	if (gy < 1) gy = 1;
+	pg.grid = dim3(gx, (unsigned)gy);
+	return pg;
+}
+constexpr int kMinPlaneElems = 64;     // smaller planes: flat-indexed kernels (e.g. global average pooling)
+
 unsigned grid_for(int64_t total)
 {
 	int64_t blocks = pz_cdiv(total, kThreads);
@@ -220,6 +418,24 @@ int fwd_dispatch(int mode, const void* x, void* y, int64_t planes, const PoolGeo
 	const unsigned grid = grid_for(total);
 	cudaStream_t s = pz_stream(stream);
 	PzProfScope prof(PZ_PROF_POOL, s, 0.0, (double)sizeof(T) * planes * ((double)g.H * g.W + (double)g.OH * g.OW));
+	if (g.OH * g.OW >= kMinPlaneElems && planes < (1ll << 31)) {
+		const PlaneGrid pg = plane_grid(g.OH * g.OW, planes);
+		switch (mode) {
+			case PZ_POOL_MAX:
+			case PZ_POOL_MAX_DETERMINISM:
+				pool_fwd_plane_kernel<T, PZ_POOL_MAX><<<pg.grid, pg.threads, 0, s>>>((const T*)x, (T*)y, (int)planes, g); break;
+			case PZ_POOL_AVG_WITH_PAD:
+				pool_fwd_plane_kernel<T, PZ_POOL_AVG_WITH_PAD><<<pg.grid, pg.threads, 0, s>>>((const T*)x, (T*)y, (int)planes, g); break;
+			case PZ_POOL_AVG_NO_PAD:
+				pool_fwd_plane_kernel<T, PZ_POOL_AVG_NO_PAD><<<pg.grid, pg.threads, 0, s>>>((const T*)x, (T*)y, (int)planes, g); break;
+			default:
+				pz_set_error(PZ_ERR_VALUE, "pool2d: unknown mode %d", mode);
+				return PZ_ERR_VALUE;
+		}
+		pz_count_launch(1);
+		PZ_LAUNCH_CHECK();
+		return PZ_OK;
+	}
 	switch (mode) {
 		case PZ_POOL_MAX:
 		case PZ_POOL_MAX_DETERMINISM:
@@ -244,6 +460,33 @@ int bwd_dispatch(int mode, const void* x, const void* y, const void* dy, void* d
 	const unsigned grid = grid_for(total);
 	cudaStream_t s = pz_stream(stream);
 	PzProfScope prof(PZ_PROF_POOL, s, 0.0, (double)sizeof(T) * planes * (2.0 * g.H * g.W + 2.0 * g.OH * g.OW));
+	if (g.H * g.W >= kMinPlaneElems && planes < (1ll << 31)) {
+		const PlaneGrid pg = plane_grid(g.H * g.W, planes);
+		switch (mode) {
+			case PZ_POOL_MAX:
+			case PZ_POOL_MAX_DETERMINISM: {
+				int32_t* winner = g.OH * g.OW >= 32 ? (int32_t*)pz_scratch((size_t)planes * g.OH * g.OW * sizeof(int32_t)) : nullptr;
+				if (winner) {
+					const PlaneGrid po = plane_grid(g.OH * g.OW, planes);
+					pool_argmax_plane_kernel<T><<<po.grid, po.threads, 0, s>>>((const T*)x, winner, (int)planes, g);
+					pool_gather_plane_kernel<T><<<pg.grid, pg.threads, 0, s>>>((const T*)dy, winner, (T*)dx, (int)planes, g);
+					pz_count_launch(1);
+				} else
+					pool_bwd_plane_kernel<T, PZ_POOL_MAX><<<pg.grid, pg.threads, 0, s>>>((const T*)x, (const T*)y, (const T*)dy, (T*)dx, (int)planes, g);
+				break;
+			}
+			case PZ_POOL_AVG_WITH_PAD:
+				pool_bwd_plane_kernel<T, PZ_POOL_AVG_WITH_PAD><<<pg.grid, pg.threads, 0, s>>>((const T*)x, (const T*)y, (const T*)dy, (T*)dx, (int)planes, g); break;
+			case PZ_POOL_AVG_NO_PAD:
+				pool_bwd_plane_kernel<T, PZ_POOL_AVG_NO_PAD><<<pg.grid, pg.threads, 0, s>>>((const T*)x, (const T*)y, (const T*)dy, (T*)dx, (int)planes, g); break;
+			default:
+				pz_set_error(PZ_ERR_VALUE, "pool2d: unknown mode %d", mode);
+				return PZ_ERR_VALUE;
+		}
+		pz_count_launch(1);
+		PZ_LAUNCH_CHECK();
+		return PZ_OK;
+	}
 	switch (mode) {
 		case PZ_POOL_MAX:
 		case PZ_POOL_MAX_DETERMINISM:
@@ -299,7 +542,12 @@ int pz_maxpool2d_mask_fwd(const float* x, float* y, int32_t* mask, int64_t plane
 	int st = check_geo(planes, g);
 	if (st != PZ_OK) return st;
 	const int64_t total = planes * OH * OW;
-	maxpool_mask_fwd_kernel<<<grid_for(total), kThreads, 0, pz_stream(stream)>>>(x, y, mask, total, g);
+	PzProfScope prof(PZ_PROF_POOL, pz_stream(stream), 0.0, 4.0 * planes * ((double)H * W + 2.0 * OH * OW));
+	if (OH * OW >= kMinPlaneElems && planes < (1ll << 31)) {
+		const PlaneGrid pg = plane_grid(OH * OW, planes);
+		maxpool_mask_fwd_plane_kernel<<<pg.grid, pg.threads, 0, pz_stream(stream)>>>(x, y, mask, (int)planes, g);
+	} else
+		maxpool_mask_fwd_kernel<<<grid_for(total), kThreads, 0, pz_stream(stream)>>>(x, y, mask, total, g);
 	pz_count_launch(1);
 	PZ_LAUNCH_CHECK();
 	return PZ_OK;
@@ -312,7 +560,12 @@ int pz_maxpool2d_mask_bwd(const float* dy, const int32_t* mask, float* dx, int64
 	int st = check_geo(planes, g);
 	if (st != PZ_OK) return st;
 	const int64_t total = planes * H * W;
-	maxpool_mask_bwd_kernel<<<grid_for(total), kThreads, 0, pz_stream(stream)>>>(dy, mask, dx, total, g);
+	PzProfScope prof(PZ_PROF_POOL, pz_stream(stream), 0.0, 4.0 * planes * ((double)H * W + 2.0 * OH * OW));
+	if (H * W >= kMinPlaneElems && planes < (1ll << 31)) {
+		const PlaneGrid pg = plane_grid(H * W, planes);
+		maxpool_mask_bwd_plane_kernel<<<pg.grid, pg.threads, 0, pz_stream(stream)>>>(dy, mask, dx, (int)planes, g);
+	} else
+		maxpool_mask_bwd_kernel<<<grid_for(total), kThreads, 0, pz_stream(stream)>>>(dy, mask, dx, total, g);
 	pz_count_launch(1);
 	PZ_LAUNCH_CHECK();
 	return PZ_OK;

@@ -34,6 +34,24 @@ int pz_num_sms()
 	return sms;
 }
 
+// Library-owned scratch.  Use is stream-ordered: the kernel that writes it and the kernel that reads it are enqueued back to
+// back on the caller's stream (the reference runs everything on the legacy default stream), and the next user overwrites it
+// only after both have run.
+void* pz_scratch(size_t bytes)
+{
+	static void* buf = nullptr;
+	static size_t cap = 0;
+	static std::mutex mu;
+	std::lock_guard<std::mutex> lock(mu);
+	if (bytes > cap) {
+		if (buf) { cudaDeviceSynchronize(); cudaFree(buf); buf = nullptr; cap = 0; }
+		size_t want = bytes < ((size_t)64 << 20) ? ((size_t)64 << 20) : bytes + (bytes >> 2);
+		if (cudaMalloc(&buf, want) != cudaSuccess) { buf = nullptr; cudaGetLastError(); return nullptr; }
+		cap = want;
+	}
+	return buf;
+}
+
 // ---------------------------------------------------------------------------------------- launch profiling
 namespace {
 struct ProfRecord { cudaEvent_t start, stop; int family; double flops, bytes; };

@@ -110,6 +110,11 @@ struct Epilogue {
 	int atomic;                  // 1: out += alpha*acc with red.global.add (split-K)
 	long long group_stride;
 	int bias_group_stride;
+	// col2im epilogue (dgrad of a filter with very few input channels, see pz_conv.cu): row m = (image, p, q) of dy, column
+	// n = (c, r, s); the product is scattered with red.add to dx[image][c][p*sh - ph + r*dh][q*sw - pw + s*dw]
+	int c2i;
+	int c2i_sh, c2i_sw, c2i_ph, c2i_pw, c2i_dh, c2i_dw, c2i_H, c2i_W;
+	FastDiv c2i_rs, c2i_s;
 };
 
 struct GemmParams {
@@ -814,9 +819,27 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, int 
 // alpha*acc + bias[n], 3 = red.add alpha*acc, 0 = generic (beta, bias with split-K, ...).  Lanes are the contiguous output
 // dimension, so every store instruction of a warp writes 128 consecutive bytes.
 __device__ __forceinline__ void epilogue_chunk(const Epilogue& E, const uint32_t (&v)[EPI_COLS], float* outp, const float* biasp, float bias_m,
-											   bool mvalid, bool addbias, int n0, int fast)
+											   bool mvalid, bool addbias, int n0, int fast, int hb, int wb)
 {
 	if (!mvalid) return;
+	if (fast == 4) {
+		// col2im scatter: the column decode is warp-uniform, the bounds test and the address are per lane
+		const int HW = E.c2i_H * E.c2i_W;
+		#pragma unroll
+		for (int j = 0; j < EPI_COLS; j++) {
+			const int col = n0 + j;
+			if (col < E.N) {
+				const uint32_t c = fdiv((uint32_t)col, E.c2i_rs);
+				const uint32_t t = (uint32_t)col - c * E.c2i_rs.d;
+				const uint32_t r = fdiv(t, E.c2i_s);
+				const uint32_t sx = t - r * E.c2i_s.d;
+				const int h = hb + (int)r * E.c2i_dh, w = wb + (int)sx * E.c2i_dw;
+				if ((unsigned)h < (unsigned)E.c2i_H && (unsigned)w < (unsigned)E.c2i_W)
+					atomicAdd(outp + ((size_t)c * HW + h * E.c2i_W + w), E.alpha * __uint_as_float(v[j]));
+			}
+		}
+		return;
+	}
 	float* dst = outp + (size_t)n0 * (unsigned)E.ncs;
 	const unsigned ncs = (unsigned)E.ncs;
 	const float alpha = E.alpha;
@@ -1019,7 +1042,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) umma_gemm_kernel(const __grid_con
 			const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN) + ((uint32_t)(lg * 32) << 16);
 			const int ncols = min(BN, E.N - w.n_tile * BN);       // valid columns of this tile (> 0)
 			// fast paths (straight-line, 2 - 3 instructions per element): plain store and split-K red.add
-			const int fast = E.atomic ? ((addbias && E.bias_mode) ? 0 : 3) : (E.beta != 0.0f ? 0 : (E.bias_mode == 1 ? 2 : 1));
+			const int fast = E.c2i ? 4 : (E.atomic ? ((addbias && E.bias_mode) ? 0 : 3) : (E.beta != 0.0f ? 0 : (E.bias_mode == 1 ? 2 : 1)));
+			const int hb = m1 * E.c2i_sh - E.c2i_ph, wb = m2 * E.c2i_sw - E.c2i_pw;
 
 			uint32_t v0[EPI_COLS], v1[EPI_COLS];
 			tmem_ld16(tmem_d, v0);
@@ -1027,11 +1051,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) umma_gemm_kernel(const __grid_con
 			for (int c0 = 0; c0 < ncols; c0 += 2 * EPI_COLS) {
 				tmem_wait_ld(v0);
 				if (c0 + EPI_COLS < ncols) tmem_ld16(tmem_d + (uint32_t)(c0 + EPI_COLS), v1);
-				epilogue_chunk(E, v0, outp, biasp, bias_m, mvalid, addbias, w.n_tile * BN + c0, fast);
+				epilogue_chunk(E, v0, outp, biasp, bias_m, mvalid, addbias, w.n_tile * BN + c0, fast, hb, wb);
 				if (c0 + EPI_COLS < ncols) {
 					tmem_wait_ld(v1);
 					if (c0 + 2 * EPI_COLS < ncols) tmem_ld16(tmem_d + (uint32_t)(c0 + 2 * EPI_COLS), v0);
-					epilogue_chunk(E, v1, outp, biasp, bias_m, mvalid, addbias, w.n_tile * BN + c0 + EPI_COLS, fast);
+					epilogue_chunk(E, v1, outp, biasp, bias_m, mvalid, addbias, w.n_tile * BN + c0 + EPI_COLS, fast, hb, wb);
 				}
 			}
 			tc_fence_before();

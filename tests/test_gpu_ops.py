@@ -42,6 +42,12 @@ CONV_CASES = [
 	(1, 130, 5, 5, 200, 3, 3, 1, 1, 1, 1, True),      # ragged: nothing a multiple of the tile sizes
 	(2, 12, 9, 9, 12, 3, 3, 1, 1, 1, 4, False),       # 4 groups
 	(1, 5, 1, 40, 7, 1, 5, 1, (0, 2), 1, 1, True),    # 1-d conv geometry (H = 1)
+	(2, 3, 30, 30, 64, 7, 7, 2, 3, 1, 1, False),      # conv1 with 64 filters: dgrad runs the col2im scatter epilogue
+	(2, 3, 17, 19, 64, 3, 3, 1, 1, 1, 1, False),      # VGG conv1_1 geometry (col2im dgrad, stride 1)
+	(3, 1, 12, 12, 32, 3, 3, 1, 0, 2, 1, False),      # one input channel, dilation (col2im dgrad)
+	(2, 48, 15, 15, 40, 3, 3, 2, 1, 1, 1, True),      # channel counts that are not multiples of 32, strided 3x3
+	(2, 96, 9, 9, 64, 5, 5, 1, 2, 1, 1, False),       # 25 taps, channel-ordered k
+	(2, 64, 10, 10, 96, 3, 3, 1, 1, 1, 2, True),      # groups with channel-ordered k
 ]
 
 
