@@ -179,16 +179,18 @@ def gpuArm(args):
 	grad = M.gpuarray.to_gpu((rng.randn(BATCH, 1000) * 1e-3).astype(np.float32))
 	hostOut = driver.PinnedBuffer((BATCH, 1000), np.float32)
 
-	def step(e2e=False):
-		if e2e:
-			data.set(pinned.array)                                   # H2D from pinned memory
+	def step(e2e=False, asyncCopy=False):
+		if e2e:                                                      # H2D of the batch from pinned host memory
+			driver.check(driver.lib.pz_memcpy_h2d(data.ptr, pinned.ptr, data.nbytes, None, 1 if asyncCopy else 0))
 		optimizer.zeroGradParams()
 		out = net(data)
 		net.backward(grad)
 		optimizer.update()                                           # N > 1: all-reduce(mean) fused with the SGD update
-		if e2e:
-			driver.check(driver.lib.pz_memcpy_d2h(hostOut.ptr, out.ptr, out.nbytes, None, 0))      # D2H of the step's result
+		if e2e:                                                      # D2H of the step's result (the softmax output)
+			driver.check(driver.lib.pz_memcpy_d2h(hostOut.ptr, out.ptr, out.nbytes, None, 1 if asyncCopy else 0))
 		net.reset()                                                  # like Handler.handle: activations go back to the pool
+
+	hostMs = [0.0]
 
 	def timed(nsteps, e2e=False):
 		node.barrier()
@@ -196,8 +198,10 @@ def gpuArm(args):
 		start, end = driver.Event(), driver.Event()
 		launches = driver.launchCount()
 		start.record()
+		t0 = time.perf_counter()
 		for _ in range(nsteps):
 			step(e2e)
+		hostMs[0] = (time.perf_counter() - t0) * 1e3 / nsteps      # host time to ENQUEUE one step (the GPU runs behind)
 		end.record()
 		end.synchronize()
 		driver.Device.synchronize()
@@ -208,16 +212,58 @@ def gpuArm(args):
 			ms = node.rendezvous.maxValue(ms)                        # device time, max over ranks
 		return ms, launches
 
-	for _ in range(max(3, args.warmup)):
+	def timedGraph(graph, nsteps):
+		node.barrier()
+		graph.synchronize()
+		driver.Device.synchronize()
+		start, end = driver.Event(), driver.Event()
+		start.record(graph.stream)
+		for _ in range(nsteps):
+			graph.launch()
+		end.record(graph.stream)
+		end.synchronize()
+		graph.synchronize()
+		ms = start.timeTill(end)
+		node.barrier()
+		if node.gridsize > 1:
+			ms = node.rendezvous.maxValue(ms)
+		return ms
+
+	for _ in range(max(10, args.warmup)):                        # >= 10: the batch-norm running-average factor reaches its floor (0.1)
 		step()
 
-	sampler = ClockSampler(node.device) if node.index == 0 else None
-	if sampler:
-		sampler.start()
-	ms, launches = timed(args.steps)
-	clocks = sampler.stop() if sampler else None
+	# ---- eager: every operator call goes through the Python module API (Module.__call__ -> Backend -> ctypes -> libpzb200.so)
+	eagerMs, launches = timed(args.steps)
+	hostEnqueueMs = hostMs[0]
+	eagerE2eMs, _ = timed(args.steps, e2e=True)
+	launchesPerStep = launches / args.steps
 
-	msE2e, _ = timed(args.steps, e2e=True)
+	# ---- graph: the same step (same module calls, same kernels, same buffers) captured once into a CUDA graph and replayed
+	graphNote, sampler, clocks = None, None, None
+	try:
+		if args.no_graph:
+			raise RuntimeError("disabled by --no-graph")
+		graph = driver.StepGraph(lambda: step(False), warmup=2)
+		graphE2e = driver.StepGraph(lambda: step(True, True), warmup=2)
+		timedGraph(graph, 3)
+		sampler = ClockSampler(node.device) if node.index == 0 else None
+		if sampler:
+			sampler.start()
+		ms = timedGraph(graph, args.steps)
+		clocks = sampler.stop() if sampler else None
+		msE2e = timedGraph(graphE2e, args.steps)
+		launches = int(round(launchesPerStep * args.steps))
+		api = "StepGraph replay of the module-API step (driver.StepGraph: capture once, one launch per step)"
+	except Exception as e:                                           # noqa: BLE001 -- report eager numbers instead
+		graphNote = "graph capture unavailable: %s" % (str(e).splitlines()[0] if str(e) else type(e).__name__)
+		driver.setDefaultStream(None)
+		sampler = ClockSampler(node.device) if node.index == 0 else None
+		if sampler:
+			sampler.start()
+		ms, launches = timed(args.steps)
+		clocks = sampler.stop() if sampler else None
+		msE2e = eagerE2eMs
+		api = "eager module API"
 
 	# roofline pass: the same K steps with CUDA events around every launch of each kernel family
 	driver.profileEnable(True)
@@ -268,7 +314,10 @@ def gpuArm(args):
 			"step": "zeroGradParams + forward + backward (incl. conv1 dgrad) + grad mean over ranks + momentum-SGD update",
 			"l2": "no explicit flush: one step streams ~20 GB of activations through the 126 MB L2, every kernel's inputs exceed L2 between reuses",
 			"model_flops_per_image": FLOP_PER_IMAGE, "achieved_model_tflops_per_gpu": value / node.gridsize * FLOP_PER_IMAGE / 1e12,
+			"api": api,
 		},
+		"eager": {"value": images / (eagerMs * 1e-3), "ms_per_step": eagerMs / args.steps, "e2e_value": images / (eagerE2eMs * 1e-3),
+				  "host_enqueue_ms_per_step": hostEnqueueMs, "note": "same step driven op by op through the Python module API"},
 		"clocks": clocks,
 		"e2e": {"value": images / (msE2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": int(data.nbytes) * node.gridsize,
 				"d2h_bytes_per_step": BATCH * 1000 * 4 * node.gridsize},
@@ -284,6 +333,8 @@ def gpuArm(args):
 					  "reference's own numpy CPU backend cannot run conv/pool/batch-norm backward (SURVEY F5)" % (args.cpu_images, dt)
 		}
 
+	if graphNote:
+		line["config"]["graph"] = graphNote
 	print(json.dumps(line), flush=True)
 	node.close()
 
@@ -296,6 +347,7 @@ def main():
 	parser.add_argument("--impl", default="ours", choices=["ours", "reference"])
 	parser.add_argument("--cpu-images", type=int, default=8, help="bounded CPU-baseline sample (images per step)")
 	parser.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+	parser.add_argument("--no-graph", action="store_true", help="time the eager module API only (no CUDA-graph replay)")
 	args = parser.parse_args()
 
 	if args.impl == "reference":

@@ -83,6 +83,15 @@ int pz_memset8(void* ptr, uint8_t value, size_t count, void* stream);    /* Buff
 int pz_memset16(void* ptr, uint16_t value, size_t count, void* stream);  /* Buffer.c fillD16 */
 int pz_memset32(void* ptr, uint32_t value, size_t count, void* stream);  /* Buffer.c fillD32 */
 
+/* NULL stream arguments resolve to the library's current stream: the legacy default stream (what the reference uses for every
+   call, SURVEY 8b "Threading / streams") unless redirected here */
+int pz_set_default_stream(void* stream);
+/* whole-step CUDA graphs (launch-overhead removal behind Sequential / Handler.handle, Containers/Sequential.py:186-234):
+   capture everything the operator API enqueues between begin and end, replay it with one launch */
+int pz_graph_begin(void* stream);
+int pz_graph_end(void* stream, void** exec);
+int pz_graph_launch(void* exec, void* stream);
+int pz_graph_destroy(void* exec);
 int pz_stream_create(void** stream);
 int pz_stream_destroy(void* stream);
 int pz_stream_synchronize(void* stream);

@@ -43,7 +43,10 @@ void pz_set_error(int code, const char* fmt, ...);
 		}                                                                                        \
 	} while (0)
 
-static inline cudaStream_t pz_stream(void* s) { return (cudaStream_t)s; }
+// a NULL stream argument means "the library's current stream": the legacy default stream (what the reference uses for
+// everything) unless pz_set_default_stream() redirected it, e.g. to a capturing stream (pz_graph_begin)
+cudaStream_t pz_stream(void* s);
+void pz_norm_graph_begin(cudaStream_t stream);      // batch-norm accumulator reset hook (pz_norm.cu)
 
 int pz_num_sms();
 // library-owned device scratch, grown on demand and used in stream order (prepared conv filters, pooling winner maps);

@@ -193,8 +193,11 @@ template <typename T, int VEC, bool TRAIN>
 __global__ void __launch_bounds__(kThreads) bn_apply_kernel(const T* __restrict__ x, T* __restrict__ y, Slab g,
 															const float* __restrict__ sums, const float* __restrict__ scale,
 															const float* __restrict__ bias, float* mean_io, float* var_io, float* save_mean,
-															float* save_invvar, float eps, float factor, float count)
+															float* save_invvar, float eps, float factor, float count, float* zero_ptr,
+															int zero_n)
 {
+	// clear the accumulators the NEXT batch-norm pass will use (two buffers alternate, so no memset launch is needed)
+	for (int i = blockIdx.x * kThreads + threadIdx.x; i < zero_n; i += gridDim.x * kThreads) zero_ptr[i] = 0.0f;
 	const ItemRange ir = my_items(g);
 	int cur = -1;
 	uint32_t j = 0;
@@ -338,9 +341,10 @@ template <typename T, int VEC>
 __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx,
 																Slab g, const float* __restrict__ sums, const float* __restrict__ scale,
 																const float* __restrict__ save_mean, const float* __restrict__ save_invvar,
-																float* dscale, float* dbias, float count)
+																float* dscale, float* dbias, float count, float* zero_ptr, int zero_n)
 {
 	constexpr int UNR = kRowUnroll / 2;
+	for (int i = blockIdx.x * kThreads + threadIdx.x; i < zero_n; i += gridDim.x * kThreads) zero_ptr[i] = 0.0f;
 	const ItemRange ir = my_items(g);
 	int cur = -1;
 	uint32_t j = 0;
@@ -406,20 +410,46 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(const T* __restr
 }
 
 // ------------------------------------------------------------------------------------------ host side
-// [C][2] fp32 accumulators, library-owned and used in stream order (zeroed by a memset before every pass)
-float* sums_buffer(int64_t C)
+// Two [C][2] fp32 accumulator buffers, library-owned and used in stream order.  A pass accumulates into one of them and its
+// apply kernel clears what the previous pass left in the other, which the next pass will use.
+struct SumsPair {
+	float* use;          // all zero over [0, C)
+	float* clear;        // to be cleared by this pass over [0, clear_n)
+	int clear_n;
+};
+
+float* g_sums[2] = {nullptr, nullptr};
+int64_t g_sums_cap = 0, g_sums_dirty[2] = {0, 0};
+int g_sums_cur = 0;
+std::mutex g_sums_mu;
+
+bool acquire_sums(int64_t C, SumsPair& sp)
 {
-	static float* buf = nullptr;
-	static int64_t cap = 0;
-	static std::mutex mu;
-	std::lock_guard<std::mutex> lock(mu);
+	float* (&buf)[2] = g_sums;
+	int64_t& cap = g_sums_cap;
+	int64_t (&dirty)[2] = g_sums_dirty;
+	int& cur = g_sums_cur;
+	std::lock_guard<std::mutex> lock(g_sums_mu);
 	if (C > cap) {
-		if (buf) { cudaDeviceSynchronize(); cudaFree(buf); buf = nullptr; cap = 0; }
+		cudaDeviceSynchronize();
 		const int64_t want = C < 65536 ? 65536 : C + C / 2;
-		if (cudaMalloc((void**)&buf, (size_t)want * 2 * sizeof(float)) != cudaSuccess) return nullptr;
+		for (int i = 0; i < 2; i++) {
+			if (buf[i]) cudaFree(buf[i]);
+			buf[i] = nullptr;
+			if (cudaMalloc((void**)&buf[i], (size_t)want * 2 * sizeof(float)) != cudaSuccess) { cap = 0; cudaGetLastError(); return false; }
+			cudaMemset(buf[i], 0, (size_t)want * 2 * sizeof(float));
+			dirty[i] = 0;
+		}
 		cap = want;
 	}
-	return buf;
+	const int other = 1 - cur;
+	sp.use = buf[cur];
+	sp.clear = buf[other];
+	sp.clear_n = (int)(dirty[other] * 2);
+	dirty[cur] = C;
+	dirty[other] = 0;
+	cur = other;
+	return true;
 }
 
 struct Plan {
@@ -486,23 +516,23 @@ int fwd_train(const void* x, void* y, int64_t N, int64_t C, int64_t S, const flo
 {
 	constexpr int V = 16 / sizeof(T);
 	cudaStream_t s = pz_stream(stream);
-	float* sums = sums_buffer(C);
-	if (!sums) { pz_set_error(PZ_ERR_MEMORY, "batchnorm: cannot allocate the statistics buffer"); return PZ_ERR_MEMORY; }
+	SumsPair sp;
+	if (!acquire_sums(C, sp)) { pz_set_error(PZ_ERR_MEMORY, "batchnorm: cannot allocate the statistics buffer"); return PZ_ERR_MEMORY; }
+	float* sums = sp.use;
 	const Plan plan = make_plan<T>({x, y}, N, C, S, 1);
 	const float count = (float)(N * S);
 	PzProfScope prof(PZ_PROF_BN_FWD, s, 0.0, 2.0 * (double)N * C * S * sizeof(T));
-	PZ_CHECK_CUDA(cudaMemsetAsync(sums, 0, (size_t)C * 2 * sizeof(float), s));
 	for (int64_t c0 = 0; c0 < C; c0 += plan.slab_channels) {
 		const int64_t c1 = c0 + plan.slab_channels < C ? c0 + plan.slab_channels : C;
 		const Slab g = make_slab(plan, N, C, S, c0, c1);
 		if (plan.vec == V) {
 			PZ_BN_LAUNCH(V, (bn_stats_kernel<T, V>), bins_per_block(V, g.S) * 2 * sizeof(float), (const T*)x, g, sums);
 			PZ_BN_LAUNCH(V, (bn_apply_kernel<T, V, true>), 0, (const T*)x, (T*)y, g, sums, scale, bias, rm, rv, sm, siv, (float)eps,
-						 (float)factor, count);
+						 (float)factor, count, sp.clear, c0 == 0 ? sp.clear_n : 0);
 		} else {
 			PZ_BN_LAUNCH(1, (bn_stats_kernel<T, 1>), bins_per_block(1, g.S) * 2 * sizeof(float), (const T*)x, g, sums);
 			PZ_BN_LAUNCH(1, (bn_apply_kernel<T, 1, true>), 0, (const T*)x, (T*)y, g, sums, scale, bias, rm, rv, sm, siv, (float)eps,
-						 (float)factor, count);
+						 (float)factor, count, sp.clear, c0 == 0 ? sp.clear_n : 0);
 		}
 	}
 	PZ_LAUNCH_CHECK();
@@ -521,10 +551,10 @@ int fwd_infer(const void* x, void* y, int64_t N, int64_t C, int64_t S, const flo
 	PzProfScope prof(PZ_PROF_BN_FWD, s, 0.0, 2.0 * (double)N * C * S * sizeof(T));
 	if (plan.vec == V)
 		PZ_BN_LAUNCH(V, (bn_apply_kernel<T, V, false>), 0, (const T*)x, (T*)y, g, nullptr, scale, bias, (float*)mean, (float*)var, nullptr,
-					 nullptr, (float)eps, 0.0f, 1.0f);
+					 nullptr, (float)eps, 0.0f, 1.0f, nullptr, 0);
 	else
 		PZ_BN_LAUNCH(1, (bn_apply_kernel<T, 1, false>), 0, (const T*)x, (T*)y, g, nullptr, scale, bias, (float*)mean, (float*)var, nullptr,
-					 nullptr, (float)eps, 0.0f, 1.0f);
+					 nullptr, (float)eps, 0.0f, 1.0f, nullptr, 0);
 	PZ_LAUNCH_CHECK();
 	return PZ_OK;
 }
@@ -535,21 +565,21 @@ int bwd(const void* x, const void* dy, void* dx, int64_t N, int64_t C, int64_t S
 {
 	constexpr int V = 16 / sizeof(T);
 	cudaStream_t s = pz_stream(stream);
-	float* sums = sums_buffer(C);
-	if (!sums) { pz_set_error(PZ_ERR_MEMORY, "batchnorm: cannot allocate the statistics buffer"); return PZ_ERR_MEMORY; }
+	SumsPair sp;
+	if (!acquire_sums(C, sp)) { pz_set_error(PZ_ERR_MEMORY, "batchnorm: cannot allocate the statistics buffer"); return PZ_ERR_MEMORY; }
+	float* sums = sp.use;
 	const Plan plan = make_plan<T>({x, dy, dx}, N, C, S, 2);
 	const float count = (float)(N * S);
 	PzProfScope prof(PZ_PROF_BN_BWD, s, 0.0, 3.0 * (double)N * C * S * sizeof(T));
-	PZ_CHECK_CUDA(cudaMemsetAsync(sums, 0, (size_t)C * 2 * sizeof(float), s));
 	for (int64_t c0 = 0; c0 < C; c0 += plan.slab_channels) {
 		const int64_t c1 = c0 + plan.slab_channels < C ? c0 + plan.slab_channels : C;
 		const Slab g = make_slab(plan, N, C, S, c0, c1);
 		if (plan.vec == V) {
 			PZ_BN_LAUNCH(V, (bn_bwd_stats_kernel<T, V>), bins_per_block(V, g.S) * 2 * sizeof(float), (const T*)x, (const T*)dy, g, sm, sums);
-			PZ_BN_LAUNCH(V, (bn_bwd_apply_kernel<T, V>), 0, (const T*)x, (const T*)dy, (T*)dx, g, sums, scale, sm, siv, dscale, dbias, count);
+			PZ_BN_LAUNCH(V, (bn_bwd_apply_kernel<T, V>), 0, (const T*)x, (const T*)dy, (T*)dx, g, sums, scale, sm, siv, dscale, dbias, count, sp.clear, c0 == 0 ? sp.clear_n : 0);
 		} else {
 			PZ_BN_LAUNCH(1, (bn_bwd_stats_kernel<T, 1>), bins_per_block(1, g.S) * 2 * sizeof(float), (const T*)x, (const T*)dy, g, sm, sums);
-			PZ_BN_LAUNCH(1, (bn_bwd_apply_kernel<T, 1>), 0, (const T*)x, (const T*)dy, (T*)dx, g, sums, scale, sm, siv, dscale, dbias, count);
+			PZ_BN_LAUNCH(1, (bn_bwd_apply_kernel<T, 1>), 0, (const T*)x, (const T*)dy, (T*)dx, g, sums, scale, sm, siv, dscale, dbias, count, sp.clear, c0 == 0 ? sp.clear_n : 0);
 		}
 	}
 	PZ_LAUNCH_CHECK();
@@ -574,6 +604,18 @@ int check_dims(int64_t N, int64_t C, int64_t S)
 }
 
 }  // namespace
+
+// A captured graph replays the same accumulator choreography every time, so it must start from a known state: both buffers
+// cleared (as the first nodes of the graph) and the alternation reset.
+void pz_norm_graph_begin(cudaStream_t stream)
+{
+	std::lock_guard<std::mutex> lock(g_sums_mu);
+	for (int i = 0; i < 2; i++) {
+		if (g_sums[i]) cudaMemsetAsync(g_sums[i], 0, (size_t)g_sums_cap * 2 * sizeof(float), stream);
+		g_sums_dirty[i] = 0;
+	}
+	g_sums_cur = 0;
+}
 
 extern "C" {
 

@@ -21,6 +21,10 @@ void pz_set_error(int code, const char* fmt, ...)
 	va_end(ap);
 }
 
+static cudaStream_t g_default_stream = nullptr;
+
+cudaStream_t pz_stream(void* s) { return s ? (cudaStream_t)s : g_default_stream; }
+
 void pz_count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
 int pz_num_sms()
@@ -341,7 +345,58 @@ int pz_fill64(void* ptr, uint64_t value, int64_t count, void* stream)
 	return pz_fill_any<uint64_t>((uint64_t*)ptr, value, (size_t)count, stream);
 }
 
-// ---------------------------------------------------------------------------------------- streams / events
+// ---------------------------------------------------------------------------------------- streams / events / graphs
+int pz_set_default_stream(void* stream)
+{
+	g_default_stream = (cudaStream_t)stream;
+	return PZ_OK;
+}
+
+// Whole-step CUDA graphs: every entry point enqueues on pz_stream(), so a step driven by the unchanged Python operator API can
+// be captured once and replayed with a single launch (no per-op host work, no inter-kernel launch gaps).  The caller must have
+// run the step at least once before (memory-pool blocks, scratch buffers and kernel attributes exist) and keep the step free
+// of host synchronisation.  Scalars (learning rate, batch-norm factor) are frozen at their capture-time values.
+int pz_graph_begin(void* stream)
+{
+	PZ_REQUIRE(stream != nullptr, "graph capture needs a real stream (the legacy default stream cannot be captured)");
+	g_default_stream = (cudaStream_t)stream;
+	PZ_CHECK_CUDA(cudaStreamBeginCapture((cudaStream_t)stream, cudaStreamCaptureModeRelaxed));
+	pz_norm_graph_begin((cudaStream_t)stream);
+	return PZ_OK;
+}
+
+int pz_graph_end(void* stream, void** exec)
+{
+	cudaGraph_t graph = nullptr;
+	cudaError_t e = cudaStreamEndCapture((cudaStream_t)stream, &graph);
+	if (e != cudaSuccess || graph == nullptr) {
+		pz_set_error(PZ_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+		cudaGetLastError();
+		return PZ_ERR_CUDA;
+	}
+	cudaGraphExec_t ge = nullptr;
+	e = cudaGraphInstantiate(&ge, graph, 0);
+	cudaGraphDestroy(graph);
+	if (e != cudaSuccess) {
+		pz_set_error(PZ_ERR_CUDA, "graph instantiation failed: %s", cudaGetErrorString(e));
+		return PZ_ERR_CUDA;
+	}
+	*exec = (void*)ge;
+	return PZ_OK;
+}
+
+int pz_graph_launch(void* exec, void* stream)
+{
+	PZ_CHECK_CUDA(cudaGraphLaunch((cudaGraphExec_t)exec, pz_stream(stream)));
+	return PZ_OK;
+}
+
+int pz_graph_destroy(void* exec)
+{
+	PZ_CHECK_CUDA(cudaGraphExecDestroy((cudaGraphExec_t)exec));
+	return PZ_OK;
+}
+
 int pz_stream_create(void** stream)
 {
 	cudaStream_t s;

@@ -92,6 +92,11 @@ _SIGNATURES = {
 	"pz_memset16": [_P, c_uint16, c_size_t, _P],
 	"pz_memset32": [_P, c_uint32, c_size_t, _P],
 	"pz_fill64": [_P, c_uint64, c_int64, _P],
+	"pz_set_default_stream": [_P],
+	"pz_graph_begin": [_P],
+	"pz_graph_end": [_P, POINTER(_P)],
+	"pz_graph_launch": [_P, _P],
+	"pz_graph_destroy": [_P],
 	"pz_stream_create": [POINTER(_P)],
 	"pz_stream_destroy": [_P],
 	"pz_stream_synchronize": [_P],
@@ -447,6 +452,56 @@ class Stream:
 			if self.handle:
 				lib.pz_stream_destroy(self.handle)
 				self.handle = None
+		except Exception:
+			pass
+
+
+def setDefaultStream(stream):
+	"""Route every operator call that does not name a stream (all of the reference API) to `stream`; None restores the legacy
+	default stream."""
+	check(lib.pz_set_default_stream(stream.handle if stream is not None else None))
+
+
+class StepGraph:
+	"""One training / inference step captured as a CUDA graph.
+
+	`fn` is any callable driving the unchanged operator API (e.g. zeroGradParams + net(data) + net.backward(grad) +
+	optimizer.update() + net.reset()).  It is run `warmup` times eagerly on a private stream -- so that the memory pool holds
+	every block the step needs, scratch buffers exist and step-count dependent scalars (batch-norm factor) have reached their
+	steady state -- then once more under stream capture.  `launch()` replays the captured kernels with a single host call;
+	device pointers, shapes and scalars are those of the captured run.
+	"""
+
+	def __init__(self, fn, warmup=2):
+		self.stream = Stream()
+		self.exec = None
+		setDefaultStream(self.stream)
+		try:
+			for _ in range(warmup):
+				fn()
+			self.stream.synchronize()
+			check(lib.pz_graph_begin(self.stream.handle))
+			try:
+				fn()
+			finally:
+				h = c_void_p()
+				status = lib.pz_graph_end(self.stream.handle, byref(h))
+			check(status)
+			self.exec = h.value
+		finally:
+			setDefaultStream(None)
+
+	def launch(self):
+		check(lib.pz_graph_launch(self.exec, self.stream.handle))
+
+	def synchronize(self):
+		self.stream.synchronize()
+
+	def __del__(self):
+		try:
+			if self.exec:
+				lib.pz_graph_destroy(self.exec)
+				self.exec = None
 		except Exception:
 			pass
 
