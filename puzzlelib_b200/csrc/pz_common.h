@@ -55,8 +55,11 @@ void* pz_scratch(size_t bytes);
 void pz_count_launch(int n);
 
 // ---- optional per-launch profiling (bench.py roofline): CUDA events around the launches of one kernel family
+// PZ_PROF_GEMM: tcgen05 launches whose arithmetic intensity (algorithmic flops / bytes) is above the machine ridge -- bounded by
+// the tensor pipe; PZ_PROF_GEMM_HBM: the ones below it (ResNet's 1x1 convolutions) -- bounded by HBM
 enum { PZ_PROF_GEMM = 0, PZ_PROF_BN_FWD = 1, PZ_PROF_BN_BWD = 2, PZ_PROF_ELTWISE = 3, PZ_PROF_POOL = 4, PZ_PROF_OTHER = 5,
-	   PZ_PROF_FAMILIES = 6 };
+	   PZ_PROF_GEMM_HBM = 6, PZ_PROF_FAMILIES = 7 };
+constexpr double kPzRidgeFlopPerByte = 108.0;     // ~709 TFLOP/s tf32 / 6.55 TB/s measured on this pool's B200s
 bool pz_prof_on();
 void pz_prof_begin(int family, cudaStream_t stream, double flops, double bytes);
 void pz_prof_end(cudaStream_t stream);

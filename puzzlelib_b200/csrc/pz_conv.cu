@@ -23,7 +23,7 @@ struct Geo {
 
 int check_desc(int dtype, const pz_conv2d_desc* d, Geo& g)
 {
-	PZ_REQUIRE(dtype == PZ_F32, "conv2d: only float32 storage is implemented (got dtype %d)", dtype);
+	PZ_REQUIRE(dtype == PZ_F32 || dtype == PZ_F16 || dtype == PZ_BF16, "conv2d: unsupported dtype %d", dtype);
 	PZ_REQUIRE(d != nullptr, "conv2d: null descriptor");
 	g = Geo{d->N, d->C, d->H, d->W, d->K, d->R, d->S, d->P, d->Q, d->stride_h, d->stride_w, d->pad_h, d->pad_w,
 			d->dil_h, d->dil_w, d->groups, 0, 0};
@@ -72,29 +72,31 @@ void set_splits(GemmParams& p, long long tiles, int min_kb_per_split)
 }
 
 // algorithmic work of one conv pass: 2*MACs; every operand read once + the result written once
-void set_alg(GemmParams& p, const Geo& g)
+void set_alg(GemmParams& p, const Geo& g, int dtype)
 {
 	const double x = (double)g.N * g.C * g.H * g.W, y = (double)g.N * g.K * g.P * g.Q, w = (double)g.K * g.Cg * g.R * g.S;
 	p.alg_flops = 2.0 * y * g.Cg * g.R * g.S;
-	p.alg_bytes = 4.0 * (x + y + w);
+	p.alg_bytes = (double)pz_dtype_size(dtype) * (x + y + w);
 }
 
-inline int round_up32(int v) { return (v + 31) & ~31; }
-inline int round_up32_c(int v) { return (v + 31) & ~31; }
 
 // Prepared filters (the TMA-fetched operand of fprop / dgrad): fp32 rows of `kpad` (multiple of 32) elements, K-major,
 // rounded to tf32 (the tensor core would otherwise truncate) and zero-padded, in the library scratch.
 
 // fprop: wp[ko_total][k] = w[ko_total][k], k = (c, r, s) < kdim
 // chan != 0: k ordered (tap, channel block, 32 channels) for MnChanProducer, kpad = RS * ceil(Cg / 32) * 32
-__global__ void prep_filter_fprop(const float* __restrict__ w, float* __restrict__ wp, int kdim, int kpad, long long total, int chan, int Cg,
+template <typename T> __device__ __forceinline__ T prep_round(T v) { return v; }
+template <> __device__ __forceinline__ float prep_round<float>(float v) { return __uint_as_float(to_tf32(v)); }
+
+template <typename T>
+__global__ void prep_filter_fprop(const T* __restrict__ w, T* __restrict__ wp, int kdim, int kpad, long long total, int chan, int Cg,
 								   int RS)
 {
 	long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= total) return;
 	const int k = (int)(i % kpad);
 	const long long row = i / kpad;
-	float v = 0.0f;
+	T v = T(0.0f);
 	if (chan) {
 		const int cpad = kpad / RS;
 		const int t = k / cpad, c = k % cpad;
@@ -102,13 +104,14 @@ __global__ void prep_filter_fprop(const float* __restrict__ w, float* __restrict
 	} else if (k < kdim) {
 		v = w[row * kdim + k];
 	}
-	wp[i] = __uint_as_float(to_tf32(v));
+	wp[i] = prep_round<T>(v);
 }
 
 // dgrad: wt[g*Cg + c][(ko, r', s')] = w[g*Kg + ko][c][r0 + sh*r'][s0 + sw*s'] -- the sub-filter of one output-parity class of
 // a strided transposed convolution (r0 = s0 = 0, sh = sw = 1, Rc = R, Sc = S: the whole filter, stride-1 dgrad)
 // chan != 0: k ordered (tap (r', s'), ko block, 32 ko) for MnChanProducer, kpad = Rc * Sc * ceil(Kg / 32) * 32
-__global__ void prep_filter_dgrad(const float* __restrict__ w, float* __restrict__ wt, int Kg, int Cg, int R, int S, int r0, int s0,
+template <typename T>
+__global__ void prep_filter_dgrad(const T* __restrict__ w, T* __restrict__ wt, int Kg, int Cg, int R, int S, int r0, int s0,
 								   int sh, int sw, int Rc, int Sc, int kpad, long long total, int chan)
 {
 	long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -129,13 +132,23 @@ __global__ void prep_filter_dgrad(const float* __restrict__ w, float* __restrict
 		rc = k % Rc;
 		ko = k / Rc;
 	}
-	float v = 0.0f;
+	T v = T(0.0f);
 	if (ko >= 0) {
 		const int c = row % Cg, g = row / Cg;
-		v = __uint_as_float(to_tf32(w[((((long long)g * Kg + ko) * Cg + c) * R + (r0 + sh * rc)) * S + (s0 + sw * sc)]));
+		v = prep_round<T>(w[((((long long)g * Kg + ko) * Cg + c) * R + (r0 + sh * rc)) * S + (s0 + sw * sc)]);
 	}
 	wt[i] = v;
 }
+
+// launch a templated prep kernel for the storage type (16-bit types are moved as raw bits)
+#define PZ_PREP_LAUNCH(dtype, kernel, total, stream, w, wt, ...)                                                                      \
+	do {                                                                                                                              \
+		if ((dtype) == PZ_F32)                                                                                                        \
+			kernel<float><<<(unsigned)pz_cdiv(total, 256), 256, 0, stream>>>((const float*)(w), (float*)(wt), __VA_ARGS__);           \
+		else                                                                                                                          \
+			kernel<__half><<<(unsigned)pz_cdiv(total, 256), 256, 0, stream>>>((const __half*)(w), (__half*)(wt), __VA_ARGS__);        \
+		pz_count_launch(1);                                                                                                           \
+	} while (0)
 
 // col2im dgrad: wt[(c, r, s)][ko] = w[ko][c][r][s] (the filter transposed), rows of kpad elements
 __global__ void prep_filter_col2im(const float* __restrict__ w, float* __restrict__ wt, int K, int CRS, int kpad, long long total)
@@ -148,25 +161,27 @@ __global__ void prep_filter_col2im(const float* __restrict__ w, float* __restric
 }
 
 // the (tap, channel) k order pads the channels of every tap to a multiple of 32: worth it unless the channel count is tiny
-inline bool use_chan_order(int chans) { return round_up32_c(chans) * 3 <= chans * 4; }
+inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+// bke = elements per k-block: 32 (float) or 64 (half / bfloat16)
+inline bool use_chan_order(int chans, int bke) { return round_up(chans, bke) * 3 <= chans * 4; }
 
 // row length of the prepared dgrad filter: `taps` taps of Kg output channels
-inline int dgrad_kpad(int Kg, int taps, bool may_chan)
+inline int dgrad_kpad(int Kg, int taps, bool may_chan, int bke)
 {
-	return may_chan && use_chan_order(Kg) ? taps * round_up32_c(Kg) : round_up32_c(Kg * taps);
+	return may_chan && use_chan_order(Kg, bke) ? taps * round_up(Kg, bke) : round_up(Kg * taps, bke);
 }
 
 
-template <int THREADS>
-__global__ void __launch_bounds__(THREADS) bias_grad_kernel(const float* __restrict__ t, float* __restrict__ db, long long N,
+template <int THREADS, typename T>
+__global__ void __launch_bounds__(THREADS) bias_grad_kernel(const T* __restrict__ t, float* __restrict__ db, long long N,
 															 long long C, long long S, float alpha, int nsplit)
 {
 	// grid = (C, nsplit): each CTA reduces a slice of the images of one channel, then one red.add
 	const long long c = blockIdx.x;
 	float acc = 0.0f;
 	for (long long n = blockIdx.y; n < N; n += nsplit) {
-		const float* plane = t + (n * C + c) * S;
-		for (long long s = threadIdx.x; s < S; s += THREADS) acc += plane[s];
+		const T* plane = t + (n * C + c) * S;
+		for (long long s = threadIdx.x; s < S; s += THREADS) acc += (float)plane[s];
 	}
 	__shared__ float part[THREADS / 32];
 	#pragma unroll
@@ -201,7 +216,9 @@ int pz_conv2d_fprop(int dtype, const pz_conv2d_desc* d, const void* x, const voi
 
 	GemmParams p{};
 	Operand& A = p.A;   // im2col view of x: rows (n,p,q), k (c,r,s)
-	A.ptr = (const float*)x;
+	const int bke = elems_per_kblock(dtype);
+	const bool h16 = dtype != PZ_F32;
+	A.ptr = x;
 	A.rd12 = make_fastdiv(PQ); A.rd2 = make_fastdiv(g.Q);
 	A.kd12 = make_fastdiv(RS); A.kd2 = make_fastdiv(g.S);
 	A.rs0 = g.C * HW; A.ks0 = HW;
@@ -215,21 +232,20 @@ int pz_conv2d_fprop(int dtype, const pz_conv2d_desc* d, const void* x, const voi
 
 	// filter: prepared copy [K][kpad], fetched by TMA
 	const bool fast = tap_entries_fit(34ll * HW, g);
-	const bool chan = fast && use_chan_order(g.Cg);
-	const int kdim = g.Cg * RS, kpad = chan ? RS * round_up32(g.Cg) : round_up32(kdim);
+	const bool chan = fast && use_chan_order(g.Cg, bke);
+	const int kdim = g.Cg * RS, kpad = chan ? RS * round_up(g.Cg, bke) : round_up(kdim, bke);
 	const long long wtotal = (long long)g.K * kpad;
-	float* wp = scratch((size_t)wtotal * sizeof(float));
+	void* wp = pz_scratch((size_t)wtotal * pz_dtype_size(dtype));
 	if (!wp) { pz_set_error(PZ_ERR_MEMORY, "conv2d fprop: cannot allocate %lld bytes of filter scratch", wtotal * 4); return PZ_ERR_MEMORY; }
-	prep_filter_fprop<<<(unsigned)pz_cdiv(wtotal, 256), 256, 0, pz_stream(stream)>>>((const float*)w, wp, kdim, kpad, wtotal, chan ? 1 : 0,
-																					 g.Cg, RS);
-	pz_count_launch(1);
+	PZ_PREP_LAUNCH(dtype, prep_filter_fprop, wtotal, pz_stream(stream), w, wp, kdim, kpad, wtotal, chan ? 1 : 0, g.Cg, RS);
 	PZ_LAUNCH_CHECK();
 	const TmaSource tsrc{wp, g.K, kpad};
 	p.tma_rows_per_group = g.Kg;
 
 	Epilogue& E = p.E;
-	E.out = (float*)y;
-	E.bias = (const float*)bias;
+	E.out = y;
+	E.bias = bias;
+	E.out_kind = out_kind_of(dtype);
 	E.md12 = make_fastdiv(PQ); E.md2 = make_fastdiv(0);
 	E.ms0 = g.K * PQ; E.ms1 = 0; E.ms2 = 1;
 	E.ncs = PQ;
@@ -241,13 +257,15 @@ int pz_conv2d_fprop(int dtype, const pz_conv2d_desc* d, const void* x, const voi
 	E.bias_group_stride = g.Kg;
 
 	A.chans = g.Cg;
-	A.kbdiv = make_fastdiv((uint32_t)(round_up32(g.Cg) / 32));
-	p.kblocks = kpad / BK;
+	A.kbdiv = make_fastdiv((uint32_t)(round_up(g.Cg, bke) / bke));
+	p.kblocks = kpad / bke;
 	p.splits = 1;
 	p.kb_per_split = p.kblocks;
-	set_alg(p, g);
+	set_alg(p, g, dtype);
 	const int bn = pick_bn(g.Kg, (long long)g.N * PQ, p.kblocks, g.G, 256);
-	return launch(p, bn, chan ? MODE_MN_CHAN : (fast ? MODE_MN_TAP : MODE_MN_GENERAL), MODE_TMA, fast && RS > 31, g.G, &tsrc, pz_stream(stream));
+	// the table-driven tap producer exists for float only; 16-bit tensors with very few channels take the general gather
+	const int amode = chan ? MODE_MN_CHAN : (fast && !h16 ? MODE_MN_TAP : MODE_MN_GENERAL);
+	return launch(p, dtype, bn, amode, MODE_TMA, amode == MODE_MN_GENERAL ? false : RS > 31, g.G, &tsrc, pz_stream(stream));
 }
 
 // the dgrad filter repack lives in the library's own scratch; callers need not supply a workspace any more
@@ -268,9 +286,13 @@ int pz_conv2d_dgrad(int dtype, const pz_conv2d_desc* d, const void* dy, const vo
 	const bool is1x1 = g.R == 1 && g.S == 1;
 	const bool strided = g.sh > 1 || g.sw > 1;
 
+	const int bke = elems_per_kblock(dtype);
+	const bool h16 = dtype != PZ_F32;
+	const size_t es = pz_dtype_size(dtype);
 	Epilogue E{};
-	E.out = (float*)dx;
-	E.bias = (const float*)bias;
+	E.out = dx;
+	E.bias = bias;
+	E.out_kind = out_kind_of(dtype);
 	E.alpha = 1.0f; E.beta = 0.0f;
 	E.bias_mode = bias ? 1 : 0;
 	E.atomic = 0;
@@ -286,18 +308,23 @@ int pz_conv2d_dgrad(int dtype, const pz_conv2d_desc* d, const void* dy, const vo
 	// input-gradient positions (a_h + sh*h', a_w + sw*w'); the whole tensor for stride 1 (a = 0, sh = sw = 1).
 	// mode 0: parity class of a strided, un-dilated filter (fast tap producer); mode 1: stride 1, any dilation (fast tap
 	// producer); mode 2: any stride and dilation through the exact-division gather (csh = csw = 1, whole filter).
-	auto run_class = [&](float* wt, int a_h, int a_w, int r0, int s0, int csh, int csw, int Rc, int Sc, int Hc, int Wc, int mode) -> int {
-		const bool chan = mode != 2 && use_chan_order(g.Kg);
-		const int kdim = g.Kg * Rc * Sc, kpad = dgrad_kpad(g.Kg, Rc * Sc, mode != 2);
+	auto run_class = [&](char* wt, int a_h, int a_w, int r0, int s0, int csh, int csw, int Rc, int Sc, int Hc, int Wc, int mode) -> int {
+		if (mode != 2 && h16 && !use_chan_order(g.Kg, bke)) {
+			// no table-driven tap producer for 16-bit tensors: few output channels take the general gather, which handles the
+			// whole (possibly strided) problem in one launch -- only legal when called for the whole tensor
+			PZ_REQUIRE(a_h == 0 && a_w == 0 && csh == 1 && csw == 1, "conv2d dgrad: 16-bit strided filters need >= 48 output channels");
+			mode = 2;
+		}
+		const bool chan = mode != 2 && use_chan_order(g.Kg, bke);
+		const int kdim = g.Kg * Rc * Sc, kpad = dgrad_kpad(g.Kg, Rc * Sc, mode != 2, bke);
 		const long long total = (long long)g.C * kpad;
-		prep_filter_dgrad<<<(unsigned)pz_cdiv(total, 256), 256, 0, pz_stream(stream)>>>((const float*)w, wt, g.Kg, g.Cg, g.R, g.S, r0, s0,
-																						csh, csw, Rc, Sc, kpad, total, chan ? 1 : 0);
-		pz_count_launch(1);
+		PZ_PREP_LAUNCH(dtype, prep_filter_dgrad, total, pz_stream(stream), w, wt, g.Kg, g.Cg, g.R, g.S, r0, s0, csh, csw, Rc, Sc, kpad, total,
+					   chan ? 1 : 0);
 		PZ_LAUNCH_CHECK();
 
 		GemmParams q{};
 		Operand& QA = q.A;                 // rows (n, h', w') of the class, k (ko, r', s')
-		QA.ptr = (const float*)dy;
+		QA.ptr = dy;
 		QA.rd12 = make_fastdiv(Hc * Wc); QA.rd2 = make_fastdiv(Wc);
 		QA.kd12 = make_fastdiv(Rc * Sc); QA.kd2 = make_fastdiv(Sc);
 		QA.rs0 = g.K * PQ; QA.ks0 = PQ;
@@ -315,33 +342,33 @@ int pz_conv2d_dgrad(int dtype, const pz_conv2d_desc* d, const void* dy, const vo
 		QA.rows = g.N * Hc * Wc; QA.kdim = kdim;
 		QA.R = Rc; QA.S = Sc;
 		QA.chans = g.Kg;
-		QA.kbdiv = make_fastdiv((uint32_t)(round_up32(g.Kg) / 32));
+		QA.kbdiv = make_fastdiv((uint32_t)(round_up(g.Kg, bke) / bke));
 		QA.group_stride = (long long)g.Kg * PQ;
 
 		q.E = E;
-		q.E.out = (float*)dx + (long long)a_h * g.W + a_w;
+		q.E.out = (char*)dx + ((long long)a_h * g.W + a_w) * es;
 		q.E.md12 = make_fastdiv(Hc * Wc); q.E.md2 = make_fastdiv(Wc);
 		q.E.ms0 = g.C * HW; q.E.ms1 = csh * g.W; q.E.ms2 = csw;
 		q.E.M = g.N * Hc * Wc;
 		q.splits = 1;
-		q.kblocks = kpad / BK;
+		q.kblocks = kpad / bke;
 		q.kb_per_split = q.kblocks;
 		q.tma_rows_per_group = g.Cg;
 		q.alg_flops = 2.0 * (double)q.E.M * g.K * g.Cg * Rc * Sc / g.G;
-		q.alg_bytes = 4.0 * ((double)g.N * g.K * PQ / (csh * csw) + (double)g.K * g.Cg * Rc * Sc + (double)q.E.M * g.C);
+		q.alg_bytes = (double)es * ((double)g.N * g.K * PQ / (csh * csw) + (double)g.K * g.Cg * Rc * Sc + (double)q.E.M * g.C);
 		const TmaSource tsrc{wt, g.C, kpad};
 		const int bn = pick_bn(g.Cg, q.E.M, q.kblocks, g.G, 256);
 		const bool cdiv = mode == 2 ? strided : Rc * Sc > 31;
-		return launch(q, bn, mode == 2 ? MODE_MN_GENERAL : (chan ? MODE_MN_CHAN : MODE_MN_TAP), MODE_TMA, cdiv, g.G, &tsrc, pz_stream(stream));
+		return launch(q, dtype, bn, mode == 2 ? MODE_MN_GENERAL : (chan ? MODE_MN_CHAN : MODE_MN_TAP), MODE_TMA, cdiv, g.G, &tsrc, pz_stream(stream));
 	};
 
-	if (g.G == 1 && g.C <= 4 && g.C * RS <= 256 && RS > 1 && bias == nullptr && use_chan_order(g.K) && tap_entries_fit(34ll * PQ, g)) {
+	if (!h16 && g.G == 1 && g.C <= 4 && g.C * RS <= 256 && RS > 1 && bias == nullptr && use_chan_order(g.K, bke) && tap_entries_fit(34ll * PQ, g)) {
 		// Very few input channels (the first layer of a network): the implicit GEMM over (n, h, w) x c would gather every dy
 		// element R*S times for a handful of output columns.  Instead  D[(n,p,q)][(c,r,s)] = sum_k dy[n,k,p,q] * w[k,c,r,s]
 		// reads dy exactly once (a 1x1-convolution-shaped GEMM) and the epilogue scatters D into dx (col2im) with red.add.
 		st = pz_memset8(dx, 0, (size_t)g.N * g.C * HW * 4, stream);
 		if (st != PZ_OK) return st;
-		const int crs = g.C * RS, kpad = round_up32(g.K);
+		const int crs = g.C * RS, kpad = round_up(g.K, 32);
 		const long long total = (long long)crs * kpad;
 		float* wt = scratch((size_t)total * sizeof(float));
 		if (!wt) { pz_set_error(PZ_ERR_MEMORY, "conv2d dgrad: cannot allocate filter scratch"); return PZ_ERR_MEMORY; }
@@ -383,21 +410,22 @@ int pz_conv2d_dgrad(int dtype, const pz_conv2d_desc* d, const void* dy, const vo
 		q.alg_bytes = 4.0 * ((double)g.N * g.K * PQ + (double)g.K * crs + (double)g.N * g.C * HW);
 		const TmaSource tsrc{wt, crs, kpad};
 		const int bn = crs <= 64 ? 64 : (crs <= 128 ? 128 : 256);
-		return launch(q, bn, MODE_MN_CHAN, MODE_TMA, false, 1, &tsrc, pz_stream(stream));
+		return launch(q, dtype, bn, MODE_MN_CHAN, MODE_TMA, false, 1, &tsrc, pz_stream(stream));
 	}
 
 	if (is1x1 && g.ph == 0 && g.pw == 0 && strided) {
 		// 1x1 strided: dx[n,c,p*sh,q*sw] = sum_k dy[n,k,p,q] * w[k,c]; all other positions of dx are zero (+ bias)
 		PZ_REQUIRE(bias == nullptr, "conv2d dgrad: bias with a strided 1x1 filter is not supported");
-		st = pz_memset8(dx, 0, (size_t)g.N * g.C * HW * 4, stream);
+		st = pz_memset8(dx, 0, (size_t)g.N * g.C * HW * es, stream);
 		if (st != PZ_OK) return st;
-		float* wt = scratch((size_t)g.C * dgrad_kpad(g.Kg, 1, true) * sizeof(float));
+		char* wt = (char*)pz_scratch((size_t)g.C * dgrad_kpad(g.Kg, 1, true, bke) * es);
 		if (!wt) { pz_set_error(PZ_ERR_MEMORY, "conv2d dgrad: cannot allocate filter scratch"); return PZ_ERR_MEMORY; }
 		PZ_REQUIRE(tap_entries_fit(34ll * PQ, g), "conv2d dgrad: tensor too large");
+		PZ_REQUIRE(!h16 || use_chan_order(g.Kg, bke), "conv2d dgrad: 16-bit strided filters need >= 48 output channels");
 		return run_class(wt, 0, 0, 0, 0, g.sh, g.sw, 1, 1, g.P, g.Q, 0);
 	}
 
-	if (strided && g.dh == 1 && g.dw == 1 && tap_entries_fit(34ll * PQ, g)) {
+	if (strided && g.dh == 1 && g.dw == 1 && tap_entries_fit(34ll * PQ, g) && (!h16 || use_chan_order(g.Kg, bke))) {
 		// A strided transposed convolution splits into sh*sw independent STRIDE-1 problems, one per parity class
 		// (h mod sh, w mod sw) of the input-gradient positions: only the taps r = r0 + sh*r' with r0 = (a_h + pad_h) mod sh
 		// can reach such a position.  No tap is ever evaluated on a zero, and each class runs on the fast tap producer.
@@ -406,9 +434,9 @@ int pz_conv2d_dgrad(int dtype, const pz_conv2d_desc* d, const void* dy, const vo
 			for (int a_w = 0; a_w < g.sw && a_w < g.W; a_w++) {
 				const int r0 = (a_h + g.ph) % g.sh, s0 = (a_w + g.pw) % g.sw;
 				const int Rc = r0 < g.R ? (g.R - r0 + g.sh - 1) / g.sh : 0, Sc = s0 < g.S ? (g.S - s0 + g.sw - 1) / g.sw : 0;
-				need += (size_t)g.C * dgrad_kpad(g.Kg, Rc * Sc, true) * sizeof(float);
+				need += (size_t)g.C * dgrad_kpad(g.Kg, Rc * Sc, true, bke) * es;
 			}
-		float* wsp = scratch(need);
+		char* wsp = (char*)pz_scratch(need);
 		if (!wsp) { pz_set_error(PZ_ERR_MEMORY, "conv2d dgrad: cannot allocate %zu bytes of filter scratch", need); return PZ_ERR_MEMORY; }
 		bool zeroed = false;
 		for (int a_h = 0; a_h < g.sh && a_h < g.H; a_h++)
@@ -420,7 +448,7 @@ int pz_conv2d_dgrad(int dtype, const pz_conv2d_desc* d, const void* dy, const vo
 					// no tap reaches this class (stride larger than the filter): those gradients are zero (+ bias)
 					if (!zeroed) {
 						PZ_REQUIRE(bias == nullptr, "conv2d dgrad: bias with stride > filter size is not supported");
-						st = pz_memset8(dx, 0, (size_t)g.N * g.C * HW * 4, stream);
+						st = pz_memset8(dx, 0, (size_t)g.N * g.C * HW * es, stream);
 						if (st != PZ_OK) return st;
 						zeroed = true;      // the memset precedes every class launch in stream order: classes only overwrite their own positions
 					}
@@ -428,14 +456,14 @@ int pz_conv2d_dgrad(int dtype, const pz_conv2d_desc* d, const void* dy, const vo
 				}
 				st = run_class(wsp, a_h, a_w, r0, s0, g.sh, g.sw, Rc, Sc, Hc, Wc, 0);
 				if (st != PZ_OK) return st;
-				wsp += (size_t)g.C * dgrad_kpad(g.Kg, Rc * Sc, true);
+				wsp += (size_t)g.C * dgrad_kpad(g.Kg, Rc * Sc, true, bke) * es;
 			}
 		return PZ_OK;
 	}
 
 	{
 		const bool tapmode = !strided && tap_entries_fit(34ll * PQ, g);
-		float* wt = scratch((size_t)g.C * dgrad_kpad(g.Kg, RS, tapmode) * sizeof(float));
+		char* wt = (char*)pz_scratch((size_t)g.C * round_up(g.Kg, bke) * RS * es);
 		if (!wt) { pz_set_error(PZ_ERR_MEMORY, "conv2d dgrad: cannot allocate filter scratch"); return PZ_ERR_MEMORY; }
 		return run_class(wt, 0, 0, 0, 0, 1, 1, g.R, g.S, g.H, g.W, tapmode ? 1 : 2);
 	}
@@ -450,14 +478,16 @@ int pz_conv2d_wgrad(int dtype, const pz_conv2d_desc* d, const void* x, const voi
 	const int RS = g.R * g.S, PQ = g.P * g.Q, HW = g.H * g.W;
 	PZ_REQUIRE((long long)g.N * PQ < (1ll << 31), "conv2d wgrad: reduction too long");
 
-	// reduction index k ordered (image, block of 32 positions): k-block kb = n * kbpi + pb (positions past PQ are zero)
-	const int kbpi = (int)pz_cdiv(PQ, BK);
+	// reduction index k ordered (image, block of positions): k-block kb = n * kbpi + pb (positions past PQ are zero)
+	const int bke = elems_per_kblock(dtype);
+	const bool h16 = dtype != PZ_F32;
+	const int kbpi = (int)pz_cdiv(PQ, bke);
 	const bool dense_x = RS == 1 && g.sh == 1 && g.sw == 1 && g.ph == 0 && g.pw == 0;
 	const bool fast = tap_entries_fit((long long)g.Cg * HW, g);
 
 	GemmParams p{};
 	Operand& A = p.A;   // im2col view of x: rows (c,r,s), k (n,p,q)
-	A.ptr = (const float*)x;
+	A.ptr = x;
 	A.rd12 = make_fastdiv(RS); A.rd2 = make_fastdiv(g.S);
 	A.kd12 = make_fastdiv(PQ); A.kd2 = make_fastdiv(g.Q);
 	A.rs0 = HW; A.ks0 = g.C * HW;
@@ -472,7 +502,7 @@ int pz_conv2d_wgrad(int dtype, const pz_conv2d_desc* d, const void* x, const voi
 	A.plane = PQ;
 
 	Operand& B = p.B;   // dy: rows ko, k (n, pq)
-	B.ptr = (const float*)dy;
+	B.ptr = dy;
 	B.rd12 = make_fastdiv(1); B.rd2 = make_fastdiv(0);
 	B.kd12 = make_fastdiv(PQ); B.kd2 = make_fastdiv(0);
 	B.rs0 = PQ; B.ks0 = g.K * PQ;
@@ -487,8 +517,9 @@ int pz_conv2d_wgrad(int dtype, const pz_conv2d_desc* d, const void* x, const voi
 	B.plane = PQ;
 
 	Epilogue& E = p.E;
-	E.out = (float*)dw;
+	E.out = dw;
 	E.bias = nullptr;
+	E.out_kind = out_kind_of(dtype);
 	E.md12 = make_fastdiv(0); E.md2 = make_fastdiv(0);
 	E.ms0 = 0; E.ms1 = 0; E.ms2 = 1;
 	E.ncs = g.Cg * RS;
@@ -498,33 +529,60 @@ int pz_conv2d_wgrad(int dtype, const pz_conv2d_desc* d, const void* x, const voi
 	E.group_stride = (long long)g.Kg * g.Cg * RS;
 	E.bias_group_stride = 0;
 
-	p.kblocks = fast ? g.N * kbpi : (int)pz_cdiv(A.kdim, BK);
+	PZ_REQUIRE(fast || !h16, "conv2d wgrad: tensor too large for the 16-bit path");
+	p.kblocks = fast ? g.N * kbpi : (int)pz_cdiv(A.kdim, bke);
 	const int bn = g.Kg > 64 ? 128 : 64;        // the x operand is re-read once per column tile: keep those few
 	set_splits(p, pz_cdiv(E.M, BM) * pz_cdiv(E.N, bn) * g.G, 8);
 	E.atomic = p.splits > 1;
-	if (E.atomic) {
-		st = prescale((float*)dw, (long long)g.K * g.Cg * RS, beta, stream);
+	set_alg(p, g, dtype);
+	const long long wcount = (long long)g.K * g.Cg * RS;
+	float* acc = nullptr;
+	if (E.atomic && h16) {
+		// split-K with 16-bit storage: red.add into an fp32 scratch, then dw = beta*dw + acc
+		acc = (float*)pz_scratch((size_t)wcount * sizeof(float));
+		if (!acc) { pz_set_error(PZ_ERR_MEMORY, "conv2d wgrad: cannot allocate the split-K accumulator"); return PZ_ERR_MEMORY; }
+		st = pz_memset8(acc, 0, (size_t)wcount * 4, stream);
+		if (st != PZ_OK) return st;
+		E.out = acc;
+		E.out_kind = OUT_F32;
+		E.beta = 0.0f;
+	} else if (E.atomic) {
+		st = prescale((float*)dw, wcount, beta, stream);
 		if (st != PZ_OK) return st;
 	}
-	set_alg(p, g);
-	if (!fast) return launch(p, bn, MODE_K_GENERAL, MODE_K_DENSE, false, g.G, nullptr, pz_stream(stream));
-	return launch(p, bn, dense_x ? MODE_K_POS_DENSE : MODE_K_POS_TAP, MODE_K_POS_DENSE, !dense_x && RS > 31, g.G, nullptr, pz_stream(stream));
+	if (!fast) st = launch(p, dtype, bn, MODE_K_GENERAL, MODE_K_DENSE, false, g.G, nullptr, pz_stream(stream));
+	else st = launch(p, dtype, bn, dense_x ? MODE_K_POS_DENSE : MODE_K_POS_TAP, MODE_K_POS_DENSE, !dense_x && RS > 31, g.G, nullptr, pz_stream(stream));
+	if (st != PZ_OK || !acc) return st;
+	return finalize16(dtype, dw, wcount, acc, 1, wcount, beta, pz_stream(stream));
 }
 
 int pz_bias_grad(int dtype, const void* t, void* db, int64_t N, int64_t C, int64_t S, float alpha, float beta, void* stream)
 {
-	PZ_REQUIRE(dtype == PZ_F32, "bias_grad: only float32 is implemented (got dtype %d)", dtype);
+	PZ_REQUIRE(dtype == PZ_F32 || dtype == PZ_F16 || dtype == PZ_BF16, "bias_grad: unsupported dtype %d", dtype);
 	if (C <= 0) return PZ_OK;
-	int st = prescale((float*)db, C, beta, stream);
+	const bool h16 = dtype != PZ_F32;
+	float* acc = (float*)db;
+	int st;
+	if (h16) {
+		// 16-bit bias gradient: reduce into an fp32 scratch, then db = beta*db + acc
+		acc = (float*)pz_scratch((size_t)C * sizeof(float));
+		if (!acc) { pz_set_error(PZ_ERR_MEMORY, "bias_grad: cannot allocate the accumulator"); return PZ_ERR_MEMORY; }
+		st = pz_memset8(acc, 0, (size_t)C * 4, stream);
+	} else
+		st = prescale(acc, C, beta, stream);
 	if (st != PZ_OK) return st;
-	if (N <= 0 || S <= 0) return PZ_OK;
-	int nsplit = (int)(pz_cdiv(4ll * pz_num_sms(), C));
-	if (nsplit > N) nsplit = (int)N;
-	if (nsplit < 1) nsplit = 1;
-	dim3 grid((unsigned)C, (unsigned)nsplit);
-	bias_grad_kernel<256><<<grid, 256, 0, pz_stream(stream)>>>((const float*)t, (float*)db, N, C, S, alpha, nsplit);
-	pz_count_launch(1);
-	PZ_LAUNCH_CHECK();
+	if (N > 0 && S > 0) {
+		int nsplit = (int)(pz_cdiv(4ll * pz_num_sms(), C));
+		if (nsplit > N) nsplit = (int)N;
+		if (nsplit < 1) nsplit = 1;
+		dim3 grid((unsigned)C, (unsigned)nsplit);
+		if (dtype == PZ_F32) bias_grad_kernel<256, float><<<grid, 256, 0, pz_stream(stream)>>>((const float*)t, acc, N, C, S, alpha, nsplit);
+		else if (dtype == PZ_F16) bias_grad_kernel<256, __half><<<grid, 256, 0, pz_stream(stream)>>>((const __half*)t, acc, N, C, S, alpha, nsplit);
+		else bias_grad_kernel<256, __nv_bfloat16><<<grid, 256, 0, pz_stream(stream)>>>((const __nv_bfloat16*)t, acc, N, C, S, alpha, nsplit);
+		pz_count_launch(1);
+		PZ_LAUNCH_CHECK();
+	}
+	if (h16) return finalize16(dtype, db, C, acc, 1, C, beta, pz_stream(stream));
 	return PZ_OK;
 }
 

@@ -34,6 +34,7 @@
 #include "pz_common.h"
 
 #include <cuda.h>
+#include <type_traits>
 
 namespace pzumma {
 
@@ -83,7 +84,7 @@ enum { MODE_K_GENERAL = 0, MODE_K_SIMPLE = 1, MODE_MN_GENERAL = 2, MODE_MN_SIMPL
 	   MODE_K_DENSE = 6, MODE_TMA = 7, MODE_MN_CHAN = 8, MODE_K_POS_TAP = 9, MODE_K_POS_DENSE = 10 };
 
 struct Operand {
-	const float* ptr;
+	const void* ptr;             // float or 16-bit (half / bfloat16) elements; all strides below are in ELEMENTS
 	FastDiv rd12, rd2, kd12, kd2;
 	int rs0, ks0;
 	int ah, bh, ch, aw, bw, cw;
@@ -98,9 +99,12 @@ struct Operand {
 	int chans, plane;
 };
 
+enum { OUT_F32 = 0, OUT_F16 = 1, OUT_BF16 = 2 };
+
 struct Epilogue {
-	float* out;
-	const float* bias;
+	void* out;
+	const void* bias;
+	int out_kind;                // element type of out / bias (OUT_*); red.add (split-K, col2im) needs OUT_F32
 	FastDiv md12, md2;
 	int ms0, ms1, ms2;           // row m -> m0*ms0 + m1*ms1 + m2*ms2
 	int ncs;                     // column n -> n*ncs
@@ -125,6 +129,7 @@ struct GemmParams {
 	int kb_per_split;
 	int tiles_m, tiles_n, groups; // tile grid; total work units = tiles_m * tiles_n * groups * splits
 	int tma_rows_per_group;      // MODE_TMA: row offset of group g in the prepared filter = g * tma_rows_per_group
+	int ab_bf16;                 // 16-bit operands: 0 = half, 1 = bfloat16 (selects the tcgen05 input format)
 	double alg_flops, alg_bytes; // host-side bookkeeping for the profiler (algorithmic work of this launch)
 };
 
@@ -230,6 +235,21 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr)
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int m, int n)
 {
 	return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// kind::f16 (half or bfloat16 inputs, fp32 accumulate, both K-major): a_format / b_format 0 = f16, 1 = bf16
+__host__ __device__ constexpr uint32_t make_idesc_f16(int m, int n, int bf16)
+{
+	return (1u << 4) | ((uint32_t)bf16 << 7) | ((uint32_t)bf16 << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
+{
+	asm volatile(
+		"{\n\t.reg .pred p;\n\t"
+		"setp.ne.b32 p, %4, 0;\n\t"
+		"tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+		::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+		: "memory");
 }
 
 // ------------------------------------------------------------------------------------------ operand producers
@@ -748,28 +768,312 @@ struct KPosTapProducer {
 	}
 };
 
+// ------------------------------------------------------------------------------------------ 16-bit producers
+// half / bfloat16 operands: a k-block is 64 elements (one 128-byte swizzle row), a 16-byte chunk 8 elements.  Values travel
+// through the register ring as packed pairs (bit patterns held in `float` registers, never touched by arithmetic) and are
+// stored unchanged: the tensor core reads 16-bit inputs exactly.
+constexpr int BK16 = 64;
+__device__ __forceinline__ uint32_t ldg16(const uint16_t* p) { return (uint32_t)__ldg(p); }
+__device__ __forceinline__ float pack16(uint32_t lo, uint32_t hi) { return __uint_as_float(lo | (hi << 16)); }
+
+template <bool CDIV>
+__device__ __forceinline__ uint32_t fetch16(const Operand& op, const uint16_t* __restrict__ base, const RowInfo& ri, const KInfo& ki)
+{
+	int hh = ri.hr + ki.hk;
+	int ww = ri.wr + ki.wk;
+	bool ok = true;
+	if (CDIV) {
+		ok = (hh % op.cdh == 0) && (ww % op.cdw == 0);
+		hh /= op.cdh;
+		ww /= op.cdw;
+	}
+	ok = ok && ((unsigned)hh < (unsigned)op.H) && ((unsigned)ww < (unsigned)op.W);
+	const int off = ri.rbase + ki.kbase + hh * op.Wd + ww;
+	return ok ? ldg16(base + off) : 0u;
+}
+
+// general MN-contiguous producer (any geometry; the slow path, e.g. a first layer with 3 input channels)
+template <int ROWS, bool CDIV>
+struct MnProducer16 {
+	static constexpr int NCH = 8 * ROWS / NPROD;
+	static constexpr int CSTEP = NPROD / ROWS;
+	static constexpr int NV = NCH * 4;
+	RowInfo ri;
+	int row_local, chunk0;
+
+	__device__ __forceinline__ void init(const Operand& op, int tile_row0, int warp, int lane, uint32_t)
+	{
+		const int t = warp * 32 + lane;
+		row_local = t % ROWS;
+		chunk0 = (warp * 32) / ROWS;
+		ri = make_rowinfo(op, tile_row0 + row_local);
+	}
+	__device__ __forceinline__ void load(const Operand& op, const uint16_t* __restrict__ base, int kb, float (&v)[NV])
+	{
+		#pragma unroll
+		for (int i = 0; i < NCH; i++) {
+			const int kc = kb * BK16 + (chunk0 + i * CSTEP) * 8;
+			#pragma unroll
+			for (int w = 0; w < 4; w++) {
+				const KInfo k0 = make_kinfo(op, kc + 2 * w), k1 = make_kinfo(op, kc + 2 * w + 1);
+				v[i * 4 + w] = pack16(fetch16<CDIV>(op, base, ri, k0), fetch16<CDIV>(op, base, ri, k1));
+			}
+		}
+	}
+	__device__ __forceinline__ void store(uint32_t tile, const float (&v)[NV])
+	{
+		#pragma unroll
+		for (int i = 0; i < NCH; i++) {
+			const int chunk = chunk0 + i * CSTEP;
+			const uint32_t addr = tile + row_local * 128 + ((chunk ^ (row_local & 7)) << 4);
+			sts128(addr, __float_as_uint(v[i * 4]), __float_as_uint(v[i * 4 + 1]), __float_as_uint(v[i * 4 + 2]), __float_as_uint(v[i * 4 + 3]));
+		}
+	}
+};
+
+// MnChanProducer for 16-bit elements: k-block kb = tap * cblocks + cb covers channels cb*64 .. cb*64+63 of one tap
+template <int ROWS, bool WIDE>
+struct MnChanProducer16 {
+	using TM = TapMask<WIDE>;
+	static constexpr int NCH = 8 * ROWS / NPROD;
+	static constexpr int CSTEP = NPROD / ROWS;
+	static constexpr int NV = NCH * 4;
+	TM mask;
+	int poff, row_local, chunk0;
+
+	__device__ __forceinline__ void init(const Operand& op, int tile_row0, int warp, int lane, uint32_t)
+	{
+		const int t = warp * 32 + lane;
+		row_local = t % ROWS;
+		chunk0 = (warp * 32) / ROWS;
+		const int row = tile_row0 + row_local;
+		mask.clear();
+		int r0, r1, r2;
+		split3((uint32_t)(row < op.rows ? row : 0), op.rd12, op.rd2, r0, r1, r2);
+		const int hr = r1 * op.ah + op.ch, wr = r2 * op.aw + op.cw;
+		poff = r0 * op.rs0 + hr * op.Wd + wr;
+		if (row < op.rows) {
+			for (int r = 0; r < op.R; r++) {
+				const bool okh = (unsigned)(hr + r * op.bh) < (unsigned)op.H;
+				for (int s = 0; s < op.S; s++)
+					if (okh && (unsigned)(wr + s * op.bw) < (unsigned)op.W) mask.set((int)TM::TOP - (r * op.S + s));
+			}
+		}
+	}
+	__device__ __forceinline__ void load(const Operand& op, const uint16_t* __restrict__ base, int kb, float (&v)[NV])
+	{
+		const uint32_t t = fdiv((uint32_t)kb, op.kbdiv);
+		const uint32_t cb = (uint32_t)kb - t * op.kbdiv.d;
+		const uint32_t r = fdiv(t, op.kd2);
+		const uint32_t sx = t - r * op.kd2.d;
+		const int tapoff = (int)r * op.bh * op.Wd + (int)sx * op.bw;
+		const bool ok = mask.test(t);
+		const int c0 = (int)cb * BK16 + chunk0 * 8;
+		const int cleft = op.chans - c0;
+		const uint16_t* __restrict__ ptr = base + ((long long)c0 * op.ks0 + (poff + tapoff));
+		#pragma unroll
+		for (int i = 0; i < NCH; i++) {
+			#pragma unroll
+			for (int w = 0; w < 4; w++) {
+				const int j = i * CSTEP * 8 + 2 * w;
+				const uint32_t lo = (ok && j < cleft) ? ldg16(ptr + (size_t)((unsigned)j * (unsigned)op.ks0)) : 0u;
+				const uint32_t hi = (ok && j + 1 < cleft) ? ldg16(ptr + (size_t)((unsigned)(j + 1) * (unsigned)op.ks0)) : 0u;
+				v[i * 4 + w] = pack16(lo, hi);
+			}
+		}
+	}
+	__device__ __forceinline__ void store(uint32_t tile, const float (&v)[NV])
+	{
+		#pragma unroll
+		for (int i = 0; i < NCH; i++) {
+			const int chunk = chunk0 + i * CSTEP;
+			const uint32_t addr = tile + row_local * 128 + ((chunk ^ (row_local & 7)) << 4);
+			sts128(addr, __float_as_uint(v[i * 4]), __float_as_uint(v[i * 4 + 1]), __float_as_uint(v[i * 4 + 2]), __float_as_uint(v[i * 4 + 3]));
+		}
+	}
+};
+
+// K-contiguous 16-bit producers: lane l owns k = 2l, 2l+1 of the 64-element k-block -- the same 4 bytes of the swizzled row that
+// lane l writes for fp32 operands, so the store code is unchanged.
+template <int ROWS>
+struct KDenseProducer16 {
+	static constexpr int NR = ROWS / NPROD_WARPS;
+	static constexpr int NV = NR;
+	int warp, lane, nvalid;
+	long long rowoff0, step;
+
+	__device__ __forceinline__ void init(const Operand& op, int tile_row0, int warp_, int lane_, uint32_t)
+	{
+		warp = warp_;
+		lane = lane_;
+		const int row0 = tile_row0 + warp_;
+		rowoff0 = (long long)row0 * op.rs0;
+		step = (long long)NPROD_WARPS * op.rs0;
+		const int left = op.rows - row0;
+		nvalid = left <= 0 ? 0 : min(NR, (left + NPROD_WARPS - 1) / NPROD_WARPS);
+	}
+	__device__ __forceinline__ void load(const Operand& op, const uint16_t* __restrict__ base, int kb, float (&v)[NV])
+	{
+		const int k = kb * BK16 + 2 * lane;
+		int koff0 = k, koff1 = k + 1;
+		if (op.kd12.d > 1) {
+			const uint32_t q0 = fdiv((uint32_t)k, op.kd12), q1 = fdiv((uint32_t)(k + 1), op.kd12);
+			koff0 = (int)q0 * op.ks0 + (int)((uint32_t)k - q0 * op.kd12.d);
+			koff1 = (int)q1 * op.ks0 + (int)((uint32_t)(k + 1) - q1 * op.kd12.d);
+		}
+		const int n0 = k < op.kdim ? nvalid : 0, n1 = k + 1 < op.kdim ? nvalid : 0;
+		const uint16_t* __restrict__ p = base + rowoff0;
+		#pragma unroll
+		for (int i = 0; i < NR; i++) {
+			v[i] = pack16(i < n0 ? ldg16(p + koff0) : 0u, i < n1 ? ldg16(p + koff1) : 0u);
+			p += step;
+		}
+	}
+	__device__ __forceinline__ void store(uint32_t tile, const float (&v)[NV])
+	{
+		const uint32_t col = ((((uint32_t)lane >> 2) ^ ((uint32_t)warp & 7)) << 4) | (((uint32_t)lane & 3) << 2);
+		#pragma unroll
+		for (int i = 0; i < NR; i++) sts32(tile + (warp + i * NPROD_WARPS) * 128 + col, __float_as_uint(v[i]));
+	}
+};
+
+template <int ROWS>
+struct KPosDenseProducer16 {
+	static constexpr int NR = ROWS / NPROD_WARPS;
+	static constexpr int NV = NR;
+	int warp, lane, nvalid;
+	long long rowoff0, step;
+
+	__device__ __forceinline__ void init(const Operand& op, int tile_row0, int warp_, int lane_, uint32_t)
+	{
+		warp = warp_;
+		lane = lane_;
+		const int row0 = tile_row0 + warp_;
+		rowoff0 = (long long)row0 * op.rs0;
+		step = (long long)NPROD_WARPS * op.rs0;
+		const int left = op.rows - row0;
+		nvalid = left <= 0 ? 0 : min(NR, (left + NPROD_WARPS - 1) / NPROD_WARPS);
+	}
+	__device__ __forceinline__ void load(const Operand& op, const uint16_t* __restrict__ base, int kb, float (&v)[NV])
+	{
+		const uint32_t n = fdiv((uint32_t)kb, op.kbdiv);
+		const int pos = (int)((uint32_t)kb - n * op.kbdiv.d) * BK16 + 2 * lane;
+		const int n0 = pos < op.plane ? nvalid : 0, n1 = pos + 1 < op.plane ? nvalid : 0;
+		const uint16_t* __restrict__ p = base + (rowoff0 + (long long)n * op.ks0 + pos);
+		#pragma unroll
+		for (int i = 0; i < NR; i++) {
+			v[i] = pack16(i < n0 ? ldg16(p) : 0u, i < n1 ? ldg16(p + 1) : 0u);
+			p += step;
+		}
+	}
+	__device__ __forceinline__ void store(uint32_t tile, const float (&v)[NV])
+	{
+		const uint32_t col = ((((uint32_t)lane >> 2) ^ ((uint32_t)warp & 7)) << 4) | (((uint32_t)lane & 3) << 2);
+		#pragma unroll
+		for (int i = 0; i < NR; i++) sts32(tile + (warp + i * NPROD_WARPS) * 128 + col, __float_as_uint(v[i]));
+	}
+};
+
+template <int ROWS, bool WIDE>
+struct KPosTapProducer16 {
+	using TM = TapMask<WIDE>;
+	static constexpr int NR = ROWS / NPROD_WARPS;
+	static constexpr int NV = NR;
+	int warp, lane;
+	uint32_t table;
+
+	__device__ __forceinline__ void init(const Operand& op, int tile_row0, int warp_, int lane_, uint32_t table_)
+	{
+		warp = warp_;
+		lane = lane_;
+		table = table_;
+		const int t = warp * 32 + lane;
+		if (t < ROWS) {
+			const int row = tile_row0 + t;
+			uint32_t entry = 0u;
+			if (row < op.rows) {
+				const uint32_t c = fdiv((uint32_t)row, op.rd12);
+				const uint32_t tp = (uint32_t)row - c * op.rd12.d;
+				const uint32_t r = fdiv(tp, op.rd2);
+				const uint32_t s = tp - r * op.rd2.d;
+				const int roff = (int)c * op.rs0 + (int)r * op.ah * op.Wd + (int)s * op.aw - tap_min(op.R, op.S, op.ah * op.Wd, op.aw);
+				entry = ((uint32_t)roff << TM::SH) | (TM::TOP - tp);
+			}
+			sts32(table + t * 4, entry);
+		}
+	}
+	__device__ __forceinline__ void position(const Operand& op, uint32_t n, int pos, TM& mask, const uint16_t* __restrict__ base,
+											 const uint16_t* __restrict__& sb)
+	{
+		const bool pvalid = pos < op.plane;
+		const uint32_t pp = fdiv((uint32_t)(pvalid ? pos : 0), op.kd2);
+		const int qq = (pvalid ? pos : 0) - (int)pp * (int)op.kd2.d;
+		const int hk = (int)pp * op.bh + op.ch, wk = qq * op.bw + op.cw;
+		mask.clear();
+		if (pvalid) {
+			TM wm;
+			wm.clear();
+			for (int s = 0; s < op.S; s++)
+				if ((unsigned)(wk + s * op.aw) < (unsigned)op.W) wm.set(s);
+			for (int r = 0; r < op.R; r++)
+				if ((unsigned)(hk + r * op.ah) < (unsigned)op.H) mask.m |= wm.m << (r * op.S);
+		}
+		sb = base + ((long long)n * op.ks0 + hk * op.Wd + wk + tap_min(op.R, op.S, op.ah * op.Wd, op.aw));
+	}
+	__device__ __forceinline__ void load(const Operand& op, const uint16_t* __restrict__ base, int kb, float (&v)[NV])
+	{
+		const uint32_t n = fdiv((uint32_t)kb, op.kbdiv);
+		const int pos = (int)((uint32_t)kb - n * op.kbdiv.d) * BK16 + 2 * lane;
+		TM m0, m1;
+		const uint16_t* __restrict__ sb0;
+		const uint16_t* __restrict__ sb1;
+		position(op, n, pos, m0, base, sb0);
+		position(op, n, pos + 1, m1, base, sb1);
+		#pragma unroll
+		for (int i = 0; i < NR; i++) {
+			uint32_t ent;
+			asm volatile("ld.shared.b32 %0, [%1];" : "=r"(ent) : "r"(table + (warp + i * NPROD_WARPS) * 4));
+			const uint32_t off = ent >> TM::SH;
+			v[i] = pack16(m0.test(ent) ? ldg16(sb0 + off) : 0u, m1.test(ent) ? ldg16(sb1 + off) : 0u);
+		}
+	}
+	__device__ __forceinline__ void store(uint32_t tile, const float (&v)[NV])
+	{
+		const uint32_t col = ((((uint32_t)lane >> 2) ^ ((uint32_t)warp & 7)) << 4) | (((uint32_t)lane & 3) << 2);
+		#pragma unroll
+		for (int i = 0; i < NR; i++) sts32(tile + (warp + i * NPROD_WARPS) * 128 + col, __float_as_uint(v[i]));
+	}
+};
+
 // filter operand fetched by TMA from the prepared (tf32-rounded, zero-padded, K-major) copy: no per-thread state
 template <int ROWS>
 struct TmaProducer {
 	static constexpr int NV = 1;
 	__device__ __forceinline__ void init(const Operand&, int, int, int, uint32_t) {}
-	__device__ __forceinline__ void load(const Operand&, const float* __restrict__, int, float (&)[NV]) {}
+	template <typename P>
+	__device__ __forceinline__ void load(const Operand&, const P* __restrict__, int, float (&)[NV]) {}
 	__device__ __forceinline__ void store(uint32_t, const float (&)[NV]) {}
 };
 
-template <int ROWS, int MODE, bool CDIV> struct ProducerSel;
-template <int ROWS, bool CDIV> struct ProducerSel<ROWS, MODE_K_GENERAL, CDIV> { using type = KProducer<ROWS, false>; };
-template <int ROWS, bool CDIV> struct ProducerSel<ROWS, MODE_K_SIMPLE, CDIV> { using type = KProducer<ROWS, true>; };
-template <int ROWS, bool CDIV> struct ProducerSel<ROWS, MODE_MN_GENERAL, CDIV> { using type = MnProducer<ROWS, false, CDIV>; };
-template <int ROWS, bool CDIV> struct ProducerSel<ROWS, MODE_MN_SIMPLE, CDIV> { using type = MnProducer<ROWS, true, false>; };
+template <int ROWS, int MODE, bool CDIV, bool H16> struct ProducerSel;
+template <int ROWS, bool CDIV> struct ProducerSel<ROWS, MODE_K_GENERAL, CDIV, false> { using type = KProducer<ROWS, false>; };
+template <int ROWS, bool CDIV> struct ProducerSel<ROWS, MODE_K_SIMPLE, CDIV, false> { using type = KProducer<ROWS, true>; };
+template <int ROWS, bool CDIV> struct ProducerSel<ROWS, MODE_MN_GENERAL, CDIV, false> { using type = MnProducer<ROWS, false, CDIV>; };
+template <int ROWS, bool CDIV> struct ProducerSel<ROWS, MODE_MN_SIMPLE, CDIV, false> { using type = MnProducer<ROWS, true, false>; };
 // for the fast producers the CDIV slot selects the 64-bit tap mask (more than 32 taps, e.g. a 7x7 filter)
-template <int ROWS, bool WIDE> struct ProducerSel<ROWS, MODE_MN_TAP, WIDE> { using type = MnTapProducer<ROWS, WIDE>; };
-template <int ROWS, bool WIDE> struct ProducerSel<ROWS, MODE_K_TAP, WIDE> { using type = KTapProducer<ROWS, WIDE>; };
-template <int ROWS, bool WIDE> struct ProducerSel<ROWS, MODE_K_DENSE, WIDE> { using type = KDenseProducer<ROWS>; };
-template <int ROWS, bool WIDE> struct ProducerSel<ROWS, MODE_TMA, WIDE> { using type = TmaProducer<ROWS>; };
-template <int ROWS, bool WIDE> struct ProducerSel<ROWS, MODE_MN_CHAN, WIDE> { using type = MnChanProducer<ROWS, WIDE>; };
-template <int ROWS, bool WIDE> struct ProducerSel<ROWS, MODE_K_POS_TAP, WIDE> { using type = KPosTapProducer<ROWS, WIDE>; };
-template <int ROWS, bool WIDE> struct ProducerSel<ROWS, MODE_K_POS_DENSE, WIDE> { using type = KPosDenseProducer<ROWS>; };
+template <int ROWS, bool WIDE> struct ProducerSel<ROWS, MODE_MN_TAP, WIDE, false> { using type = MnTapProducer<ROWS, WIDE>; };
+template <int ROWS, bool WIDE> struct ProducerSel<ROWS, MODE_K_TAP, WIDE, false> { using type = KTapProducer<ROWS, WIDE>; };
+template <int ROWS, bool WIDE> struct ProducerSel<ROWS, MODE_K_DENSE, WIDE, false> { using type = KDenseProducer<ROWS>; };
+template <int ROWS, bool WIDE, bool H16> struct ProducerSel<ROWS, MODE_TMA, WIDE, H16> { using type = TmaProducer<ROWS>; };
+template <int ROWS, bool WIDE> struct ProducerSel<ROWS, MODE_MN_CHAN, WIDE, false> { using type = MnChanProducer<ROWS, WIDE>; };
+template <int ROWS, bool WIDE> struct ProducerSel<ROWS, MODE_K_POS_TAP, WIDE, false> { using type = KPosTapProducer<ROWS, WIDE>; };
+template <int ROWS, bool WIDE> struct ProducerSel<ROWS, MODE_K_POS_DENSE, WIDE, false> { using type = KPosDenseProducer<ROWS>; };
+// half / bfloat16 operands
+template <int ROWS, bool CDIV> struct ProducerSel<ROWS, MODE_MN_GENERAL, CDIV, true> { using type = MnProducer16<ROWS, CDIV>; };
+template <int ROWS, bool WIDE> struct ProducerSel<ROWS, MODE_MN_CHAN, WIDE, true> { using type = MnChanProducer16<ROWS, WIDE>; };
+template <int ROWS, bool WIDE> struct ProducerSel<ROWS, MODE_K_DENSE, WIDE, true> { using type = KDenseProducer16<ROWS>; };
+template <int ROWS, bool WIDE> struct ProducerSel<ROWS, MODE_K_POS_TAP, WIDE, true> { using type = KPosTapProducer16<ROWS, WIDE>; };
+template <int ROWS, bool WIDE> struct ProducerSel<ROWS, MODE_K_POS_DENSE, WIDE, true> { using type = KPosDenseProducer16<ROWS>; };
 
 template <int BN> struct Cfg {
 	static constexpr int STAGE_BYTES = (BM + BN) * 128;
@@ -815,16 +1119,34 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, int 
 		: "memory");
 }
 
+// output element access by kind (OUT_F32 / OUT_F16 / OUT_BF16); `idx` in elements
+__device__ __forceinline__ void out_store(void* base, size_t idx, float r, int kind)
+{
+	if (kind == OUT_F32) ((float*)base)[idx] = r;
+	else if (kind == OUT_F16) ((__half*)base)[idx] = __float2half_rn(r);
+	else ((__nv_bfloat16*)base)[idx] = __float2bfloat16_rn(r);
+}
+__device__ __forceinline__ float out_load(const void* base, size_t idx, int kind)
+{
+	if (kind == OUT_F32) return ((const float*)base)[idx];
+	if (kind == OUT_F16) return __half2float(((const __half*)base)[idx]);
+	return __bfloat162float(((const __nv_bfloat16*)base)[idx]);
+}
+
 // one 32-lane x 16-column chunk of the accumulator -> global memory.  `fast`: 1 = store alpha*acc + bias[m], 2 = store
-// alpha*acc + bias[n], 3 = red.add alpha*acc, 0 = generic (beta, bias with split-K, ...).  Lanes are the contiguous output
-// dimension, so every store instruction of a warp writes 128 consecutive bytes.
-__device__ __forceinline__ void epilogue_chunk(const Epilogue& E, const uint32_t (&v)[EPI_COLS], float* outp, const float* biasp, float bias_m,
+// alpha*acc + bias[n], 3 = red.add alpha*acc, 4 = col2im scatter, 0 = generic (beta, bias with split-K, 16-bit outputs, ...).
+// Lanes are the contiguous output dimension, so every store instruction of a warp writes consecutive addresses.
+// `outp` points at the row's first element (element offsets are scaled by the element size here).
+__device__ __forceinline__ void epilogue_chunk(const Epilogue& E, const uint32_t (&v)[EPI_COLS], char* outp, const void* biasp, float bias_m,
 											   bool mvalid, bool addbias, int n0, int fast, int hb, int wb)
 {
 	if (!mvalid) return;
+	const unsigned ncs = (unsigned)E.ncs;
+	const float alpha = E.alpha;
 	if (fast == 4) {
 		// col2im scatter: the column decode is warp-uniform, the bounds test and the address are per lane
 		const int HW = E.c2i_H * E.c2i_W;
+		float* o = (float*)outp;
 		#pragma unroll
 		for (int j = 0; j < EPI_COLS; j++) {
 			const int col = n0 + j;
@@ -835,20 +1157,18 @@ __device__ __forceinline__ void epilogue_chunk(const Epilogue& E, const uint32_t
 				const uint32_t sx = t - r * E.c2i_s.d;
 				const int h = hb + (int)r * E.c2i_dh, w = wb + (int)sx * E.c2i_dw;
 				if ((unsigned)h < (unsigned)E.c2i_H && (unsigned)w < (unsigned)E.c2i_W)
-					atomicAdd(outp + ((size_t)c * HW + h * E.c2i_W + w), E.alpha * __uint_as_float(v[j]));
+					atomicAdd(o + ((size_t)c * HW + h * E.c2i_W + w), alpha * __uint_as_float(v[j]));
 			}
 		}
 		return;
 	}
-	float* dst = outp + (size_t)n0 * (unsigned)E.ncs;
-	const unsigned ncs = (unsigned)E.ncs;
-	const float alpha = E.alpha;
 	if (fast != 0 && n0 + EPI_COLS <= E.N) {
+		float* dst = (float*)outp + (size_t)n0 * ncs;
 		if (fast == 1) {
 			#pragma unroll
 			for (int j = 0; j < EPI_COLS; j++) dst[(size_t)j * ncs] = fmaf(alpha, __uint_as_float(v[j]), bias_m);
 		} else if (fast == 2) {
-			const float* bn = biasp + n0;
+			const float* bn = (const float*)biasp + n0;
 			#pragma unroll
 			for (int j = 0; j < EPI_COLS; j++) dst[(size_t)j * ncs] = fmaf(alpha, __uint_as_float(v[j]), __ldg(bn + j));
 		} else {
@@ -857,30 +1177,46 @@ __device__ __forceinline__ void epilogue_chunk(const Epilogue& E, const uint32_t
 		}
 		return;
 	}
+	const int kind = E.out_kind;
+	if (kind != OUT_F32 && !E.atomic && E.beta == 0.0f && n0 + EPI_COLS <= E.N) {
+		// 16-bit store path (fprop / dgrad of half / bfloat16 tensors)
+		#pragma unroll
+		for (int j = 0; j < EPI_COLS; j++) {
+			float r = alpha * __uint_as_float(v[j]);
+			if (E.bias_mode == 1) r += out_load(biasp, (size_t)(n0 + j), kind);
+			else r += bias_m;
+			const size_t idx = (size_t)(n0 + j) * ncs;
+			if (kind == OUT_F16) ((__half*)outp)[idx] = __float2half_rn(r);
+			else ((__nv_bfloat16*)outp)[idx] = __float2bfloat16_rn(r);
+		}
+		return;
+	}
 	#pragma unroll
 	for (int j = 0; j < EPI_COLS; j++) {
 		if (n0 + j < E.N) {
 			float r = alpha * __uint_as_float(v[j]);
 			if (addbias) {
-				if (E.bias_mode == 1) r += biasp[n0 + j];
+				if (E.bias_mode == 1) r += out_load(biasp, (size_t)(n0 + j), kind);
 				else if (E.bias_mode == 2) r += bias_m;
 			}
-			float* d = dst + (size_t)j * ncs;
+			const size_t idx = (size_t)(n0 + j) * ncs;
 			if (E.atomic) {
-				atomicAdd(d, r);                             // out was pre-scaled by beta on the host side
+				atomicAdd((float*)outp + idx, r);            // out (fp32) was pre-scaled by beta on the host side
 			} else {
-				if (E.beta != 0.0f) r += E.beta * *d;
-				*d = r;
+				if (E.beta != 0.0f) r += E.beta * out_load(outp, idx, kind);
+				out_store(outp, idx, r, kind);
 			}
 		}
 	}
 }
 
 // ------------------------------------------------------------------------------------------ the kernel
-template <int BN, int AMODE, int BMODE, bool CDIV>
+template <int BN, int AMODE, int BMODE, bool CDIV, bool H16>
 __global__ void __launch_bounds__(NTHREADS, 1) umma_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ CUtensorMap tmapB)
 {
 	using C = Cfg<BN>;
+	using EL = typename std::conditional<H16, uint16_t, float>::type;      // operand element as the producers see it
+	constexpr int BKE = H16 ? BK16 : BK;                                   // elements per k-block (one 128-byte row)
 	constexpr bool B_TMA = BMODE == MODE_TMA;
 	constexpr int PF = B_TMA ? 3 : 2;                        // k-blocks of global loads in flight per producer thread
 	extern __shared__ uint8_t smem_raw[];
@@ -920,8 +1256,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) umma_gemm_kernel(const __grid_con
 
 	if (warp < NPROD_WARPS) {
 		// ===================== producers =====================
-		typename ProducerSel<BM, AMODE, CDIV>::type prodA;
-		typename ProducerSel<BN, BMODE, false>::type prodB;
+		typename ProducerSel<BM, AMODE, CDIV, H16>::type prodA;
+		typename ProducerSel<BN, BMODE, false, H16>::type prodB;
 		using PA = decltype(prodA);
 		using PB = decltype(prodB);
 		float va[PF][PA::NV];
@@ -933,8 +1269,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) umma_gemm_kernel(const __grid_con
 		Work lw{};
 		bool lvalid = lwork < total_work;
 		if (lvalid) { lw = decode_work(p, lwork); lkb = lw.kb_begin; }
-		const float* baseA = p.A.ptr;
-		const float* baseB = p.B.ptr;
+		const EL* baseA = (const EL*)p.A.ptr;
+		const EL* baseB = (const EL*)p.B.ptr;
 		int issued = 0, done = 0;
 		int stage = 0;
 		uint32_t phase = 0;
@@ -945,14 +1281,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) umma_gemm_kernel(const __grid_con
 				const uint32_t tset = tables + (uint32_t)(lseq & 1) * C::TABLE_BYTES;
 				prodA.init(p.A, lw.m_tile * BM, warp, lane, tset);
 				prodB.init(p.B, lw.n_tile * BN, warp, lane, tset + BM * 16);
-				baseA = p.A.ptr + (long long)lw.group * p.A.group_stride;
-				baseB = p.B.ptr + (long long)lw.group * p.B.group_stride;
+				baseA = (const EL*)p.A.ptr + (long long)lw.group * p.A.group_stride;
+				baseB = (const EL*)p.B.ptr + (long long)lw.group * p.B.group_stride;
 				named_bar_sync(1, NPROD);
 				lseq++;
 			}
 			prodA.load(p.A, baseA, lkb, a);
 			prodB.load(p.B, baseB, lkb, b);
-			k_elem = lkb * BK;
+			k_elem = lkb * BKE;
 			b_row = lw.group * p.tma_rows_per_group + lw.n_tile * BN;
 			issued++;
 			if (++lkb == lw.kb_end) {
@@ -991,7 +1327,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) umma_gemm_kernel(const __grid_con
 		}
 	} else if (warp == NPROD_WARPS) {
 		// ===================== MMA issuer (one thread) =====================
-		constexpr uint32_t idesc = make_idesc_tf32(BM, BN);
+		const uint32_t idesc = H16 ? make_idesc_f16(BM, BN, p.ab_bf16) : make_idesc_tf32(BM, BN);
 		int stage = 0;
 		uint32_t phase = 0;
 		int as = 0;
@@ -1008,8 +1344,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) umma_gemm_kernel(const __grid_con
 					const uint32_t tileA = smem0 + stage * C::STAGE_BYTES;
 					const uint64_t da = make_smem_desc(tileA), db = make_smem_desc(tileA + BM * 128);
 					#pragma unroll
-					for (int kk = 0; kk < BK / 8; kk++)    // 8 tf32 = 32 bytes per MMA: +2 in the (addr >> 4) field
-						umma_tf32(tmem_d, da + 2 * kk, db + 2 * kk, idesc, (kb > w.kb_begin || kk > 0) ? 1u : 0u);
+					for (int kk = 0; kk < 4; kk++) {       // 8 tf32 / 16 halves = 32 bytes per MMA: +2 in the (addr >> 4) field
+						if (H16) umma_f16(tmem_d, da + 2 * kk, db + 2 * kk, idesc, (kb > w.kb_begin || kk > 0) ? 1u : 0u);
+						else umma_tf32(tmem_d, da + 2 * kk, db + 2 * kk, idesc, (kb > w.kb_begin || kk > 0) ? 1u : 0u);
+					}
 					umma_commit(bar_empty + 8 * stage);
 				}
 				__syncwarp();
@@ -1032,17 +1370,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) umma_gemm_kernel(const __grid_con
 			const bool mvalid = m < E.M;
 			int m0, m1, m2;
 			split3((uint32_t)(mvalid ? m : 0), E.md12, E.md2, m0, m1, m2);
-			float* outp = E.out + (long long)w.group * E.group_stride + ((long long)m0 * E.ms0 + (long long)m1 * E.ms1 + (long long)m2 * E.ms2);
-			const float* biasp = E.bias ? E.bias + (long long)w.group * E.bias_group_stride : nullptr;
+			const int oes = E.out_kind == OUT_F32 ? 4 : 2;       // bytes per output / bias element
+			char* outp = (char*)E.out + ((long long)w.group * E.group_stride + ((long long)m0 * E.ms0 + (long long)m1 * E.ms1 + (long long)m2 * E.ms2)) * oes;
+			const char* biasp = E.bias ? (const char*)E.bias + (long long)w.group * E.bias_group_stride * oes : nullptr;
 			const bool addbias = !E.atomic || w.split == 0;      // with split-K the bias is contributed once
-			const float bias_m = (E.bias_mode == 2 && mvalid && addbias) ? biasp[m] : 0.0f;
+			const float bias_m = (E.bias_mode == 2 && mvalid && addbias) ? out_load(biasp, (size_t)m, E.out_kind) : 0.0f;
 
 			mbar_wait(bar_accfull + 8 * as, aphase);
 			tc_fence_after();
 			const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN) + ((uint32_t)(lg * 32) << 16);
 			const int ncols = min(BN, E.N - w.n_tile * BN);       // valid columns of this tile (> 0)
 			// fast paths (straight-line, 2 - 3 instructions per element): plain store and split-K red.add
-			const int fast = E.c2i ? 4 : (E.atomic ? ((addbias && E.bias_mode) ? 0 : 3) : (E.beta != 0.0f ? 0 : (E.bias_mode == 1 ? 2 : 1)));
+			const int fast = E.c2i ? 4 : (E.out_kind != OUT_F32 ? 0 : (E.atomic ? ((addbias && E.bias_mode) ? 0 : 3) : (E.beta != 0.0f ? 0 : (E.bias_mode == 1 ? 2 : 1))));
 			const int hb = m1 * E.c2i_sh - E.c2i_ph, wb = m2 * E.c2i_sw - E.c2i_pw;
 
 			uint32_t v0[EPI_COLS], v1[EPI_COLS];
@@ -1076,15 +1415,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) umma_gemm_kernel(const __grid_con
 // host-side launcher (defined in pz_gemm.cu).  `bn` = 0 lets the launcher pick the tile width; tmap_src (MODE_TMA only) is
 // the prepared filter: fp32 [tma_rows][tma_kpad], tf32-rounded, zero-padded, 16-byte aligned.
 struct TmaSource {
-	const float* ptr;
+	const void* ptr;
 	long long rows, kpad;
 };
-int launch(GemmParams& p, int bn, int amode, int bmode, bool cdiv, int groups, const TmaSource* tma, cudaStream_t stream);
+// dtype: PZ_F32 (tf32 products), PZ_F16 or PZ_BF16 -- the element type of both operands
+int launch(GemmParams& p, int dtype, int bn, int amode, int bmode, bool cdiv, int groups, const TmaSource* tma, cudaStream_t stream);
+inline int elems_per_kblock(int dtype) { return dtype == PZ_F32 ? BK : BK16; }
+int finalize16(int dtype, void* out, int64_t ldo, const float* acc, int64_t rows, int64_t cols, float beta, cudaStream_t stream);
+inline int out_kind_of(int dtype) { return dtype == PZ_F32 ? OUT_F32 : (dtype == PZ_F16 ? OUT_F16 : OUT_BF16); }
 int pick_bn(int n, long long m_rows, int kblocks, int groups, int max_bn);
 float* scratch(size_t bytes);                   // library-owned, stream-ordered scratch (prepared filters)
 
 // helpers to build operands
-Operand dense_k(const float* ptr, int rows, int kdim, long long ld);     // element (row,k) at ptr[row*ld + k]
-Operand dense_mn(const float* ptr, int rows, int kdim, long long ld);    // element (row,k) at ptr[k*ld + row]
+Operand dense_k(const void* ptr, int rows, int kdim, long long ld);      // element (row,k) at ptr[row*ld + k]
+Operand dense_mn(const void* ptr, int rows, int kdim, long long ld, int bke);   // element (row,k) at ptr[k*ld + row] (MODE_MN_CHAN)
 
 }  // namespace pzumma

@@ -268,7 +268,7 @@ def launchCount():
 	return int(lib.pz_launch_count())
 
 
-PROF_FAMILIES = {"gemm": 0, "bn_fwd": 1, "bn_bwd": 2, "eltwise": 3, "pool": 4, "other": 5}
+PROF_FAMILIES = {"gemm": 0, "bn_fwd": 1, "bn_bwd": 2, "eltwise": 3, "pool": 4, "other": 5, "gemm_hbm": 6}
 
 
 def profileEnable(on):

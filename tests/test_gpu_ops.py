@@ -118,6 +118,87 @@ def test_deconv2d(bnd, case):
 	assert relerr(wgrad.get(), want[0]) < REL_TC and relerr(bgrad.get(), want[1]) < 1e-5
 
 
+# 16-bit storage (the reference has fp16; bf16 is added with the same rules): operands are read exactly by the
+# tensor core (kind::f16), fp32 accumulation, outputs rounded once to the storage type.  Tolerance = a few storage ulps.
+CONV16_CASES = [
+	# N, C, H, W, K, R, S, stride, pad, dil, groups, bias
+	(2, 64, 14, 14, 96, 3, 3, 1, 1, 1, 1, True),       # channel-ordered k, 64-element k-blocks
+	(2, 48, 15, 15, 80, 3, 3, 2, 1, 1, 1, False),      # strided 3x3 (parity classes), ragged channel counts
+	(3, 128, 7, 7, 64, 1, 1, 1, 0, 1, 1, False),       # 1x1
+	(2, 64, 12, 12, 128, 1, 1, 2, 0, 1, 1, False),     # strided 1x1
+	(2, 3, 20, 20, 64, 3, 3, 1, 1, 1, 1, True),        # 3 input channels: general gather for fprop, >= 48 filters for dgrad
+	(2, 96, 9, 9, 64, 3, 3, 1, 1, 1, 2, True),         # groups
+]
+
+
+def _dtypes16():
+	from puzzlelib_b200.driver import bfloat16
+	return [np.dtype(np.float16)] + ([bfloat16] if bfloat16 is not None else [])
+
+
+@pytest.mark.parametrize("case", CONV16_CASES)
+@pytest.mark.parametrize("dtname", ["float16", "bfloat16"])
+def test_conv2d_16bit(bnd, case, dtname):
+	from puzzlelib_b200.driver import bfloat16
+	dt = np.dtype(np.float16) if dtname == "float16" else bfloat16
+	if dt is None:
+		pytest.skip("ml_dtypes.bfloat16 is not available")
+	tol = 4e-3 if dtname == "float16" else 2e-2
+	N, C, H, W, K, R, S, stride, pad, dil, groups, bias = case
+	rng = np.random.RandomState(hash(case) % (2 ** 31))
+	x = rng.randn(N, C, H, W).astype(dt)
+	w = (rng.randn(K, C // groups, R, S) * 0.2).astype(dt)
+	b = rng.randn(K).astype(dt) if bias else None
+	xf, wf = x.astype(np.float64), w.astype(np.float64)
+
+	y = ops.conv2d(xf, wf, b.astype(np.float64) if bias else None, stride, pad, dil, groups)
+	dy = rng.randn(*y.shape).astype(dt)
+	dyf = dy.astype(np.float64)
+
+	dx_, dw_ = G(bnd, x), G(bnd, w)
+	out = bnd.dnn.convNd(dx_, dw_, G(bnd, b) if bias else None, stride, pad, dil, groups, allocator=bnd.memoryPool)
+	assert out.dtype == dt and out.shape == y.shape
+	assert relerr(out.get().astype(np.float64), y) < tol
+
+	dgrad = bnd.dnn.convNdBackwardData(G(bnd, dy), dw_, None, dx_, stride, pad, dil, None, groups, allocator=bnd.memoryPool)
+	assert dgrad.dtype == dt
+	assert relerr(dgrad.get().astype(np.float64), ops.conv2d_bwd_data(dyf, wf, x.shape, None, stride, pad, dil, 0, groups)) < tol
+
+	w0, b0 = rng.randn(*w.shape).astype(dt), rng.randn(K).astype(dt)
+	wgrad, bgrad = G(bnd, w0), G(bnd, b0)
+	bnd.dnn.convNdBackwardParams(dx_, G(bnd, dy), dw_, stride, pad, dil, groups, bias, False, wgrad, bgrad if bias else None, 0.5, 0.25,
+								 allocator=bnd.memoryPool)
+	want = ops.conv2d_bwd_params(xf, dyf, w.shape, stride, pad, dil, groups, True, False, w0.astype(np.float64), b0.astype(np.float64),
+								 0.5, 0.25)
+	assert relerr(wgrad.get().astype(np.float64), want[0]) < tol
+	if bias:
+		assert relerr(bgrad.get().astype(np.float64), want[1]) < tol
+
+
+@pytest.mark.parametrize("case", [(64, 1000, 2048, 0, 0), (128, 96, 300, 0, 1), (70, 130, 64, 1, 0), (33, 17, 4, 0, 0), (16, 4096, 8192, 0, 0)])
+@pytest.mark.parametrize("dtname", ["float16", "bfloat16"])
+def test_gemm_16bit(bnd, case, dtname):
+	from puzzlelib_b200.driver import bfloat16
+	dt = np.dtype(np.float16) if dtname == "float16" else bfloat16
+	if dt is None:
+		pytest.skip("ml_dtypes.bfloat16 is not available")
+	tol = 4e-3 if dtname == "float16" else 2e-2
+	M, N, K, ta, tb = case
+	rng = np.random.RandomState(M * 31 + N)
+	A = (rng.randn(*((K, M) if ta else (M, K))) * 0.3).astype(dt)
+	B = (rng.randn(*((N, K) if tb else (K, N))) * 0.3).astype(dt)
+	C0 = rng.randn(M, N).astype(dt)
+	Af, Bf = A.astype(np.float64), B.astype(np.float64)
+
+	out = bnd.blas.gemm(G(bnd, A), G(bnd, B), None, bool(ta), bool(tb), allocator=bnd.memoryPool)
+	assert out.dtype == dt
+	assert relerr(out.get().astype(np.float64), ops.gemm(Af, Bf, None, ta, tb)) < tol
+
+	acc = G(bnd, C0)
+	bnd.blas.gemm(G(bnd, A), G(bnd, B), acc, bool(ta), bool(tb), 0.5, 0.75)
+	assert relerr(acc.get().astype(np.float64), ops.gemm(Af, Bf, C0.astype(np.float64), ta, tb, 0.5, 0.75)) < tol
+
+
 def test_conv2d_argument_errors(bnd):
 	x = bnd.GPUArray.zeros((2, 4, 8, 8), np.float32)
 	w = bnd.GPUArray.zeros((6, 3, 3, 3), np.float32)
