@@ -168,16 +168,31 @@ def gpuArm(args):
 
 	bnd = backend()
 	np.random.seed(1234)                       # same initial weights on every rank (and broadcast from rank 0 anyway)
-	net = loadResNet(None, "50", initscheme="he")
+	# the headline is ResNet-50 fp32 (BASELINE.json configs[1]); --model / --dtype / --batch time the other configs for profiles/
+	global BATCH, FLOP_PER_IMAGE, METRIC
+	if args.batch:
+		BATCH = args.batch
+	if args.model == "vgg16":
+		from puzzlelib_b200.nets import loadVGG
+		net = loadVGG(None, "16", initscheme="he")
+		FLOP_PER_IMAGE = 92.8e9
+	else:
+		net = loadResNet(None, "50", initscheme="he")
+	dt = np.dtype(np.float32)
+	if args.dtype != "f32":
+		dt = driver.bfloat16 if args.dtype == "bf16" else np.dtype(np.float16)
+		net.calcMode(dt)
+	if args.model != "resnet50" or args.dtype != "f32":
+		METRIC = "%s %s fwd+bwd images/sec" % ({"resnet50": "ResNet-50", "vgg16": "VGG-16"}[args.model], args.dtype)
 	optimizer = MomentumSGD(learnRate=1e-3, momRate=0.9, nodeinfo=node if node.gridsize > 1 else None)
 	optimizer.setupOn(net, useGlobalState=True)
 
 	rng = np.random.RandomState(1234 + node.index)      # every rank draws its own shard of the global batch
-	pinned = driver.PinnedBuffer((BATCH, 3, 224, 224), np.float32)
-	pinned.array[...] = rng.randn(BATCH, 3, 224, 224).astype(np.float32)
+	pinned = driver.PinnedBuffer((BATCH, 3, 224, 224), dt)
+	pinned.array[...] = rng.randn(BATCH, 3, 224, 224).astype(dt)
 	data = M.gpuarray.to_gpu(pinned.array)
-	grad = M.gpuarray.to_gpu((rng.randn(BATCH, 1000) * 1e-3).astype(np.float32))
-	hostOut = driver.PinnedBuffer((BATCH, 1000), np.float32)
+	grad = M.gpuarray.to_gpu((rng.randn(BATCH, 1000) * 1e-3).astype(dt))
+	hostOut = driver.PinnedBuffer((BATCH, 1000), dt)
 
 	def step(e2e=False, asyncCopy=False):
 		if e2e:                                                      # H2D of the batch from pinned host memory
@@ -309,10 +324,14 @@ def gpuArm(args):
 	line = {
 		"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": node.gridsize, "steps": args.steps, "warmup": max(3, args.warmup),
 		"ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-		"dtype": "f32 (tensor-core contractions: tf32 products, f32 accumulation -- what cuDNN/cuBLAS TENSOR_OP_MATH give the reference here)",
+		"dtype": "f32 (tensor-core contractions: tf32 products, f32 accumulation -- what cuDNN/cuBLAS TENSOR_OP_MATH give the reference here)"
+				 if args.dtype == "f32" else "%s storage, f32 accumulation" % args.dtype,
 		"data": "synthetic",
 		"config": {
-			"workload": "ResNet-50 fp32 fwd+bwd, synthetic 64x3x224x224 per GPU (BASELINE.json configs[1])", "batch_per_gpu": BATCH,
+			"workload": "%s %s fwd+bwd, synthetic %dx3x224x224 per GPU%s" % (
+				{"resnet50": "ResNet-50", "vgg16": "VGG-16"}[args.model], {"f32": "fp32"}.get(args.dtype, args.dtype), BATCH,
+				" (BASELINE.json configs[1])" if args.model == "resnet50" and args.dtype == "f32" and BATCH == 64 else ""),
+			"batch_per_gpu": BATCH,
 			"global_batch": BATCH * node.gridsize, "parallelism": "dp%d" % node.gridsize,
 			"step": "zeroGradParams + forward + backward (incl. conv1 dgrad) + grad mean over ranks + momentum-SGD update",
 			"l2": "no explicit flush: one step streams ~20 GB of activations through the 126 MB L2, every kernel's inputs exceed L2 between reuses",
@@ -323,7 +342,7 @@ def gpuArm(args):
 				  "host_enqueue_ms_per_step": hostEnqueueMs, "note": "same step driven op by op through the Python module API"},
 		"clocks": clocks,
 		"e2e": {"value": images / (msE2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": int(data.nbytes) * node.gridsize,
-				"d2h_bytes_per_step": BATCH * 1000 * 4 * node.gridsize},
+				"d2h_bytes_per_step": BATCH * 1000 * dt.itemsize * node.gridsize},
 		"gpu_launches": launches,
 		"roofline": roofline,
 	}
@@ -351,6 +370,9 @@ def main():
 	parser.add_argument("--cpu-images", type=int, default=8, help="bounded CPU-baseline sample (images per step)")
 	parser.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
 	parser.add_argument("--no-graph", action="store_true", help="time the eager module API only (no CUDA-graph replay)")
+	parser.add_argument("--model", default="resnet50", choices=["resnet50", "vgg16"], help="side measurements; the headline is resnet50")
+	parser.add_argument("--dtype", default="f32", choices=["f32", "bf16", "f16"], help="storage type (side measurements)")
+	parser.add_argument("--batch", type=int, default=0, help="per-GPU batch (default 64)")
 	args = parser.parse_args()
 
 	if args.impl == "reference":

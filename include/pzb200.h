@@ -219,6 +219,15 @@ int pz_conv2d_wgrad(int dtype, const pz_conv2d_desc* d, const void* x, const voi
 int pz_bias_grad(int dtype, const void* t, void* db, int64_t N, int64_t C, int64_t S, float alpha, float beta,
 				 void* stream);
 
+/* ---- recurrent cells (Cuda/Source/Libs/CuDnnRnn.c:565-1000 cudnnRNNForwardTraining / BackwardData cell math; the matrix
+   products are pz_gemm calls).  fp32; gate order in a 4H row: i, f, c, o (Cuda/Backend.py:264-306 linear layers 0..3) */
+int pz_lstm_cell_fwd(float* gates, const float* bw, const float* br, const float* c_prev, float* c_out, float* h_out, int64_t B,
+                     int64_t H, void* stream);
+int pz_lstm_cell_bwd(const float* dy, const float* dh_next, float* dc_io, const float* acts, const float* c, const float* c_prev,
+                     float* dgates, int64_t B, int64_t H, int first, void* stream);
+int pz_rnn_cell_fwd(float* h, const float* bw, const float* br, int64_t B, int64_t H, int mode, void* stream);
+int pz_rnn_cell_bwd(const float* dy, const float* dh_next, const float* h, float* dpre, int64_t n, int mode, void* stream);
+
 /* ---------------------------------------------------------------- data-parallel gradient sync (NCCL over NVLink)
  * replaces Grid.py's CUDA-IPC parent/child star (Grid.py:66-157; Buffer.c:411-424) */
 int pz_nccl_version(int* version);                                   /* ncclGetVersion of the loaded libnccl */

@@ -440,3 +440,96 @@ def grid_mean(tensors, dtype=np.float64):
 	for t in tensors:
 		acc += t.astype(dtype)
 	return acc / len(tensors)
+
+
+# ================================================================================================ recurrent layers
+def _sigmoid(x):
+	return 1.0 / (1.0 + np.exp(-x))
+
+
+def lstm_forward(x, params, h0=None, c0=None, dtype=np.float64):
+	"""One uni-directional LSTM layer.  Follows the reference's own host loop (Cuda/Wrappers/CuDnnRnn.py:178-236): gates
+	i, f, o sigmoid, candidate c tanh; c_t = f*c_{t-1} + i*g; h_t = o*tanh(c_t); double bias bw* + br*.
+	x (T, B, in); params: dict wi wf wc wo (H, in), ri rf rc ro (H, H), bw*/br* (H,).  Returns (out (T,B,H), cache)."""
+	x = np.asarray(x, dtype)
+	T, B, _ = x.shape
+	H = params["ri"].shape[0]
+	p = {k: np.asarray(v, dtype) for k, v in params.items()}
+	h = np.zeros((B, H), dtype) if h0 is None else np.asarray(h0, dtype)
+	c = np.zeros((B, H), dtype) if c0 is None else np.asarray(c0, dtype)
+	out = np.empty((T, B, H), dtype)
+	cache = {"i": [], "f": [], "g": [], "o": [], "c": [], "hprev": [], "cprev": []}
+	for t in range(T):
+		pre = {g: x[t] @ p["w" + g].T + h @ p["r" + g].T + p["bw" + g] + p["br" + g] for g in "ifco"}
+		i, f, o, g = _sigmoid(pre["i"]), _sigmoid(pre["f"]), _sigmoid(pre["o"]), np.tanh(pre["c"])
+		cache["hprev"].append(h)
+		cache["cprev"].append(c)
+		c = f * c + i * g
+		h = o * np.tanh(c)
+		out[t] = h
+		for k, v in (("i", i), ("f", f), ("g", g), ("o", o), ("c", c)):
+			cache[k].append(v)
+	return out, cache
+
+
+def lstm_backward(x, params, cache, dy, dtype=np.float64):
+	"""Gradients of lstm_forward (reference host loop: CuDnnRnn.py:238-300): returns (dx, dparams dict)."""
+	x, dy = np.asarray(x, dtype), np.asarray(dy, dtype)
+	T, B, insz = x.shape
+	p = {k: np.asarray(v, dtype) for k, v in params.items()}
+	H = p["ri"].shape[0]
+	dp = {k: np.zeros_like(v) for k, v in p.items()}
+	dx = np.zeros((T, B, insz), dtype)
+	dhn, dcn = np.zeros((B, H), dtype), np.zeros((B, H), dtype)
+	for t in range(T - 1, -1, -1):
+		i, f, g, o, c = (cache[k][t] for k in ("i", "f", "g", "o", "c"))
+		hprev, cprev = cache["hprev"][t], cache["cprev"][t]
+		dh = dy[t] + dhn
+		tc = np.tanh(c)
+		dc = dh * o * (1.0 - tc * tc) + dcn
+		dpre = {"i": dc * g * i * (1 - i), "f": dc * cprev * f * (1 - f), "c": dc * i * (1 - g * g), "o": dh * tc * o * (1 - o)}
+		dhn = np.zeros((B, H), dtype)
+		for gname, d in dpre.items():
+			dp["w" + gname] += d.T @ x[t]
+			dp["r" + gname] += d.T @ hprev
+			dp["bw" + gname] += d.sum(axis=0)
+			dp["br" + gname] += d.sum(axis=0)
+			dx[t] += d @ p["w" + gname]
+			dhn += d @ p["r" + gname]
+		dcn = dc * f
+	return dx, dp
+
+
+def rnn_forward(x, params, mode="tanh", h0=None, dtype=np.float64):
+	"""Plain RNN layer h_t = act(x_t wi^T + h_{t-1} ri^T + bwi + bri) (reference host loop: CuDnnRnn.py:28-58, 95-118)."""
+	x = np.asarray(x, dtype)
+	T, B, _ = x.shape
+	p = {k: np.asarray(v, dtype) for k, v in params.items()}
+	H = p["ri"].shape[0]
+	h = np.zeros((B, H), dtype) if h0 is None else np.asarray(h0, dtype)
+	out = np.empty((T, B, H), dtype)
+	for t in range(T):
+		pre = x[t] @ p["wi"].T + h @ p["ri"].T + p["bwi"] + p["bri"]
+		h = np.maximum(pre, 0.0) if mode == "relu" else np.tanh(pre)
+		out[t] = h
+	return out
+
+
+def rnn_backward(x, params, out, dy, mode="tanh", h0=None, dtype=np.float64):
+	x, out, dy = np.asarray(x, dtype), np.asarray(out, dtype), np.asarray(dy, dtype)
+	T, B, insz = x.shape
+	p = {k: np.asarray(v, dtype) for k, v in params.items()}
+	H = p["ri"].shape[0]
+	dp = {k: np.zeros_like(v) for k, v in p.items()}
+	dx = np.zeros((T, B, insz), dtype)
+	dhn = np.zeros((B, H), dtype)
+	for t in range(T - 1, -1, -1):
+		d = (dy[t] + dhn) * ((out[t] > 0) if mode == "relu" else (1.0 - out[t] ** 2))
+		hprev = out[t - 1] if t > 0 else (np.zeros((B, H), dtype) if h0 is None else np.asarray(h0, dtype))
+		dp["wi"] += d.T @ x[t]
+		dp["ri"] += d.T @ hprev
+		dp["bwi"] += d.sum(axis=0)
+		dp["bri"] += d.sum(axis=0)
+		dx[t] = d @ p["wi"]
+		dhn = d @ p["ri"]
+	return dx, dp

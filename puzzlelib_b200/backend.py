@@ -642,6 +642,21 @@ class B200Backend:
 		spatial = 1
 		spatialPersistent = 2
 
+	class RNNAlgo(Enum):
+		standard = 0
+		persistStatic = 1
+		persistDynamic = 2
+
+	class RNNMode(Enum):
+		relu = 0
+		tanh = 1
+		lstm = 2
+		gru = 3
+
+	class DirectionMode(Enum):
+		uni = 0
+		bi = 1
+
 	def __init__(self, deviceIdx, initmode=0, logger=None):
 		self.deviceIdx = deviceIdx
 		self.logger = logger
@@ -833,6 +848,28 @@ class B200Backend:
 															allocator=self.memoryPool))
 		bwdParam = bench(lambda: self.dnn.convNdBackwardParams(data, out, W, stride, pad, dilation, groups, wgrad=wgrad))
 		return [ConvPerf(0, fwd, 0)], [ConvPerf(0, bwdData, 0)], [ConvPerf(0, bwdParam, 0)]
+
+	# ---- recurrent layers (reference: Cuda/Backend.py:171-350)
+	def createRnn(self, insize, hsize, dtype, layers=1, algo=None, mode=None, direction=None, dropout=0.0, seed=0, batchsize=0):
+		from .rnn import Rnn
+		algo = self.RNNAlgo.standard if algo is None else algo
+		mode = self.RNNMode.lstm if mode is None else mode
+		direction = self.DirectionMode.uni if direction is None else direction
+
+		self.updateBackend(2)
+		rnn = Rnn(self, insize, hsize, np.dtype(dtype), layers, algo.value, mode.value, direction.value, dropout, seed, batchsize)
+		W = GPUArray.empty((rnn.wsize, ), dtype=dtype)
+		return rnn, W, self.acquireRnnParams(rnn, W)
+
+	def acquireRnnParams(self, rnn, W):
+		return rnn.acquireParams(W)
+
+	def updateRnnParams(self, rnn, W, params):
+		# the named parameters ARE views into W here (no cuDNN-owned copy to refresh, Cuda/Backend.py:320-350)
+		pass
+
+	def deviceSupportsBatchHint(self):
+		return self.device.computeCapability() >= (6, 1)
 
 	def instanceNorm2d(self, data, scale, bias, epsilon, allocator=None):
 		"""BN over a (1, N*C, H, W) view with the affine parameters tiled N times (reference: GPUBackend.py:381-398)"""

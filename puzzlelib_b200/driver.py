@@ -132,6 +132,10 @@ _SIGNATURES = {
 	"pz_maxunpool2d_bwd": [_P, _P, _P, c_int64, c_int, c_int, _P],
 	"pz_softmax_fwd": [c_int, c_int, _P, _P, c_int64, c_int64, c_int64, _P],
 	"pz_softmax_bwd": [c_int, c_int, _P, _P, _P, c_int64, c_int64, c_int64, _P],
+	"pz_lstm_cell_fwd": [_P, _P, _P, _P, _P, _P, c_int64, c_int64, _P],
+	"pz_lstm_cell_bwd": [_P, _P, _P, _P, _P, _P, _P, c_int64, c_int64, c_int, _P],
+	"pz_rnn_cell_fwd": [_P, _P, _P, c_int64, c_int64, c_int, _P],
+	"pz_rnn_cell_bwd": [_P, _P, _P, _P, c_int64, c_int, _P],
 	"pz_gemm": [c_int, _P, _P, _P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int, c_int, c_float, c_float,
 				_P, _P],
 	"pz_conv2d_fprop": [c_int, POINTER(Conv2dDesc), _P, _P, _P, _P, _P],

@@ -17,7 +17,7 @@ import numpy as np
 
 from . import Config
 from .shim import gpuarray, Dnn, Blas, MatVec, Pool, PoolMode, ConvFwdAlgo, ConvBwdDataAlgo, ConvBwdFilterAlgo, memoryPool, \
-	backend
+	backend, Rnn
 from .driver import bfloat16
 
 
@@ -612,6 +612,138 @@ class Linear(Module):
 		if np.dtype(T) not in _floatTypes():
 			raise ModuleError("Unsupported dtype %s" % T)
 		self._recastVars(T)
+
+
+# ---------------------------------------------------------------------------------------------------------- recurrent
+class RNNMode(str, Enum):
+	relu = "relu"
+	tanh = "tanh"
+	lstm = "lstm"
+	gru = "gru"
+
+
+class DirectionMode(str, Enum):
+	uni = "uni"
+	bi = "bi"
+
+
+class WeightModifier(str, Enum):
+	orthogonal = "orthogonal"
+	identity = "identity"
+
+
+class RNN(Module):
+	"""reference: Modules/RNN.py:31-240 (same constructor, parameter initialisation draws, last-step selection and gradient
+	scatter in Python; uni-directional relu / tanh / lstm -- what the B200 Rnn object implements)"""
+
+	def __init__(self, insize, hsize, layers=1, mode="relu", direction="uni", dropout=0.0, getSequences=False, initscheme=None,
+				 modifier="orthogonal", wscale=1.0, hintBatchSize=None, name=None):
+		super().__init__(name)
+		self.gradUsesOutData = True
+
+		self.insize, self.hsize, self.layers = insize, hsize, layers
+		self.mode, self.direction = RNNMode(mode), DirectionMode(direction)
+		self.dropout, self.getSequences, self.hintBatchSize = dropout, getSequences, hintBatchSize
+
+		bnd = backend()
+		mode = {RNNMode.relu: bnd.RNNMode.relu, RNNMode.tanh: bnd.RNNMode.tanh, RNNMode.lstm: bnd.RNNMode.lstm,
+				RNNMode.gru: bnd.RNNMode.gru}[self.mode]
+		direction = {DirectionMode.uni: bnd.DirectionMode.uni, DirectionMode.bi: bnd.DirectionMode.bi}[self.direction]
+
+		self.descRnn, W, params = Rnn.createRnn(insize, hsize, layers, mode, direction, dropout, seed=np.random.randint(1 << 31),
+												batchsize=hintBatchSize)
+		self.W = None
+		self.setVar("W", Variable(W))
+		self.params = params
+		self.initParams(initscheme, wscale, modifier)
+		self.reserve, self.fulldata, self.dw = None, None, None
+
+	def initParams(self, initscheme, wscale, modifier):
+		modifier = WeightModifier(modifier)
+		for key in sorted(self.params.keys()):
+			for paramName, param in sorted(self.params[key].items()):
+				if paramName.startswith("b"):
+					param.fill(0.0)
+					continue
+				if paramName.startswith("r"):
+					if modifier == WeightModifier.orthogonal:
+						a = np.random.normal(0.0, 1.0, param.shape)
+						u, _, v = np.linalg.svd(a, full_matrices=False)
+						W = u if u.shape == param.shape else v
+						W = W[:param.shape[0], :param.shape[1]].astype(np.float32)
+					elif modifier == WeightModifier.identity:
+						W = np.identity(param.shape[0], dtype=np.float32)
+					else:
+						raise NotImplementedError(modifier)
+				else:
+					W = self.createTensorWithScheme(initscheme, param.shape, wscale)
+					if W is None:
+						continue
+				param.set(W)
+		self.updateDeviceMemory()
+
+	def updateDeviceMemory(self):
+		Rnn.updateRnnParams(self.descRnn, self.W, self.params)
+
+	def setVar(self, name, var):
+		if name == "W" and hasattr(self, "params"):
+			_, self.params = Rnn.acquireRnnParams(self.descRnn, w=var.data)
+		super().setVar(name, var)
+
+	def updateData(self, data):
+		if self.train:
+			self.fulldata, self.reserve = Rnn.forwardRnn(data, self.W, self.descRnn)
+		else:
+			self.fulldata = Rnn.forwardRnn(data, self.W, self.descRnn, test=True)
+		self.data = self.fulldata if self.getSequences else self.fulldata[-1]
+
+	def updateGrad(self, grad):
+		if self.getSequences:
+			fullgrad = grad
+		else:
+			seqlen = self.fulldata.shape[0]
+			fullgrad = gpuarray.empty((seqlen, ) + grad.shape, dtype=grad.dtype, allocator=memoryPool())
+			if seqlen > 1:
+				fullgrad[:seqlen - 1].fill(0.0)
+			fullgrad[seqlen - 1].set(grad)
+		self.grad, self.reserve = Rnn.backwardDataRnn(fullgrad, self.fulldata, self.W, self.reserve, self.descRnn)
+
+	def accGradParams(self, grad, scale=1.0, momentum=0.0):
+		self.dw = Rnn.backwardParamsRnn(self.inData, self.fulldata, self.W, self.reserve, self.descRnn)
+		Blas.addVectorToVector(self.dw, self.getVar("W").grad, out=self.getVar("W").grad, alpha=scale, beta=momentum)
+
+	def checkDataShape(self, shape):
+		if len(shape) != 3:
+			raise ModuleError("Data must be 3d tensor")
+		if self.hintBatchSize is not None and shape[1] != self.hintBatchSize:
+			raise ModuleError("Data batch size must be = %s (was given %s)" % (self.hintBatchSize, shape[1]))
+		if shape[2] != self.insize:
+			raise ModuleError("Data must have data size = %s (was given %s)" % (self.insize, shape[2]))
+
+	def checkGradShape(self, shape):
+		if self.getSequences:
+			if len(shape) != 3:
+				raise ModuleError("Grad must be 3d tensor")
+		else:
+			if len(shape) != 2:
+				raise ModuleError("Grad must be 2d matrix")
+			if shape[-1] != self.hsize:
+				raise ModuleError("Grad must have data size = %s (was given %s)" % (self.hsize, shape[-1]))
+
+	def dataShapeFrom(self, shape):
+		return shape[:2] + (self.hsize, ) if self.getSequences else (shape[1], self.hsize)
+
+	def gradShapeFrom(self, shape):
+		return self.inData.shape[0], shape[1] if self.getSequences else shape[0], self.insize
+
+	def reset(self):
+		super().reset()
+		self.reserve, self.fulldata, self.dw = None, None, None
+
+	def calcMode(self, T):
+		if T != np.float32:
+			raise ModuleError("Unsupported dtype %s" % T)
+		self.calctype = T
 
 
 # ---------------------------------------------------------------------------------------------------------- norm

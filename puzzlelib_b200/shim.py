@@ -169,6 +169,37 @@ class Dnn:
 		return backend().instanceNorm2dBackward(grad, data, extscale, savemean, saveinvvar, epsilon, affine, allocator=memoryPool())
 
 
+class Rnn:
+	"""reference: Backend/Dnn.py:299-333 (initRnnGPU)"""
+
+	@staticmethod
+	def createRnn(insize, hsize, layers, mode, direction, dropout, seed, batchsize):
+		rnn, W, params = backend().createRnn(insize, hsize, np.float32, layers, mode=mode, direction=direction, dropout=dropout,
+											 seed=seed, batchsize=0 if batchsize is None else batchsize)
+		return rnn, W, {i: layer for i, layer in enumerate(params)}
+
+	@staticmethod
+	def acquireRnnParams(descRnn, w):
+		return w, {i: layer for i, layer in enumerate(backend().acquireRnnParams(descRnn, w))}
+
+	@staticmethod
+	def updateRnnParams(descRnn, w, params):
+		backend().updateRnnParams(descRnn, w, [params[layer] for layer in sorted(params.keys())])
+
+	@staticmethod
+	def forwardRnn(data, W, descRnn, test=False):
+		return descRnn.forward(data, W, test=test, allocator=memoryPool())
+
+	@staticmethod
+	def backwardDataRnn(grad, outdata, W, reserve, descRnn):
+		ingrad, _, _ = descRnn.backwardData(grad, outdata, W, reserve, allocator=memoryPool())
+		return ingrad, reserve
+
+	@staticmethod
+	def backwardParamsRnn(data, outdata, _, reserve, descRnn):
+		return descRnn.backwardParams(data, outdata, reserve, allocator=memoryPool())
+
+
 class Blas:
 	"""reference: Backend/Blas.py:43-70"""
 

@@ -557,3 +557,94 @@ def test_concatenate_split_tile_sharedarray(bnd):
 	shared["b"].fill(2.0)
 	flat = shared.ary.get()
 	assert flat[:15].sum() == 15 and (flat[16:23] == 2).all()
+
+
+# ================================================================================================ recurrent layers
+def _rnn_host_params(params):
+	return {k: v.get().astype(np.float64) for k, v in params.items()}
+
+
+@pytest.mark.parametrize("case", [(4, 2, 4, 2, 1), (7, 5, 33, 20, 1), (6, 16, 64, 96, 2), (12, 64, 128, 128, 1)])
+def test_lstm_forward_backward(bnd, case):
+	# reference test: Cuda/Wrappers/CuDnnRnn.py:178-300 (lstmTest); GEMMs run as TF32 on the tensor cores
+	T, B, insz, H, layers = case
+	rng = np.random.RandomState(T * 100 + H)
+	rnn, W, params = bnd.createRnn(insz, H, np.float32, layers=layers, mode=bnd.RNNMode.lstm)
+	assert W.shape == (sum(4 * H * ((insz if l == 0 else H) + H) + 8 * H for l in range(layers)), )
+	W.set((rng.randn(*W.shape) * 0.2).astype(np.float32))
+	host = [_rnn_host_params(p) for p in params]
+
+	x = rng.randn(T, B, insz).astype(np.float32)
+	dy = rng.randn(T, B, H).astype(np.float32)
+	out, reserve = rnn.forward(G(bnd, x), W, allocator=bnd.memoryPool)
+
+	acts, caches = [x.astype(np.float64)], []
+	for l in range(layers):
+		o, cache = ops.lstm_forward(acts[-1], host[l])
+		acts.append(o)
+		caches.append(cache)
+	tol = REL_TC * (1 + T / 4.0)          # tf32 rounding compounds through the recurrence
+	assert relerr(out.get(), acts[-1]) < tol
+
+	ingrad, dhx, dcx = rnn.backwardData(G(bnd, dy), out, W, reserve, allocator=bnd.memoryPool)
+	dw = rnn.backwardParams(G(bnd, x), out, reserve, allocator=bnd.memoryPool)
+	dwparams = bnd.acquireRnnParams(rnn, dw)
+
+	g = dy.astype(np.float64)
+	for l in range(layers - 1, -1, -1):
+		g, dp = ops.lstm_backward(acts[l], host[l], caches[l], g)
+		for name, want in dp.items():
+			assert relerr(dwparams[l][name].get(), want) < 2 * tol, name
+	assert relerr(ingrad.get(), g) < 2 * tol
+
+
+@pytest.mark.parametrize("mode", ["relu", "tanh"])
+def test_plain_rnn_forward_backward(bnd, mode):
+	# reference tests: Cuda/Wrappers/CuDnnRnn.py:20-176 (reluTest / tanhTest, uni-directional part)
+	T, B, insz, H = 5, 6, 24, 40
+	rng = np.random.RandomState(9)
+	rnn, W, params = bnd.createRnn(insz, H, np.float32, mode=getattr(bnd.RNNMode, mode))
+	W.set((rng.randn(*W.shape) * 0.2).astype(np.float32))
+	host = _rnn_host_params(params[0])
+	x, dy = rng.randn(T, B, insz).astype(np.float32), rng.randn(T, B, H).astype(np.float32)
+
+	out, reserve = rnn.forward(G(bnd, x), W, allocator=bnd.memoryPool)
+	want = ops.rnn_forward(x, host, mode)
+	tol = REL_TC * (1 + T / 4.0)          # tf32 rounding compounds through the recurrence
+	assert relerr(out.get(), want) < tol
+
+	ingrad, _, _ = rnn.backwardData(G(bnd, dy), out, W, reserve, allocator=bnd.memoryPool)
+	dw = rnn.backwardParams(G(bnd, x), out, reserve, allocator=bnd.memoryPool)
+	dx, dp = ops.rnn_backward(x, host, want, dy, mode)
+	assert relerr(ingrad.get(), dx) < 2 * tol
+	dwparams = bnd.acquireRnnParams(rnn, dw)[0]
+	for name, w in dp.items():
+		assert relerr(dwparams[name].get(), w) < 2 * tol, name
+
+
+def test_rnn_module_last_step_and_sequences(bnd):
+	# Modules/RNN.py:122-161: getSequences=False returns the last step and scatters the gradient into a zero sequence
+	from puzzlelib_b200 import modules as M
+	rng = np.random.RandomState(3)
+	np.random.seed(3)
+	T, B, insz, H = 6, 4, 16, 32
+	mod = M.RNN(insz, H, mode="lstm", getSequences=False)
+	x = rng.randn(T, B, insz).astype(np.float32)
+	out = mod(G(bnd, x))
+	assert out.shape == (B, H)
+	host = _rnn_host_params(mod.params[0])
+	want, cache = ops.lstm_forward(x, host)
+	assert relerr(out.get(), want[-1]) < REL_TC
+
+	g = rng.randn(B, H).astype(np.float32)
+	mod.zeroGradParams() if hasattr(mod, "zeroGradParams") else None
+	mod.backward(G(bnd, g))
+	full = np.zeros((T, B, H))
+	full[-1] = g
+	dx, dp = ops.lstm_backward(x, host, cache, full)
+	assert relerr(mod.grad.get(), dx) < 2 * REL_TC
+	dwparams = bnd.acquireRnnParams(mod.descRnn, mod.vars["W"].grad)[0]
+	assert relerr(dwparams["ri"].get(), dp["ri"]) < 2 * REL_TC
+
+	with pytest.raises(NotImplementedError):
+		M.RNN(insz, H, mode="gru")

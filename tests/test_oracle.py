@@ -213,3 +213,58 @@ def test_refnet_resnet50_shapes():
 	assert len(convs) == 53 and len(bns) == 53
 	nparams = sum(l.W.size for l in convs) + sum(2 * l.scale.size for l in bns) + 2048 * 1000 + 1000
 	assert nparams == 25557032      # 25.56 M parameters
+
+
+def test_lstm_oracle_gradients_match_finite_differences():
+	# the LSTM restatement follows the reference's host loop (Cuda/Wrappers/CuDnnRnn.py:178-300); its backward is pinned here
+	# against central differences of its own forward (fp64)
+	rng = np.random.RandomState(5)
+	T, B, insz, H = 3, 2, 4, 3
+	params = {}
+	for g in "ifco":
+		params["w" + g] = rng.randn(H, insz) * 0.5
+		params["r" + g] = rng.randn(H, H) * 0.5
+		params["bw" + g] = rng.randn(H) * 0.1
+		params["br" + g] = rng.randn(H) * 0.1
+	x = rng.randn(T, B, insz)
+	dy = rng.randn(T, B, H)
+
+	out, cache = ops.lstm_forward(x, params)
+	dx, dp = ops.lstm_backward(x, params, cache, dy)
+
+	def loss(xv, pv):
+		return float((ops.lstm_forward(xv, pv)[0] * dy).sum())
+
+	eps = 1e-6
+	for idx in [(0, 0, 0), (1, 1, 2), (2, 0, 3)]:
+		xp, xm = x.copy(), x.copy()
+		xp[idx] += eps
+		xm[idx] -= eps
+		assert abs((loss(xp, params) - loss(xm, params)) / (2 * eps) - dx[idx]) < 1e-6
+	for name, idx in [("wi", (0, 1)), ("rf", (2, 0)), ("wc", (1, 3)), ("ro", (1, 1)), ("bwf", (2, )), ("brc", (0, ))]:
+		pp, pm = {k: v.copy() for k, v in params.items()}, {k: v.copy() for k, v in params.items()}
+		pp[name][idx] += eps
+		pm[name][idx] -= eps
+		assert abs((loss(x, pp) - loss(x, pm)) / (2 * eps) - dp[name][idx]) < 1e-6
+
+
+def test_rnn_oracle_gradients_match_finite_differences():
+	rng = np.random.RandomState(6)
+	T, B, insz, H = 4, 2, 3, 3
+	params = {"wi": rng.randn(H, insz) * 0.5, "ri": rng.randn(H, H) * 0.5, "bwi": rng.randn(H) * 0.1, "bri": rng.randn(H) * 0.1}
+	x, dy = rng.randn(T, B, insz), rng.randn(T, B, H)
+	out = ops.rnn_forward(x, params, "tanh")
+	dx, dp = ops.rnn_backward(x, params, out, dy, "tanh")
+	eps = 1e-6
+
+	def loss(xv, pv):
+		return float((ops.rnn_forward(xv, pv, "tanh") * dy).sum())
+
+	xp, xm = x.copy(), x.copy()
+	xp[1, 0, 2] += eps
+	xm[1, 0, 2] -= eps
+	assert abs((loss(xp, params) - loss(xm, params)) / (2 * eps) - dx[1, 0, 2]) < 1e-6
+	pp, pm = {k: v.copy() for k, v in params.items()}, {k: v.copy() for k, v in params.items()}
+	pp["ri"][1, 2] += eps
+	pm["ri"][1, 2] -= eps
+	assert abs((loss(x, pp) - loss(x, pm)) / (2 * eps) - dp["ri"][1, 2]) < 1e-6
