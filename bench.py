@@ -255,11 +255,13 @@ def gpuArm(args):
 
 	# ---- graph: the same step (same module calls, same kernels, same buffers) captured once into a CUDA graph and replayed
 	graphNote, sampler, clocks = None, None, None
+	graphs = []
 	try:
 		if args.no_graph:
 			raise RuntimeError("disabled by --no-graph")
 		graph = driver.StepGraph(lambda: step(False), warmup=2)
 		graphE2e = driver.StepGraph(lambda: step(True, True), warmup=2)
+		graphs += [graph, graphE2e]
 		timedGraph(graph, 3)
 		sampler = ClockSampler(node.device) if node.index == 0 else None
 		if sampler:
@@ -279,6 +281,10 @@ def gpuArm(args):
 		clocks = sampler.stop() if sampler else None
 		msE2e = eagerE2eMs
 		api = "eager module API"
+
+	for g in graphs:                       # graphs hold captured NCCL work: release them before the communicator goes away
+		g.destroy()
+	graphs.clear()
 
 	# roofline pass: the same K steps with CUDA events around every launch of each kernel family
 	driver.profileEnable(True)
@@ -374,6 +380,10 @@ def main():
 	parser.add_argument("--dtype", default="f32", choices=["f32", "bf16", "f16"], help="storage type (side measurements)")
 	parser.add_argument("--batch", type=int, default=0, help="per-GPU batch (default 64)")
 	args = parser.parse_args()
+
+	if os.environ.get("PZ_BENCH_WATCHDOG"):      # debugging aid: dump every thread's stack and exit if the run takes too long
+		import faulthandler
+		faulthandler.dump_traceback_later(int(os.environ["PZ_BENCH_WATCHDOG"]), exit=True)
 
 	if args.impl == "reference":
 		referenceArm(args)

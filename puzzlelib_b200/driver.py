@@ -501,11 +501,16 @@ class StepGraph:
 	def synchronize(self):
 		self.stream.synchronize()
 
+	def destroy(self):
+		"""Release the graph (graphs that captured NCCL collectives must be destroyed BEFORE their communicator)."""
+		if self.exec:
+			self.stream.synchronize()
+			lib.pz_graph_destroy(self.exec)
+			self.exec = None
+
 	def __del__(self):
 		try:
-			if self.exec:
-				lib.pz_graph_destroy(self.exec)
-				self.exec = None
+			self.destroy()
 		except Exception:
 			pass
 
