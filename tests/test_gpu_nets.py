@@ -368,3 +368,62 @@ def test_momentum_sgd_global_state_matches_oracle(M):
 		assert np.allclose(flat.data.get(), p0, atol=1e-6)
 		off = (conv.W.ptr - flat.data.ptr) // 4
 		assert np.array_equal(conv.W.get().ravel(), flat.data.get()[off:off + conv.W.size])
+
+
+def test_step_graph_replay_matches_eager_steps(M):
+	# driver.StepGraph: a step driven through the unchanged module API, captured once and replayed, must do
+	# exactly what the same number of eager steps does -- same kernels, same buffers, deterministic kernels only on this net.
+	from puzzlelib_b200 import driver
+	from puzzlelib_b200.optim import MomentumSGD
+
+	def build():
+		np.random.seed(21)
+		net = M.Sequential()
+		# minFactor = 1: the running-average factor max(1/n, minFactor) is the same scalar at every step, as a graph requires
+		net.append(M.Conv2D(8, 16, 3, pad=1, initscheme="he")).append(M.BatchNorm2D(16, minFactor=1.0)).append(M.Activation(M.relu))
+		net.append(M.MaxPool2D(2, 2)).append(M.Conv2D(16, 32, 1, useBias=False, initscheme="he")).append(M.AvgPool2D(4, 4))
+		net.append(M.Flatten()).append(M.Linear(32 * 2 * 2, 10, initscheme="he")).append(M.SoftMax())
+		opt = MomentumSGD(learnRate=1e-2, momRate=0.9)
+		opt.setupOn(net, useGlobalState=True)
+		return net, opt
+
+	rng = np.random.RandomState(0)
+	x = M.gpuarray.to_gpu(rng.randn(4, 8, 16, 16).astype(np.float32))
+	gy = M.gpuarray.to_gpu((rng.randn(4, 10) * 0.1).astype(np.float32))
+
+	def make_step(net, opt):
+		def step():
+			opt.zeroGradParams()
+			net(x)
+			net.backward(gy)
+			opt.update()
+			net.reset()
+		return step
+
+	warm, replays = 2, 3
+
+	def eager():
+		net, opt = build()
+		step = make_step(net, opt)
+		for _ in range(warm + replays):      # StepGraph runs the step `warmup` times eagerly; the capture pass only records
+			step()
+		driver.Device.synchronize()
+		return net
+
+	net1, net3 = eager(), eager()
+	# split-K / statistics accumulate with fp32 red.add, so two eager runs agree to rounding only: that is the bar for the graph
+	noise = max(relerr(net3.graph[0].W.get(), net1.graph[0].W.get()), relerr(net3.graph[7].W.get(), net1.graph[7].W.get()))
+	tol = max(1e-5, 20 * noise)
+
+	net2, opt2 = build()
+	graph = driver.StepGraph(make_step(net2, opt2), warmup=warm)
+	for _ in range(replays):
+		graph.launch()
+	graph.synchronize()
+
+	w1 = net1.graph[0].W.get()
+	w2 = net2.graph[0].W.get()
+	assert np.abs(w1).max() > 0 and relerr(w2, w1) < tol
+	assert relerr(net2.graph[7].W.get(), net1.graph[7].W.get()) < tol
+	assert relerr(net2.graph[1].mean.get(), net1.graph[1].mean.get()) < tol
+	graph.destroy()
