@@ -232,7 +232,9 @@ int pz_conv2d_fprop(int dtype, const pz_conv2d_desc* d, const void* x, const voi
 
 	// filter: prepared copy [K][kpad], fetched by TMA
 	const bool fast = tap_entries_fit(34ll * HW, g);
-	const bool chan = fast && use_chan_order(g.Cg, bke);
+	// 16-bit tensors have no table-driven tap producer: even a 3-channel first layer takes the channel-ordered path (its padded
+	// channels cost predicated-off loads and cheap MMA work, far less than the general gather)
+	const bool chan = fast && (use_chan_order(g.Cg, bke) || h16);
 	const int kdim = g.Cg * RS, kpad = chan ? RS * round_up(g.Cg, bke) : round_up(kdim, bke);
 	const long long wtotal = (long long)g.K * kpad;
 	void* wp = pz_scratch((size_t)wtotal * pz_dtype_size(dtype));

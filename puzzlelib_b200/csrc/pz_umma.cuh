@@ -640,13 +640,28 @@ struct MnChanProducer {
 		const bool ok = mask.test(t);                                 // bit (TOP - t) of the mask, see init
 		const int c0 = (int)cb * 32 + chunk0 * 4;
 		const int cleft = op.chans - c0;
-		const float* __restrict__ ptr = base + ((long long)c0 * op.ks0 + (poff + tapoff));
-		#pragma unroll
-		for (int i = 0; i < NCH; i++) {
+		// one 64-bit base per stage; channel j is a 32x32 -> 64-bit multiply-add on it (a single IMAD.WIDE each)
+		const char* __restrict__ ptr = reinterpret_cast<const char*>(base + ((long long)c0 * op.ks0 + (poff + tapoff)));
+		const unsigned ksb = (unsigned)op.ks0 * 4u;
+		constexpr int JMAX = (NCH - 1) * CSTEP * 4 + 3;
+		if (cleft > JMAX) {
+			// every channel of the block exists (channel counts that are multiples of 32): one predicate for all loads
 			#pragma unroll
-			for (int e = 0; e < 4; e++) {
-				const int j = i * CSTEP * 4 + e;
-				v[i * 4 + e] = (ok && j < cleft) ? __ldg(ptr + (size_t)((unsigned)j * (unsigned)op.ks0)) : 0.0f;
+			for (int i = 0; i < NCH; i++) {
+				#pragma unroll
+				for (int e = 0; e < 4; e++) {
+					const unsigned j = (unsigned)(i * CSTEP * 4 + e);
+					v[i * 4 + e] = ok ? __ldg(reinterpret_cast<const float*>(ptr + (unsigned long long)ksb * j)) : 0.0f;
+				}
+			}
+		} else {
+			#pragma unroll
+			for (int i = 0; i < NCH; i++) {
+				#pragma unroll
+				for (int e = 0; e < 4; e++) {
+					const int j = i * CSTEP * 4 + e;
+					v[i * 4 + e] = (ok && j < cleft) ? __ldg(reinterpret_cast<const float*>(ptr + (unsigned long long)ksb * (unsigned)j)) : 0.0f;
+				}
 			}
 		}
 	}
@@ -742,7 +757,16 @@ struct KPosTapProducer {
 		const int hk = (int)pp * op.bh + op.ch, wk = qq * op.bw + op.cw;
 		TM mask;
 		mask.clear();
-		if (pvalid) {
+		if (op.R == 3 && op.S == 3) {
+			// the common 3x3 filter: straight-line code (no loop / branch overhead per k-block)
+			const uint32_t w0 = (unsigned)wk < (unsigned)op.W, w1 = (unsigned)(wk + op.aw) < (unsigned)op.W,
+						   w2 = (unsigned)(wk + 2 * op.aw) < (unsigned)op.W;
+			const uint32_t wm = w0 | (w1 << 1) | (w2 << 2);
+			const uint32_t h0 = (unsigned)hk < (unsigned)op.H, h1 = (unsigned)(hk + op.ah) < (unsigned)op.H,
+						   h2 = (unsigned)(hk + 2 * op.ah) < (unsigned)op.H;
+			const uint32_t m9 = (h0 ? wm : 0u) | (h1 ? wm << 3 : 0u) | (h2 ? wm << 6 : 0u);
+			mask.m = pvalid ? m9 : 0u;
+		} else if (pvalid) {
 			// valid(r, s) = vh(r) & vw(s): build the row of column bits once, then place it for every valid filter row
 			TM wm;
 			wm.clear();
@@ -1010,7 +1034,15 @@ struct KPosTapProducer16 {
 		const int qq = (pvalid ? pos : 0) - (int)pp * (int)op.kd2.d;
 		const int hk = (int)pp * op.bh + op.ch, wk = qq * op.bw + op.cw;
 		mask.clear();
-		if (pvalid) {
+		if (op.R == 3 && op.S == 3) {
+			const uint32_t w0 = (unsigned)wk < (unsigned)op.W, w1 = (unsigned)(wk + op.aw) < (unsigned)op.W,
+						   w2 = (unsigned)(wk + 2 * op.aw) < (unsigned)op.W;
+			const uint32_t wm = w0 | (w1 << 1) | (w2 << 2);
+			const uint32_t h0 = (unsigned)hk < (unsigned)op.H, h1 = (unsigned)(hk + op.ah) < (unsigned)op.H,
+						   h2 = (unsigned)(hk + 2 * op.ah) < (unsigned)op.H;
+			const uint32_t m9 = (h0 ? wm : 0u) | (h1 ? wm << 3 : 0u) | (h2 ? wm << 6 : 0u);
+			mask.m = pvalid ? m9 : 0u;
+		} else if (pvalid) {
 			TM wm;
 			wm.clear();
 			for (int s = 0; s < op.S; s++)
@@ -1218,7 +1250,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) umma_gemm_kernel(const __grid_con
 	using EL = typename std::conditional<H16, uint16_t, float>::type;      // operand element as the producers see it
 	constexpr int BKE = H16 ? BK16 : BK;                                   // elements per k-block (one 128-byte row)
 	constexpr bool B_TMA = BMODE == MODE_TMA;
-	constexpr int PF = B_TMA ? 3 : 2;                        // k-blocks of global loads in flight per producer thread
+	// k-blocks of global loads in flight per producer thread (register ring depth): as deep as the register budget allows,
+	// a k-block of scattered 128-byte row segments needs a full DRAM round trip
+	constexpr int PF = B_TMA ? 3 : 2;       // (measured: a deeper ring for the gather-gather modes spills and is slower)
 	extern __shared__ uint8_t smem_raw[];
 	const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
 	const uint32_t tables = smem0 + C::STAGES * C::STAGE_BYTES;
