@@ -312,6 +312,17 @@ def gpuArm(args):
 		achieved = fam["bytes"] / (fam["ms"] * 1e-3) / 1e9
 		roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm"], "unit": "GB/s", "frac": achieved / peaks["hbm"],
 					"traffic": None, "peak_note": "%s STREAM-style copy bandwidth" % peaks["src"]}
+	# DRAM traffic per launch of that family from the committed ncu capture of this command (profiles/, tools/summarize_launches.py)
+	try:
+		with open(os.path.join(ROOT, "profiles", "r01_family_traffic.json")) as f:
+			captured = json.load(f)["families"]
+		key = "gemm" if top.startswith("gemm") else top
+		roofline["traffic"] = captured[key]["dram_bytes_per_launch"]
+		roofline["traffic_note"] = "dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over the family's launches in " \
+								   "profiles/r01r_launches.md (ncu, cold cache); algorithmic bytes per launch: %.0f" % (
+									   fam["bytes"] / max(1, fam["launches"]))
+	except Exception:      # noqa: BLE001 -- no capture committed
+		pass
 	roofline.update({
 		"kernel": {"gemm": "umma_gemm_kernel, launches with arithmetic intensity above the ridge (tcgen05 implicit-GEMM 3x3 / 7x7 conv, GEMM)",
 				   "gemm_hbm": "umma_gemm_kernel, launches below the ridge (1x1 convolutions: HBM-bound even at full efficiency)",

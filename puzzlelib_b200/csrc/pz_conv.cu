@@ -71,6 +71,26 @@ void set_splits(GemmParams& p, long long tiles, int min_kb_per_split)
 	p.splits = (int)pz_cdiv(p.kblocks, p.kb_per_split);
 }
 
+// fprop / dgrad of small maps (14x14, 7x7 at batch 64) have fewer output tiles than the GPU has SMs.  Splitting the reduction
+// (red.add epilogue into a zeroed output) keeps every SM busy: the output is a few MB, the reduction is where the work is.
+void fill_machine_splits(GemmParams& p, long long units)
+{
+	const long long sms = pz_num_sms();
+	p.splits = 1;
+	p.kb_per_split = p.kblocks;
+	if (units * 5 >= sms * 4 || units <= 0) return;   // >= 80% of one wave already
+	// rounds of the persistent schedule x k-blocks per unit (+ a fixed per-unit cost: pipeline fill, red.add epilogue)
+	const long long overhead = 6;
+	long long best = 1, best_cost = (p.kblocks + overhead) * pz_cdiv(units, sms);
+	for (long long sp = 2; sp <= 16 && sp * 6 <= p.kblocks; sp++) {
+		const long long cost = pz_cdiv(units * sp, sms) * (pz_cdiv(p.kblocks, sp) + overhead);
+		if (cost * 100 < best_cost * 92) { best = sp; best_cost = cost; }
+	}
+	if (best < 2) return;
+	p.kb_per_split = (int)pz_cdiv(p.kblocks, best);
+	p.splits = (int)pz_cdiv(p.kblocks, p.kb_per_split);
+}
+
 // algorithmic work of one conv pass: 2*MACs; every operand read once + the result written once
 void set_alg(GemmParams& p, const Geo& g, int dtype)
 {
@@ -261,10 +281,15 @@ int pz_conv2d_fprop(int dtype, const pz_conv2d_desc* d, const void* x, const voi
 	A.chans = g.Cg;
 	A.kbdiv = make_fastdiv((uint32_t)(round_up(g.Cg, bke) / bke));
 	p.kblocks = kpad / bke;
-	p.splits = 1;
-	p.kb_per_split = p.kblocks;
 	set_alg(p, g, dtype);
 	const int bn = pick_bn(g.Kg, (long long)g.N * PQ, p.kblocks, g.G, 256);
+	fill_machine_splits(p, pz_cdiv(E.M, BM) * pz_cdiv(E.N, bn) * g.G);
+	if (h16) { p.splits = 1; p.kb_per_split = p.kblocks; }       // red.add needs an fp32 output
+	if (p.splits > 1) {
+		E.atomic = 1;
+		int st2 = pz_memset8(y, 0, (size_t)g.N * g.K * PQ * 4, stream);
+		if (st2 != PZ_OK) return st2;
+	}
 	// the table-driven tap producer exists for float only; 16-bit tensors with very few channels take the general gather
 	const int amode = chan ? MODE_MN_CHAN : (fast && !h16 ? MODE_MN_TAP : MODE_MN_GENERAL);
 	return launch(p, dtype, bn, amode, MODE_TMA, amode == MODE_MN_GENERAL ? false : RS > 31, g.G, &tsrc, pz_stream(stream));
@@ -352,14 +377,23 @@ int pz_conv2d_dgrad(int dtype, const pz_conv2d_desc* d, const void* dy, const vo
 		q.E.md12 = make_fastdiv(Hc * Wc); q.E.md2 = make_fastdiv(Wc);
 		q.E.ms0 = g.C * HW; q.E.ms1 = csh * g.W; q.E.ms2 = csw;
 		q.E.M = g.N * Hc * Wc;
-		q.splits = 1;
 		q.kblocks = kpad / bke;
+		q.splits = 1;
 		q.kb_per_split = q.kblocks;
 		q.tma_rows_per_group = g.Cg;
 		q.alg_flops = 2.0 * (double)q.E.M * g.K * g.Cg * Rc * Sc / g.G;
 		q.alg_bytes = (double)es * ((double)g.N * g.K * PQ / (csh * csw) + (double)g.K * g.Cg * Rc * Sc + (double)q.E.M * g.C);
 		const TmaSource tsrc{wt, g.C, kpad};
 		const int bn = pick_bn(g.Cg, q.E.M, q.kblocks, g.G, 256);
+		if (!h16 && a_h == 0 && a_w == 0 && csh == 1 && csw == 1) {
+			// whole-tensor problem: split the reduction when there are too few tiles to fill the machine
+			fill_machine_splits(q, pz_cdiv(q.E.M, BM) * pz_cdiv(q.E.N, bn) * g.G);
+			if (q.splits > 1) {
+				q.E.atomic = 1;
+				int st2 = pz_memset8(dx, 0, (size_t)g.N * g.C * HW * es, stream);
+				if (st2 != PZ_OK) return st2;
+			}
+		}
 		const bool cdiv = mode == 2 ? strided : Rc * Sc > 31;
 		return launch(q, dtype, bn, mode == 2 ? MODE_MN_GENERAL : (chan ? MODE_MN_CHAN : MODE_MN_TAP), MODE_TMA, cdiv, g.G, &tsrc, pz_stream(stream));
 	};
