@@ -132,7 +132,7 @@ __global__ void prep_filter_fprop(const T* __restrict__ w, T* __restrict__ wp, i
 // chan != 0: k ordered (tap (r', s'), ko block, 32 ko) for MnChanProducer, kpad = Rc * Sc * ceil(Kg / 32) * 32
 template <typename T>
 __global__ void prep_filter_dgrad(const T* __restrict__ w, T* __restrict__ wt, int Kg, int Cg, int R, int S, int r0, int s0,
-								   int sh, int sw, int Rc, int Sc, int kpad, long long total, int chan)
+								   int sh, int sw, int Rc, int Sc, int kpad, long long total, int chan, int flip)
 {
 	long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= total) return;
@@ -146,6 +146,7 @@ __global__ void prep_filter_dgrad(const T* __restrict__ w, T* __restrict__ wt, i
 		if (ko >= Kg) ko = -1;
 		rc = t / Sc;
 		sc = t % Sc;
+		if (flip) { rc = Rc - 1 - rc; sc = Sc - 1 - sc; }     // halo dgrad: tap t' reads the filter mirrored
 	} else if (k < Kg * Rc * Sc) {
 		sc = k % Sc;
 		k /= Sc;
@@ -282,6 +283,22 @@ int pz_conv2d_fprop(int dtype, const pz_conv2d_desc* d, const void* x, const voi
 	A.kbdiv = make_fastdiv((uint32_t)(round_up(g.Cg, bke) / bke));
 	p.kblocks = kpad / bke;
 	set_alg(p, g, dtype);
+	if (chan && RS > 1 && g.sh == 1 && g.sw == 1 && g.dh == 1 && g.dw == 1) {
+		// stride-1 filters with more than one tap: halo path (x staged once per channel block, taps = shifted windows)
+		HaloGeometry hg{};
+		hg.src = x;
+		hg.N = g.N; hg.Hs = g.H; hg.Ws = g.W; hg.ph = g.ph; hg.pw = g.pw;
+		hg.R = g.R; hg.S = g.S;
+		hg.chans = g.Cg; hg.out_chans = g.Kg;
+		hg.out_h = g.P; hg.out_w = g.Q;
+		hg.groups = g.G;
+		hg.img_stride = (long long)g.C * HW; hg.chan_stride = HW; hg.group_stride = (long long)g.Cg * HW;
+		Epilogue HE = E;
+		HE.ms0 = g.K * PQ; HE.ms1 = g.Q; HE.ms2 = 1;
+		HE.M = 0;
+		const int hst = launch_halo(hg, dtype, tsrc, HE, p.alg_flops, p.alg_bytes, pz_stream(stream));
+		if (hst != PZ_ERR_UNSUPPORTED) return hst;
+	}
 	const int bn = pick_bn(g.Kg, (long long)g.N * PQ, p.kblocks, g.G, 256);
 	fill_machine_splits(p, pz_cdiv(E.M, BM) * pz_cdiv(E.N, bn) * g.G);
 	if (h16) { p.splits = 1; p.kb_per_split = p.kblocks; }       // red.add needs an fp32 output
@@ -345,9 +362,33 @@ int pz_conv2d_dgrad(int dtype, const pz_conv2d_desc* d, const void* dy, const vo
 		const bool chan = mode != 2 && use_chan_order(g.Kg, bke);
 		const int kdim = g.Kg * Rc * Sc, kpad = dgrad_kpad(g.Kg, Rc * Sc, mode != 2, bke);
 		const long long total = (long long)g.C * kpad;
+		// stride-1 filters with more than one tap: halo path (dy staged once per channel block, taps = shifted windows)
+		const bool halo = mode == 1 && chan && g.dh == 1 && g.dw == 1 && Rc * Sc > 1 && g.R - 1 - g.ph >= 0 && g.S - 1 - g.pw >= 0;
 		PZ_PREP_LAUNCH(dtype, prep_filter_dgrad, total, pz_stream(stream), w, wt, g.Kg, g.Cg, g.R, g.S, r0, s0, csh, csw, Rc, Sc, kpad, total,
-					   chan ? 1 : 0);
+					   chan ? 1 : 0, halo ? 1 : 0);
 		PZ_LAUNCH_CHECK();
+		if (halo) {
+			HaloGeometry hg{};
+			hg.src = dy;
+			hg.N = g.N; hg.Hs = g.P; hg.Ws = g.Q; hg.ph = g.R - 1 - g.ph; hg.pw = g.S - 1 - g.pw;
+			hg.R = g.R; hg.S = g.S;
+			hg.chans = g.Kg; hg.out_chans = g.Cg;
+			hg.out_h = g.H; hg.out_w = g.W;
+			hg.groups = g.G;
+			hg.img_stride = (long long)g.K * PQ; hg.chan_stride = PQ; hg.group_stride = (long long)g.Kg * PQ;
+			Epilogue HE = E;
+			HE.ms0 = g.C * HW; HE.ms1 = g.W; HE.ms2 = 1;
+			HE.M = 0; HE.N = g.Cg;
+			const TmaSource htsrc{wt, g.C, kpad};
+			const double flops = 2.0 * (double)g.N * HW * g.K * g.Cg * Rc * Sc;
+			const double bytes = (double)es * ((double)g.N * g.K * PQ + (double)g.K * g.Cg * Rc * Sc + (double)g.N * g.C * HW);
+			const int hst = launch_halo(hg, dtype, htsrc, HE, flops, bytes, pz_stream(stream));
+			if (hst != PZ_ERR_UNSUPPORTED) return hst;
+			// geometry does not fit the halo kernel: re-prepare the filter un-mirrored and take the gather path
+			PZ_PREP_LAUNCH(dtype, prep_filter_dgrad, total, pz_stream(stream), w, wt, g.Kg, g.Cg, g.R, g.S, r0, s0, csh, csw, Rc, Sc, kpad,
+						   total, chan ? 1 : 0, 0);
+			PZ_LAUNCH_CHECK();
+		}
 
 		GemmParams q{};
 		Operand& QA = q.A;                 // rows (n, h', w') of the class, k (ko, r', s')

@@ -92,6 +92,41 @@ static int launch_inst(const GemmParams& p, const CUtensorMap& tmap, int grid, c
 	return PZ_OK;
 }
 
+// 2-d tensor map over the prepared filter: rows of kpad elements, box = one k-block x bn rows, 128-byte swizzle
+int make_filter_tmap(CUtensorMap* tmap, int dtype, const TmaSource& tma, int bn)
+{
+	const int bke = elems_per_kblock(dtype);
+	const size_t es = dtype == PZ_F32 ? 4 : 2;
+	PZ_REQUIRE(tma.ptr != nullptr && ((uintptr_t)tma.ptr & 15) == 0 && (tma.kpad * es) % 16 == 0, "bad TMA source");
+	cuuint64_t dims[2] = {(cuuint64_t)tma.kpad, (cuuint64_t)tma.rows};
+	cuuint64_t strides[1] = {(cuuint64_t)tma.kpad * es};
+	cuuint32_t box[2] = {(cuuint32_t)bke, (cuuint32_t)bn};
+	cuuint32_t estr[2] = {1, 1};
+	const CUtensorMapDataType dt = dtype == PZ_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+								   : (dtype == PZ_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+	// resolved through the runtime so that the library has no link-time dependency on libcuda.so (it must load, and
+	// export its symbols, on a machine without a driver)
+	typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+								 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+								 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+	static EncodeFn encode = nullptr;
+	if (!encode) {
+		void* fn = nullptr;
+		cudaDriverEntryPointQueryResult qres;
+		PZ_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+		PZ_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled is not available in this driver");
+		encode = (EncodeFn)fn;
+	}
+	memset(tmap, 0, sizeof(*tmap));
+	CUresult r = encode(tmap, dt, 2, (void*)tma.ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+						CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	if (r != CUDA_SUCCESS) {
+		pz_set_error(PZ_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+		return PZ_ERR_CUDA;
+	}
+	return PZ_OK;
+}
+
 int launch(GemmParams& p, int dtype, int bn, int amode, int bmode, bool cdiv, int groups, const TmaSource* tma, cudaStream_t stream)
 {
 	const int M = p.E.M, N = p.E.N;
@@ -111,34 +146,9 @@ int launch(GemmParams& p, int dtype, int bn, int amode, int bmode, bool cdiv, in
 	alignas(64) CUtensorMap tmap;
 	memset(&tmap, 0, sizeof(tmap));
 	if (bmode == MODE_TMA) {
-		const int bke = elems_per_kblock(dtype);
-		const size_t es = h16 ? 2 : 4;
-		PZ_REQUIRE(tma != nullptr && tma->ptr != nullptr && ((uintptr_t)tma->ptr & 15) == 0 && (tma->kpad * es) % 16 == 0, "bad TMA source");
-		cuuint64_t dims[2] = {(cuuint64_t)tma->kpad, (cuuint64_t)tma->rows};
-		cuuint64_t strides[1] = {(cuuint64_t)tma->kpad * es};
-		cuuint32_t box[2] = {(cuuint32_t)bke, (cuuint32_t)bn};
-		cuuint32_t estr[2] = {1, 1};
-		const CUtensorMapDataType dt = dtype == PZ_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
-									   : (dtype == PZ_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
-		// resolved through the runtime so that the library has no link-time dependency on libcuda.so (it must load, and
-		// export its symbols, on a machine without a driver)
-		typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-									 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-									 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-		static EncodeFn encode = nullptr;
-		if (!encode) {
-			void* fn = nullptr;
-			cudaDriverEntryPointQueryResult qres;
-			PZ_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-			PZ_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled is not available in this driver");
-			encode = (EncodeFn)fn;
-		}
-		CUresult r = encode(&tmap, dt, 2, (void*)tma->ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-							CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-		if (r != CUDA_SUCCESS) {
-			pz_set_error(PZ_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
-			return PZ_ERR_CUDA;
-		}
+		PZ_REQUIRE(tma != nullptr, "bad TMA source");
+		int st = make_filter_tmap(&tmap, dtype, *tma, bn);
+		if (st != PZ_OK) return st;
 	}
 
 #define PZ_INST(BNV, AMV, BMV, CD, H)                                                  \

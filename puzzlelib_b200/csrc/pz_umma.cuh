@@ -1455,6 +1455,19 @@ struct TmaSource {
 // dtype: PZ_F32 (tf32 products), PZ_F16 or PZ_BF16 -- the element type of both operands
 int launch(GemmParams& p, int dtype, int bn, int amode, int bmode, bool cdiv, int groups, const TmaSource* tma, cudaStream_t stream);
 inline int elems_per_kblock(int dtype) { return dtype == PZ_F32 ? BK : BK16; }
+// ---- halo path (pz_halo.cu): stride-1 R x S convolution with the activation operand staged once per channel block
+struct HaloGeometry {
+	const void* src;             // (N, C_total, Hs, Ws) source of the correlation: x (fprop) or dy (dgrad)
+	int N, Hs, Ws, ph, pw;       // zero padding added on every side of the source
+	int R, S;
+	int chans, out_chans;        // reduction / output channels per group
+	int out_h, out_w;            // must equal Hs + 2*ph - R + 1, Ws + 2*pw - S + 1
+	int groups;
+	long long img_stride, chan_stride, group_stride;   // source strides in elements
+};
+int launch_halo(const HaloGeometry& g, int dtype, const TmaSource& tsrc, const Epilogue& E, double alg_flops, double alg_bytes,
+				cudaStream_t stream);
+int make_filter_tmap(CUtensorMap* tmap, int dtype, const TmaSource& tma, int bn);
 int finalize16(int dtype, void* out, int64_t ldo, const float* acc, int64_t rows, int64_t cols, float beta, cudaStream_t stream);
 inline int out_kind_of(int dtype) { return dtype == PZ_F32 ? OUT_F32 : (dtype == PZ_F16 ? OUT_F16 : OUT_BF16); }
 int pick_bn(int n, long long m_rows, int kblocks, int groups, int max_bn);

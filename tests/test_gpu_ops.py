@@ -48,6 +48,10 @@ CONV_CASES = [
 	(2, 48, 15, 15, 40, 3, 3, 2, 1, 1, 1, True),      # channel counts that are not multiples of 32, strided 3x3
 	(2, 96, 9, 9, 64, 5, 5, 1, 2, 1, 1, False),       # 25 taps, channel-ordered k
 	(2, 64, 10, 10, 96, 3, 3, 1, 1, 1, 2, True),      # groups with channel-ordered k
+	(1, 32, 12, 224, 40, 3, 3, 1, 1, 1, 1, True),     # a 224-wide map: too wide for the halo kernel, per-tap gather
+	(1, 32, 9, 126, 40, 3, 3, 1, 1, 1, 1, True),      # the widest map the stride-1 halo kernel takes (halo of 386 rows)
+	(2, 40, 30, 31, 48, 3, 3, 1, 0, 1, 1, False),     # halo kernel without padding (output smaller than the input)
+	(2, 32, 11, 13, 32, 3, 2, 1, (1, 0), 1, 1, False),    # non-square filter, asymmetric padding per axis
 ]
 
 
