@@ -13,16 +13,20 @@
 // positions that are not real outputs (q >= Q or p >= P) are computed and dropped by the epilogue (7% of the rows of a
 // 55x55 map, 13% of 28x28, 23% of 14x14).  Accumulators are double-buffered in TMEM, one persistent CTA per SM.
 //
-// Warp roles: 15 gather warps | 1 TMA-issuing warp | 1 MMA-issuing warp | 4 epilogue warps (672 threads).
+// Warp roles: 16 gather warps | 1 TMA-issuing warp | 1 MMA-issuing warp | 4 epilogue warps (704 threads; the register file is
+// allocated in units of 4 warps, so 22 warps cost what 21 do).  The gather warps software-pipeline their loads: the halo of
+// stage s+1 is in flight while the halo of stage s is rounded and stored.
 #include "pz_umma.cuh"
 
 namespace pzumma {
 
-constexpr int NGATHER_WARPS = 15;
+constexpr int NGATHER_WARPS = 16;
 constexpr int NGATHER = NGATHER_WARPS * 32;
+constexpr int NTHREADS_HALO = NGATHER + 64 + NEPI_WARPS * 32;
+constexpr int PIPE_TASKS = 4;        // chunk tasks per thread whose loads are double-buffered in registers (halo <= 256 rows)
 constexpr int HALO_STAGES = 2;
 constexpr int MAX_BSTAGES = 8;
-constexpr int MAX_TASKS = 8;         // halo chunk tasks per gather thread and stage (8 * 480 / 8 = 480 halo rows at most)
+constexpr int MAX_TASKS = 8;         // halo chunk tasks per gather thread and stage (8 * 512 / 8 = 512 halo rows at most)
 
 struct HaloParams {
 	const void* x;               // source tensor (N, C_total, H, W): x for fprop, dy for dgrad
@@ -49,7 +53,7 @@ struct HaloParams {
 __device__ __forceinline__ uint64_t make_smem_desc_rows(uint32_t halo, uint32_t rows) { return make_smem_desc(halo + rows * 128u); }
 
 template <int BN, bool H16>
-__global__ void __launch_bounds__(NTHREADS, 1) umma_halo_kernel(const __grid_constant__ HaloParams p, const __grid_constant__ CUtensorMap tmapB)
+__global__ void __launch_bounds__(NTHREADS_HALO, 1) umma_halo_kernel(const __grid_constant__ HaloParams p, const __grid_constant__ CUtensorMap tmapB)
 {
 	using EL = typename std::conditional<H16, uint16_t, float>::type;
 	constexpr int BKE = H16 ? BK16 : BK;
@@ -111,6 +115,96 @@ __global__ void __launch_bounds__(NTHREADS, 1) umma_halo_kernel(const __grid_con
 		const int ntasks = rows_pad * 8;
 		int hs = 0;
 		uint32_t hphase = 0;
+
+		if (ntasks <= PIPE_TASKS * NGATHER) {
+			// ---- pipelined gather (halos of at most 256 rows): two register buffers, loads of the next stage in flight
+			uint32_t saddr[PIPE_TASKS];
+			#pragma unroll
+			for (int i = 0; i < PIPE_TASKS; i++) {
+				const int task = t + i * NGATHER;
+				saddr[i] = 0xffffffffu;
+				if (task < ntasks) {
+					const int chunk = task / rows_pad, row = task - chunk * rows_pad;
+					if (row < p.halo_rows) saddr[i] = (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4));
+					else saddr[i] = 0xfffffff0u | (uint32_t)chunk;      // nothing to store; keeps the chunk for the decode below
+				}
+			}
+			// load cursor
+			int lwork = blockIdx.x, lcb = 0;
+			int rowoff[PIPE_TASKS];
+			const EL* __restrict__ lbase = (const EL*)p.x;
+			auto issue = [&](uint32_t (&v)[PIPE_TASKS][4]) {
+				if (lcb == 0) {
+					int m_tile, n_tile, group;
+					decode(lwork, m_tile, n_tile, group);
+					lbase = (const EL*)p.x + (long long)group * p.group_stride;
+					#pragma unroll
+					for (int i = 0; i < PIPE_TASKS; i++) {
+						const int task = t + i * NGATHER;
+						rowoff[i] = -1;
+						if (task < ntasks) {
+							const int row = task % rows_pad;
+							const long long pm = (long long)m_tile * BM + row;
+							if (row < p.halo_rows && pm < p.rows_total) {
+								const uint32_t n = fdiv((uint32_t)pm, p.ldiv);
+								const uint32_t rem = (uint32_t)pm - n * p.ldiv.d;
+								const uint32_t hp = fdiv(rem, p.wpdiv);
+								const int h = (int)hp - p.ph, w = (int)(rem - hp * p.wpdiv.d) - p.pw;
+								if ((unsigned)h < (unsigned)p.H && (unsigned)w < (unsigned)p.W)
+									rowoff[i] = (int)((long long)n * p.img_stride + (long long)h * p.W + w);
+							}
+						}
+					}
+				}
+				const int cbase = lcb * BKE;
+				#pragma unroll
+				for (int i = 0; i < PIPE_TASKS; i++) {
+					const uint32_t sa = saddr[i];
+					const int chunk = sa >= 0xfffffff0u ? (int)(sa & 7u) : (int)(((sa >> 4) ^ (sa >> 7)) & 7u);
+					const int c0 = cbase + chunk * CH;
+					const bool ok = rowoff[i] >= 0;
+					const EL* __restrict__ src = lbase + (rowoff[i] + (long long)c0 * p.chan_stride);
+					#pragma unroll
+					for (int e = 0; e < 4; e++) {
+						if (H16) {
+							const uint32_t lo = (ok && c0 + 2 * e < p.chans) ? (uint32_t)__ldg(src + (long long)(2 * e) * p.chan_stride) : 0u;
+							const uint32_t hi = (ok && c0 + 2 * e + 1 < p.chans) ? (uint32_t)__ldg(src + (long long)(2 * e + 1) * p.chan_stride) : 0u;
+							v[i][e] = lo | (hi << 16);
+						} else {
+							// raw bits; rounded to tf32 when stored
+							v[i][e] = (ok && c0 + e < p.chans) ? __float_as_uint(__ldg(reinterpret_cast<const float*>(src) + (long long)e * p.chan_stride)) : 0u;
+						}
+					}
+				}
+				if (++lcb == p.cblocks) { lcb = 0; lwork += gridDim.x; }
+			};
+			auto commit = [&](const uint32_t (&v)[PIPE_TASKS][4]) {
+				mbar_wait(bar_hempty + 8 * hs, hphase ^ 1);
+				const uint32_t halo = halo0 + hs * p.halo_bytes;
+				#pragma unroll
+				for (int i = 0; i < PIPE_TASKS; i++)
+					if (saddr[i] < 0xfffffff0u) {
+						if (H16) sts128(halo + saddr[i], v[i][0], v[i][1], v[i][2], v[i][3]);
+						else sts128(halo + saddr[i], v[i][0] + 0x1000u, v[i][1] + 0x1000u, v[i][2] + 0x1000u, v[i][3] + 0x1000u);   // to_tf32
+					}
+				fence_async_smem();
+				__syncwarp();
+				if (lane == 0) mbar_arrive(bar_hfull + 8 * hs);
+				if (++hs == HALO_STAGES) { hs = 0; hphase ^= 1; }
+			};
+			uint32_t va[PIPE_TASKS][4], vb[PIPE_TASKS][4];
+			int pending = 0;                              // stages loaded but not yet stored
+			if (lwork < total_work) { issue(va); pending++; }
+			while (pending > 0) {
+				if (lwork < total_work) { issue(vb); pending++; }
+				commit(va);
+				pending--;
+				if (pending == 0) break;
+				if (lwork < total_work) { issue(va); pending++; }
+				commit(vb);
+				pending--;
+			}
+		} else
 		for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
 			int m_tile, n_tile, group;
 			decode(work, m_tile, n_tile, group);
@@ -300,7 +394,7 @@ static int launch_halo_inst(const HaloParams& p, const CUtensorMap& tmap, int gr
 	{
 		const bool hbm = p.alg_bytes > 0.0 && p.alg_flops / p.alg_bytes < kPzRidgeFlopPerByte;
 		PzProfScope prof(hbm ? PZ_PROF_GEMM_HBM : PZ_PROF_GEMM, stream, p.alg_flops, p.alg_bytes);
-		kern<<<grid, NTHREADS, smem, stream>>>(p, tmap);
+		kern<<<grid, NTHREADS_HALO, smem, stream>>>(p, tmap);
 	}
 	pz_count_launch(1);
 	PZ_LAUNCH_CHECK();
