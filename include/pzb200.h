@@ -125,6 +125,8 @@ int pz_scale_shift(int dtype, void* out, const void* in, float a, float b, int64
 int pz_mul(int dtype, void* out, const void* a, const void* b, int64_t n, void* stream);    /* mulKer :1047-1071 */
 int pz_add2(int dtype, void* out, const void* a, const void* b, int64_t n, void* stream);   /* Add.py:15-23 as one pass */
 int pz_cast(int dst_dtype, void* dst, int src_dtype, const void* src, int64_t n, void* stream); /* GPUArray.py astype */
+/* dst[r][i] += src[r][i], pitched rows (3-d transposed convolution: scatter-add of per-slice gradients) */
+int pz_add2d(int dtype, void* dst, int64_t dpitch, const void* src, int64_t spitch, int64_t width, int64_t rows, void* stream);
 int pz_fill64(void* ptr, uint64_t value, int64_t count, void* stream);                      /* GPUArray.py:167-180 8-byte fill */
 /* mom = momRate*mom + learnRate*grad; param += mom  (ElementWise.py:771-800 classicMomSGD) */
 int pz_sgd_momentum(int dtype, void* param, const void* grad, void* mom, float learn_rate, float mom_rate,

@@ -533,3 +533,121 @@ def rnn_backward(x, params, out, dy, mode="tanh", h0=None, dtype=np.float64):
 		dx[t] = d @ p["wi"]
 		dhn = d @ p["ri"]
 	return dx, dp
+
+
+# ================================================================================================ 3-d convolution / pooling
+def _triple(v):
+	return (v, v, v) if isinstance(v, (int, np.integer)) else tuple(v)
+
+
+def _windows3d(xp, fsize, stride, dilation, outshape):
+	"""View (N, C, Do, P, Q, T, R, S) of the padded input: element [.., do, p, q, t, r, s] = xp[.., do*sd + t*dd, ...]."""
+	N, C = xp.shape[:2]
+	sN, sC, sD, sH, sW = xp.strides
+	(T, R, S), (sd, sh, sw), (dd, dh, dw) = fsize, stride, dilation
+	Do, P, Q = outshape
+	return np.lib.stride_tricks.as_strided(
+		xp, shape=(N, C, Do, P, Q, T, R, S), strides=(sN, sC, sD * sd, sH * sh, sW * sw, sD * dd, sH * dh, sW * dw), writeable=False)
+
+
+def conv3d(x, w, bias=None, stride=1, pad=0, dilation=1, groups=1, dtype=np.float64):
+	"""y[n,k,d,p,q] = sum_{c,t,r,s} x[n, g*Cg+c, d*sd-pd+t*dd, ...] * w[k,c,t,r,s] (+ b[k]); out size as CuDnn.c:242-266 with
+	nd = 3; the reference pins it with a host loop in Cuda/Wrappers/CuDnn.py:106-144."""
+	x, w = np.asarray(x, dtype), np.asarray(w, dtype)
+	stride, pad, dilation = _triple(stride), _triple(pad), _triple(dilation)
+	N, C = x.shape[:2]
+	K, Cg = w.shape[:2]
+	fsize = w.shape[2:]
+	outshape = tuple(conv_out_size(x.shape[2 + i], fsize[i], stride[i], pad[i], dilation[i]) for i in range(3))
+	xp = np.pad(x, ((0, 0), (0, 0)) + tuple((p, p) for p in pad))
+	win = _windows3d(xp, fsize, stride, dilation, outshape)
+	Kg = K // groups
+	y = np.empty((N, K) + outshape, dtype)
+	for g in range(groups):
+		y[:, g * Kg:(g + 1) * Kg] = np.einsum("ncdpqtrs,kctrs->nkdpq", win[:, g * Cg:(g + 1) * Cg], w[g * Kg:(g + 1) * Kg], optimize=True)
+	if bias is not None:
+		y += np.asarray(bias, dtype).reshape(1, K, 1, 1, 1)
+	return y
+
+
+def conv3d_bwd_params(x, dy, wshape, stride=1, pad=0, dilation=1, groups=1, dtype=np.float64):
+	x, dy = np.asarray(x, dtype), np.asarray(dy, dtype)
+	stride, pad, dilation = _triple(stride), _triple(pad), _triple(dilation)
+	K, Cg = wshape[:2]
+	fsize = tuple(wshape[2:])
+	xp = np.pad(x, ((0, 0), (0, 0)) + tuple((p, p) for p in pad))
+	win = _windows3d(xp, fsize, stride, dilation, dy.shape[2:])
+	Kg = K // groups
+	dw = np.empty(wshape, dtype)
+	for g in range(groups):
+		dw[g * Kg:(g + 1) * Kg] = np.einsum("ncdpqtrs,nkdpq->kctrs", win[:, g * Cg:(g + 1) * Cg], dy[:, g * Kg:(g + 1) * Kg], optimize=True)
+	return dw, dy.sum(axis=(0, 2, 3, 4))
+
+
+def conv3d_bwd_data(dy, w, inshape, stride=1, pad=0, dilation=1, groups=1, dtype=np.float64):
+	dy, w = np.asarray(dy, dtype), np.asarray(w, dtype)
+	stride, pad, dilation = _triple(stride), _triple(pad), _triple(dilation)
+	N, C, D, H, W = inshape
+	K, Cg, T, R, S = w.shape
+	Kg = K // groups
+	Do, P, Q = dy.shape[2:]
+	dxp = np.zeros((N, C, D + 2 * pad[0], H + 2 * pad[1], W + 2 * pad[2]), dtype)
+	for g in range(groups):
+		dyg, wg = dy[:, g * Kg:(g + 1) * Kg], w[g * Kg:(g + 1) * Kg]
+		for t in range(T):
+			for r in range(R):
+				for s in range(S):
+					contrib = np.einsum("nkdpq,kc->ncdpq", dyg, wg[:, :, t, r, s], optimize=True)
+					d0, h0, w0 = t * dilation[0], r * dilation[1], s * dilation[2]
+					dxp[:, g * Cg:(g + 1) * Cg, d0:d0 + Do * stride[0]:stride[0], h0:h0 + P * stride[1]:stride[1],
+						w0:w0 + Q * stride[2]:stride[2]] += contrib
+	return dxp[:, :, pad[0]:pad[0] + D, pad[1]:pad[1] + H, pad[2]:pad[2] + W]
+
+
+def pool3d(x, size=2, stride=2, pad=0, mode="max", dtype=np.float64):
+	"""(fd, fh, fw) pooling, out size (in + 2 pad - size) / stride + 1 (CuDnnPool.c:24-41 with nd = 3).  Returns (y, argmax) where
+	argmax is the flat in-volume index of the first maximum (row-major scan), -1 for the average modes."""
+	x = np.asarray(x, dtype)
+	size, stride, pad = _triple(size), _triple(stride), _triple(pad)
+	N, C, D, H, W = x.shape
+	out = tuple((x.shape[2 + i] + 2 * pad[i] - size[i]) // stride[i] + 1 for i in range(3))
+	y = np.zeros((N, C) + out, dtype)
+	arg = np.full((N, C) + out, -1, np.int64)
+	for do in range(out[0]):
+		d0, d1 = max(do * stride[0] - pad[0], 0), min(do * stride[0] - pad[0] + size[0], D)
+		for p in range(out[1]):
+			h0, h1 = max(p * stride[1] - pad[1], 0), min(p * stride[1] - pad[1] + size[1], H)
+			for q in range(out[2]):
+				w0, w1 = max(q * stride[2] - pad[2], 0), min(q * stride[2] - pad[2] + size[2], W)
+				box = x[:, :, d0:d1, h0:h1, w0:w1].reshape(N, C, -1)
+				if mode == "max":
+					idx = box.argmax(axis=2)
+					y[:, :, do, p, q] = np.take_along_axis(box, idx[..., None], axis=2)[..., 0]
+					bd, bh, bw = d1 - d0, h1 - h0, w1 - w0
+					arg[:, :, do, p, q] = ((d0 + idx // (bh * bw)) * H + h0 + (idx // bw) % bh) * W + w0 + idx % bw
+				else:
+					cnt = size[0] * size[1] * size[2] if mode == "avgWithPad" else box.shape[2]
+					y[:, :, do, p, q] = box.sum(axis=2) / cnt
+	return y, arg
+
+
+def pool3d_bwd(x, dy, size=2, stride=2, pad=0, mode="max", dtype=np.float64):
+	x, dy = np.asarray(x, dtype), np.asarray(dy, dtype)
+	size, stride, pad = _triple(size), _triple(stride), _triple(pad)
+	N, C, D, H, W = x.shape
+	dx = np.zeros_like(x)
+	_, arg = pool3d(x, size, stride, pad, mode, dtype)
+	out = dy.shape[2:]
+	flat = dx.reshape(N, C, -1)
+	for do in range(out[0]):
+		d0, d1 = max(do * stride[0] - pad[0], 0), min(do * stride[0] - pad[0] + size[0], D)
+		for p in range(out[1]):
+			h0, h1 = max(p * stride[1] - pad[1], 0), min(p * stride[1] - pad[1] + size[1], H)
+			for q in range(out[2]):
+				w0, w1 = max(q * stride[2] - pad[2], 0), min(q * stride[2] - pad[2] + size[2], W)
+				if mode == "max":
+					np.add.at(flat, (np.arange(N)[:, None], np.arange(C)[None, :], arg[:, :, do, p, q]), dy[:, :, do, p, q])
+				else:
+					cnt = size[0] * size[1] * size[2] if mode == "avgWithPad" else (d1 - d0) * (h1 - h0) * (w1 - w0)
+					dx[:, :, d0:d1, h0:h1, w0:w1] += (dy[:, :, do, p, q] / cnt)[:, :, None, None, None]
+	return dx

@@ -88,13 +88,29 @@ class DnnContext:
 	@staticmethod
 	def _check4d(ary, name):
 		_requireArray(ary, name)
-		if ary.ndim == 5:
-			raise NotImplementedError("3-d convolution / pooling is not implemented in the B200 backend yet")
 		if ary.ndim != 4:
 			raise ValueError("invalid %s gpuarray dims" % name)
 
+	@staticmethod
+	def _is3d(*arys):
+		"""5-d tensors take the 3-d decomposition of dnn3d.py (cuDNN descriptors are 4-d or 5-d, Libs.h:46-56)."""
+		for ary in arys:
+			_requireArray(ary, "tensor")
+		nd = {ary.ndim for ary in arys}
+		if nd == {5}:
+			return True
+		if 5 in nd:
+			raise ValueError("mixed 4-d / 5-d gpuarray dims")
+		return False
+
 	def convNd(self, data, W, bias=None, stride=1, pad=0, dilation=1, groups=1, algo=0, out=None, allocator=None):
 		"""reference: CuDnn_Context_pyConvNd, CuDnn.c:457-514 (out shape :242-266)"""
+		if self._is3d(data, W):
+			from . import dnn3d
+			if data.dtype != W.dtype:
+				raise ValueError("invalid W gpuarray data layout")
+			return dnn3d.conv3d(self, data, W, bias, _seq(stride, 3, 1, "stride"), _seq(pad, 3, 0, "pad"),
+								_seq(dilation, 3, 1, "dilation"), groups, out, allocator)
 		self._check4d(data, "data")
 		self._check4d(W, "W")
 		stride, pad, dilation = _seq(stride, 2, 1, "stride"), _seq(pad, 2, 0, "pad"), _seq(dilation, 2, 1, "dilation")
@@ -129,6 +145,12 @@ class DnnContext:
 	def convNdBackwardData(self, grad, W, bias=None, data=None, stride=1, pad=0, dilation=1, postpad=0, groups=1,
 						   algo=0, out=None, allocator=None):
 		"""reference: CuDnn_Context_pyConvNdBackwardData, CuDnn.c:579-649 (in shape :269-322)"""
+		if self._is3d(grad, W):
+			from . import dnn3d
+			if grad.dtype != W.dtype or grad.shape[1] != W.shape[0]:
+				raise ValueError("invalid W gpuarray data layout")
+			return dnn3d.conv3dBackwardData(self, grad, W, bias, data, _seq(stride, 3, 1, "stride"), _seq(pad, 3, 0, "pad"),
+											_seq(dilation, 3, 1, "dilation"), _seq(postpad, 3, 0, "postpad"), groups, out, allocator)
 		self._check4d(grad, "grad")
 		self._check4d(W, "W")
 		stride, pad, dilation = _seq(stride, 2, 1, "stride"), _seq(pad, 2, 0, "pad"), _seq(dilation, 2, 1, "dilation")
@@ -171,6 +193,13 @@ class DnnContext:
 							 wgrad=None, bgrad=None, scale=1.0, momentum=0.0, algo=0, allocator=None):
 		"""reference: CuDnn_Context_pyConvNdBackwardParams, CuDnn.c:722-800; wgrad / bgrad accumulate IN PLACE with
 		alpha = scale, beta = momentum (:682-685, :388)"""
+		if self._is3d(data, grad, W):
+			from . import dnn3d
+			if data.dtype != grad.dtype or data.dtype != W.dtype:
+				raise ValueError("invalid gpuarray data layout")
+			return dnn3d.conv3dBackwardParams(self, data, grad, W, _seq(stride, 3, 1, "stride"), _seq(pad, 3, 0, "pad"),
+											  _seq(dilation, 3, 1, "dilation"), groups, withbias, deconv, wgrad, bgrad, scale, momentum,
+											  allocator)
 		self._check4d(data, "data")
 		self._check4d(grad, "grad")
 		self._check4d(W, "W")
@@ -207,6 +236,10 @@ class DnnContext:
 	# ------------------------------------------------------------------------------------------ pooling
 	def poolNd(self, data, size=2, stride=2, pad=0, mode=0, out=None, allocator=None):
 		"""reference: CuDnn_Context_pyPoolNd, CuDnnPool.c:102-152"""
+		if self._is3d(data):
+			from . import dnn3d
+			return dnn3d.pool3d(self, data, _seq(size, 3, 2, "size"), _seq(stride, 3, 2, "stride"), _seq(pad, 3, 0, "pad"), mode, out,
+								allocator)
 		self._check4d(data, "data")
 		size, stride, pad = _seq(size, 2, 2, "size"), _seq(stride, 2, 2, "stride"), _seq(pad, 2, 0, "pad")
 
@@ -226,6 +259,10 @@ class DnnContext:
 
 	def poolNdBackward(self, grad, indata, outdata, size=2, stride=2, pad=0, mode=0, out=None, allocator=None):
 		"""reference: CuDnn_Context_pyPoolNdBackward, CuDnnPool.c:197-245"""
+		if self._is3d(grad, indata, outdata):
+			from . import dnn3d
+			return dnn3d.pool3dBackward(self, grad, indata, outdata, _seq(size, 3, 2, "size"), _seq(stride, 3, 2, "stride"),
+										_seq(pad, 3, 0, "pad"), mode, out, allocator)
 		self._check4d(grad, "grad")
 		self._check4d(indata, "indata")
 		self._check4d(outdata, "outdata")

@@ -289,6 +289,17 @@ __global__ void __launch_bounds__(1024) minmax_kernel(const T* __restrict__ in, 
 
 }  // namespace
 
+template <typename T>
+__global__ void add2d_kernel(T* __restrict__ dst, int64_t dpitch, const T* __restrict__ src, int64_t spitch, int64_t width, int64_t rows)
+{
+	const int64_t total = width * rows;
+	for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+		const int64_t r = i / width, c = i - r * width;
+		T* d = dst + r * dpitch + c;
+		*d = (T)((float)*d + (float)src[r * spitch + c]);
+	}
+}
+
 extern "C" {
 
 int pz_act_fwd(int kind, int dtype, void* out, const void* in, int64_t n, float a, float b, void* stream)
@@ -353,6 +364,25 @@ int pz_cast(int dd, void* dst, int sd, const void* src, int64_t n, void* stream)
 #undef PZ_CAST_CASE
 	pz_set_error(PZ_ERR_UNSUPPORTED, "unsupported cast %d -> %d", sd, dd);
 	return PZ_ERR_UNSUPPORTED;
+}
+
+// dst[r][i] += src[r][i] over `rows` rows of `width` elements with independent row pitches (in elements): the scatter-add of the
+// 3-d transposed convolution's per-slice input gradients into dx[n, c, d0:d0+T] (dnn3d.py)
+int pz_add2d(int dtype, void* dst, int64_t dpitch, const void* src, int64_t spitch, int64_t width, int64_t rows, void* stream)
+{
+	if (width <= 0 || rows <= 0) return PZ_OK;
+	PZ_REQUIRE(width * rows < (1ll << 40), "add2d: too large");
+	int64_t blocks = pz_cdiv(width * rows, 256);
+	if (blocks > (int64_t)pz_num_sms() * 16) blocks = (int64_t)pz_num_sms() * 16;
+	switch (dtype) {
+		case PZ_F32: add2d_kernel<float><<<(unsigned)blocks, 256, 0, pz_stream(stream)>>>((float*)dst, dpitch, (const float*)src, spitch, width, rows); break;
+		case PZ_F16: add2d_kernel<__half><<<(unsigned)blocks, 256, 0, pz_stream(stream)>>>((__half*)dst, dpitch, (const __half*)src, spitch, width, rows); break;
+		case PZ_BF16: add2d_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, pz_stream(stream)>>>((__nv_bfloat16*)dst, dpitch, (const __nv_bfloat16*)src, spitch, width, rows); break;
+		default: pz_set_error(PZ_ERR_UNSUPPORTED, "unsupported dtype %d", dtype); return PZ_ERR_UNSUPPORTED;
+	}
+	pz_count_launch(1);
+	PZ_LAUNCH_CHECK();
+	return PZ_OK;
 }
 
 int pz_reduce_minmax(int dtype, const void* in, int64_t n, int want_max, void* out, void* stream)

@@ -22,7 +22,9 @@ __global__ void __launch_bounds__(256) addvec_kernel(T* __restrict__ out, const 
 	const int64_t step = (int64_t)gridDim.x * blockDim.x;
 	for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += step) {
 		int64_t x = i % cols, t = i / cols, y = t % rows, z = t / rows;
-		int64_t vi = mode == 0 ? z * cols + x : (mode == 1 ? z * cols + x % vecdim : z * rows + y);
+		// mode 0: vec[z][x]; 1: vec[z][x % vecdim]; 2: vec[z][y]; 3: vec[y % vecdim] (one vector tiled down the rows, e.g. a
+		// per-channel bias over an (N*C, S) view of an N-d tensor)
+		int64_t vi = mode == 0 ? z * cols + x : (mode == 1 ? z * cols + x % vecdim : (mode == 2 ? z * rows + y : y % vecdim));
 		stf<T>(out, i, ldf<T>(mat, i) + ldf<T>(vec, vi));
 	}
 }
@@ -174,7 +176,12 @@ int pz_addvec2mat(int dtype, void* out, const void* mat, const void* vec, int64_
 					   (long long)cols, (long long)vecdim);
 			mode = 1;
 		}
-	} else mode = 2;
+	} else if (vecdim == rows || vecdim <= 0) mode = 2;
+	else {
+		PZ_REQUIRE(rows % vecdim == 0, "addvec2mat: matrix height %lld is not a multiple of the vector length %lld", (long long)rows,
+				   (long long)vecdim);
+		mode = 3;
+	}
 	PZ_DISPATCH_FLOAT(dtype, addvec_launch<T>(out, mat, vec, z, rows, cols, mode, vecdim, stream));
 }
 

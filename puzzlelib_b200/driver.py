@@ -136,6 +136,7 @@ _SIGNATURES = {
 	"pz_lstm_cell_bwd": [_P, _P, _P, _P, _P, _P, _P, c_int64, c_int64, c_int, _P],
 	"pz_rnn_cell_fwd": [_P, _P, _P, c_int64, c_int64, c_int, _P],
 	"pz_rnn_cell_bwd": [_P, _P, _P, _P, c_int64, c_int, _P],
+	"pz_add2d": [c_int, _P, c_int64, _P, c_int64, c_int64, c_int64, _P],
 	"pz_gemm": [c_int, _P, _P, _P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int, c_int, c_float, c_float,
 				_P, _P],
 	"pz_conv2d_fprop": [c_int, POINTER(Conv2dDesc), _P, _P, _P, _P, _P],

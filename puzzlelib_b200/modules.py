@@ -406,6 +406,38 @@ class Conv2D(ConvND):
 		return batchsize, inmaps * self.groups, inh, inw
 
 
+class Conv3D(ConvND):
+	"""reference: Modules/Conv3D.py (ConvND with nd = 3; the backend folds the filter depth into the channels, dnn3d.py)"""
+
+	def __init__(self, inmaps, outmaps, size, stride=1, pad=0, dilation=1, wscale=1.0, useBias=True, name=None,
+				 initscheme=None, empty=False, groups=1):
+		super().__init__(3, inmaps, outmaps, size, stride, pad, dilation, wscale, useBias, name, initscheme, empty, groups)
+
+	def checkDataShape(self, shape):
+		if len(shape) != 5:
+			raise ModuleError("Data must be 5d tensor")
+		if shape[1] != self.W.shape[1] * self.groups:
+			raise ModuleError("Data has %d maps (expected: %d)" % (shape[1], self.W.shape[1] * self.groups))
+		for i, name in enumerate(("depth", "height", "width")):
+			ext, extf = shape[2 + i] + 2 * self.pad[i], self.dilation[i] * (self.W.shape[2 + i] - 1) + 1
+			if ext < extf:
+				raise ModuleError("Data maps %s is too small (got %d, expected at least %d)" % (name, ext, extf))
+
+	def dataShapeFrom(self, shape):
+		return (shape[0], self.W.shape[0]) + tuple(
+			(shape[2 + i] + 2 * self.pad[i] - self.dilation[i] * (self.W.shape[2 + i] - 1) - 1) // self.stride[i] + 1 for i in range(3))
+
+	def checkGradShape(self, shape):
+		if len(shape) != 5:
+			raise ModuleError("Grad must be 5d tensor")
+		if shape[1] != self.W.shape[0]:
+			raise ModuleError("Grad has %d maps (expected: %d)" % (shape[1], self.W.shape[0]))
+
+	def gradShapeFrom(self, shape):
+		return (shape[0], self.W.shape[1] * self.groups) + tuple(
+			(shape[2 + i] - 1) * self.stride[i] + self.dilation[i] * (self.W.shape[2 + i] - 1) - 2 * self.pad[i] + 1 for i in range(3))
+
+
 class Conv1D(ConvND):
 	"""1-d convolution run as a 2-d one with H = 1 (reference: Modules/Conv1D.py:14-35)"""
 
@@ -1032,6 +1064,56 @@ class AvgPool2D(Pool2D):
 	def updateGrad(self, grad):
 		self.grad = Dnn.poolNdBackward(self.inData, self.data, grad, self.workspace, size=self.size, stride=self.stride,
 									   pad=self.pad, mode=self.mode)
+
+
+class Pool3D(Module):
+	"""reference: Modules/Pool3D.py (the backend pools the slices, then the depth axis: dnn3d.py)"""
+
+	def __init__(self, size=2, stride=2, pad=0, name=None):
+		super().__init__(name)
+		self.gradUsesOutData = True
+		self.size, self.stride, self.pad = self.repeat(size, 3), self.repeat(stride, 3), self.repeat(pad, 3)
+		self.workspace = None
+		self.mode = PoolMode.max
+
+	def updateData(self, data):
+		self.data, self.workspace = Dnn.poolNd(data, size=self.size, stride=self.stride, pad=self.pad, mode=self.mode,
+											   test=not self.train)
+
+	def updateGrad(self, grad):
+		self.grad = Dnn.poolNdBackward(self.inData, self.data, grad, self.workspace, size=self.size, stride=self.stride,
+									   pad=self.pad, mode=self.mode)
+
+	def dataShapeFrom(self, shape):
+		return tuple(shape[:2]) + tuple((shape[2 + i] + 2 * self.pad[i] - self.size[i]) // self.stride[i] + 1 for i in range(3))
+
+	def checkDataShape(self, shape):
+		if len(shape) != 5:
+			raise ModuleError("Data must be 5d tensor")
+		for i in range(3):
+			if shape[2 + i] + 2 * self.pad[i] < self.size[i]:
+				raise ModuleError("Data maps are too small on dim #%d" % (i + 1))
+
+	def gradShapeFrom(self, shape):
+		return tuple(shape[:2]) + tuple((shape[2 + i] - 1) * self.stride[i] - 2 * self.pad[i] + self.size[i] for i in range(3))
+
+	def checkGradShape(self, shape):
+		if len(shape) != 5:
+			raise ModuleError("Grad must be 5d tensor")
+
+	def reset(self):
+		super().reset()
+		self.workspace = None
+
+
+class MaxPool3D(Pool3D):
+	pass
+
+
+class AvgPool3D(Pool3D):
+	def __init__(self, size=2, stride=2, pad=0, includePad=True, name=None):
+		super().__init__(size, stride, pad, name)
+		self.mode = PoolMode.avgWithPad if includePad else PoolMode.avgNoPad
 
 
 class MaxUnpool2D(Module):

@@ -652,3 +652,77 @@ def test_rnn_module_last_step_and_sequences(bnd):
 
 	with pytest.raises(NotImplementedError):
 		M.RNN(insz, H, mode="gru")
+
+
+# ================================================================================================ 3-d convolution / pooling
+CONV3D_CASES = [
+	# N, C, D, H, W, K, (T, R, S), stride, pad, dilation, groups, bias
+	(2, 4, 6, 9, 9, 8, (3, 3, 3), 1, 1, 1, 1, True),                  # reference test geometry (Cuda/Wrappers/CuDnn.py:106-144)
+	(2, 32, 5, 12, 10, 48, (2, 3, 3), (1, 2, 1), (0, 1, 1), 1, 1, False),
+	(1, 6, 7, 8, 8, 4, (3, 1, 2), (2, 1, 1), (1, 0, 0), (2, 1, 1), 2, True),     # depth stride + depth dilation + groups
+]
+
+
+@pytest.mark.parametrize("case", CONV3D_CASES)
+def test_conv3d_fwd_bwd(bnd, case):
+	N, C, D, H, W, K, fsize, stride, pad, dil, groups, bias = case
+	rng = np.random.RandomState(abs(hash(case)) % (2 ** 31))
+	x = rng.randn(N, C, D, H, W).astype(np.float32)
+	w = rng.randn(K, C // groups, *fsize).astype(np.float32)
+	b = rng.randn(K).astype(np.float32) if bias else None
+	y = ops.conv3d(x, w, b, stride, pad, dil, groups)
+	dy = rng.randn(*y.shape).astype(np.float32)
+
+	gx, gw = G(bnd, x), G(bnd, w)
+	out = bnd.dnn.convNd(gx, gw, G(bnd, b) if bias else None, stride, pad, dil, groups, allocator=bnd.memoryPool)
+	assert out.shape == y.shape
+	assert relerr(out.get(), y) < REL_TC
+
+	dgrad = bnd.dnn.convNdBackwardData(G(bnd, dy), gw, None, gx, stride, pad, dil, None, groups, allocator=bnd.memoryPool)
+	assert relerr(dgrad.get(), ops.conv3d_bwd_data(dy, w, x.shape, stride, pad, dil, groups)) < REL_TC
+
+	w0 = rng.randn(*w.shape).astype(np.float32)
+	wgrad, bgrad = G(bnd, w0), G(bnd, np.zeros(K, np.float32))
+	bnd.dnn.convNdBackwardParams(gx, G(bnd, dy), gw, stride, pad, dil, groups, True, False, wgrad, bgrad, 0.5, 0.25,
+								 allocator=bnd.memoryPool)
+	dw, db = ops.conv3d_bwd_params(x, dy, w.shape, stride, pad, dil, groups)
+	assert relerr(wgrad.get(), 0.5 * dw + 0.25 * w0) < REL_TC
+	assert relerr(bgrad.get(), 0.5 * db) < 1e-5
+
+
+@pytest.mark.parametrize("case", [((2, 3, 6, 8, 8), 2, 2, 0), ((2, 5, 7, 9, 10), (3, 2, 3), (2, 1, 2), (1, 0, 1)), ((1, 4, 5, 6, 6), 3, 1, 1)])
+@pytest.mark.parametrize("mode", ["max", "avgWithPad", "avgNoPad"])
+def test_pool3d(bnd, case, mode):
+	# reference test: Cuda/Wrappers/CuDnn.py:414-451 (3-d max pooling with padding, forward + backward)
+	shape, size, stride, pad = case
+	rng = np.random.RandomState(sum(shape))
+	x = rng.randn(*shape).astype(np.float32)
+	code = {"max": bnd.PoolMode.max, "avgWithPad": bnd.PoolMode.avgWithPad, "avgNoPad": bnd.PoolMode.avgNoPad}[mode].value
+	want, _ = ops.pool3d(x, size, stride, pad, mode)
+	gx = G(bnd, x)
+	out = bnd.dnn.poolNd(gx, size, stride, pad, code, allocator=bnd.memoryPool)
+	assert out.shape == want.shape
+	assert relerr(out.get(), want) < 1e-6
+	dy = rng.randn(*want.shape).astype(np.float32)
+	dx = bnd.dnn.poolNdBackward(G(bnd, dy), gx, out, size, stride, pad, code, allocator=bnd.memoryPool)
+	assert relerr(dx.get(), ops.pool3d_bwd(x, dy, size, stride, pad, mode)) < 1e-6
+
+
+def test_conv3d_pool3d_modules(bnd):
+	from puzzlelib_b200 import modules as M
+	np.random.seed(4)
+	rng = np.random.RandomState(4)
+	net = M.Sequential()
+	net.append(M.Conv3D(3, 8, 3, pad=1, initscheme="he")).append(M.MaxPool3D(2, 2)).append(M.AvgPool3D(2, 1, includePad=False))
+	x = rng.randn(2, 3, 6, 8, 8).astype(np.float32)
+	out = net(M.gpuarray.to_gpu(x))
+	conv = net.graph[0]
+	y = ops.conv3d(x, conv.W.get(), conv.b.get().ravel(), 1, 1, 1)
+	p1, _ = ops.pool3d(y, 2, 2, 0, "max")
+	p2, _ = ops.pool3d(p1, 2, 1, 0, "avgNoPad")
+	assert out.shape == p2.shape and relerr(out.get(), p2) < REL_TC
+	g = rng.randn(*p2.shape).astype(np.float32)
+	net.backward(M.gpuarray.to_gpu(g))
+	d1 = ops.pool3d_bwd(p1, g, 2, 1, 0, "avgNoPad")
+	d0 = ops.pool3d_bwd(y, d1, 2, 2, 0, "max")
+	assert relerr(net.grad.get(), ops.conv3d_bwd_data(d0, conv.W.get(), x.shape, 1, 1, 1)) < REL_TC
