@@ -227,6 +227,11 @@ int pz_lstm_cell_fwd(float* gates, const float* bw, const float* br, const float
                      int64_t H, void* stream);
 int pz_lstm_cell_bwd(const float* dy, const float* dh_next, float* dc_io, const float* acts, const float* c, const float* c_prev,
                      float* dgates, int64_t B, int64_t H, int first, void* stream);
+/* GRU, gate order r, i, h (Cuda/Backend.py:309-350 linear layers 0..2; formulas pinned by CuDnnRnn.py:303-352) */
+int pz_gru_cell_fwd(float* gx, float* gh, const float* bw, const float* br, const float* h_prev, float* h_out, int64_t B, int64_t H,
+                    void* stream);
+int pz_gru_cell_bwd(const float* dy, const float* dh_next, const float* acts, const float* gh, const float* h_prev, float* dgx,
+                    float* dgh, float* dh_carry, int64_t B, int64_t H, void* stream);
 int pz_rnn_cell_fwd(float* h, const float* bw, const float* br, int64_t B, int64_t H, int mode, void* stream);
 int pz_rnn_cell_bwd(const float* dy, const float* dh_next, const float* h, float* dpre, int64_t n, int mode, void* stream);
 

@@ -447,7 +447,7 @@ def _sigmoid(x):
 	return 1.0 / (1.0 + np.exp(-x))
 
 
-def lstm_forward(x, params, h0=None, c0=None, dtype=np.float64):
+def lstm_forward(x, params, h0=None, c0=None, dtype=np.float64, reverse=False):
 	"""One uni-directional LSTM layer.  Follows the reference's own host loop (Cuda/Wrappers/CuDnnRnn.py:178-236): gates
 	i, f, o sigmoid, candidate c tanh; c_t = f*c_{t-1} + i*g; h_t = o*tanh(c_t); double bias bw* + br*.
 	x (T, B, in); params: dict wi wf wc wo (H, in), ri rf rc ro (H, H), bw*/br* (H,).  Returns (out (T,B,H), cache)."""
@@ -458,17 +458,18 @@ def lstm_forward(x, params, h0=None, c0=None, dtype=np.float64):
 	h = np.zeros((B, H), dtype) if h0 is None else np.asarray(h0, dtype)
 	c = np.zeros((B, H), dtype) if c0 is None else np.asarray(c0, dtype)
 	out = np.empty((T, B, H), dtype)
-	cache = {"i": [], "f": [], "g": [], "o": [], "c": [], "hprev": [], "cprev": []}
-	for t in range(T):
+	cache = {k: [None] * T for k in ("i", "f", "g", "o", "c", "hprev", "cprev")}
+	cache["reverse"] = reverse
+	for t in (range(T - 1, -1, -1) if reverse else range(T)):
 		pre = {g: x[t] @ p["w" + g].T + h @ p["r" + g].T + p["bw" + g] + p["br" + g] for g in "ifco"}
 		i, f, o, g = _sigmoid(pre["i"]), _sigmoid(pre["f"]), _sigmoid(pre["o"]), np.tanh(pre["c"])
-		cache["hprev"].append(h)
-		cache["cprev"].append(c)
+		cache["hprev"][t] = h
+		cache["cprev"][t] = c
 		c = f * c + i * g
 		h = o * np.tanh(c)
 		out[t] = h
 		for k, v in (("i", i), ("f", f), ("g", g), ("o", o), ("c", c)):
-			cache[k].append(v)
+			cache[k][t] = v
 	return out, cache
 
 
@@ -481,7 +482,7 @@ def lstm_backward(x, params, cache, dy, dtype=np.float64):
 	dp = {k: np.zeros_like(v) for k, v in p.items()}
 	dx = np.zeros((T, B, insz), dtype)
 	dhn, dcn = np.zeros((B, H), dtype), np.zeros((B, H), dtype)
-	for t in range(T - 1, -1, -1):
+	for t in (range(T) if cache.get("reverse") else range(T - 1, -1, -1)):
 		i, f, g, o, c = (cache[k][t] for k in ("i", "f", "g", "o", "c"))
 		hprev, cprev = cache["hprev"][t], cache["cprev"][t]
 		dh = dy[t] + dhn
@@ -532,6 +533,54 @@ def rnn_backward(x, params, out, dy, mode="tanh", h0=None, dtype=np.float64):
 		dp["bri"] += d.sum(axis=0)
 		dx[t] = d @ p["wi"]
 		dhn = d @ p["ri"]
+	return dx, dp
+
+
+def gru_forward(x, params, h0=None, reverse=False, dtype=np.float64):
+	"""One GRU layer direction in cuDNN's formulation (reference host loop Cuda/Wrappers/CuDnnRnn.py:303-352):
+	r = sigm(wr x + rr h + bwr + brr), i = sigm(wi x + ri h + bwi + bri), h~ = tanh(wh x + bwh + r * (rh h + brh)),
+	h' = (1 - i) h~ + i h.  Returns (out (T,B,H), cache)."""
+	x = np.asarray(x, dtype)
+	T, B, _ = x.shape
+	p = {k: np.asarray(v, dtype) for k, v in params.items()}
+	H = p["ri"].shape[0]
+	h = np.zeros((B, H), dtype) if h0 is None else np.asarray(h0, dtype)
+	out = np.empty((T, B, H), dtype)
+	cache = {}
+	for t in (range(T - 1, -1, -1) if reverse else range(T)):
+		r = _sigmoid(x[t] @ p["wr"].T + h @ p["rr"].T + p["bwr"] + p["brr"])
+		i = _sigmoid(x[t] @ p["wi"].T + h @ p["ri"].T + p["bwi"] + p["bri"])
+		q = h @ p["rh"].T + p["brh"]
+		ht = np.tanh(x[t] @ p["wh"].T + p["bwh"] + r * q)
+		cache[t] = (r, i, ht, q, h)
+		h = (1.0 - i) * ht + i * h
+		out[t] = h
+	return out, cache
+
+
+def gru_backward(x, params, cache, dy, reverse=False, dtype=np.float64):
+	"""Gradients of gru_forward (reference host loop: CuDnnRnn.py:354-419): returns (dx, dparams dict)."""
+	x, dy = np.asarray(x, dtype), np.asarray(dy, dtype)
+	T, B, insz = x.shape
+	p = {k: np.asarray(v, dtype) for k, v in params.items()}
+	H = p["ri"].shape[0]
+	dp = {k: np.zeros_like(v) for k, v in p.items()}
+	dx = np.zeros((T, B, insz), dtype)
+	dhn = np.zeros((B, H), dtype)
+	for t in (range(T) if reverse else range(T - 1, -1, -1)):
+		r, i, ht, q, hprev = cache[t]
+		dh = dy[t] + dhn
+		dpre_h = dh * (1.0 - i) * (1.0 - ht * ht)
+		dpre_i = dh * (hprev - ht) * i * (1.0 - i)
+		dpre_r = dpre_h * q * r * (1.0 - r)
+		dq = dpre_h * r
+		for gname, dxside, dhside in (("r", dpre_r, dpre_r), ("i", dpre_i, dpre_i), ("h", dpre_h, dq)):
+			dp["w" + gname] += dxside.T @ x[t]
+			dp["r" + gname] += dhside.T @ hprev
+			dp["bw" + gname] += dxside.sum(axis=0)
+			dp["br" + gname] += dhside.sum(axis=0)
+			dx[t] += dxside @ p["w" + gname]
+		dhn = dh * i + dpre_r @ p["rr"] + dpre_i @ p["ri"] + dq @ p["rh"]
 	return dx, dp
 
 

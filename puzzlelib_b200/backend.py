@@ -403,6 +403,50 @@ class BlasContext:
 						  int(transpB), alpha, beta, None, None))
 		return out
 
+	def gemmBatched(self, A, B, formatA=0, formatB=0, formatOut=0, transpA=False, transpB=False, alpha=1.0, beta=0.0, out=None,
+					allocator=None):
+		"""One GEMM per group over 3-d tensors in (group, batch, param) = gbp (0) or (batch, group, param) = bgp (1) layout
+		(reference: CuBlas_Context_gemmBatched, CuBlas.c:207-320; tests Cuda/Wrappers/CuBlas.py:60-189).  A bgp operand is a
+		pitched matrix per group, so every group is one pz_gemm call with the right leading dimension -- no repacking."""
+		_requireArray(A, "A")
+		_requireArray(B, "B")
+		if A.ndim != 3 or B.ndim != 3 or A.dtype != B.dtype:
+			raise ValueError("invalid gemmBatched operands")
+		if transpA and transpB:
+			raise ValueError("only one of the gemm operands can be transposed")
+
+		def geometry(ary, fmt):
+			# -> groups, rows, cols, leading dimension, element offset between groups
+			if fmt == 0:
+				g, r, c = ary.shape
+				return g, r, c, c, r * c
+			r, g, c = ary.shape
+			return g, r, c, g * c, c
+
+		ga, ra, ca, lda, sa = geometry(A, formatA)
+		gb, rb, cb, ldb, sb = geometry(B, formatB)
+		if ga != gb:
+			raise ValueError("gemmBatched operands have different group counts")
+		M, K = (ca, ra) if transpA else (ra, ca)
+		Kb, N = (cb, rb) if transpB else (rb, cb)
+		if K != Kb:
+			raise ValueError("gemmBatched operand shapes %s and %s do not match" % (A.shape, B.shape))
+
+		outshape = (ga, M, N) if formatOut == 0 else (M, ga, N)
+		if out is None:
+			out = GPUArray(outshape, A.dtype, allocator=allocator)
+			if beta != 0.0:
+				out.fill(0)
+		else:
+			_checkOut(out, outshape, A.dtype)
+		_, _, _, ldc, sc = geometry(out, formatOut)
+
+		code, es = dtypeCode(A.dtype), A.dtype.itemsize
+		for g in range(ga):
+			check(lib.pz_gemm(code, A.ptr + g * sa * es, B.ptr + g * sb * es, out.ptr + g * sc * es, M, N, K, lda, ldb, ldc,
+							  int(transpA), int(transpB), alpha, beta, None, None))
+		return out
+
 	def gemmBias(self, A, B, bias, out=None, transpB=False, allocator=None):
 		"""Linear forward with the bias add folded into the GEMM epilogue (Linear.py:36-40 as one kernel)."""
 		M, K = A.shape

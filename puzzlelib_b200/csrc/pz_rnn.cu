@@ -84,9 +84,86 @@ __global__ void __launch_bounds__(kThreads) rnn_cell_bwd_kernel(const float* __r
 	dpre[idx] = mode == 0 ? (y > 0.0f ? dh : 0.0f) : dh * (1.0f - y * y);
 }
 
+// GRU (cuDNN formulation, reference host loop Cuda/Wrappers/CuDnnRnn.py:303-352): gate order r, i, h in every 3H row;
+//   r = sigm(Wr x + Rr h + bwr + brr), i = sigm(Wi x + Ri h + bwi + bri), h~ = tanh(Wh x + bwh + r * (Rh h + brh)),
+//   h' = (1 - i) * h~ + i * h.
+// gx: input projections in, activations (r, i, h~) out; gh: recurrent projections in, its h part becomes q = Rh h + brh (kept
+// for the backward pass).
+__global__ void __launch_bounds__(kThreads) gru_cell_fwd_kernel(float* __restrict__ gx, float* __restrict__ gh, const float* __restrict__ bw,
+																 const float* __restrict__ br, const float* __restrict__ h_prev,
+																 float* __restrict__ h_out, int B, int H)
+{
+	const int idx = blockIdx.x * kThreads + threadIdx.x;
+	if (idx >= B * H) return;
+	const int b = idx / H, j = idx - b * H;
+	float* x = gx + (size_t)b * 3 * H;
+	float* h = gh + (size_t)b * 3 * H;
+	const float r = sigmoidf_(x[j] + h[j] + bw[j] + br[j]);
+	const float i = sigmoidf_(x[H + j] + h[H + j] + bw[H + j] + br[H + j]);
+	const float q = h[2 * H + j] + br[2 * H + j];
+	const float ht = tanhf(x[2 * H + j] + bw[2 * H + j] + r * q);
+	const float hp = h_prev ? h_prev[idx] : 0.0f;
+	x[j] = r;
+	x[H + j] = i;
+	x[2 * H + j] = ht;
+	h[2 * H + j] = q;
+	h_out[idx] = (1.0f - i) * ht + i * hp;
+}
+
+// dgx / dgh: gradients w.r.t. the input-side / recurrent-side pre-activations; dh_carry = dh * i (the direct path to h[t-1],
+// the caller adds dgh * R to it)
+__global__ void __launch_bounds__(kThreads) gru_cell_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ dh_next,
+																 const float* __restrict__ acts, const float* __restrict__ gh,
+																 const float* __restrict__ h_prev, float* __restrict__ dgx,
+																 float* __restrict__ dgh, float* __restrict__ dh_carry, int B, int H)
+{
+	const int idx = blockIdx.x * kThreads + threadIdx.x;
+	if (idx >= B * H) return;
+	const int b = idx / H, j = idx - b * H;
+	const float* a = acts + (size_t)b * 3 * H;
+	const float r = a[j], i = a[H + j], ht = a[2 * H + j];
+	const float q = gh[(size_t)b * 3 * H + 2 * H + j];
+	const float hp = h_prev ? h_prev[idx] : 0.0f;
+	const float dh = dy[idx] + (dh_next ? dh_next[idx] : 0.0f);
+	const float dpre_h = dh * (1.0f - i) * (1.0f - ht * ht);
+	const float dpre_i = dh * (hp - ht) * i * (1.0f - i);
+	const float dpre_r = dpre_h * q * r * (1.0f - r);
+	float* gx = dgx + (size_t)b * 3 * H;
+	float* gr = dgh + (size_t)b * 3 * H;
+	gx[j] = dpre_r;
+	gx[H + j] = dpre_i;
+	gx[2 * H + j] = dpre_h;
+	gr[j] = dpre_r;
+	gr[H + j] = dpre_i;
+	gr[2 * H + j] = dpre_h * r;
+	dh_carry[idx] = dh * i;
+}
+
 }  // namespace
 
 extern "C" {
+
+int pz_gru_cell_fwd(float* gx, float* gh, const float* bw, const float* br, const float* h_prev, float* h_out, int64_t B, int64_t H,
+					void* stream)
+{
+	PZ_REQUIRE(B > 0 && H > 0 && B * H < (1ll << 31), "gru cell: invalid size %lld x %lld", (long long)B, (long long)H);
+	gru_cell_fwd_kernel<<<(unsigned)pz_cdiv(B * H, kThreads), kThreads, 0, pz_stream(stream)>>>(gx, gh, bw, br, h_prev, h_out, (int)B, (int)H);
+	pz_count_launch(1);
+	PZ_LAUNCH_CHECK();
+	return PZ_OK;
+}
+
+int pz_gru_cell_bwd(const float* dy, const float* dh_next, const float* acts, const float* gh, const float* h_prev, float* dgx,
+					float* dgh, float* dh_carry, int64_t B, int64_t H, void* stream)
+{
+	PZ_REQUIRE(B > 0 && H > 0 && B * H < (1ll << 31), "gru cell: invalid size %lld x %lld", (long long)B, (long long)H);
+	gru_cell_bwd_kernel<<<(unsigned)pz_cdiv(B * H, kThreads), kThreads, 0, pz_stream(stream)>>>(dy, dh_next, acts, gh, h_prev, dgx, dgh,
+																									dh_carry, (int)B, (int)H);
+	pz_count_launch(1);
+	PZ_LAUNCH_CHECK();
+	return PZ_OK;
+}
+
 
 int pz_lstm_cell_fwd(float* gates, const float* bw, const float* br, const float* c_prev, float* c_out, float* h_out, int64_t B,
 					 int64_t H, void* stream)

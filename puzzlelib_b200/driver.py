@@ -134,6 +134,8 @@ _SIGNATURES = {
 	"pz_softmax_bwd": [c_int, c_int, _P, _P, _P, c_int64, c_int64, c_int64, _P],
 	"pz_lstm_cell_fwd": [_P, _P, _P, _P, _P, _P, c_int64, c_int64, _P],
 	"pz_lstm_cell_bwd": [_P, _P, _P, _P, _P, _P, _P, c_int64, c_int64, c_int, _P],
+	"pz_gru_cell_fwd": [_P, _P, _P, _P, _P, _P, c_int64, c_int64, _P],
+	"pz_gru_cell_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int64, _P],
 	"pz_rnn_cell_fwd": [_P, _P, _P, c_int64, c_int64, c_int, _P],
 	"pz_rnn_cell_bwd": [_P, _P, _P, _P, c_int64, c_int, _P],
 	"pz_add2d": [c_int, _P, c_int64, _P, c_int64, c_int64, c_int64, _P],

@@ -666,7 +666,7 @@ class WeightModifier(str, Enum):
 
 class RNN(Module):
 	"""reference: Modules/RNN.py:31-240 (same constructor, parameter initialisation draws, last-step selection and gradient
-	scatter in Python; uni-directional relu / tanh / lstm -- what the B200 Rnn object implements)"""
+	scatter in Python; relu / tanh / lstm / gru, uni- and bidirectional)"""
 
 	def __init__(self, insize, hsize, layers=1, mode="relu", direction="uni", dropout=0.0, getSequences=False, initscheme=None,
 				 modifier="orthogonal", wscale=1.0, hintBatchSize=None, name=None):
@@ -727,17 +727,31 @@ class RNN(Module):
 			self.fulldata, self.reserve = Rnn.forwardRnn(data, self.W, self.descRnn)
 		else:
 			self.fulldata = Rnn.forwardRnn(data, self.W, self.descRnn, test=True)
-		self.data = self.fulldata if self.getSequences else self.fulldata[-1]
+		if self.direction == DirectionMode.uni:
+			self.data = self.fulldata if self.getSequences else self.fulldata[-1]
+		elif self.getSequences:
+			self.data = self.fulldata
+		else:
+			# last step of the forward direction, first step of the backward one (Modules/RNN.py:131-138)
+			sections = (self.hsize, self.hsize)
+			self.data = [gpuarray.split(self.fulldata[-1], sections, axis=1)[0], gpuarray.split(self.fulldata[0], sections, axis=1)[1]]
 
 	def updateGrad(self, grad):
 		if self.getSequences:
 			fullgrad = grad
 		else:
 			seqlen = self.fulldata.shape[0]
-			fullgrad = gpuarray.empty((seqlen, ) + grad.shape, dtype=grad.dtype, allocator=memoryPool())
-			if seqlen > 1:
-				fullgrad[:seqlen - 1].fill(0.0)
-			fullgrad[seqlen - 1].set(grad)
+			if self.direction == DirectionMode.uni:
+				fullgrad = gpuarray.empty((seqlen, ) + grad.shape, dtype=grad.dtype, allocator=memoryPool())
+				if seqlen > 1:
+					fullgrad[:seqlen - 1].fill(0.0)
+				fullgrad[seqlen - 1].set(grad)
+			else:
+				fwdgrad, bwdgrad = grad
+				batchsize = fwdgrad.shape[0]
+				fullgrad = gpuarray.zeros((seqlen, batchsize, 2 * self.hsize), dtype=fwdgrad.dtype, allocator=memoryPool())
+				fullgrad[0, :, self.hsize:].set(bwdgrad)
+				fullgrad[seqlen - 1, :, :self.hsize].set(fwdgrad)
 		self.grad, self.reserve = Rnn.backwardDataRnn(fullgrad, self.fulldata, self.W, self.reserve, self.descRnn)
 
 	def accGradParams(self, grad, scale=1.0, momentum=0.0):
@@ -756,17 +770,30 @@ class RNN(Module):
 		if self.getSequences:
 			if len(shape) != 3:
 				raise ModuleError("Grad must be 3d tensor")
-		else:
+		elif self.direction == DirectionMode.uni:
 			if len(shape) != 2:
 				raise ModuleError("Grad must be 2d matrix")
 			if shape[-1] != self.hsize:
 				raise ModuleError("Grad must have data size = %s (was given %s)" % (self.hsize, shape[-1]))
+		else:
+			fwdshape, bwdshape = shape
+			if len(fwdshape) != 2 or len(bwdshape) != 2:
+				raise ModuleError("Grads must be 2d matrices")
+			if fwdshape[-1] != self.hsize or bwdshape[-1] != self.hsize:
+				raise ModuleError("Grads must have data size = %s (was given %s and %s)" % (self.hsize, fwdshape[1], bwdshape[1]))
 
 	def dataShapeFrom(self, shape):
-		return shape[:2] + (self.hsize, ) if self.getSequences else (shape[1], self.hsize)
+		hsize = self.hsize if self.direction == DirectionMode.uni else 2 * self.hsize
+		if self.getSequences:
+			return shape[:2] + (hsize, )
+		return (shape[1], hsize) if self.direction == DirectionMode.uni else [(shape[1], self.hsize), (shape[1], self.hsize)]
 
 	def gradShapeFrom(self, shape):
-		return self.inData.shape[0], shape[1] if self.getSequences else shape[0], self.insize
+		if self.getSequences:
+			batchsize = shape[1]
+		else:
+			batchsize = shape[0] if self.direction == DirectionMode.uni else shape[0][0]
+		return self.inData.shape[0], batchsize, self.insize
 
 	def reset(self):
 		super().reset()

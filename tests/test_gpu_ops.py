@@ -239,6 +239,30 @@ def test_gemm(bnd, case):
 	assert relerr(acc.get(), ops.gemm(A, B, C0, ta, tb, 0.5, 0.75)) < REL_TC
 
 
+@pytest.mark.parametrize("formats", [(0, 0, 0), (0, 1, 1), (1, 0, 1), (1, 1, 0)])
+def test_gemm_batched(bnd, formats):
+	# reference tests: Cuda/Wrappers/CuBlas.py:60-189 (gbp / bgp operand and output layouts, one transposed operand at a time)
+	fa, fb, fo = formats
+	rng = np.random.RandomState(17)
+	groups, M, K, N = 3, 20, 33, 12
+
+	def layout(mats, fmt):          # list of per-group matrices -> gbp or bgp tensor
+		t = np.stack(mats)
+		return np.ascontiguousarray(t if fmt == 0 else t.transpose(1, 0, 2)).astype(np.float32)
+
+	def per_group(t, fmt):
+		return [t[g] if fmt == 0 else t[:, g, :] for g in range(groups)]
+
+	As = [rng.randn(M, K) for _ in range(groups)]
+	for ta, tb in ((False, False), (True, False), (False, True)):
+		Bs = [rng.randn(*((N, K) if tb else ((M, N) if ta else (K, N)))) for _ in range(groups)]
+		out = bnd.blas.gemmBatched(G(bnd, layout(As, fa)), G(bnd, layout(Bs, fb)), fa, fb, fo, ta, tb, allocator=bnd.memoryPool)
+		want = [(a.T if ta else a) @ (b.T if tb else b) for a, b in zip(As, Bs)]
+		got = per_group(out.get(), fo)
+		for g in range(groups):
+			assert relerr(got[g], want[g]) < REL_TC
+
+
 def test_gemm_bias_epilogue_and_errors(bnd):
 	rng = np.random.RandomState(3)
 	A, B, b = rng.randn(64, 800).astype(np.float32), rng.randn(800, 1024).astype(np.float32), rng.randn(1024).astype(np.float32)
@@ -650,8 +674,88 @@ def test_rnn_module_last_step_and_sequences(bnd):
 	dwparams = bnd.acquireRnnParams(mod.descRnn, mod.vars["W"].grad)[0]
 	assert relerr(dwparams["ri"].get(), dp["ri"]) < 2 * REL_TC
 
-	with pytest.raises(NotImplementedError):
-		M.RNN(insz, H, mode="gru")
+
+
+@pytest.mark.parametrize("case", [(3, 3, 4, 2), (6, 8, 40, 24), (10, 32, 64, 64)])
+def test_gru_forward_backward(bnd, case):
+	# reference test: Cuda/Wrappers/CuDnnRnn.py:303-419 (gruTest)
+	T, B, insz, H = case
+	rng = np.random.RandomState(T * 7 + H)
+	rnn, W, params = bnd.createRnn(insz, H, np.float32, mode=bnd.RNNMode.gru)
+	assert W.shape == (3 * H * (insz + H) + 6 * H, )
+	W.set((rng.randn(*W.shape) * 0.3).astype(np.float32))
+	host = _rnn_host_params(params[0])
+	x, dy = rng.randn(T, B, insz).astype(np.float32), rng.randn(T, B, H).astype(np.float32)
+	h0 = rng.randn(1, B, H).astype(np.float32)
+
+	out, reserve = rnn.forward(G(bnd, x), W, hidden=G(bnd, h0), allocator=bnd.memoryPool)
+	want, cache = ops.gru_forward(x, host, h0[0])
+	tol = REL_TC * (1 + T / 4.0)
+	assert relerr(out.get(), want) < tol
+	ingrad, dhx, _ = rnn.backwardData(G(bnd, dy), out, W, reserve, allocator=bnd.memoryPool)
+	dw = rnn.backwardParams(G(bnd, x), out, reserve, allocator=bnd.memoryPool)
+	dx, dp = ops.gru_backward(x, host, cache, dy)
+	assert relerr(ingrad.get(), dx) < 2 * tol
+	dwparams = bnd.acquireRnnParams(rnn, dw)[0]
+	for name, w in dp.items():
+		assert relerr(dwparams[name].get(), w) < 2 * tol, name
+
+
+@pytest.mark.parametrize("mode", ["lstm", "gru", "tanh"])
+def test_bidirectional_rnn(bnd, mode):
+	# reference test: Cuda/Wrappers/CuDnnRnn.py:95-176 (bidirectional tanhTest): two parameter sets, outputs concatenated
+	T, B, insz, H = 5, 4, 12, 16
+	rng = np.random.RandomState(31)
+	rnn, W, params = bnd.createRnn(insz, H, np.float32, mode=getattr(bnd.RNNMode, mode), direction=bnd.DirectionMode.bi)
+	assert len(params) == 2
+	W.set((rng.randn(*W.shape) * 0.3).astype(np.float32))
+	host = [_rnn_host_params(params[d]) for d in range(2)]
+	x, dy = rng.randn(T, B, insz).astype(np.float32), rng.randn(T, B, 2 * H).astype(np.float32)
+
+	out, reserve = rnn.forward(G(bnd, x), W, allocator=bnd.memoryPool)
+	assert out.shape == (T, B, 2 * H)
+	ingrad, _, _ = rnn.backwardData(G(bnd, dy), out, W, reserve, allocator=bnd.memoryPool)
+	dw = rnn.backwardParams(G(bnd, x), out, reserve, allocator=bnd.memoryPool)
+	dwparams = bnd.acquireRnnParams(rnn, dw)
+
+	wantdx = np.zeros(x.shape)
+	tol = REL_TC * (1 + T / 4.0)
+	for d, reverse in ((0, False), (1, True)):
+		dyd = dy[:, :, d * H:(d + 1) * H]
+		if mode == "lstm":
+			o, cache = ops.lstm_forward(x, host[d], reverse=reverse)
+			dxd, dp = ops.lstm_backward(x, host[d], cache, dyd)
+		elif mode == "gru":
+			o, cache = ops.gru_forward(x, host[d], reverse=reverse)
+			dxd, dp = ops.gru_backward(x, host[d], cache, dyd, reverse=reverse)
+		else:
+			xs, dys = (x[::-1], dyd[::-1]) if reverse else (x, dyd)
+			o = ops.rnn_forward(xs, host[d], "tanh")
+			dxd, dp = ops.rnn_backward(xs, host[d], o, dys, "tanh")
+			if reverse:
+				o, dxd = o[::-1], dxd[::-1]
+		assert relerr(out.get()[:, :, d * H:(d + 1) * H], o) < tol
+		wantdx += dxd
+		for name, w in dp.items():
+			assert relerr(dwparams[d][name].get(), w) < 2 * tol, (d, name)
+	assert relerr(ingrad.get(), wantdx) < 2 * tol
+
+
+def test_bidirectional_rnn_module_last_steps(bnd):
+	# Modules/RNN.py:131-161: a bidirectional layer without sequences returns [forward last step, backward first step]
+	from puzzlelib_b200 import modules as M
+	np.random.seed(9)
+	rng = np.random.RandomState(9)
+	T, B, insz, H = 4, 3, 8, 8
+	mod = M.RNN(insz, H, mode="gru", direction="bi", getSequences=False)
+	x = rng.randn(T, B, insz).astype(np.float32)
+	fwd, bwd = mod(G(bnd, x))
+	assert fwd.shape == (B, H) and bwd.shape == (B, H)
+	host = [_rnn_host_params(mod.params[i]) for i in range(2)]
+	assert relerr(fwd.get(), ops.gru_forward(x, host[0])[0][-1]) < 3e-3
+	assert relerr(bwd.get(), ops.gru_forward(x, host[1], reverse=True)[0][0]) < 3e-3
+	mod.backward([G(bnd, rng.randn(B, H).astype(np.float32)), G(bnd, rng.randn(B, H).astype(np.float32))])
+	assert mod.grad.shape == (T, B, insz)
 
 
 # ================================================================================================ 3-d convolution / pooling

@@ -268,3 +268,49 @@ def test_rnn_oracle_gradients_match_finite_differences():
 	pp["ri"][1, 2] += eps
 	pm["ri"][1, 2] -= eps
 	assert abs((loss(x, pp) - loss(x, pm)) / (2 * eps) - dp["ri"][1, 2]) < 1e-6
+
+
+def test_gru_oracle_gradients_match_finite_differences():
+	rng = np.random.RandomState(8)
+	T, B, insz, H = 3, 2, 4, 3
+	params = {}
+	for g in "rih":
+		params["w" + g] = rng.randn(H, insz) * 0.5
+		params["r" + g] = rng.randn(H, H) * 0.5
+		params["bw" + g] = rng.randn(H) * 0.1
+		params["br" + g] = rng.randn(H) * 0.1
+	x, dy = rng.randn(T, B, insz), rng.randn(T, B, H)
+	for reverse in (False, True):
+		out, cache = ops.gru_forward(x, params, reverse=reverse)
+		dx, dp = ops.gru_backward(x, params, cache, dy, reverse=reverse)
+
+		def loss(xv, pv):
+			return float((ops.gru_forward(xv, pv, reverse=reverse)[0] * dy).sum())
+
+		eps = 1e-6
+		xp, xm = x.copy(), x.copy()
+		xp[1, 1, 2] += eps
+		xm[1, 1, 2] -= eps
+		assert abs((loss(xp, params) - loss(xm, params)) / (2 * eps) - dx[1, 1, 2]) < 1e-6
+		for name, idx in [("wr", (0, 1)), ("rh", (2, 0)), ("ri", (1, 1)), ("brh", (2, )), ("bwh", (0, )), ("brr", (1, ))]:
+			pp, pm = {k: v.copy() for k, v in params.items()}, {k: v.copy() for k, v in params.items()}
+			pp[name][idx] += eps
+			pm[name][idx] -= eps
+			assert abs((loss(x, pp) - loss(x, pm)) / (2 * eps) - dp[name][idx]) < 1e-6
+
+
+def test_lstm_oracle_reverse_direction_is_the_time_flipped_forward():
+	rng = np.random.RandomState(2)
+	T, B, insz, H = 4, 2, 3, 3
+	params = {}
+	for g in "ifco":
+		params["w" + g], params["r" + g] = rng.randn(H, insz) * 0.5, rng.randn(H, H) * 0.5
+		params["bw" + g], params["br" + g] = rng.randn(H) * 0.1, rng.randn(H) * 0.1
+	x, dy = rng.randn(T, B, insz), rng.randn(T, B, H)
+	out_r, cache_r = ops.lstm_forward(x, params, reverse=True)
+	out_f, cache_f = ops.lstm_forward(x[::-1], params)
+	assert np.allclose(out_r, out_f[::-1])
+	dx_r, dp_r = ops.lstm_backward(x, params, cache_r, dy)
+	dx_f, dp_f = ops.lstm_backward(x[::-1], params, cache_f, dy[::-1])
+	assert np.allclose(dx_r, dx_f[::-1])
+	assert all(np.allclose(dp_r[k], dp_f[k]) for k in dp_r)
