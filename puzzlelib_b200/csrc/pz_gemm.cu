@@ -139,6 +139,9 @@ int launch(GemmParams& p, int dtype, int bn, int amode, int bmode, bool cdiv, in
 	p.tiles_m = (int)pz_cdiv(M, BM);
 	p.tiles_n = (int)pz_cdiv(N, bn);
 	p.groups = groups;
+	p.fd_tiles_n = make_fastdiv((uint32_t)p.tiles_n);
+	p.fd_tiles_m = make_fastdiv((uint32_t)p.tiles_m);
+	p.fd_splits = make_fastdiv((uint32_t)p.splits);
 	const long long units = (long long)p.tiles_m * p.tiles_n * groups * p.splits;
 	PZ_REQUIRE(units < (1ll << 31), "tile grid too large");
 	const int grid = (int)(units < pz_num_sms() ? units : pz_num_sms());

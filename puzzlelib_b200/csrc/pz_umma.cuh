@@ -40,10 +40,26 @@ namespace pzumma {
 
 constexpr int BM = 128;          // tile rows  = TMEM lanes
 constexpr int BK = 32;           // floats per k-block = one 128-byte swizzle row
-constexpr int NPROD_WARPS = 16;
-constexpr int NPROD = NPROD_WARPS * 32;
+// Producers work in NGROUPS independent groups of NPROD_WARPS warps: group g fills k-blocks g, g + NGROUPS, ... of the CTA's
+// k-block sequence -- a whole k-block per group, every thread with its share of it (32 four-byte loads per operand) in
+// flight at once.  What bounds a gather of 4-byte lanes is bytes in flight per SM (tools/ubench/gather_bw.cu: 512 threads
+// with 8 loads each sustain 23.6 GB/s per SM, with 32 loads each 44 GB/s = the HBM rate), and a register ring of several
+// k-blocks per thread does NOT add to it: all global loads of a thread land on one hardware scoreboard, a wait on a
+// scoreboard waits for every load outstanding on it, so the ring degenerates to one k-block per DRAM round trip.
+constexpr int NGROUPS = 4;
+constexpr int NPROD_WARPS = 4;               // warps of one producer group
+constexpr int NPROD = NPROD_WARPS * 32;      // threads of one producer group
+constexpr int NPROD_WARPS_ALL = NGROUPS * NPROD_WARPS;
 constexpr int NEPI_WARPS = 4;
-constexpr int NTHREADS = NPROD + 32 + NEPI_WARPS * 32;
+// 24 warps = 6 warpgroups: 0-3 producer groups, 4 = MMA issuer (warp 16; 17-19 only give their registers away), 5 = epilogue.
+// The kernel starts at 80 registers per thread; setmaxnreg moves registers from the MMA / epilogue warpgroups to the
+// producers (a k-block of both operands in registers).  The pool is the launch allocation: 512*96 + 128*32 + 128*64 = 768*80.
+constexpr int MMA_WARP = NPROD_WARPS_ALL;
+constexpr int EPI_WARP0 = NPROD_WARPS_ALL + 4;
+constexpr int NTHREADS = (EPI_WARP0 + NEPI_WARPS) * 32;
+constexpr int REGS_PROD = 96, REGS_MMA = 32, REGS_EPI = 64;
+template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 constexpr int INVALID = -(1 << 28);
 
 struct FastDiv {
@@ -128,6 +144,7 @@ struct GemmParams {
 	int splits;                  // split-K factor
 	int kb_per_split;
 	int tiles_m, tiles_n, groups; // tile grid; total work units = tiles_m * tiles_n * groups * splits
+	FastDiv fd_tiles_n, fd_tiles_m, fd_splits;   // the same counts as magic-number divisors (the decode runs per tile per warp)
 	int tma_rows_per_group;      // MODE_TMA: row offset of group g in the prepared filter = g * tma_rows_per_group
 	int ab_bf16;                 // 16-bit operands: 0 = half, 1 = bfloat16 (selects the tcgen05 input format)
 	double alg_flops, alg_bytes; // host-side bookkeeping for the profiler (algorithmic work of this launch)
@@ -212,6 +229,23 @@ __device__ __forceinline__ uint32_t to_tf32(float x)
 {
 	return __float_as_uint(x) + 0x1000u;
 }
+// Predicated global loads of the producers as volatile asm: they stay in program order ahead of the (volatile) shared
+// stores, so a k-block's loads are ALL in flight before the first value is consumed.  (With __ldg the compiler is free to sink
+// loads between the stores to save registers -- measured: ten load / wait / store rounds per k-block instead of one.)
+__device__ __forceinline__ float ldg_pred(const void* p, bool ok)
+{
+	float v;
+	asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\tmov.b32 %0, 0;\n\t@p ld.global.nc.b32 %0, [%1];\n\t}"
+				 : "=f"(v) : "l"(p), "r"((int)ok));
+	return v;
+}
+__device__ __forceinline__ uint32_t ldg16_pred(const void* p, bool ok)
+{
+	uint16_t v;
+	asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\tmov.b16 %0, 0;\n\t@p ld.global.nc.b16 %0, [%1];\n\t}"
+				 : "=h"(v) : "l"(p), "r"((int)ok));
+	return (uint32_t)v;
+}
 __device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
 {
@@ -292,7 +326,7 @@ __device__ __forceinline__ float fetch(const Operand& op, const float* __restric
 	if (SIMPLE) {
 		bool ok = ri.valid && ki.valid;
 		int off = ri.rbase + ki.kbase + hh * op.Wd + ww;
-		return ok ? __ldg(base + off) : 0.0f;
+		return ldg_pred(base + off, ok);
 	}
 	bool ok = true;
 	if (CDIV) {
@@ -302,7 +336,7 @@ __device__ __forceinline__ float fetch(const Operand& op, const float* __restric
 	}
 	ok = ok && ((unsigned)hh < (unsigned)op.H) && ((unsigned)ww < (unsigned)op.W);
 	int off = ri.rbase + ki.kbase + hh * op.Wd + ww;
-	return ok ? __ldg(base + off) : 0.0f;
+	return ldg_pred(base + off, ok);
 }
 
 // MN-contiguous producer: thread owns one tile row (kept in registers) and ROWS/32 16-byte chunks per stage.
@@ -377,10 +411,11 @@ struct KProducer {
 	}
 	__device__ __forceinline__ void store(uint32_t tile, const float (&v)[NV])
 	{
-		// row & 7 == warp & 7 for every row of this warp, so the swizzled column offset is a thread constant
-		uint32_t col = ((((uint32_t)lane >> 2) ^ ((uint32_t)warp & 7)) << 4) | (((uint32_t)lane & 3) << 2);
 		#pragma unroll
-		for (int i = 0; i < NR; i++) sts32(tile + (warp + i * NPROD_WARPS) * 128 + col, to_tf32(v[i]));
+		for (int i = 0; i < NR; i++) {
+			const uint32_t row = (uint32_t)(warp + i * NPROD_WARPS);
+			sts32(tile + row * 128 + (((((uint32_t)lane >> 2) ^ (row & 7)) << 4) | (((uint32_t)lane & 3) << 2)), to_tf32(v[i]));
+		}
 	}
 };
 
@@ -477,7 +512,7 @@ struct MnTapProducer {
 			asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
 						 : "=r"(e4[0]), "=r"(e4[1]), "=r"(e4[2]), "=r"(e4[3]) : "r"(tab + (chunk0 + i * CSTEP) * 16));
 			#pragma unroll
-			for (int e = 0; e < 4; e++) v[i * 4 + e] = mask.test(e4[e]) ? ldg_off(sb, e4[e] >> TM::SH) : 0.0f;
+			for (int e = 0; e < 4; e++) v[i * 4 + e] = ldg_pred(sb + ((unsigned long long)(e4[e] >> TM::SH) << 2), mask.test(e4[e]));
 		}
 	}
 	__device__ __forceinline__ void store(uint32_t tile, const float (&v)[NV])
@@ -542,14 +577,16 @@ struct KTapProducer {
 		for (int i = 0; i < NR; i++) {
 			uint32_t ent;
 			asm volatile("ld.shared.b32 %0, [%1];" : "=r"(ent) : "r"(table + (warp + i * NPROD_WARPS) * 4));
-			v[i] = mask.test(ent) ? ldg_off(sb, ent >> TM::SH) : 0.0f;
+			v[i] = ldg_pred(sb + ((unsigned long long)(ent >> TM::SH) << 2), mask.test(ent));
 		}
 	}
 	__device__ __forceinline__ void store(uint32_t tile, const float (&v)[NV])
 	{
-		const uint32_t col = ((((uint32_t)lane >> 2) ^ ((uint32_t)warp & 7)) << 4) | (((uint32_t)lane & 3) << 2);
 		#pragma unroll
-		for (int i = 0; i < NR; i++) sts32(tile + (warp + i * NPROD_WARPS) * 128 + col, to_tf32(v[i]));
+		for (int i = 0; i < NR; i++) {
+			const uint32_t row = (uint32_t)(warp + i * NPROD_WARPS);
+			sts32(tile + row * 128 + (((((uint32_t)lane >> 2) ^ (row & 7)) << 4) | (((uint32_t)lane & 3) << 2)), to_tf32(v[i]));
+		}
 	}
 };
 
@@ -585,15 +622,17 @@ struct KDenseProducer {
 		const char* __restrict__ p = reinterpret_cast<const char*>(base + rowoff0 + koff);
 		#pragma unroll
 		for (int i = 0; i < NR; i++) {
-			v[i] = i < n ? __ldg(reinterpret_cast<const float*>(p)) : 0.0f;
+			v[i] = ldg_pred(p, i < n);
 			p += step;
 		}
 	}
 	__device__ __forceinline__ void store(uint32_t tile, const float (&v)[NV])
 	{
-		const uint32_t col = ((((uint32_t)lane >> 2) ^ ((uint32_t)warp & 7)) << 4) | (((uint32_t)lane & 3) << 2);
 		#pragma unroll
-		for (int i = 0; i < NR; i++) sts32(tile + (warp + i * NPROD_WARPS) * 128 + col, to_tf32(v[i]));
+		for (int i = 0; i < NR; i++) {
+			const uint32_t row = (uint32_t)(warp + i * NPROD_WARPS);
+			sts32(tile + row * 128 + (((((uint32_t)lane >> 2) ^ (row & 7)) << 4) | (((uint32_t)lane & 3) << 2)), to_tf32(v[i]));
+		}
 	}
 };
 
@@ -651,7 +690,7 @@ struct MnChanProducer {
 				#pragma unroll
 				for (int e = 0; e < 4; e++) {
 					const unsigned j = (unsigned)(i * CSTEP * 4 + e);
-					v[i * 4 + e] = ok ? __ldg(reinterpret_cast<const float*>(ptr + (unsigned long long)ksb * j)) : 0.0f;
+					v[i * 4 + e] = ldg_pred(ptr + (unsigned long long)ksb * j, ok);
 				}
 			}
 		} else {
@@ -660,7 +699,7 @@ struct MnChanProducer {
 				#pragma unroll
 				for (int e = 0; e < 4; e++) {
 					const int j = i * CSTEP * 4 + e;
-					v[i * 4 + e] = (ok && j < cleft) ? __ldg(reinterpret_cast<const float*>(ptr + (unsigned long long)ksb * (unsigned)j)) : 0.0f;
+					v[i * 4 + e] = ldg_pred(ptr + (unsigned long long)ksb * (unsigned)j, ok && j < cleft);
 				}
 			}
 		}
@@ -706,15 +745,17 @@ struct KPosDenseProducer {
 		const char* __restrict__ p = reinterpret_cast<const char*>(base + (rowoff0 + (long long)n * op.ks0 + pos));
 		#pragma unroll
 		for (int i = 0; i < NR; i++) {
-			v[i] = i < cnt ? __ldg(reinterpret_cast<const float*>(p)) : 0.0f;
+			v[i] = ldg_pred(p, i < cnt);
 			p += step;
 		}
 	}
 	__device__ __forceinline__ void store(uint32_t tile, const float (&v)[NV])
 	{
-		const uint32_t col = ((((uint32_t)lane >> 2) ^ ((uint32_t)warp & 7)) << 4) | (((uint32_t)lane & 3) << 2);
 		#pragma unroll
-		for (int i = 0; i < NR; i++) sts32(tile + (warp + i * NPROD_WARPS) * 128 + col, to_tf32(v[i]));
+		for (int i = 0; i < NR; i++) {
+			const uint32_t row = (uint32_t)(warp + i * NPROD_WARPS);
+			sts32(tile + row * 128 + (((((uint32_t)lane >> 2) ^ (row & 7)) << 4) | (((uint32_t)lane & 3) << 2)), to_tf32(v[i]));
+		}
 	}
 };
 
@@ -781,14 +822,16 @@ struct KPosTapProducer {
 		for (int i = 0; i < NR; i++) {
 			uint32_t ent;
 			asm volatile("ld.shared.b32 %0, [%1];" : "=r"(ent) : "r"(table + (warp + i * NPROD_WARPS) * 4));
-			v[i] = mask.test(ent) ? ldg_off(sb, ent >> TM::SH) : 0.0f;
+			v[i] = ldg_pred(sb + ((unsigned long long)(ent >> TM::SH) << 2), mask.test(ent));
 		}
 	}
 	__device__ __forceinline__ void store(uint32_t tile, const float (&v)[NV])
 	{
-		const uint32_t col = ((((uint32_t)lane >> 2) ^ ((uint32_t)warp & 7)) << 4) | (((uint32_t)lane & 3) << 2);
 		#pragma unroll
-		for (int i = 0; i < NR; i++) sts32(tile + (warp + i * NPROD_WARPS) * 128 + col, to_tf32(v[i]));
+		for (int i = 0; i < NR; i++) {
+			const uint32_t row = (uint32_t)(warp + i * NPROD_WARPS);
+			sts32(tile + row * 128 + (((((uint32_t)lane >> 2) ^ (row & 7)) << 4) | (((uint32_t)lane & 3) << 2)), to_tf32(v[i]));
+		}
 	}
 };
 
@@ -813,7 +856,7 @@ __device__ __forceinline__ uint32_t fetch16(const Operand& op, const uint16_t* _
 	}
 	ok = ok && ((unsigned)hh < (unsigned)op.H) && ((unsigned)ww < (unsigned)op.W);
 	const int off = ri.rbase + ki.kbase + hh * op.Wd + ww;
-	return ok ? ldg16(base + off) : 0u;
+	return ldg16_pred(base + off, ok);
 }
 
 // general MN-contiguous producer (any geometry; the slow path, e.g. a first layer with 3 input channels)
@@ -900,8 +943,8 @@ struct MnChanProducer16 {
 			#pragma unroll
 			for (int w = 0; w < 4; w++) {
 				const int j = i * CSTEP * 8 + 2 * w;
-				const uint32_t lo = (ok && j < cleft) ? ldg16(ptr + (size_t)((unsigned)j * (unsigned)op.ks0)) : 0u;
-				const uint32_t hi = (ok && j + 1 < cleft) ? ldg16(ptr + (size_t)((unsigned)(j + 1) * (unsigned)op.ks0)) : 0u;
+				const uint32_t lo = ldg16_pred(ptr + (size_t)((unsigned)j * (unsigned)op.ks0), ok && j < cleft);
+				const uint32_t hi = ldg16_pred(ptr + (size_t)((unsigned)(j + 1) * (unsigned)op.ks0), ok && j + 1 < cleft);
 				v[i * 4 + w] = pack16(lo, hi);
 			}
 		}
@@ -949,15 +992,17 @@ struct KDenseProducer16 {
 		const uint16_t* __restrict__ p = base + rowoff0;
 		#pragma unroll
 		for (int i = 0; i < NR; i++) {
-			v[i] = pack16(i < n0 ? ldg16(p + koff0) : 0u, i < n1 ? ldg16(p + koff1) : 0u);
+			v[i] = pack16(ldg16_pred(p + koff0, i < n0), ldg16_pred(p + koff1, i < n1));
 			p += step;
 		}
 	}
 	__device__ __forceinline__ void store(uint32_t tile, const float (&v)[NV])
 	{
-		const uint32_t col = ((((uint32_t)lane >> 2) ^ ((uint32_t)warp & 7)) << 4) | (((uint32_t)lane & 3) << 2);
 		#pragma unroll
-		for (int i = 0; i < NR; i++) sts32(tile + (warp + i * NPROD_WARPS) * 128 + col, __float_as_uint(v[i]));
+		for (int i = 0; i < NR; i++) {
+			const uint32_t row = (uint32_t)(warp + i * NPROD_WARPS);
+			sts32(tile + row * 128 + (((((uint32_t)lane >> 2) ^ (row & 7)) << 4) | (((uint32_t)lane & 3) << 2)), __float_as_uint(v[i]));
+		}
 	}
 };
 
@@ -986,15 +1031,17 @@ struct KPosDenseProducer16 {
 		const uint16_t* __restrict__ p = base + (rowoff0 + (long long)n * op.ks0 + pos);
 		#pragma unroll
 		for (int i = 0; i < NR; i++) {
-			v[i] = pack16(i < n0 ? ldg16(p) : 0u, i < n1 ? ldg16(p + 1) : 0u);
+			v[i] = pack16(ldg16_pred(p, i < n0), ldg16_pred(p + 1, i < n1));
 			p += step;
 		}
 	}
 	__device__ __forceinline__ void store(uint32_t tile, const float (&v)[NV])
 	{
-		const uint32_t col = ((((uint32_t)lane >> 2) ^ ((uint32_t)warp & 7)) << 4) | (((uint32_t)lane & 3) << 2);
 		#pragma unroll
-		for (int i = 0; i < NR; i++) sts32(tile + (warp + i * NPROD_WARPS) * 128 + col, __float_as_uint(v[i]));
+		for (int i = 0; i < NR; i++) {
+			const uint32_t row = (uint32_t)(warp + i * NPROD_WARPS);
+			sts32(tile + row * 128 + (((((uint32_t)lane >> 2) ^ (row & 7)) << 4) | (((uint32_t)lane & 3) << 2)), __float_as_uint(v[i]));
+		}
 	}
 };
 
@@ -1066,14 +1113,16 @@ struct KPosTapProducer16 {
 			uint32_t ent;
 			asm volatile("ld.shared.b32 %0, [%1];" : "=r"(ent) : "r"(table + (warp + i * NPROD_WARPS) * 4));
 			const uint32_t off = ent >> TM::SH;
-			v[i] = pack16(m0.test(ent) ? ldg16(sb0 + off) : 0u, m1.test(ent) ? ldg16(sb1 + off) : 0u);
+			v[i] = pack16(ldg16_pred(sb0 + off, m0.test(ent)), ldg16_pred(sb1 + off, m1.test(ent)));
 		}
 	}
 	__device__ __forceinline__ void store(uint32_t tile, const float (&v)[NV])
 	{
-		const uint32_t col = ((((uint32_t)lane >> 2) ^ ((uint32_t)warp & 7)) << 4) | (((uint32_t)lane & 3) << 2);
 		#pragma unroll
-		for (int i = 0; i < NR; i++) sts32(tile + (warp + i * NPROD_WARPS) * 128 + col, __float_as_uint(v[i]));
+		for (int i = 0; i < NR; i++) {
+			const uint32_t row = (uint32_t)(warp + i * NPROD_WARPS);
+			sts32(tile + row * 128 + (((((uint32_t)lane >> 2) ^ (row & 7)) << 4) | (((uint32_t)lane & 3) << 2)), __float_as_uint(v[i]));
+		}
 	}
 };
 
@@ -1110,9 +1159,9 @@ template <int ROWS, bool WIDE> struct ProducerSel<ROWS, MODE_K_POS_DENSE, WIDE, 
 template <int BN> struct Cfg {
 	static constexpr int STAGE_BYTES = (BM + BN) * 128;
 	static constexpr int STAGES = (192 * 1024) / STAGE_BYTES;          // 8 / 6 / 4 stages for BN = 64 / 128 / 256
-	static constexpr int TABLE_BYTES = (BM + (BN > 128 ? BN : 128)) * 16;  // one set of producer tables (two sets: per-tile ping-pong)
+	static constexpr int TABLE_BYTES = (BM + (BN > 128 ? BN : 128)) * 16;  // one set of producer tables per producer group
 	static constexpr int BAR_BYTES = 256;
-	static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * TABLE_BYTES + BAR_BYTES + 1024;  // + align slack
+	static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + NGROUPS * TABLE_BYTES + BAR_BYTES + 1024;  // + align slack
 	static constexpr int TMEM_COLS = 2 * BN;                           // double-buffered accumulator (power of two >= 32)
 };
 
@@ -1124,12 +1173,16 @@ struct Work {
 __device__ __forceinline__ Work decode_work(const GemmParams& p, int t)
 {
 	Work w;
-	w.n_tile = t % p.tiles_n;           // n fastest: CTAs running together share the activation tile through L2
-	t /= p.tiles_n;
-	w.m_tile = t % p.tiles_m;
-	t /= p.tiles_m;
-	w.split = t % p.splits;
-	w.group = t / p.splits;
+	// n fastest: CTAs running together share the activation tile through L2
+	uint32_t u = (uint32_t)t, q = fdiv(u, p.fd_tiles_n);
+	w.n_tile = (int)(u - q * (uint32_t)p.tiles_n);
+	u = q;
+	q = fdiv(u, p.fd_tiles_m);
+	w.m_tile = (int)(u - q * (uint32_t)p.tiles_m);
+	u = q;
+	q = fdiv(u, p.fd_splits);
+	w.split = (int)(u - q * (uint32_t)p.splits);
+	w.group = (int)q;
 	w.kb_begin = w.split * p.kb_per_split;
 	w.kb_end = min(p.kblocks, w.kb_begin + p.kb_per_split);
 	return w;
@@ -1250,13 +1303,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) umma_gemm_kernel(const __grid_con
 	using EL = typename std::conditional<H16, uint16_t, float>::type;      // operand element as the producers see it
 	constexpr int BKE = H16 ? BK16 : BK;                                   // elements per k-block (one 128-byte row)
 	constexpr bool B_TMA = BMODE == MODE_TMA;
-	// k-blocks of global loads in flight per producer thread (register ring depth): as deep as the register budget allows,
-	// a k-block of scattered 128-byte row segments needs a full DRAM round trip
-	constexpr int PF = B_TMA ? 3 : 2;       // (measured: a deeper ring for the gather-gather modes spills and is slower)
 	extern __shared__ uint8_t smem_raw[];
 	const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
 	const uint32_t tables = smem0 + C::STAGES * C::STAGE_BYTES;
-	const uint32_t bars = tables + 2 * C::TABLE_BYTES;      // full[STAGES], empty[STAGES], acc_full[2], acc_empty[2], tmem ptr
+	const uint32_t bars = tables + NGROUPS * C::TABLE_BYTES;      // full[STAGES], empty[STAGES], acc_full[2], acc_empty[2], tmem ptr
 	const uint32_t bar_full = bars, bar_empty = bars + 8 * C::STAGES;
 	const uint32_t bar_accfull = bars + 16 * C::STAGES, bar_accempty = bar_accfull + 16;
 	const uint32_t tmem_slot = bar_accempty + 16;
@@ -1265,7 +1315,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) umma_gemm_kernel(const __grid_con
 	const int lane = threadIdx.x & 31;
 	const int total_work = p.tiles_m * p.tiles_n * p.groups * p.splits;
 
-	if (warp == NPROD_WARPS) {
+	if (warp == MMA_WARP) {
 		if (lane == 0) {
 			for (int s = 0; s < C::STAGES; s++) {
 				mbar_init(bar_full + 8 * s, NPROD_WARPS + (B_TMA ? 1 : 0));
@@ -1288,112 +1338,112 @@ __global__ void __launch_bounds__(NTHREADS, 1) umma_gemm_kernel(const __grid_con
 	uint32_t tmem_base;
 	asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-	if (warp < NPROD_WARPS) {
+	if (warp < NPROD_WARPS_ALL) {
 		// ===================== producers =====================
+		setmaxnreg_inc<REGS_PROD>();
+		const int grp = warp / NPROD_WARPS, gw = warp % NPROD_WARPS;       // producer group, warp within it
 		typename ProducerSel<BM, AMODE, CDIV, H16>::type prodA;
 		typename ProducerSel<BN, BMODE, false, H16>::type prodB;
 		using PA = decltype(prodA);
 		using PB = decltype(prodB);
-		float va[PF][PA::NV];
-		float vb[PF][PB::NV];
-		int tk[PF], tr[PF];                                  // TMA coordinates of the slot (k element, filter row)
+		float va[PA::NV];
+		float vb[PB::NV];
+		const uint32_t tset = tables + (uint32_t)grp * C::TABLE_BYTES;
 
-		// load cursor (runs PF-1 k-blocks ahead of the store cursor)
-		int lwork = blockIdx.x, lkb = 0, lseq = 0;
+		// cursor over the CTA's k-block sequence (work units x their k-blocks); this group owns every NGROUPS-th k-block
+		int lwork = blockIdx.x, lkb = 0, inited = -1;
+		int stage = 0;
+		uint32_t phase = 0;
 		Work lw{};
 		bool lvalid = lwork < total_work;
 		if (lvalid) { lw = decode_work(p, lwork); lkb = lw.kb_begin; }
-		const EL* baseA = (const EL*)p.A.ptr;
-		const EL* baseB = (const EL*)p.B.ptr;
-		int issued = 0, done = 0;
-		int stage = 0;
-		uint32_t phase = 0;
-
-		auto issue_load = [&](float (&a)[PA::NV], float (&b)[PB::NV], int& k_elem, int& b_row) {
-			if (lkb == lw.kb_begin) {
-				// first k-block of a work unit: per-tile producer state + smem tables (ping-pong sets, one named barrier)
-				const uint32_t tset = tables + (uint32_t)(lseq & 1) * C::TABLE_BYTES;
-				prodA.init(p.A, lw.m_tile * BM, warp, lane, tset);
-				prodB.init(p.B, lw.n_tile * BN, warp, lane, tset + BM * 16);
-				baseA = (const EL*)p.A.ptr + (long long)lw.group * p.A.group_stride;
-				baseB = (const EL*)p.B.ptr + (long long)lw.group * p.B.group_stride;
-				named_bar_sync(1, NPROD);
-				lseq++;
-			}
-			prodA.load(p.A, baseA, lkb, a);
-			prodB.load(p.B, baseB, lkb, b);
-			k_elem = lkb * BKE;
-			b_row = lw.group * p.tma_rows_per_group + lw.n_tile * BN;
-			issued++;
-			if (++lkb == lw.kb_end) {
+		auto advance = [&](int n) {
+			// n k-blocks further: whole work units are skipped without decoding them
+			while (lvalid && n > 0) {
+				const int left = lw.kb_end - lkb;
+				if (n < left) { lkb += n; break; }
+				n -= left;
 				lwork += gridDim.x;
 				lvalid = lwork < total_work;
 				if (lvalid) { lw = decode_work(p, lwork); lkb = lw.kb_begin; }
 			}
 		};
-
-		#pragma unroll
-		for (int b = 0; b < PF - 1; b++)
-			if (lvalid) issue_load(va[b], vb[b], tk[b], tr[b]);
-
-		bool more = issued > 0;
-		while (more) {
-			#pragma unroll
-			for (int b = 0; b < PF; b++) {
-				if (lvalid) issue_load(va[(b + PF - 1) % PF], vb[(b + PF - 1) % PF], tk[(b + PF - 1) % PF], tr[(b + PF - 1) % PF]);
-				if (done == issued) { more = false; break; }
-				mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-				const uint32_t tileA = smem0 + stage * C::STAGE_BYTES;
-				if (B_TMA) {
-					if (warp == 0 && lane == 0) {
-						mbar_arrive_expect_tx(bar_full + 8 * stage, BN * 128);
-						tma_load_2d(tileA + BM * 128, &tmapB, tk[b], tr[b], bar_full + 8 * stage);
-					}
-				}
-				prodA.store(tileA, va[b]);
-				prodB.store(tileA + BM * 128, vb[b]);
-				fence_async_smem();
-				__syncwarp();
-				if (lane == 0) mbar_arrive(bar_full + 8 * stage);
-				if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
-				done++;
+		auto advance_stage = [&](int n) {
+			stage += n;
+			if (stage >= C::STAGES) { stage -= C::STAGES; phase ^= 1; }
+		};
+		advance(grp);
+		advance_stage(grp);
+		const EL* baseA = (const EL*)p.A.ptr;
+		const EL* baseB = (const EL*)p.B.ptr;
+		while (lvalid) {
+			if (inited != lwork) {
+				// first k-block this group sees of a work unit: per-tile producer state + the group's smem tables
+				named_bar_sync(1 + grp, NPROD);                       // every warp of the group is done reading the old tables
+				prodA.init(p.A, lw.m_tile * BM, gw, lane, tset);
+				prodB.init(p.B, lw.n_tile * BN, gw, lane, tset + BM * 16);
+				baseA = (const EL*)p.A.ptr + (long long)lw.group * p.A.group_stride;
+				baseB = (const EL*)p.B.ptr + (long long)lw.group * p.B.group_stride;
+				named_bar_sync(1 + grp, NPROD);
+				inited = lwork;
 			}
-		}
-	} else if (warp == NPROD_WARPS) {
-		// ===================== MMA issuer (one thread) =====================
-		const uint32_t idesc = H16 ? make_idesc_f16(BM, BN, p.ab_bf16) : make_idesc_tf32(BM, BN);
-		int stage = 0;
-		uint32_t phase = 0;
-		int as = 0;
-		uint32_t aphase = 0;
-		for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
-			const Work w = decode_work(p, work);
-			mbar_wait(bar_accempty + 8 * as, aphase ^ 1);        // epilogue has drained this accumulator buffer
-			tc_fence_after();
-			const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
-			for (int kb = w.kb_begin; kb < w.kb_end; kb++) {
-				mbar_wait(bar_full + 8 * stage, phase);
-				tc_fence_after();
-				if (lane == 0) {
-					const uint32_t tileA = smem0 + stage * C::STAGE_BYTES;
-					const uint64_t da = make_smem_desc(tileA), db = make_smem_desc(tileA + BM * 128);
-					#pragma unroll
-					for (int kk = 0; kk < 4; kk++) {       // 8 tf32 / 16 halves = 32 bytes per MMA: +2 in the (addr >> 4) field
-						if (H16) umma_f16(tmem_d, da + 2 * kk, db + 2 * kk, idesc, (kb > w.kb_begin || kk > 0) ? 1u : 0u);
-						else umma_tf32(tmem_d, da + 2 * kk, db + 2 * kk, idesc, (kb > w.kb_begin || kk > 0) ? 1u : 0u);
-					}
-					umma_commit(bar_empty + 8 * stage);
+			prodA.load(p.A, baseA, lkb, va);
+			prodB.load(p.B, baseB, lkb, vb);
+			mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+			const uint32_t tileA = smem0 + stage * C::STAGE_BYTES;
+			if (B_TMA) {
+				if (gw == 0 && lane == 0) {
+					mbar_arrive_expect_tx(bar_full + 8 * stage, BN * 128);
+					tma_load_2d(tileA + BM * 128, &tmapB, lkb * BKE, lw.group * p.tma_rows_per_group + lw.n_tile * BN, bar_full + 8 * stage);
 				}
-				__syncwarp();
-				if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
 			}
-			if (lane == 0) umma_commit(bar_accfull + 8 * as);
+			prodA.store(tileA, va);
+			prodB.store(tileA + BM * 128, vb);
+			fence_async_smem();
 			__syncwarp();
-			if (++as == 2) { as = 0; aphase ^= 1; }
+			if (lane == 0) mbar_arrive(bar_full + 8 * stage);
+			advance(NGROUPS);
+			advance_stage(NGROUPS);
 		}
-		tc_fence_before();
+	} else if (warp < EPI_WARP0) {
+		// ===================== MMA issuer (one thread of warp 16) =====================
+		setmaxnreg_dec<REGS_MMA>();
+		if (warp == MMA_WARP) {
+			const uint32_t idesc = H16 ? make_idesc_f16(BM, BN, p.ab_bf16) : make_idesc_tf32(BM, BN);
+			int stage = 0;
+			uint32_t phase = 0;
+			int as = 0;
+			uint32_t aphase = 0;
+			for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
+				const Work w = decode_work(p, work);
+				mbar_wait(bar_accempty + 8 * as, aphase ^ 1);        // epilogue has drained this accumulator buffer
+				tc_fence_after();
+				const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+				for (int kb = w.kb_begin; kb < w.kb_end; kb++) {
+					mbar_wait(bar_full + 8 * stage, phase);
+					tc_fence_after();
+					if (lane == 0) {
+						const uint32_t tileA = smem0 + stage * C::STAGE_BYTES;
+						const uint64_t da = make_smem_desc(tileA), db = make_smem_desc(tileA + BM * 128);
+						#pragma unroll
+						for (int kk = 0; kk < 4; kk++) {       // 8 tf32 / 16 halves = 32 bytes per MMA: +2 in the (addr >> 4) field
+							if (H16) umma_f16(tmem_d, da + 2 * kk, db + 2 * kk, idesc, (kb > w.kb_begin || kk > 0) ? 1u : 0u);
+							else umma_tf32(tmem_d, da + 2 * kk, db + 2 * kk, idesc, (kb > w.kb_begin || kk > 0) ? 1u : 0u);
+						}
+						umma_commit(bar_empty + 8 * stage);
+					}
+					__syncwarp();
+					if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+				}
+				if (lane == 0) umma_commit(bar_accfull + 8 * as);
+				__syncwarp();
+				if (++as == 2) { as = 0; aphase ^= 1; }
+			}
+			tc_fence_before();
+		}
 	} else {
 		// ===================== epilogue (4 warps; warp w may touch TMEM lanes 32*(w%4) .. +31) =====================
+		setmaxnreg_dec<REGS_EPI>();
 		const Epilogue& E = p.E;
 		const int lg = warp & 3;
 		int as = 0;
@@ -1440,7 +1490,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) umma_gemm_kernel(const __grid_con
 
 	tc_fence_before();
 	__syncthreads();
-	if (warp == NPROD_WARPS) {
+	if (warp == MMA_WARP) {
 		tc_fence_after();
 		tmem_dealloc(tmem_base, C::TMEM_COLS);
 	}
