@@ -50,14 +50,15 @@ constexpr int NGROUPS = 4;
 constexpr int NPROD_WARPS = 4;               // warps of one producer group
 constexpr int NPROD = NPROD_WARPS * 32;      // threads of one producer group
 constexpr int NPROD_WARPS_ALL = NGROUPS * NPROD_WARPS;
-constexpr int NEPI_WARPS = 4;
-// 24 warps = 6 warpgroups: 0-3 producer groups, 4 = MMA issuer (warp 16; 17-19 only give their registers away), 5 = epilogue.
-// The kernel starts at 80 registers per thread; setmaxnreg moves registers from the MMA / epilogue warpgroups to the
-// producers (a k-block of both operands in registers).  The pool is the launch allocation: 512*96 + 128*32 + 128*64 = 768*80.
+constexpr int NEPI_WARPS = 4;               // (halo kernel)
+constexpr int NEPI_WARPS_GEMM = 8;          // two warps per TMEM lane quadrant, alternating 16-column chunks
+// 28 warps = 7 warpgroups: 0-3 producer groups, 4 = MMA issuer (warp 16; 17-19 only give their registers away), 5-6 = epilogue.
+// The kernel starts at 72 registers per thread; setmaxnreg moves registers from the MMA / epilogue warpgroups to the
+// producers (a k-block of both operands in registers).  The pool is the launch allocation of 896*72 registers.
 constexpr int MMA_WARP = NPROD_WARPS_ALL;
 constexpr int EPI_WARP0 = NPROD_WARPS_ALL + 4;
-constexpr int NTHREADS = (EPI_WARP0 + NEPI_WARPS) * 32;
-constexpr int REGS_PROD = 96, REGS_MMA = 32, REGS_EPI = 64;
+constexpr int NTHREADS = (EPI_WARP0 + NEPI_WARPS_GEMM) * 32;
+constexpr int REGS_PROD = 88, REGS_MMA = 32, REGS_EPI = 56;    // 512*88 + 128*32 + 256*56 <= 896*72
 template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 constexpr int INVALID = -(1 << 28);
@@ -1323,7 +1324,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) umma_gemm_kernel(const __grid_con
 			}
 			for (int a = 0; a < 2; a++) {
 				mbar_init(bar_accfull + 8 * a, 1);
-				mbar_init(bar_accempty + 8 * a, NEPI_WARPS);
+				mbar_init(bar_accempty + 8 * a, NEPI_WARPS_GEMM);
 			}
 			fence_barrier_init();
 		}
@@ -1468,17 +1469,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) umma_gemm_kernel(const __grid_con
 			const int fast = E.c2i ? 4 : (E.out_kind != OUT_F32 ? 0 : (E.atomic ? ((addbias && E.bias_mode) ? 0 : 3) : (E.beta != 0.0f ? 0 : (E.bias_mode == 1 ? 2 : 1))));
 			const int hb = m1 * E.c2i_sh - E.c2i_ph, wb = m2 * E.c2i_sw - E.c2i_pw;
 
+			// this warp's chunks: columns half*16 + 32*i (the quadrant's other warp takes the chunks in between)
+			const int half = (warp - EPI_WARP0) >> 2;
+			constexpr int CSTRIDE = 2 * EPI_COLS;
 			uint32_t v0[EPI_COLS], v1[EPI_COLS];
-			tmem_ld16(tmem_d, v0);
+			const int cfirst = half * EPI_COLS;
+			if (cfirst < ncols) tmem_ld16(tmem_d + (uint32_t)cfirst, v0);
 			#pragma unroll 1
-			for (int c0 = 0; c0 < ncols; c0 += 2 * EPI_COLS) {
+			for (int c0 = cfirst; c0 < ncols; c0 += 2 * CSTRIDE) {
 				tmem_wait_ld(v0);
-				if (c0 + EPI_COLS < ncols) tmem_ld16(tmem_d + (uint32_t)(c0 + EPI_COLS), v1);
+				if (c0 + CSTRIDE < ncols) tmem_ld16(tmem_d + (uint32_t)(c0 + CSTRIDE), v1);
 				epilogue_chunk(E, v0, outp, biasp, bias_m, mvalid, addbias, w.n_tile * BN + c0, fast, hb, wb);
-				if (c0 + EPI_COLS < ncols) {
+				if (c0 + CSTRIDE < ncols) {
 					tmem_wait_ld(v1);
-					if (c0 + 2 * EPI_COLS < ncols) tmem_ld16(tmem_d + (uint32_t)(c0 + 2 * EPI_COLS), v0);
-					epilogue_chunk(E, v1, outp, biasp, bias_m, mvalid, addbias, w.n_tile * BN + c0 + EPI_COLS, fast, hb, wb);
+					if (c0 + 2 * CSTRIDE < ncols) tmem_ld16(tmem_d + (uint32_t)(c0 + 2 * CSTRIDE), v0);
+					epilogue_chunk(E, v1, outp, biasp, bias_m, mvalid, addbias, w.n_tile * BN + c0 + CSTRIDE, fast, hb, wb);
 				}
 			}
 			tc_fence_before();
