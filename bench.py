@@ -316,10 +316,10 @@ def gpuArm(args):
 	try:
 		with open(os.path.join(ROOT, "profiles", "r01_family_traffic.json")) as f:
 			captured = json.load(f)["families"]
-		key = "gemm" if top.startswith("gemm") else top
+		key = top if top in captured else ("gemm" if top.startswith("gemm") else top)
 		roofline["traffic"] = captured[key]["dram_bytes_per_launch"]
 		roofline["traffic_note"] = "dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over the family's launches in " \
-								   "profiles/r01r_launches.md (ncu, cold cache); algorithmic bytes per launch: %.0f" % (
+								   "profiles/r01z_launches.md (ncu, cold cache); algorithmic bytes per launch: %.0f" % (
 									   fam["bytes"] / max(1, fam["launches"]))
 	except Exception:      # noqa: BLE001 -- no capture committed
 		pass

@@ -11,7 +11,7 @@ import sys
 
 
 def family(name):
-	if "umma_gemm" in name:
+	if "umma_gemm" in name or "umma_halo" in name:
 		return "gemm"
 	if "bn_bwd" in name:
 		return "bn_bwd"
@@ -46,7 +46,13 @@ def main(path, jsonpath=None):
 	for rec in launches.values():
 		if "us" not in rec:
 			continue
-		for table, key in ((agg, rec["name"]), (fam, family(rec["name"]))):
+		famname = family(rec["name"])
+		# the engine's launches split like bench.py's families: a launch that moves more than 1 DRAM byte per 108 tensor flops
+		# cannot be told from the name, so the split uses what ncu measured -- DRAM GB/s above 1 TB/s with the tensor pipe under
+		# 30 % active is an HBM-bound launch (1x1 convolutions), the rest is tensor-pipe work
+		if famname == "gemm" and rec.get("tensor", 100.0) < 30.0 and rec.get("dram", 0.0) / max(rec["us"], 1e-9) / 1e3 > 1000.0:
+			famname = "gemm_hbm"
+		for table, key in ((agg, rec["name"]), (fam, famname)):
 			a = table[key]
 			a["n"] += 1
 			a["us"] += rec["us"]
