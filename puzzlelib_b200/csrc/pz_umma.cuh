@@ -1373,6 +1373,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) umma_gemm_kernel(const __grid_con
 			stage += n;
 			if (stage >= C::STAGES) { stage -= C::STAGES; phase ^= 1; }
 		};
+		// A group may run ahead of the MMAs by less than one lap of the stage ring only (the empty-barrier wait is a parity
+		// test): its consecutive k-blocks are NGROUPS apart, so NGROUPS <= STAGES.  (Measured: pairs of k-blocks per group --
+		// 64 loads in flight per thread -- change nothing, and need an 8-stage ring to be safe.)
+		static_assert(C::STAGES >= NGROUPS, "a producer group would lap the stage ring");
 		advance(grp);
 		advance_stage(grp);
 		const EL* baseA = (const EL*)p.A.ptr;
