@@ -221,6 +221,19 @@ int pz_conv2d_wgrad(int dtype, const pz_conv2d_desc* d, const void* x, const voi
 int pz_bias_grad(int dtype, const void* t, void* db, int64_t N, int64_t C, int64_t S, float alpha, float beta,
 				 void* stream);
 
+/* ---- training closure either side of the path
+ * pz_cross_entropy: Cuda/Kernels/Costs.py:77-106,133-157,213-247 (CostModule.crossEntropy after its softmax): probs
+ *   (samples, cases, spatial) fp32 row-major, labels (samples, spatial) int32, weights (cases,) fp32 or NULL;
+ *   grad = w_c * ((c == label) - p) / samples, *error += sum(-w_label * log(p_label)) / spatial  (error is NOT cleared here).
+ * pz_count_mismatch: Costs.py:178-182 (calcAccuracy): *out += number of i with x[i] != y[i] (int32 inputs, fp32 count).
+ * pz_sgd_nesterov: ElementWise.py:815-857; pz_adam: ElementWise.py:709-755 (mg / ms are fp32 whatever the parameter dtype). */
+int pz_cross_entropy(const void* probs, const void* labels, const void* weights, int64_t samples, int64_t cases, int64_t spatial,
+					 void* error, void* grad, void* stream);
+int pz_count_mismatch(const void* x, const void* y, int64_t n, void* out, void* stream);
+int pz_sgd_nesterov(int dtype, void* param, const void* grad, void* mom, float learn_rate, float mom_rate, int64_t n, void* stream);
+int pz_adam(int dtype, void* param, const void* grad, void* mg, void* ms, float learn_rate, float fix1, float fix2, float epsilon,
+			int64_t n, void* stream);
+
 /* ---- recurrent cells (Cuda/Source/Libs/CuDnnRnn.c:565-1000 cudnnRNNForwardTraining / BackwardData cell math; the matrix
    products are pz_gemm calls).  fp32; gate order in a 4H row: i, f, c, o (Cuda/Backend.py:264-306 linear layers 0..3) */
 int pz_lstm_cell_fwd(float* gates, const float* bw, const float* br, const float* c_prev, float* c_out, float* h_out, int64_t B,

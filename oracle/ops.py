@@ -700,3 +700,37 @@ def pool3d_bwd(x, dy, size=2, stride=2, pad=0, mode="max", dtype=np.float64):
 					cnt = size[0] * size[1] * size[2] if mode == "avgWithPad" else (d1 - d0) * (h1 - h0) * (w1 - w0)
 					dx[:, :, d0:d1, h0:h1, w0:w1] += (dy[:, :, do, p, q] / cnt)[:, :, None, None, None]
 	return dx
+
+
+# ================================================================================================ training closure
+def cross_entropy(scores, labels, weights=None, dtype=np.float64):
+	"""Softmax over axis 1 + cross-entropy cost as the reference computes it (Cuda/Kernels/Costs.py:77-106,133-157,213-247):
+	scores (N, C[, ...spatial]), labels (N[, ...spatial]) int.  Returns (error, grad) with
+	grad = w_c * ((c == label) - p) / N  (ascent direction) and error = sum(-w_label * log p_label) / spatial."""
+	x = np.asarray(scores, dtype)
+	N, C = x.shape[:2]
+	S = int(np.prod(x.shape[2:])) if x.ndim > 2 else 1
+	z = x.reshape(N, C, S)
+	p = np.exp(z - z.max(axis=1, keepdims=True))
+	p /= p.sum(axis=1, keepdims=True)
+	lab = np.asarray(labels).reshape(N, S)
+	onehot = (np.arange(C).reshape(1, C, 1) == lab.reshape(N, 1, S)).astype(dtype)
+	w = np.ones(C, dtype) if weights is None else np.asarray(weights, dtype)
+	grad = w.reshape(1, C, 1) * (onehot - p) / N
+	picked = np.take_along_axis(p, lab.reshape(N, 1, S), axis=1)[:, 0, :]
+	error = float((-w[lab] * np.log(picked)).sum() / S)
+	return error, grad.reshape(x.shape)
+
+
+def nesterov_update(param, grad, mom, lr, mr, dtype=np.float64):
+	"""reference: Cuda/Kernels/ElementWise.py:815-857 -- returns (param', mom')"""
+	p, g, m = (np.asarray(a, dtype) for a in (param, grad, mom))
+	return p + mr * mr * m + (1.0 + mr) * lr * g, mr * m + lr * g
+
+
+def adam_update(param, grad, mg, ms, lr, fix1, fix2, eps, dtype=np.float64):
+	"""reference: Cuda/Kernels/ElementWise.py:709-755 -- returns (param', mg', ms')"""
+	p, g, a, s = (np.asarray(v, dtype) for v in (param, grad, mg, ms))
+	a = a + fix1 * (g - a)
+	s = s + fix2 * (g * g - s)
+	return p + lr * a / (np.sqrt(s) + eps), a, s

@@ -565,6 +565,41 @@ class PoolModule:
 
 
 # ============================================================================================================ SharedArray
+# ============================================================================================================ costmod
+class CostModule:
+	"""reference: Cuda/Kernels/Costs.py:160-247 (the cross-entropy entry and the accuracy reduction of the training closure)"""
+
+	def __init__(self, backend):
+		self.backend = backend
+
+	def crossEntropy(self, scores, labels, weights=None, error=None, allocator=None):
+		"""softmax over axis 1 + cost; returns (error scalar on the device, grad) -- Costs.py:213-247"""
+		_requireArray(scores, "scores")
+		_requireArray(labels, "labels")
+		if scores.dtype != _f32 or labels.dtype != np.int32:
+			raise ValueError("crossEntropy needs float32 scores and int32 labels")
+
+		shape = scores.shape
+		if scores.ndim < 4:
+			scores = scores.reshape(*shape, *(1 for _ in range(4 - scores.ndim)))
+
+		softmax = self.backend.dnn.softmaxNd(scores, mode=self.backend.SoftMaxMode.spatial.value, allocator=allocator)
+		grad = GPUArray.empty(shape, _f32, allocator=allocator)
+		if error is None:
+			error = GPUArray.empty((), _f32, allocator=allocator)
+		error.fill(0.0)
+
+		samples, cases, spatial = scores.shape[0], scores.shape[1], prod(scores.shape[2:])
+		if labels.size != samples * spatial:
+			raise ValueError("labels must hold one class index per sample and position")
+		if weights is not None and (weights.dtype != _f32 or weights.size != cases):
+			raise ValueError("weights must be a float32 vector with one entry per class")
+
+		check(lib.pz_cross_entropy(softmax.ptr, labels.ptr, None if weights is None else weights.ptr, samples, cases, spatial,
+								   error.ptr, grad.ptr, None))
+		return error, grad
+
+
 class SharedArray:
 	"""One flat buffer with 16-byte aligned named views (reference: Cuda/Utils.py:19-64); the per-dtype flat
 	parameter / gradient buffers of Optimizer.setupGlobalState and the payload of the DP all-reduce."""
@@ -763,14 +798,14 @@ class B200Backend:
 
 		self.initmode = 0
 		self.blas, self.dnn = None, None
-		self.matmod, self.poolmod = None, None
+		self.matmod, self.poolmod, self.costmod = None, None, None
 		self.updateBackend(initmode)
 
 	def updateBackend(self, initmode):
 		if initmode >= 1 and self.dnn is None:
 			self.blas, self.dnn = BlasContext(self), DnnContext(self)
 		if initmode >= 2 and self.matmod is None:
-			self.matmod, self.poolmod = MatModule(self), PoolModule(self)
+			self.matmod, self.poolmod, self.costmod = MatModule(self), PoolModule(self), CostModule(self)
 		self.initmode = max(self.initmode, initmode)
 
 	# ---- kernel factories (reference attribute names: Cuda/GPUBackend.py:85-131)
@@ -829,6 +864,43 @@ class B200Backend:
 
 		def ker(param, grad, mom, learnRate, momRate, **kwargs):
 			check(lib.pz_sgd_momentum(dt, param.ptr, grad.ptr, mom.ptr, float(learnRate), float(momRate), param.size, None))
+
+		return ker
+
+	@staticmethod
+	def nesterovMomSGDKer(dtype):
+		dt = dtypeCode(dtype)
+
+		def ker(param, grad, mom, learnRate, momRate, **kwargs):
+			check(lib.pz_sgd_nesterov(dt, param.ptr, grad.ptr, mom.ptr, float(learnRate), float(momRate), param.size, None))
+
+		return ker
+
+	@staticmethod
+	def adamKer(dtype):
+		dt = dtypeCode(dtype)
+
+		def ker(param, grad, mg, ms, learnRate, fix1, fix2, epsilon, **kwargs):
+			if mg.dtype != _f32 or ms.dtype != _f32:
+				raise ValueError("adam moments must be float32")
+			check(lib.pz_adam(dt, param.ptr, grad.ptr, mg.ptr, ms.ptr, float(learnRate), float(fix1), float(fix2), float(epsilon),
+							  param.size, None))
+
+		return ker
+
+	@staticmethod
+	def getAccuracyKernel(name):
+		"""reference: Cuda/Kernels/Costs.py:172-182 -- `calcAccuracy(x, y)`: the number of positions where two int32 label
+		tensors differ, as a float32 device scalar"""
+		if name != "calcAccuracy":
+			raise NotImplementedError(name)
+
+		def ker(x, y, allocator=None):
+			if x.dtype != np.int32 or y.dtype != np.int32 or x.size != y.size:
+				raise ValueError("calcAccuracy needs two int32 tensors of one size")
+			out = GPUArray.zeros((), _f32, allocator=allocator)
+			check(lib.pz_count_mismatch(x.ptr, y.ptr, x.size, out.ptr, None))
+			return out
 
 		return ker
 

@@ -117,6 +117,10 @@ _SIGNATURES = {
 	"pz_add2": [c_int, _P, _P, _P, c_int64, _P],
 	"pz_cast": [c_int, _P, c_int, _P, c_int64, _P],
 	"pz_sgd_momentum": [c_int, _P, _P, _P, c_float, c_float, c_int64, _P],
+	"pz_sgd_nesterov": [c_int, _P, _P, _P, c_float, c_float, c_int64, _P],
+	"pz_adam": [c_int, _P, _P, _P, _P, c_float, c_float, c_float, c_float, c_int64, _P],
+	"pz_cross_entropy": [_P, _P, _P, c_int64, c_int64, c_int64, _P, _P, _P],
+	"pz_count_mismatch": [_P, _P, c_int64, _P, _P],
 	"pz_reduce_minmax": [c_int, _P, c_int64, c_int, _P, _P],
 	"pz_addvec2mat": [c_int, _P, _P, _P, c_int64, c_int64, c_int64, c_int, c_int64, _P],
 	"pz_matsum": [c_int, _P, _P, c_int64, c_int64, c_int64, c_int, c_float, c_float, _P],

@@ -1,4 +1,4 @@
-"""Optimizers on the hot path: `Optimizer` with the reference's local / GLOBAL-state modes, SGD and MomentumSGD.
+"""Optimizers on the hot path: `Optimizer` with the reference's local / GLOBAL-state modes, SGD, MomentumSGD, NesterovSGD, Adam.
 
 Global-state mode is the data-parallel hook: all parameters (and all gradients) of one dtype are re-homed into ONE flat
 `SharedArray`, module variables become views of it, and `update()` runs `nodeinfo.sumTensor("grad", flatGrad)` followed by
@@ -7,6 +7,7 @@ MomentumSGD.py:12-27).  With an NCCL `NodeInfo` and MomentumSGD the all-reduce a
 C call (pz_nccl_allreduce_sgd_momentum): the 1/P of the mean is folded into the update kernel, saving a full pass over
 the gradient buffer.
 """
+import math
 from collections import OrderedDict
 
 import numpy as np
@@ -168,6 +169,46 @@ class SGD(Optimizer):
 
 	def updateVar(self, var, state, stream=None):
 		backend().toVectorAddVectorKer(var.data.dtype)(var.data, var.grad, self.learnRate * var.learnRate)
+
+
+class NesterovSGD(SGD):
+	"""reference: Optimizers/NesterovSGD.py:12-27"""
+
+	def __init__(self, learnRate=1e-3, momRate=0.9, nodeinfo=None):
+		super().__init__(learnRate, nodeinfo)
+		self.momRate = None
+		self.setAttr("momRate", momRate)
+
+	def setupState(self, var):
+		return {"mom": gpuarray.zeros(var.data.shape, dtype=var.data.dtype)}
+
+	def updateVar(self, var, state, stream=None):
+		backend().nesterovMomSGDKer(var.data.dtype)(
+			var.data, var.grad, state["mom"], self.learnRate * var.learnRate, self.momRate * var.momRate
+		)
+
+
+class Adam(Optimizer):
+	"""reference: Optimizers/Adam.py:14-45 (bias correction folded into the step size, fp32 moments)"""
+
+	def __init__(self, alpha=1e-3, beta1=0.9, beta2=0.999, epsilon=1e-8, nodeinfo=None):
+		super().__init__(nodeinfo)
+		self.alpha, self.beta1, self.beta2, self.epsilon = None, None, None, None
+		self.setAttr("alpha", alpha)
+		self.setAttr("beta1", beta1)
+		self.setAttr("beta2", beta2)
+		self.setAttr("epsilon", epsilon)
+
+	def setupState(self, var):
+		return {"mg": gpuarray.zeros(var.data.shape, dtype=np.float32), "ms": gpuarray.zeros(var.data.shape, dtype=np.float32)}
+
+	def updateVar(self, var, state, stream=None):
+		fix1, fix2 = 1.0 - self.beta1 ** self.t, 1.0 - self.beta2 ** self.t
+		self.learnRate = self.alpha * math.sqrt(fix2) / fix1
+		backend().adamKer(var.data.dtype)(
+			var.data, var.grad, state["mg"], state["ms"], self.learnRate * var.learnRate, 1.0 - self.beta1, 1.0 - self.beta2,
+			self.epsilon
+		)
 
 
 class MomentumSGD(SGD):

@@ -830,3 +830,88 @@ def test_conv3d_pool3d_modules(bnd):
 	d1 = ops.pool3d_bwd(p1, g, 2, 1, 0, "avgNoPad")
 	d0 = ops.pool3d_bwd(y, d1, 2, 2, 0, "max")
 	assert relerr(net.grad.get(), ops.conv3d_bwd_data(d0, conv.W.get(), x.shape, 1, 1, 1)) < REL_TC
+
+
+# ------------------------------------------------------------------------------------------ training closure
+@pytest.mark.parametrize("shape", [(64, 10), (7, 1000), (5, 6, 3, 4), (1, 2)])
+@pytest.mark.parametrize("weighted", [False, True])
+def test_cross_entropy(bnd, shape, weighted):
+	# reference test: Cuda/Kernels/Costs.py:253-301 (crossEntropyTest / wceTest)
+	rng = np.random.RandomState(sum(shape))
+	scores = rng.randn(*shape).astype(np.float32)
+	labels = rng.randint(0, shape[1], (shape[0], ) + shape[2:]).astype(np.int32)
+	weights = (rng.rand(shape[1]) + 0.5).astype(np.float32) if weighted else None
+	err, grad = bnd.costmod.crossEntropy(G(bnd, scores), G(bnd, labels), None if weights is None else G(bnd, weights),
+										 allocator=bnd.memoryPool)
+	assert grad.shape == shape and err.shape == ()
+	want_err, want_grad = ops.cross_entropy(scores, labels, weights)
+	assert np.abs(grad.get() - want_grad).max() < 1e-6
+	assert abs(float(err.get()) - want_err) < 1e-4 * max(1.0, abs(want_err))
+
+
+def test_cross_entropy_cost_object_and_accuracy(bnd):
+	# Cost/CrossEntropy.py:27-55: error per sample, accumulated mean error, validation = fraction of wrong arg-max labels
+	from puzzlelib_b200.cost import CrossEntropy
+	rng = np.random.RandomState(12)
+	cost = CrossEntropy(maxlabels=10)
+	total = 0.0
+	for step in range(2):
+		scores = rng.randn(32, 10).astype(np.float32)
+		labels = rng.randint(0, 10, (32, )).astype(np.int32)
+		error, grad = cost(G(bnd, scores), G(bnd, labels))
+		want_err, want_grad = ops.cross_entropy(scores, labels)
+		total += want_err
+		assert abs(error - want_err / 32) < 1e-5
+		assert np.abs(grad.get() - want_grad).max() < 1e-6
+	assert abs(cost.getMeanError() - total / 64) < 1e-5
+	val = cost.validate(G(bnd, scores), G(bnd, labels))
+	assert abs(val - float((scores.argmax(axis=1) != labels).mean())) < 1e-7
+	maps = rng.randn(4, 5, 3, 3).astype(np.float32)
+	maplabels = rng.randint(0, 5, (4, 3, 3)).astype(np.int32)
+	assert abs(CrossEntropy().validate(G(bnd, maps), G(bnd, maplabels)) - float((maps.argmax(axis=1) != maplabels).mean())) < 1e-7
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float16])
+def test_nesterov_and_adam_kernels(bnd, dtype):
+	# reference tests: Optimizers/NesterovSGD.py:39-58, Optimizers/Adam.py:57-80 (calcTest)
+	rng = np.random.RandomState(3)
+	shape = (11, 13)
+	atol = 1e-5 if dtype == np.float32 else 2e-2
+	w, dw, mom = (rng.randn(*shape).astype(dtype) for _ in range(3))
+	gw, gm = G(bnd, w), G(bnd, mom)
+	bnd.nesterovMomSGDKer(np.dtype(dtype))(gw, G(bnd, dw), gm, 0.01, 0.9)
+	pw, pm = ops.nesterov_update(w, dw, mom, 0.01, 0.9)
+	assert np.abs(gw.get() - pw).max() < atol and np.abs(gm.get() - pm).max() < atol
+
+	ms = (1.0 + rng.randn(*shape) ** 2).astype(np.float32)
+	mg = rng.randn(*shape).astype(np.float32)
+	gw, gmg, gms = G(bnd, w), G(bnd, mg), G(bnd, ms)
+	bnd.adamKer(np.dtype(dtype))(gw, G(bnd, dw), gmg, gms, 0.0316, 0.1, 0.001, 1e-8)
+	pw, pa, ps = ops.adam_update(w, dw, mg, ms, 0.0316, 0.1, 0.001, 1e-8)
+	assert np.abs(gw.get() - pw).max() < atol
+	assert np.abs(gmg.get() - pa).max() < 1e-5 and np.abs(gms.get() - ps).max() < 1e-5
+
+
+def test_adam_and_nesterov_optimizers_train_a_linear_layer(bnd):
+	# Optimizers/Optimizer.py trainSimpleTest: the cost of a small regression goes down under every optimizer
+	from puzzlelib_b200 import modules as M
+	from puzzlelib_b200.cost import CrossEntropy
+	from puzzlelib_b200.optim import Adam, NesterovSGD
+	for make in (lambda: Adam(alpha=1e-2), lambda: NesterovSGD(learnRate=1e-1, momRate=0.9)):
+		np.random.seed(5)
+		rng = np.random.RandomState(5)
+		net = M.Sequential()
+		net.append(M.Linear(20, 4))
+		data = rng.randn(64, 20).astype(np.float32)
+		labels = (data[:, :4].argmax(axis=1)).astype(np.int32)
+		opt = make()
+		opt.setupOn(net)
+		cost = CrossEntropy()
+		errors = []
+		for step in range(40):
+			opt.zeroGradParams()
+			error, grad = cost(net(G(bnd, data)), G(bnd, labels))
+			net.backward(grad)
+			opt.update()
+			errors.append(float(error))
+		assert errors[-1] < 0.5 * errors[0], errors[::8]

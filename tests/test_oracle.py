@@ -314,3 +314,40 @@ def test_lstm_oracle_reverse_direction_is_the_time_flipped_forward():
 	dx_f, dp_f = ops.lstm_backward(x[::-1], params, cache_f, dy[::-1])
 	assert np.allclose(dx_r, dx_f[::-1])
 	assert all(np.allclose(dp_r[k], dp_f[k]) for k in dp_r)
+
+
+def test_cross_entropy_oracle_gradient_is_the_negated_derivative_of_the_error():
+	# the reference's costs emit ascent-direction gradients: grad = -d(error / N) / d(scores)  
+	rng = np.random.RandomState(4)
+	N, C, S = 3, 5, 2
+	scores, labels = rng.randn(N, C, S), rng.randint(0, C, (N, S))
+	weights = rng.rand(C) + 0.5
+	err, grad = ops.cross_entropy(scores, labels)
+	eps = 1e-6
+	for idx in [(0, 1, 0), (2, 4, 1), (1, 0, 1)]:
+		sp, sm = scores.copy(), scores.copy()
+		sp[idx] += eps
+		sm[idx] -= eps
+		num = (ops.cross_entropy(sp, labels)[0] - ops.cross_entropy(sm, labels)[0]) / (2 * eps)
+		assert abs(-num * S / N - grad[idx]) < 1e-6
+	# the weighted variant scales the gradient by the weight of the OUTPUT class c, not of the label (Costs.py:147), and
+	# the error by the weight of the label
+	werr, wgrad = ops.cross_entropy(scores, labels, weights)
+	assert np.allclose(wgrad, grad * weights.reshape(1, C, 1))
+	assert werr != err
+	# a 2-d problem is the spatial one with a single position
+	e2, g2 = ops.cross_entropy(scores[:, :, 0], labels[:, 0])
+	e4, g4 = ops.cross_entropy(scores[:, :, :1], labels[:, :1])
+	assert abs(e2 - e4) < 1e-12 and np.allclose(g2, g4[:, :, 0])
+
+
+def test_optimizer_update_oracles():
+	rng = np.random.RandomState(6)
+	p, g, m = rng.randn(7), rng.randn(7), rng.randn(7)
+	p1, m1 = ops.nesterov_update(p, g, m, 0.1, 0.9)
+	# Nesterov in the reference's form: classic momentum step followed by a look-ahead of the NEW momentum
+	assert np.allclose(m1, 0.9 * m + 0.1 * g) and np.allclose(p1, p + 0.9 * m1 + 0.1 * g)
+	a, s = rng.randn(7), rng.rand(7) + 1.0
+	p2, a2, s2 = ops.adam_update(p, g, a, s, 0.01, 0.1, 0.001, 1e-8)
+	assert np.allclose(a2, 0.9 * a + 0.1 * g) and np.allclose(s2, 0.999 * s + 0.001 * g * g)
+	assert np.allclose(p2, p + 0.01 * a2 / (np.sqrt(s2) + 1e-8))
