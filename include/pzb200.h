@@ -230,6 +230,17 @@ int pz_bias_grad(int dtype, const void* t, void* db, int64_t N, int64_t C, int64
 int pz_cross_entropy(const void* probs, const void* labels, const void* weights, int64_t samples, int64_t cases, int64_t spatial,
 					 void* error, void* grad, void* stream);
 int pz_count_mismatch(const void* x, const void* y, int64_t n, void* out, void* stream);
+/* axis permutation of a contiguous tensor (Cuda/Source/Libs/CuDnnMemory.c transpose / moveaxis / swapaxes):
+ * out (contiguous, extents out_shape[0..ndim)) [i0..] = in[sum_d i_d * in_stride[d]] (strides in elements), ndim <= 8 */
+int pz_permute(int itemsize, void* out, const void* in, int ndim, const int64_t* out_shape, const int64_t* in_stride, void* stream);
+/* random fills (Cuda/Source/Libs/CuRand.c:119-230): kind 0 = n raw uint32, 1 = n floats uniform in (a, b], 2 = n floats
+ * normal(mean a, stddev b).  Counter-based Philox4x32-10: the values are a function of (seed, offset, index) only; the caller
+ * advances offset by ceil(n / 4) per fill.  Not bit-compatible with cuRAND's XORWOW.
+ * pz_dropout (ElementWise.py:495-580): out = in * (rands[i / mapsize] < partition) / p; rands are uint32 for float32 data,
+ * uint16 for half / bfloat16; mapsize 1 = dropoutKer, H*W = dropout2dKer */
+int pz_rng_fill(int kind, void* out, int64_t n, uint64_t seed, uint64_t offset, float a, float b, void* stream);
+int pz_dropout(int dtype, void* out, const void* in, const void* rands, uint32_t partition, float p, int64_t n, int64_t mapsize,
+			   void* stream);
 int pz_sgd_nesterov(int dtype, void* param, const void* grad, void* mom, float learn_rate, float mom_rate, int64_t n, void* stream);
 int pz_adam(int dtype, void* param, const void* grad, void* mg, void* ms, float learn_rate, float fix1, float fix2, float epsilon,
 			int64_t n, void* stream);

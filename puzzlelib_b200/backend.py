@@ -17,6 +17,8 @@ from enum import Enum
 from collections import OrderedDict
 from ctypes import byref
 
+import ctypes
+
 import numpy as np
 
 from . import driver
@@ -303,6 +305,92 @@ class DnnContext:
 		out = GPUArray(grad.shape, grad.dtype, allocator=allocator) if out is None else _checkOut(out, grad.shape, grad.dtype)
 		check(lib.pz_softmax_bwd(dtypeCode(grad.dtype), int(mode), outdata.ptr, grad.ptr, out.ptr, N, C, S, None))
 		return out
+
+	# ------------------------------------------------------------------------------------------ memory reorganisation
+	# (reference: Cuda/Source/Libs/CuDnnMemory.c, Backend/Memory.py:43-66)
+	def transpose(self, data, axes=None, out=None, allocator=None):
+		_requireArray(data, "data")
+		data.enforceContiguous()
+		ndim = data.ndim
+		axes = tuple(reversed(range(ndim))) if axes is None else tuple(int(a) % ndim if ndim else 0 for a in axes)
+		if sorted(axes) != list(range(ndim)):
+			raise ValueError("axes is not a permutation of the tensor's axes")
+
+		shape = tuple(data.shape[a] for a in axes)
+		if out is None:
+			out = GPUArray(shape, data.dtype, allocator=allocator)
+		else:
+			_checkOut(out, shape, data.dtype)
+
+		if ndim == 0 or data.size == 0:
+			return out
+
+		elemstrides = [st // data.dtype.itemsize for st in data.strides]
+		oshape = (ctypes.c_int64 * ndim)(*shape)
+		istride = (ctypes.c_int64 * ndim)(*[elemstrides[a] for a in axes])
+		check(lib.pz_permute(data.dtype.itemsize, out.ptr, data.ptr, ndim, oshape, istride, None))
+		return out
+
+	def moveaxis(self, data, src, dst, out=None, allocator=None):
+		ndim = data.ndim
+		if not (0 <= src < ndim and 0 <= dst < ndim):
+			raise ValueError("axis is out of range")
+		axes = [a for a in range(ndim) if a != src]
+		axes.insert(dst, src)
+		return self.transpose(data, tuple(axes), out=out, allocator=allocator)
+
+	def swapaxes(self, data, axis1, axis2, out=None, allocator=None):
+		ndim = data.ndim
+		if not (0 <= axis1 < ndim and 0 <= axis2 < ndim):
+			raise ValueError("axis is out of range")
+		axes = list(range(ndim))
+		axes[axis1], axes[axis2] = axes[axis2], axes[axis1]
+		return self.transpose(data, tuple(axes), out=out, allocator=allocator)
+
+	@staticmethod
+	def _depthLayout(data):
+		maps = [ary.shape[1] for ary in data]
+		height, width = max(ary.shape[2] for ary in data), max(ary.shape[3] for ary in data)
+		return maps, height, width
+
+	def depthConcat(self, data, out=None, allocator=None):
+		"""maps of different sizes stacked along the channel axis, each centred in the largest plane, zero elsewhere"""
+		for ary in data:
+			self._check4d(ary, "data")
+		batchsize, dtype = data[0].shape[0], data[0].dtype
+		if any(ary.shape[0] != batchsize or ary.dtype != dtype for ary in data):
+			raise ValueError("tensors must share batch size and datatype")
+
+		maps, height, width = self._depthLayout(data)
+		shape = (batchsize, sum(maps), height, width)
+		if out is None:
+			out = GPUArray.zeros(shape, dtype, allocator=allocator)
+		else:
+			_checkOut(out, shape, dtype)
+			out.fill(0)
+
+		c0 = 0
+		for ary in data:
+			_, c, h, w = ary.shape
+			oh, ow = (height - h) // 2, (width - w) // 2
+			if ary.size:
+				ary.copy(out=out[:, c0:c0 + c, oh:oh + h, ow:ow + w])
+			c0 += c
+		return out
+
+	def depthSplit(self, grad, indata, allocator=None):
+		self._check4d(grad, "grad")
+		maps, height, width = self._depthLayout(indata)
+		if grad.shape != (indata[0].shape[0], sum(maps), height, width):
+			raise ValueError("grad has invalid shape %s" % (grad.shape, ))
+
+		ingrads, c0 = [], 0
+		for ary in indata:
+			_, c, h, w = ary.shape
+			oh, ow = (height - h) // 2, (width - w) // 2
+			ingrads.append(grad[:, c0:c0 + c, oh:oh + h, ow:ow + w].copy(allocator=allocator))
+			c0 += c
+		return ingrads
 
 	# ------------------------------------------------------------------------------------------ batch norm
 	@staticmethod
@@ -600,6 +688,34 @@ class CostModule:
 		return error, grad
 
 
+# ============================================================================================================ rng
+class RandomNumberGenerator:
+	"""reference: Cuda/Source/Libs/CuRand.c (the generator object behind `gpuarray.globalRng`): fillInteger / fillUniform /
+	fillNormal of a whole gpuarray.  Philox4x32-10 on the device; (seed, offset) is the whole state."""
+
+	def __init__(self, type=None, seed=0):
+		self.type = "philox4x32-10" if type is None else type
+		self.seed = int(seed) & 0xffffffffffffffff
+		self.offset = 0
+
+	def _fill(self, kind, ary, a, b, dtype):
+		_requireArray(ary, "ary")
+		ary.enforceContiguous()
+		if ary.dtype != dtype:
+			raise ValueError("unsupported gpuarray dtype")
+		check(lib.pz_rng_fill(kind, ary.ptr, ary.size, self.seed, self.offset, float(a), float(b), None))
+		self.offset += (ary.size + 3) // 4
+
+	def fillInteger(self, ary):
+		self._fill(0, ary, 0.0, 0.0, np.dtype(np.uint32) if ary.dtype == np.uint32 else np.dtype(np.int32))
+
+	def fillUniform(self, ary, minval=0.0, maxval=1.0):
+		self._fill(1, ary, minval, maxval, _f32)
+
+	def fillNormal(self, ary, mean=0.0, stddev=1.0):
+		self._fill(2, ary, mean, stddev, _f32)
+
+
 class SharedArray:
 	"""One flat buffer with 16-byte aligned named views (reference: Cuda/Utils.py:19-64); the per-dtype flat
 	parameter / gradient buffers of Optimizer.setupGlobalState and the payload of the DP all-reduce."""
@@ -792,9 +908,9 @@ class B200Backend:
 			logger.debug("Using device #%s (%s), %d SMs", deviceIdx, self.device.name(), driver.Device.smCount())
 
 		self.memoryPool = driver.MemoryPool()
+		self.globalRng = RandomNumberGenerator(seed=int(np.random.randint(np.iinfo(np.int64).max, dtype=np.int64)))
 		self.streamManager = QueueManager(driver.Stream)
 		self.eventManager = QueueManager(driver.Event)
-		self.globalRng = None
 
 		self.initmode = 0
 		self.blas, self.dnn = None, None
@@ -903,6 +1019,29 @@ class B200Backend:
 			return out
 
 		return ker
+
+	@staticmethod
+	def _dropoutKer(dtype, mapped):
+		dt = dtypeCode(dtype)
+		parttype = np.dtype(np.uint32) if np.dtype(dtype) == _f32 else np.dtype(np.uint16)
+
+		def ker(outdata, indata, b, v, p, mapsize=1, **kwargs):
+			_noSlice(kwargs)
+			if b.dtype != parttype or b.size * (mapsize if mapped else 1) < indata.size:
+				raise ValueError("dropout needs one %s random word per %s" % (parttype, "map" if mapped else "element"))
+			check(lib.pz_dropout(dt, outdata.ptr, indata.ptr, b.ptr, int(v), float(p), indata.size, int(mapsize) if mapped else 1, None))
+
+		return ker
+
+	@classmethod
+	def dropoutKer(cls, dtype):
+		"""reference: Cuda/Kernels/ElementWise.py:495-536 -- ker(outdata, indata, rands, partition, p)"""
+		return cls._dropoutKer(dtype, False)
+
+	@classmethod
+	def dropout2dKer(cls, dtype):
+		"""reference: ElementWise.py:539-580 -- ker(outdata, indata, rands, partition, p, mapsize): one word per feature map"""
+		return cls._dropoutKer(dtype, True)
 
 	@staticmethod
 	def add2Ker(dtype):

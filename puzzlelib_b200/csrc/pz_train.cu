@@ -182,3 +182,175 @@ int pz_adam(int dtype, void* param, const void* grad, void* mg, void* ms, float 
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------ axis permutation
+// reference: Cuda/Source/Libs/CuDnnMemory.c (cudnnTransformTensor-based transpose / moveaxis / swapaxes).  One thread per
+// output element: coalesced writes, gathered reads through the read-only path.  out[i0..ik] = in[sum_d i_d * stride_in[d]].
+namespace {
+
+constexpr int kMaxDims = 8;
+struct PermuteGeo {
+	int ndim;
+	unsigned shape[kMaxDims];          // output shape
+	long long stride[kMaxDims];        // input element stride of every output axis
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) permute_kernel(T* __restrict__ out, const T* __restrict__ in, PermuteGeo g, long long total)
+{
+	for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
+		long long rem = i, off = 0;
+		#pragma unroll
+		for (int d = kMaxDims - 1; d >= 0; d--) {
+			if (d < g.ndim) {
+				const long long q = rem / g.shape[d];
+				off += (rem - q * g.shape[d]) * g.stride[d];
+				rem = q;
+			}
+		}
+		out[i] = in[off];
+	}
+}
+
+}  // namespace
+
+extern "C" int pz_permute(int itemsize, void* out, const void* in, int ndim, const int64_t* out_shape, const int64_t* in_stride,
+						  void* stream)
+{
+	PZ_REQUIRE(ndim >= 1 && ndim <= kMaxDims, "permute: between 1 and %d axes are supported (got %d)", kMaxDims, ndim);
+	PermuteGeo g{};
+	g.ndim = ndim;
+	long long total = 1;
+	for (int d = 0; d < ndim; d++) {
+		PZ_REQUIRE(out_shape[d] >= 0 && out_shape[d] < (1ll << 32), "permute: bad extent");
+		g.shape[d] = (unsigned)out_shape[d];
+		g.stride[d] = in_stride[d];
+		total *= out_shape[d];
+	}
+	if (total == 0) return PZ_OK;
+	PzProfScope prof(PZ_PROF_ELTWISE, pz_stream(stream), 0.0, 2.0 * (double)total * itemsize);
+	const unsigned grid = grid_for(total);
+	switch (itemsize) {
+		case 1: permute_kernel<uint8_t><<<grid, kThreads, 0, pz_stream(stream)>>>((uint8_t*)out, (const uint8_t*)in, g, total); break;
+		case 2: permute_kernel<uint16_t><<<grid, kThreads, 0, pz_stream(stream)>>>((uint16_t*)out, (const uint16_t*)in, g, total); break;
+		case 4: permute_kernel<uint32_t><<<grid, kThreads, 0, pz_stream(stream)>>>((uint32_t*)out, (const uint32_t*)in, g, total); break;
+		case 8: permute_kernel<uint64_t><<<grid, kThreads, 0, pz_stream(stream)>>>((uint64_t*)out, (const uint64_t*)in, g, total); break;
+		default: pz_set_error(PZ_ERR_UNSUPPORTED, "permute: unsupported item size %d", itemsize); return PZ_ERR_UNSUPPORTED;
+	}
+	pz_count_launch(1);
+	PZ_LAUNCH_CHECK();
+	return PZ_OK;
+}
+
+// ------------------------------------------------------------------------------------------ random fills + dropout
+// reference: Cuda/Source/Libs/CuRand.c:119-230 (fillInteger / fillUniform / fillNormal of a generator object),
+// Cuda/Kernels/ElementWise.py:495-580 (dropoutKer, dropout2dKer).  The generator is counter-based (Philox4x32-10, the
+// published Random123 algorithm): element i of a fill is a pure function of (seed, offset + i / 4), so fills are
+// reproducible from (seed, offset) and need no state in device memory; it is NOT bit-compatible with cuRAND's XORWOW stream.
+namespace {
+
+__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1)
+{
+	const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+	const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+	const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+	c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+}
+
+__device__ __forceinline__ void philox4x32(unsigned long long counter, unsigned long long seed, uint32_t (&out)[4])
+{
+	uint32_t c[4] = {(uint32_t)counter, (uint32_t)(counter >> 32), 0u, 0u};
+	uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+	#pragma unroll
+	for (int r = 0; r < 10; r++) {
+		philox_round(c, k0, k1);
+		k0 += 0x9E3779B9u;
+		k1 += 0xBB67AE85u;
+	}
+	out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
+}
+
+// kind 0: raw 32-bit integers; 1: uniform in (lo, hi]; 2: normal(mean = lo, stddev = hi) by Box-Muller
+__global__ void __launch_bounds__(kThreads) rng_fill_kernel(void* __restrict__ out, long long n, unsigned long long seed,
+														   unsigned long long offset, int kind, float lo, float hi)
+{
+	const long long quads = (n + 3) / 4;
+	for (long long q = (long long)blockIdx.x * kThreads + threadIdx.x; q < quads; q += (long long)gridDim.x * kThreads) {
+		uint32_t r[4];
+		philox4x32(offset + (unsigned long long)q, seed, r);
+		float f[4];
+		if (kind == 1) {
+			#pragma unroll
+			for (int e = 0; e < 4; e++) f[e] = lo + (hi - lo) * ((float)r[e] * 2.3283064365386963e-10f + 2.3283064365386963e-10f * 0.5f);
+		} else if (kind == 2) {
+			#pragma unroll
+			for (int e = 0; e < 4; e += 2) {
+				const float u1 = (float)r[e] * 2.3283064365386963e-10f + 2.3283064365386963e-10f * 0.5f;
+				const float u2 = (float)r[e + 1] * 2.3283064365386963e-10f;
+				const float rad = sqrtf(-2.0f * logf(u1));
+				float sn, cs;
+				sincospif(2.0f * u2, &sn, &cs);
+				f[e] = lo + hi * rad * cs;
+				f[e + 1] = lo + hi * rad * sn;
+			}
+		}
+		#pragma unroll
+		for (int e = 0; e < 4; e++) {
+			const long long i = q * 4 + e;
+			if (i < n) {
+				if (kind == 0) ((uint32_t*)out)[i] = r[e];
+				else ((float*)out)[i] = f[e];
+			}
+		}
+	}
+}
+
+// out = x * (b < v) / p with one random word per element (mapsize = 1) or per map of `mapsize` elements (dropout2d)
+template <typename T, typename B>
+__global__ void __launch_bounds__(kThreads) dropout_kernel(T* __restrict__ out, const T* __restrict__ in, const B* __restrict__ b,
+														  unsigned v, float p, long long n, int mapsize)
+{
+	for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kThreads) {
+		const B word = b[mapsize == 1 ? i : i / mapsize];
+		out[i] = from_f<T>(to_f(in[i]) * ((unsigned)word < v ? 1.0f : 0.0f) / p);
+	}
+}
+
+}  // namespace
+
+extern "C" int pz_rng_fill(int kind, void* out, int64_t n, uint64_t seed, uint64_t offset, float a, float b, void* stream)
+{
+	PZ_REQUIRE(kind >= 0 && kind <= 2, "rng fill: unknown kind %d", kind);
+	if (n <= 0) return PZ_OK;
+	rng_fill_kernel<<<grid_for((n + 3) / 4), kThreads, 0, pz_stream(stream)>>>(out, (long long)n, seed, offset, kind, a, b);
+	pz_count_launch(1);
+	PZ_LAUNCH_CHECK();
+	return PZ_OK;
+}
+
+extern "C" int pz_dropout(int dtype, void* out, const void* in, const void* rands, uint32_t partition, float p, int64_t n,
+						  int64_t mapsize, void* stream)
+{
+	PZ_REQUIRE(p > 0.0f && mapsize >= 1 && mapsize < (1ll << 31), "dropout: bad arguments");
+	if (n <= 0) return PZ_OK;
+	PzProfScope prof(PZ_PROF_ELTWISE, pz_stream(stream), 0.0, 3.0 * (double)n * pz_dtype_size(dtype));
+	const unsigned grid = grid_for(n);
+	switch (dtype) {
+		case PZ_F32:
+			dropout_kernel<float, uint32_t><<<grid, kThreads, 0, pz_stream(stream)>>>((float*)out, (const float*)in, (const uint32_t*)rands,
+																					  partition, p, (long long)n, (int)mapsize);
+			break;
+		case PZ_F16:
+			dropout_kernel<__half, uint16_t><<<grid, kThreads, 0, pz_stream(stream)>>>((__half*)out, (const __half*)in, (const uint16_t*)rands,
+																					   partition, p, (long long)n, (int)mapsize);
+			break;
+		case PZ_BF16:
+			dropout_kernel<__nv_bfloat16, uint16_t><<<grid, kThreads, 0, pz_stream(stream)>>>(
+				(__nv_bfloat16*)out, (const __nv_bfloat16*)in, (const uint16_t*)rands, partition, p, (long long)n, (int)mapsize);
+			break;
+		default: pz_set_error(PZ_ERR_UNSUPPORTED, "unsupported dtype %d", dtype); return PZ_ERR_UNSUPPORTED;
+	}
+	pz_count_launch(1);
+	PZ_LAUNCH_CHECK();
+	return PZ_OK;
+}

@@ -16,7 +16,7 @@ from enum import Enum
 import numpy as np
 
 from . import Config
-from .shim import gpuarray, Dnn, Blas, MatVec, Pool, PoolMode, ConvFwdAlgo, ConvBwdDataAlgo, ConvBwdFilterAlgo, memoryPool, \
+from .shim import gpuarray, Dnn, Blas, MatVec, Memory, Pool, PoolMode, ConvFwdAlgo, ConvBwdDataAlgo, ConvBwdFilterAlgo, memoryPool, \
 	backend, Rnn
 from .driver import bfloat16
 
@@ -1383,6 +1383,206 @@ class Flatten(Module):
 
 	def gradShapeFrom(self, shape):
 		return (shape[0], ) + self.inshape[1:]
+
+	def calcMode(self, T):
+		self.calctype = T
+
+
+class Dropout(Module):
+	"""reference: Modules/Dropout.py:12-95 (train: one random word per element, keep where word < partition and rescale by 1/(1-p);
+	eval: identity).  `slicing` is not supported."""
+
+	def __init__(self, p=0.5, rng=None, slicing=None, inplace=False, name=None):
+		super().__init__(name)
+		if slicing is not None:
+			raise NotImplementedError("slicing")
+		self.p = p
+		self.partition, self.rands = None, None
+		self.rng = backend().globalRng if rng is None else rng
+		self.inplace = inplace
+
+	def updateData(self, data):
+		if not self.train:
+			self.data = data
+			return
+
+		self.data = data if self.inplace else gpuarray.empty(data.shape, dtype=data.dtype, allocator=memoryPool())
+		parttype = np.uint32 if data.dtype == np.float32 else np.uint16
+		nwords = (data.nbytes + 3) // 4
+		words = gpuarray.empty((nwords, ), dtype=np.uint32, allocator=memoryPool())
+		self.rng.fillInteger(words)
+		self.rands = words.view(parttype)
+
+		p = 1.0 - self.p
+		self.partition = int(p * np.iinfo(parttype).max)
+		backend().dropoutKer(data.dtype)(self.data, data, self.rands, self.partition, np.float32(p))
+
+	def updateGrad(self, grad):
+		if not self.train:
+			self.grad = grad
+			return
+		self.grad = grad if self.inplace else gpuarray.empty(grad.shape, dtype=grad.dtype, allocator=memoryPool())
+		backend().dropoutKer(grad.dtype)(self.grad, grad, self.rands, self.partition, 1.0 - self.p)
+
+	def dataShapeFrom(self, shape):
+		return shape
+
+	def gradShapeFrom(self, shape):
+		return shape
+
+	def reset(self):
+		super().reset()
+		self.rands = None
+
+	def calcMode(self, T):
+		if np.dtype(T) not in _floatTypes():
+			raise ModuleError("Unsupported dtype %s" % T)
+		self.calctype = T
+
+
+class Transpose(Module):
+	"""reference: Modules/Transpose.py:7-45"""
+
+	def __init__(self, axes=None, name=None):
+		super().__init__(name)
+		self.axes = axes
+		if axes is None:
+			self.invaxes = None
+		else:
+			self.invaxes = [0] * len(axes)
+			for i, axis in enumerate(axes):
+				self.invaxes[axis] = i
+
+	def updateData(self, data):
+		self.data = Memory.transpose(data, self.axes)
+
+	def updateGrad(self, grad):
+		self.grad = Memory.transpose(grad, self.invaxes)
+
+	def checkDataShape(self, shape):
+		if self.axes is not None and len(shape) != len(self.axes):
+			raise ModuleError("Data dimension needs to be %d, (data has %d)" % (len(self.axes), len(shape)))
+
+	checkGradShape = checkDataShape
+
+	def dataShapeFrom(self, shape):
+		return tuple(shape[axis] for axis in (self.axes if self.axes is not None else reversed(range(len(shape)))))
+
+	def gradShapeFrom(self, shape):
+		return tuple(shape[axis] for axis in (self.invaxes if self.invaxes is not None else reversed(range(len(shape)))))
+
+	def calcMode(self, T):
+		self.calctype = T
+
+
+class MoveAxis(Module):
+	"""reference: Modules/MoveAxis.py:7-60"""
+
+	def __init__(self, src, dst, name=None):
+		super().__init__(name)
+		if src == dst:
+			raise ModuleError("Trivial axis move is treated as error")
+		self.src, self.dst = src, dst
+
+	def updateData(self, data):
+		self.data = Memory.moveaxis(data, self.src, self.dst)
+
+	def updateGrad(self, grad):
+		self.grad = Memory.moveaxis(grad, self.dst, self.src)
+
+	def checkDataShape(self, shape):
+		ln = max(self.src, self.dst)
+		if len(shape) - 1 < ln:
+			raise ModuleError("Data dimension needs to be at least %d, (data has %d)" % (ln + 1, len(shape)))
+
+	checkGradShape = checkDataShape
+
+	@staticmethod
+	def _moved(shape, src, dst):
+		axes = [a for a in range(len(shape)) if a != src]
+		axes.insert(dst, src)
+		return tuple(shape[a] for a in axes)
+
+	def dataShapeFrom(self, shape):
+		return self._moved(shape, self.src, self.dst)
+
+	def gradShapeFrom(self, shape):
+		return self._moved(shape, self.dst, self.src)
+
+	def calcMode(self, T):
+		self.calctype = T
+
+
+class SwapAxes(Module):
+	"""reference: Modules/SwapAxes.py:7-55"""
+
+	def __init__(self, axis1, axis2, name=None):
+		super().__init__(name)
+		if axis1 == axis2:
+			raise ModuleError("Trivial axes swap is treated as error")
+		self.axis1, self.axis2 = (axis2, axis1) if axis1 > axis2 else (axis1, axis2)
+
+	def updateData(self, data):
+		self.data = Memory.swapaxes(data, self.axis1, self.axis2)
+
+	def updateGrad(self, grad):
+		self.grad = Memory.swapaxes(grad, self.axis1, self.axis2)
+
+	def checkDataShape(self, shape):
+		if len(shape) - 1 < self.axis2:
+			raise ModuleError("Data dimension needs to be at least %d, (data has %d)" % (self.axis2 + 1, len(shape)))
+
+	checkGradShape = checkDataShape
+
+	def dataShapeFrom(self, shape):
+		shape = list(shape)
+		shape[self.axis1], shape[self.axis2] = shape[self.axis2], shape[self.axis1]
+		return tuple(shape)
+
+	gradShapeFrom = dataShapeFrom
+
+	def calcMode(self, T):
+		self.calctype = T
+
+
+class DepthConcat(Module):
+	"""reference: Modules/DepthConcat.py:7-70 (Inception-style join of branches with different plane sizes)"""
+
+	def __init__(self, name=None):
+		super().__init__(name)
+		self.movesData = True
+
+	def updateData(self, data):
+		self.data = Memory.depthConcat(data)
+
+	def updateGrad(self, grad):
+		self.grad = Memory.depthSplit(grad, self.inData)
+
+	def checkDataShape(self, shapes):
+		if not isinstance(shapes, list):
+			raise ModuleError("Data must be list of tensors")
+		for shape in shapes:
+			if len(shape) != 4:
+				raise ModuleError("Data must consist of 4d tensors")
+			if shape[0] != shapes[0][0]:
+				raise ModuleError("Inconsistency in batch size")
+
+	def dataShapeFrom(self, shapes):
+		depth, h, w = 0, 0, 0
+		for shape in shapes:
+			depth += shape[1]
+			h, w = max(h, shape[2]), max(w, shape[3])
+		return shapes[0][0], depth, h, w
+
+	def checkGradShape(self, shape):
+		if len(shape) != 4:
+			raise ModuleError("Grad must be 4d tensor")
+		gradshape = self.dataShapeFrom([data.shape for data in self.inData])
+		if shape != gradshape:
+			raise ModuleError("Bad grad shape (%s given, %s expected)" % (shape, gradshape))
+
+	def gradShapeFrom(self, shape):
+		return [data.shape for data in self.inData]
 
 	def calcMode(self, T):
 		self.calctype = T

@@ -239,6 +239,30 @@ class MatVec:
 		return backend().matmod.argmax(tensor, axis, memoryPool())
 
 
+class Memory:
+	"""reference: Backend/Memory.py:43-66"""
+
+	@staticmethod
+	def depthConcat(data):
+		return backend().dnn.depthConcat(data, allocator=memoryPool())
+
+	@staticmethod
+	def depthSplit(grad, indata):
+		return backend().dnn.depthSplit(grad, indata, allocator=memoryPool())
+
+	@staticmethod
+	def moveaxis(data, src, dst):
+		return backend().dnn.moveaxis(data, src, dst, allocator=memoryPool())
+
+	@staticmethod
+	def swapaxes(data, axis1, axis2):
+		return backend().dnn.swapaxes(data, axis1, axis2, allocator=memoryPool())
+
+	@staticmethod
+	def transpose(data, axes):
+		return backend().dnn.transpose(data, axes, allocator=memoryPool())
+
+
 class Pool:
 	"""reference: Backend/Kernels/Pool.py:38-56"""
 

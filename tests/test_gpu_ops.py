@@ -915,3 +915,116 @@ def test_adam_and_nesterov_optimizers_train_a_linear_layer(bnd):
 			opt.update()
 			errors.append(float(error))
 		assert errors[-1] < 0.5 * errors[0], errors[::8]
+
+
+# ------------------------------------------------------------------------------------------ memory reorganisation
+@pytest.mark.parametrize("dtype", [np.float32, np.float16])
+def test_transpose_moveaxis_swapaxes(bnd, dtype):
+	# reference tests: Cuda/Kernels/Memory.py:221-260 (every permutation / axis pair of these shapes)
+	import itertools
+	rng = np.random.RandomState(0)
+	for shape in [(10, ), (10, 3), (10, 3, 5, 4, 2)]:
+		host = rng.randn(*shape).astype(dtype)
+		data = G(bnd, host)
+		for axes in itertools.permutations(range(len(shape))):
+			assert np.array_equal(bnd.dnn.transpose(data, axes=axes, allocator=bnd.memoryPool).get(), np.transpose(host, axes))
+		for a, b in itertools.product(range(len(shape)), repeat=2):
+			assert np.array_equal(bnd.dnn.moveaxis(data, a, b, allocator=bnd.memoryPool).get(), np.moveaxis(host, a, b))
+			assert np.array_equal(bnd.dnn.swapaxes(data, a, b, allocator=bnd.memoryPool).get(), np.swapaxes(host, a, b))
+	assert np.array_equal(bnd.dnn.transpose(G(bnd, host)).get(), host.T)
+	with pytest.raises(ValueError):
+		bnd.dnn.transpose(data, axes=(0, 0, 1, 2, 3))
+	big = rng.randn(64, 49, 512).astype(np.float32)
+	assert np.array_equal(bnd.dnn.transpose(G(bnd, big), axes=(0, 2, 1)).get(), big.transpose(0, 2, 1))
+
+
+def test_depth_concat_and_split(bnd):
+	# reference test: Cuda/Kernels/Memory.py:263-296 (maps centred in the largest plane)
+	rng = np.random.RandomState(1)
+	hosts = [rng.randn(3, 4, 3, 3).astype(np.float32), rng.randn(3, 2, 6, 6).astype(np.float32), rng.randn(3, 5, 4, 4).astype(np.float32)]
+	arys = [G(bnd, h) for h in hosts]
+	out = bnd.dnn.depthConcat(arys, allocator=bnd.memoryPool)
+	want = np.zeros((3, 11, 6, 6), np.float32)
+	want[:, :4, 1:4, 1:4], want[:, 4:6], want[:, 6:, 1:5, 1:5] = hosts
+	assert np.array_equal(out.get(), want)
+	hostgrad = rng.randn(*want.shape).astype(np.float32)
+	grads = bnd.dnn.depthSplit(G(bnd, hostgrad), arys, allocator=bnd.memoryPool)
+	for got, ref in zip(grads, [hostgrad[:, :4, 1:4, 1:4], hostgrad[:, 4:6], hostgrad[:, 6:, 1:5, 1:5]]):
+		assert np.array_equal(got.get(), ref)
+
+
+def test_memory_modules(bnd):
+	# Modules/Transpose.py, MoveAxis.py, SwapAxes.py, DepthConcat.py: forward reorganises, backward undoes it
+	from puzzlelib_b200 import modules as M
+	rng = np.random.RandomState(2)
+	x = rng.randn(4, 3, 5, 2).astype(np.float32)
+	for mod, fwd in ((M.Transpose(axes=(2, 0, 3, 1)), lambda a: a.transpose(2, 0, 3, 1)), (M.MoveAxis(1, 3), lambda a: np.moveaxis(a, 1, 3)),
+					 (M.SwapAxes(0, 2), lambda a: np.swapaxes(a, 0, 2))):
+		out = mod(G(bnd, x))
+		assert np.array_equal(out.get(), fwd(x))
+		mod.backward(out)
+		assert np.array_equal(mod.grad.get(), x)
+	cat = M.DepthConcat()
+	a, b = rng.randn(2, 3, 4, 4).astype(np.float32), rng.randn(2, 1, 2, 2).astype(np.float32)
+	out = cat([G(bnd, a), G(bnd, b)])
+	assert out.shape == (2, 4, 4, 4) and np.array_equal(out.get()[:, 3:, 1:3, 1:3], b)
+	cat.backward(out)
+	assert np.array_equal(cat.grad[0].get(), a) and np.array_equal(cat.grad[1].get(), b)
+
+
+def test_rng_fills_are_reproducible_and_well_distributed(bnd):
+	# reference: Cuda/Source/Libs/CuRand.c fillInteger / fillUniform / fillNormal (moments and range checks; the stream itself is
+	# Philox here, XORWOW there)
+	from puzzlelib_b200.backend import RandomNumberGenerator
+	n = 1 << 20
+	a, b = RandomNumberGenerator(seed=77), RandomNumberGenerator(seed=77)
+	x, y = bnd.GPUArray.empty((n, ), np.uint32), bnd.GPUArray.empty((n + 3, ), np.uint32)
+	a.fillInteger(x)
+	b.fillInteger(y)
+	hx = x.get()
+	assert np.array_equal(hx, y.get()[:n])                       # a function of (seed, offset, index) only
+	a.fillInteger(x)
+	assert not np.array_equal(hx, x.get())                        # the offset advances
+	bits = np.unpackbits(hx.view(np.uint8))
+	assert abs(bits.mean() - 0.5) < 2e-3 and len(np.unique(hx)) > 0.999 * n
+	u = bnd.GPUArray.empty((n, ), np.float32)
+	a.fillUniform(u, -2.0, 3.0)
+	hu = u.get()
+	assert hu.min() > -2.0 and hu.max() <= 3.0 and abs(hu.mean() - 0.5) < 1e-2 and abs(hu.var() - 25.0 / 12.0) < 2e-2
+	a.fillNormal(u, 1.0, 2.0)
+	hn = u.get()
+	assert abs(hn.mean() - 1.0) < 1e-2 and abs(hn.std() - 2.0) < 1e-2 and abs(((hn - 1.0) ** 3).mean()) < 0.1
+	assert abs((np.abs(hn - 1.0) < 2.0).mean() - 0.6827) < 5e-3
+	with pytest.raises(ValueError):
+		a.fillUniform(x)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float16])
+def test_dropout_kernel_and_module(bnd, dtype):
+	# reference: Cuda/Kernels/ElementWise.py:495-580, Modules/Dropout.py:36-75
+	from puzzlelib_b200 import modules as M
+	rng = np.random.RandomState(8)
+	shape = (8, 6, 5, 7)
+	x = rng.randn(*shape).astype(dtype)
+	parttype = np.uint32 if dtype == np.float32 else np.uint16
+	words = rng.randint(0, np.iinfo(parttype).max, size=x.size, dtype=np.int64).astype(parttype)
+	v, p = int(0.7 * np.iinfo(parttype).max), 0.7
+	out = bnd.GPUArray.empty(shape, dtype)
+	bnd.dropoutKer(np.dtype(dtype))(out, G(bnd, x), G(bnd, words), v, np.float32(p))
+	want = (x.astype(np.float32) * (words.reshape(shape) < v) / np.float32(p)).astype(dtype)
+	assert np.array_equal(out.get(), want)
+	mapwords = words[:shape[0] * shape[1]]
+	bnd.dropout2dKer(np.dtype(dtype))(out, G(bnd, x), G(bnd, mapwords), v, np.float32(p), shape[2] * shape[3])
+	want2 = (x.astype(np.float32) * (mapwords.reshape(shape[0], shape[1], 1, 1) < v) / np.float32(p)).astype(dtype)
+	assert np.array_equal(out.get(), want2)
+
+	mod = M.Dropout(p=0.3)
+	mod.calcMode(dtype)
+	big = np.ones((64, 1024), dtype)
+	y = mod(G(bnd, big)).get().astype(np.float32)
+	kept = y != 0
+	assert abs(kept.mean() - 0.7) < 0.02 and np.allclose(y[kept], 1.0 / 0.7, rtol=2e-3)
+	mod.backward(G(bnd, big))
+	assert np.array_equal(mod.grad.get().astype(np.float32) != 0, kept)      # the same mask on the way back
+	mod.evalMode()
+	assert np.array_equal(mod(G(bnd, big)).get(), big)
