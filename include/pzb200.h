@@ -238,6 +238,13 @@ int pz_permute(int itemsize, void* out, const void* in, int ndim, const int64_t*
  * advances offset by ceil(n / 4) per fill.  Not bit-compatible with cuRAND's XORWOW.
  * pz_dropout (ElementWise.py:495-580): out = in * (rands[i / mapsize] < partition) / p; rands are uint32 for float32 data,
  * uint16 for half / bfloat16; mapsize 1 = dropoutKer, H*W = dropout2dKer */
+/* local response normalisation (Cuda/Source/Libs/CuDnnNorm.c:329-690; formulas Cuda/Wrappers/CuDnnNorm.py:185-268):
+ * mode 0 = across maps (crossMapLRN), 1 = within a map (mapLRN, no means tensor); window [i - (n-1)/2, i + n - (n-1)/2) clipped.
+ * pz_lrn_bwd needs `tmp`: N*C*H*W floats of scratch. */
+int pz_lrn_fwd(int dtype, int mode, const void* x, void* y, int64_t N, int64_t C, int64_t H, int64_t W, int n, float alpha, float beta,
+			   float K, void* stream);
+int pz_lrn_bwd(int dtype, int mode, const void* x, const void* grad, void* dx, void* tmp, int64_t N, int64_t C, int64_t H, int64_t W,
+			   int n, float alpha, float beta, float K, void* stream);
 int pz_rng_fill(int kind, void* out, int64_t n, uint64_t seed, uint64_t offset, float a, float b, void* stream);
 int pz_dropout(int dtype, void* out, const void* in, const void* rands, uint32_t partition, float p, int64_t n, int64_t mapsize,
 			   void* stream);

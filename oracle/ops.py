@@ -734,3 +734,33 @@ def adam_update(param, grad, mg, ms, lr, fix1, fix2, eps, dtype=np.float64):
 	a = a + fix1 * (g - a)
 	s = s + fix2 * (g * g - s)
 	return p + lr * a / (np.sqrt(s) + eps), a, s
+
+
+def lrn(x, N, alpha, beta, K, across_maps, grad=None, dtype=np.float64):
+	"""Local response normalisation and its gradient by the host formulas of the reference's tests
+	(Cuda/Wrappers/CuDnnNorm.py:185-268): window [i - (N-1)//2, i + N - (N-1)//2) clipped, over maps (across_maps) or over the
+	N x N neighbourhood inside a map.  Returns y, or (y, dx) when grad is given."""
+	x = np.asarray(x, dtype)
+	B, C, H, W = x.shape
+	lb = (N - 1) // 2
+	la = N - lb
+	scale = alpha / N if across_maps else alpha / N ** 2
+
+	def window_sum(t):
+		out = np.zeros_like(t)
+		if across_maps:
+			for c in range(C):
+				out[:, c] = t[:, max(0, c - lb):min(C, c + la)].sum(axis=1)
+		else:
+			for y in range(H):
+				for xx in range(W):
+					out[:, :, y, xx] = t[:, :, max(0, y - lb):min(H, y + la), max(0, xx - lb):min(W, xx + la)].sum(axis=(2, 3))
+		return out
+
+	norms = K + scale * window_sum(x * x)
+	y = x / norms ** beta
+	if grad is None:
+		return y
+	g = np.asarray(grad, dtype)
+	dx = g / norms ** beta - 2.0 * beta * scale * x * window_sum(g * x / norms ** (beta + 1))
+	return y, dx

@@ -392,6 +392,41 @@ class DnnContext:
 			c0 += c
 		return ingrads
 
+	# ------------------------------------------------------------------------------------------ local response normalisation
+	# (reference: Backend/Dnn.py:93-111, Cuda/Source/Libs/CuDnnNorm.c:329-690)
+	def _lrn(self, mode, data, N, alpha, beta, K, out, allocator):
+		self._check4d(data, "data")
+		data.enforceContiguous()
+		out = GPUArray(data.shape, data.dtype, allocator=allocator) if out is None else _checkOut(out, data.shape, data.dtype)
+		check(lib.pz_lrn_fwd(dtypeCode(data.dtype), mode, data.ptr, out.ptr, *data.shape, int(N), float(alpha), float(beta), float(K), None))
+		return out
+
+	def _lrnBackward(self, mode, data, grad, N, alpha, beta, K, out, allocator):
+		self._check4d(data, "data")
+		if grad.shape != data.shape or grad.dtype != data.dtype:
+			raise ValueError("invalid grad gpuarray data layout")
+		out = GPUArray(data.shape, data.dtype, allocator=allocator) if out is None else _checkOut(out, data.shape, data.dtype)
+		tmp = GPUArray(data.shape, _f32, allocator=allocator)
+		check(lib.pz_lrn_bwd(dtypeCode(data.dtype), mode, data.ptr, grad.ptr, out.ptr, tmp.ptr, *data.shape, int(N), float(alpha),
+							 float(beta), float(K), None))
+		return out
+
+	def crossMapLRN(self, data, N=5, alpha=1e-4, beta=0.75, K=2.0, out=None, allocator=None):
+		return self._lrn(0, data, N, alpha, beta, K, out, allocator)
+
+	def crossMapLRNBackward(self, data, outdata, grad, N=5, alpha=1e-4, beta=0.75, K=2.0, out=None, allocator=None):
+		return self._lrnBackward(0, data, grad, N, alpha, beta, K, out, allocator)
+
+	def mapLRN(self, data, means=None, N=5, alpha=1e-4, beta=0.75, K=2.0, out=None, allocator=None):
+		if means is not None:
+			raise NotImplementedError("mapLRN with a means tensor")
+		return self._lrn(1, data, N, alpha, beta, K, out, allocator)
+
+	def mapLRNBackward(self, data, grad, means=None, N=5, alpha=1e-4, beta=0.75, K=2.0, out=None, allocator=None):
+		if means is not None:
+			raise NotImplementedError("mapLRN with a means tensor")
+		return self._lrnBackward(1, data, grad, N, alpha, beta, K, out, allocator)
+
 	# ------------------------------------------------------------------------------------------ batch norm
 	@staticmethod
 	def _bnGeometry(data, mode):

@@ -354,3 +354,117 @@ extern "C" int pz_dropout(int dtype, void* out, const void* in, const void* rand
 	PZ_LAUNCH_CHECK();
 	return PZ_OK;
 }
+
+// ------------------------------------------------------------------------------------------ local response normalisation
+// reference: Cuda/Source/Libs/CuDnnNorm.c:329-690 (cudnnLRNCrossChannel*, cudnnDivisiveNormalization*), host formulas of
+// Cuda/Wrappers/CuDnnNorm.py:185-268.  norm_i = K + alpha / |N|^d * sum_{j in win(i)} x_j^2, win(i) = [i - lb, i + la) clipped,
+// lb = (N - 1) / 2, la = N - lb; d = 1 across maps (mode 0), d = 2 within a map (mode 1).
+//   y_i  = x_i * norm_i^-beta
+//   dx_i = g_i * norm_i^-beta - (2 alpha beta / |N|^d) * x_i * sum_{j in win(i)} g_j x_j norm_j^-(beta + 1)
+namespace {
+
+struct LrnGeo {
+	int C, H, W, n, lb, la, mode;
+	float scale, beta, K;              // scale = alpha / N^d
+};
+
+template <typename T>
+__device__ __forceinline__ float lrn_norm(const T* __restrict__ x, const LrnGeo& g, long long img, int c, int h, int w)
+{
+	float s = 0.0f;
+	if (g.mode == 0) {
+		const long long plane = (long long)g.H * g.W, pos = (long long)h * g.W + w;
+		for (int j = max(0, c - g.lb); j < min(g.C, c + g.la); j++) { const float v = to_f(x[img + j * plane + pos]); s = fmaf(v, v, s); }
+	} else {
+		const long long base = img + (long long)c * g.H * g.W;
+		for (int yy = max(0, h - g.lb); yy < min(g.H, h + g.la); yy++)
+			for (int xx = max(0, w - g.lb); xx < min(g.W, w + g.la); xx++) { const float v = to_f(x[base + (long long)yy * g.W + xx]); s = fmaf(v, v, s); }
+	}
+	return g.K + g.scale * s;
+}
+
+// pass 0: y = x * norm^-beta.  pass 1: tmp = g * x * norm^-(beta+1).  pass 2: dx from g, x, tmp.
+template <typename T, int PASS>
+__global__ void __launch_bounds__(kThreads) lrn_kernel(const T* __restrict__ x, const T* __restrict__ grad, T* __restrict__ out,
+													  float* __restrict__ tmp, LrnGeo g, long long total)
+{
+	for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
+		const int w = (int)(i % g.W);
+		long long r = i / g.W;
+		const int h = (int)(r % g.H);
+		r /= g.H;
+		const int c = (int)(r % g.C);
+		const long long img = (r / g.C) * (long long)g.C * g.H * g.W;
+		const float norm = lrn_norm(x, g, img, c, h, w);
+		const float xv = to_f(x[i]);
+		if (PASS == 0) {
+			out[i] = from_f<T>(xv * powf(norm, -g.beta));
+		} else if (PASS == 1) {
+			tmp[i] = to_f(grad[i]) * xv * powf(norm, -(g.beta + 1.0f));
+		} else {
+			float s = 0.0f;
+			if (g.mode == 0) {
+				const long long plane = (long long)g.H * g.W, pos = (long long)h * g.W + w;
+				for (int j = max(0, c - g.lb); j < min(g.C, c + g.la); j++) s += tmp[img + j * plane + pos];
+			} else {
+				const long long base = img + (long long)c * g.H * g.W;
+				for (int yy = max(0, h - g.lb); yy < min(g.H, h + g.la); yy++)
+					for (int xx = max(0, w - g.lb); xx < min(g.W, w + g.la); xx++) s += tmp[base + (long long)yy * g.W + xx];
+			}
+			out[i] = from_f<T>(to_f(grad[i]) * powf(norm, -g.beta) - 2.0f * g.beta * g.scale * xv * s);
+		}
+	}
+}
+
+template <typename T>
+int lrn_launch(int pass, const void* x, const void* grad, void* out, float* tmp, const LrnGeo& g, long long total, void* stream)
+{
+	const unsigned grid = grid_for(total);
+	cudaStream_t s = pz_stream(stream);
+	if (pass == 0) lrn_kernel<T, 0><<<grid, kThreads, 0, s>>>((const T*)x, nullptr, (T*)out, nullptr, g, total);
+	else {
+		lrn_kernel<T, 1><<<grid, kThreads, 0, s>>>((const T*)x, (const T*)grad, nullptr, tmp, g, total);
+		lrn_kernel<T, 2><<<grid, kThreads, 0, s>>>((const T*)x, (const T*)grad, (T*)out, tmp, g, total);
+		pz_count_launch(1);
+	}
+	pz_count_launch(1);
+	PZ_LAUNCH_CHECK();
+	return PZ_OK;
+}
+
+int lrn_geo(LrnGeo& g, int mode, int64_t C, int64_t H, int64_t W, int n, float alpha, float beta, float K)
+{
+	PZ_REQUIRE(mode == 0 || mode == 1, "lrn: unknown mode %d", mode);
+	PZ_REQUIRE(n >= 1 && C > 0 && H > 0 && W > 0 && C < (1ll << 31) && H < (1ll << 31) && W < (1ll << 31), "lrn: bad geometry");
+	g.C = (int)C; g.H = (int)H; g.W = (int)W;
+	g.n = n; g.lb = (n - 1) / 2; g.la = n - g.lb; g.mode = mode;
+	g.scale = mode == 0 ? alpha / (float)n : alpha / ((float)n * (float)n);
+	g.beta = beta; g.K = K;
+	return PZ_OK;
+}
+
+}  // namespace
+
+extern "C" int pz_lrn_fwd(int dtype, int mode, const void* x, void* y, int64_t N, int64_t C, int64_t H, int64_t W, int n, float alpha,
+						  float beta, float K, void* stream)
+{
+	LrnGeo g{};
+	int st = lrn_geo(g, mode, C, H, W, n, alpha, beta, K);
+	if (st != PZ_OK) return st;
+	const long long total = (long long)N * C * H * W;
+	if (total <= 0) return PZ_OK;
+	PzProfScope prof(PZ_PROF_ELTWISE, pz_stream(stream), 0.0, 2.0 * (double)total * pz_dtype_size(dtype));
+	PZ_TRAIN_DISPATCH(dtype, lrn_launch<T>(0, x, nullptr, y, nullptr, g, total, stream));
+}
+
+extern "C" int pz_lrn_bwd(int dtype, int mode, const void* x, const void* grad, void* dx, void* tmp, int64_t N, int64_t C, int64_t H,
+						  int64_t W, int n, float alpha, float beta, float K, void* stream)
+{
+	LrnGeo g{};
+	int st = lrn_geo(g, mode, C, H, W, n, alpha, beta, K);
+	if (st != PZ_OK) return st;
+	const long long total = (long long)N * C * H * W;
+	if (total <= 0) return PZ_OK;
+	PzProfScope prof(PZ_PROF_ELTWISE, pz_stream(stream), 0.0, 3.0 * (double)total * pz_dtype_size(dtype));
+	PZ_TRAIN_DISPATCH(dtype, lrn_launch<T>(1, x, grad, dx, (float*)tmp, g, total, stream));
+}

@@ -1028,3 +1028,20 @@ def test_dropout_kernel_and_module(bnd, dtype):
 	assert np.array_equal(mod.grad.get().astype(np.float32) != 0, kept)      # the same mask on the way back
 	mod.evalMode()
 	assert np.array_equal(mod(G(bnd, big)).get(), big)
+
+
+@pytest.mark.parametrize("dtype,atol", [(np.float32, 1e-5), (np.float16, 2e-2)])
+def test_lrn_across_and_within_maps(bnd, dtype, atol):
+	# reference tests: Cuda/Wrappers/CuDnnNorm.py:185-268 (mapLRN2dTest, crossMapLRN2dTest) + larger / even-window cases
+	rng = np.random.RandomState(14)
+	for shape, N in [((2, 2, 9, 10), 5), ((2, 10, 2, 3), 5), ((3, 17, 6, 7), 4), ((1, 3, 5, 5), 7)]:
+		x, g = rng.randn(*shape).astype(dtype), rng.randn(*shape).astype(dtype)
+		alpha, beta, K = 1.0, 0.5, 2.0
+		y = bnd.dnn.crossMapLRN(G(bnd, x), N=N, alpha=alpha, beta=beta, K=K, allocator=bnd.memoryPool)
+		dx = bnd.dnn.crossMapLRNBackward(G(bnd, x), y, G(bnd, g), N=N, alpha=alpha, beta=beta, K=K, allocator=bnd.memoryPool)
+		wy, wdx = ops.lrn(x, N, alpha, beta, K, True, grad=g)
+		assert np.abs(y.get() - wy).max() < atol and np.abs(dx.get() - wdx).max() < 4 * atol
+		y = bnd.dnn.mapLRN(G(bnd, x), N=N, alpha=alpha, beta=beta, K=K, allocator=bnd.memoryPool)
+		dx = bnd.dnn.mapLRNBackward(G(bnd, x), G(bnd, g), N=N, alpha=alpha, beta=beta, K=K, allocator=bnd.memoryPool)
+		wy, wdx = ops.lrn(x, N, alpha, beta, K, False, grad=g)
+		assert np.abs(y.get() - wy).max() < atol and np.abs(dx.get() - wdx).max() < 4 * atol

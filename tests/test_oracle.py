@@ -351,3 +351,17 @@ def test_optimizer_update_oracles():
 	p2, a2, s2 = ops.adam_update(p, g, a, s, 0.01, 0.1, 0.001, 1e-8)
 	assert np.allclose(a2, 0.9 * a + 0.1 * g) and np.allclose(s2, 0.999 * s + 0.001 * g * g)
 	assert np.allclose(p2, p + 0.01 * a2 / (np.sqrt(s2) + 1e-8))
+
+
+def test_lrn_oracle_gradient_matches_finite_differences_for_odd_windows():
+	rng = np.random.RandomState(10)
+	x, g = rng.randn(2, 6, 4, 5), rng.randn(2, 6, 4, 5)
+	for across in (True, False):
+		y, dx = ops.lrn(x, 3, 0.7, 0.75, 2.0, across, grad=g)
+		eps = 1e-6
+		for idx in [(0, 0, 0, 0), (1, 3, 2, 4), (0, 5, 3, 1)]:
+			xp, xm = x.copy(), x.copy()
+			xp[idx] += eps
+			xm[idx] -= eps
+			num = ((ops.lrn(xp, 3, 0.7, 0.75, 2.0, across) - ops.lrn(xm, 3, 0.7, 0.75, 2.0, across)) * g).sum() / (2 * eps)
+			assert abs(num - dx[idx]) < 1e-6
