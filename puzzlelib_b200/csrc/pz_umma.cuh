@@ -11,14 +11,16 @@
 //   * operands are staged in shared memory as K-major tiles of 32 floats (128-byte rows) in the canonical
 //     SWIZZLE_128B layout (8-row x 128-byte atoms, 16-byte chunk index XOR row%8) - the same layout a TMA
 //     SWIZZLE_128B box produces, so a TMA producer can replace a gather producer tile by tile;
-//   * warp roles: 16 producer warps | 1 MMA-issuer warp | 4 epilogue warps (672 threads, <= 96 registers each);
+//   * warp roles: 16 producer warps in 4 independent groups | 1 MMA-issuer warp | 8 epilogue warps (896 threads;
+//     setmaxnreg hands the producers 88 registers, the epilogue 56, the MMA warpgroup 32);
 //   * the producer warps gather the activation operand straight from the reference's NCHW / row-major tensors
 //     (no im2col buffer, no NHWC shadow copy), round fp32 -> tf32 (tcgen05 itself would truncate, which biases
-//     every product by ~ -2^-11) and write the swizzled tile.  Loads are software-pipelined through a ring of
-//     PF register buffers, so PF k-blocks of global loads are in flight per thread while older ones are stored;
+//     every product by ~ -2^-11) and write the swizzled tile.  A group owns whole k-blocks (every 4th one): all of
+//     a k-block's loads are issued -- as volatile asm, so that they stay ahead of the stores -- before the first
+//     value is consumed, and the four groups keep four k-blocks in flight per SM;
 //   * the filter operand of fprop / dgrad is pre-rounded + zero-padded by a tiny prep kernel and then fetched by
 //     TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B box of 32 floats x BN rows) - no thread instructions at all;
-//   * a ring of mbarriers (full: 16 warp arrivals [+ TMA transaction bytes], empty: tcgen05.commit) pipelines
+//   * a ring of mbarriers (full: 4 warp arrivals [+ TMA transaction bytes], empty: tcgen05.commit) pipelines
 //     4 - 8 smem stages (192 KB); accum-full / accum-empty barriers hand TMEM buffers to the epilogue warps;
 //   * epilogue warps: tcgen05.ld 32 lanes x 32 columns, alpha/beta/bias, coalesced stores (TMEM lanes are always
 //     mapped to the contiguous dimension of the output) or red.add for split-K.
@@ -838,7 +840,7 @@ struct KPosTapProducer {
 
 // ------------------------------------------------------------------------------------------ 16-bit producers
 // half / bfloat16 operands: a k-block is 64 elements (one 128-byte swizzle row), a 16-byte chunk 8 elements.  Values travel
-// through the register ring as packed pairs (bit patterns held in `float` registers, never touched by arithmetic) and are
+// through the producers' registers as packed pairs (bit patterns held in `float` registers, never touched by arithmetic) and are
 // stored unchanged: the tensor core reads 16-bit inputs exactly.
 constexpr int BK16 = 64;
 __device__ __forceinline__ uint32_t ldg16(const uint16_t* p) { return (uint32_t)__ldg(p); }
