@@ -167,12 +167,12 @@ __global__ void __launch_bounds__(NTHREADS_HALO, 1) umma_halo_kernel(const __gri
 					#pragma unroll
 					for (int e = 0; e < 4; e++) {
 						if (H16) {
-							const uint32_t lo = (ok && c0 + 2 * e < p.chans) ? (uint32_t)__ldg(src + (long long)(2 * e) * p.chan_stride) : 0u;
-							const uint32_t hi = (ok && c0 + 2 * e + 1 < p.chans) ? (uint32_t)__ldg(src + (long long)(2 * e + 1) * p.chan_stride) : 0u;
+							const uint32_t lo = ldg16_pred(src + (long long)(2 * e) * p.chan_stride, ok && c0 + 2 * e < p.chans);
+							const uint32_t hi = ldg16_pred(src + (long long)(2 * e + 1) * p.chan_stride, ok && c0 + 2 * e + 1 < p.chans);
 							v[i][e] = lo | (hi << 16);
 						} else {
 							// raw bits; rounded to tf32 when stored
-							v[i][e] = (ok && c0 + e < p.chans) ? __float_as_uint(__ldg(reinterpret_cast<const float*>(src) + (long long)e * p.chan_stride)) : 0u;
+							v[i][e] = __float_as_uint(ldg_pred(reinterpret_cast<const float*>(src) + (long long)e * p.chan_stride, ok && c0 + e < p.chans));
 						}
 					}
 				}
@@ -252,11 +252,11 @@ __global__ void __launch_bounds__(NTHREADS_HALO, 1) umma_halo_kernel(const __gri
 						#pragma unroll
 						for (int e = 0; e < 4; e++) {
 							if (H16) {
-								const uint32_t lo = (ok && c0 + 2 * e < p.chans) ? (uint32_t)__ldg(src + (long long)(2 * e) * p.chan_stride) : 0u;
-								const uint32_t hi = (ok && c0 + 2 * e + 1 < p.chans) ? (uint32_t)__ldg(src + (long long)(2 * e + 1) * p.chan_stride) : 0u;
+								const uint32_t lo = ldg16_pred(src + (long long)(2 * e) * p.chan_stride, ok && c0 + 2 * e < p.chans);
+								const uint32_t hi = ldg16_pred(src + (long long)(2 * e + 1) * p.chan_stride, ok && c0 + 2 * e + 1 < p.chans);
 								v[i][e] = lo | (hi << 16);
 							} else {
-								v[i][e] = (ok && c0 + e < p.chans) ? to_tf32(__ldg(reinterpret_cast<const float*>(src) + (long long)e * p.chan_stride)) : 0u;
+								v[i][e] = to_tf32(ldg_pred(reinterpret_cast<const float*>(src) + (long long)e * p.chan_stride, ok && c0 + e < p.chans));
 							}
 						}
 					}
