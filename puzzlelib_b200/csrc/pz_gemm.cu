@@ -136,6 +136,10 @@ int launch(GemmParams& p, int dtype, int bn, int amode, int bmode, bool cdiv, in
 	PZ_REQUIRE((long long)(p.splits - 1) * p.kb_per_split < p.kblocks, "empty split");
 	const bool h16 = dtype != PZ_F32;
 	p.ab_bf16 = dtype == PZ_BF16 ? 1 : 0;
+	{
+		static const int skip = [] { const char* e = getenv("PZ_DEBUG_SKIP"); return e ? atoi(e) : 0; }();
+		p.debug_skip = skip;
+	}
 	p.tiles_m = (int)pz_cdiv(M, BM);
 	p.tiles_n = (int)pz_cdiv(N, bn);
 	p.groups = groups;

@@ -150,6 +150,7 @@ struct GemmParams {
 	FastDiv fd_tiles_n, fd_tiles_m, fd_splits;   // the same counts as magic-number divisors (the decode runs per tile per warp)
 	int tma_rows_per_group;      // MODE_TMA: row offset of group g in the prepared filter = g * tma_rows_per_group
 	int ab_bf16;                 // 16-bit operands: 0 = half, 1 = bfloat16 (selects the tcgen05 input format)
+	int debug_skip;              // PZ_DEBUG_SKIP (timing experiments only, results are wrong): 1 no epilogue stores, 2 no filter TMA, 4 no MMAs
 	double alg_flops, alg_bytes; // host-side bookkeeping for the profiler (algorithmic work of this launch)
 };
 
@@ -1400,8 +1401,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) umma_gemm_kernel(const __grid_con
 			const uint32_t tileA = smem0 + stage * C::STAGE_BYTES;
 			if (B_TMA) {
 				if (gw == 0 && lane == 0) {
-					mbar_arrive_expect_tx(bar_full + 8 * stage, BN * 128);
-					tma_load_2d(tileA + BM * 128, &tmapB, lkb * BKE, lw.group * p.tma_rows_per_group + lw.n_tile * BN, bar_full + 8 * stage);
+					if (p.debug_skip & 2) mbar_arrive(bar_full + 8 * stage);
+					else {
+						mbar_arrive_expect_tx(bar_full + 8 * stage, BN * 128);
+						tma_load_2d(tileA + BM * 128, &tmapB, lkb * BKE, lw.group * p.tma_rows_per_group + lw.n_tile * BN, bar_full + 8 * stage);
+					}
 				}
 			}
 			prodA.store(tileA, va);
@@ -1434,6 +1438,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) umma_gemm_kernel(const __grid_con
 						const uint64_t da = make_smem_desc(tileA), db = make_smem_desc(tileA + BM * 128);
 						#pragma unroll
 						for (int kk = 0; kk < 4; kk++) {       // 8 tf32 / 16 halves = 32 bytes per MMA: +2 in the (addr >> 4) field
+							if (p.debug_skip & 4) continue;
 							if (H16) umma_f16(tmem_d, da + 2 * kk, db + 2 * kk, idesc, (kb > w.kb_begin || kk > 0) ? 1u : 0u);
 							else umma_tf32(tmem_d, da + 2 * kk, db + 2 * kk, idesc, (kb > w.kb_begin || kk > 0) ? 1u : 0u);
 						}
@@ -1482,7 +1487,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) umma_gemm_kernel(const __grid_con
 			const int cfirst = half * EPI_COLS;
 			if (cfirst < ncols) tmem_ld16(tmem_d + (uint32_t)cfirst, v0);
 			#pragma unroll 1
-			for (int c0 = cfirst; c0 < ncols; c0 += 2 * CSTRIDE) {
+			for (int c0 = cfirst; c0 < ((p.debug_skip & 1) ? 0 : ncols); c0 += 2 * CSTRIDE) {
 				tmem_wait_ld(v0);
 				if (c0 + CSTRIDE < ncols) tmem_ld16(tmem_d + (uint32_t)(c0 + CSTRIDE), v1);
 				epilogue_chunk(E, v0, outp, biasp, bias_m, mvalid, addbias, w.n_tile * BN + c0, fast, hb, wb);
