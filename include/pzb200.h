@@ -238,6 +238,9 @@ int pz_permute(int itemsize, void* out, const void* in, int ndim, const int64_t*
  * advances offset by ceil(n / 4) per fill.  Not bit-compatible with cuRAND's XORWOW.
  * pz_dropout (ElementWise.py:495-580): out = in * (rands[i / mapsize] < partition) / p; rands are uint32 for float32 data,
  * uint16 for half / bfloat16; mapsize 1 = dropoutKer, H*W = dropout2dKer */
+/* vector reductions behind blas.dot / l1norm / l2norm (Cuda/Source/Libs/CuBlas.c: cublasSdot, cublasSasum, cublasSnrm2):
+ * kind 0 = sum x*y, 1 = sum |x|, 2 = sum x*x; fp32 accumulation; *out (float, device) += result */
+int pz_vec_reduce(int dtype, int kind, const void* x, const void* y, int64_t n, void* out, void* stream);
 /* local response normalisation (Cuda/Source/Libs/CuDnnNorm.c:329-690; formulas Cuda/Wrappers/CuDnnNorm.py:185-268):
  * mode 0 = across maps (crossMapLRN), 1 = within a map (mapLRN, no means tensor); window [i - (n-1)/2, i + n - (n-1)/2) clipped.
  * pz_lrn_bwd needs `tmp`: N*C*H*W floats of scratch. */

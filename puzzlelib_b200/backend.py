@@ -526,6 +526,28 @@ class BlasContext:
 						  int(transpB), alpha, beta, None, None))
 		return out
 
+	# ---- level-1 reductions returning host scalars (reference: Cuda/Source/Libs/CuBlas.c dot / l1norm / l2norm)
+	def _reduce(self, kind, x, y=None):
+		_requireArray(x, "x")
+		x.enforceContiguous()
+		if y is not None:
+			_requireArray(y, "y")
+			y.enforceContiguous()
+			if y.size != x.size or y.dtype != x.dtype:
+				raise ValueError("vectors must share size and datatype")
+		out = GPUArray.zeros((), _f32, allocator=self.backend.memoryPool)
+		check(lib.pz_vec_reduce(dtypeCode(x.dtype), kind, x.ptr, None if y is None else y.ptr, x.size, out.ptr, None))
+		return float(out.get())
+
+	def dot(self, x, y):
+		return self._reduce(0, x, y)
+
+	def l1norm(self, x):
+		return self._reduce(1, x)
+
+	def l2norm(self, x):
+		return float(np.sqrt(self._reduce(2, x)))
+
 	def gemmBatched(self, A, B, formatA=0, formatB=0, formatOut=0, transpA=False, transpB=False, alpha=1.0, beta=0.0, out=None,
 					allocator=None):
 		"""One GEMM per group over 3-d tensors in (group, batch, param) = gbp (0) or (batch, group, param) = bgp (1) layout

@@ -468,3 +468,40 @@ extern "C" int pz_lrn_bwd(int dtype, int mode, const void* x, const void* grad, 
 	PzProfScope prof(PZ_PROF_ELTWISE, pz_stream(stream), 0.0, 3.0 * (double)total * pz_dtype_size(dtype));
 	PZ_TRAIN_DISPATCH(dtype, lrn_launch<T>(1, x, grad, dx, (float*)tmp, g, total, stream));
 }
+
+// ------------------------------------------------------------------------------------------ vector reductions
+// reference: Cuda/Source/Libs/CuBlas.c (cublasSdot / cublasSasum / cublasSnrm2 behind blas.dot / l1norm / l2norm).
+// kind 0: sum x*y, 1: sum |x|, 2: sum x*x (the caller takes the root); fp32 accumulation, *out += result.
+namespace {
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) vec_reduce_kernel(const T* __restrict__ x, const T* __restrict__ y, long long n, int kind,
+															 float* __restrict__ out)
+{
+	__shared__ float red[kThreads / 32];
+	float s = 0.0f;
+	for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kThreads) {
+		const float a = to_f(x[i]);
+		s += kind == 0 ? a * to_f(y[i]) : (kind == 1 ? fabsf(a) : a * a);
+	}
+	const float t = block_sum(s, red);
+	if (threadIdx.x == 0 && t != 0.0f) atomicAdd(out, t);
+}
+
+template <typename T>
+int vec_reduce_launch(const void* x, const void* y, int64_t n, int kind, void* out, void* stream)
+{
+	vec_reduce_kernel<T><<<grid_for(n), kThreads, 0, pz_stream(stream)>>>((const T*)x, (const T*)y, (long long)n, kind, (float*)out);
+	pz_count_launch(1);
+	PZ_LAUNCH_CHECK();
+	return PZ_OK;
+}
+
+}  // namespace
+
+extern "C" int pz_vec_reduce(int dtype, int kind, const void* x, const void* y, int64_t n, void* out, void* stream)
+{
+	PZ_REQUIRE(kind >= 0 && kind <= 2, "vector reduction: unknown kind %d", kind);
+	if (n <= 0) return PZ_OK;
+	PZ_TRAIN_DISPATCH(dtype, vec_reduce_launch<T>(x, kind == 0 ? y : x, n, kind, out, stream));
+}

@@ -1045,3 +1045,18 @@ def test_lrn_across_and_within_maps(bnd, dtype, atol):
 		dx = bnd.dnn.mapLRNBackward(G(bnd, x), G(bnd, g), N=N, alpha=alpha, beta=beta, K=K, allocator=bnd.memoryPool)
 		wy, wdx = ops.lrn(x, N, alpha, beta, K, False, grad=g)
 		assert np.abs(y.get() - wy).max() < atol and np.abs(dx.get() - wdx).max() < 4 * atol
+
+
+@pytest.mark.parametrize("dtype,rtol", [(np.float32, 1e-5), (np.float16, 2e-3)])
+def test_blas_dot_and_norms(bnd, dtype, rtol):
+	# reference tests: Cuda/Wrappers/CuBlas.py (dot / l1norm / l2norm against numpy)
+	rng = np.random.RandomState(21)
+	for n in (1, 1000, 1 << 20):
+		x, y = rng.randn(n).astype(dtype), rng.randn(n).astype(dtype)
+		x64, y64 = x.astype(np.float64), y.astype(np.float64)
+		scale = np.abs(x64 * y64).sum() + 1e-30
+		assert abs(bnd.blas.dot(G(bnd, x), G(bnd, y)) - float(x64 @ y64)) < rtol * scale
+		assert abs(bnd.blas.l1norm(G(bnd, x)) - np.abs(x64).sum()) < rtol * np.abs(x64).sum()
+		assert abs(bnd.blas.l2norm(G(bnd, x)) - np.sqrt((x64 * x64).sum())) < rtol * np.sqrt((x64 * x64).sum())
+	with pytest.raises(ValueError):
+		bnd.blas.dot(G(bnd, x), G(bnd, y[:5]))
