@@ -1060,3 +1060,49 @@ def test_blas_dot_and_norms(bnd, dtype, rtol):
 		assert abs(bnd.blas.l2norm(G(bnd, x)) - np.sqrt((x64 * x64).sum())) < rtol * np.sqrt((x64 * x64).sum())
 	with pytest.raises(ValueError):
 		bnd.blas.dot(G(bnd, x), G(bnd, y[:5]))
+
+
+def test_training_kernels_match_the_reference_cpu_backend_golden_vectors(bnd):
+	# tests/golden/ref_cpu_train.npz holds outputs of the reference's own gcc-JIT CPU kernels / optimizer objects
+	import os
+	from puzzlelib_b200 import modules as M
+	from puzzlelib_b200.optim import Adam, NesterovSGD, MomentumSGD
+	g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_cpu_train.npz"))
+	f32 = np.dtype(np.float32)
+	w, dw, mom, mg, ms = (g[k] for k in ("w", "dw", "mom", "mg", "ms"))
+	for name, ker in (("classic", bnd.classicMomSGDKer), ("nesterov", bnd.nesterovMomSGDKer)):
+		gw, gm = G(bnd, w), G(bnd, mom)
+		ker(f32)(gw, G(bnd, dw), gm, 0.01, 0.9)
+		assert np.allclose(gw.get(), g["%s_w" % name], rtol=0, atol=1e-6) and np.allclose(gm.get(), g["%s_mom" % name], rtol=0, atol=1e-6)
+	gw, gmg, gms = G(bnd, w), G(bnd, mg), G(bnd, ms)
+	lr, fix1, fix2, eps = (float(v) for v in g["adam_args"])
+	bnd.adamKer(f32)(gw, G(bnd, dw), gmg, gms, lr, fix1, fix2, eps)
+	assert np.allclose(gw.get(), g["adam_w"], rtol=0, atol=1e-6) and np.allclose(gmg.get(), g["adam_mg"], rtol=0, atol=1e-6)
+	assert np.allclose(gms.get(), g["adam_ms"], rtol=0, atol=1e-6)
+
+	x = g["drop_x"]
+	out = bnd.GPUArray.empty(x.shape, np.float32)
+	bnd.dropoutKer(f32)(out, G(bnd, x), G(bnd, g["drop_words"]), int(g["drop_v"][0]), g["drop_p"][0])
+	assert np.allclose(out.get(), g["drop_y"], rtol=3e-7, atol=0) and np.array_equal(out.get() == 0, g["drop_y"] == 0)
+	bnd.dropout2dKer(f32)(out, G(bnd, x), G(bnd, g["drop2d_words"]), int(g["drop_v"][0]), g["drop_p"][0], x.shape[2] * x.shape[3])
+	assert np.allclose(out.get(), g["drop2d_y"], rtol=3e-7, atol=0) and np.array_equal(out.get() == 0, g["drop2d_y"] == 0)
+
+	class Holder:
+		def __init__(self, var):
+			self.var = var
+
+		def getVarTable(self):
+			return {self.var: ["w"]}
+
+		def getVar(self, name):
+			return self.var
+
+	for name, make in (("adam", lambda: Adam(alpha=1e-2)), ("nesterov", lambda: NesterovSGD(learnRate=1e-1, momRate=0.9)),
+					   ("momentum", lambda: MomentumSGD(learnRate=1e-1, momRate=0.9))):
+		var = M.Variable(G(bnd, w))
+		opt = make()
+		opt.setupOn(Holder(var))
+		for gr in g["opt_grads"]:
+			var.grad.set(gr)
+			opt.update()
+		assert np.allclose(var.data.get(), g["opt_%s_w" % name], rtol=0, atol=2e-5), name

@@ -365,3 +365,44 @@ def test_lrn_oracle_gradient_matches_finite_differences_for_odd_windows():
 			xm[idx] -= eps
 			num = ((ops.lrn(xp, 3, 0.7, 0.75, 2.0, across) - ops.lrn(xm, 3, 0.7, 0.75, 2.0, across)) * g).sum() / (2 * eps)
 			assert abs(num - dx[idx]) < 1e-6
+
+
+def _train_gold():
+	import os
+	return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_cpu_train.npz"))
+
+
+def test_optimizer_and_dropout_oracles_match_the_reference_cpu_kernels():
+	# tests/golden/ref_cpu_train.npz: outputs of the reference's own CPU kernels and optimizer objects (tools/gen_golden_train.py)
+	g = _train_gold()
+	w, dw, mom, mg, ms = (g[k] for k in ("w", "dw", "mom", "mg", "ms"))
+	f32 = np.float32
+	pw, pm = ops.nesterov_update(w, dw, mom, f32(0.01), f32(0.9), dtype=f32)
+	assert np.allclose(pw, g["nesterov_w"], rtol=0, atol=1e-6) and np.allclose(pm, g["nesterov_mom"], rtol=0, atol=1e-6)
+	cm = f32(0.9) * mom + f32(0.01) * dw
+	assert np.allclose(cm, g["classic_mom"], rtol=0, atol=1e-6) and np.allclose(w + cm, g["classic_w"], rtol=0, atol=1e-6)
+	lr, fix1, fix2, eps = g["adam_args"]
+	aw, amg, ams = ops.adam_update(w, dw, mg, ms, lr, fix1, fix2, eps, dtype=f32)
+	assert np.allclose(aw, g["adam_w"], rtol=0, atol=1e-6) and np.allclose(amg, g["adam_mg"], rtol=0, atol=1e-6)
+	assert np.allclose(ams, g["adam_ms"], rtol=0, atol=1e-6)
+
+	x, words, v, p = g["drop_x"], g["drop_words"], g["drop_v"][0], g["drop_p"][0]
+	# (the reference's gcc build may multiply by 1/p instead of dividing: one ulp)
+	assert np.allclose((x * (words.reshape(x.shape) < v) / p).astype(f32), g["drop_y"], rtol=3e-7, atol=0)
+	assert np.array_equal(g["drop_y"] == 0, ~(words.reshape(x.shape) < v) | (x == 0))
+	mw = g["drop2d_words"].reshape(x.shape[0], x.shape[1], 1, 1)
+	assert np.allclose((x * (mw < v) / p).astype(f32), g["drop2d_y"], rtol=3e-7, atol=0)
+
+	# the optimizer objects: three updates with the reference's bias-corrected Adam step size etc. (Optimizers/Adam.py:36-45)
+	grads = g["opt_grads"]
+	wa, a, s2 = w.astype(np.float64), np.zeros_like(w, np.float64), np.zeros_like(w, np.float64)
+	wn, mn = w.astype(np.float64), np.zeros_like(w, np.float64)
+	wm, mm = w.astype(np.float64), np.zeros_like(w, np.float64)
+	for t, gr in enumerate(grads, start=1):
+		lr = 1e-2 * np.sqrt(1.0 - 0.999 ** t) / (1.0 - 0.9 ** t)
+		wa, a, s2 = ops.adam_update(wa, gr, a, s2, lr, 0.1, 0.001, 1e-8)
+		wn, mn = ops.nesterov_update(wn, gr, mn, 1e-1, 0.9)
+		mm = 0.9 * mm + 1e-1 * gr
+		wm = wm + mm
+	assert np.allclose(wa, g["opt_adam_w"], atol=2e-5) and np.allclose(wn, g["opt_nesterov_w"], atol=2e-5)
+	assert np.allclose(wm, g["opt_momentum_w"], atol=2e-5)
