@@ -112,10 +112,12 @@ template <typename T>
 __global__ void prep_filter_fprop(const T* __restrict__ w, T* __restrict__ wp, int kdim, int kpad, long long total, int chan, int Cg,
 								   int RS)
 {
-	long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= total) return;
-	const int k = (int)(i % kpad);
-	const long long row = i / kpad;
+	// (prepared filters hold < 2^31 elements: 32-bit index arithmetic, a 64-bit division costs ~100 instructions per element)
+	const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+	if ((long long)i >= total) return;
+	const unsigned urow = i / (unsigned)kpad;
+	const int k = (int)(i - urow * (unsigned)kpad);
+	const long long row = urow;
 	T v = T(0.0f);
 	if (chan) {
 		const int cpad = kpad / RS;
@@ -134,10 +136,10 @@ template <typename T>
 __global__ void prep_filter_dgrad(const T* __restrict__ w, T* __restrict__ wt, int Kg, int Cg, int R, int S, int r0, int s0,
 								   int sh, int sw, int Rc, int Sc, int kpad, long long total, int chan, int flip)
 {
-	long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= total) return;
-	int k = (int)(i % kpad);
-	const int row = (int)(i / kpad);
+	const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+	if ((long long)i >= total) return;
+	const int row = (int)(i / (unsigned)kpad);
+	int k = (int)(i - (unsigned)row * (unsigned)kpad);
 	int ko = -1, rc = 0, sc = 0;
 	if (chan) {
 		const int kopad = kpad / (Rc * Sc);
@@ -164,6 +166,7 @@ __global__ void prep_filter_dgrad(const T* __restrict__ w, T* __restrict__ wt, i
 // launch a templated prep kernel for the storage type (16-bit types are moved as raw bits)
 #define PZ_PREP_LAUNCH(dtype, kernel, total, stream, w, wt, ...)                                                                      \
 	do {                                                                                                                              \
+		PZ_REQUIRE((long long)(total) < (1ll << 32), "conv2d: prepared filter exceeds 2^32 elements");                                \
 		if ((dtype) == PZ_F32)                                                                                                        \
 			kernel<float><<<(unsigned)pz_cdiv(total, 256), 256, 0, stream>>>((const float*)(w), (float*)(wt), __VA_ARGS__);           \
 		else                                                                                                                          \
@@ -174,10 +177,11 @@ __global__ void prep_filter_dgrad(const T* __restrict__ w, T* __restrict__ wt, i
 // col2im dgrad: wt[(c, r, s)][ko] = w[ko][c][r][s] (the filter transposed), rows of kpad elements
 __global__ void prep_filter_col2im(const float* __restrict__ w, float* __restrict__ wt, int K, int CRS, int kpad, long long total)
 {
-	long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= total) return;
-	const int ko = (int)(i % kpad);
-	const long long row = i / kpad;
+	const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+	if ((long long)i >= total) return;
+	const unsigned urow = i / (unsigned)kpad;
+	const int ko = (int)(i - urow * (unsigned)kpad);
+	const long long row = urow;
 	wt[i] = ko < K ? __uint_as_float(to_tf32(w[(long long)ko * CRS + row])) : 0.0f;
 }
 
