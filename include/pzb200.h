@@ -238,6 +238,10 @@ int pz_permute(int itemsize, void* out, const void* in, int ndim, const int64_t*
  * advances offset by ceil(n / 4) per fill.  Not bit-compatible with cuRAND's XORWOW.
  * pz_dropout (ElementWise.py:495-580): out = in * (rands[i / mapsize] < partition) / p; rands are uint32 for float32 data,
  * uint16 for half / bfloat16; mapsize 1 = dropoutKer, H*W = dropout2dKer */
+/* grouped matrix-vector product (Cuda/Kernels/MatVec.py:93-124,311-343; Backend/Blas.py:82-86 mulTensorOnVecGroup):
+ * mat [z][h][w]; on_rows: out[z][h] = beta*out + alpha*sum_w mat*vec[z][w]; else out[z][w] = beta*out + alpha*sum_h mat*vec[z][h] */
+int pz_matvec(int dtype, void* out, const void* mat, const void* vec, int64_t z, int64_t h, int64_t w, int on_rows, float alpha,
+			  float beta, void* stream);
 /* vector reductions behind blas.dot / l1norm / l2norm (Cuda/Source/Libs/CuBlas.c: cublasSdot, cublasSasum, cublasSnrm2):
  * kind 0 = sum x*y, 1 = sum |x|, 2 = sum x*x; fp32 accumulation; *out (float, device) += result */
 int pz_vec_reduce(int dtype, int kind, const void* x, const void* y, int64_t n, void* out, void* stream);

@@ -609,6 +609,27 @@ class MatModule:
 	def __init__(self, backend):
 		self.backend = backend
 
+	def matvec(self, mat, vec, axis=0, out=None, alpha=1.0, beta=0.0, allocator=None):
+		"""reference: Cuda/Kernels/MatVec.py:311-343 -- mat (..., h, w); axis 1: out (..., h) = mat . vec(..., w);
+		axis 0: out (..., w) = mat^T . vec(..., h); out = beta * out + alpha * product"""
+		_requireArray(mat, "mat")
+		_requireArray(vec, "vec")
+		if vec.dtype != mat.dtype or vec.ndim != mat.ndim - 1 or not 0 <= axis < 2 or mat.ndim < 2:
+			raise ValueError("invalid matrix / vector layout")
+		mat.enforceContiguous()
+		vec.enforceContiguous()
+		h, w = mat.shape[-2:]
+		if vec.shape != mat.shape[:-2] + ((w, ) if axis == 1 else (h, )):
+			raise ValueError("vector shape %s does not fit matrix shape %s along axis %d" % (vec.shape, mat.shape, axis))
+		shape = mat.shape[:-2] + ((h, ) if axis == 1 else (w, ))
+		if out is None:
+			out = GPUArray.zeros(shape, mat.dtype, allocator=allocator)
+		else:
+			_checkOut(out, shape, mat.dtype)
+		check(lib.pz_matvec(dtypeCode(mat.dtype), out.ptr, mat.ptr, vec.ptr, prod(mat.shape[:-2]), h, w, 1 if axis == 1 else 0,
+							float(alpha), float(beta), None))
+		return out
+
 	def addVecToMat(self, vec, mat, axis=0, out=None, allocator=None):
 		assert vec.dtype == mat.dtype
 		assert vec.ndim == mat.ndim - 1 and 0 <= axis < 2

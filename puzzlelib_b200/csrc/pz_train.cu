@@ -505,3 +505,67 @@ extern "C" int pz_vec_reduce(int dtype, int kind, const void* x, const void* y, 
 	if (n <= 0) return PZ_OK;
 	PZ_TRAIN_DISPATCH(dtype, vec_reduce_launch<T>(x, kind == 0 ? y : x, n, kind, out, stream));
 }
+
+// ------------------------------------------------------------------------------------------ grouped matrix-vector product
+// reference: Cuda/Kernels/MatVec.py:93-124,311-343 (vecMulOnRow / vecMulOnCol behind matmod.matvec and mulTensorOnVecGroup):
+// mat [z][h][w]; on_rows: out[z][h] = beta*out + alpha * sum_w mat*vec[z][w]; else out[z][w] = beta*out + alpha * sum_h mat*vec[z][h].
+// Exact fp32 accumulation (not a tensor-core contraction).
+namespace {
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) matvec_rows_kernel(T* __restrict__ out, const T* __restrict__ mat, const T* __restrict__ vec,
+															  long long rows, int h, int w, float alpha, float beta)
+{
+	// one warp per output element (z, row)
+	const int lane = threadIdx.x & 31;
+	for (long long r = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); r < rows; r += (long long)gridDim.x * (kThreads / 32)) {
+		const long long z = r / h;
+		const T* m = mat + r * w;
+		const T* v = vec + z * w;
+		float acc = 0.0f;
+		for (int i = lane; i < w; i += 32) acc = fmaf(to_f(m[i]), to_f(v[i]), acc);
+		#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+		if (lane == 0) out[r] = from_f<T>((beta != 0.0f ? beta * to_f(out[r]) : 0.0f) + alpha * acc);
+	}
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) matvec_cols_kernel(T* __restrict__ out, const T* __restrict__ mat, const T* __restrict__ vec,
+															  long long cols, int h, int w, float alpha, float beta)
+{
+	// one thread per output element (z, column): consecutive threads read consecutive columns of a row
+	for (long long c = (long long)blockIdx.x * kThreads + threadIdx.x; c < cols; c += (long long)gridDim.x * kThreads) {
+		const long long z = c / w;
+		const int col = (int)(c - z * w);
+		const T* m = mat + z * (long long)h * w + col;
+		const T* v = vec + z * h;
+		float acc = 0.0f;
+		for (int i = 0; i < h; i++) acc = fmaf(to_f(m[(long long)i * w]), to_f(v[i]), acc);
+		out[c] = from_f<T>((beta != 0.0f ? beta * to_f(out[c]) : 0.0f) + alpha * acc);
+	}
+}
+
+template <typename T>
+int matvec_launch(void* out, const void* mat, const void* vec, int64_t z, int64_t h, int64_t w, int on_rows, float alpha, float beta,
+				  void* stream)
+{
+	cudaStream_t s = pz_stream(stream);
+	if (on_rows)
+		matvec_rows_kernel<T><<<grid_for(z * h * 32), kThreads, 0, s>>>((T*)out, (const T*)mat, (const T*)vec, (long long)(z * h), (int)h, (int)w, alpha, beta);
+	else
+		matvec_cols_kernel<T><<<grid_for(z * w), kThreads, 0, s>>>((T*)out, (const T*)mat, (const T*)vec, (long long)(z * w), (int)h, (int)w, alpha, beta);
+	pz_count_launch(1);
+	PZ_LAUNCH_CHECK();
+	return PZ_OK;
+}
+
+}  // namespace
+
+extern "C" int pz_matvec(int dtype, void* out, const void* mat, const void* vec, int64_t z, int64_t h, int64_t w, int on_rows,
+						 float alpha, float beta, void* stream)
+{
+	PZ_REQUIRE(z >= 0 && h >= 0 && w >= 0 && h < (1ll << 31) && w < (1ll << 31), "matvec: bad shape");
+	if (z == 0 || (on_rows ? h : w) == 0) return PZ_OK;
+	PZ_TRAIN_DISPATCH(dtype, matvec_launch<T>(out, mat, vec, z, h, w, on_rows, alpha, beta, stream));
+}

@@ -122,6 +122,7 @@ _SIGNATURES = {
 	"pz_cross_entropy": [_P, _P, _P, c_int64, c_int64, c_int64, _P, _P, _P],
 	"pz_count_mismatch": [_P, _P, c_int64, _P, _P],
 	"pz_permute": [c_int, _P, _P, c_int, _P, _P, _P],
+	"pz_matvec": [c_int, _P, _P, _P, c_int64, c_int64, c_int64, c_int, c_float, c_float, _P],
 	"pz_vec_reduce": [c_int, c_int, _P, _P, c_int64, _P, _P],
 	"pz_lrn_fwd": [c_int, c_int, _P, _P, c_int64, c_int64, c_int64, c_int64, c_int, c_float, c_float, c_float, _P],
 	"pz_lrn_bwd": [c_int, c_int, _P, _P, _P, _P, c_int64, c_int64, c_int64, c_int64, c_int, c_float, c_float, c_float, _P],

@@ -1106,3 +1106,25 @@ def test_training_kernels_match_the_reference_cpu_backend_golden_vectors(bnd):
 			var.grad.set(gr)
 			opt.update()
 		assert np.allclose(var.data.get(), g["opt_%s_w" % name], rtol=0, atol=2e-5), name
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float32, 1e-5), (np.float16, 2e-2)])
+def test_matvec_grouped(bnd, dtype, tol):
+	# reference: Cuda/Kernels/MatVec.py:311-343 (matmod.matvec behind Blas.mulTensorOnVecGroup); exact fp32 accumulation
+	rng = np.random.RandomState(17)
+	for shape in [(5, 7), (3, 33, 65), (2, 4, 1, 9), (6, 128, 40)]:
+		mat = rng.randn(*shape).astype(dtype)
+		m64 = mat.astype(np.float64)
+		for axis in (0, 1):
+			vec = rng.randn(*(shape[:-2] + ((shape[-1], ) if axis == 1 else (shape[-2], )))).astype(dtype)
+			v64 = vec.astype(np.float64)
+			want = np.einsum("...hw,...w->...h", m64, v64) if axis == 1 else np.einsum("...hw,...h->...w", m64, v64)
+			got = bnd.matmod.matvec(G(bnd, mat), G(bnd, vec), axis=axis, allocator=bnd.memoryPool)
+			assert got.shape == want.shape and np.abs(got.get() - want).max() < tol * max(1.0, np.abs(want).max())
+			base = rng.randn(*want.shape).astype(dtype)
+			out = G(bnd, base)
+			bnd.matmod.matvec(G(bnd, mat), G(bnd, vec), axis=axis, out=out, alpha=0.5, beta=2.0)
+			ref = 2.0 * base.astype(np.float64) + 0.5 * want
+			assert np.abs(out.get() - ref).max() < 2 * tol * max(1.0, np.abs(ref).max())
+	with pytest.raises(ValueError):
+		bnd.matmod.matvec(G(bnd, mat), G(bnd, vec[:, :3]), axis=0)
