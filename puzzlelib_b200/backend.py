@@ -605,6 +605,7 @@ class BlasContext:
 # ============================================================================================================ matmod
 class MatModule:
 	"""reference: Cuda/Kernels/MatVec.py:216-374"""
+	GPUArray = GPUArray
 
 	def __init__(self, backend):
 		self.backend = backend
@@ -681,6 +682,7 @@ class MatModule:
 # ============================================================================================================ poolmod
 class PoolModule:
 	"""reference: Cuda/Kernels/Pool.py:115-213 (bit-exact int32 argmax masks)"""
+	GPUArray = GPUArray
 
 	def __init__(self, backend):
 		self.backend = backend
@@ -734,6 +736,7 @@ class PoolModule:
 # ============================================================================================================ costmod
 class CostModule:
 	"""reference: Cuda/Kernels/Costs.py:160-247 (the cross-entropy entry and the accuracy reduction of the training closure)"""
+	GPUArray = GPUArray
 
 	def __init__(self, backend):
 		self.backend = backend
@@ -897,6 +900,25 @@ class ConvPerf:
 		return "Algo %s time %.6f secs memory %.6f mbytes" % (self.algo, self.time, self.memory / 1024 ** 2)
 
 
+class NotBehindTheSeam:
+	"""An attribute of the reference backend object that this backend does not implement: binding it (the reference's
+	Backend/Kernels/*.py do so at import time) works, USING it raises -- loudly, never a CPU or library fallback."""
+
+	def __init__(self, name):
+		self._name = name
+
+	def __call__(self, *args, **kwargs):
+		raise NotImplementedError("%s is not implemented in the B200 backend" % self._name)
+
+	def __getattr__(self, attr):
+		if attr.startswith("__"):
+			raise AttributeError(attr)
+		return NotBehindTheSeam("%s.%s" % (self._name, attr))
+
+	def __repr__(self):
+		return "<%s: not implemented in the B200 backend>" % self._name
+
+
 # ============================================================================================================ backend
 class B200Backend:
 	BackendName = "B200"
@@ -967,6 +989,13 @@ class B200Backend:
 		uni = 0
 		bi = 1
 
+	notImplemented = (
+		"ctcmod", "embedmod", "padmod", "prelumod", "upsamplemod", "memmod",
+		"bceKer", "hingeKer", "smoothL1Ker", "l1HingeKer", "rbmKer", "absKer",
+		"rmspropKer", "rmspropGravesKer", "adagradKer", "adadeltaKer", "smorms3Ker",
+		"weightDecayKer", "l1penaltyKer", "l1gradKer"
+	)
+
 	def __init__(self, deviceIdx, initmode=0, logger=None):
 		self.deviceIdx = deviceIdx
 		self.logger = logger
@@ -993,6 +1022,13 @@ class B200Backend:
 		self.initmode = 0
 		self.blas, self.dnn = None, None
 		self.matmod, self.poolmod, self.costmod = None, None, None
+
+		# attributes the reference's Backend/Kernels/*.py bind at import time (Cuda/GPUBackend.py:74-131) that sit outside the
+		# hot path and are not implemented: binding works, use raises NotImplementedError
+		for name in self.notImplemented:
+			if getattr(self, name, None) is None:
+				setattr(self, name, NotBehindTheSeam(name))
+
 		self.updateBackend(initmode)
 
 	def updateBackend(self, initmode):
@@ -1081,6 +1117,21 @@ class B200Backend:
 							  param.size, None))
 
 		return ker
+
+	@staticmethod
+	def castFP16toFP32(outdata, indata, **kwargs):
+		"""reference: Cuda/Kernels/ElementWise.py castFP16toFP32 -- a kernel object, not a factory"""
+		_noSlice(kwargs)
+		if outdata.dtype != _f32 or indata.dtype != np.float16 or outdata.size != indata.size:
+			raise ValueError("castFP16toFP32 needs a float32 output and a float16 input of one size")
+		check(lib.pz_cast(driver.PZ_F32, outdata.ptr, driver.PZ_F16, indata.ptr, indata.size, None))
+
+	@staticmethod
+	def castFP32toFP16(outdata, indata, **kwargs):
+		_noSlice(kwargs)
+		if outdata.dtype != np.float16 or indata.dtype != _f32 or outdata.size != indata.size:
+			raise ValueError("castFP32toFP16 needs a float16 output and a float32 input of one size")
+		check(lib.pz_cast(driver.PZ_F16, outdata.ptr, driver.PZ_F32, indata.ptr, indata.size, None))
 
 	@staticmethod
 	def getAccuracyKernel(name):

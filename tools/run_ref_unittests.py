@@ -1,0 +1,180 @@
+"""Run the REFERENCE's own unit tests (every `unittest()` of PuzzleLib/{Modules,Containers,Cost,Optimizers,Handlers,...}
+and the backend-object tests of Cuda/Wrappers/*.py, Cuda/Kernels/*.py, Cuda/GPUArray.py, Cuda/Utils.py) against
+
+    --impl b200   this repository's backend behind the Cuda/Backend.py seam (puzzlelib_b200.seam.install), or
+    --impl ref    the reference's own cuDNN / cuBLAS backend built by baseline/build_ref.py,
+
+on the GPU box, and write one JSON report (pass / fail + reason per test).  The tests use unseeded random inputs and
+np.allclose, so like the reference's Unittester.py (Unittester.py:13-48) a failing test is retried a few times.
+
+    python tools/run_ref_unittests.py --impl b200 --out gpurun_out/ref_unittests_b200.json [--only Conv2D,Linear]
+"""
+import argparse, importlib, json, os, signal, sys, time, traceback
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+class Timeout(Exception):
+	pass
+
+
+def alarm(signum, frame):
+	raise Timeout()
+
+
+PACKAGES = ["Modules", "Containers", "Cost", "Optimizers", "Handlers", "Passes", "Models/Nets", "Models/Misc"]
+# files whose unittest() needs data files / network / a display / minutes of training
+SKIP = {
+	"Handlers/Trainer.py": None, "Handlers/Validator.py": None, "Handlers/Calculator.py": None,
+}
+
+
+def discover(refpkg):
+	names = []
+	for pkg in PACKAGES:
+		path = os.path.join(refpkg, pkg)
+		if not os.path.isdir(path):
+			continue
+		for fname in sorted(os.listdir(path)):
+			if fname.endswith(".py") and fname != "__init__.py":
+				names.append("%s/%s" % (pkg, fname))
+	return names
+
+
+def runOne(fn, retries, limit):
+	last = None
+	for attempt in range(retries):
+		signal.signal(signal.SIGALRM, alarm)
+		signal.alarm(limit)
+		try:
+			fn()
+			return {"ok": True, "tries": attempt + 1}
+		except Timeout:
+			return {"ok": False, "tries": attempt + 1, "error": "timeout after %d s" % limit}
+		except NotImplementedError as e:
+			return {"ok": False, "tries": attempt + 1, "error": "NotImplementedError: %s" % e, "unsupported": True}
+		except BaseException as e:
+			tb = traceback.extract_tb(sys.exc_info()[-1])
+			where = " <- ".join("%s:%d" % (os.path.basename(f.filename), f.lineno) for f in reversed(tb[-4:]))
+			last = {"ok": False, "tries": attempt + 1, "error": "%s: %s" % (type(e).__name__, str(e)[:300]), "where": where,
+					"line": tb[-1].line}
+			if not isinstance(e, AssertionError):
+				break
+		finally:
+			signal.alarm(0)
+	return last
+
+
+def backendLevelTests(Backend, impl):
+	"""the reference's tests that take the backend object (or a kernel module of it)"""
+	from PuzzleLib.Cuda.Wrappers import CuDnn, CuDnnNorm, CuBlas, CuDnnMemory
+	from PuzzleLib.Cuda.Kernels import MatVec, Pool, Costs, Memory
+	from PuzzleLib.Cuda import GPUArray as GPUArrayTests, Utils
+
+	tests = {}
+	bnd = Backend.getBackend(0, initmode=2)
+
+	for mod in (CuDnn, CuDnnNorm, CuBlas):
+		for name in dir(mod):
+			if not name.endswith("Test") or name == "backendTest":
+				continue
+			fn = getattr(mod, name)
+			nargs = fn.__code__.co_argcount
+			for dtype, atol in bnd.dtypesSupported():
+				import numpy as np
+				key = "Cuda/Wrappers/%s.py::%s[%s]" % (mod.__name__.split(".")[-1], name, np.dtype(dtype).name)
+				if nargs == 1:
+					tests[key.split("[")[0]] = (lambda fn=fn: fn(bnd))
+				elif nargs == 3:
+					tests[key] = (lambda fn=fn, dtype=dtype, atol=atol: fn(bnd, dtype, atol))
+				elif nargs == 4:   # CuDnnNorm: (bnd, dtype, atol, calctype)
+					tests[key] = (lambda fn=fn, dtype=dtype, atol=atol: fn(bnd, dtype, atol, np.float32))
+
+	tests["Cuda/Wrappers/CuDnnMemory.py::backendTest"] = lambda: CuDnnMemory.backendTest(Backend)
+	tests["Cuda/GPUArray.py::backendTest"] = lambda: GPUArrayTests.backendTest(Backend)
+	tests["Cuda/Utils.py::backendTest"] = lambda: Utils.backendTest(Backend)
+
+	if impl == "ref":
+		tests["Cuda/Kernels/MatVec.py::calc"] = lambda: [
+			(MatVec.calcTest(MatVec.MatModule(bnd), d, a), MatVec.batchCalcTest(MatVec.MatModule(bnd), d, a)) for d, a in bnd.dtypesSupported()
+		]
+		tests["Cuda/Kernels/Pool.py::backendTest"] = lambda: Pool.backendTest(Backend)
+		tests["Cuda/Kernels/Costs.py::backendTest"] = lambda: Costs.backendTest(Backend)
+		tests["Cuda/Kernels/Memory.py::backendTest"] = lambda: Memory.backendTest(Backend)
+	else:
+		# the kernel-module tests take a module object: hand them this backend's modules instead of the NVRTC ones
+		tests["Cuda/Kernels/MatVec.py::calc"] = lambda: [
+			(MatVec.calcTest(bnd.matmod, d, a), MatVec.batchCalcTest(bnd.matmod, d, a)) for d, a in bnd.dtypesSupported()
+		]
+		tests["Cuda/Kernels/Pool.py::poolTest"] = lambda: Pool.poolTest(bnd.poolmod)
+		tests["Cuda/Kernels/Pool.py::unpoolTest"] = lambda: Pool.unpoolTest(bnd.poolmod)
+		tests["Cuda/Kernels/Costs.py::crossEntropyTest"] = lambda: Costs.crossEntropyTest(bnd.costmod)
+		tests["Cuda/Kernels/Costs.py::svmTest"] = lambda: Costs.svmTest(bnd.costmod)
+	return tests
+
+
+def main():
+	ap = argparse.ArgumentParser()
+	ap.add_argument("--impl", choices=("b200", "ref"), required=True)
+	ap.add_argument("--out", default=None)
+	ap.add_argument("--only", default=None, help="comma separated substrings of test names")
+	ap.add_argument("--retries", type=int, default=4)
+	ap.add_argument("--limit", type=int, default=180, help="seconds per test")
+	args = ap.parse_args()
+
+	refroot = os.path.join(ROOT, "baseline", "_ref")
+	if args.impl == "b200":
+		from puzzlelib_b200 import seam
+		seam.install(refroot)
+	else:
+		sys.path[:0] = [refroot]
+		sys.path.append(os.path.join(refroot, "stubs"))
+
+	from PuzzleLib import Config
+	Config.showWarnings = False
+	from PuzzleLib.Cuda import Backend
+
+	only = args.only.split(",") if args.only else None
+	report, t0 = {}, time.time()
+
+	def wanted(name):
+		return only is None or any(s in name for s in only)
+
+	for name, fn in backendLevelTests(Backend, args.impl).items():
+		if wanted(name):
+			report[name] = runOne(fn, args.retries, args.limit)
+			print("%-70s %s" % (name, "ok" if report[name]["ok"] else report[name]["error"]), flush=True)
+
+	refpkg = os.path.join(refroot, "PuzzleLib")
+	for rel in discover(refpkg):
+		if not wanted(rel) or rel in SKIP:
+			continue
+		modname = "PuzzleLib." + rel[:-3].replace("/", ".")
+		try:
+			mod = importlib.import_module(modname)
+		except BaseException as e:
+			report[rel] = {"ok": False, "error": "import: %s: %s" % (type(e).__name__, str(e)[:300])}
+			print("%-70s %s" % (rel, report[rel]["error"]), flush=True)
+			continue
+		if not hasattr(mod, "unittest") or hasattr(mod, "main"):
+			continue
+		cwd = os.getcwd()
+		os.chdir(os.path.dirname(os.path.join(refpkg, rel)))
+		try:
+			report[rel] = runOne(mod.unittest, args.retries, args.limit)
+		finally:
+			os.chdir(cwd)
+		print("%-70s %s" % (rel, "ok" if report[rel]["ok"] else report[rel]["error"]), flush=True)
+
+	npass = sum(1 for r in report.values() if r["ok"])
+	summary = {"impl": args.impl, "passed": npass, "failed": len(report) - npass, "seconds": round(time.time() - t0, 1), "tests": report}
+	print("SUMMARY %s: %d passed, %d failed in %.0f s" % (args.impl, npass, len(report) - npass, time.time() - t0))
+	if args.out:
+		os.makedirs(os.path.dirname(os.path.abspath(args.out)), exist_ok=True)
+		with open(args.out, "w") as f:
+			json.dump(summary, f, indent=1, sort_keys=True)
+
+
+if __name__ == "__main__":
+	main()
