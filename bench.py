@@ -4,10 +4,16 @@
   python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...   data parallel, one rank per GPU
   python bench.py --impl reference ...                               the CPU arm (oracle port on the host cores)
 
+The model, the containers, the optimizer and their whole Python call path are the REFERENCE's own
+(`PuzzleLib.Models.Nets.ResNet.loadResNet`, `Containers.Sequential / Parallel`, `Optimizers.MomentumSGD`, `Backend/*.py`),
+imported unmodified from baseline/_ref with this repository behind the `Cuda/Backend.py` seam (puzzlelib_b200/seam.py).
+
 One "step" = zeroGradParams + net(data) + net.backward(grad) + gradient sync (mean over ranks, NCCL) + momentum-SGD
 update, i.e. one Trainer.handleBatch of the reference with the cost replaced by a fixed synthetic output gradient
 (SURVEY 8d C2/C4).  `value` times K steps with the input batch already resident in HBM; `e2e` repeats the measurement
 with the batch copied from pinned host memory every step and the softmax output read back to the host every step.
+At N=1 the line also carries `reference_gpu`: the same step through the reference's OWN cuDNN / cuBLAS / NVRTC backend
+on the same GPU (tools/bench_ref_cuda.py --impl ref, a separate process: the backend is an import-time global).
 torch is used only as the rendezvous (gloo) between ranks; all device work goes through libpzb200.so.
 """
 import argparse
@@ -149,31 +155,67 @@ def referenceArm(args):
 
 
 # ---------------------------------------------------------------------------------------------------- GPU arm
+def referenceGpu(args):
+	"""the reference's own CUDA backend (cuDNN / cuBLAS / NVRTC) on the same box, same model / batch / step"""
+	cmd = [sys.executable, os.path.join(ROOT, "tools", "bench_ref_cuda.py"), "--impl", "ref", "--model", args.model, "--batch", str(BATCH),
+		   "--steps", str(max(3, min(10, args.steps))), "--warmup", "3", "--dtype", "f32" if args.dtype == "f32" else "f16"]
+	try:
+		out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+		line = [l for l in out.stdout.splitlines() if l.startswith("{")]
+		if not line:
+			return {"unavailable": (out.stderr.strip().splitlines() or ["no output"])[-1][:200]}
+		res = json.loads(line[-1])
+		return {"value": res["images_per_s"], "unit": "images/s", "ms_per_step": res["ms_per_step"], "steps": res["steps"],
+				"backend": "PuzzleLib Cuda backend (cuDNN %s, cuBLAS, NVRTC) built by baseline/build_ref.py; eager, host-driven" % cudnnVersion(),
+				"dtype": res["dtype"]}
+	except Exception as e:      # noqa: BLE001
+		return {"unavailable": "%s: %s" % (type(e).__name__, str(e)[:200])}
+
+
+def cudnnVersion():
+	try:
+		import ctypes
+		return str(ctypes.CDLL("libcudnn.so.9").cudnnGetVersion())
+	except Exception:      # noqa: BLE001
+		return "9"
+
+
+def calcMode16(net, dt):
+	"""net.calcMode for a 16-bit type.  float16 is the reference's own path (Containers/Container.py:216-223); bfloat16 is this
+	backend's extension through seam.calcMode, which also covers modules whose calcMode only checks a
+	{float16, float32} whitelist (Modules/BatchNormND.py:102-110)."""
+	from puzzlelib_b200 import seam
+	if np.dtype(dt) == np.float16:
+		net.calcMode(np.float16)
+	else:
+		seam.calcMode(net, dt)
+
+
 def gpuArm(args):
-	from puzzlelib_b200 import Config, driver
+	from puzzlelib_b200 import seam, driver
 	from puzzlelib_b200.grid import nodeFromEnvironment
 
 	node = nodeFromEnvironment()
 	if node.gridsize != args.gpus:
 		raise SystemExit("--gpus %d does not match WORLD_SIZE %d (launch with torch.distributed.run)" % (args.gpus, node.gridsize))
 
-	Config.deviceIdx = node.device
+	seam.install(deviceIdx=node.device)            # the reference tree (baseline/_ref) over this backend; Config.deviceIdx = our GPU
 	driver.Device(node.device).set()
 	node.attach()
 
-	from puzzlelib_b200 import modules as M
-	from puzzlelib_b200.nets import loadResNet
-	from puzzlelib_b200.optim import MomentumSGD
-	from puzzlelib_b200.shim import backend
+	from PuzzleLib import Config
+	Config.showWarnings = False
+	from PuzzleLib.Backend import gpuarray
+	from PuzzleLib.Models.Nets.ResNet import loadResNet
+	from PuzzleLib.Optimizers.MomentumSGD import MomentumSGD
 
-	bnd = backend()
 	np.random.seed(1234)                       # same initial weights on every rank (and broadcast from rank 0 anyway)
 	# the headline is ResNet-50 fp32 (BASELINE.json configs[1]); --model / --dtype / --batch time the other configs for profiles/
 	global BATCH, FLOP_PER_IMAGE, METRIC
 	if args.batch:
 		BATCH = args.batch
 	if args.model == "vgg16":
-		from puzzlelib_b200.nets import loadVGG
+		from PuzzleLib.Models.Nets.VGG import loadVGG
 		net = loadVGG(None, "16", initscheme="he")
 		FLOP_PER_IMAGE = 92.8e9
 	else:
@@ -181,7 +223,7 @@ def gpuArm(args):
 	dt = np.dtype(np.float32)
 	if args.dtype != "f32":
 		dt = driver.bfloat16 if args.dtype == "bf16" else np.dtype(np.float16)
-		net.calcMode(dt)
+		calcMode16(net, dt)
 	if args.model != "resnet50" or args.dtype != "f32":
 		METRIC = "%s %s fwd+bwd images/sec" % ({"resnet50": "ResNet-50", "vgg16": "VGG-16"}[args.model], args.dtype)
 	optimizer = MomentumSGD(learnRate=1e-3, momRate=0.9, nodeinfo=node if node.gridsize > 1 else None)
@@ -190,8 +232,8 @@ def gpuArm(args):
 	rng = np.random.RandomState(1234 + node.index)      # every rank draws its own shard of the global batch
 	pinned = driver.PinnedBuffer((BATCH, 3, 224, 224), dt)
 	pinned.array[...] = rng.randn(BATCH, 3, 224, 224).astype(dt)
-	data = M.gpuarray.to_gpu(pinned.array)
-	grad = M.gpuarray.to_gpu((rng.randn(BATCH, 1000) * 1e-3).astype(dt))
+	data = gpuarray.to_gpu(pinned.array)
+	grad = gpuarray.to_gpu((rng.randn(BATCH, 1000) * 1e-3).astype(dt))
 	hostOut = driver.PinnedBuffer((BATCH, 1000), dt)
 
 	def step(e2e=False, asyncCopy=False):
@@ -200,7 +242,7 @@ def gpuArm(args):
 		optimizer.zeroGradParams()
 		out = net(data)
 		net.backward(grad)
-		optimizer.update()                                           # N > 1: all-reduce(mean) fused with the SGD update
+		optimizer.update()                                           # N > 1: nodeinfo.sumTensor (NCCL mean) + the SGD kernel
 		if e2e:                                                      # D2H of the step's result (the softmax output)
 			driver.check(driver.lib.pz_memcpy_d2h(hostOut.ptr, out.ptr, out.nbytes, None, 1 if asyncCopy else 0))
 		net.reset()                                                  # like Handler.handle: activations go back to the pool
@@ -244,7 +286,8 @@ def gpuArm(args):
 			ms = node.rendezvous.maxValue(ms)
 		return ms
 
-	for _ in range(max(10, args.warmup)):                        # >= 10: the batch-norm running-average factor reaches its floor (0.1)
+	warmup = max(10, args.warmup)                                # >= 10: the batch-norm running-average factor reaches its floor (0.1)
+	for _ in range(warmup):
 		step()
 
 	# ---- eager: every operator call goes through the Python module API (Module.__call__ -> Backend -> ctypes -> libpzb200.so)
@@ -305,9 +348,14 @@ def gpuArm(args):
 	fam = families[top]
 	if top == "gemm":     # tcgen05 launches above the machine ridge (3x3 / 7x7 convolutions, large GEMMs)
 		achieved = fam["flops"] / (fam["ms"] * 1e-3) / 1e12
-		peak = peaks["bf16"] / 2.0
+		if args.dtype == "f32":
+			peak = peaks["bf16"] / 2.0
+			note = "tf32 products: 0.5 x the %s bf16 sustained GEMM peak (no tf32 figure in MEASURED_PEAKS.json)" % peaks["src"]
+		else:
+			peak = peaks["bf16"]
+			note = "%s bf16 sustained GEMM peak (16-bit products, f32 accumulation)" % peaks["src"]
 		roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
-					"peak_note": "tf32 products: 0.5 x the %s bf16 sustained GEMM peak (no tf32 figure in MEASURED_PEAKS.json)" % peaks["src"]}
+					"peak_note": note}
 	else:
 		achieved = fam["bytes"] / (fam["ms"] * 1e-3) / 1e9
 		roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm"], "unit": "GB/s", "frac": achieved / peaks["hbm"],
@@ -339,7 +387,7 @@ def gpuArm(args):
 	})
 
 	line = {
-		"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": node.gridsize, "steps": args.steps, "warmup": max(3, args.warmup),
+		"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": node.gridsize, "steps": args.steps, "warmup": warmup,
 		"ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
 		"dtype": "f32 (tensor-core contractions: tf32 products, f32 accumulation -- what cuDNN/cuBLAS TENSOR_OP_MATH give the reference here)"
 				 if args.dtype == "f32" else "%s storage, f32 accumulation" % args.dtype,
@@ -372,6 +420,9 @@ def gpuArm(args):
 					  "reference's own numpy CPU backend cannot run conv/pool/batch-norm backward (SURVEY F5)" % (args.cpu_images, dt)
 		}
 
+	if node.gridsize == 1 and not args.no_ref_gpu:
+		line["reference_gpu"] = referenceGpu(args)
+
 	if graphNote:
 		line["config"]["graph"] = graphNote
 	print(json.dumps(line), flush=True)
@@ -386,6 +437,7 @@ def main():
 	parser.add_argument("--impl", default="ours", choices=["ours", "reference"])
 	parser.add_argument("--cpu-images", type=int, default=8, help="bounded CPU-baseline sample (images per step)")
 	parser.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+	parser.add_argument("--no-ref-gpu", action="store_true", help="skip the reference-CUDA-backend leg (reference_gpu)")
 	parser.add_argument("--no-graph", action="store_true", help="time the eager module API only (no CUDA-graph replay)")
 	parser.add_argument("--model", default="resnet50", choices=["resnet50", "vgg16"], help="side measurements; the headline is resnet50")
 	parser.add_argument("--dtype", default="f32", choices=["f32", "bf16", "f16"], help="storage type (side measurements)")

@@ -124,6 +124,41 @@ int pz_axpby(int dtype, void* out, const void* x, float alpha, const void* y, fl
 int pz_scale_shift(int dtype, void* out, const void* in, float a, float b, int64_t n, void* stream); /* linearKer :1073-1099 */
 int pz_mul(int dtype, void* out, const void* a, const void* b, int64_t n, void* stream);    /* mulKer :1047-1071 */
 int pz_add2(int dtype, void* out, const void* a, const void* b, int64_t n, void* stream);   /* Add.py:15-23 as one pass */
+/* `slice=` launches (Cuda/SourceModule.py:162-200, the `<name>_strided` twin of every ElementwiseKernel; callers:
+ * Modules/Activation.py:71-76, NoiseInjector.py:73-93, Dropout.py:58-74): elements start, start + step, ... < min(stop, n) */
+int pz_act_fwd_slice(int kind, int dtype, void* out, const void* in, int64_t n, float a, float b, int64_t start, int64_t stop,
+					 int64_t step, void* stream);
+int pz_act_bwd_slice(int kind, int dtype, void* ingrad, const void* outgrad, const void* ref, int64_t n, float a, float b,
+					 int64_t start, int64_t stop, int64_t step, void* stream);
+int pz_axpby_slice(int dtype, void* out, const void* x, float alpha, const void* y, float beta, int64_t n, int64_t start,
+				   int64_t stop, int64_t step, void* stream);
+int pz_mul_slice(int dtype, void* out, const void* a, const void* b, int64_t n, int64_t start, int64_t stop, int64_t step,
+				 void* stream);
+
+/* The remaining elementwise kernels `Backend/Kernels/ElementWise.py:96-125` and `Costs.py:45-49` bind from the backend object.
+ * One entry: `ptrs` are the kernel's pointer arguments in the reference's order, `scalars` its float arguments, `aux` its two
+ * int arguments (pointwise costs); element i = start + k * step < min(stop, n).
+ *   PZ_EW_ABS (out, in)                                  absKer           ElementWise.py:1117
+ *   PZ_EW_WEIGHT_DECAY (grad, param; rate)               weightDecayKer   :1109    grad -= rate * param
+ *   PZ_EW_L1_PENALTY (outgrad, ingrad, data; a)          l1penaltyKer     :1125
+ *   PZ_EW_L1_GRAD (grad, pred, target; norm)             l1gradKer        :1133
+ *   PZ_EW_RBM (out, in, uni)                             rbmKer           :1100    out = uni < sigmoid(in)
+ *   PZ_EW_RMSPROP (param, grad, ms; lr, factor, eps)     rmspropKer       :860
+ *   PZ_EW_RMSPROP_GRAVES (param, grad, mg, ms, delta; lr, alpha, momRate, eps)     :906
+ *   PZ_EW_ADAGRAD (param, grad, h; lr, eps)              adagradKer       :664
+ *   PZ_EW_ADADELTA (param, grad, msg, msdx; rho, eps)    adadeltaKer      :614
+ *   PZ_EW_SMORMS3 (param, grad, mem f32, mg f32, ms f32; lr, eps)  smorms3Ker :957
+ *   PZ_EW_BCE (scores, labels i32, totalError, grad; aux numsamples, spatialDim)   Costs.py:8
+ *   PZ_EW_HINGE (scores, labels i32, totalError, grad; aux numsamples, numcases)   Costs.py:25
+ *   PZ_EW_SMOOTH_L1 (pred, target, totalError, grad; norm, fullnorm)               Costs.py:42
+ *   PZ_EW_L1_HINGE (x1, x2, labels i32, totalError, g1, g2; aux numsamples, numcases)  Costs.py:58 */
+enum {
+	PZ_EW_ABS = 0, PZ_EW_WEIGHT_DECAY = 1, PZ_EW_L1_PENALTY = 2, PZ_EW_L1_GRAD = 3, PZ_EW_RBM = 4, PZ_EW_RMSPROP = 5,
+	PZ_EW_RMSPROP_GRAVES = 6, PZ_EW_ADAGRAD = 7, PZ_EW_ADADELTA = 8, PZ_EW_SMORMS3 = 9,
+	PZ_EW_BCE = 10, PZ_EW_HINGE = 11, PZ_EW_SMOOTH_L1 = 12, PZ_EW_L1_HINGE = 13
+};
+int pz_eltwise(int op, int dtype, void* const* ptrs, int nptrs, const float* scalars, int nscalars, const int* aux, int64_t n,
+			   int64_t start, int64_t stop, int64_t step, void* stream);
 int pz_cast(int dst_dtype, void* dst, int src_dtype, const void* src, int64_t n, void* stream); /* GPUArray.py astype */
 /* dst[r][i] += src[r][i], pitched rows (3-d transposed convolution: scatter-add of per-slice gradients) */
 int pz_add2d(int dtype, void* dst, int64_t dpitch, const void* src, int64_t spitch, int64_t width, int64_t rows, void* stream);
@@ -255,6 +290,15 @@ int pz_lrn_bwd(int dtype, int mode, const void* x, const void* grad, void* dx, v
 int pz_rng_fill(int kind, void* out, int64_t n, uint64_t seed, uint64_t offset, float a, float b, void* stream);
 int pz_dropout(int dtype, void* out, const void* in, const void* rands, uint32_t partition, float p, int64_t n, int64_t mapsize,
 			   void* stream);
+/* costmod.svm (Cuda/Kernels/Costs.py:109-130,249-279): l1 / squared hinge over (samples, cases, spatial...) scores */
+int pz_svm(int l2, const void* scores, const void* labels, int64_t samples, int64_t cases, int64_t spatial, void* error, void* grad,
+		   void* stream);
+/* getAccuracyKernel reductions (Costs.py:172-205): kind 0 calcBCEAccuracy, 1 klDivergence (also writes grad), 2 l1HingeAccuracy;
+ * *out += the sum */
+int pz_cost_reduce(int kind, const void* x, const void* y, void* grad, float gradnorm, int64_t n, void* out, void* stream);
+int pz_reduce_minmax_i32(const void* in, int64_t n, int want_max, void* out, void* stream);
+int pz_dropout_slice(int dtype, void* out, const void* in, const void* rands, uint32_t partition, float p, int64_t n,
+					 int64_t mapsize, int64_t start, int64_t stop, int64_t step, void* stream);
 int pz_sgd_nesterov(int dtype, void* param, const void* grad, void* mom, float learn_rate, float mom_rate, int64_t n, void* stream);
 int pz_adam(int dtype, void* param, const void* grad, void* mg, void* ms, float learn_rate, float fix1, float fix2, float epsilon,
 			int64_t n, void* stream);

@@ -15,11 +15,17 @@ IS in the tree.  Each function below therefore follows either
 Pinning.  (a) tests/golden/ref_cpu_*.npz hold outputs of the REFERENCE ITSELF (its numpy CPU backend, imported from
 /root/reference by tools/gen_golden.py in the build container) for conv2d / pool2d / batch-norm-inference forward,
 Linear forward+backward and every activation forward+backward; tests/test_oracle.py checks this oracle against them.
-(b) The backward conv / pool / batch-norm / softmax formulas cannot be produced by the reference without a GPU (its
-CPU backend is inference-only) -- they are pinned by finite-difference gradient checks of this oracle in
-fp64 (the reference's own TestLib/GradientCheck.py:25-52 method) and by adjoint identities.
-(c) cuDNN's max-pool-backward tie routing, the biased-vs-unbiased running variance and TF32 rounding are asserted by
-no reference test: "parity unpinned" for exactly those three behaviours ("Oracle").
+(b) tests/golden/ref_cuda_ops.npz holds outputs of the reference's OWN CUDA backend (cuDNN 9.10 / cuBLAS 12.9 / NVRTC),
+built from the unmodified tree by baseline/build_ref.py and run on a B200 by tools/gen_golden_cuda.py: forward AND backward
+of conv (dgrad / wgrad / bgrad incl. scale / momentum accumulation, groups, dilation, 3-d), deconv, batch-norm train /
+backward / inference (incl. the running variance: the UNBIASED estimate), pooling backward on tied maxima (the first maximum
+of a window in row-major order takes the gradient), softmax, LRN, GEMM, cross-entropy, the optimizer kernels, argmax (whose
+tie order along the last axis is the reference kernel's butterfly order, not the first occurrence).
+tests/test_oracle_cuda_golden.py checks every function of this oracle against them: PARITY PINNED for forward and backward.
+(c) Not pinned by reference output: recurrent layers (the reference's cuDNN-7 RNN API does not exist in cuDNN 9, so its RNN
+cannot run on this stack; the oracle follows the host formulas of Cuda/Wrappers/CuDnnRnn.py:178-300) and TF32 rounding
+(cuDNN computes float32 convolutions in full fp32 on this stack; this backend's tcgen05 path uses TF32 products and is held
+to the 1e-3 relative bar of BASELINE.json's north_star).
 
 All functions take and return numpy arrays; `dtype` selects the accumulation type (float64 for parity checks,
 float32 for the timed CPU baseline).
@@ -181,8 +187,29 @@ def matsum(tensor, axis, out=None, alpha=1.0, beta=0.0, dtype=np.float64):
 
 
 def argmax(tensor, axis):
-	"""first occurrence wins (reference: Cuda/Kernels/MatVec.py:8-57)"""
-	return np.argmax(tensor, axis=axis).astype(np.int32)
+	"""reference: Cuda/Kernels/MatVec.py:8-57.  Along any axis but the last the kernel scans sequentially with a strict
+	comparison: the first occurrence wins.  Along the LAST axis (minMaxOnRow) 32 lanes scan i = lane, lane + 32, ... (strict),
+	merge in an xor butterfly (strict: a lane keeps its own survivor on a tie) and lane 0's survivor is what lands in memory
+	-- pinned by the reference's own CUDA backend (tests/golden/ref_cuda_ops.npz, matvec_f32/argmaxties)."""
+	tensor = np.asarray(tensor)
+	if axis % tensor.ndim != tensor.ndim - 1:
+		return np.argmax(tensor, axis=axis).astype(np.int32)
+
+	w = tensor.shape[-1]
+	rows = tensor.reshape(-1, w).astype(np.float64)
+	padded = np.full((rows.shape[0], -(-w // 32) * 32), -np.inf)
+	padded[:, :w] = rows
+	lanes = padded.reshape(rows.shape[0], -1, 32)                       # [row][round][lane]
+	best = lanes.max(axis=1)
+	idx = (lanes.argmax(axis=1) * 32 + np.arange(32)).astype(np.int64)     # first (strict) occurrence inside every lane
+	idx[np.isneginf(best)] = -1
+	mask = 16
+	while mask:
+		partner = np.arange(32) ^ mask
+		take = best[:, partner] > best
+		best, idx = np.where(take, best[:, partner], best), np.where(take, idx[:, partner], idx)
+		mask //= 2
+	return idx[:, 0].reshape(tensor.shape[:-1]).astype(np.int32)
 
 
 # ================================================================================================ batch norm

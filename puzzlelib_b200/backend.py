@@ -570,8 +570,14 @@ class BlasContext:
 
 		ga, ra, ca, lda, sa = geometry(A, formatA)
 		gb, rb, cb, ldb, sb = geometry(B, formatB)
-		if ga != gb:
-			raise ValueError("gemmBatched operands have different group counts")
+		if ga != gb and ga != 1 and gb != 1:
+			raise ValueError("invalid input gpuarray dims")
+		# a single-group operand is shared by every group of the other one (CuBlas.c:255-262,304-305: stride 0)
+		if ga == 1 and gb > 1:
+			sa = 0
+		elif gb == 1 and ga > 1:
+			sb = 0
+		ga = max(ga, gb)
 		M, K = (ca, ra) if transpA else (ra, ca)
 		Kb, N = (cb, rb) if transpB else (rb, cb)
 		if K != Kb:
@@ -769,6 +775,51 @@ class CostModule:
 		return error, grad
 
 
+	def svm(self, scores, labels, mode, error=None, allocator=None):
+		"""reference: Cuda/Kernels/Costs.py:249-279 -- mode "l1" (hinge) or "l2" (squared hinge); -> (error, grad)"""
+		_requireArray(scores, "scores")
+		_requireArray(labels, "labels")
+		if scores.dtype != _f32 or labels.dtype != np.int32:
+			raise ValueError("svm needs float32 scores and int32 labels")
+		if mode not in ("l1", "l2"):
+			raise KeyError(mode)
+
+		grad = GPUArray.empty(scores.shape, _f32, allocator=allocator)
+		if error is None:
+			error = GPUArray.empty((), _f32, allocator=allocator)
+		error.fill(0.0)
+
+		samples, cases, spatial = scores.shape[0], scores.shape[1], prod(scores.shape[2:])
+		if labels.size != samples * spatial:
+			raise ValueError("labels must hold one class index per sample and position")
+		check(lib.pz_svm(1 if mode == "l2" else 0, scores.ptr, labels.ptr, samples, cases, spatial, error.ptr, grad.ptr, None))
+		return error, grad
+
+	def getAccuracyKernel(self, name):
+		"""reference: Cuda/Kernels/Costs.py:172-210 -- reductions returning a float32 device scalar"""
+		if name == "calcAccuracy":
+			def ker(x, y, allocator=None):
+				if x.dtype != np.int32 or y.dtype != np.int32 or x.size != y.size:
+					raise ValueError("calcAccuracy needs two int32 tensors of one size")
+				out = GPUArray.zeros((), _f32, allocator=allocator)
+				check(lib.pz_count_mismatch(x.ptr, y.ptr, x.size, out.ptr, None))
+				return out
+			return ker
+
+		kinds = {"calcBCEAccuracy": (0, _i32), "klDivergence": (1, _f32), "l1HingeAccuracy": (2, _i32)}
+		if name not in kinds:
+			raise NotImplementedError(name)
+		kind, ytype = kinds[name]
+
+		def ker(x, y, grad=None, gradnorm=0.0, allocator=None):
+			if x.dtype != _f32 or y.dtype != ytype or x.size != y.size or (kind == 1) != (grad is not None):
+				raise ValueError("%s: invalid arguments" % name)
+			out = GPUArray.zeros((), _f32, allocator=allocator)
+			check(lib.pz_cost_reduce(kind, x.ptr, y.ptr, grad.ptr if grad is not None else None, float(gradnorm), x.size, out.ptr, None))
+			return out
+		return ker
+
+
 # ============================================================================================================ rng
 class RandomNumberGenerator:
 	"""reference: Cuda/Source/Libs/CuRand.c (the generator object behind `gpuarray.globalRng`): fillInteger / fillUniform /
@@ -860,7 +911,20 @@ _ACT_KINDS = {"sigmoid": 0, "tanh": 1, "relu": 2, "leakyRelu": 3, "elu": 4, "sof
 
 def _noSlice(kwargs):
 	if kwargs.get("slice") is not None:
-		raise NotImplementedError("strided `slice=` elementwise launches are not implemented in the B200 backend")
+		raise NotImplementedError("this kernel has no strided `slice=` form in the B200 backend")
+
+
+def _slice(kwargs, size):
+	"""`slice=` of an elementwise launch -> (start, stop, step) or None (reference: Cuda/SourceModule.py:162-173)"""
+	slc = kwargs.get("slice")
+	if slc is None:
+		return None
+	start = 0 if slc.start is None else int(slc.start)
+	stop = size if slc.stop is None else int(slc.stop)
+	step = 1 if slc.step is None else int(slc.step)
+	if start < 0 or step < 1:
+		raise ValueError("invalid elementwise slice %s" % (slc, ))
+	return start, min(stop, size), step
 
 
 def _actFactory(kind, nscalars):
@@ -870,10 +934,13 @@ def _actFactory(kind, nscalars):
 		dt = dtypeCode(dtype)
 
 		def fwd(out, inp, *scalars, **kwargs):
-			_noSlice(kwargs)
 			a = float(scalars[0]) if nscalars > 0 else 0.0
 			b = float(scalars[1]) if nscalars > 1 else 0.0
-			check(lib.pz_act_fwd(code, dt, out.ptr, inp.ptr, out.size, a, b, None))
+			slc = _slice(kwargs, out.size)
+			if slc is None:
+				check(lib.pz_act_fwd(code, dt, out.ptr, inp.ptr, out.size, a, b, None))
+			else:
+				check(lib.pz_act_fwd_slice(code, dt, out.ptr, inp.ptr, out.size, a, b, *slc, None))
 
 		return fwd
 
@@ -881,14 +948,71 @@ def _actFactory(kind, nscalars):
 		dt = dtypeCode(dtype)
 
 		def bwd(ingrad, outgrad, ref, *scalars, **kwargs):
-			_noSlice(kwargs)
 			a = float(scalars[0]) if nscalars > 0 else 0.0
 			b = float(scalars[1]) if nscalars > 1 else 0.0
-			check(lib.pz_act_bwd(code, dt, ingrad.ptr, outgrad.ptr, ref.ptr, ingrad.size, a, b, None))
+			slc = _slice(kwargs, ingrad.size)
+			if slc is None:
+				check(lib.pz_act_bwd(code, dt, ingrad.ptr, outgrad.ptr, ref.ptr, ingrad.size, a, b, None))
+			else:
+				check(lib.pz_act_bwd_slice(code, dt, ingrad.ptr, outgrad.ptr, ref.ptr, ingrad.size, a, b, *slc, None))
 
 		return bwd
 
 	return factory, derFactory
+
+
+_EW_OPS = {
+	"absKer": 0, "weightDecayKer": 1, "l1penaltyKer": 2, "l1gradKer": 3, "rbmKer": 4, "rmspropKer": 5, "rmspropGravesKer": 6,
+	"adagradKer": 7, "adadeltaKer": 8, "smorms3Ker": 9, "bceKer": 10, "hingeKer": 11, "smoothL1Ker": 12, "l1HingeKer": 13
+}
+
+
+def _genericKernel(name, nptrs, nscalars, naux=0, dtype=None, f32state=()):
+	"""A kernel object with the reference's calling convention `(ptr args..., scalar args..., slice=None)` over pz_eltwise
+	(reference objects: Cuda/Kernels/ElementWise.py, Costs.py:8-74).  `dtype` None -> taken from the first array."""
+	op = _EW_OPS[name]
+
+	def ker(*args, **kwargs):
+		if len(args) != nptrs + nscalars + naux:
+			raise TypeError("%s takes %d arguments (%d given)" % (name, nptrs + nscalars + naux, len(args)))
+		arrays, rest = args[:nptrs], args[nptrs:]
+		dt = arrays[0].dtype if dtype is None else dtype
+		for i, ary in enumerate(arrays):
+			_requireArray(ary, "argument #%d" % (i + 1))
+			want = _f32 if i in f32state else (dt if ary.dtype != _i32 else _i32)
+			if ary.dtype != want:
+				raise ValueError("%s: argument #%d has dtype %s" % (name, i + 1, ary.dtype))
+
+		# the launch size is the size of the first array argument (Cuda/SourceModule.py:128-137)
+		size = arrays[0].size
+		start, stop, step = _slice(kwargs, size) or (0, size, 1)
+
+		ptrs = (ctypes.c_void_p * nptrs)(*[ary.ptr for ary in arrays])
+		if naux:       # pointwise costs: scalars are (int, int) or (float, float) after the pointers
+			scalars = (ctypes.c_float * 4)()
+			aux = (ctypes.c_int * 2)(int(rest[0]), int(rest[1]))
+			check(lib.pz_eltwise(op, dtypeCode(dt), ptrs, nptrs, scalars, 0, aux, size, start, stop, step, None))
+		else:
+			scalars = (ctypes.c_float * max(1, nscalars))(*[float(v) for v in rest])
+			check(lib.pz_eltwise(op, dtypeCode(dt), ptrs, nptrs, scalars, nscalars, None, size, start, stop, step, None))
+
+	ker.__name__ = name
+	return ker
+
+
+def _genericFactory(name, nptrs, nscalars, f32state=()):
+	"""`fooKer(dtype)` -> kernel, like the reference's memoized factories"""
+	cache = {}
+
+	def factory(dtype):
+		dtype = np.dtype(dtype)
+		if dtype not in cache:
+			dtypeCode(dtype)
+			cache[dtype] = _genericKernel(name, nptrs, nscalars, f32state=f32state)
+		return cache[dtype]
+
+	factory.__name__ = name
+	return factory
 
 
 class ConvPerf:
@@ -989,12 +1113,7 @@ class B200Backend:
 		uni = 0
 		bi = 1
 
-	notImplemented = (
-		"ctcmod", "embedmod", "padmod", "prelumod", "upsamplemod", "memmod",
-		"bceKer", "hingeKer", "smoothL1Ker", "l1HingeKer", "rbmKer", "absKer",
-		"rmspropKer", "rmspropGravesKer", "adagradKer", "adadeltaKer", "smorms3Ker",
-		"weightDecayKer", "l1penaltyKer", "l1gradKer"
-	)
+	notImplemented = ("ctcmod", "embedmod", "padmod", "prelumod", "upsamplemod", "memmod")
 
 	def __init__(self, deviceIdx, initmode=0, logger=None):
 		self.deviceIdx = deviceIdx
@@ -1063,8 +1182,11 @@ class B200Backend:
 		dt = dtypeCode(dtype)
 
 		def ker(out, x, alpha, y, beta, **kwargs):
-			_noSlice(kwargs)
-			check(lib.pz_axpby(dt, out.ptr, x.ptr, float(alpha), y.ptr, float(beta), out.size, None))
+			slc = _slice(kwargs, out.size)
+			if slc is None:
+				check(lib.pz_axpby(dt, out.ptr, x.ptr, float(alpha), y.ptr, float(beta), out.size, None))
+			else:
+				check(lib.pz_axpby_slice(dt, out.ptr, x.ptr, float(alpha), y.ptr, float(beta), out.size, *slc, None))
 
 		return ker
 
@@ -1073,8 +1195,11 @@ class B200Backend:
 		dt = dtypeCode(dtype)
 
 		def ker(out, a, b, **kwargs):
-			_noSlice(kwargs)
-			check(lib.pz_mul(dt, out.ptr, a.ptr, b.ptr, out.size, None))
+			slc = _slice(kwargs, out.size)
+			if slc is None:
+				check(lib.pz_mul(dt, out.ptr, a.ptr, b.ptr, out.size, None))
+			else:
+				check(lib.pz_mul_slice(dt, out.ptr, a.ptr, b.ptr, out.size, *slc, None))
 
 		return ker
 
@@ -1118,6 +1243,25 @@ class B200Backend:
 
 		return ker
 
+	# reference: Cuda/Kernels/ElementWise.py:1100-1138 (kernel objects, float32 only) and :614-706,860-1003 (factories)
+	absKer = staticmethod(_genericKernel("absKer", 2, 0, dtype=_f32))
+	weightDecayKer = staticmethod(_genericKernel("weightDecayKer", 2, 1, dtype=_f32))
+	l1penaltyKer = staticmethod(_genericKernel("l1penaltyKer", 3, 1, dtype=_f32))
+	l1gradKer = staticmethod(_genericKernel("l1gradKer", 3, 1, dtype=_f32))
+	rbmKer = staticmethod(_genericKernel("rbmKer", 3, 0, dtype=_f32))
+
+	rmspropKer = staticmethod(_genericFactory("rmspropKer", 3, 3))
+	rmspropGravesKer = staticmethod(_genericFactory("rmspropGravesKer", 5, 4))
+	adagradKer = staticmethod(_genericFactory("adagradKer", 3, 2))
+	adadeltaKer = staticmethod(_genericFactory("adadeltaKer", 4, 2))
+	smorms3Ker = staticmethod(_genericFactory("smorms3Ker", 5, 2, f32state=(2, 3, 4)))
+
+	# reference: Cuda/Kernels/Costs.py:8-74 -- (scores / pred, labels / target, totalError, grad..., two ints or two floats)
+	bceKer = staticmethod(_genericKernel("bceKer", 4, 0, naux=2, dtype=_f32))
+	hingeKer = staticmethod(_genericKernel("hingeKer", 4, 0, naux=2, dtype=_f32))
+	smoothL1Ker = staticmethod(_genericKernel("smoothL1Ker", 4, 2, dtype=_f32))
+	l1HingeKer = staticmethod(_genericKernel("l1HingeKer", 6, 0, naux=2, dtype=_f32))
+
 	@staticmethod
 	def castFP16toFP32(outdata, indata, **kwargs):
 		"""reference: Cuda/Kernels/ElementWise.py castFP16toFP32 -- a kernel object, not a factory"""
@@ -1133,21 +1277,10 @@ class B200Backend:
 			raise ValueError("castFP32toFP16 needs a float16 output and a float32 input of one size")
 		check(lib.pz_cast(driver.PZ_F16, outdata.ptr, driver.PZ_F32, indata.ptr, indata.size, None))
 
-	@staticmethod
-	def getAccuracyKernel(name):
-		"""reference: Cuda/Kernels/Costs.py:172-182 -- `calcAccuracy(x, y)`: the number of positions where two int32 label
-		tensors differ, as a float32 device scalar"""
-		if name != "calcAccuracy":
-			raise NotImplementedError(name)
-
-		def ker(x, y, allocator=None):
-			if x.dtype != np.int32 or y.dtype != np.int32 or x.size != y.size:
-				raise ValueError("calcAccuracy needs two int32 tensors of one size")
-			out = GPUArray.zeros((), _f32, allocator=allocator)
-			check(lib.pz_count_mismatch(x.ptr, y.ptr, x.size, out.ptr, None))
-			return out
-
-		return ker
+	def getAccuracyKernel(self, name):
+		"""reference: Cuda/GPUBackend.py:159 -- bound from costmod (Cuda/Kernels/Costs.py:172-210)"""
+		self.updateBackend(2)
+		return self.costmod.getAccuracyKernel(name)
 
 	@staticmethod
 	def _dropoutKer(dtype, mapped):
@@ -1155,10 +1288,11 @@ class B200Backend:
 		parttype = np.dtype(np.uint32) if np.dtype(dtype) == _f32 else np.dtype(np.uint16)
 
 		def ker(outdata, indata, b, v, p, mapsize=1, **kwargs):
-			_noSlice(kwargs)
 			if b.dtype != parttype or b.size * (mapsize if mapped else 1) < indata.size:
 				raise ValueError("dropout needs one %s random word per %s" % (parttype, "map" if mapped else "element"))
-			check(lib.pz_dropout(dt, outdata.ptr, indata.ptr, b.ptr, int(v), float(p), indata.size, int(mapsize) if mapped else 1, None))
+			start, stop, step = _slice(kwargs, indata.size) or (0, indata.size, 1)
+			check(lib.pz_dropout_slice(dt, outdata.ptr, indata.ptr, b.ptr, int(v), float(p), indata.size, int(mapsize) if mapped else 1,
+									   start, stop, step, None))
 
 		return ker
 
@@ -1186,10 +1320,26 @@ class B200Backend:
 	# ---- misc surface used by Backend/gpuarray.py
 	@staticmethod
 	def dtypesSupported():
-		supported = [(np.float32, 1e-5), (np.float16, 1e-2)]
-		if driver.bfloat16 is not None:
-			supported.append((driver.bfloat16, 5e-2))
-		return supported
+		"""the calculation types with the tolerance the reference's own tests hold them to (Cuda/GPUBackend.py:218-220);
+		bfloat16 works everywhere float16 does but is not advertised here: the reference's Modules / tests iterate
+		this list and key python dicts by it (Modules/Cast.py:76, Dropout.py:43)"""
+		return [(np.float32, 1e-5), (np.float16, 1e-2)]
+
+	@staticmethod
+	def dtypesExtra():
+		return [(driver.bfloat16, 5e-2)] if driver.bfloat16 is not None else []
+
+	def fillUniform(self, data, minval=0.0, maxval=1.0, rng=None):
+		"""reference: Cuda/GPUBackend.py:234-241"""
+		if data.dtype != _f32:
+			raise ValueError("fillUniform needs a float32 gpuarray")
+		rng = self.globalRng if rng is None else rng
+		rng.fillUniform(data, minval, maxval)
+
+	def fillNormal(self, data, mean=0.0, stddev=1.0, rng=None):
+		"""reference: Cuda/GPUBackend.py:244-246"""
+		rng = self.globalRng if rng is None else rng
+		rng.fillNormal(data, mean=mean, stddev=stddev)
 
 	@staticmethod
 	def copy(dest, source, allocator=None):
@@ -1292,7 +1442,7 @@ class B200Backend:
 	def deviceSupportsBatchHint(self):
 		return self.device.computeCapability() >= (6, 1)
 
-	def instanceNorm2d(self, data, scale, bias, epsilon, allocator=None):
+	def instanceNorm2d(self, data, scale, bias, epsilon=1e-5, out=None, allocator=None):
 		"""BN over a (1, N*C, H, W) view with the affine parameters tiled N times (reference: GPUBackend.py:381-398)"""
 		batchsize, maps, height, width = data.shape
 		extmaps = batchsize * maps
@@ -1303,18 +1453,18 @@ class B200Backend:
 		if batchsize > 1:
 			scale, bias = self.tile(scale, batchsize, axis=0, allocator=allocator), self.tile(bias, batchsize, axis=0, allocator=allocator)
 
-		outdata, savemean, saveinvvar = self.dnn.batchNormNd(indata, mean, var, scale, bias, epsilon, 1.0, False, 1,
+		outdata, savemean, saveinvvar = self.dnn.batchNormNd(indata, mean, var, scale, bias, epsilon, 1.0, False, 1, out=out,
 															 allocator=allocator)
 		return outdata.reshape(data.shape), savemean, saveinvvar, scale
 
-	def instanceNorm2dBackward(self, grad, data, extscale, savemean, saveinvvar, epsilon, affine, allocator=None):
+	def instanceNorm2dBackward(self, grad, data, extscale, savemean, saveinvvar, epsilon, affine=True, out=None, allocator=None):
 		"""reference: GPUBackend.py:401-416"""
 		batchsize, maps, height, width = grad.shape
 		extmaps = batchsize * maps
 
 		outgrad, scalegrad, biasgrad = self.dnn.batchNormNdBackward(
 			grad.reshape(1, extmaps, height, width), data.reshape(1, extmaps, height, width), extscale, savemean, saveinvvar,
-			epsilon, 1, allocator=allocator
+			epsilon, 1, out=out, allocator=allocator
 		)
 		outgrad = outgrad.reshape(grad.shape)
 

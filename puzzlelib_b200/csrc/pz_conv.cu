@@ -494,15 +494,14 @@ int pz_conv2d_dgrad(int dtype, const pz_conv2d_desc* d, const void* dy, const vo
 		return launch(q, dtype, bn, MODE_MN_CHAN, MODE_TMA, false, 1, &tsrc, pz_stream(stream));
 	}
 
-	if (is1x1 && g.ph == 0 && g.pw == 0 && strided) {
-		// 1x1 strided: dx[n,c,p*sh,q*sw] = sum_k dy[n,k,p,q] * w[k,c]; all other positions of dx are zero (+ bias)
-		PZ_REQUIRE(bias == nullptr, "conv2d dgrad: bias with a strided 1x1 filter is not supported");
+	if (is1x1 && g.ph == 0 && g.pw == 0 && strided && bias == nullptr && (!h16 || use_chan_order(g.Kg, bke))) {
+		// 1x1 strided: dx[n,c,p*sh,q*sw] = sum_k dy[n,k,p,q] * w[k,c]; all other positions of dx are zero.  Small 16-bit
+		// filters and the deconvolution-forward bias take the general gather path at the end of this function instead.
 		st = pz_memset8(dx, 0, (size_t)g.N * g.C * HW * es, stream);
 		if (st != PZ_OK) return st;
 		char* wt = (char*)pz_scratch((size_t)g.C * dgrad_kpad(g.Kg, 1, true, bke) * es);
 		if (!wt) { pz_set_error(PZ_ERR_MEMORY, "conv2d dgrad: cannot allocate filter scratch"); return PZ_ERR_MEMORY; }
 		PZ_REQUIRE(tap_entries_fit(34ll * PQ, g), "conv2d dgrad: tensor too large");
-		PZ_REQUIRE(!h16 || use_chan_order(g.Kg, bke), "conv2d dgrad: 16-bit strided filters need >= 48 output channels");
 		return run_class(wt, 0, 0, 0, 0, g.sh, g.sw, 1, 1, g.P, g.Q, 0);
 	}
 

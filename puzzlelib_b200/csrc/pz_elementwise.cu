@@ -131,6 +131,45 @@ int ew_launch(void* io0, void* io1, const void* in0, const void* in1, const void
 	return PZ_OK;
 }
 
+// `slice=` form of an elementwise launch (reference: Cuda/SourceModule.py:162-200, the `<name>_strided` twin every
+// ElementwiseKernel is compiled with): element i = start + k * step < stop of every pointer argument
+template <typename T, int NIO, int NIN, bool READ_IO, typename Op>
+__global__ void __launch_bounds__(kThreads) ew_strided_kernel(T* io0, T* io1, const T* in0, const T* in1, const T* in2,
+															  int64_t start, int64_t step, int64_t count, Op op)
+{
+	T* ios[2] = {io0, io1};
+	const T* ins[3] = {in0, in1, in2};
+	for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < count; k += (int64_t)gridDim.x * blockDim.x) {
+		const int64_t i = start + k * step;
+		float fin[NIN > 0 ? NIN : 1], fio[NIO];
+		#pragma unroll
+		for (int j = 0; j < NIN; j++) fin[j] = to_f<T>(ins[j][i]);
+		#pragma unroll
+		for (int j = 0; j < NIO; j++) fio[j] = READ_IO ? to_f<T>(ios[j][i]) : 0.0f;
+		op.apply(fio, fin);
+		#pragma unroll
+		for (int j = 0; j < NIO; j++) ios[j][i] = from_f<T>(fio[j]);
+	}
+}
+
+template <typename T, int NIO, int NIN, bool READ_IO, typename Op>
+int ew_launch_slice(void* io0, void* io1, const void* in0, const void* in1, const void* in2, int64_t n, int64_t start, int64_t stop,
+					int64_t step, Op op, void* stream)
+{
+	PZ_REQUIRE(step >= 1 && start >= 0, "bad slice (start %lld, step %lld)", (long long)start, (long long)step);
+	if (stop > n) stop = n;
+	if (stop <= start) return PZ_OK;
+	const int64_t count = (stop - start + step - 1) / step;
+	int64_t blocks = pz_cdiv(count, kThreads);
+	const int64_t maxblocks = (int64_t)pz_num_sms() * 8;
+	if (blocks > maxblocks) blocks = maxblocks;
+	ew_strided_kernel<T, NIO, NIN, READ_IO, Op><<<(unsigned)blocks, kThreads, 0, pz_stream(stream)>>>(
+		(T*)io0, (T*)io1, (const T*)in0, (const T*)in1, (const T*)in2, start, step, count, op);
+	pz_count_launch(1);
+	PZ_LAUNCH_CHECK();
+	return PZ_OK;
+}
+
 #define PZ_DISPATCH_FLOAT(dtype, ...)                                                    \
 	switch (dtype) {                                                                     \
 		case PZ_F32: { using T = float; return __VA_ARGS__; }                            \
@@ -319,6 +358,31 @@ int pz_act_bwd(int kind, int dtype, void* ingrad, const void* outgrad, const voi
 		PZ_DISPATCH_FLOAT(dtype, ew_launch<T, 1, 2, false>(ingrad, nullptr, outgrad, ref, nullptr, n, ReluBwd{}, stream));
 	}
 	PZ_DISPATCH_FLOAT(dtype, ew_launch<T, 1, 2, false>(ingrad, nullptr, outgrad, ref, nullptr, n, ActBwd{kind, a, b}, stream));
+}
+
+int pz_act_fwd_slice(int kind, int dtype, void* out, const void* in, int64_t n, float a, float b, int64_t start, int64_t stop,
+					 int64_t step, void* stream)
+{
+	PZ_REQUIRE(kind >= PZ_ACT_SIGMOID && kind <= PZ_ACT_GELU, "unknown activation kind %d", kind);
+	PZ_DISPATCH_FLOAT(dtype, ew_launch_slice<T, 1, 1, false>(out, nullptr, in, nullptr, nullptr, n, start, stop, step, ActFwd{kind, a, b}, stream));
+}
+
+int pz_act_bwd_slice(int kind, int dtype, void* ingrad, const void* outgrad, const void* ref, int64_t n, float a, float b,
+					 int64_t start, int64_t stop, int64_t step, void* stream)
+{
+	PZ_REQUIRE(kind >= PZ_ACT_SIGMOID && kind <= PZ_ACT_GELU, "unknown activation kind %d", kind);
+	PZ_DISPATCH_FLOAT(dtype, ew_launch_slice<T, 1, 2, false>(ingrad, nullptr, outgrad, ref, nullptr, n, start, stop, step, ActBwd{kind, a, b}, stream));
+}
+
+int pz_axpby_slice(int dtype, void* out, const void* x, float alpha, const void* y, float beta, int64_t n, int64_t start, int64_t stop,
+				   int64_t step, void* stream)
+{
+	PZ_DISPATCH_FLOAT(dtype, ew_launch_slice<T, 1, 2, false>(out, nullptr, x, y, nullptr, n, start, stop, step, Axpby{alpha, beta}, stream));
+}
+
+int pz_mul_slice(int dtype, void* out, const void* a, const void* b, int64_t n, int64_t start, int64_t stop, int64_t step, void* stream)
+{
+	PZ_DISPATCH_FLOAT(dtype, ew_launch_slice<T, 1, 2, false>(out, nullptr, a, b, nullptr, n, start, stop, step, Mul{}, stream));
 }
 
 int pz_axpy(int dtype, void* y, const void* x, float alpha, int64_t n, void* stream)

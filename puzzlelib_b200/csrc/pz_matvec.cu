@@ -97,8 +97,10 @@ __global__ void __launch_bounds__(256) argrow_kernel(int32_t* __restrict__ idx, 
 	for (int o = 16; o > 0; o >>= 1) {
 		float ob = __shfl_xor_sync(0xffffffffu, best, o);
 		int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-		bool take = MAX ? (ob > best) : (ob < best);
-		if (take || (ob == best && oi < bi)) { best = ob; bi = oi; }
+		// strict comparison in the xor butterfly, lane 0 reports: on TIES this is exactly the element the reference kernel
+		// returns (Cuda/Kernels/MatVec.py:10-35 -- every lane stores its own survivor to the same address and lane 0's store
+		// is the one that lands; pinned by tests/golden/ref_cuda_ops.npz matvec_f32/argmaxties), not the first occurrence
+		if (MAX ? (ob > best) : (ob < best)) { best = ob; bi = oi; }
 	}
 	if (lane == 0) idx[row] = bi == 0x7fffffff ? -1 : bi;
 }

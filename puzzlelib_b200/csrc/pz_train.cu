@@ -56,6 +56,34 @@ __global__ void __launch_bounds__(kThreads) cross_entropy_kernel(const float* __
 	if (threadIdx.x == 0 && s != 0.0f) atomicAdd(error, s);
 }
 
+// reference: Cuda/Kernels/Costs.py:109-130 (svmL1Logic / svmL2Logic in the same cost template): cls = +1 for the labelled
+// class, -1 otherwise; l1: hinge, l2: squared hinge.  error is summed over every (sample, class, position).
+__global__ void __launch_bounds__(kThreads) svm_kernel(const float* __restrict__ scores, const int* __restrict__ labels, long long size,
+													  int mapStride, int spatialDim, int numCases, int numSamples, int l2,
+													  float* __restrict__ error, float* __restrict__ grad)
+{
+	__shared__ float red[kThreads / 32];
+	float err = 0.0f;
+	for (long long index = (long long)blockIdx.x * kThreads + threadIdx.x; index < size; index += (long long)gridDim.x * kThreads) {
+		const int b = (int)(index / mapStride);
+		const int m = (int)(index % spatialDim);
+		const int c = (int)((index / spatialDim) % numCases);
+		const float score = scores[index];
+		const int label = labels[(long long)b * spatialDim + m];
+		const float cls = label == c ? 1.0f : -1.0f;
+		if (l2) {
+			const float e = fmaxf(0.0f, 1.0f - score * cls);
+			grad[index] = 2.0f * cls * e / numCases / numSamples;
+			err += e * e / numCases / spatialDim;
+		} else {
+			grad[index] = score * cls < 1.0f ? cls / numCases / numSamples : 0.0f;
+			err += fmaxf(0.0f, 1.0f - score * cls) / numCases / spatialDim;
+		}
+	}
+	const float s = block_sum(err, red);
+	if (threadIdx.x == 0 && s != 0.0f) atomicAdd(error, s);
+}
+
 // reference: Cuda/Kernels/Costs.py:178-182 (calcAccuracy reduction: sum of x[i] != y[i] as float)
 __global__ void __launch_bounds__(kThreads) mismatch_kernel(const int* __restrict__ x, const int* __restrict__ y, long long n,
 														   float* __restrict__ out)
@@ -119,6 +147,20 @@ int pz_cross_entropy(const void* probs, const void* labels, const void* weights,
 	cross_entropy_kernel<<<grid_for(size), kThreads, 0, pz_stream(stream)>>>(
 		(const float*)probs, (const int*)labels, (const float*)weights, size, (int)(cases * spatial), (int)spatial, (int)cases,
 		1.0f / (float)samples, 1.0f / (float)spatial, (float*)error, (float*)grad);
+	pz_count_launch(1);
+	PZ_LAUNCH_CHECK();
+	return PZ_OK;
+}
+
+int pz_svm(int l2, const void* scores, const void* labels, int64_t samples, int64_t cases, int64_t spatial, void* error, void* grad,
+		   void* stream)
+{
+	PZ_REQUIRE(samples >= 0 && cases > 0 && spatial > 0, "svm: bad shape");
+	const long long size = (long long)samples * cases * spatial;
+	if (size == 0) return PZ_OK;
+	PZ_REQUIRE(cases * spatial < (1ll << 31) && samples * spatial < (1ll << 31), "svm: tensor too large");
+	svm_kernel<<<grid_for(size), kThreads, 0, pz_stream(stream)>>>((const float*)scores, (const int*)labels, size, (int)(cases * spatial),
+																  (int)spatial, (int)cases, (int)samples, l2 ? 1 : 0, (float*)error, (float*)grad);
 	pz_count_launch(1);
 	PZ_LAUNCH_CHECK();
 	return PZ_OK;
@@ -308,9 +350,10 @@ __global__ void __launch_bounds__(kThreads) rng_fill_kernel(void* __restrict__ o
 // out = x * (b < v) / p with one random word per element (mapsize = 1) or per map of `mapsize` elements (dropout2d)
 template <typename T, typename B>
 __global__ void __launch_bounds__(kThreads) dropout_kernel(T* __restrict__ out, const T* __restrict__ in, const B* __restrict__ b,
-														  unsigned v, float p, long long n, int mapsize)
+														  unsigned v, float p, long long count, int mapsize, long long start, long long step)
 {
-	for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kThreads) {
+	for (long long k = (long long)blockIdx.x * kThreads + threadIdx.x; k < count; k += (long long)gridDim.x * kThreads) {
+		const long long i = start + k * step;
 		const B word = b[mapsize == 1 ? i : i / mapsize];
 		out[i] = from_f<T>(to_f(in[i]) * ((unsigned)word < v ? 1.0f : 0.0f) / p);
 	}
@@ -328,31 +371,40 @@ extern "C" int pz_rng_fill(int kind, void* out, int64_t n, uint64_t seed, uint64
 	return PZ_OK;
 }
 
-extern "C" int pz_dropout(int dtype, void* out, const void* in, const void* rands, uint32_t partition, float p, int64_t n,
-						  int64_t mapsize, void* stream)
+extern "C" int pz_dropout_slice(int dtype, void* out, const void* in, const void* rands, uint32_t partition, float p, int64_t n,
+								int64_t mapsize, int64_t start, int64_t stop, int64_t step, void* stream)
 {
 	PZ_REQUIRE(p > 0.0f && mapsize >= 1 && mapsize < (1ll << 31), "dropout: bad arguments");
-	if (n <= 0) return PZ_OK;
-	PzProfScope prof(PZ_PROF_ELTWISE, pz_stream(stream), 0.0, 3.0 * (double)n * pz_dtype_size(dtype));
-	const unsigned grid = grid_for(n);
+	PZ_REQUIRE(step >= 1 && start >= 0, "dropout: bad slice");
+	if (stop > n) stop = n;
+	if (stop <= start) return PZ_OK;
+	const long long count = (stop - start + step - 1) / step;
+	PzProfScope prof(PZ_PROF_ELTWISE, pz_stream(stream), 0.0, 3.0 * (double)count * pz_dtype_size(dtype));
+	const unsigned grid = grid_for(count);
 	switch (dtype) {
 		case PZ_F32:
 			dropout_kernel<float, uint32_t><<<grid, kThreads, 0, pz_stream(stream)>>>((float*)out, (const float*)in, (const uint32_t*)rands,
-																					  partition, p, (long long)n, (int)mapsize);
+																					  partition, p, count, (int)mapsize, start, step);
 			break;
 		case PZ_F16:
 			dropout_kernel<__half, uint16_t><<<grid, kThreads, 0, pz_stream(stream)>>>((__half*)out, (const __half*)in, (const uint16_t*)rands,
-																					   partition, p, (long long)n, (int)mapsize);
+																					   partition, p, count, (int)mapsize, start, step);
 			break;
 		case PZ_BF16:
 			dropout_kernel<__nv_bfloat16, uint16_t><<<grid, kThreads, 0, pz_stream(stream)>>>(
-				(__nv_bfloat16*)out, (const __nv_bfloat16*)in, (const uint16_t*)rands, partition, p, (long long)n, (int)mapsize);
+				(__nv_bfloat16*)out, (const __nv_bfloat16*)in, (const uint16_t*)rands, partition, p, count, (int)mapsize, start, step);
 			break;
 		default: pz_set_error(PZ_ERR_UNSUPPORTED, "unsupported dtype %d", dtype); return PZ_ERR_UNSUPPORTED;
 	}
 	pz_count_launch(1);
 	PZ_LAUNCH_CHECK();
 	return PZ_OK;
+}
+
+extern "C" int pz_dropout(int dtype, void* out, const void* in, const void* rands, uint32_t partition, float p, int64_t n,
+						  int64_t mapsize, void* stream)
+{
+	return pz_dropout_slice(dtype, out, in, rands, partition, p, n, mapsize, 0, n, 1, stream);
 }
 
 // ------------------------------------------------------------------------------------------ local response normalisation

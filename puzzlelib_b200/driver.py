@@ -116,11 +116,20 @@ _SIGNATURES = {
 	"pz_mul": [c_int, _P, _P, _P, c_int64, _P],
 	"pz_add2": [c_int, _P, _P, _P, c_int64, _P],
 	"pz_cast": [c_int, _P, c_int, _P, c_int64, _P],
+	"pz_act_fwd_slice": [c_int, c_int, _P, _P, c_int64, c_float, c_float, c_int64, c_int64, c_int64, _P],
+	"pz_act_bwd_slice": [c_int, c_int, _P, _P, _P, c_int64, c_float, c_float, c_int64, c_int64, c_int64, _P],
+	"pz_axpby_slice": [c_int, _P, _P, c_float, _P, c_float, c_int64, c_int64, c_int64, c_int64, _P],
+	"pz_mul_slice": [c_int, _P, _P, _P, c_int64, c_int64, c_int64, c_int64, _P],
+	"pz_eltwise": [c_int, c_int, POINTER(_P), c_int, POINTER(c_float), c_int, POINTER(c_int), c_int64, c_int64, c_int64, c_int64, _P],
+	"pz_dropout_slice": [c_int, _P, _P, _P, c_uint32, c_float, c_int64, c_int64, c_int64, c_int64, c_int64, _P],
 	"pz_sgd_momentum": [c_int, _P, _P, _P, c_float, c_float, c_int64, _P],
 	"pz_sgd_nesterov": [c_int, _P, _P, _P, c_float, c_float, c_int64, _P],
 	"pz_adam": [c_int, _P, _P, _P, _P, c_float, c_float, c_float, c_float, c_int64, _P],
 	"pz_cross_entropy": [_P, _P, _P, c_int64, c_int64, c_int64, _P, _P, _P],
 	"pz_count_mismatch": [_P, _P, c_int64, _P, _P],
+	"pz_svm": [c_int, _P, _P, c_int64, c_int64, c_int64, _P, _P, _P],
+	"pz_cost_reduce": [c_int, _P, _P, _P, c_float, c_int64, _P, _P],
+	"pz_reduce_minmax_i32": [_P, c_int64, c_int, _P, _P],
 	"pz_permute": [c_int, _P, _P, c_int, _P, _P, _P],
 	"pz_matvec": [c_int, _P, _P, _P, c_int64, c_int64, c_int64, c_int, c_float, c_float, _P],
 	"pz_vec_reduce": [c_int, c_int, _P, _P, c_int64, _P, _P],

@@ -416,7 +416,10 @@ class GPUArray:
 	def _reduce(self, wantMax):
 		self.enforceContiguous()
 		out = GPUArray((), self.dtype, allocator=self._findAllocator())
-		check(lib.pz_reduce_minmax(dtypeCode(self.dtype), self.ptr, self.size, 1 if wantMax else 0, out.ptr, None))
+		if self.dtype == np.int32:
+			check(lib.pz_reduce_minmax_i32(self.ptr, self.size, 1 if wantMax else 0, out.ptr, None))
+		else:
+			check(lib.pz_reduce_minmax(dtypeCode(self.dtype), self.ptr, self.size, 1 if wantMax else 0, out.ptr, None))
 		return out
 
 	def min(self):

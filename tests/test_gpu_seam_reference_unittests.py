@@ -1,0 +1,117 @@
+"""GPU tier: the reference's OWN unit tests, unmodified, running on this backend through the Cuda/Backend.py seam.
+
+Every `unittest()` of the reference's Modules / Containers / Cost / Optimizers (they build inputs with numpy, run the module on
+the GPU and compare with a host recomputation) and the backend-object tests of Cuda/Wrappers/*.py, Cuda/GPUArray.py,
+Cuda/Utils.py are imported from baseline/_ref and called as they are.  Inputs are unseeded and compared with np.allclose, so
+-- like the reference's Unittester.py:13-48 -- a failed assertion is retried a few times.
+
+TENSOR_CORE lists the tests whose host check compares a float32 contraction at np.allclose's default 1e-5 / 1e-8: they need
+full-fp32 products (cuDNN gives the reference that on this stack), which this backend provides in its exact mode
+(`dnn.enableTensorOps(False)`: 3 x TF32 split products); in the default TF32 mode they are held to the 1e-3 bar elsewhere.
+"""
+import importlib
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+MODULES = [
+	"Modules/Activation", "Modules/Add", "Modules/AvgPool1D", "Modules/AvgPool2D", "Modules/AvgPool3D", "Modules/BatchNorm",
+	"Modules/BatchNorm1D", "Modules/BatchNorm2D", "Modules/BatchNorm3D", "Modules/Cast", "Modules/Concat", "Modules/CrossMapLRN",
+	"Modules/DepthConcat", "Modules/Dropout", "Modules/Dropout2D", "Modules/Flatten", "Modules/Gelu", "Modules/Glue",
+	"Modules/GroupLinear", "Modules/Identity", "Modules/InstanceNorm2D", "Modules/KMaxPool", "Modules/Linear", "Modules/MapLRN",
+	"Modules/MaxPool1D", "Modules/MaxPool2D", "Modules/MaxPool3D", "Modules/MaxUnpool2D", "Modules/MoveAxis", "Modules/Mul",
+	"Modules/MulAddConst", "Modules/NoiseInjector", "Modules/Penalty", "Modules/Replicate", "Modules/Reshape", "Modules/Slice",
+	"Modules/SoftMax", "Modules/Split", "Modules/SubtractMean", "Modules/Sum", "Modules/SwapAxes", "Modules/Tile", "Modules/ToList",
+	"Modules/Transpose",
+	"Containers/Sequential", "Containers/Parallel", "Containers/Graph",
+	"Cost/Abs", "Cost/BCE", "Cost/CrossEntropy", "Cost/Hinge", "Cost/KLDivergence", "Cost/L1Hinge", "Cost/MSE", "Cost/Multi",
+	"Cost/SVM", "Cost/SmoothL1",
+	"Optimizers/AdaDelta", "Optimizers/AdaGrad", "Optimizers/Adam", "Optimizers/MomentumSGD", "Optimizers/NesterovSGD",
+	"Optimizers/RMSProp", "Optimizers/RMSPropGraves", "Optimizers/SGD", "Optimizers/SMORMS3",
+	"Models/Nets/LeNet", "Models/Nets/ResNet", "Models/Nets/VGG", "Models/Nets/NiN", "Models/Nets/Inception",
+]
+
+TENSOR_CORE = [
+	"Modules/Conv1D", "Modules/Conv2D", "Modules/Conv3D", "Modules/Deconv1D", "Modules/Deconv2D", "Modules/Deconv3D", "Modules/RNN",
+]
+
+WRAPPERS = ["CuDnn", "CuDnnNorm", "CuBlas", "CuDnnMemory"]
+
+
+def retry(fn, tries=4):
+	for attempt in range(tries):
+		try:
+			return fn()
+		except AssertionError:
+			if attempt == tries - 1:
+				raise
+
+
+@pytest.fixture(scope="module")
+def refroot(bnd):
+	import refshim
+	refshim.modules()
+	import PuzzleLib
+	return os.path.dirname(PuzzleLib.__file__)
+
+
+def runUnittest(refroot, name):
+	mod = importlib.import_module("PuzzleLib." + name.replace("/", "."))
+	cwd = os.getcwd()
+	os.chdir(os.path.dirname(os.path.join(refroot, name)))         # some tests open ../TestData relative to their file
+	try:
+		retry(mod.unittest)
+	finally:
+		os.chdir(cwd)
+
+
+@pytest.mark.parametrize("name", MODULES)
+def test_reference_unittest(refroot, name):
+	runUnittest(refroot, name)
+
+
+@pytest.mark.parametrize("name", TENSOR_CORE)
+def test_reference_unittest_with_exact_fp32_products(refroot, bnd, name):
+	bnd.dnn.enableTensorOps(False)
+	bnd.blas.enableTensorOps(False)
+	try:
+		runUnittest(refroot, name)
+	finally:
+		bnd.dnn.enableTensorOps(True)
+		bnd.blas.enableTensorOps(True)
+
+
+@pytest.mark.parametrize("name", WRAPPERS)
+def test_reference_backend_object_tests(refroot, bnd, name):
+	"""Cuda/Wrappers/*.py: `backendTest(Backend)` takes the seam module itself (getBackend / getDeviceCount)"""
+	from PuzzleLib.Cuda import Backend
+	mod = importlib.import_module("PuzzleLib.Cuda.Wrappers." + name)
+	exact = name in ("CuDnn", "CuBlas")          # conv / gemm host checks at atol 1e-5
+	if exact:
+		bnd.dnn.enableTensorOps(False)
+		bnd.blas.enableTensorOps(False)
+	try:
+		retry(lambda: mod.backendTest(Backend))
+	finally:
+		bnd.dnn.enableTensorOps(True)
+		bnd.blas.enableTensorOps(True)
+
+
+def test_reference_gpuarray_utils_and_kernel_module_tests(refroot, bnd):
+	from PuzzleLib.Cuda import Backend, GPUArray as GPUArrayTests, Utils
+	from PuzzleLib.Cuda.Kernels import MatVec, Pool, Costs
+
+	retry(lambda: GPUArrayTests.backendTest(Backend))
+	retry(lambda: Utils.backendTest(Backend))
+
+	# the kernel-module tests take a module object: hand them this backend's modules (matmod / poolmod / costmod)
+	for dtype, atol in bnd.dtypesSupported():
+		retry(lambda: MatVec.calcTest(bnd.matmod, dtype, atol))
+		retry(lambda: MatVec.batchCalcTest(bnd.matmod, dtype, atol))
+	Pool.poolTest(bnd.poolmod)
+	Pool.unpoolTest(bnd.poolmod)
+	retry(lambda: Costs.crossEntropyTest(bnd.costmod))
+	retry(lambda: Costs.svmTest(bnd.costmod))

@@ -6,8 +6,15 @@ import sys
 import numpy as np
 sys.path.insert(0, ".")
 from puzzlelib_b200 import driver
-from puzzlelib_b200 import modules as M
-from puzzlelib_b200.shim import backend
+from puzzlelib_b200 import seam
+
+seam.install()                      # the reference's Modules/RNN.py over this backend
+import PuzzleLib.Modules as M                      # noqa: E402
+from PuzzleLib.Backend import gpuarray             # noqa: E402
+
+
+def backend():
+	return gpuarray.backend
 
 
 def main():
@@ -15,8 +22,8 @@ def main():
 	backend()
 	np.random.seed(1)
 	rnn = M.RNN(H, H, layers=1, mode="lstm", getSequences=True, initscheme="xavier")
-	x = M.gpuarray.to_gpu(np.random.randn(T, B, H).astype(np.float32))
-	g = M.gpuarray.to_gpu(np.random.randn(T, B, H).astype(np.float32))
+	x = gpuarray.to_gpu(np.random.randn(T, B, H).astype(np.float32))
+	g = gpuarray.to_gpu(np.random.randn(T, B, H).astype(np.float32))
 
 	def step():
 		rnn.zeroGradParams()

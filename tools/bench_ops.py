@@ -3,7 +3,11 @@ Prints ms and GB/s over the algorithmic bytes.  usage: python tools/
 import sys
 import numpy as np
 sys.path.insert(0, ".")
-from puzzlelib_b200.shim import backend
+from puzzlelib_b200.backend import getBackend
+
+
+def backend():
+	return getBackend(0, 2)
 from puzzlelib_b200 import driver
 
 # (C, H) of the batch-norm inputs of ResNet-50 with their multiplicity
