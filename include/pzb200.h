@@ -124,6 +124,9 @@ int pz_axpby(int dtype, void* out, const void* x, float alpha, const void* y, fl
 int pz_scale_shift(int dtype, void* out, const void* in, float a, float b, int64_t n, void* stream); /* linearKer :1073-1099 */
 int pz_mul(int dtype, void* out, const void* a, const void* b, int64_t n, void* stream);    /* mulKer :1047-1071 */
 int pz_add2(int dtype, void* out, const void* a, const void* b, int64_t n, void* stream);   /* Add.py:15-23 as one pass */
+/* x = hi + lo with hi = x rounded to tf32 and lo = x - hi: the operand split behind the exact-fp32 mode of the contractions
+ * (`dnn.enableTensorOps(False)`: hi*hi + hi*lo + lo*hi on the tensor cores, fp32 accumulation -- "3xTF32") */
+int pz_tf32_split(const void* x, void* hi, void* lo, int64_t n, void* stream);
 /* `slice=` launches (Cuda/SourceModule.py:162-200, the `<name>_strided` twin of every ElementwiseKernel; callers:
  * Modules/Activation.py:71-76, NoiseInjector.py:73-93, Dropout.py:58-74): elements start, start + step, ... < min(stop, n) */
 int pz_act_fwd_slice(int kind, int dtype, void* out, const void* in, int64_t n, float a, float b, int64_t start, int64_t stop,

@@ -76,8 +76,32 @@ class DnnContext:
 		return int(lib.pz_version())
 
 	def enableTensorOps(self, enable):
-		# the tcgen05 path is the only one; fp32 storage always computes as TF32 like cuDNN's TENSOR_OP_MATH
+		"""reference: CuDnn_Context_enableTensorOps (CuDnn.c:61-74; the reference switches it on, Cuda/GPUBackend.py:152).
+		True (default): float32 tensors are contracted as TF32 products with fp32 accumulation -- within 1e-3 of full fp32.
+		False: exact mode -- every float32 contraction runs as three tensor-core passes over the tf32 split of its operands
+		(hi*hi + hi*lo + lo*hi, "3xTF32"): full-fp32 accuracy, what cuDNN gives the reference on this stack, at 3x the cost."""
 		self.tensorOps = bool(enable)
+		return self
+
+	def _exact(self, ary):
+		return not self.tensorOps and ary.dtype == _f32
+
+	@staticmethod
+	def _split(ary, allocator):
+		hi, lo = GPUArray(ary.shape, _f32, allocator=allocator), GPUArray(ary.shape, _f32, allocator=allocator)
+		check(lib.pz_tf32_split(ary.ptr, hi.ptr, lo.ptr, ary.size, None))
+		return hi, lo
+
+	def _exact3(self, fn, A, B, out, allocator):
+		"""out = fn(A, B) in exact mode.  `fn(a, b, first, out)` runs the TF32 contraction; it gets first=True for the call that
+		also carries bias / beta and must write into `out` (or allocate it), first=False for pure products."""
+		Ah, Al = self._split(A, allocator)
+		Bh, Bl = self._split(B, allocator)
+		out = fn(Ah, Bh, True, out)
+		for a, b in ((Ah, Bl), (Al, Bh)):
+			part = fn(a, b, False, None)
+			check(lib.pz_axpy(driver.PZ_F32, out.ptr, part.ptr, 1.0, out.size, None))
+		return out
 
 	# ------------------------------------------------------------------------------------------ convolution
 	@staticmethod
@@ -107,6 +131,12 @@ class DnnContext:
 
 	def convNd(self, data, W, bias=None, stride=1, pad=0, dilation=1, groups=1, algo=0, out=None, allocator=None):
 		"""reference: CuDnn_Context_pyConvNd, CuDnn.c:457-514 (out shape :242-266)"""
+		if isinstance(data, GPUArray) and isinstance(W, GPUArray) and self._exact(data) and self._exact(W):
+			return self._exact3(lambda a, b, first, o: self._convNd(a, b, bias if first else None, stride, pad, dilation, groups, algo, o,
+																	  allocator), data, W, out, allocator)
+		return self._convNd(data, W, bias, stride, pad, dilation, groups, algo, out, allocator)
+
+	def _convNd(self, data, W, bias=None, stride=1, pad=0, dilation=1, groups=1, algo=0, out=None, allocator=None):
 		if self._is3d(data, W):
 			from . import dnn3d
 			if data.dtype != W.dtype:
@@ -147,6 +177,13 @@ class DnnContext:
 	def convNdBackwardData(self, grad, W, bias=None, data=None, stride=1, pad=0, dilation=1, postpad=0, groups=1,
 						   algo=0, out=None, allocator=None):
 		"""reference: CuDnn_Context_pyConvNdBackwardData, CuDnn.c:579-649 (in shape :269-322)"""
+		if isinstance(grad, GPUArray) and isinstance(W, GPUArray) and self._exact(grad) and self._exact(W):
+			return self._exact3(lambda a, b, first, o: self._convNdBackwardData(a, b, bias if first else None, data, stride, pad, dilation,
+																				  postpad, groups, algo, o, allocator), grad, W, out, allocator)
+		return self._convNdBackwardData(grad, W, bias, data, stride, pad, dilation, postpad, groups, algo, out, allocator)
+
+	def _convNdBackwardData(self, grad, W, bias=None, data=None, stride=1, pad=0, dilation=1, postpad=0, groups=1,
+							algo=0, out=None, allocator=None):
 		if self._is3d(grad, W):
 			from . import dnn3d
 			if grad.dtype != W.dtype or grad.shape[1] != W.shape[0]:
@@ -195,6 +232,27 @@ class DnnContext:
 							 wgrad=None, bgrad=None, scale=1.0, momentum=0.0, algo=0, allocator=None):
 		"""reference: CuDnn_Context_pyConvNdBackwardParams, CuDnn.c:722-800; wgrad / bgrad accumulate IN PLACE with
 		alpha = scale, beta = momentum (:682-685, :388)"""
+		if isinstance(data, GPUArray) and isinstance(grad, GPUArray) and self._exact(data) and self._exact(grad):
+			# exact mode: three tensor-core passes over the tf32 split of both operands; the bias gradient is a plain fp32 sum, taken
+			# over the hi part by the first pass and completed with the lo part of the bias-side tensor
+			(dh, dl), (gh, gl) = self._split(data, allocator), self._split(grad, allocator)
+			res = self._convNdBackwardParams(dh, gh, W, stride, pad, dilation, groups, withbias, deconv, wgrad, bgrad, scale, momentum,
+											 algo, allocator)
+			if withbias:
+				wgrad, bgrad = res
+				side = dl if deconv else gl
+				check(lib.pz_bias_grad(dtypeCode(side.dtype), side.ptr, bgrad.ptr, side.shape[0], side.shape[1], prod(side.shape[2:]),
+									   scale, 1.0, None))
+			else:
+				wgrad = res
+			for a, b in ((dh, gl), (dl, gh)):
+				self._convNdBackwardParams(a, b, W, stride, pad, dilation, groups, False, deconv, wgrad, None, scale, 1.0, algo, allocator)
+			return (wgrad, bgrad) if withbias else wgrad
+		return self._convNdBackwardParams(data, grad, W, stride, pad, dilation, groups, withbias, deconv, wgrad, bgrad, scale, momentum,
+										  algo, allocator)
+
+	def _convNdBackwardParams(self, data, grad, W, stride=1, pad=0, dilation=1, groups=1, withbias=False, deconv=False,
+							  wgrad=None, bgrad=None, scale=1.0, momentum=0.0, algo=0, allocator=None):
 		if self._is3d(data, grad, W):
 			from . import dnn3d
 			if data.dtype != grad.dtype or data.dtype != W.dtype:
@@ -496,13 +554,26 @@ class DnnContext:
 class BlasContext:
 	def __init__(self, backend):
 		self.backend = backend
+		self.tensorOps = True
 
 	def enableTensorOps(self, enable):
-		pass
+		"""reference: CuBlas_Context_enableTensorOps (CuBlas.c:91-106).  False selects the exact 3xTF32 mode, see
+		DnnContext.enableTensorOps"""
+		self.tensorOps = bool(enable)
+		return self
 
 	def gemm(self, A, B, out=None, transpA=False, transpB=False, alpha=1.0, beta=0.0, allocator=None):
 		"""Row-major out = alpha * op(A) op(B) + beta * out; at most one operand transposed (reference:
 		CuBlas_Context_gemm, CuBlas.c:327-403, shape rules :168-203)"""
+		if not self.tensorOps and isinstance(A, GPUArray) and isinstance(B, GPUArray) and A.dtype == _f32 and B.dtype == _f32:
+			Ah, Al = DnnContext._split(A, allocator)
+			Bh, Bl = DnnContext._split(B, allocator)
+			out = self._gemm(Ah, Bh, out, transpA, transpB, alpha, beta, allocator)
+			self._gemm(Ah, Bl, out, transpA, transpB, alpha, 1.0, allocator)
+			return self._gemm(Al, Bh, out, transpA, transpB, alpha, 1.0, allocator)
+		return self._gemm(A, B, out, transpA, transpB, alpha, beta, allocator)
+
+	def _gemm(self, A, B, out=None, transpA=False, transpB=False, alpha=1.0, beta=0.0, allocator=None):
 		_requireArray(A, "A")
 		_requireArray(B, "B")
 		if A.ndim != 2 or B.ndim != 2 or A.dtype != B.dtype:

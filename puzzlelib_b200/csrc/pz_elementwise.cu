@@ -233,6 +233,14 @@ struct ReluBwd {
 	__device__ __forceinline__ void apply(float* io, const float* in) const { io[0] = in[0] * (in[1] > 0.0f); }
 };
 
+struct Tf32Split {   // io[0] = x rounded to tf32 (nearest, ties away), io[1] = x - io[0] (exact in fp32)
+	__device__ __forceinline__ void apply(float* io, const float* in) const
+	{
+		const float hi = __uint_as_float((__float_as_uint(in[0]) + 0x1000u) & 0xffffe000u);
+		io[0] = hi;
+		io[1] = in[0] - hi;
+	}
+};
 struct Axpy {   // y = y + x * alpha   (ElementWise.py:591)
 	float alpha;
 	__device__ __forceinline__ void apply(float* io, const float* in) const { io[0] = io[0] + in[0] * alpha; }
@@ -383,6 +391,11 @@ int pz_axpby_slice(int dtype, void* out, const void* x, float alpha, const void*
 int pz_mul_slice(int dtype, void* out, const void* a, const void* b, int64_t n, int64_t start, int64_t stop, int64_t step, void* stream)
 {
 	PZ_DISPATCH_FLOAT(dtype, ew_launch_slice<T, 1, 2, false>(out, nullptr, a, b, nullptr, n, start, stop, step, Mul{}, stream));
+}
+
+int pz_tf32_split(const void* x, void* hi, void* lo, int64_t n, void* stream)
+{
+	return ew_launch<float, 2, 1, false>(hi, lo, x, nullptr, nullptr, n, Tf32Split{}, stream);
 }
 
 int pz_axpy(int dtype, void* y, const void* x, float alpha, int64_t n, void* stream)

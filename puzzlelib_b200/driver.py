@@ -116,6 +116,7 @@ _SIGNATURES = {
 	"pz_mul": [c_int, _P, _P, _P, c_int64, _P],
 	"pz_add2": [c_int, _P, _P, _P, c_int64, _P],
 	"pz_cast": [c_int, _P, c_int, _P, c_int64, _P],
+	"pz_tf32_split": [_P, _P, _P, c_int64, _P],
 	"pz_act_fwd_slice": [c_int, c_int, _P, _P, c_int64, c_float, c_float, c_int64, c_int64, c_int64, _P],
 	"pz_act_bwd_slice": [c_int, c_int, _P, _P, _P, c_int64, c_float, c_float, c_int64, c_int64, c_int64, _P],
 	"pz_axpby_slice": [c_int, _P, _P, c_float, _P, c_float, c_int64, c_int64, c_int64, c_int64, _P],

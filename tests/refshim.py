@@ -30,10 +30,11 @@ def modules():
 		from PuzzleLib.Backend import gpuarray
 		from PuzzleLib.Containers import Sequential, Parallel, Graph
 		from PuzzleLib.Modules.Module import Module, ModuleError
+		from PuzzleLib.Variable import Variable
 
 		_ns = types.SimpleNamespace(**{name: getattr(Mods, name) for name in dir(Mods) if not name.startswith("_")})
 		_ns.Sequential, _ns.Parallel, _ns.Graph = Sequential, Parallel, Graph
-		_ns.Module, _ns.ModuleError, _ns.gpuarray, _ns.Config = Module, ModuleError, gpuarray, Config
+		_ns.Module, _ns.ModuleError, _ns.gpuarray, _ns.Config, _ns.Variable = Module, ModuleError, gpuarray, Config, Variable
 	return _ns
 
 
