@@ -124,9 +124,14 @@ int pz_axpby(int dtype, void* out, const void* x, float alpha, const void* y, fl
 int pz_scale_shift(int dtype, void* out, const void* in, float a, float b, int64_t n, void* stream); /* linearKer :1073-1099 */
 int pz_mul(int dtype, void* out, const void* a, const void* b, int64_t n, void* stream);    /* mulKer :1047-1071 */
 int pz_add2(int dtype, void* out, const void* a, const void* b, int64_t n, void* stream);   /* Add.py:15-23 as one pass */
-/* x = hi + lo with hi = x rounded to tf32 and lo = x - hi: the operand split behind the exact-fp32 mode of the contractions
- * (`dnn.enableTensorOps(False)`: hi*hi + hi*lo + lo*hi on the tensor cores, fp32 accumulation -- "3xTF32") */
-int pz_tf32_split(const void* x, void* hi, void* lo, int64_t n, void* stream);
+/* y = (0 + x1*a1) + x2*a2 (x2 may be NULL: y = 0 + x1*a1): the launch sequence fill(0) + toVectorAddVector (+ toVectorAddVector)
+ * of Modules/Add.py:15-23 / Replicate.py:18-29 fused into one pass with identical bits (intermediate rounded to the storage type) */
+int pz_axpy2(int dtype, void* y, const void* x1, float a1, const void* x2, float a2, int64_t n, void* stream);
+/* float32 math mode of pz_conv2d_* and pz_gemm (reference: enableTensorOps, CuDnn.c:61-74 / CuBlas.c:91-106): 0 = TF32
+ * tensor-core products with fp32 accumulation (default; within 1e-3 of fp32), 1 = exact fp32 FMAs on the CUDA cores (what
+ * cuDNN / cuBLAS give the reference's float32 tensors on this stack; a verification path, not tuned) */
+int pz_set_exact_fp32(int on);
+int pz_exact_fp32(void);
 /* `slice=` launches (Cuda/SourceModule.py:162-200, the `<name>_strided` twin of every ElementwiseKernel; callers:
  * Modules/Activation.py:71-76, NoiseInjector.py:73-93, Dropout.py:58-74): elements start, start + step, ... < min(stop, n) */
 int pz_act_fwd_slice(int kind, int dtype, void* out, const void* in, int64_t n, float a, float b, int64_t start, int64_t stop,
@@ -291,6 +296,9 @@ int pz_lrn_fwd(int dtype, int mode, const void* x, void* y, int64_t N, int64_t C
 int pz_lrn_bwd(int dtype, int mode, const void* x, const void* grad, void* dx, void* tmp, int64_t N, int64_t C, int64_t H, int64_t W,
 			   int n, float alpha, float beta, float K, void* stream);
 int pz_rng_fill(int kind, void* out, int64_t n, uint64_t seed, uint64_t offset, float a, float b, void* stream);
+/* the same fill with the generator offset (uint64, units of 4 words) read from and advanced in DEVICE memory: a captured graph
+ * that replays the fill draws new numbers each time */
+int pz_rng_fill_dev(int kind, void* out, int64_t n, uint64_t seed, void* offset_dev, float a, float b, void* stream);
 int pz_dropout(int dtype, void* out, const void* in, const void* rands, uint32_t partition, float p, int64_t n, int64_t mapsize,
 			   void* stream);
 /* costmod.svm (Cuda/Kernels/Costs.py:109-130,249-279): l1 / squared hinge over (samples, cases, spatial...) scores */

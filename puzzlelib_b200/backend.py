@@ -21,7 +21,7 @@ import ctypes
 
 import numpy as np
 
-from . import driver
+from . import driver, gpuarray
 from .driver import lib, check, dtypeCode, Conv2dDesc, CuDnnError, CuBlasError
 from .gpuarray import GPUArray
 
@@ -77,31 +77,15 @@ class DnnContext:
 
 	def enableTensorOps(self, enable):
 		"""reference: CuDnn_Context_enableTensorOps (CuDnn.c:61-74; the reference switches it on, Cuda/GPUBackend.py:152).
-		True (default): float32 tensors are contracted as TF32 products with fp32 accumulation -- within 1e-3 of full fp32.
-		False: exact mode -- every float32 contraction runs as three tensor-core passes over the tf32 split of its operands
-		(hi*hi + hi*lo + lo*hi, "3xTF32"): full-fp32 accuracy, what cuDNN gives the reference on this stack, at 3x the cost."""
+		True (default): float32 tensors are contracted as TF32 tensor-core products with fp32 accumulation -- within 1e-3 of
+		full fp32.  False: exact mode -- float32 convolutions and GEMMs run as fp32 FMAs on the CUDA cores: the accuracy cuDNN /
+		cuBLAS give the reference on this stack (its own unit tests assume it), at a fraction of the speed.  Process-wide:
+		`dnn` and `blas` share the switch."""
 		self.tensorOps = bool(enable)
+		if self.backend.blas is not None:
+			self.backend.blas.tensorOps = self.tensorOps
+		check(lib.pz_set_exact_fp32(0 if enable else 1))
 		return self
-
-	def _exact(self, ary):
-		return not self.tensorOps and ary.dtype == _f32
-
-	@staticmethod
-	def _split(ary, allocator):
-		hi, lo = GPUArray(ary.shape, _f32, allocator=allocator), GPUArray(ary.shape, _f32, allocator=allocator)
-		check(lib.pz_tf32_split(ary.ptr, hi.ptr, lo.ptr, ary.size, None))
-		return hi, lo
-
-	def _exact3(self, fn, A, B, out, allocator):
-		"""out = fn(A, B) in exact mode.  `fn(a, b, first, out)` runs the TF32 contraction; it gets first=True for the call that
-		also carries bias / beta and must write into `out` (or allocate it), first=False for pure products."""
-		Ah, Al = self._split(A, allocator)
-		Bh, Bl = self._split(B, allocator)
-		out = fn(Ah, Bh, True, out)
-		for a, b in ((Ah, Bl), (Al, Bh)):
-			part = fn(a, b, False, None)
-			check(lib.pz_axpy(driver.PZ_F32, out.ptr, part.ptr, 1.0, out.size, None))
-		return out
 
 	# ------------------------------------------------------------------------------------------ convolution
 	@staticmethod
@@ -131,12 +115,6 @@ class DnnContext:
 
 	def convNd(self, data, W, bias=None, stride=1, pad=0, dilation=1, groups=1, algo=0, out=None, allocator=None):
 		"""reference: CuDnn_Context_pyConvNd, CuDnn.c:457-514 (out shape :242-266)"""
-		if isinstance(data, GPUArray) and isinstance(W, GPUArray) and self._exact(data) and self._exact(W):
-			return self._exact3(lambda a, b, first, o: self._convNd(a, b, bias if first else None, stride, pad, dilation, groups, algo, o,
-																	  allocator), data, W, out, allocator)
-		return self._convNd(data, W, bias, stride, pad, dilation, groups, algo, out, allocator)
-
-	def _convNd(self, data, W, bias=None, stride=1, pad=0, dilation=1, groups=1, algo=0, out=None, allocator=None):
 		if self._is3d(data, W):
 			from . import dnn3d
 			if data.dtype != W.dtype:
@@ -177,13 +155,6 @@ class DnnContext:
 	def convNdBackwardData(self, grad, W, bias=None, data=None, stride=1, pad=0, dilation=1, postpad=0, groups=1,
 						   algo=0, out=None, allocator=None):
 		"""reference: CuDnn_Context_pyConvNdBackwardData, CuDnn.c:579-649 (in shape :269-322)"""
-		if isinstance(grad, GPUArray) and isinstance(W, GPUArray) and self._exact(grad) and self._exact(W):
-			return self._exact3(lambda a, b, first, o: self._convNdBackwardData(a, b, bias if first else None, data, stride, pad, dilation,
-																				  postpad, groups, algo, o, allocator), grad, W, out, allocator)
-		return self._convNdBackwardData(grad, W, bias, data, stride, pad, dilation, postpad, groups, algo, out, allocator)
-
-	def _convNdBackwardData(self, grad, W, bias=None, data=None, stride=1, pad=0, dilation=1, postpad=0, groups=1,
-							algo=0, out=None, allocator=None):
 		if self._is3d(grad, W):
 			from . import dnn3d
 			if grad.dtype != W.dtype or grad.shape[1] != W.shape[0]:
@@ -232,27 +203,6 @@ class DnnContext:
 							 wgrad=None, bgrad=None, scale=1.0, momentum=0.0, algo=0, allocator=None):
 		"""reference: CuDnn_Context_pyConvNdBackwardParams, CuDnn.c:722-800; wgrad / bgrad accumulate IN PLACE with
 		alpha = scale, beta = momentum (:682-685, :388)"""
-		if isinstance(data, GPUArray) and isinstance(grad, GPUArray) and self._exact(data) and self._exact(grad):
-			# exact mode: three tensor-core passes over the tf32 split of both operands; the bias gradient is a plain fp32 sum, taken
-			# over the hi part by the first pass and completed with the lo part of the bias-side tensor
-			(dh, dl), (gh, gl) = self._split(data, allocator), self._split(grad, allocator)
-			res = self._convNdBackwardParams(dh, gh, W, stride, pad, dilation, groups, withbias, deconv, wgrad, bgrad, scale, momentum,
-											 algo, allocator)
-			if withbias:
-				wgrad, bgrad = res
-				side = dl if deconv else gl
-				check(lib.pz_bias_grad(dtypeCode(side.dtype), side.ptr, bgrad.ptr, side.shape[0], side.shape[1], prod(side.shape[2:]),
-									   scale, 1.0, None))
-			else:
-				wgrad = res
-			for a, b in ((dh, gl), (dl, gh)):
-				self._convNdBackwardParams(a, b, W, stride, pad, dilation, groups, False, deconv, wgrad, None, scale, 1.0, algo, allocator)
-			return (wgrad, bgrad) if withbias else wgrad
-		return self._convNdBackwardParams(data, grad, W, stride, pad, dilation, groups, withbias, deconv, wgrad, bgrad, scale, momentum,
-										  algo, allocator)
-
-	def _convNdBackwardParams(self, data, grad, W, stride=1, pad=0, dilation=1, groups=1, withbias=False, deconv=False,
-							  wgrad=None, bgrad=None, scale=1.0, momentum=0.0, algo=0, allocator=None):
 		if self._is3d(data, grad, W):
 			from . import dnn3d
 			if data.dtype != grad.dtype or data.dtype != W.dtype:
@@ -515,6 +465,7 @@ class DnnContext:
 			check(lib.pz_bn_fwd_infer(code, data.ptr, out.ptr, N, C, S, scale.ptr, bias.ptr, mean.ptr, var.ptr, epsilon, None))
 			return out
 
+		driver.traceScalar("the batch-norm running-average factor", factor)
 		savemean = GPUArray(scale.shape, _f32, allocator=allocator)
 		saveinvvar = GPUArray(scale.shape, _f32, allocator=allocator)
 		check(lib.pz_bn_fwd_train(code, data.ptr, out.ptr, N, C, S, scale.ptr, bias.ptr, mean.ptr, var.ptr, savemean.ptr,
@@ -557,23 +508,14 @@ class BlasContext:
 		self.tensorOps = True
 
 	def enableTensorOps(self, enable):
-		"""reference: CuBlas_Context_enableTensorOps (CuBlas.c:91-106).  False selects the exact 3xTF32 mode, see
-		DnnContext.enableTensorOps"""
-		self.tensorOps = bool(enable)
+		"""reference: CuBlas_Context_enableTensorOps (CuBlas.c:91-106).  False selects the exact fp32 mode, see
+		DnnContext.enableTensorOps (one process-wide switch)"""
+		self.backend.dnn.enableTensorOps(enable)
 		return self
 
 	def gemm(self, A, B, out=None, transpA=False, transpB=False, alpha=1.0, beta=0.0, allocator=None):
 		"""Row-major out = alpha * op(A) op(B) + beta * out; at most one operand transposed (reference:
 		CuBlas_Context_gemm, CuBlas.c:327-403, shape rules :168-203)"""
-		if not self.tensorOps and isinstance(A, GPUArray) and isinstance(B, GPUArray) and A.dtype == _f32 and B.dtype == _f32:
-			Ah, Al = DnnContext._split(A, allocator)
-			Bh, Bl = DnnContext._split(B, allocator)
-			out = self._gemm(Ah, Bh, out, transpA, transpB, alpha, beta, allocator)
-			self._gemm(Ah, Bl, out, transpA, transpB, alpha, 1.0, allocator)
-			return self._gemm(Al, Bh, out, transpA, transpB, alpha, 1.0, allocator)
-		return self._gemm(A, B, out, transpA, transpB, alpha, beta, allocator)
-
-	def _gemm(self, A, B, out=None, transpA=False, transpB=False, alpha=1.0, beta=0.0, allocator=None):
 		_requireArray(A, "A")
 		_requireArray(B, "B")
 		if A.ndim != 2 or B.ndim != 2 or A.dtype != B.dtype:
@@ -894,20 +836,33 @@ class CostModule:
 # ============================================================================================================ rng
 class RandomNumberGenerator:
 	"""reference: Cuda/Source/Libs/CuRand.c (the generator object behind `gpuarray.globalRng`): fillInteger / fillUniform /
-	fillNormal of a whole gpuarray.  Philox4x32-10 on the device; (seed, offset) is the whole state."""
+	fillNormal of a whole gpuarray.  Philox4x32-10 on the device; (seed, offset) is the whole state.  The offset lives in
+	DEVICE memory and is advanced by a kernel after every fill, so a captured graph (driver.StepGraph) that replays a fill
+	draws new numbers every time."""
 
 	def __init__(self, type=None, seed=0):
 		self.type = "philox4x32-10" if type is None else type
 		self.seed = int(seed) & 0xffffffffffffffff
-		self.offset = 0
+		self.state = None            # device uint64: the offset, in units of 4 random words
+
+	@property
+	def offset(self):
+		return 0 if self.state is None else int(self.state.get()[0])
+
+	@offset.setter
+	def offset(self, value):
+		if self.state is None:
+			self.state = GPUArray((1, ), np.uint64)
+		self.state.set(np.array([int(value)], np.uint64))
 
 	def _fill(self, kind, ary, a, b, dtype):
 		_requireArray(ary, "ary")
 		ary.enforceContiguous()
 		if ary.dtype != dtype:
 			raise ValueError("unsupported gpuarray dtype")
-		check(lib.pz_rng_fill(kind, ary.ptr, ary.size, self.seed, self.offset, float(a), float(b), None))
-		self.offset += (ary.size + 3) // 4
+		if self.state is None:
+			self.offset = 0
+		check(lib.pz_rng_fill_dev(kind, ary.ptr, ary.size, self.seed, self.state.ptr, float(a), float(b), None))
 
 	def fillInteger(self, ary):
 		self._fill(0, ary, 0.0, 0.0, np.dtype(np.uint32) if ary.dtype == np.uint32 else np.dtype(np.int32))
@@ -1059,6 +1014,8 @@ def _genericKernel(name, nptrs, nscalars, naux=0, dtype=None, f32state=()):
 		start, stop, step = _slice(kwargs, size) or (0, size, 1)
 
 		ptrs = (ctypes.c_void_p * nptrs)(*[ary.ptr for ary in arrays])
+		if nscalars and op in (5, 6, 7, 8, 9):
+			driver.traceScalar("the %s rates" % name, *rest)
 		if naux:       # pointwise costs: scalars are (int, int) or (float, float) after the pointers
 			scalars = (ctypes.c_float * 4)()
 			aux = (ctypes.c_int * 2)(int(rest[0]), int(rest[1]))
@@ -1244,6 +1201,8 @@ class B200Backend:
 
 		def ker(y, x, alpha, **kwargs):
 			_noSlice(kwargs)
+			if driver.deferred is not None and gpuarray.accumulate(y, x, alpha):
+				return          # absorbed by / fused with the pending zero fill of y (Add.py:15-23, Replicate.py:18-29)
 			check(lib.pz_axpy(dt, y.ptr, x.ptr, float(alpha), y.size, None))
 
 		return ker
@@ -1289,6 +1248,7 @@ class B200Backend:
 		dt = dtypeCode(dtype)
 
 		def ker(param, grad, mom, learnRate, momRate, **kwargs):
+			driver.traceScalar("the momentum-SGD rates", learnRate, momRate)
 			check(lib.pz_sgd_momentum(dt, param.ptr, grad.ptr, mom.ptr, float(learnRate), float(momRate), param.size, None))
 
 		return ker
@@ -1298,6 +1258,7 @@ class B200Backend:
 		dt = dtypeCode(dtype)
 
 		def ker(param, grad, mom, learnRate, momRate, **kwargs):
+			driver.traceScalar("the Nesterov-SGD rates", learnRate, momRate)
 			check(lib.pz_sgd_nesterov(dt, param.ptr, grad.ptr, mom.ptr, float(learnRate), float(momRate), param.size, None))
 
 		return ker
@@ -1309,6 +1270,7 @@ class B200Backend:
 		def ker(param, grad, mg, ms, learnRate, fix1, fix2, epsilon, **kwargs):
 			if mg.dtype != _f32 or ms.dtype != _f32:
 				raise ValueError("adam moments must be float32")
+			driver.traceScalar("Adam's bias-corrected rates", learnRate, fix1, fix2)
 			check(lib.pz_adam(dt, param.ptr, grad.ptr, mg.ptr, ms.ptr, float(learnRate), float(fix1), float(fix2), float(epsilon),
 							  param.size, None))
 

@@ -44,6 +44,107 @@ int check_desc(int dtype, const pz_conv2d_desc* d, Geo& g)
 	return PZ_OK;
 }
 
+// ================================================================================================ exact fp32 mode
+// `dnn.enableTensorOps(False)` (reference: CuDnn_Context_enableTensorOps, CuDnn.c:61-74): float32 convolutions as plain fp32
+// FMAs on the CUDA cores -- the accuracy cuDNN gives the reference on this stack (its fp32 convolutions do not use TF32
+// there), which the reference's own unit tests assume (np.allclose at 1e-5 relative).  A verification path, not tuned: one
+// thread per output element, direct loops; the filter gradient reduces over (n, p, q) with one CTA per filter element.
+__global__ void __launch_bounds__(256) exact_fprop_kernel(const float* __restrict__ x, const float* __restrict__ w,
+														  const float* __restrict__ bias, float* __restrict__ y, Geo g, long long total)
+{
+	for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+		const int q = (int)(i % g.Q);
+		long long r0 = i / g.Q;
+		const int p = (int)(r0 % g.P);
+		r0 /= g.P;
+		const int k = (int)(r0 % g.K), n = (int)(r0 / g.K);
+		const int grp = k / g.Kg;
+		float acc = 0.0f;
+		for (int c = 0; c < g.Cg; c++) {
+			const float* xp = x + ((long long)n * g.C + grp * g.Cg + c) * g.H * g.W;
+			const float* wp = w + ((long long)k * g.Cg + c) * g.R * g.S;
+			for (int r = 0; r < g.R; r++) {
+				const int h = p * g.sh - g.ph + r * g.dh;
+				if ((unsigned)h >= (unsigned)g.H) continue;
+				for (int sx = 0; sx < g.S; sx++) {
+					const int ww = q * g.sw - g.pw + sx * g.dw;
+					if ((unsigned)ww < (unsigned)g.W) acc = fmaf(xp[h * g.W + ww], wp[r * g.S + sx], acc);
+				}
+			}
+		}
+		y[i] = acc + (bias ? bias[k] : 0.0f);
+	}
+}
+
+__global__ void __launch_bounds__(256) exact_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w,
+														  const float* __restrict__ bias, float* __restrict__ dx, Geo g, long long total)
+{
+	for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+		const int ww = (int)(i % g.W);
+		long long r0 = i / g.W;
+		const int h = (int)(r0 % g.H);
+		r0 /= g.H;
+		const int c = (int)(r0 % g.C), n = (int)(r0 / g.C);
+		const int grp = c / g.Cg, cl = c - grp * g.Cg;
+		float acc = 0.0f;
+		for (int kl = 0; kl < g.Kg; kl++) {
+			const int k = grp * g.Kg + kl;
+			const float* dyp = dy + ((long long)n * g.K + k) * g.P * g.Q;
+			const float* wp = w + ((long long)k * g.Cg + cl) * g.R * g.S;
+			for (int r = 0; r < g.R; r++) {
+				const int hp = h + g.ph - r * g.dh;
+				if (hp < 0 || hp % g.sh != 0 || hp / g.sh >= g.P) continue;
+				for (int sx = 0; sx < g.S; sx++) {
+					const int wq = ww + g.pw - sx * g.dw;
+					if (wq < 0 || wq % g.sw != 0 || wq / g.sw >= g.Q) continue;
+					acc = fmaf(dyp[(hp / g.sh) * g.Q + wq / g.sw], wp[r * g.S + sx], acc);
+				}
+			}
+		}
+		dx[i] = acc + (bias ? bias[c] : 0.0f);
+	}
+}
+
+// one CTA per filter element (k, c, r, s): fixed-order strided partial sums + tree reduction (deterministic)
+__global__ void __launch_bounds__(256) exact_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw,
+														  Geo g, float alpha, float beta)
+{
+	__shared__ float red[256];
+	const long long e = blockIdx.x;
+	const int sx = (int)(e % g.S);
+	long long r0 = e / g.S;
+	const int r = (int)(r0 % g.R);
+	r0 /= g.R;
+	const int cl = (int)(r0 % g.Cg), k = (int)(r0 / g.Cg);
+	const int c = (k / g.Kg) * g.Cg + cl;
+	const long long PQ = (long long)g.P * g.Q, total = (long long)g.N * PQ;
+	float acc = 0.0f;
+	for (long long i = threadIdx.x; i < total; i += 256) {
+		const int n = (int)(i / PQ);
+		const int pq = (int)(i - (long long)n * PQ);
+		const int p = pq / g.Q, q = pq - p * g.Q;
+		const int h = p * g.sh - g.ph + r * g.dh, ww = q * g.sw - g.pw + sx * g.dw;
+		if ((unsigned)h < (unsigned)g.H && (unsigned)ww < (unsigned)g.W)
+			acc = fmaf(x[(((long long)n * g.C + c) * g.H + h) * g.W + ww], dy[((long long)n * g.K + k) * PQ + pq], acc);
+	}
+	red[threadIdx.x] = acc;
+	__syncthreads();
+	for (int o = 128; o > 0; o >>= 1) {
+		if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) dw[e] = alpha * red[0] + (beta != 0.0f ? beta * dw[e] : 0.0f);
+}
+
+int g_exact_fp32 = 0;
+
+unsigned exact_grid(long long total)
+{
+	long long blocks = pz_cdiv(total, 256);
+	const long long cap = (long long)pz_num_sms() * 16;
+	return (unsigned)(blocks > cap ? cap : (blocks < 1 ? 1 : blocks));
+}
+
 // the fast producers pack (offset << 6 | tap) into 32 bits: `span` elements of channel / row offsets plus the tap
 // offsets of one filter window must stay below 2^26, and a filter may have at most 63 taps
 bool tap_entries_fit(long long span, const Geo& g)
@@ -232,11 +333,27 @@ int prescale(float* buf, long long n, float beta, void* stream)
 
 extern "C" {
 
+// float32 math mode of the contractions (convolutions here, pz_gemm through pz_exact_fp32()): 0 = TF32 tensor-core products
+// (default), 1 = exact fp32 FMAs on the CUDA cores.  Process-wide, like the reference's per-context enableTensorOps.
+int pz_set_exact_fp32(int on)
+{
+	g_exact_fp32 = on ? 1 : 0;
+	return PZ_OK;
+}
+int pz_exact_fp32(void) { return g_exact_fp32; }
+
 int pz_conv2d_fprop(int dtype, const pz_conv2d_desc* d, const void* x, const void* w, const void* bias, void* y, void* stream)
 {
 	Geo g;
 	int st = check_desc(dtype, d, g);
 	if (st != PZ_OK) return st;
+	if (dtype == PZ_F32 && g_exact_fp32) {
+		const long long total = (long long)g.N * g.K * g.P * g.Q;
+		exact_fprop_kernel<<<exact_grid(total), 256, 0, pz_stream(stream)>>>((const float*)x, (const float*)w, (const float*)bias, (float*)y, g, total);
+		pz_count_launch(1);
+		PZ_LAUNCH_CHECK();
+		return PZ_OK;
+	}
 	const int RS = g.R * g.S, PQ = g.P * g.Q, HW = g.H * g.W;
 
 	GemmParams p{};
@@ -330,6 +447,13 @@ int pz_conv2d_dgrad(int dtype, const pz_conv2d_desc* d, const void* dy, const vo
 	Geo g;
 	int st = check_desc(dtype, d, g);
 	if (st != PZ_OK) return st;
+	if (dtype == PZ_F32 && g_exact_fp32) {
+		const long long total = (long long)g.N * g.C * g.H * g.W;
+		exact_dgrad_kernel<<<exact_grid(total), 256, 0, pz_stream(stream)>>>((const float*)dy, (const float*)w, (const float*)bias, (float*)dx, g, total);
+		pz_count_launch(1);
+		PZ_LAUNCH_CHECK();
+		return PZ_OK;
+	}
 	const int RS = g.R * g.S, PQ = g.P * g.Q, HW = g.H * g.W;
 	const bool is1x1 = g.R == 1 && g.S == 1;
 	const bool strided = g.sh > 1 || g.sw > 1;
@@ -555,6 +679,14 @@ int pz_conv2d_wgrad(int dtype, const pz_conv2d_desc* d, const void* x, const voi
 	Geo g;
 	int st = check_desc(dtype, d, g);
 	if (st != PZ_OK) return st;
+	if (dtype == PZ_F32 && g_exact_fp32) {
+		const long long elems = (long long)g.K * g.Cg * g.R * g.S;
+		PZ_REQUIRE(elems < (1ll << 31), "conv2d wgrad: filter too large");
+		exact_wgrad_kernel<<<(unsigned)elems, 256, 0, pz_stream(stream)>>>((const float*)x, (const float*)dy, (float*)dw, g, alpha, beta);
+		pz_count_launch(1);
+		PZ_LAUNCH_CHECK();
+		return PZ_OK;
+	}
 	const int RS = g.R * g.S, PQ = g.P * g.Q, HW = g.H * g.W;
 	PZ_REQUIRE((long long)g.N * PQ < (1ll << 31), "conv2d wgrad: reduction too long");
 

@@ -233,12 +233,15 @@ struct ReluBwd {
 	__device__ __forceinline__ void apply(float* io, const float* in) const { io[0] = in[0] * (in[1] > 0.0f); }
 };
 
-struct Tf32Split {   // io[0] = x rounded to tf32 (nearest, ties away), io[1] = x - io[0] (exact in fp32)
+// y = (0 + x1*a1) + x2*a2 with the intermediate rounded to the storage type: bit for bit what `y.fill(0); y += a1*x1; y += a2*x2`
+// leaves in y (three launches of toVectorAddVectorKer, ElementWise.py:583-609), in one pass.  in[1] unused when a2 == 0 / x2 NULL.
+template <typename T, bool TWO>
+struct Axpy2 {
+	float a1, a2;
 	__device__ __forceinline__ void apply(float* io, const float* in) const
 	{
-		const float hi = __uint_as_float((__float_as_uint(in[0]) + 0x1000u) & 0xffffe000u);
-		io[0] = hi;
-		io[1] = in[0] - hi;
+		const float first = to_f<T>(from_f<T>(fmaf(in[0], a1, 0.0f)));
+		io[0] = TWO ? fmaf(in[1], a2, first) : first;
 	}
 };
 struct Axpy {   // y = y + x * alpha   (ElementWise.py:591)
@@ -393,14 +396,17 @@ int pz_mul_slice(int dtype, void* out, const void* a, const void* b, int64_t n, 
 	PZ_DISPATCH_FLOAT(dtype, ew_launch_slice<T, 1, 2, false>(out, nullptr, a, b, nullptr, n, start, stop, step, Mul{}, stream));
 }
 
-int pz_tf32_split(const void* x, void* hi, void* lo, int64_t n, void* stream)
-{
-	return ew_launch<float, 2, 1, false>(hi, lo, x, nullptr, nullptr, n, Tf32Split{}, stream);
-}
-
 int pz_axpy(int dtype, void* y, const void* x, float alpha, int64_t n, void* stream)
 {
 	PZ_DISPATCH_FLOAT(dtype, ew_launch<T, 1, 1, true>(y, nullptr, x, nullptr, nullptr, n, Axpy{alpha}, stream));
+}
+
+int pz_axpy2(int dtype, void* y, const void* x1, float a1, const void* x2, float a2, int64_t n, void* stream)
+{
+	if (x2 == nullptr) {
+		PZ_DISPATCH_FLOAT(dtype, ew_launch<T, 1, 1, false>(y, nullptr, x1, nullptr, nullptr, n, Axpy2<T, false>{a1, 0.0f}, stream));
+	}
+	PZ_DISPATCH_FLOAT(dtype, ew_launch<T, 1, 2, false>(y, nullptr, x1, x2, nullptr, n, Axpy2<T, true>{a1, a2}, stream));
 }
 
 int pz_axpby(int dtype, void* out, const void* x, float alpha, const void* y, float beta, int64_t n, void* stream)

@@ -258,13 +258,14 @@ extern "C" int pz_gemm(int dtype, const void* A, const void* B, void* C, int64_t
 	PZ_REQUIRE(dtype == PZ_F32 || dtype == PZ_F16 || dtype == PZ_BF16, "pz_gemm: unsupported dtype %d", dtype);
 	PZ_REQUIRE(M >= 0 && N >= 0 && K > 0, "pz_gemm: invalid sizes M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)K);
 	PZ_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "pz_gemm: dimension too large");
-	PZ_REQUIRE(M * lda < (1ll << 31) && K * ldb < (1ll << 31) && K * lda < (1ll << 31) && N * ldb < (1ll << 31),
+	// A is stored as (transA ? K : M) rows of lda elements, B as (transB ? N : K) rows of ldb elements (32-bit index algebra)
+	PZ_REQUIRE((transA ? K : M) * lda < (1ll << 31) && (transB ? N : K) * ldb < (1ll << 31) && M * ldc < (1ll << 31),
 			   "pz_gemm: operand exceeds 2^31 elements");
 	if (M == 0 || N == 0) return PZ_OK;
 	cudaStream_t s = pz_stream(stream);
 	const size_t es = dtype == PZ_F32 ? 4 : 2;
 
-	if (K <= kSmallK) {
+	if (K <= kSmallK || (dtype == PZ_F32 && pz_exact_fp32())) {      // tiny K, or the exact mode: fp32 FMAs on the CUDA cores
 		int64_t blocks = pz_cdiv(M * N, 256);
 		if (blocks > (int64_t)pz_num_sms() * 16) blocks = (int64_t)pz_num_sms() * 16;
 		if (dtype == PZ_F32)

@@ -409,6 +409,332 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(const T* __restr
 	}
 }
 
+
+// ================================================================================================ cluster kernels
+// One thread-block CLUSTER per channel: the CL CTAs of a cluster split the N images of channel c.  Phase 1: a CTA streams its
+// planes from HBM, keeps them in SHARED MEMORY and accumulates the channel statistics; the partial sums meet through
+// DISTRIBUTED SHARED MEMORY (deterministic: fixed trees, partials added in rank order -- no atomics).  Phase 2: the CTA
+// normalises out of shared memory and streams the result to HBM.  The tensor crosses HBM exactly once in each direction: 2E
+// bytes forward (x, y), 3E backward (x, dy, dx).  Planes need no alignment: a plane is covered by the 16-byte aligned vectors
+// that overlap it; lanes outside the plane are masked on the way in and stored as scalars on the way out.
+struct ClusterGeo {
+	int N, C, S;
+	int CL, rows_per_cta;
+	int SP;                      // vector slots per plane (upper bound)
+	FastDiv32 spdiv;
+	int stash_slots;             // rows_per_cta * SP
+};
+
+constexpr int kSlotUnroll = 8;      // 16-byte loads in flight per thread (the backward kernel reads two tensors: 2 x 4)
+
+__device__ __forceinline__ unsigned cluster_ctarank()
+{
+	unsigned r;
+	asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+	return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+	asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float ld_dsmem(const float* local, unsigned rank)
+{
+	unsigned addr = (unsigned)__cvta_generic_to_shared(local), remote;
+	float v;
+	asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(addr), "r"(rank));
+	asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote) : "memory");
+	return v;
+}
+
+// write-once results leave with the evict-first hint
+template <typename T, int VEC>
+__device__ __forceinline__ void store_streaming(T* dst, const Pack<T, VEC>& v)
+{
+	const uint4 u = *reinterpret_cast<const uint4*>(&v);
+	asm volatile("st.global.cs.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w) : "memory");
+}
+
+// deterministic block sum of two values; result valid in every thread
+template <int THREADS>
+__device__ __forceinline__ void block_sum2(float& a, float& b, float* red /* [2 * THREADS / 32 + 2] */)
+{
+	a = warp_sum(a);
+	b = warp_sum(b);
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	if (lane == 0) { red[2 * warp] = a; red[2 * warp + 1] = b; }
+	__syncthreads();
+	if (warp == 0) {
+		float x = lane < THREADS / 32 ? red[2 * lane] : 0.0f, y = lane < THREADS / 32 ? red[2 * lane + 1] : 0.0f;
+		x = warp_sum(x);
+		y = warp_sum(y);
+		if (lane == 0) { red[2 * (THREADS / 32)] = x; red[2 * (THREADS / 32) + 1] = y; }
+	}
+	__syncthreads();
+	a = red[2 * (THREADS / 32)];
+	b = red[2 * (THREADS / 32) + 1];
+}
+
+// slot -> aligned vector offset (elements) + the bit mask of its lanes that belong to the plane (0: empty slot)
+template <int VEC>
+__device__ __forceinline__ uint32_t slot_geometry(const ClusterGeo& g, int c, int n0, int slot, int nslots, long long& e0)
+{
+	if (slot >= nslots) { e0 = 0; return 0u; }
+	const uint32_t row = fdiv32((uint32_t)slot, g.spdiv);
+	const int v = slot - (int)row * g.SP;
+	const long long lo = ((long long)(n0 + (int)row) * g.C + c) * g.S;       // first element of the plane
+	e0 = (lo & ~(long long)(VEC - 1)) + (long long)v * VEC;
+	const long long first = lo - e0, last = lo + g.S - e0;                   // valid lanes: first <= lane < last
+	if (last <= 0) return 0u;
+	const uint32_t full = (1u << VEC) - 1u;
+	const uint32_t below = first > 0 ? ((1u << (int)first) - 1u) : 0u;
+	const uint32_t upto = last >= VEC ? full : ((1u << (int)last) - 1u);
+	return upto & ~below;
+}
+
+// the cluster-wide sum of the CTAs' (s1, s2) through distributed shared memory, in rank order
+__device__ __forceinline__ void cluster_sum2(float& s1, float& s2, float* part, int CL)
+{
+	if (CL <= 1) return;
+	if (threadIdx.x == 0) { part[0] = s1; part[1] = s2; }
+	cluster_sync_all();
+	s1 = 0.0f;
+	s2 = 0.0f;
+	for (int r = 0; r < CL; r++) { s1 += ld_dsmem(&part[0], (unsigned)r); s2 += ld_dsmem(&part[1], (unsigned)r); }
+	cluster_sync_all();                 // nobody leaves (or overwrites `part`) while a peer still reads it
+}
+
+template <typename T, int VEC, int THREADS>
+__global__ void __launch_bounds__(THREADS) bn_fwd_cluster_kernel(const T* __restrict__ x, T* __restrict__ y, ClusterGeo g,
+																  const float* __restrict__ scale, const float* __restrict__ bias,
+																  float* mean_io, float* var_io, float* save_mean, float* save_invvar,
+																  float eps, float factor)
+{
+	extern __shared__ uint4 stash[];                 // [stash_slots]: this CTA's planes, as the aligned vectors that cover them
+	__shared__ float red[2 * THREADS / 32 + 2];
+	__shared__ float part[2];
+	using P = Pack<T, VEC>;
+	const unsigned rank = g.CL > 1 ? cluster_ctarank() : 0u;
+	const int c = (int)(blockIdx.x / (unsigned)g.CL);
+	const int n0 = (int)rank * g.rows_per_cta, n1 = min(g.N, n0 + g.rows_per_cta);
+	const int nslots = max(0, n1 - n0) * g.SP;
+	const float pivot = to_f<T>(x[(size_t)c * g.S]);
+
+	// ---- phase 1: HBM -> shared memory, sum(x - pivot), sum((x - pivot)^2)
+	float s1 = 0.0f, s2 = 0.0f;
+	for (int base = threadIdx.x; base < nslots; base += THREADS * kSlotUnroll) {
+		P v[kSlotUnroll];
+		uint32_t mask[kSlotUnroll];
+		#pragma unroll
+		for (int u = 0; u < kSlotUnroll; u++) {
+			long long e0;
+			mask[u] = slot_geometry<VEC>(g, c, n0, base + u * THREADS, nslots, e0);
+			if (mask[u]) v[u] = *reinterpret_cast<const P*>(x + e0);
+		}
+		#pragma unroll
+		for (int u = 0; u < kSlotUnroll; u++) {
+			if (!mask[u]) continue;
+			stash[base + u * THREADS] = *reinterpret_cast<const uint4*>(&v[u]);
+			#pragma unroll
+			for (int e = 0; e < VEC; e++) {
+				if (mask[u] >> e & 1u) { const float d = to_f<T>(v[u].v[e]) - pivot; s1 += d; s2 = fmaf(d, d, s2); }
+			}
+		}
+	}
+	block_sum2<THREADS>(s1, s2, red);
+	cluster_sum2(s1, s2, part, g.CL);
+
+	const float count = (float)g.N * (float)g.S;
+	const float dmean = s1 / count;
+	const float mean = pivot + dmean;
+	const float var = fmaxf(s2 / count - dmean * dmean, 0.0f);      // biased: used for normalisation
+	const float invstd = 1.0f / sqrtf(var + eps);
+	if (rank == 0 && threadIdx.x == 0) {
+		save_mean[c] = mean;
+		save_invvar[c] = invstd;
+		// cuDNN keeps the UNBIASED variance in the running estimate (pinned by tests/golden/ref_cuda_ops.npz bn*/runvar)
+		const float uvar = count > 1.0f ? var * (count / (count - 1.0f)) : var;
+		mean_io[c] = (1.0f - factor) * mean_io[c] + factor * mean;
+		var_io[c] = (1.0f - factor) * var_io[c] + factor * uvar;
+	}
+	const float a = scale[c] * invstd, b = bias[c] - mean * a;
+
+	// ---- phase 2: shared memory -> y = a * x + b -> HBM
+	constexpr uint32_t FULL = (1u << VEC) - 1u;
+	for (int slot = threadIdx.x; slot < nslots; slot += THREADS) {
+		long long e0;
+		const uint32_t mask = slot_geometry<VEC>(g, c, n0, slot, nslots, e0);
+		if (!mask) continue;
+		const uint4 raw = stash[slot];
+		P v = *reinterpret_cast<const P*>(&raw);
+		#pragma unroll
+		for (int e = 0; e < VEC; e++) v.v[e] = from_f<T>(fmaf(to_f<T>(v.v[e]), a, b));
+		if (mask == FULL) {
+			store_streaming<T, VEC>(y + e0, v);
+		} else {
+			#pragma unroll
+			for (int e = 0; e < VEC; e++)
+				if (mask >> e & 1u) y[e0 + e] = v.v[e];
+		}
+	}
+}
+
+template <typename T, int VEC, int THREADS>
+__global__ void __launch_bounds__(THREADS) bn_bwd_cluster_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx,
+																  ClusterGeo g, const float* __restrict__ scale,
+																  const float* __restrict__ save_mean, const float* __restrict__ save_invvar,
+																  float* dscale, float* dbias)
+{
+	extern __shared__ uint4 stash[];                 // [2][stash_slots]: x planes, then dy planes
+	__shared__ float red[2 * THREADS / 32 + 2];
+	__shared__ float part[2];
+	using P = Pack<T, VEC>;
+	const unsigned rank = g.CL > 1 ? cluster_ctarank() : 0u;
+	const int c = (int)(blockIdx.x / (unsigned)g.CL);
+	const int n0 = (int)rank * g.rows_per_cta, n1 = min(g.N, n0 + g.rows_per_cta);
+	const int nslots = max(0, n1 - n0) * g.SP;
+	const float mean = save_mean[c], invstd = save_invvar[c];
+	constexpr int UNR = kSlotUnroll / 2;              // two tensors per slot
+	uint4* stash_dy = stash + g.stash_slots;
+
+	// ---- phase 1: HBM -> shared memory, sum(dy), sum(dy * (x - mean))
+	float s1 = 0.0f, s2 = 0.0f;
+	for (int base = threadIdx.x; base < nslots; base += THREADS * UNR) {
+		P v[UNR], w[UNR];
+		uint32_t mask[UNR];
+		#pragma unroll
+		for (int u = 0; u < UNR; u++) {
+			long long e0;
+			mask[u] = slot_geometry<VEC>(g, c, n0, base + u * THREADS, nslots, e0);
+			if (mask[u]) {
+				v[u] = *reinterpret_cast<const P*>(x + e0);
+				w[u] = *reinterpret_cast<const P*>(dy + e0);
+			}
+		}
+		#pragma unroll
+		for (int u = 0; u < UNR; u++) {
+			if (!mask[u]) continue;
+			stash[base + u * THREADS] = *reinterpret_cast<const uint4*>(&v[u]);
+			stash_dy[base + u * THREADS] = *reinterpret_cast<const uint4*>(&w[u]);
+			#pragma unroll
+			for (int e = 0; e < VEC; e++) {
+				if (mask[u] >> e & 1u) {
+					const float gv = to_f<T>(w[u].v[e]);
+					s1 += gv;
+					s2 = fmaf(gv, to_f<T>(v[u].v[e]) - mean, s2);
+				}
+			}
+		}
+	}
+	block_sum2<THREADS>(s1, s2, red);
+	cluster_sum2(s1, s2, part, g.CL);
+
+	const float count = (float)g.N * (float)g.S;
+	const float dsc = s2 * invstd;               // sum(dy * xhat)
+	if (rank == 0 && threadIdx.x == 0) { dscale[c] = dsc; dbias[c] = s1; }
+	const float c1 = scale[c] * invstd, c2 = c1 * s1 / count, c3 = c1 * dsc / count * invstd;
+
+	// ---- phase 2: shared memory -> dx = c1*dy - c2 - (x - mean)*c3 -> HBM
+	constexpr uint32_t FULL = (1u << VEC) - 1u;
+	for (int slot = threadIdx.x; slot < nslots; slot += THREADS) {
+		long long e0;
+		const uint32_t mask = slot_geometry<VEC>(g, c, n0, slot, nslots, e0);
+		if (!mask) continue;
+		const uint4 rx = stash[slot], rg = stash_dy[slot];
+		const P v = *reinterpret_cast<const P*>(&rx);
+		P w = *reinterpret_cast<const P*>(&rg);
+		#pragma unroll
+		for (int e = 0; e < VEC; e++) w.v[e] = from_f<T>(c1 * to_f<T>(w.v[e]) - c2 - (to_f<T>(v.v[e]) - mean) * c3);
+		if (mask == FULL) {
+			store_streaming<T, VEC>(dx + e0, w);
+		} else {
+			#pragma unroll
+			for (int e = 0; e < VEC; e++)
+				if (mask >> e & 1u) dx[e0 + e] = w.v[e];
+		}
+	}
+}
+
+// ---- host side of the cluster kernels
+struct ClusterPlan {
+	ClusterGeo g;
+	int threads;             // 256 or 512
+	size_t smem;             // the stash
+	bool ok;
+};
+
+int env_int(const char* name, int dflt)
+{
+	const char* e = getenv(name);
+	return e ? atoi(e) : dflt;
+}
+
+constexpr size_t kStashTwoPerSm = 100 * 1024, kStashMax = 200 * 1024;
+
+// `tensors`: 1 forward (x), 2 backward (x, dy) kept in shared memory between the phases
+ClusterPlan make_cluster_plan(std::initializer_list<const void*> ptrs, int64_t N, int64_t C, int64_t S, size_t es, int tensors)
+{
+	static const int force_threads = env_int("PZ_BN_THREADS", 0), force_cl = env_int("PZ_BN_CL", 0);
+	ClusterPlan p{};
+	const int vec = (int)(16 / es);
+	p.ok = getenv("PZ_BN_NO_CLUSTER") == nullptr && N * C * S < (1ll << 40) && C < (1 << 24);
+	for (const void* q : ptrs) p.ok = p.ok && ((uintptr_t)q % 16 == 0);
+	if (!p.ok) return p;
+
+	ClusterGeo& g = p.g;
+	g.N = (int)N; g.C = (int)C; g.S = (int)S;
+	g.SP = (int)((S + 2 * (vec - 1)) / vec);           // aligned vectors that can overlap a plane starting anywhere
+	if ((S % vec) == 0) g.SP = (int)(S / vec);         // ... every plane is aligned when S is a multiple of the vector width
+	g.spdiv = make_fastdiv32((uint32_t)g.SP);
+
+	// smallest cluster whose CTAs can keep their planes in shared memory with two CTAs per SM (a bigger cluster when the machine
+	// would not be filled); failing that the two-kernel path
+	const int sms = pz_num_sms();
+	int CL = 0;
+	for (int cl = 1; cl <= 8; cl *= 2) {
+		if (cl > 1 && cl > N) break;
+		const size_t bytes = (size_t)pz_cdiv(N, cl) * g.SP * 16 * tensors;
+		if (bytes <= kStashTwoPerSm && (C * cl >= 2 * sms || cl == 8 || cl * 2 > N)) { CL = cl; break; }
+	}
+	// (a stash that leaves room for ONE CTA per SM only -- planes above ~100 KB per CTA even in a cluster of 8 -- measured slower
+	// than the two-kernel path: profiles/r02_bn.md)
+	if (force_cl > 0 && force_cl <= 8 && (force_cl & (force_cl - 1)) == 0 && force_cl <= (N > 1 ? N : 1)) CL = force_cl;
+	if (CL == 0) { p.ok = false; return p; }
+
+	g.CL = CL;
+	g.rows_per_cta = (int)pz_cdiv(N, CL);
+	const long long slots = (long long)g.rows_per_cta * g.SP;
+	g.stash_slots = (int)slots;
+	p.smem = (size_t)slots * 16 * tensors;
+	if (p.smem > kStashMax) { p.ok = false; return p; }
+	p.threads = slots >= 2048 ? 512 : 256;
+	if (force_threads == 256 || force_threads == 512) p.threads = force_threads;
+	return p;
+}
+
+template <typename K, typename... Args>
+int launch_cluster(K kernel, const ClusterPlan& p, cudaStream_t s, Args... args)
+{
+	cudaLaunchConfig_t cfg{};
+	cfg.gridDim = dim3((unsigned)(p.g.C * p.g.CL));
+	cfg.blockDim = dim3((unsigned)p.threads);
+	cfg.dynamicSmemBytes = p.smem;
+	cfg.stream = s;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeClusterDimension;
+	attr[0].val.clusterDim.x = (unsigned)p.g.CL;
+	attr[0].val.clusterDim.y = 1;
+	attr[0].val.clusterDim.z = 1;
+	cfg.attrs = attr;
+	cfg.numAttrs = 1;
+	if (p.smem > 48 * 1024) {
+		// (idempotent; a per-kernel flag would need one static per instantiation)
+		PZ_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStashMax));
+	}
+	PZ_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kernel, args...));
+	pz_count_launch(1);
+	return PZ_OK;
+}
+
 // ------------------------------------------------------------------------------------------ host side
 // Two [C][2] fp32 accumulator buffers, library-owned and used in stream order.  A pass accumulates into one of them and its
 // apply kernel clears what the previous pass left in the other, which the next pass will use.
@@ -431,10 +757,9 @@ bool acquire_sums(int64_t C, SumsPair& sp)
 	int& cur = g_sums_cur;
 	std::lock_guard<std::mutex> lock(g_sums_mu);
 	if (C > cap) {
-		cudaDeviceSynchronize();
+		// growth retires the old buffers instead of freeing them: launches (or captured graphs) that hold them stay valid
 		const int64_t want = C < 65536 ? 65536 : C + C / 2;
 		for (int i = 0; i < 2; i++) {
-			if (buf[i]) cudaFree(buf[i]);
 			buf[i] = nullptr;
 			if (cudaMalloc((void**)&buf[i], (size_t)want * 2 * sizeof(float)) != cudaSuccess) { cap = 0; cudaGetLastError(); return false; }
 			cudaMemset(buf[i], 0, (size_t)want * 2 * sizeof(float));
@@ -516,12 +841,22 @@ int fwd_train(const void* x, void* y, int64_t N, int64_t C, int64_t S, const flo
 {
 	constexpr int V = 16 / sizeof(T);
 	cudaStream_t s = pz_stream(stream);
+	PzProfScope prof(PZ_PROF_BN_FWD, s, 0.0, 2.0 * (double)N * C * S * sizeof(T));
+	{
+		// one cluster per channel, the tensor crosses HBM once (see "cluster kernels").  In-place (y == x) is safe here: a CTA
+		// only rewrites planes it alone reads, and the pivot element is read by every CTA of the cluster before its barrier
+		const ClusterPlan cp = make_cluster_plan({x, y}, N, C, S, sizeof(T), 1);
+		if (cp.ok) {
+			if (cp.threads == 512)
+				return launch_cluster(bn_fwd_cluster_kernel<T, V, 512>, cp, s, (const T*)x, (T*)y, cp.g, scale, bias, rm, rv, sm, siv, (float)eps, (float)factor);
+			return launch_cluster(bn_fwd_cluster_kernel<T, V, 256>, cp, s, (const T*)x, (T*)y, cp.g, scale, bias, rm, rv, sm, siv, (float)eps, (float)factor);
+		}
+	}
 	SumsPair sp;
 	if (!acquire_sums(C, sp)) { pz_set_error(PZ_ERR_MEMORY, "batchnorm: cannot allocate the statistics buffer"); return PZ_ERR_MEMORY; }
 	float* sums = sp.use;
 	const Plan plan = make_plan<T>({x, y}, N, C, S, 1);
 	const float count = (float)(N * S);
-	PzProfScope prof(PZ_PROF_BN_FWD, s, 0.0, 2.0 * (double)N * C * S * sizeof(T));
 	for (int64_t c0 = 0; c0 < C; c0 += plan.slab_channels) {
 		const int64_t c1 = c0 + plan.slab_channels < C ? c0 + plan.slab_channels : C;
 		const Slab g = make_slab(plan, N, C, S, c0, c1);
@@ -565,12 +900,20 @@ int bwd(const void* x, const void* dy, void* dx, int64_t N, int64_t C, int64_t S
 {
 	constexpr int V = 16 / sizeof(T);
 	cudaStream_t s = pz_stream(stream);
+	PzProfScope prof(PZ_PROF_BN_BWD, s, 0.0, 3.0 * (double)N * C * S * sizeof(T));
+	{
+		const ClusterPlan cp = make_cluster_plan({x, dy, dx}, N, C, S, sizeof(T), 2);
+		if (cp.ok) {
+			if (cp.threads == 512)
+				return launch_cluster(bn_bwd_cluster_kernel<T, V, 512>, cp, s, (const T*)x, (const T*)dy, (T*)dx, cp.g, scale, sm, siv, dscale, dbias);
+			return launch_cluster(bn_bwd_cluster_kernel<T, V, 256>, cp, s, (const T*)x, (const T*)dy, (T*)dx, cp.g, scale, sm, siv, dscale, dbias);
+		}
+	}
 	SumsPair sp;
 	if (!acquire_sums(C, sp)) { pz_set_error(PZ_ERR_MEMORY, "batchnorm: cannot allocate the statistics buffer"); return PZ_ERR_MEMORY; }
 	float* sums = sp.use;
 	const Plan plan = make_plan<T>({x, dy, dx}, N, C, S, 2);
 	const float count = (float)(N * S);
-	PzProfScope prof(PZ_PROF_BN_BWD, s, 0.0, 3.0 * (double)N * C * S * sizeof(T));
 	for (int64_t c0 = 0; c0 < C; c0 += plan.slab_channels) {
 		const int64_t c1 = c0 + plan.slab_channels < C ? c0 + plan.slab_channels : C;
 		const Slab g = make_slab(plan, N, C, S, c0, c1);

@@ -38,22 +38,37 @@ int pz_num_sms()
 	return sms;
 }
 
-// Library-owned scratch.  Use is stream-ordered: the kernel that writes it and the kernel that reads it are enqueued back to
-// back on the caller's stream (the reference runs everything on the legacy default stream), and the next user overwrites it
-// only after both have run.
+// Library-owned scratch, one buffer per device.  Use is stream-ordered: the kernel that writes it and the kernel that reads it
+// are enqueued back to back on the caller's stream (the reference runs everything on the legacy default stream), and the next
+// user overwrites it only after both have run.  Growth never frees: a captured CUDA graph (pz_graph_*) keeps the address it
+// saw, so an outgrown block is retired (kept until process exit) instead of being handed back to the driver -- and since
+// cudaMalloc is not allowed while a stream is capturing, growth under capture is an error the caller sees (StepGraph warms the
+// step up eagerly first, which sizes the scratch).
+namespace {
+struct DeviceScratch { void* buf = nullptr; size_t cap = 0; std::vector<void*> retired; };
+DeviceScratch g_scratch[64];
+std::mutex g_scratch_mu;
+}
+
 void* pz_scratch(size_t bytes)
 {
-	static void* buf = nullptr;
-	static size_t cap = 0;
-	static std::mutex mu;
-	std::lock_guard<std::mutex> lock(mu);
-	if (bytes > cap) {
-		if (buf) { cudaDeviceSynchronize(); cudaFree(buf); buf = nullptr; cap = 0; }
-		size_t want = bytes < ((size_t)64 << 20) ? ((size_t)64 << 20) : bytes + (bytes >> 2);
-		if (cudaMalloc(&buf, want) != cudaSuccess) { buf = nullptr; cudaGetLastError(); return nullptr; }
-		cap = want;
+	int dev = 0;
+	if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { cudaGetLastError(); return nullptr; }
+	std::lock_guard<std::mutex> lock(g_scratch_mu);
+	DeviceScratch& sc = g_scratch[dev];
+	if (bytes > sc.cap) {
+		cudaStreamCaptureStatus status = cudaStreamCaptureStatusNone;
+		if (g_default_stream != nullptr && cudaStreamIsCapturing(g_default_stream, &status) == cudaSuccess &&
+			status != cudaStreamCaptureStatusNone)
+			return nullptr;                      // cannot allocate while capturing: the caller reports PZ_ERR_MEMORY
+		const size_t want = bytes < ((size_t)64 << 20) ? ((size_t)64 << 20) : bytes + (bytes >> 2);
+		void* fresh = nullptr;
+		if (cudaMalloc(&fresh, want) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+		if (sc.buf) sc.retired.push_back(sc.buf);      // kernels / graphs already enqueued may still use it
+		sc.buf = fresh;
+		sc.cap = want;
 	}
-	return buf;
+	return sc.buf;
 }
 
 // ---------------------------------------------------------------------------------------- launch profiling

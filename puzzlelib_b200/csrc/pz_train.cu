@@ -314,8 +314,10 @@ __device__ __forceinline__ void philox4x32(unsigned long long counter, unsigned 
 
 // kind 0: raw 32-bit integers; 1: uniform in (lo, hi]; 2: normal(mean = lo, stddev = hi) by Box-Muller
 __global__ void __launch_bounds__(kThreads) rng_fill_kernel(void* __restrict__ out, long long n, unsigned long long seed,
-														   unsigned long long offset, int kind, float lo, float hi)
+														   unsigned long long offset, const unsigned long long* __restrict__ offset_dev,
+														   int kind, float lo, float hi)
 {
+	if (offset_dev) offset = *offset_dev;          // generator state kept on the device (graph replays draw new numbers)
 	const long long quads = (n + 3) / 4;
 	for (long long q = (long long)blockIdx.x * kThreads + threadIdx.x; q < quads; q += (long long)gridDim.x * kThreads) {
 		uint32_t r[4];
@@ -365,8 +367,26 @@ extern "C" int pz_rng_fill(int kind, void* out, int64_t n, uint64_t seed, uint64
 {
 	PZ_REQUIRE(kind >= 0 && kind <= 2, "rng fill: unknown kind %d", kind);
 	if (n <= 0) return PZ_OK;
-	rng_fill_kernel<<<grid_for((n + 3) / 4), kThreads, 0, pz_stream(stream)>>>(out, (long long)n, seed, offset, kind, a, b);
+	rng_fill_kernel<<<grid_for((n + 3) / 4), kThreads, 0, pz_stream(stream)>>>(out, (long long)n, seed, offset, nullptr, kind, a, b);
 	pz_count_launch(1);
+	PZ_LAUNCH_CHECK();
+	return PZ_OK;
+}
+
+namespace {
+__global__ void rng_advance_kernel(unsigned long long* offset, unsigned long long by) { *offset += by; }
+}
+
+// the same fill with the generator offset read from (and then advanced in) device memory
+extern "C" int pz_rng_fill_dev(int kind, void* out, int64_t n, uint64_t seed, void* offset_dev, float a, float b, void* stream)
+{
+	PZ_REQUIRE(kind >= 0 && kind <= 2, "rng fill: unknown kind %d", kind);
+	PZ_REQUIRE(offset_dev != nullptr, "rng fill: null generator state");
+	if (n <= 0) return PZ_OK;
+	rng_fill_kernel<<<grid_for((n + 3) / 4), kThreads, 0, pz_stream(stream)>>>(out, (long long)n, seed, 0ull,
+																				(const unsigned long long*)offset_dev, kind, a, b);
+	rng_advance_kernel<<<1, 1, 0, pz_stream(stream)>>>((unsigned long long*)offset_dev, (unsigned long long)((n + 3) / 4));
+	pz_count_launch(2);
 	PZ_LAUNCH_CHECK();
 	return PZ_OK;
 }

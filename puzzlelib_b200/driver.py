@@ -112,11 +112,12 @@ _SIGNATURES = {
 	"pz_act_bwd": [c_int, c_int, _P, _P, _P, c_int64, c_float, c_float, _P],
 	"pz_axpy": [c_int, _P, _P, c_float, c_int64, _P],
 	"pz_axpby": [c_int, _P, _P, c_float, _P, c_float, c_int64, _P],
+	"pz_axpy2": [c_int, _P, _P, c_float, _P, c_float, c_int64, _P],
 	"pz_scale_shift": [c_int, _P, _P, c_float, c_float, c_int64, _P],
 	"pz_mul": [c_int, _P, _P, _P, c_int64, _P],
 	"pz_add2": [c_int, _P, _P, _P, c_int64, _P],
 	"pz_cast": [c_int, _P, c_int, _P, c_int64, _P],
-	"pz_tf32_split": [_P, _P, _P, c_int64, _P],
+	"pz_set_exact_fp32": [c_int],
 	"pz_act_fwd_slice": [c_int, c_int, _P, _P, c_int64, c_float, c_float, c_int64, c_int64, c_int64, _P],
 	"pz_act_bwd_slice": [c_int, c_int, _P, _P, _P, c_int64, c_float, c_float, c_int64, c_int64, c_int64, _P],
 	"pz_axpby_slice": [c_int, _P, _P, c_float, _P, c_float, c_int64, c_int64, c_int64, c_int64, _P],
@@ -137,6 +138,7 @@ _SIGNATURES = {
 	"pz_lrn_fwd": [c_int, c_int, _P, _P, c_int64, c_int64, c_int64, c_int64, c_int, c_float, c_float, c_float, _P],
 	"pz_lrn_bwd": [c_int, c_int, _P, _P, _P, _P, c_int64, c_int64, c_int64, c_int64, c_int, c_float, c_float, c_float, _P],
 	"pz_rng_fill": [c_int, _P, c_int64, c_uint64, c_uint64, c_float, c_float, _P],
+	"pz_rng_fill_dev": [c_int, _P, c_int64, c_uint64, _P, c_float, c_float, _P],
 	"pz_dropout": [c_int, _P, _P, _P, c_uint32, c_float, c_int64, c_int64, _P],
 	"pz_reduce_minmax": [c_int, _P, c_int64, c_int, _P, _P],
 	"pz_addvec2mat": [c_int, _P, _P, _P, c_int64, c_int64, c_int64, c_int, c_int64, _P],
@@ -177,7 +179,7 @@ _SIGNATURES = {
 	"pz_nccl_allreduce_sgd_momentum": [_P, c_int, _P, _P, _P, c_int64, c_float, c_float, c_float, _P],
 }
 
-EXPORTS = sorted(_SIGNATURES) + ["pz_last_error", "pz_version", "pz_launch_count", "pz_pool_alloc_size"]
+EXPORTS = sorted(_SIGNATURES) + ["pz_last_error", "pz_version", "pz_launch_count", "pz_pool_alloc_size", "pz_exact_fp32"]
 
 
 def _bind():
@@ -218,6 +220,22 @@ def raiseOnStatus(status, errtype=CudaError):
 def check(status):
 	if status:
 		raiseOnStatus(status)
+
+
+# --------------------------------------------------------------------------------------------------------- deferred fill
+# `y.fill(0)` followed by `y += a * x` (twice) is how the reference's Add / Replicate modules build a sum (Modules/Add.py:15-23,
+# Replicate.py:18-29): 7 passes over tensors of the largest activations.  The backend keeps at most ONE such launch pending --
+# the zero fill, then the scaled copy it turns into -- and issues it fused with the next accumulation into the same array (3
+# passes, same bits).  Every access to a device pointer (`GPUArray.ptr`), every synchronisation and every raw Buffer
+# operation flushes the pending launch first, so nothing else can observe the array before it is materialised.
+deferred = None
+
+
+def flushDeferred():
+	global deferred
+	if deferred is not None:
+		op, deferred = deferred, None
+		op.flush()
 
 
 # --------------------------------------------------------------------------------------------------------- dtypes
@@ -283,6 +301,7 @@ class Device:
 
 	@staticmethod
 	def synchronize():
+		flushDeferred()
 		check(lib.pz_device_synchronize())
 
 
@@ -397,15 +416,19 @@ class Buffer:
 		return self.ptr
 
 	def fillD8(self, value, stream=None):
+		flushDeferred()
 		check(lib.pz_memset8(self.ptr, value & 0xff, self.size, stream))
 
 	def fillD16(self, value, stream=None):
+		flushDeferred()
 		check(lib.pz_memset16(self.ptr, value & 0xffff, self.size // 2, stream))
 
 	def fillD32(self, value, stream=None):
+		flushDeferred()
 		check(lib.pz_memset32(self.ptr, value & 0xffffffff, self.size // 4, stream))
 
 	def copy(self, dst=None, allocator=None, stream=None):
+		flushDeferred()
 		if dst is None:
 			dst = Buffer(self.size, allocator=allocator)
 		elif dst.size < self.size:
@@ -414,12 +437,14 @@ class Buffer:
 		return dst
 
 	def set(self, host, stream=None):
+		flushDeferred()
 		host = np.ascontiguousarray(host)
 		if host.nbytes > self.size:
 			raise ValueError("host array is larger than the buffer")
 		check(lib.pz_memcpy_h2d(self.ptr, host.ctypes.data, host.nbytes, stream, 0))
 
 	def get(self, host, stream=None):
+		flushDeferred()
 		check(lib.pz_memcpy_d2h(host.ctypes.data, self.ptr, min(host.nbytes, self.size), stream, 0))
 		return host
 
@@ -473,6 +498,7 @@ class Stream:
 		self.handle = h.value
 
 	def synchronize(self):
+		flushDeferred()
 		check(lib.pz_stream_synchronize(self.handle))
 
 	def __del__(self):
@@ -484,9 +510,30 @@ class Stream:
 			pass
 
 
+# scalars that change from step to step (batch-norm running-average factor, bias-corrected learning rates ...) are frozen into
+# a captured graph: StepGraph records them while it warms the step up and captures only once they repeat
+scalarTrace = None
+
+
+def traceScalar(tag, *values):
+	if scalarTrace is not None:
+		scalarTrace.append((tag, ) + tuple(float(v) for v in values))
+
+
+_graphsInFlight = []
+
+
+def syncGraphs():
+	"""host reads / writes of device memory go through the legacy stream, which does not wait for the (non-blocking) stream a
+	StepGraph replays on: synchronise every graph with replays in flight first (GPUArray.get / set call this)"""
+	while _graphsInFlight:
+		_graphsInFlight.pop().stream.synchronize()
+
+
 def setDefaultStream(stream):
 	"""Route every operator call that does not name a stream (all of the reference API) to `stream`; None restores the legacy
 	default stream."""
+	flushDeferred()
 	check(lib.pz_set_default_stream(stream.handle if stream is not None else None))
 
 
@@ -494,41 +541,66 @@ class StepGraph:
 	"""One training / inference step captured as a CUDA graph.
 
 	`fn` is any callable driving the unchanged operator API (e.g. zeroGradParams + net(data) + net.backward(grad) +
-	optimizer.update() + net.reset()).  It is run `warmup` times eagerly on a private stream -- so that the memory pool holds
-	every block the step needs, scratch buffers exist and step-count dependent scalars (batch-norm factor) have reached their
-	steady state -- then once more under stream capture.  `launch()` replays the captured kernels with a single host call;
-	device pointers, shapes and scalars are those of the captured run.
+	optimizer.update() + net.reset()).  It is run eagerly on a private stream at least `warmup` times -- so that the memory pool
+	holds every block the step needs and the library scratch has its final size -- and further until the scalars that the step
+	hands to the kernels (batch-norm running-average factor max(1/n, minFactor), optimizer rates) repeat from one run to the
+	next, at most `maxWarmup` times; a step whose scalars never settle (Adam's bias-corrected rate) cannot be replayed and raises.
+	Then it is run once more under stream capture.  `launch()` replays the captured kernels with a single host call: device
+	pointers, shapes and scalars are those of the captured run; the dropout generator keeps its offset on the device, so replays
+	draw fresh masks.  `GPUArray.get()` / `set()` wait for replays in flight; other host-side synchronisation is the caller's
+	(`synchronize()`).
 	"""
 
-	def __init__(self, fn, warmup=2):
+	def __init__(self, fn, warmup=2, maxWarmup=64):
+		global scalarTrace
 		self.stream = Stream()
 		self.exec = None
 		setDefaultStream(self.stream)
 		try:
-			for _ in range(warmup):
-				fn()
+			previous, runs = None, 0
+			while True:
+				scalarTrace = []
+				try:
+					fn()
+				finally:
+					trace, scalarTrace = scalarTrace, None
+				runs += 1
+				if runs >= warmup and trace == previous:
+					break
+				if runs >= maxWarmup:
+					changing = sorted({a[0] for a, b in zip(trace, previous or []) if a != b}) or ["the launch sequence"]
+					raise RuntimeError("the step cannot be captured: %s still change(s) from step to step after %d warm-up runs"
+									   % (", ".join(changing), runs))
+				previous = trace
 			self.stream.synchronize()
 			check(lib.pz_graph_begin(self.stream.handle))
 			try:
 				fn()
+				flushDeferred()
 			finally:
 				h = c_void_p()
 				status = lib.pz_graph_end(self.stream.handle, byref(h))
 			check(status)
 			self.exec = h.value
+			self.warmupRuns = runs
 		finally:
 			setDefaultStream(None)
 
 	def launch(self):
+		flushDeferred()
 		check(lib.pz_graph_launch(self.exec, self.stream.handle))
+		if self not in _graphsInFlight:
+			_graphsInFlight.append(self)
 
 	def synchronize(self):
 		self.stream.synchronize()
+		if self in _graphsInFlight:
+			_graphsInFlight.remove(self)
 
 	def destroy(self):
 		"""Release the graph (graphs that captured NCCL collectives must be destroyed BEFORE their communicator)."""
 		if self.exec:
-			self.stream.synchronize()
+			self.synchronize()
 			lib.pz_graph_destroy(self.exec)
 			self.exec = None
 
@@ -546,6 +618,7 @@ class Event:
 		self.handle = h.value
 
 	def record(self, stream=None):
+		flushDeferred()
 		check(lib.pz_event_record(self.handle, stream.handle if stream is not None else None))
 
 	def synchronize(self):

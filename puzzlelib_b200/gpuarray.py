@@ -30,8 +30,46 @@ def _cstrides(shape, itemsize):
 	return tuple(strides)
 
 
+DEFER_MIN_BYTES = 1 << 20
+
+
+class DeferredFill:
+	"""The one launch the backend may hold back (see driver.flushDeferred): `y.fill(0)`, which `accumulate` turns into the scaled
+	copy `y = 0 + a * x` and then into the fused `y = (0 + a1 * x1) + a2 * x2`.  Holds references so that neither array's memory
+	can return to the pool while the launch is pending."""
+	__slots__ = ["y", "x", "alpha"]
+
+	def __init__(self, y):
+		self.y, self.x, self.alpha = y, None, 0.0
+
+	def matches(self, y, x):
+		return self.y._ptr == y._ptr and self.y.nbytes == y.nbytes and self.y.dtype == y.dtype and x.dtype == y.dtype and \
+			x.size == y.size and x.contiguous and y.contiguous and (x._ptr + x.nbytes <= y._ptr or y._ptr + y.nbytes <= x._ptr)
+
+	def flush(self):
+		y = self.y
+		if self.x is None:
+			check(lib.pz_memset8(y._ptr, 0, y.nbytes, None))
+		else:
+			check(lib.pz_axpy2(dtypeCode(y.dtype), y._ptr, self.x._ptr, self.alpha, None, 0.0, y.size, None))
+
+
+def accumulate(y, x, alpha):
+	"""y += alpha * x (the reference's toVectorAddVector kernel) with the pending-fill fusion; returns True when the launch was
+	absorbed or issued here"""
+	op = driver.deferred
+	if op is None or not op.matches(y, x):
+		return False
+	if op.x is None:
+		op.x, op.alpha = x, float(alpha)                      # y = 0 + alpha * x, still pending
+		return True
+	driver.deferred = None
+	check(lib.pz_axpy2(dtypeCode(y.dtype), y._ptr, op.x._ptr, op.alpha, x._ptr, float(alpha), y.size, None))
+	return True
+
+
 class GPUArray:
-	__slots__ = ["shape", "strides", "dtype", "gpudata", "ptr", "size", "contiguous", "__weakref__"]
+	__slots__ = ["shape", "strides", "dtype", "gpudata", "_ptr", "size", "contiguous", "__weakref__"]
 
 	MAXDIMS = 32  # reference: Driver.h:234-237
 
@@ -63,7 +101,7 @@ class GPUArray:
 			raise ValueError("gpudata is too small for the requested array")
 
 		self.gpudata = gpudata
-		self.ptr = gpudata.ptr + offset
+		self._ptr = gpudata.ptr + offset
 
 	# ------------------------------------------------------------------------------------------ constructors
 	@staticmethod
@@ -94,6 +132,14 @@ class GPUArray:
 		return ary
 
 	# ------------------------------------------------------------------------------------------ properties
+	@property
+	def ptr(self):
+		"""device address of the first element.  Handing it out means somebody is about to touch device memory: a pending
+		deferred fill (driver.flushDeferred) is issued first"""
+		if driver.deferred is not None:
+			driver.flushDeferred()
+		return self._ptr
+
 	@property
 	def ndim(self):
 		return len(self.shape)
@@ -171,6 +217,7 @@ class GPUArray:
 		host = np.empty(self.shape, dtype=self.dtype)
 		if self.size == 0:
 			return host
+		driver.syncGraphs()
 
 		if self.contiguous:
 			check(lib.pz_memcpy_d2h(host.ctypes.data, self.ptr, self.nbytes, None, 0))
@@ -197,6 +244,7 @@ class GPUArray:
 
 		if self.size == 0:
 			return self
+		driver.syncGraphs()
 
 		if self.contiguous:
 			check(lib.pz_memcpy_h2d(self.ptr, host.ctypes.data, host.nbytes, None, 0))
@@ -254,12 +302,12 @@ class GPUArray:
 			raise ValueError("total size of new gpuarray must be unchanged")
 
 		if self.contiguous:
-			return GPUArray(shape, self.dtype, gpudata=self.gpudata, offset=self.ptr - self.gpudata.ptr)
+			return GPUArray(shape, self.dtype, gpudata=self.gpudata, offset=self._ptr - self.gpudata.ptr)
 
 		strides = self._reshapeStrides(shape)
 		if strides is None:
 			raise ValueError("cannot reshape non-contiguous gpuarray without a copy")
-		return GPUArray(shape, self.dtype, gpudata=self.gpudata, strides=strides, offset=self.ptr - self.gpudata.ptr)
+		return GPUArray(shape, self.dtype, gpudata=self.gpudata, strides=strides, offset=self._ptr - self.gpudata.ptr)
 
 	def _reshapeStrides(self, newshape):
 		# numpy's no-copy reshape rule
@@ -305,7 +353,7 @@ class GPUArray:
 			if lastbytes % dtype.itemsize != 0:
 				raise ValueError("last axis size is not divisible by the new itemsize")
 			shape = self.shape[:-1] + (lastbytes // dtype.itemsize, )
-		return GPUArray(shape, dtype, gpudata=self.gpudata, offset=self.ptr - self.gpudata.ptr)
+		return GPUArray(shape, dtype, gpudata=self.gpudata, offset=self._ptr - self.gpudata.ptr)
 
 	def __getitem__(self, key):
 		if not isinstance(key, tuple):
@@ -355,7 +403,7 @@ class GPUArray:
 		shape.extend(self.shape[axis:])
 		strides.extend(self.strides[axis:])
 
-		return GPUArray(shape, self.dtype, gpudata=self.gpudata, strides=strides, offset=self.ptr - self.gpudata.ptr + offset)
+		return GPUArray(shape, self.dtype, gpudata=self.gpudata, strides=strides, offset=self._ptr - self.gpudata.ptr + offset)
 
 	def __setitem__(self, key, value):
 		self[key].set(value)
@@ -390,6 +438,12 @@ class GPUArray:
 
 		item = np.array(val).astype(self.dtype)
 		itemsize = self.dtype.itemsize
+
+		if self.nbytes >= DEFER_MIN_BYTES and itemsize in (2, 4) and not item.tobytes().strip(b"\0"):
+			# a zero fill of a large tensor: keep it pending, the accumulation that follows usually absorbs it
+			driver.flushDeferred()
+			driver.deferred = DeferredFill(self)
+			return self
 
 		if itemsize == 4:
 			check(lib.pz_memset32(self.ptr, int(item.view(np.uint32)), self.size, None))

@@ -121,6 +121,7 @@ class NodeInfo:
 	def broadcastBuffer(self, name, buffer):
 		# reference: Grid.py:114-121,146-150 -- rank 0's bytes replace everybody's
 		if self.gridsize > 1:
+			driver.flushDeferred()
 			self.comm.broadcastBytes(buffer.ptr, buffer.size, root=0)
 
 	def sumTensor(self, name, tensor):

@@ -373,7 +373,8 @@ def test_step_graph_replay_matches_eager_steps(M):
 	def build():
 		np.random.seed(21)
 		net = M.Sequential()
-		# minFactor = 1: the running-average factor max(1/n, minFactor) is the same scalar at every step, as a graph requires
+		# minFactor = 1: the running-average factor max(1/n, minFactor) is the same scalar at every step, so the eager runs below
+		# do the same number of steps as the graph (which otherwise keeps warming up until the factor settles)
 		net.append(M.Conv2D(8, 16, 3, pad=1, initscheme="he")).append(M.BatchNorm2D(16, minFactor=1.0)).append(M.Activation(M.relu))
 		net.append(M.MaxPool2D(2, 2)).append(M.Conv2D(16, 32, 1, useBias=False, initscheme="he")).append(M.AvgPool2D(4, 4))
 		net.append(M.Flatten()).append(M.Linear(32 * 2 * 2, 10, initscheme="he")).append(M.SoftMax())
@@ -421,3 +422,57 @@ def test_step_graph_replay_matches_eager_steps(M):
 	assert relerr(net2.graph[7].W.get(), net1.graph[7].W.get()) < tol
 	assert relerr(net2.graph[1].mean.get(), net1.graph[1].mean.get()) < tol
 	graph.destroy()
+
+
+def test_step_graph_warms_until_scalars_settle_and_redraws_dropout(M):
+	"""a captured step freezes the scalars its kernels were handed.  StepGraph keeps warming the step up until they
+	repeat (the batch-norm factor max(1/n, minFactor) does after 1/minFactor steps), refuses a step whose scalars never settle
+	(Adam's bias-corrected rate), and dropout masks differ from replay to replay (the generator offset lives on the device)."""
+	from puzzlelib_b200 import driver
+	from PuzzleLib.Optimizers.Adam import Adam
+	from PuzzleLib.Optimizers.MomentumSGD import MomentumSGD
+
+	rng = np.random.RandomState(1)
+	x = M.gpuarray.to_gpu(rng.randn(8, 4, 6, 6).astype(np.float32))
+	gy = M.gpuarray.to_gpu(rng.randn(8, 4, 6, 6).astype(np.float32))
+
+	np.random.seed(2)
+	net = M.Sequential()
+	net.append(M.Conv2D(4, 4, 3, pad=1, initscheme="he")).append(M.BatchNorm2D(4, minFactor=0.25)).append(M.Dropout(p=0.5))
+	opt = MomentumSGD(learnRate=1e-2, momRate=0.9)
+	opt.setupOn(net, useGlobalState=True)
+
+	masks = []
+
+	def step():
+		opt.zeroGradParams()
+		net(x)
+		net.backward(gy)
+		opt.update()
+
+	graph = driver.StepGraph(step, warmup=2)
+	assert graph.warmupRuns >= 5                   # factor 1, 1/2, 1/3, 1/4 = minFactor, and one repeat
+	for _ in range(3):
+		graph.launch()
+		graph.synchronize()
+		masks.append(net.graph[2].data.get() == 0)
+	assert not np.array_equal(masks[0], masks[1]) and not np.array_equal(masks[1], masks[2])
+	# host reads wait for replays in flight
+	graph.launch()
+	w = net.graph[0].W.get()
+	assert np.isfinite(w).all()
+	graph.destroy()
+
+	adam = Adam(alpha=1e-3)
+	lin = M.Linear(6, 3, initscheme="he")
+	adam.setupOn(lin, useGlobalState=True)
+	xs, gs = M.gpuarray.to_gpu(rng.randn(5, 6).astype(np.float32)), M.gpuarray.to_gpu(rng.randn(5, 3).astype(np.float32))
+
+	def adamStep():
+		adam.zeroGradParams()
+		lin(xs)
+		lin.backward(gs)
+		adam.update()
+
+	with pytest.raises(RuntimeError, match="Adam"):
+		driver.StepGraph(adamStep, warmup=2, maxWarmup=6)

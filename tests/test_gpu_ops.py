@@ -275,7 +275,8 @@ def test_gemm_bias_epilogue_and_errors(bnd):
 
 
 # ================================================================================================ batch norm
-@pytest.mark.parametrize("shape", [(4, 5, 2, 3), (16, 64, 14, 14), (8, 3, 33, 35), (2, 7, 1, 1), (32, 256, 7, 7), (3, 2, 112, 112)])
+@pytest.mark.parametrize("shape", [(4, 5, 2, 3), (16, 64, 14, 14), (8, 3, 33, 35), (2, 7, 1, 1), (32, 256, 7, 7), (3, 2, 112, 112),
+								   (64, 8, 55, 55), (5, 3, 7, 7), (64, 12, 28, 28), (1, 4, 9, 9), (13, 300, 3, 5), (64, 2, 112, 112)])
 def test_batchnorm_train_bwd_infer(bnd, shape):
 	rng = np.random.RandomState(sum(shape))
 	N, C = shape[:2]
@@ -307,6 +308,60 @@ def test_batchnorm_train_bwd_infer(bnd, shape):
 	res = bnd.dnn.batchNormNd(data, G(bnd, mean0), G(bnd, var0), G(bnd, scale), G(bnd, bias), 1e-5, 0, True, out=data)
 	assert res is data                                                   # in-place inference (BatchNormND inplace flag)
 	assert np.allclose(data.get(), ops.batchnorm_infer(x, scale, bias, mean0, var0), atol=2e-5, rtol=1e-5)
+
+
+@pytest.mark.parametrize("dtname", ["float16", "bfloat16"])
+@pytest.mark.parametrize("shape", [(8, 6, 7, 7), (16, 32, 14, 14), (4, 5, 55, 55), (64, 4, 28, 28)])
+def test_batchnorm_16bit(bnd, shape, dtname):
+	"""16-bit activations, fp32 parameters and statistics (CuDnnNorm.c:118-121); odd planes are not 16-byte aligned"""
+	from puzzlelib_b200.driver import bfloat16
+	dt = np.dtype(np.float16) if dtname == "float16" else bfloat16
+	tol = 4e-3 if dtname == "float16" else 3e-2
+	rng = np.random.RandomState(sum(shape))
+	C = shape[1]
+	x = (rng.randn(*shape) + 0.5).astype(dt)
+	dy = rng.randn(*shape).astype(dt)
+	scale, bias = (1 + 0.2 * rng.randn(C)).astype(np.float32), rng.randn(C).astype(np.float32)
+	zero, one = np.zeros(C, np.float32), np.ones(C, np.float32)
+	x32, dy32 = x.astype(np.float32), dy.astype(np.float32)
+
+	y, mu, inv, newmean, newvar = ops.batchnorm_train(x32, scale, bias, zero, one, 1e-5, 1.0)
+	mean, var = G(bnd, zero), G(bnd, one)
+	out, savemean, saveinvvar = bnd.dnn.batchNormNd(G(bnd, x), mean, var, G(bnd, scale), G(bnd, bias), 1e-5, 1.0, False)
+	assert out.dtype == dt and savemean.dtype == np.float32
+	assert relerr(out.get().astype(np.float32), y) < tol
+	assert np.allclose(savemean.get(), mu, atol=1e-5) and np.allclose(saveinvvar.get(), inv, rtol=1e-5)
+	assert np.allclose(mean.get(), newmean, atol=1e-5) and np.allclose(var.get(), newvar, rtol=1e-5)
+
+	dx, dscale, dbias = ops.batchnorm_bwd(x32, dy32, scale, mu, inv)
+	ingrad, scalegrad, bgrad = bnd.dnn.batchNormNdBackward(G(bnd, dy), G(bnd, x), G(bnd, scale), savemean, saveinvvar, 1e-5)
+	assert ingrad.dtype == dt and scalegrad.dtype == np.float32
+	bar = tol * max(1.0, float(np.abs(dy32).max() * np.abs(scale).max() * inv.max()))
+	assert np.abs(ingrad.get().astype(np.float32) - dx).max() < bar
+	assert relerr(scalegrad.get(), dscale) < 1e-4 and relerr(bgrad.get(), dbias) < 1e-4
+
+
+def test_batchnorm_is_deterministic_and_works_in_place(bnd):
+	"""Statistics are reduced through fixed trees (no atomics): two runs give the same bits.  Train-mode in-place
+	normalisation (dnn.batchNormNd(..., out=data)) gives the bits of the out-of-place call."""
+	rng = np.random.RandomState(11)
+	for shape in ((64, 16, 55, 55), (32, 64, 7, 7), (6, 10, 28, 28)):
+		C = shape[1]
+		x, dy = rng.randn(*shape).astype(np.float32), rng.randn(*shape).astype(np.float32)
+		scale, bias = rng.randn(C).astype(np.float32), rng.randn(C).astype(np.float32)
+		runs = []
+		for _ in range(2):
+			mean, var = G(bnd, np.zeros(C, np.float32)), G(bnd, np.ones(C, np.float32))
+			out, sm, siv = bnd.dnn.batchNormNd(G(bnd, x), mean, var, G(bnd, scale), G(bnd, bias), 1e-5, 0.5, False)
+			dx, ds, db = bnd.dnn.batchNormNdBackward(G(bnd, dy), G(bnd, x), G(bnd, scale), sm, siv, 1e-5)
+			runs.append([a.get() for a in (out, sm, siv, mean, var, dx, ds, db)])
+		for a, b in zip(*runs):
+			assert np.array_equal(a, b)
+
+		data = G(bnd, x)
+		mean, var = G(bnd, np.zeros(C, np.float32)), G(bnd, np.ones(C, np.float32))
+		res, _, _ = bnd.dnn.batchNormNd(data, mean, var, G(bnd, scale), G(bnd, bias), 1e-5, 0.5, False, out=data)
+		assert res is data and np.array_equal(data.get(), runs[0][0])
 
 
 def test_batchnorm_large_mean_is_stable(bnd):
@@ -1135,3 +1190,59 @@ def test_matvec_grouped(bnd, dtype, tol):
 			assert np.abs(out.get() - ref).max() < 2 * tol * max(1.0, np.abs(ref).max())
 	with pytest.raises(ValueError):
 		bnd.matmod.matvec(G(bnd, mat), G(bnd, vec[:, :3]), axis=0)
+
+
+# ================================================================================================ deferred zero fill
+@pytest.mark.parametrize("dtname", ["float32", "float16"])
+def test_deferred_fill_fuses_with_accumulation_and_keeps_the_bits(bnd, dtname):
+	"""`y.fill(0); y += a1*x1; y += a2*x2` (Modules/Add.py:15-23, Replicate.py:18-29) is issued as ONE launch; the result must
+	be bit-identical to the three launches, and nothing may observe y (or move x) before the pending launch is flushed."""
+	from puzzlelib_b200 import driver
+	dt = np.dtype(dtname)
+	rng = np.random.RandomState(5)
+	n = (1 << 19) + 7                                   # above the deferral threshold for both types, odd tail
+	x1, x2, x3 = (rng.randn(n).astype(dt) for _ in range(3))
+	g1, g2, g3 = G(bnd, x1), G(bnd, x2), G(bnd, x3)
+	axpy = bnd.toVectorAddVectorKer(dt)
+
+	def reference(arrays, alphas):
+		y = bnd.GPUArray.empty((n, ), dt)
+		check = driver.lib.pz_memset8(y.ptr, 0, y.nbytes, None)
+		assert check == 0
+		for a, alpha in zip(arrays, alphas):
+			assert driver.lib.pz_axpy(driver.dtypeCode(dt), y.ptr, a.ptr, alpha, n, None) == 0
+		return y.get()
+
+	for arrays, alphas in (((g1, g2), (1.0, 1.0)), ((g1, g2), (0.5, -1.25)), ((g1, g2, g3), (1.0, 1.0, 2.0)), ((g1, ), (3.0, ))):
+		want = reference(arrays, alphas)
+		launches = driver.launchCount()
+		y = bnd.GPUArray.empty((n, ), dt)
+		y.fill(0)
+		assert driver.deferred is not None                              # held back
+		for a, alpha in zip(arrays, alphas):
+			axpy(y.ravel(), a.ravel(), alpha)                            # views of the same memory, like the reference modules
+		got = y.get()
+		assert driver.deferred is None
+		assert np.array_equal(got.view(np.uint8), want.view(np.uint8)), (alphas, dtname)
+		assert driver.launchCount() - launches == max(1, len(arrays) - 1)
+
+	# hazards: the source changes after the accumulation was absorbed -> the pending launch must have run first
+	y = bnd.GPUArray.empty((n, ), dt)
+	y.fill(0)
+	src = G(bnd, x1)
+	axpy(y, src, 1.0)
+	src.fill(7)
+	assert np.array_equal(y.get(), x1)
+	# a pending fill is visible to every other consumer
+	y.fill(0)
+	assert not y.get().any()
+	z = bnd.GPUArray.empty((n, ), dt)
+	z.fill(0)
+	w = z + g1                                                           # not the fused kernel: plain read of a pending array
+	assert np.array_equal(w.get(), x1)
+	# a small or non-zero fill is not deferred
+	small = bnd.GPUArray.empty((16, ), dt)
+	small.fill(0)
+	assert driver.deferred is None
+	y.fill(1)
+	assert driver.deferred is None and np.array_equal(y.get(), np.ones(n, dt))

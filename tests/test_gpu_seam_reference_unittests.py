@@ -17,6 +17,10 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
+# fails IDENTICALLY on the reference's own CUDA backend on this stack (profiles/r02_ref_unittests_ref.json): its fp16 host check
+# recomputes the derivative from the unrounded host output (Modules/Activation.py:150-159)
+KNOWN_REFERENCE_FAILURES = {"Modules/Activation"}
+
 MODULES = [
 	"Modules/Activation", "Modules/Add", "Modules/AvgPool1D", "Modules/AvgPool2D", "Modules/AvgPool3D", "Modules/BatchNorm",
 	"Modules/BatchNorm1D", "Modules/BatchNorm2D", "Modules/BatchNorm3D", "Modules/Cast", "Modules/Concat", "Modules/CrossMapLRN",
@@ -41,7 +45,7 @@ TENSOR_CORE = [
 WRAPPERS = ["CuDnn", "CuDnnNorm", "CuBlas", "CuDnnMemory"]
 
 
-def retry(fn, tries=4):
+def retry(fn, tries=20):      # Unittester.py:13 (threshold=20): unseeded inputs against np.allclose's atol=1e-8
 	for attempt in range(tries):
 		try:
 			return fn()
@@ -70,6 +74,12 @@ def runUnittest(refroot, name):
 
 @pytest.mark.parametrize("name", MODULES)
 def test_reference_unittest(refroot, name):
+	if name in KNOWN_REFERENCE_FAILURES:
+		try:
+			runUnittest(refroot, name)
+		except AssertionError:
+			pytest.xfail("the reference's own CUDA backend fails this test the same way on this stack")
+		return
 	runUnittest(refroot, name)
 
 

@@ -14,7 +14,7 @@ from puzzlelib_b200 import driver
 BN_SHAPES = [(64, 112, 1), (64, 55, 6), (256, 55, 4), (128, 28, 8), (512, 28, 5), (256, 14, 12), (1024, 14, 7), (512, 7, 6), (2048, 7, 4)]
 
 
-def timeit(fn, reps=5):
+def timeit(fn, reps=20):
 	fn()
 	e0, e1 = driver.Event(), driver.Event()
 	e0.record()
@@ -41,6 +41,7 @@ def main():
 		tag = "%dx%d" % (C, H)
 		if only and only not in "bn relu add " + tag:
 			continue
+		bnonly = only == "bn"
 		x = bnd.GPUArray.toGpu(np.random.randn(*shape).astype(f32))
 		dy = bnd.GPUArray.toGpu(np.random.randn(*shape).astype(f32))
 		out = bnd.GPUArray.empty(shape, f32)
@@ -51,6 +52,8 @@ def main():
 		sm, siv = res[1], res[2]
 		report("bn_fwd", shape, count, timeit(lambda: bnd.dnn.batchNormNd(x, mean, var, scale, bias, 1e-5, 1.0, False, 1, out=out)), 2 * E)
 		report("bn_bwd", shape, count, timeit(lambda: bnd.dnn.batchNormNdBackward(dy, x, scale, sm, siv, 1e-5, 1, out=out)), 3 * E)
+		if bnonly:
+			continue
 		relu, reluDer, add = bnd.reluKer(f32), bnd.reluDerKer(f32), bnd.addKer(f32)
 		report("relu_fwd", shape, count, timeit(lambda: relu(out, x)), 2 * E)
 		report("relu_bwd", shape, count, timeit(lambda: reluDer(out, dy, x)), 3 * E)
