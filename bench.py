@@ -335,6 +335,16 @@ def gpuArm(args):
 	driver.profileEnable(False)
 	families = {name: driver.profileCollect(name) for name in driver.PROF_FAMILIES}
 
+	# data parallelism keeps the replicas identical: after all those steps every rank must hold the same parameters, bit for bit
+	# (same initial broadcast, same averaged gradients, same update kernel)
+	checksumEqual = None
+	if node.gridsize > 1:
+		flat = [gv.data.get() for gv in optimizer.globalVar.values()]
+		chk = float(sum(np.frombuffer(a.tobytes(), np.uint32).astype(np.uint64).sum() % (1 << 52) for a in flat))
+		checksumEqual = node.rendezvous.maxValue(chk) == -node.rendezvous.maxValue(-chk)
+		if not checksumEqual:
+			raise SystemExit("data-parallel replicas diverged: parameter checksums differ across ranks")
+
 	if node.index != 0:
 		node.close()
 		return
@@ -419,6 +429,11 @@ def gpuArm(args):
 			"sample": "%d images, 1 warm-up + 1 timed fwd+bwd step of the numpy float32 oracle port (oracle/refnet.py), %.1f s; the "
 					  "reference's own numpy CPU backend cannot run conv/pool/batch-norm backward (SURVEY F5)" % (args.cpu_images, dt)
 		}
+
+	if node.gridsize > 1:
+		line["config"]["gradient_sync"] = "NCCL mean of ~24 MB gradient buckets on a communication stream, overlapped with the backward pass" \
+			if node.sync is not None else "one NCCL all-reduce after the backward pass"
+		line["config"]["param_checksum_equal_across_ranks"] = checksumEqual
 
 	if node.gridsize == 1 and not args.no_ref_gpu:
 		line["reference_gpu"] = referenceGpu(args)

@@ -96,6 +96,7 @@ int pz_stream_create(void** stream);
 int pz_stream_destroy(void* stream);
 int pz_stream_synchronize(void* stream);
 int pz_event_create(void** event);
+int pz_event_create_sync(void** event);                      /* stream-ordering only (no timing), usable under capture */
 int pz_event_destroy(void* event);
 int pz_event_record(void* event, void* stream);
 int pz_event_synchronize(void* event);
@@ -336,6 +337,9 @@ int pz_nccl_comm_init(void** comm, int nranks, int rank, const void* id128);
 int pz_nccl_comm_destroy(void* comm);
 /* in-place sum all-reduce then scale by `scale` (1/P for Grid.sumTensor's mean, Grid.py:126-133) */
 int pz_nccl_allreduce_mean(void* comm, int dtype, void* buf, int64_t count, float scale, void* stream);
+/* the mean over the ranks of `nseg` disjoint segments of a buffer as ONE grouped launch on `stream` (ncclAvg): a bucket of the
+ * overlapped gradient synchronisation (puzzlelib_b200/grid.py GradientSync; replaces the star reduce of Grid.py:123-157) */
+int pz_nccl_allreduce_avg_segments(void* comm, int dtype, void* const* ptrs, const int64_t* counts, int nseg, void* stream);
 int pz_nccl_broadcast(void* comm, int dtype, void* buf, int64_t count, int root, void* stream); /* Grid.py:114-121 */
 /* fused: all-reduce(sum) the flat gradient, then mom = mr*mom + lr*(grad/P); param += mom in one pass
  * (Optimizer.py:166-170 + MomentumSGD.py:24-27) */

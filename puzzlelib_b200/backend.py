@@ -227,6 +227,8 @@ class DnnContext:
 
 		desc = self._convDesc(data.shape, W.shape, grad.shape, stride, pad, dilation, groups)
 		code = dtypeCode(data.dtype)
+		if driver.gradientWriteHook is not None:
+			driver.gradientWriteHook(wgrad)
 		check(lib.pz_conv2d_wgrad(code, byref(desc), data.ptr, grad.ptr, wgrad.ptr, scale, momentum, None))
 
 		if not withbias:
@@ -239,6 +241,8 @@ class DnnContext:
 		else:
 			_checkOut(bgrad, (side.shape[1], ), side.dtype)
 
+		if driver.gradientWriteHook is not None:
+			driver.gradientWriteHook(bgrad)
 		check(lib.pz_bias_grad(code, side.ptr, bgrad.ptr, side.shape[0], side.shape[1], prod(side.shape[2:]), scale,
 							   momentum, None))
 		return wgrad, bgrad
@@ -534,6 +538,8 @@ class BlasContext:
 				out.fill(0)
 		else:
 			_checkOut(out, (M, N), A.dtype)
+			if driver.gradientWriteHook is not None:
+				driver.gradientWriteHook(out)
 
 		check(lib.pz_gemm(dtypeCode(A.dtype), A.ptr, B.ptr, out.ptr, M, N, K, A.shape[1], B.shape[1], N, int(transpA),
 						  int(transpB), alpha, beta, None, None))
@@ -675,6 +681,8 @@ class MatModule:
 			out = GPUArray.zeros(outshape, tensor.dtype, allocator=allocator)
 		else:
 			assert out.shape == outshape
+			if driver.gradientWriteHook is not None:
+				driver.gradientWriteHook(out)
 
 		if axis == tensor.ndim - 1:
 			z, h, w, rows = 1, prod(tensor.shape[:-1]), tensor.shape[-1], 1
@@ -1201,6 +1209,8 @@ class B200Backend:
 
 		def ker(y, x, alpha, **kwargs):
 			_noSlice(kwargs)
+			if driver.gradientWriteHook is not None:
+				driver.gradientWriteHook(y)
 			if driver.deferred is not None and gpuarray.accumulate(y, x, alpha):
 				return          # absorbed by / fused with the pending zero fill of y (Add.py:15-23, Replicate.py:18-29)
 			check(lib.pz_axpy(dt, y.ptr, x.ptr, float(alpha), y.size, None))
@@ -1213,6 +1223,8 @@ class B200Backend:
 
 		def ker(out, x, alpha, y, beta, **kwargs):
 			slc = _slice(kwargs, out.size)
+			if driver.gradientWriteHook is not None:
+				driver.gradientWriteHook(out)
 			if slc is None:
 				check(lib.pz_axpby(dt, out.ptr, x.ptr, float(alpha), y.ptr, float(beta), out.size, None))
 			else:

@@ -24,6 +24,8 @@ struct NcclApi {
 	ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
 	const char* (*GetErrorString)(ncclResult_t) = nullptr;
 	ncclResult_t (*GetVersion)(int*) = nullptr;
+	ncclResult_t (*GroupStart)() = nullptr;
+	ncclResult_t (*GroupEnd)() = nullptr;
 };
 
 NcclApi g_api;
@@ -56,6 +58,8 @@ int load_api()
 	PZ_SYM(Broadcast, "ncclBroadcast")
 	PZ_SYM(GetErrorString, "ncclGetErrorString")
 	PZ_SYM(GetVersion, "ncclGetVersion")
+	PZ_SYM(GroupStart, "ncclGroupStart")
+	PZ_SYM(GroupEnd, "ncclGroupEnd")
 #undef PZ_SYM
 	g_api.handle = h;
 	return PZ_OK;
@@ -198,6 +202,34 @@ int pz_nccl_allreduce_mean(void* comm, int dtype, void* buf, int64_t count, floa
 	if (count <= 0) return PZ_OK;
 	PZ_CHECK_NCCL(g_api.AllReduce(buf, buf, (size_t)count, dt, ncclSum, (ncclComm_t)comm, pz_stream(stream)));
 	if (scale != 1.0f) return pz_scale_shift(dtype, buf, buf, scale, 0.0f, count, stream);
+	return PZ_OK;
+}
+
+// One bucket of the overlapped gradient synchronisation: the mean over the ranks of `nseg` disjoint segments of the flat
+// gradient buffer, as ONE grouped NCCL launch (ncclAvg) on `stream` -- the communication stream of grid.GradientSync, which
+// runs it while the compute stream is still producing the gradients of the earlier layers.
+int pz_nccl_allreduce_avg_segments(void* comm, int dtype, void* const* ptrs, const int64_t* counts, int nseg, void* stream)
+{
+	int st = load_api();
+	if (st != PZ_OK) return st;
+	ncclDataType_t dt;
+	st = nccl_dtype(dtype, &dt);
+	if (st != PZ_OK) return st;
+	PZ_REQUIRE(nseg >= 0 && (nseg == 0 || (ptrs != nullptr && counts != nullptr)), "nccl: bad segment list");
+	PZ_REQUIRE(stream != nullptr, "nccl: the segment all-reduce needs an explicit stream");
+	if (nseg == 0) return PZ_OK;
+	PZ_CHECK_NCCL(g_api.GroupStart());
+	for (int i = 0; i < nseg; i++) {
+		if (counts[i] <= 0) continue;
+		ncclResult_t r = g_api.AllReduce(ptrs[i], ptrs[i], (size_t)counts[i], dt, ncclAvg, (ncclComm_t)comm, (cudaStream_t)stream);
+		if (r != ncclSuccess) {
+			g_api.GroupEnd();
+			pz_set_error(PZ_ERR_NCCL, "%s (%s:%d)", g_api.GetErrorString(r), __FILE__, __LINE__);
+			return PZ_ERR_NCCL;
+		}
+	}
+	PZ_CHECK_NCCL(g_api.GroupEnd());
+	pz_count_launch(1);
 	return PZ_OK;
 }
 

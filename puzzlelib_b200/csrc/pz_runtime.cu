@@ -429,6 +429,14 @@ int pz_event_create(void** event)
 	*event = (void*)e;
 	return PZ_OK;
 }
+// an event used only to order streams (fork / join, also under graph capture): no timing
+int pz_event_create_sync(void** event)
+{
+	cudaEvent_t e;
+	PZ_CHECK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+	*event = (void*)e;
+	return PZ_OK;
+}
 int pz_event_destroy(void* event) { PZ_CHECK_CUDA(cudaEventDestroy((cudaEvent_t)event)); return PZ_OK; }
 int pz_event_record(void* event, void* stream) { PZ_CHECK_CUDA(cudaEventRecord((cudaEvent_t)event, pz_stream(stream))); return PZ_OK; }
 int pz_event_synchronize(void* event) { PZ_CHECK_CUDA(cudaEventSynchronize((cudaEvent_t)event)); return PZ_OK; }

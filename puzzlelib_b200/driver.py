@@ -101,6 +101,7 @@ _SIGNATURES = {
 	"pz_stream_destroy": [_P],
 	"pz_stream_synchronize": [_P],
 	"pz_event_create": [POINTER(_P)],
+	"pz_event_create_sync": [POINTER(_P)],
 	"pz_event_destroy": [_P],
 	"pz_event_record": [_P, _P],
 	"pz_event_synchronize": [_P],
@@ -176,6 +177,7 @@ _SIGNATURES = {
 	"pz_nccl_comm_destroy": [_P],
 	"pz_nccl_allreduce_mean": [_P, c_int, _P, c_int64, c_float, _P],
 	"pz_nccl_broadcast": [_P, c_int, _P, c_int64, c_int, _P],
+	"pz_nccl_allreduce_avg_segments": [_P, c_int, POINTER(_P), POINTER(c_int64), c_int, _P],
 	"pz_nccl_allreduce_sgd_momentum": [_P, c_int, _P, _P, _P, c_int64, c_float, c_float, c_float, _P],
 }
 
@@ -497,6 +499,9 @@ class Stream:
 		check(lib.pz_stream_create(byref(h)))
 		self.handle = h.value
 
+	def waitEvent(self, event):
+		check(lib.pz_stream_wait_event(self.handle, event.handle))
+
 	def synchronize(self):
 		flushDeferred()
 		check(lib.pz_stream_synchronize(self.handle))
@@ -530,10 +535,19 @@ def syncGraphs():
 		_graphsInFlight.pop().stream.synchronize()
 
 
+currentStream = None          # the Stream every operator call runs on (None: the legacy default stream)
+
+# hook of the data-parallel gradient synchronisation (grid.GradientSync.noteWrite): called with every array a backend op is
+# about to write parameter gradients into; None outside a grid
+gradientWriteHook = None
+
+
 def setDefaultStream(stream):
 	"""Route every operator call that does not name a stream (all of the reference API) to `stream`; None restores the legacy
 	default stream."""
+	global currentStream
 	flushDeferred()
+	currentStream = stream
 	check(lib.pz_set_default_stream(stream.handle if stream is not None else None))
 
 
@@ -612,9 +626,9 @@ class StepGraph:
 
 
 class Event:
-	def __init__(self):
+	def __init__(self, timing=True):
 		h = c_void_p()
-		check(lib.pz_event_create(byref(h)))
+		check(lib.pz_event_create(byref(h)) if timing else lib.pz_event_create_sync(byref(h)))
 		self.handle = h.value
 
 	def record(self, stream=None):

@@ -97,6 +97,126 @@ class NcclCommunicator:
 			self.handle = None
 
 
+class GradientSync:
+	"""Overlaps the gradient mean with the backward pass (the reference reduces after backward, Grid.py:123-157).
+
+	The flat gradient buffer of `Optimizer.setupGlobalState` (Optimizers/Optimizer.py:66-111) is learned from the first
+	`sumTensor` call.  From then on every backend op that writes parameter gradients (convNdBackwardParams, gemm / matsum /
+	addKer with an `out` inside the buffer) reports the range it is about to write; once `bucketBytes` of freshly written
+	ranges have piled up they are averaged over the ranks by ONE grouped NCCL launch on a communication stream, ordered after
+	the kernels that wrote them by an event, while the compute stream goes on with the earlier layers.  `finish` (the
+	reference's `sumTensor` call in `Optimizer.updateGlobalState`) reduces whatever is not known to be clean and makes the
+	compute stream wait for the communication stream.
+
+	Safety: a range that is written again after it was reduced (accumulation into a shared variable) is simply dirty again --
+	the mean of (mean(g1) + g2_r) over the ranks is mean(g1) + mean(g2), so reducing twice is exact; the writer first waits for
+	a reduction of that range still in flight.  Ranges nobody reported are never assumed clean.  The kernels and the NCCL
+	launches of a step are the same on every rank in the same order (same model, same shapes), as NCCL requires."""
+
+	def __init__(self, comm, bucketBytes=24 << 20):
+		self.comm = comm
+		self.bucketBytes = bucketBytes
+		self.regions = {}                # ptr of the flat buffer -> [ptr, nbytes, dtype, clean ranges, dirty ranges, dirty bytes]
+		self.stream = driver.Stream()
+		self.inflight = []               # (event, [(lo, hi)]) of buckets whose reduction may still be running
+		self.launches = 0
+
+	# ---- range bookkeeping (byte addresses, half-open)
+	@staticmethod
+	def _merge(ranges):
+		out = []
+		for lo, hi in sorted(ranges):
+			if out and lo <= out[-1][1]:
+				out[-1][1] = max(out[-1][1], hi)
+			else:
+				out.append([lo, hi])
+		return out
+
+	@staticmethod
+	def _subtract(ranges, cut):
+		lo, hi = cut
+		out = []
+		for a, b in ranges:
+			if b <= lo or a >= hi:
+				out.append([a, b])
+			else:
+				if a < lo:
+					out.append([a, lo])
+				if b > hi:
+					out.append([hi, b])
+		return out
+
+	def _region(self, ptr):
+		for reg in self.regions.values():
+			if reg[0] <= ptr < reg[0] + reg[1]:
+				return reg
+		return None
+
+	def noteWrite(self, ary):
+		"""`ary` (a view of a flat gradient buffer, or anything else) is about to be written by a kernel that the caller enqueues
+		on the compute stream right AFTER this call"""
+		reg = self._region(ary._ptr)
+		if reg is None:
+			return
+		# the ranges reported so far have all their writers enqueued: if a bucket is full, send it off now (the range reported
+		# by THIS call is not part of it -- its writer is not on the stream yet)
+		if reg[5] >= self.bucketBytes:
+			self._launch(reg, self._merge(reg[4]))
+			reg[3] = self._merge(reg[3] + reg[4])
+			reg[4], reg[5] = [], 0
+		lo, hi = ary._ptr, ary._ptr + ary.nbytes
+		# a reduction of this range still in flight must finish before the range changes under it
+		for event, ranges in self.inflight:
+			if any(a < hi and lo < b for a, b in ranges):
+				check(lib.pz_stream_wait_event(None, event.handle))
+		reg[3] = self._subtract(reg[3], (lo, hi))
+		reg[4].append([lo, hi])
+		reg[5] += hi - lo
+
+	def _launch(self, reg, ranges):
+		if not ranges:
+			return
+		itemsize = reg[2].itemsize
+		n = len(ranges)
+		ptrs = (ctypes.c_void_p * n)(*[lo for lo, _ in ranges])
+		counts = (ctypes.c_int64 * n)(*[(hi - lo) // itemsize for lo, hi in ranges])
+		ready = driver.Event(timing=False)
+		ready.record()                                   # after the kernels that produced these gradients (compute stream)
+		self.stream.waitEvent(ready)
+		check(lib.pz_nccl_allreduce_avg_segments(self.comm.handle, dtypeCode(reg[2]), ptrs, counts, n, self.stream.handle))
+		done = driver.Event(timing=False)
+		done.record(self.stream)
+		self.inflight.append((done, ranges))
+		self.launches += 1
+
+	def finish(self, tensor):
+		"""the reference's sumTensor(name, tensor): on return (in stream order) `tensor` holds the mean over the ranks"""
+		key = tensor._ptr
+		reg = self.regions.get(key)
+		if reg is None or reg[1] != tensor.nbytes:
+			# first step with this buffer (or it changed): reduce all of it, remember the region for the next steps
+			reg = [key, tensor.nbytes, tensor.dtype, [], [], 0]
+			self.regions[key] = reg
+			todo = [[key, key + tensor.nbytes]]
+		else:
+			# everything that is not known to be clean: the complement of the clean ranges
+			todo, cursor = [], key
+			for lo, hi in self._merge(reg[3]):
+				if lo > cursor:
+					todo.append([cursor, lo])
+				cursor = max(cursor, hi)
+			if cursor < key + tensor.nbytes:
+				todo.append([cursor, key + tensor.nbytes])
+		self._launch(reg, todo)
+		for event, _ in self.inflight:                      # join: the update kernel runs after every bucket
+			check(lib.pz_stream_wait_event(None, event.handle))
+		self.inflight = []
+		reg[3], reg[4], reg[5] = [], [], 0                   # next step: nothing is clean until it has been reduced again
+
+	def close(self):
+		self.regions, self.inflight = {}, []
+
+
 class NodeInfo:
 	"""reference: Grid.py:38-157 (ParentNode / ChildNode collapse into one symmetric class: NCCL has no parent)"""
 
@@ -107,11 +227,16 @@ class NodeInfo:
 
 		self.rendezvous = rendezvous
 		self.comm = comm
+		self.sync = None
 
-	def attach(self):
-		"""Create the NCCL communicator; call after the device of this process has been selected."""
+	def attach(self, overlap=True):
+		"""Create the NCCL communicator; call after the device of this process has been selected.  `overlap`: average gradient
+		buckets on a communication stream while the backward pass is still running (GradientSync)."""
 		if self.comm is None and self.gridsize > 1:
 			self.comm = NcclCommunicator(self.rendezvous)
+		if self.gridsize > 1 and overlap and os.environ.get("PZ_GRID_NO_OVERLAP") is None:
+			self.sync = GradientSync(self.comm)
+			driver.gradientWriteHook = self.sync.noteWrite
 		return self
 
 	def meanValue(self, value):
@@ -127,7 +252,10 @@ class NodeInfo:
 	def sumTensor(self, name, tensor):
 		# reference: Grid.py:123-135,153-157 -- despite the name the result is the MEAN over the grid (beta = 1 / P)
 		if self.gridsize > 1:
-			self.comm.allReduceMean(tensor)
+			if self.sync is not None:
+				self.sync.finish(tensor)
+			else:
+				self.comm.allReduceMean(tensor)
 
 	def sumTensorAndMomentumSGD(self, param, grad, mom, learnRate, momRate):
 		if self.gridsize > 1:
@@ -142,6 +270,10 @@ class NodeInfo:
 			self.rendezvous.barrier()
 
 	def close(self):
+		if self.sync is not None:
+			driver.gradientWriteHook = None
+			self.sync.close()
+			self.sync = None
 		if self.comm is not None:
 			self.comm.close()
 			self.comm = None
