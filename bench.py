@@ -286,6 +286,14 @@ def gpuArm(args):
 			ms = node.rendezvous.maxValue(ms)
 		return ms
 
+	if args.profile_run:
+		# under ncu (tools/gpu_profile.sh): a few eager steps, nothing else -- every launch of the last step is a row of the launch list
+		for _ in range(args.warmup + args.steps):
+			step()
+		driver.Device.synchronize()
+		node.close()
+		return
+
 	warmup = max(10, args.warmup)                                # >= 10: the batch-norm running-average factor reaches its floor (0.1)
 	for _ in range(warmup):
 		step()
@@ -453,6 +461,7 @@ def main():
 	parser.add_argument("--cpu-images", type=int, default=8, help="bounded CPU-baseline sample (images per step)")
 	parser.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
 	parser.add_argument("--no-ref-gpu", action="store_true", help="skip the reference-CUDA-backend leg (reference_gpu)")
+	parser.add_argument("--profile-run", action="store_true", help="eager steps only, no timing / JSON: the command ncu wraps")
 	parser.add_argument("--no-graph", action="store_true", help="time the eager module API only (no CUDA-graph replay)")
 	parser.add_argument("--model", default="resnet50", choices=["resnet50", "vgg16"], help="side measurements; the headline is resnet50")
 	parser.add_argument("--dtype", default="f32", choices=["f32", "bf16", "f16"], help="storage type (side measurements)")

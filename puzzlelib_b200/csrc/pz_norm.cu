@@ -419,6 +419,7 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(const T* __restr
 // that overlap it; lanes outside the plane are masked on the way in and stored as scalars on the way out.
 struct ClusterGeo {
 	int N, C, S;
+	uint32_t plane_step;         // C * S (elements between the planes of consecutive images)
 	int CL, rows_per_cta;
 	int SP;                      // vector slots per plane (upper bound)
 	FastDiv32 spdiv;
@@ -454,6 +455,16 @@ __device__ __forceinline__ void store_streaming(T* dst, const Pack<T, VEC>& v)
 	asm volatile("st.global.cs.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w) : "memory");
 }
 
+// the first / last vector of an unaligned plane: only the lanes inside the plane are written.  Out of line on purpose -- inlined
+// it gets if-converted into the hot loop and doubles its instruction count.
+template <typename T, int VEC>
+__device__ __noinline__ void store_partial(T* dst, const Pack<T, VEC>& v, uint32_t mask)
+{
+	#pragma unroll
+	for (int e = 0; e < VEC; e++)
+		if (mask >> e & 1u) dst[e] = v.v[e];
+}
+
 // deterministic block sum of two values; result valid in every thread
 template <int THREADS>
 __device__ __forceinline__ void block_sum2(float& a, float& b, float* red /* [2 * THREADS / 32 + 2] */)
@@ -474,21 +485,49 @@ __device__ __forceinline__ void block_sum2(float& a, float& b, float* red /* [2 
 	b = red[2 * (THREADS / 32) + 1];
 }
 
-// slot -> aligned vector offset (elements) + the bit mask of its lanes that belong to the plane (0: empty slot)
+// Slot decode.  Slot s of a CTA = vector v = s % SP of its plane s / SP; the plane starts at element lo = (n*C + c)*S, the
+// vector at e0 = lo - head + v*VEC with head = lo % VEC.  Only vector 0 (when head > 0) and the vector holding the plane's end
+// (when (head + S) % VEC > 0) are partial.  The hot loops touch FULL vectors only -- no lane masks, 32-bit index math (the host
+// checks N*C*S < 2^31), about 12 integer instructions per 16-byte vector; the at most two partial vectors per plane are done
+// by a short masked loop afterwards (the kernels were issue-bound on the general decode: profiles/r02_bn_fwd_ncu_keys.txt).
 template <int VEC>
-__device__ __forceinline__ uint32_t slot_geometry(const ClusterGeo& g, int c, int n0, int slot, int nslots, long long& e0)
+struct SlotGeo {
+	uint32_t lo, head, v;
+	// full vectors of the plane: vlo <= v < vhi
+	__device__ __forceinline__ bool full(uint32_t S) const { return v >= (head > 0u ? 1u : 0u) && (v + 1u) * VEC <= head + S; }
+	__device__ __forceinline__ uint32_t e0() const { return lo - head + v * VEC; }
+};
+
+template <int VEC>
+__device__ __forceinline__ SlotGeo<VEC> slot_decode(const ClusterGeo& g, uint32_t plane0, uint32_t slot)
 {
-	if (slot >= nslots) { e0 = 0; return 0u; }
-	const uint32_t row = fdiv32((uint32_t)slot, g.spdiv);
-	const int v = slot - (int)row * g.SP;
-	const long long lo = ((long long)(n0 + (int)row) * g.C + c) * g.S;       // first element of the plane
-	e0 = (lo & ~(long long)(VEC - 1)) + (long long)v * VEC;
-	const long long first = lo - e0, last = lo + g.S - e0;                   // valid lanes: first <= lane < last
-	if (last <= 0) return 0u;
-	const uint32_t full = (1u << VEC) - 1u;
-	const uint32_t below = first > 0 ? ((1u << (int)first) - 1u) : 0u;
-	const uint32_t upto = last >= VEC ? full : ((1u << (int)last) - 1u);
-	return upto & ~below;
+	SlotGeo<VEC> q;
+	const uint32_t row = fdiv32(slot, g.spdiv);
+	q.v = slot - row * (uint32_t)g.SP;
+	q.lo = plane0 + row * g.plane_step;
+	q.head = q.lo & (uint32_t)(VEC - 1);
+	return q;
+}
+
+// partial vector `which` (0: the head, 1: the tail) of plane `row`: vector index and lane mask, 0 when that vector is not partial
+template <int VEC>
+__device__ __forceinline__ uint32_t partial_vector(const ClusterGeo& g, uint32_t plane0, uint32_t row, int which, uint32_t& v, uint32_t& e0)
+{
+	const uint32_t lo = plane0 + row * g.plane_step, head = lo & (uint32_t)(VEC - 1), S = (uint32_t)g.S;
+	const uint32_t vend = (head + S) / VEC, rem = head + S - vend * VEC;      // the plane ends `rem` lanes into vector vend
+	uint32_t mask;
+	if (which == 0) {
+		if (head == 0u) return 0u;
+		v = 0u;
+		mask = ~((1u << head) - 1u) & ((1u << VEC) - 1u);
+		if (vend == 0u) mask &= (1u << rem) - 1u;                               // plane shorter than one vector
+	} else {
+		if (rem == 0u || (vend == 0u && head > 0u)) return 0u;                  // aligned end, or already handled as the head
+		v = vend;
+		mask = (1u << rem) - 1u;
+	}
+	e0 = lo - head + v * VEC;
+	return mask;
 }
 
 // the cluster-wide sum of the CTAs' (s1, s2) through distributed shared memory, in rank order
@@ -520,25 +559,37 @@ __global__ void __launch_bounds__(THREADS) bn_fwd_cluster_kernel(const T* __rest
 	const float pivot = to_f<T>(x[(size_t)c * g.S]);
 
 	// ---- phase 1: HBM -> shared memory, sum(x - pivot), sum((x - pivot)^2)
+	const uint32_t nrows = (uint32_t)max(0, n1 - n0), S = (uint32_t)g.S;
+	const uint32_t plane0 = ((uint32_t)n0 * (uint32_t)g.C + (uint32_t)c) * S;
 	float s1 = 0.0f, s2 = 0.0f;
-	for (int base = threadIdx.x; base < nslots; base += THREADS * kSlotUnroll) {
+	for (uint32_t base = threadIdx.x; base < (uint32_t)nslots; base += THREADS * kSlotUnroll) {
 		P v[kSlotUnroll];
-		uint32_t mask[kSlotUnroll];
+		bool ok[kSlotUnroll];
 		#pragma unroll
 		for (int u = 0; u < kSlotUnroll; u++) {
-			long long e0;
-			mask[u] = slot_geometry<VEC>(g, c, n0, base + u * THREADS, nslots, e0);
-			if (mask[u]) v[u] = *reinterpret_cast<const P*>(x + e0);
+			const uint32_t slot = base + u * THREADS;
+			const SlotGeo<VEC> q = slot_decode<VEC>(g, plane0, slot);
+			ok[u] = slot < (uint32_t)nslots && q.full(S);
+			if (ok[u]) v[u] = *reinterpret_cast<const P*>(x + q.e0());
 		}
 		#pragma unroll
 		for (int u = 0; u < kSlotUnroll; u++) {
-			if (!mask[u]) continue;
+			if (!ok[u]) continue;
 			stash[base + u * THREADS] = *reinterpret_cast<const uint4*>(&v[u]);
 			#pragma unroll
-			for (int e = 0; e < VEC; e++) {
-				if (mask[u] >> e & 1u) { const float d = to_f<T>(v[u].v[e]) - pivot; s1 += d; s2 = fmaf(d, d, s2); }
-			}
+			for (int e = 0; e < VEC; e++) { const float d = to_f<T>(v[u].v[e]) - pivot; s1 += d; s2 = fmaf(d, d, s2); }
 		}
+	}
+	// the (at most two) partial vectors of every plane
+	for (uint32_t i = threadIdx.x; i < 2u * nrows; i += THREADS) {
+		uint32_t vv, e0;
+		const uint32_t mask = partial_vector<VEC>(g, plane0, i >> 1, (int)(i & 1u), vv, e0);
+		if (!mask) continue;
+		const P pv = *reinterpret_cast<const P*>(x + e0);
+		stash[(i >> 1) * (uint32_t)g.SP + vv] = *reinterpret_cast<const uint4*>(&pv);
+		#pragma unroll
+		for (int e = 0; e < VEC; e++)
+			if (mask >> e & 1u) { const float d = to_f<T>(pv.v[e]) - pivot; s1 += d; s2 = fmaf(d, d, s2); }
 	}
 	block_sum2<THREADS>(s1, s2, red);
 	cluster_sum2(s1, s2, part, g.CL);
@@ -559,22 +610,25 @@ __global__ void __launch_bounds__(THREADS) bn_fwd_cluster_kernel(const T* __rest
 	const float a = scale[c] * invstd, b = bias[c] - mean * a;
 
 	// ---- phase 2: shared memory -> y = a * x + b -> HBM
-	constexpr uint32_t FULL = (1u << VEC) - 1u;
-	for (int slot = threadIdx.x; slot < nslots; slot += THREADS) {
-		long long e0;
-		const uint32_t mask = slot_geometry<VEC>(g, c, n0, slot, nslots, e0);
-		if (!mask) continue;
+	__syncthreads();                              // partial vectors were stashed by other threads than the ones that read them
+	for (uint32_t slot = threadIdx.x; slot < (uint32_t)nslots; slot += THREADS) {
+		const SlotGeo<VEC> q = slot_decode<VEC>(g, plane0, slot);
+		if (!q.full(S)) continue;
 		const uint4 raw = stash[slot];
 		P v = *reinterpret_cast<const P*>(&raw);
 		#pragma unroll
 		for (int e = 0; e < VEC; e++) v.v[e] = from_f<T>(fmaf(to_f<T>(v.v[e]), a, b));
-		if (mask == FULL) {
-			store_streaming<T, VEC>(y + e0, v);
-		} else {
-			#pragma unroll
-			for (int e = 0; e < VEC; e++)
-				if (mask >> e & 1u) y[e0 + e] = v.v[e];
-		}
+		store_streaming<T, VEC>(y + q.e0(), v);
+	}
+	for (uint32_t i = threadIdx.x; i < 2u * nrows; i += THREADS) {
+		uint32_t vv, e0;
+		const uint32_t mask = partial_vector<VEC>(g, plane0, i >> 1, (int)(i & 1u), vv, e0);
+		if (!mask) continue;
+		const uint4 raw = stash[(i >> 1) * (uint32_t)g.SP + vv];
+		P v = *reinterpret_cast<const P*>(&raw);
+		#pragma unroll
+		for (int e = 0; e < VEC; e++) v.v[e] = from_f<T>(fmaf(to_f<T>(v.v[e]), a, b));
+		store_partial<T, VEC>(y + e0, v, mask);
 	}
 }
 
@@ -597,33 +651,49 @@ __global__ void __launch_bounds__(THREADS) bn_bwd_cluster_kernel(const T* __rest
 	uint4* stash_dy = stash + g.stash_slots;
 
 	// ---- phase 1: HBM -> shared memory, sum(dy), sum(dy * (x - mean))
+	const uint32_t nrows = (uint32_t)max(0, n1 - n0), S = (uint32_t)g.S;
+	const uint32_t plane0 = ((uint32_t)n0 * (uint32_t)g.C + (uint32_t)c) * S;
 	float s1 = 0.0f, s2 = 0.0f;
-	for (int base = threadIdx.x; base < nslots; base += THREADS * UNR) {
+	for (uint32_t base = threadIdx.x; base < (uint32_t)nslots; base += THREADS * UNR) {
 		P v[UNR], w[UNR];
-		uint32_t mask[UNR];
+		bool ok[UNR];
 		#pragma unroll
 		for (int u = 0; u < UNR; u++) {
-			long long e0;
-			mask[u] = slot_geometry<VEC>(g, c, n0, base + u * THREADS, nslots, e0);
-			if (mask[u]) {
-				v[u] = *reinterpret_cast<const P*>(x + e0);
-				w[u] = *reinterpret_cast<const P*>(dy + e0);
+			const uint32_t slot = base + u * THREADS;
+			const SlotGeo<VEC> q = slot_decode<VEC>(g, plane0, slot);
+			ok[u] = slot < (uint32_t)nslots && q.full(S);
+			if (ok[u]) {
+				v[u] = *reinterpret_cast<const P*>(x + q.e0());
+				w[u] = *reinterpret_cast<const P*>(dy + q.e0());
 			}
 		}
 		#pragma unroll
 		for (int u = 0; u < UNR; u++) {
-			if (!mask[u]) continue;
+			if (!ok[u]) continue;
 			stash[base + u * THREADS] = *reinterpret_cast<const uint4*>(&v[u]);
 			stash_dy[base + u * THREADS] = *reinterpret_cast<const uint4*>(&w[u]);
 			#pragma unroll
 			for (int e = 0; e < VEC; e++) {
-				if (mask[u] >> e & 1u) {
-					const float gv = to_f<T>(w[u].v[e]);
-					s1 += gv;
-					s2 = fmaf(gv, to_f<T>(v[u].v[e]) - mean, s2);
-				}
+				const float gv = to_f<T>(w[u].v[e]);
+				s1 += gv;
+				s2 = fmaf(gv, to_f<T>(v[u].v[e]) - mean, s2);
 			}
 		}
+	}
+	for (uint32_t i = threadIdx.x; i < 2u * nrows; i += THREADS) {
+		uint32_t vv, e0;
+		const uint32_t mask = partial_vector<VEC>(g, plane0, i >> 1, (int)(i & 1u), vv, e0);
+		if (!mask) continue;
+		const P pv = *reinterpret_cast<const P*>(x + e0), pw = *reinterpret_cast<const P*>(dy + e0);
+		stash[(i >> 1) * (uint32_t)g.SP + vv] = *reinterpret_cast<const uint4*>(&pv);
+		stash_dy[(i >> 1) * (uint32_t)g.SP + vv] = *reinterpret_cast<const uint4*>(&pw);
+		#pragma unroll
+		for (int e = 0; e < VEC; e++)
+			if (mask >> e & 1u) {
+				const float gv = to_f<T>(pw.v[e]);
+				s1 += gv;
+				s2 = fmaf(gv, to_f<T>(pv.v[e]) - mean, s2);
+			}
 	}
 	block_sum2<THREADS>(s1, s2, red);
 	cluster_sum2(s1, s2, part, g.CL);
@@ -634,23 +704,27 @@ __global__ void __launch_bounds__(THREADS) bn_bwd_cluster_kernel(const T* __rest
 	const float c1 = scale[c] * invstd, c2 = c1 * s1 / count, c3 = c1 * dsc / count * invstd;
 
 	// ---- phase 2: shared memory -> dx = c1*dy - c2 - (x - mean)*c3 -> HBM
-	constexpr uint32_t FULL = (1u << VEC) - 1u;
-	for (int slot = threadIdx.x; slot < nslots; slot += THREADS) {
-		long long e0;
-		const uint32_t mask = slot_geometry<VEC>(g, c, n0, slot, nslots, e0);
-		if (!mask) continue;
+	__syncthreads();
+	for (uint32_t slot = threadIdx.x; slot < (uint32_t)nslots; slot += THREADS) {
+		const SlotGeo<VEC> q = slot_decode<VEC>(g, plane0, slot);
+		if (!q.full(S)) continue;
 		const uint4 rx = stash[slot], rg = stash_dy[slot];
 		const P v = *reinterpret_cast<const P*>(&rx);
 		P w = *reinterpret_cast<const P*>(&rg);
 		#pragma unroll
 		for (int e = 0; e < VEC; e++) w.v[e] = from_f<T>(c1 * to_f<T>(w.v[e]) - c2 - (to_f<T>(v.v[e]) - mean) * c3);
-		if (mask == FULL) {
-			store_streaming<T, VEC>(dx + e0, w);
-		} else {
-			#pragma unroll
-			for (int e = 0; e < VEC; e++)
-				if (mask >> e & 1u) dx[e0 + e] = w.v[e];
-		}
+		store_streaming<T, VEC>(dx + q.e0(), w);
+	}
+	for (uint32_t i = threadIdx.x; i < 2u * nrows; i += THREADS) {
+		uint32_t vv, e0;
+		const uint32_t mask = partial_vector<VEC>(g, plane0, i >> 1, (int)(i & 1u), vv, e0);
+		if (!mask) continue;
+		const uint4 rx = stash[(i >> 1) * (uint32_t)g.SP + vv], rg = stash_dy[(i >> 1) * (uint32_t)g.SP + vv];
+		const P v = *reinterpret_cast<const P*>(&rx);
+		P w = *reinterpret_cast<const P*>(&rg);
+		#pragma unroll
+		for (int e = 0; e < VEC; e++) w.v[e] = from_f<T>(c1 * to_f<T>(w.v[e]) - c2 - (to_f<T>(v.v[e]) - mean) * c3);
+		store_partial<T, VEC>(dx + e0, w, mask);
 	}
 }
 
@@ -674,14 +748,17 @@ constexpr size_t kStashTwoPerSm = 100 * 1024, kStashMax = 200 * 1024;
 ClusterPlan make_cluster_plan(std::initializer_list<const void*> ptrs, int64_t N, int64_t C, int64_t S, size_t es, int tensors)
 {
 	static const int force_threads = env_int("PZ_BN_THREADS", 0), force_cl = env_int("PZ_BN_CL", 0);
+	static const int max_cl = env_int("PZ_BN_MAX_CL", 8);              // 16 needs the non-portable cluster size opt-in
+	static const size_t stash_target = (size_t)env_int("PZ_BN_STASH_KB", 100) * 1024;
 	ClusterPlan p{};
 	const int vec = (int)(16 / es);
-	p.ok = getenv("PZ_BN_NO_CLUSTER") == nullptr && N * C * S < (1ll << 40) && C < (1 << 24);
+	p.ok = getenv("PZ_BN_NO_CLUSTER") == nullptr && N * C * S < (1ll << 31) - 64 && C < (1 << 24);      // 32-bit element offsets
 	for (const void* q : ptrs) p.ok = p.ok && ((uintptr_t)q % 16 == 0);
 	if (!p.ok) return p;
 
 	ClusterGeo& g = p.g;
 	g.N = (int)N; g.C = (int)C; g.S = (int)S;
+	g.plane_step = (uint32_t)(C * S);
 	g.SP = (int)((S + 2 * (vec - 1)) / vec);           // aligned vectors that can overlap a plane starting anywhere
 	if ((S % vec) == 0) g.SP = (int)(S / vec);         // ... every plane is aligned when S is a multiple of the vector width
 	g.spdiv = make_fastdiv32((uint32_t)g.SP);
@@ -690,14 +767,14 @@ ClusterPlan make_cluster_plan(std::initializer_list<const void*> ptrs, int64_t N
 	// would not be filled); failing that the two-kernel path
 	const int sms = pz_num_sms();
 	int CL = 0;
-	for (int cl = 1; cl <= 8; cl *= 2) {
+	for (int cl = 1; cl <= max_cl; cl *= 2) {
 		if (cl > 1 && cl > N) break;
 		const size_t bytes = (size_t)pz_cdiv(N, cl) * g.SP * 16 * tensors;
-		if (bytes <= kStashTwoPerSm && (C * cl >= 2 * sms || cl == 8 || cl * 2 > N)) { CL = cl; break; }
+		if (bytes <= stash_target && (C * cl >= 2 * sms || cl == max_cl || cl * 2 > N)) { CL = cl; break; }
 	}
 	// (a stash that leaves room for ONE CTA per SM only -- planes above ~100 KB per CTA even in a cluster of 8 -- measured slower
 	// than the two-kernel path: profiles/r02_bn.md)
-	if (force_cl > 0 && force_cl <= 8 && (force_cl & (force_cl - 1)) == 0 && force_cl <= (N > 1 ? N : 1)) CL = force_cl;
+	if (force_cl > 0 && force_cl <= 16 && (force_cl & (force_cl - 1)) == 0 && force_cl <= (N > 1 ? N : 1)) CL = force_cl;
 	if (CL == 0) { p.ok = false; return p; }
 
 	g.CL = CL;
@@ -730,6 +807,7 @@ int launch_cluster(K kernel, const ClusterPlan& p, cudaStream_t s, Args... args)
 		// (idempotent; a per-kernel flag would need one static per instantiation)
 		PZ_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStashMax));
 	}
+	if (p.g.CL > 8) PZ_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
 	PZ_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kernel, args...));
 	pz_count_launch(1);
 	return PZ_OK;
