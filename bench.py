@@ -380,19 +380,20 @@ def gpuArm(args):
 					"traffic": None, "peak_note": "%s STREAM-style copy bandwidth" % peaks["src"]}
 	# DRAM traffic per launch of that family from the committed ncu capture of this command (profiles/, tools/summarize_launches.py)
 	try:
-		with open(os.path.join(ROOT, "profiles", "r01_family_traffic.json")) as f:
+		with open(os.path.join(ROOT, "profiles", "r02_family_traffic.json")) as f:
 			captured = json.load(f)["families"]
 		key = top if top in captured else ("gemm" if top.startswith("gemm") else top)
 		roofline["traffic"] = captured[key]["dram_bytes_per_launch"]
 		roofline["traffic_note"] = "dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over the family's launches in " \
-								   "profiles/r01z_launches.md (ncu, cold cache); algorithmic bytes per launch: %.0f" % (
+								   "profiles/r02_launches.md (ncu, cold cache); algorithmic bytes per launch: %.0f" % (
 									   fam["bytes"] / max(1, fam["launches"]))
 	except Exception:      # noqa: BLE001 -- no capture committed
 		pass
 	roofline.update({
 		"kernel": {"gemm": "umma_gemm_kernel, launches with arithmetic intensity above the ridge (tcgen05 implicit-GEMM 3x3 / 7x7 conv, GEMM)",
 				   "gemm_hbm": "umma_gemm_kernel, launches below the ridge (1x1 convolutions: HBM-bound even at full efficiency)",
-				   "bn_fwd": "bn_stats_kernel + bn_apply_kernel", "bn_bwd": "bn_bwd_stats_kernel + bn_bwd_apply_kernel",
+				   "bn_fwd": "bn_fwd_cluster_kernel (bn_stats_kernel + bn_apply_kernel for planes beyond the stash)",
+				   "bn_bwd": "bn_bwd_cluster_kernel (bn_bwd_stats_kernel + bn_bwd_apply_kernel for planes beyond the stash)",
 				   "eltwise": "ew_kernel", "pool": "pool kernels", "other": "other"}[top],
 		"launches_per_step": fam["launches"] / args.steps, "avg_launch_us": fam["ms"] * 1e3 / max(1, fam["launches"]),
 		"share_of_profiled_kernel_time": fam["ms"] / total, "profiled_ms_per_step": msProf / args.steps,
