@@ -7,7 +7,7 @@ Cuda/Utils.py are imported from baseline/_ref and called as they are.  Inputs ar
 
 TENSOR_CORE lists the tests whose host check compares a float32 contraction at np.allclose's default 1e-5 / 1e-8: they need
 full-fp32 products (cuDNN gives the reference that on this stack), which this backend provides in its exact mode
-(`dnn.enableTensorOps(False)`: 3 x TF32 split products); in the default TF32 mode they are held to the 1e-3 bar elsewhere.
+(`dnn.enableTensorOps(False)`: plain fp32 FMAs on the CUDA cores); in the default TF32 mode they are held to the 1e-3 bar elsewhere.
 """
 import importlib
 import os
