@@ -40,8 +40,15 @@ def loadPeaks():
 	if os.path.exists(path):
 		with open(path) as f:
 			peaks = json.load(f)
-		return {"hbm": float(peaks["hbm_gbs"]), "bf16": float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])), "src": "measured"}
-	return {"hbm": 6650.0, "bf16": 1400.0, "src": "fallback"}
+		out = {"hbm": float(peaks["hbm_gbs"]), "bf16": float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])), "src": "measured"}
+	else:
+		out = {"hbm": 6650.0, "bf16": 1400.0, "src": "fallback"}
+	# the TF32 figure is not in MEASURED_PEAKS.json: tools/measure_tf32_peak.py (cuBLAS fp32 GEMM with TF32 math on a B200 of this pool)
+	tf32 = os.path.join(ROOT, "profiles", "r02_tf32_peak.json")
+	if os.path.exists(tf32):
+		with open(tf32) as f:
+			out["tf32"] = float(json.load(f)["tf32_tflops_sustained"])
+	return out
 
 
 # ---------------------------------------------------------------------------------------------------- clocks
@@ -168,6 +175,20 @@ def referenceGpu(args):
 		return {"value": res["images_per_s"], "unit": "images/s", "ms_per_step": res["ms_per_step"], "steps": res["steps"],
 				"backend": "PuzzleLib Cuda backend (cuDNN %s, cuBLAS, NVRTC) built by baseline/build_ref.py; eager, host-driven" % cudnnVersion(),
 				"dtype": res["dtype"]}
+	except Exception as e:      # noqa: BLE001
+		return {"unavailable": "%s: %s" % (type(e).__name__, str(e)[:200])}
+
+
+def referenceCpuForward():
+	"""the reference's own numpy CPU backend on what it can run: the FORWARD pass (LeNet N=64 = BASELINE.json configs[0]; ResNet-50 up to
+	fc1000) -- a second, clearly labelled CPU number next to the fwd+bwd oracle port of `cpu_baseline`"""
+	cmd = [sys.executable, os.path.join(ROOT, "tools", "bench_ref_cpu.py"), "--batch", "8", "--reps", "3"]
+	try:
+		out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+		line = [l for l in out.stdout.splitlines() if l.startswith("{")]
+		if not line:
+			return {"unavailable": (out.stderr.strip().splitlines() or ["no output"])[-1][:200]}
+		return json.loads(line[-1])
 	except Exception as e:      # noqa: BLE001
 		return {"unavailable": "%s: %s" % (type(e).__name__, str(e)[:200])}
 
@@ -366,7 +387,10 @@ def gpuArm(args):
 	fam = families[top]
 	if top == "gemm":     # tcgen05 launches above the machine ridge (3x3 / 7x7 convolutions, large GEMMs)
 		achieved = fam["flops"] / (fam["ms"] * 1e-3) / 1e12
-		if args.dtype == "f32":
+		if args.dtype == "f32" and "tf32" in peaks:
+			peak = peaks["tf32"]
+			note = "tf32 products: cuBLAS fp32 GEMM with TF32 math, 8192^3, sustained, measured on a B200 of this pool (profiles/r02_tf32_peak.json)"
+		elif args.dtype == "f32":
 			peak = peaks["bf16"] / 2.0
 			note = "tf32 products: 0.5 x the %s bf16 sustained GEMM peak (no tf32 figure in MEASURED_PEAKS.json)" % peaks["src"]
 		else:
@@ -446,6 +470,8 @@ def gpuArm(args):
 
 	if node.gridsize == 1 and not args.no_ref_gpu:
 		line["reference_gpu"] = referenceGpu(args)
+	if node.gridsize == 1 and not args.no_cpu and args.model == "resnet50":
+		line["cpu_reference_forward"] = referenceCpuForward()
 
 	if graphNote:
 		line["config"]["graph"] = graphNote

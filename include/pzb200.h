@@ -92,6 +92,9 @@ int pz_graph_begin(void* stream);
 int pz_graph_end(void* stream, void** exec);
 int pz_graph_launch(void* exec, void* stream);
 int pz_graph_destroy(void* exec);
+/* diagnosis: the 32 per-role phase clock sums of the tcgen05 engine since the last call (only in builds with -DPZ_TIMELINE,
+ * PZ_ERR_UNSUPPORTED otherwise); no reference counterpart */
+int pz_debug_timeline(unsigned long long* out);
 int pz_stream_create(void** stream);
 int pz_stream_destroy(void* stream);
 int pz_stream_synchronize(void* stream);

@@ -329,6 +329,44 @@ int prescale(float* buf, long long n, float beta, void* stream)
 	return pz_scale_shift(PZ_F32, buf, buf, beta, 0.0f, n, stream);
 }
 
+
+// staged epilogue stores (Epilogue::staged): plain fp32 stores only; 16-byte lanes when the rows of a tile are contiguous in
+// memory (row offset = image * ms0 + position) and everything is a multiple of four elements.  OFF by default: measured on the
+// ResNet-50 layers (profiles/r02_conv_epilogue_gather_experiments.md) the two barriers per 32 columns cost more than the wider
+// requests gain (64 -> 256 channels at 55 x 55: 0.068 -> 0.158 ms).  PZ_STAGED_EPI=1 enables it for experiments.
+void set_staged(Epilogue& E, int dtype)
+{
+	static const bool on = [] { const char* e = getenv("PZ_STAGED_EPI"); return e && atoi(e); }();
+	E.staged = 0;
+	if (!on || dtype != PZ_F32 || E.atomic || E.beta != 0.0f || E.bias_mode == 2 || E.c2i || E.out_kind != OUT_F32) return;
+	const bool contiguous = E.ms2 == 1 && (E.md2.d == 0 || (long long)E.ms1 == (long long)E.md2.d);
+	const bool vec = contiguous && E.md12.d % 4 == 0 && E.ms0 % 4 == 0 && E.ncs % 4 == 0 && E.group_stride % 4 == 0 && ((uintptr_t)E.out & 15) == 0;
+	E.staged = vec ? 2 : 1;
+}
+
+// 16-byte producer lanes (MODE_MN_VEC / MODE_K_POS_VEC in pz_umma.cuh) need float tensors whose planes, image and group strides are
+// multiples of four elements on a 16-byte aligned base.  PZ_VEC_GATHER: 0 = never, 1 = where it measured faster (default: the dy
+// operand of wgrad next to a tap-gathered x, and 1x1 wgrad over small planes), 2 = wherever it is legal (experiments).  Four times
+// fewer load instructions do NOT make the fprop / dgrad gather faster (28 x 28, 128 -> 512 channels: 0.043 -> 0.048 ms): the
+// gather is bound behind the LSU, not by issue (profiles/r02_conv_epilogue_gather_experiments.md).
+int vec_gather_level()
+{
+	static const int level = [] { const char* e = getenv("PZ_VEC_GATHER"); return e ? atoi(e) : 1; }();
+	return level;
+}
+// the MnChan operand of a 1 x 1 / stride-1 / un-padded filter: position offset = row index inside the plane
+bool mn_vec_ok(const Operand& A, int dtype)
+{
+	return vec_gather_level() >= 2 && dtype == PZ_F32 && A.R == 1 && A.S == 1 && A.ah == 1 && A.aw == 1 && A.ch == 0 && A.cw == 0 && A.cdh == 1 &&
+		   A.cdw == 1 && (long long)A.H * A.W == (long long)A.rd12.d && A.Wd == A.W && (int)A.rd2.d == A.W && A.rd12.d % 4 == 0 && A.rs0 % 4 == 0 &&
+		   A.ks0 % 4 == 0 && A.group_stride % 4 == 0 && ((uintptr_t)A.ptr & 15) == 0;
+}
+// the KPosDense operand (wgrad): rows = planes, k = positions of one image
+bool kpos_vec_ok(const Operand& B, int dtype)
+{
+	return vec_gather_level() >= 1 && dtype == PZ_F32 && B.plane % 4 == 0 && B.rs0 % 4 == 0 && B.ks0 % 4 == 0 && B.group_stride % 4 == 0 &&
+		   ((uintptr_t)B.ptr & 15) == 0;
+}
 }  // namespace
 
 extern "C" {
@@ -429,7 +467,9 @@ int pz_conv2d_fprop(int dtype, const pz_conv2d_desc* d, const void* x, const voi
 		if (st2 != PZ_OK) return st2;
 	}
 	// the table-driven tap producer exists for float only; 16-bit tensors with very few channels take the general gather
-	const int amode = chan ? MODE_MN_CHAN : (fast && !h16 ? MODE_MN_TAP : MODE_MN_GENERAL);
+	int amode = chan ? MODE_MN_CHAN : (fast && !h16 ? MODE_MN_TAP : MODE_MN_GENERAL);
+	if (amode == MODE_MN_CHAN && mn_vec_ok(A, dtype)) amode = MODE_MN_VEC;
+	set_staged(E, dtype);
 	return launch(p, dtype, bn, amode, MODE_TMA, amode == MODE_MN_GENERAL ? false : RS > 31, g.G, &tsrc, pz_stream(stream));
 }
 
@@ -564,7 +604,10 @@ int pz_conv2d_dgrad(int dtype, const pz_conv2d_desc* d, const void* dy, const vo
 			}
 		}
 		const bool cdiv = mode == 2 ? strided : Rc * Sc > 31;
-		return launch(q, dtype, bn, mode == 2 ? MODE_MN_GENERAL : (chan ? MODE_MN_CHAN : MODE_MN_TAP), MODE_TMA, cdiv, g.G, &tsrc, pz_stream(stream));
+		int amode = mode == 2 ? MODE_MN_GENERAL : (chan ? MODE_MN_CHAN : MODE_MN_TAP);
+		if (amode == MODE_MN_CHAN && mn_vec_ok(QA, dtype)) amode = MODE_MN_VEC;
+		set_staged(q.E, dtype);
+		return launch(q, dtype, bn, amode, MODE_TMA, cdiv, g.G, &tsrc, pz_stream(stream));
 	};
 
 	if (!h16 && g.G == 1 && g.C <= 4 && g.C * RS <= 256 && RS > 1 && bias == nullptr && use_chan_order(g.K, bke) && tap_entries_fit(34ll * PQ, g)) {
@@ -615,7 +658,7 @@ int pz_conv2d_dgrad(int dtype, const pz_conv2d_desc* d, const void* dy, const vo
 		q.alg_bytes = 4.0 * ((double)g.N * g.K * PQ + (double)g.K * crs + (double)g.N * g.C * HW);
 		const TmaSource tsrc{wt, crs, kpad};
 		const int bn = crs <= 64 ? 64 : (crs <= 128 ? 128 : 256);
-		return launch(q, dtype, bn, MODE_MN_CHAN, MODE_TMA, false, 1, &tsrc, pz_stream(stream));
+		return launch(q, dtype, bn, mn_vec_ok(QA, dtype) ? MODE_MN_VEC : MODE_MN_CHAN, MODE_TMA, false, 1, &tsrc, pz_stream(stream));
 	}
 
 	if (is1x1 && g.ph == 0 && g.pw == 0 && strided && bias == nullptr && (!h16 || use_chan_order(g.Kg, bke))) {
@@ -763,7 +806,13 @@ int pz_conv2d_wgrad(int dtype, const pz_conv2d_desc* d, const void* x, const voi
 		if (st != PZ_OK) return st;
 	}
 	if (!fast) st = launch(p, dtype, bn, MODE_K_GENERAL, MODE_K_DENSE, false, g.G, nullptr, pz_stream(stream));
-	else st = launch(p, dtype, bn, dense_x ? MODE_K_POS_DENSE : MODE_K_POS_TAP, MODE_K_POS_DENSE, !dense_x && RS > 31, g.G, nullptr, pz_stream(stream));
+	else {
+		const bool vec_dy = kpos_vec_ok(B, dtype);
+		const bool vec_x = dense_x && kpos_vec_ok(A, dtype) && (PQ < 512 || vec_gather_level() >= 2);    // 28 x 28 planes: measured slower
+		const int amode = dense_x ? (vec_x && vec_dy ? MODE_K_POS_VEC : MODE_K_POS_DENSE) : MODE_K_POS_TAP;
+		const int bmode = vec_dy && (!dense_x || vec_x) ? MODE_K_POS_VEC : MODE_K_POS_DENSE;
+		st = launch(p, dtype, bn, amode, bmode, !dense_x && RS > 31, g.G, nullptr, pz_stream(stream));
+	}
 	if (st != PZ_OK || !acc) return st;
 	return finalize16(dtype, dw, wcount, acc, 1, wcount, beta, pz_stream(stream));
 }

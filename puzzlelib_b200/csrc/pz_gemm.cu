@@ -177,6 +177,10 @@ int launch(GemmParams& p, int dtype, int bn, int amode, int bmode, bool cdiv, in
 	PZ_INST_BN(MODE_K_POS_TAP, MODE_K_POS_DENSE, true, false)  //   ... with more than 31 taps
 	PZ_INST_BN(MODE_K_POS_DENSE, MODE_K_POS_DENSE, false, false)   // wgrad of a 1x1 / stride-1 / un-padded filter
 	PZ_INST_BN(MODE_K_GENERAL, MODE_K_DENSE, false, false)     // fallback for wgrad
+	PZ_INST_BN3(MODE_MN_VEC, MODE_TMA, false, false)           // 1x1 fprop / dgrad over 16-byte aligned planes: 16-byte producer lanes
+	PZ_INST_BN(MODE_K_POS_VEC, MODE_K_POS_VEC, false, false)   // wgrad of a 1x1 filter over 16-byte aligned planes
+	PZ_INST_BN(MODE_K_POS_TAP, MODE_K_POS_VEC, false, false)   // wgrad: dy planes 16-byte aligned
+	PZ_INST_BN(MODE_K_POS_TAP, MODE_K_POS_VEC, true, false)
 	// ---- half / bfloat16 storage
 	PZ_INST_BN3(MODE_MN_CHAN, MODE_TMA, false, true)
 	PZ_INST_BN3(MODE_MN_CHAN, MODE_TMA, true, true)
@@ -356,4 +360,20 @@ extern "C" int pz_gemm(int dtype, const void* A, const void* B, void* C, int64_t
 		}
 	}
 	return launch(p, dtype, bn, amode, bmode, false, 1, nullptr, s);
+}
+
+// instrumented builds (-DPZ_TIMELINE): copy the 32 phase counters of umma_gemm_kernel to `out` and reset them; PZ_ERR_UNSUPPORTED otherwise
+extern "C" int pz_debug_timeline(unsigned long long* out)
+{
+#ifdef PZ_TIMELINE
+	PZ_CHECK_CUDA(cudaDeviceSynchronize());
+	PZ_CHECK_CUDA(cudaMemcpyFromSymbol(out, pzumma::pz_timeline, sizeof(unsigned long long) * 32));
+	unsigned long long zero[32] = {};
+	PZ_CHECK_CUDA(cudaMemcpyToSymbol(pzumma::pz_timeline, zero, sizeof(zero)));
+	return PZ_OK;
+#else
+	(void)out;
+	pz_set_error(PZ_ERR_UNSUPPORTED, "pz_debug_timeline: the library was built without -DPZ_TIMELINE");
+	return PZ_ERR_UNSUPPORTED;
+#endif
 }

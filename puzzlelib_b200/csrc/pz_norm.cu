@@ -465,6 +465,55 @@ __device__ __noinline__ void store_partial(T* dst, const Pack<T, VEC>& v, uint32
 		if (mask >> e & 1u) dst[e] = v.v[e];
 }
 
+// ---- bulk asynchronous copies (TMA, non-tensor form) of whole planes into the stash.  One elected warp issues a
+// cp.async.bulk per plane -- the 16-byte aligned byte range that covers it, which is exactly the plane's stash layout -- so a CTA
+// has ALL of its planes (up to 100 KB) in flight at once without holding a register or a scoreboard per load; completion is counted
+// by an mbarrier.  (The per-thread loads of the first version kept ~8 KB per CTA in flight: DRAM utilisation 39 %, ncu
+// profiles/r02_bn_fwd_ncu_keys.txt.)
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init1(uint32_t bar)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect(uint32_t bar, uint32_t bytes)
+{
+	asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive1(uint32_t bar)
+{
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait0(uint32_t bar)
+{
+	asm volatile(
+		"{\n\t.reg .pred p;\n\t"
+		"WAIT_%=:\n\t"
+		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t"
+		"@!p bra WAIT_%=;\n\t}"
+		::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+				 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// warp 0 of the CTA: plane `row` of each of `ntensors` tensors -> its SP-vector region of the matching stash
+template <typename T, int VEC>
+__device__ __forceinline__ void bulk_load_planes(const ClusterGeo& g, uint32_t plane0, uint32_t nrows, const T* const (&src)[2], uint4* const (&dst)[2],
+												 int ntensors, uint32_t bar)
+{
+	const uint32_t lane = threadIdx.x & 31u, S = (uint32_t)g.S;
+	for (uint32_t row = lane; row < nrows; row += 32u) {
+		const uint32_t lo = plane0 + row * g.plane_step, head = lo & (uint32_t)(VEC - 1);
+		const uint32_t bytes = ((head + S + VEC - 1) / VEC) * 16u;
+		mbar_expect(bar, bytes * (uint32_t)ntensors);
+		for (int t = 0; t < ntensors; t++) bulk_g2s(smem_addr(dst[t] + row * (uint32_t)g.SP), src[t] + (lo - head), bytes, bar);
+	}
+	__syncwarp();
+	if (lane == 0) mbar_arrive1(bar);
+}
+
 // deterministic block sum of two values; result valid in every thread
 template <int THREADS>
 __device__ __forceinline__ void block_sum2(float& a, float& b, float* red /* [2 * THREADS / 32 + 2] */)
@@ -542,7 +591,7 @@ __device__ __forceinline__ void cluster_sum2(float& s1, float& s2, float* part, 
 	cluster_sync_all();                 // nobody leaves (or overwrites `part`) while a peer still reads it
 }
 
-template <typename T, int VEC, int THREADS>
+template <typename T, int VEC, int THREADS, bool BULK>
 __global__ void __launch_bounds__(THREADS) bn_fwd_cluster_kernel(const T* __restrict__ x, T* __restrict__ y, ClusterGeo g,
 																  const float* __restrict__ scale, const float* __restrict__ bias,
 																  float* mean_io, float* var_io, float* save_mean, float* save_invvar,
@@ -562,6 +611,36 @@ __global__ void __launch_bounds__(THREADS) bn_fwd_cluster_kernel(const T* __rest
 	const uint32_t nrows = (uint32_t)max(0, n1 - n0), S = (uint32_t)g.S;
 	const uint32_t plane0 = ((uint32_t)n0 * (uint32_t)g.C + (uint32_t)c) * S;
 	float s1 = 0.0f, s2 = 0.0f;
+	if (BULK) {
+		__shared__ uint64_t bar;
+		const uint32_t barp = smem_addr(&bar);
+		if (threadIdx.x == 0) mbar_init1(barp);
+		__syncthreads();
+		if (threadIdx.x < 32) {
+			const T* const src[2] = {x, x};
+			uint4* const dst[2] = {stash, stash};
+			bulk_load_planes<T, VEC>(g, plane0, nrows, src, dst, 1, barp);
+		}
+		mbar_wait0(barp);
+		for (uint32_t slot = threadIdx.x; slot < (uint32_t)nslots; slot += THREADS) {
+			const SlotGeo<VEC> q = slot_decode<VEC>(g, plane0, slot);
+			if (!q.full(S)) continue;
+			const uint4 raw = stash[slot];
+			const P v = *reinterpret_cast<const P*>(&raw);
+			#pragma unroll
+			for (int e = 0; e < VEC; e++) { const float d = to_f<T>(v.v[e]) - pivot; s1 += d; s2 = fmaf(d, d, s2); }
+		}
+		for (uint32_t i = threadIdx.x; i < 2u * nrows; i += THREADS) {
+			uint32_t vv, e0;
+			const uint32_t mask = partial_vector<VEC>(g, plane0, i >> 1, (int)(i & 1u), vv, e0);
+			if (!mask) continue;
+			const uint4 raw = stash[(i >> 1) * (uint32_t)g.SP + vv];
+			const P pv = *reinterpret_cast<const P*>(&raw);
+			#pragma unroll
+			for (int e = 0; e < VEC; e++)
+				if (mask >> e & 1u) { const float d = to_f<T>(pv.v[e]) - pivot; s1 += d; s2 = fmaf(d, d, s2); }
+		}
+	} else {
 	for (uint32_t base = threadIdx.x; base < (uint32_t)nslots; base += THREADS * kSlotUnroll) {
 		P v[kSlotUnroll];
 		bool ok[kSlotUnroll];
@@ -590,6 +669,7 @@ __global__ void __launch_bounds__(THREADS) bn_fwd_cluster_kernel(const T* __rest
 		#pragma unroll
 		for (int e = 0; e < VEC; e++)
 			if (mask >> e & 1u) { const float d = to_f<T>(pv.v[e]) - pivot; s1 += d; s2 = fmaf(d, d, s2); }
+	}
 	}
 	block_sum2<THREADS>(s1, s2, red);
 	cluster_sum2(s1, s2, part, g.CL);
@@ -632,7 +712,7 @@ __global__ void __launch_bounds__(THREADS) bn_fwd_cluster_kernel(const T* __rest
 	}
 }
 
-template <typename T, int VEC, int THREADS>
+template <typename T, int VEC, int THREADS, bool BULK>
 __global__ void __launch_bounds__(THREADS) bn_bwd_cluster_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx,
 																  ClusterGeo g, const float* __restrict__ scale,
 																  const float* __restrict__ save_mean, const float* __restrict__ save_invvar,
@@ -654,6 +734,44 @@ __global__ void __launch_bounds__(THREADS) bn_bwd_cluster_kernel(const T* __rest
 	const uint32_t nrows = (uint32_t)max(0, n1 - n0), S = (uint32_t)g.S;
 	const uint32_t plane0 = ((uint32_t)n0 * (uint32_t)g.C + (uint32_t)c) * S;
 	float s1 = 0.0f, s2 = 0.0f;
+	if (BULK) {
+		__shared__ uint64_t bar;
+		const uint32_t barp = smem_addr(&bar);
+		if (threadIdx.x == 0) mbar_init1(barp);
+		__syncthreads();
+		if (threadIdx.x < 32) {
+			const T* const src[2] = {x, dy};
+			uint4* const dst[2] = {stash, stash_dy};
+			bulk_load_planes<T, VEC>(g, plane0, nrows, src, dst, 2, barp);
+		}
+		mbar_wait0(barp);
+		for (uint32_t slot = threadIdx.x; slot < (uint32_t)nslots; slot += THREADS) {
+			const SlotGeo<VEC> q = slot_decode<VEC>(g, plane0, slot);
+			if (!q.full(S)) continue;
+			const uint4 rx = stash[slot], rg = stash_dy[slot];
+			const P v = *reinterpret_cast<const P*>(&rx), w = *reinterpret_cast<const P*>(&rg);
+			#pragma unroll
+			for (int e = 0; e < VEC; e++) {
+				const float gv = to_f<T>(w.v[e]);
+				s1 += gv;
+				s2 = fmaf(gv, to_f<T>(v.v[e]) - mean, s2);
+			}
+		}
+		for (uint32_t i = threadIdx.x; i < 2u * nrows; i += THREADS) {
+			uint32_t vv, e0;
+			const uint32_t mask = partial_vector<VEC>(g, plane0, i >> 1, (int)(i & 1u), vv, e0);
+			if (!mask) continue;
+			const uint4 rx = stash[(i >> 1) * (uint32_t)g.SP + vv], rg = stash_dy[(i >> 1) * (uint32_t)g.SP + vv];
+			const P pv = *reinterpret_cast<const P*>(&rx), pw = *reinterpret_cast<const P*>(&rg);
+			#pragma unroll
+			for (int e = 0; e < VEC; e++)
+				if (mask >> e & 1u) {
+					const float gv = to_f<T>(pw.v[e]);
+					s1 += gv;
+					s2 = fmaf(gv, to_f<T>(pv.v[e]) - mean, s2);
+				}
+		}
+	} else {
 	for (uint32_t base = threadIdx.x; base < (uint32_t)nslots; base += THREADS * UNR) {
 		P v[UNR], w[UNR];
 		bool ok[UNR];
@@ -695,6 +813,7 @@ __global__ void __launch_bounds__(THREADS) bn_bwd_cluster_kernel(const T* __rest
 				s2 = fmaf(gv, to_f<T>(pv.v[e]) - mean, s2);
 			}
 	}
+	}
 	block_sum2<THREADS>(s1, s2, red);
 	cluster_sum2(s1, s2, part, g.CL);
 
@@ -734,6 +853,7 @@ struct ClusterPlan {
 	int threads;             // 256 or 512
 	size_t smem;             // the stash
 	bool ok;
+	bool bulk;               // planes arrive by cp.async.bulk (the tensor must end on a 16-byte boundary: the last plane's cover is read whole)
 };
 
 int env_int(const char* name, int dflt)
@@ -785,6 +905,8 @@ ClusterPlan make_cluster_plan(std::initializer_list<const void*> ptrs, int64_t N
 	if (p.smem > kStashMax) { p.ok = false; return p; }
 	p.threads = slots >= 2048 ? 512 : 256;
 	if (force_threads == 256 || force_threads == 512) p.threads = force_threads;
+	static const bool bulk_on = env_int("PZ_BN_BULK", 1) != 0;
+	p.bulk = bulk_on && (N * C * S) % vec == 0;
 	return p;
 }
 
@@ -925,9 +1047,10 @@ int fwd_train(const void* x, void* y, int64_t N, int64_t C, int64_t S, const flo
 		// only rewrites planes it alone reads, and the pivot element is read by every CTA of the cluster before its barrier
 		const ClusterPlan cp = make_cluster_plan({x, y}, N, C, S, sizeof(T), 1);
 		if (cp.ok) {
-			if (cp.threads == 512)
-				return launch_cluster(bn_fwd_cluster_kernel<T, V, 512>, cp, s, (const T*)x, (T*)y, cp.g, scale, bias, rm, rv, sm, siv, (float)eps, (float)factor);
-			return launch_cluster(bn_fwd_cluster_kernel<T, V, 256>, cp, s, (const T*)x, (T*)y, cp.g, scale, bias, rm, rv, sm, siv, (float)eps, (float)factor);
+#define PZ_BN_FWD_CLUSTER(TH, BK) launch_cluster(bn_fwd_cluster_kernel<T, V, TH, BK>, cp, s, (const T*)x, (T*)y, cp.g, scale, bias, rm, rv, sm, siv, (float)eps, (float)factor)
+			if (cp.threads == 512) return cp.bulk ? PZ_BN_FWD_CLUSTER(512, true) : PZ_BN_FWD_CLUSTER(512, false);
+			return cp.bulk ? PZ_BN_FWD_CLUSTER(256, true) : PZ_BN_FWD_CLUSTER(256, false);
+#undef PZ_BN_FWD_CLUSTER
 		}
 	}
 	SumsPair sp;
@@ -982,9 +1105,10 @@ int bwd(const void* x, const void* dy, void* dx, int64_t N, int64_t C, int64_t S
 	{
 		const ClusterPlan cp = make_cluster_plan({x, dy, dx}, N, C, S, sizeof(T), 2);
 		if (cp.ok) {
-			if (cp.threads == 512)
-				return launch_cluster(bn_bwd_cluster_kernel<T, V, 512>, cp, s, (const T*)x, (const T*)dy, (T*)dx, cp.g, scale, sm, siv, dscale, dbias);
-			return launch_cluster(bn_bwd_cluster_kernel<T, V, 256>, cp, s, (const T*)x, (const T*)dy, (T*)dx, cp.g, scale, sm, siv, dscale, dbias);
+#define PZ_BN_BWD_CLUSTER(TH, BK) launch_cluster(bn_bwd_cluster_kernel<T, V, TH, BK>, cp, s, (const T*)x, (const T*)dy, (T*)dx, cp.g, scale, sm, siv, dscale, dbias)
+			if (cp.threads == 512) return cp.bulk ? PZ_BN_BWD_CLUSTER(512, true) : PZ_BN_BWD_CLUSTER(512, false);
+			return cp.bulk ? PZ_BN_BWD_CLUSTER(256, true) : PZ_BN_BWD_CLUSTER(256, false);
+#undef PZ_BN_BWD_CLUSTER
 		}
 	}
 	SumsPair sp;

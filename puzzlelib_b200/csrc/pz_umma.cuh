@@ -40,6 +40,21 @@
 
 namespace pzumma {
 
+// -DPZ_TIMELINE: per-role phase clocks of umma_gemm_kernel, summed over the launch (lane 0 of every warp adds its counters at the
+// end; read and reset with pz_debug_timeline).  Instrumented builds are for diagnosis only (tools/gpu_timeline.sh).
+#ifdef PZ_TIMELINE
+static __device__ unsigned long long pz_timeline[32];
+#define PZ_TL_DECL(n) long long tl_[n] = {}; long long tl_t = clock64();
+#define PZ_TL(i) { const long long now_ = clock64(); tl_[i] += now_ - tl_t; tl_t = now_; }
+#define PZ_TL_FLUSH(base, n) if (lane == 0) { for (int i_ = 0; i_ < (n); i_++) atomicAdd(&pz_timeline[(base) + i_], (unsigned long long)tl_[i_]); }
+#define PZ_TL_TOUCH(x) asm volatile("" ::"f"(x));
+#else
+#define PZ_TL_DECL(n)
+#define PZ_TL(i)
+#define PZ_TL_FLUSH(base, n)
+#define PZ_TL_TOUCH(x)
+#endif
+
 constexpr int BM = 128;          // tile rows  = TMEM lanes
 constexpr int BK = 32;           // floats per k-block = one 128-byte swizzle row
 // Producers work in NGROUPS independent groups of NPROD_WARPS warps: group g fills k-blocks g, g + NGROUPS, ... of the CTA's
@@ -60,7 +75,7 @@ constexpr int NEPI_WARPS_GEMM = 8;          // two warps per TMEM lane quadrant,
 constexpr int MMA_WARP = NPROD_WARPS_ALL;
 constexpr int EPI_WARP0 = NPROD_WARPS_ALL + 4;
 constexpr int NTHREADS = (EPI_WARP0 + NEPI_WARPS_GEMM) * 32;
-constexpr int REGS_PROD = 88, REGS_MMA = 32, REGS_EPI = 56;    // 512*88 + 128*32 + 256*56 <= 896*72
+constexpr int REGS_PROD = 88, REGS_MMA = 32, REGS_EPI = 56;    // 512*88 + 128*32 + 256*56 <= 896*72 (setmaxnreg.inc blocks until the CTA has released enough)
 template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 constexpr int INVALID = -(1 << 28);
@@ -100,7 +115,8 @@ __device__ __forceinline__ void split3(uint32_t x, const FastDiv& d12, const Fas
 // MN_TAP / K_TAP / K_DENSE are the fast paths: per-row (or per-k) base offsets and tap-validity bit masks are
 // computed once, the per-element work is one predicated load + one tf32 rounding.
 enum { MODE_K_GENERAL = 0, MODE_K_SIMPLE = 1, MODE_MN_GENERAL = 2, MODE_MN_SIMPLE = 3, MODE_MN_TAP = 4, MODE_K_TAP = 5,
-	   MODE_K_DENSE = 6, MODE_TMA = 7, MODE_MN_CHAN = 8, MODE_K_POS_TAP = 9, MODE_K_POS_DENSE = 10 };
+	   MODE_K_DENSE = 6, MODE_TMA = 7, MODE_MN_CHAN = 8, MODE_K_POS_TAP = 9, MODE_K_POS_DENSE = 10, MODE_MN_VEC = 11,
+	   MODE_K_POS_VEC = 12 };
 
 struct Operand {
 	const void* ptr;             // float or 16-bit (half / bfloat16) elements; all strides below are in ELEMENTS
@@ -131,6 +147,10 @@ struct Epilogue {
 	float alpha, beta;
 	int bias_mode;               // 0 none, 1 bias[n], 2 bias[m]
 	int atomic;                  // 1: out += alpha*acc with red.global.add (split-K)
+	// staged store (fp32 plain stores with bias_mode 0 / 1, see the epilogue of umma_gemm_kernel): the accumulator goes through a
+	// [32 columns][128 rows] shared-memory tile so that a warp writes the 512 contiguous bytes of one output column back to back.
+	// 0 off, 1 four 128-byte requests per column, 2 one 16-byte-lane request (row offsets contiguous and 16-byte aligned)
+	int staged;
 	long long group_stride;
 	int bias_group_stride;
 	// col2im epilogue (dgrad of a filter with very few input channels, see pz_conv.cu): row m = (image, p, q) of dy, column
@@ -242,6 +262,13 @@ __device__ __forceinline__ float ldg_pred(const void* p, bool ok)
 	asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\tmov.b32 %0, 0;\n\t@p ld.global.nc.b32 %0, [%1];\n\t}"
 				 : "=f"(v) : "l"(p), "r"((int)ok));
 	return v;
+}
+// 16-byte lane (the address must be 16-byte aligned when the predicate holds)
+__device__ __forceinline__ void ldg128_pred(const void* p, bool ok, float& a, float& b, float& c, float& d)
+{
+	asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %5, 0;\n\tmov.b32 %0, 0;\n\tmov.b32 %1, 0;\n\tmov.b32 %2, 0;\n\tmov.b32 %3, 0;\n\t"
+				 "@p ld.global.nc.v4.b32 {%0, %1, %2, %3}, [%4];\n\t}"
+				 : "=f"(a), "=f"(b), "=f"(c), "=f"(d) : "l"(p), "r"((int)ok));
 }
 __device__ __forceinline__ uint32_t ldg16_pred(const void* p, bool ok)
 {
@@ -839,6 +866,103 @@ struct KPosTapProducer {
 	}
 };
 
+// ---- 16-byte lanes (float tensors whose planes are a multiple of four elements and 16-byte aligned: 28 x 28, 14 x 14, ...)
+//
+// A stage holds the same bytes as with the 4-byte producers; a thread issues 8 LDG.128 instead of 32 LDG.32 for them, and the
+// shared-memory image is written with STS.128 in both cases.
+//
+// MnVec: the MnChan operand of a 1 x 1 / stride-1 / un-padded filter (rows = positions, contiguous in memory; k = channels).  A
+// thread owns FOUR consecutive rows (one 16-byte vector per channel) and 8 channels: the 4 x 4 blocks it loads are transposed by
+// register naming alone -- vector e of the load is channel e, word j of the store is channel j.  lane = (row quad % 8, channel
+// quad % 4): a load instruction reads 4 channels x 128 contiguous bytes, a store instruction hits every 16-byte bank group 4 times.
+template <int ROWS>
+struct MnVecProducer {
+	static_assert(ROWS == 128, "one row quad per thread");
+	static constexpr int NV = 32;
+	int poff, row0, cq0;
+	bool rvalid;
+
+	__device__ __forceinline__ void init(const Operand& op, int tile_row0, int warp, int lane, uint32_t)
+	{
+		row0 = (warp * 8 + (lane & 7)) * 4;
+		cq0 = lane >> 3;
+		const int row = tile_row0 + row0;
+		rvalid = row < op.rows;                                       // rows % 4 == 0: a quad is valid as a whole
+		const uint32_t r0 = fdiv((uint32_t)(rvalid ? row : 0), op.rd12);
+		poff = (int)r0 * op.rs0 + (int)((uint32_t)(rvalid ? row : 0) - r0 * op.rd12.d);
+	}
+	__device__ __forceinline__ void load(const Operand& op, const float* __restrict__ base, int kb, float (&v)[NV])
+	{
+		const int c0 = kb * 32 + cq0 * 4;
+		const char* __restrict__ ptr = reinterpret_cast<const char*>(base + ((long long)c0 * op.ks0 + poff));
+		const unsigned long long ksb = (unsigned long long)(unsigned)op.ks0 * 4ull;
+		#pragma unroll
+		for (int it = 0; it < 2; it++) {
+			#pragma unroll
+			for (int e = 0; e < 4; e++) {
+				const int j = it * 16 + e;
+				ldg128_pred(ptr + ksb * (unsigned)j, rvalid && c0 + j < op.chans, v[it * 16 + e * 4], v[it * 16 + e * 4 + 1], v[it * 16 + e * 4 + 2],
+							v[it * 16 + e * 4 + 3]);
+			}
+		}
+	}
+	__device__ __forceinline__ void store(uint32_t tile, const float (&v)[NV])
+	{
+		#pragma unroll
+		for (int it = 0; it < 2; it++) {
+			const int chunk = it * 4 + cq0;
+			#pragma unroll
+			for (int j = 0; j < 4; j++) {
+				const int row = row0 + j;
+				sts128(tile + row * 128 + ((chunk ^ (row & 7)) << 4), to_tf32(v[it * 16 + j]), to_tf32(v[it * 16 + 4 + j]), to_tf32(v[it * 16 + 8 + j]),
+					   to_tf32(v[it * 16 + 12 + j]));
+			}
+		}
+	}
+};
+
+// KPosVec: the KPosDense operand (rows = channel planes, k = positions of one image per k-block).  lane = (row % 4, 16-byte chunk of
+// the 128-byte k-block): a load instruction reads 4 rows x 128 contiguous bytes, the vector goes to shared memory as it is.
+template <int ROWS>
+struct KPosVecProducer {
+	static constexpr int NR = ROWS / 16;
+	static constexpr int NV = NR * 4;
+	int row0, chunk, nvalid;
+	long long rowoff0, step;
+
+	__device__ __forceinline__ void init(const Operand& op, int tile_row0, int warp, int lane, uint32_t)
+	{
+		row0 = warp * 4 + (lane >> 3);
+		chunk = lane & 7;
+		const int row = tile_row0 + row0;
+		rowoff0 = (long long)row * op.rs0;
+		step = 16ll * op.rs0 * 4;
+		const int left = op.rows - row;
+		nvalid = left <= 0 ? 0 : min(NR, (left + 15) / 16);
+	}
+	__device__ __forceinline__ void load(const Operand& op, const float* __restrict__ base, int kb, float (&v)[NV])
+	{
+		const uint32_t n = fdiv((uint32_t)kb, op.kbdiv);              // warp-uniform
+		const int pos = (int)((uint32_t)kb - n * op.kbdiv.d) * BK + chunk * 4;
+		const int cnt = pos < op.plane ? nvalid : 0;                  // plane % 4 == 0: a vector is valid as a whole
+		const char* __restrict__ p = reinterpret_cast<const char*>(base + (rowoff0 + (long long)n * op.ks0 + pos));
+		#pragma unroll
+		for (int i = 0; i < NR; i++) {
+			ldg128_pred(p, i < cnt, v[i * 4], v[i * 4 + 1], v[i * 4 + 2], v[i * 4 + 3]);
+			p += step;
+		}
+	}
+	__device__ __forceinline__ void store(uint32_t tile, const float (&v)[NV])
+	{
+		#pragma unroll
+		for (int i = 0; i < NR; i++) {
+			const uint32_t row = (uint32_t)(row0 + i * 16);
+			sts128(tile + row * 128 + ((((uint32_t)chunk) ^ (row & 7)) << 4), to_tf32(v[i * 4]), to_tf32(v[i * 4 + 1]), to_tf32(v[i * 4 + 2]),
+				   to_tf32(v[i * 4 + 3]));
+		}
+	}
+};
+
 // ------------------------------------------------------------------------------------------ 16-bit producers
 // half / bfloat16 operands: a k-block is 64 elements (one 128-byte swizzle row), a 16-byte chunk 8 elements.  Values travel
 // through the producers' registers as packed pairs (bit patterns held in `float` registers, never touched by arithmetic) and are
@@ -1153,6 +1277,8 @@ template <int ROWS, bool WIDE, bool H16> struct ProducerSel<ROWS, MODE_TMA, WIDE
 template <int ROWS, bool WIDE> struct ProducerSel<ROWS, MODE_MN_CHAN, WIDE, false> { using type = MnChanProducer<ROWS, WIDE>; };
 template <int ROWS, bool WIDE> struct ProducerSel<ROWS, MODE_K_POS_TAP, WIDE, false> { using type = KPosTapProducer<ROWS, WIDE>; };
 template <int ROWS, bool WIDE> struct ProducerSel<ROWS, MODE_K_POS_DENSE, WIDE, false> { using type = KPosDenseProducer<ROWS>; };
+template <int ROWS, bool WIDE> struct ProducerSel<ROWS, MODE_MN_VEC, WIDE, false> { using type = MnVecProducer<ROWS>; };
+template <int ROWS, bool WIDE> struct ProducerSel<ROWS, MODE_K_POS_VEC, WIDE, false> { using type = KPosVecProducer<ROWS>; };
 // half / bfloat16 operands
 template <int ROWS, bool CDIV> struct ProducerSel<ROWS, MODE_MN_GENERAL, CDIV, true> { using type = MnProducer16<ROWS, CDIV>; };
 template <int ROWS, bool WIDE> struct ProducerSel<ROWS, MODE_MN_CHAN, WIDE, true> { using type = MnChanProducer16<ROWS, WIDE>; };
@@ -1299,6 +1425,68 @@ __device__ __forceinline__ void epilogue_chunk(const Epilogue& E, const uint32_t
 	}
 }
 
+// Staged epilogue of one tile (Epilogue::staged; the 8 epilogue warps together).  Rounds of 32 columns: phase 1 moves each warp's
+// 16 columns x 32 rows from TMEM to the staging tile stg[column][row] (rows contiguous, 16 KB); phase 2 lets warp ew write
+// columns 4*ew .. 4*ew+3, each as the 512 contiguous bytes of 128 rows -- one 16-byte-lane request (VEC: row offsets contiguous
+// and 16-byte aligned) or four adjacent 128-byte requests issued back to back.  Measured on the store pattern alone
+// (tools/ubench/store_pattern.cu): 4.9 TB/s against 3.0 TB/s for 128-byte requests scattered over the channel planes.
+template <bool VEC>
+__device__ __forceinline__ void staged_tile(const Epilogue& E, int row0, int col0, int group, int ncols, uint32_t tmem_d, uint32_t stg, int ew,
+											 int lane)
+{
+	const int half = ew >> 2, lg = ew & 3;
+	constexpr int NOFF = VEC ? 1 : 4;
+	int roff[NOFF];
+	bool rval[NOFF];
+	#pragma unroll
+	for (int e = 0; e < NOFF; e++) {
+		const int mm = row0 + (VEC ? 4 * lane : 32 * e + lane);
+		rval[e] = mm < E.M;
+		int a0, a1, a2;
+		split3((uint32_t)(rval[e] ? mm : 0), E.md12, E.md2, a0, a1, a2);
+		roff[e] = a0 * E.ms0 + a1 * E.ms1 + a2 * E.ms2;
+	}
+	float* outg = (float*)E.out + (long long)group * E.group_stride + (long long)col0 * E.ncs;
+	const float* biasg = (E.bias && E.bias_mode == 1) ? (const float*)E.bias + (long long)group * E.bias_group_stride + col0 : nullptr;
+	const float alpha = E.alpha;
+	const uint32_t wr = stg + (uint32_t)(((half * EPI_COLS) * BM + lg * 32 + lane) * 4);
+	const uint32_t rd = stg + (uint32_t)(((ew * 4) * BM + (VEC ? 4 * lane : lane)) * 4);
+
+	uint32_t v[EPI_COLS];
+	if (half * EPI_COLS < ncols) tmem_ld16(tmem_d + (uint32_t)(half * EPI_COLS), v);
+	#pragma unroll 1
+	for (int c0 = 0; c0 < ncols; c0 += 32) {
+		if (c0 + half * EPI_COLS < ncols) {
+			tmem_wait_ld(v);
+			#pragma unroll
+			for (int j = 0; j < EPI_COLS; j++) sts32(wr + j * BM * 4, v[j]);
+		}
+		named_bar_sync(5, NEPI_WARPS_GEMM * 32);
+		if (c0 + 32 + half * EPI_COLS < ncols) tmem_ld16(tmem_d + (uint32_t)(c0 + 32 + half * EPI_COLS), v);
+		#pragma unroll 1
+		for (int i = 0; i < 4; i++) {
+			const int cl = c0 + ew * 4 + i;
+			if (cl >= ncols) break;
+			const float b = biasg ? __ldg(biasg + cl) : 0.0f;
+			float* dstc = outg + (long long)cl * E.ncs;
+			if (VEC) {
+				float x0, x1, x2, x3;
+				asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x0), "=f"(x1), "=f"(x2), "=f"(x3) : "r"(rd + i * BM * 4));
+				if (rval[0])
+					*reinterpret_cast<float4*>(dstc + roff[0]) = make_float4(fmaf(alpha, x0, b), fmaf(alpha, x1, b), fmaf(alpha, x2, b), fmaf(alpha, x3, b));
+			} else {
+				float x[4];
+				#pragma unroll
+				for (int e = 0; e < 4; e++) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x[e]) : "r"(rd + (i * BM + 32 * e) * 4));
+				#pragma unroll
+				for (int e = 0; e < 4; e++)
+					if (rval[e]) dstc[roff[e]] = fmaf(alpha, x[e], b);
+			}
+		}
+		named_bar_sync(5, NEPI_WARPS_GEMM * 32);
+	}
+}
+
 // ------------------------------------------------------------------------------------------ the kernel
 template <int BN, int AMODE, int BMODE, bool CDIV, bool H16>
 __global__ void __launch_bounds__(NTHREADS, 1) umma_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ CUtensorMap tmapB)
@@ -1384,7 +1572,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) umma_gemm_kernel(const __grid_con
 		advance_stage(grp);
 		const EL* baseA = (const EL*)p.A.ptr;
 		const EL* baseB = (const EL*)p.B.ptr;
+		PZ_TL_DECL(8)
 		while (lvalid) {
+			PZ_TL(6)
 			if (inited != lwork) {
 				// first k-block this group sees of a work unit: per-tile producer state + the group's smem tables
 				named_bar_sync(1 + grp, NPROD);                       // every warp of the group is done reading the old tables
@@ -1395,9 +1585,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) umma_gemm_kernel(const __grid_con
 				named_bar_sync(1 + grp, NPROD);
 				inited = lwork;
 			}
+			PZ_TL(0)
 			prodA.load(p.A, baseA, lkb, va);
 			prodB.load(p.B, baseB, lkb, vb);
+			PZ_TL(1)
 			mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+			PZ_TL(2)
+			PZ_TL_TOUCH(va[PA::NV - 1])
+			PZ_TL(3)
 			const uint32_t tileA = smem0 + stage * C::STAGE_BYTES;
 			if (B_TMA) {
 				if (gw == 0 && lane == 0) {
@@ -1410,12 +1605,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) umma_gemm_kernel(const __grid_con
 			}
 			prodA.store(tileA, va);
 			prodB.store(tileA + BM * 128, vb);
+			PZ_TL(4)
 			fence_async_smem();
 			__syncwarp();
 			if (lane == 0) mbar_arrive(bar_full + 8 * stage);
+			PZ_TL(5)
 			advance(NGROUPS);
 			advance_stage(NGROUPS);
 		}
+		PZ_TL_FLUSH(0, 8)
 	} else if (warp < EPI_WARP0) {
 		// ===================== MMA issuer (one thread of warp 16) =====================
 		setmaxnreg_dec<REGS_MMA>();
@@ -1425,14 +1623,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) umma_gemm_kernel(const __grid_con
 			uint32_t phase = 0;
 			int as = 0;
 			uint32_t aphase = 0;
+			PZ_TL_DECL(4)
 			for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
 				const Work w = decode_work(p, work);
+				PZ_TL(0)
 				mbar_wait(bar_accempty + 8 * as, aphase ^ 1);        // epilogue has drained this accumulator buffer
 				tc_fence_after();
+				PZ_TL(1)
 				const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
 				for (int kb = w.kb_begin; kb < w.kb_end; kb++) {
+					PZ_TL(3)
 					mbar_wait(bar_full + 8 * stage, phase);
 					tc_fence_after();
+					PZ_TL(2)
 					if (lane == 0) {
 						const uint32_t tileA = smem0 + stage * C::STAGE_BYTES;
 						const uint64_t da = make_smem_desc(tileA), db = make_smem_desc(tileA + BM * 128);
@@ -1450,7 +1653,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) umma_gemm_kernel(const __grid_con
 				if (lane == 0) umma_commit(bar_accfull + 8 * as);
 				__syncwarp();
 				if (++as == 2) { as = 0; aphase ^= 1; }
+				PZ_TL(3)
 			}
+			PZ_TL_FLUSH(8, 4)
 			tc_fence_before();
 		}
 	} else {
@@ -1460,8 +1665,31 @@ __global__ void __launch_bounds__(NTHREADS, 1) umma_gemm_kernel(const __grid_con
 		const int lg = warp & 3;
 		int as = 0;
 		uint32_t aphase = 0;
+		// staged stores reuse the producer tables, which the channel-ordered / 16-byte producers and the TMA operand do not use
+		constexpr bool STAGED_OK = (AMODE == MODE_MN_CHAN || AMODE == MODE_MN_VEC) && BMODE == MODE_TMA && !H16;
+		static_assert(NGROUPS * C::TABLE_BYTES >= 32 * BM * 4, "the staging tile does not fit the table area");
+		PZ_TL_DECL(2)
+		// (two separate tile loops: sharing one would keep the state of both paths live across it)
+		if (STAGED_OK && E.staged) {
+			for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
+				const Work w = decode_work(p, work);
+				PZ_TL(1)
+				mbar_wait(bar_accfull + 8 * as, aphase);
+				tc_fence_after();
+				PZ_TL(0)
+				const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN) + ((uint32_t)(lg * 32) << 16);
+				const int ncols = (p.debug_skip & 1) ? 0 : min(BN, E.N - w.n_tile * BN);
+				if (E.staged == 2) staged_tile<true>(E, w.m_tile * BM, w.n_tile * BN, w.group, ncols, tmem_d, tables, warp - EPI_WARP0, lane);
+				else staged_tile<false>(E, w.m_tile * BM, w.n_tile * BN, w.group, ncols, tmem_d, tables, warp - EPI_WARP0, lane);
+				tc_fence_before();
+				__syncwarp();
+				if (lane == 0) mbar_arrive(bar_accempty + 8 * as);
+				if (++as == 2) { as = 0; aphase ^= 1; }
+			}
+		} else
 		for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
 			const Work w = decode_work(p, work);
+			PZ_TL(1)
 			const int m = w.m_tile * BM + lg * 32 + lane;
 			const bool mvalid = m < E.M;
 			int m0, m1, m2;
@@ -1474,6 +1702,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) umma_gemm_kernel(const __grid_con
 
 			mbar_wait(bar_accfull + 8 * as, aphase);
 			tc_fence_after();
+			PZ_TL(0)
 			const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN) + ((uint32_t)(lg * 32) << 16);
 			const int ncols = min(BN, E.N - w.n_tile * BN);       // valid columns of this tile (> 0)
 			// fast paths (straight-line, 2 - 3 instructions per element): plain store and split-K red.add
@@ -1502,6 +1731,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) umma_gemm_kernel(const __grid_con
 			if (lane == 0) mbar_arrive(bar_accempty + 8 * as);
 			if (++as == 2) { as = 0; aphase ^= 1; }
 		}
+		PZ_TL(1)
+		PZ_TL_FLUSH(12, 2)
 	}
 
 	tc_fence_before();

@@ -37,7 +37,8 @@ class NcclError(CudaError):
 PZ_OK, PZ_ERR_VALUE, PZ_ERR_CUDA, PZ_ERR_MEMORY, PZ_ERR_NCCL, PZ_ERR_UNSUPPORTED = range(6)
 
 LIBNAME = "libpzb200.so"
-LIBPATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), LIBNAME)
+# PZB200_LIB: an instrumented build of the same library (tools/gpu_timeline.sh); never a different implementation
+LIBPATH = os.environ.get("PZB200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), LIBNAME)
 
 
 def _load():
@@ -97,6 +98,7 @@ _SIGNATURES = {
 	"pz_graph_end": [_P, POINTER(_P)],
 	"pz_graph_launch": [_P, _P],
 	"pz_graph_destroy": [_P],
+	"pz_debug_timeline": [_P],
 	"pz_stream_create": [POINTER(_P)],
 	"pz_stream_destroy": [_P],
 	"pz_stream_synchronize": [_P],

@@ -5,8 +5,9 @@ mapped memory with `multiprocessing.SimpleQueue`s as the control plane (referenc
 model and the NodeInfo surface stay -- `sumTensor(name, tensor)`, `broadcastBuffer(name, buffer)`, `meanValue(value)`,
 `index`, `gridsize`, `device`, `close()` -- so `Optimizer` is untouched, while the data plane is ONE ncclAllReduce /
 ncclBroadcast per call over NVLink / NVSwitch and the control plane (exchange of the 128-byte ncclUniqueId, scalar
-means, barriers) is a `Rendezvous` object.  `TorchRendezvous` rides on torch.distributed's gloo backend (present in the
-image and what `torchrun` sets up for bench.py); torch is plumbing here -- no tensor of the hot path ever enters it.
+means, barriers) is a `Rendezvous` object: `SocketRendezvous` (plain TCP, what `runGrid` uses -- like the reference's
+queues it needs nothing beyond the standard library) or `TorchRendezvous` over torch.distributed's gloo backend for processes
+that `torchrun` started (bench.py).  No tensor of the hot path ever enters either.
 """
 import ctypes
 import os
@@ -16,8 +17,116 @@ from . import driver
 from .driver import lib, check, dtypeCode
 
 
+class SocketRendezvous:
+	"""Host-side control plane over plain TCP: a star through rank 0 (the role of the parent's SimpleQueues in Grid.py:14-57).
+
+	Every collective is one round trip: the other ranks send their contribution to rank 0, which combines and answers."""
+
+	def __init__(self, rank, size, masterAddr="127.0.0.1", masterPort=29533, timeout=600):
+		import socket
+		import time
+
+		self.rank, self.size = int(rank), int(size)
+		self.peers = {}
+
+		if self.rank == 0:
+			server = socket.socket(socket.AF_INET, socket.SOCK_STREAM)
+			server.setsockopt(socket.SOL_SOCKET, socket.SO_REUSEADDR, 1)
+			server.bind((masterAddr, int(masterPort)))
+			server.listen(self.size)
+			server.settimeout(timeout)
+			try:
+				while len(self.peers) < self.size - 1:
+					conn, _ = server.accept()
+					conn.setsockopt(socket.IPPROTO_TCP, socket.TCP_NODELAY, 1)
+					conn.settimeout(timeout)
+					peer = self._recv(conn)
+					if not isinstance(peer, int) or not 0 < peer < self.size or peer in self.peers:
+						raise RuntimeError("rendezvous: unexpected hello %r" % (peer, ))
+					self.peers[peer] = conn
+			finally:
+				server.close()
+		else:
+			deadline = time.time() + timeout
+			while True:
+				conn = socket.socket(socket.AF_INET, socket.SOCK_STREAM)
+				try:
+					conn.connect((masterAddr, int(masterPort)))
+					break
+				except OSError:
+					conn.close()
+					if time.time() > deadline:
+						raise
+					time.sleep(0.05)
+			conn.setsockopt(socket.IPPROTO_TCP, socket.TCP_NODELAY, 1)
+			conn.settimeout(timeout)
+			self._send(conn, self.rank)
+			self.peers[0] = conn
+
+	@staticmethod
+	def _send(conn, obj):
+		import pickle
+		import struct
+		payload = pickle.dumps(obj, protocol=pickle.HIGHEST_PROTOCOL)
+		conn.sendall(struct.pack("<Q", len(payload)) + payload)
+
+	@staticmethod
+	def _recv(conn):
+		import pickle
+		import struct
+
+		def exactly(n):
+			chunks = []
+			while n > 0:
+				chunk = conn.recv(n)
+				if not chunk:
+					raise ConnectionError("rendezvous: peer closed the connection")
+				chunks.append(chunk)
+				n -= len(chunk)
+			return b"".join(chunks)
+
+		(n, ) = struct.unpack("<Q", exactly(8))
+		return pickle.loads(exactly(n))
+
+	def _collective(self, value, combine):
+		"""every rank contributes `value`; all get combine([values in rank order])"""
+		if self.size == 1:
+			return combine([value])
+		if self.rank == 0:
+			values = [value] + [self._recv(self.peers[r]) for r in range(1, self.size)]
+			result = combine(values)
+			for r in range(1, self.size):
+				self._send(self.peers[r], result)
+			return result
+		self._send(self.peers[0], value)
+		return self._recv(self.peers[0])
+
+	def broadcastBytes(self, payload, root=0):
+		return self._collective(payload if self.rank == root else None, lambda values: values[root])
+
+	def barrier(self):
+		self._collective(None, lambda values: None)
+
+	def maxValue(self, value):
+		return self._collective(float(value), max)
+
+	def sumValue(self, value):
+		return self._collective(float(value), sum)
+
+	def meanValue(self, value):
+		return self.sumValue(value) / self.size
+
+	def close(self):
+		for conn in self.peers.values():
+			try:
+				conn.close()
+			except OSError:
+				pass
+		self.peers = {}
+
+
 class TorchRendezvous:
-	"""Host-side control plane over torch.distributed (gloo): bytes broadcast, barrier, float max / mean."""
+	"""The same control plane over torch.distributed (gloo), for processes that torchrun launched and initialised."""
 
 	def __init__(self, rank=None, size=None, masterAddr=None, masterPort=None, timeout=600):
 		import datetime
@@ -304,7 +413,7 @@ def _nodeRunner(target, index, size, device, port, args, kwargs):
 	from PuzzleLib import Config
 	Config.allowMultiContext = True
 
-	nodeinfo = NodeInfo(index, size, device, TorchRendezvous(index, size, "127.0.0.1", port) if size > 1 else None)
+	nodeinfo = NodeInfo(index, size, device, SocketRendezvous(index, size, "127.0.0.1", port) if size > 1 else None)
 	try:
 		driver.Device(device).set()
 		nodeinfo.attach()

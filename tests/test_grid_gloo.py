@@ -41,3 +41,35 @@ def test_two_ranks_over_gloo():
 	for r in results:
 		assert np.allclose(r["grad_mean_head"], want, atol=1e-7)
 	assert results[0]["shard"] == [0, 65] and results[1]["shard"] == [65, 130]
+
+
+_SOCKET_WORKER = """
+import json, sys
+sys.path.insert(0, %r)
+from puzzlelib_b200.grid import SocketRendezvous
+rank, size, port = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
+rv = SocketRendezvous(rank, size, "127.0.0.1", port, timeout=120)
+out = {"rank": rank}
+out["uid"] = rv.broadcastBytes(bytes(range(128)) if rank == 0 else None, root=0) == bytes(range(128))
+out["from2"] = rv.broadcastBytes(b"two" if rank == 2 else None, root=2).decode()
+out["max"], out["sum"], out["mean"] = rv.maxValue(rank * 1.5), rv.sumValue(rank + 1), rv.meanValue(2.0 * rank)
+rv.barrier()
+rv.close()
+print(json.dumps(out), flush=True)
+"""
+
+
+def test_socket_rendezvous_three_ranks():
+	"""the torch-free control plane `runGrid` uses: unique-id broadcast from any root, max / sum / mean, barrier"""
+	root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+	port = _free_port()
+	procs = [subprocess.Popen([sys.executable, "-c", _SOCKET_WORKER % root, str(rank), "3", str(port)], stdout=subprocess.PIPE,
+							  stderr=subprocess.PIPE, text=True) for rank in range(3)]
+	results = []
+	for proc in procs:
+		stdout, stderr = proc.communicate(timeout=300)
+		assert proc.returncode == 0, stderr[-2000:]
+		results.append(json.loads(stdout.strip().splitlines()[-1]))
+	for r in results:
+		assert r["uid"] and r["from2"] == "two"
+		assert r["max"] == 3.0 and r["sum"] == 6.0 and r["mean"] == 2.0

@@ -29,6 +29,25 @@ def timeit(fn, reps=5):
 	return e0.timeTill(e1) / reps
 
 
+def timeline(launches):
+	"""per-role phase breakdown of the tcgen05 engine (instrumented library only: PZB200_LIB=puzzlelib_b200/libpzb200_timeline.so)"""
+	import ctypes
+	buf = (ctypes.c_ulonglong * 32)()
+	if driver.lib.pz_debug_timeline(ctypes.cast(buf, ctypes.c_void_p)) != 0:
+		return ""
+	v = [float(x) for x in buf]
+	sms, ghz = 148.0, 1.965
+	def us(x, warps):      # clock sum -> microseconds per warp per launch (upper bound on the grid: 148 CTAs)
+		return x / (warps * sms * launches) / (ghz * 1e3)
+	prod = ["setup", "issue", "wait_empty", "wait_data", "store", "fence+arrive", "advance"]
+	mma = ["decode", "wait_accempty", "wait_full", "mma+commit"]
+	epi = ["wait_accfull", "drain+store"]
+	out = ["    producers (us/warp): " + "  ".join("%s %.1f" % (n, us(v[i], 16)) for i, n in enumerate(prod)),
+		   "    mma thread (us):     " + "  ".join("%s %.1f" % (n, us(v[8 + i], 1)) for i, n in enumerate(mma)),
+		   "    epilogue (us/warp):  " + "  ".join("%s %.1f" % (n, us(v[12 + i], 8)) for i, n in enumerate(epi))]
+	return "\n".join(out)
+
+
 def main():
 	N = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 	only = sys.argv[2] if len(sys.argv) > 2 else None
@@ -48,16 +67,24 @@ def main():
 		dw = bnd.GPUArray.zeros((K, C, R, R), np.float32)
 		flops = 2.0 * N * K * P * P * C * R * R
 		nbytes = 4.0 * (x.size + w.size + y.size)
-		t = {
-			"fprop": timeit(lambda: bnd.dnn.convNd(x, w, None, s, p, 1, 1, out=y)),
-			"dgrad": timeit(lambda: bnd.dnn.convNdBackwardData(dy, w, None, x, s, p, 1, None, 1, out=dx, allocator=bnd.memoryPool)),
-			"wgrad": timeit(lambda: bnd.dnn.convNdBackwardParams(x, dy, w, s, p, 1, 1, False, False, dw, None, 1.0, 1.0)),
+		passes = {
+			"fprop": lambda: bnd.dnn.convNd(x, w, None, s, p, 1, 1, out=y),
+			"dgrad": lambda: bnd.dnn.convNdBackwardData(dy, w, None, x, s, p, 1, None, 1, out=dx, allocator=bnd.memoryPool),
+			"wgrad": lambda: bnd.dnn.convNdBackwardParams(x, dy, w, s, p, 1, 1, False, False, dw, None, 1.0, 1.0),
 		}
+		t, tl = {}, {}
+		for name, fn in passes.items():
+			timeline(1)
+			t[name] = timeit(fn)
+			tl[name] = timeline(6)
 		cells = []
 		for name in ("fprop", "dgrad", "wgrad"):
 			total[name] += t[name] * count
 			cells.append("%6.3f|%5.1f|%5.0f" % (t[name], flops / t[name] / 1e9, nbytes / t[name] / 1e6))
 		print("%2d %4dx%-3d^2 -> %4d %dx%d s%d  x%d   %s" % (idx, C, H, K, R, R, s, count, "  ".join(cells)))
+		for name in ("fprop", "dgrad", "wgrad"):
+			if tl[name]:
+				print("  %s\n%s" % (name, tl[name]))
 	print("sum over the net (ms): fprop %.2f dgrad %.2f wgrad %.2f total %.2f" % (total["fprop"], total["dgrad"], total["wgrad"], sum(total.values())))
 
 
