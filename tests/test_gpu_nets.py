@@ -476,3 +476,65 @@ def test_step_graph_warms_until_scalars_settle_and_redraws_dropout(M):
 
 	with pytest.raises(RuntimeError, match="Adam"):
 		driver.StepGraph(adamStep, warmup=2, maxWarmup=6)
+
+
+def test_checkpoint_round_trip_through_the_reference_save_and_load(M):
+	"""the reference's own Module / Container / Optimizer save + load above the seam.  The file object is an
+	in-memory stand-in with h5py's call surface (tests/h5standin.py; h5py is not in this image) -- the backend's part of a
+	checkpoint is GPUArray.get / set, parameters shared through varlinks, batch-norm running statistics as attrs."""
+	import h5standin
+	from PuzzleLib.Containers.Sequential import Sequential
+	from PuzzleLib.Modules import Conv2D, BatchNorm2D, Activation, MaxPool2D, Flatten, Linear
+	from PuzzleLib.Modules.Activation import relu
+	from PuzzleLib.Optimizers.MomentumSGD import MomentumSGD
+	from PuzzleLib.Backend import gpuarray
+
+	def build(seed):
+		np.random.seed(seed)
+		net = Sequential(name="ckpt")
+		net.append(Conv2D(3, 8, 3, pad=1, name="conv"))
+		net.append(BatchNorm2D(8, name="bn"))
+		net.append(Activation(relu, name="relu"))
+		net.append(MaxPool2D(name="pool"))
+		net.append(Flatten(name="flat"))
+		net.append(Linear(8 * 4 * 4, 5, name="fc"))
+		return net
+
+	rng = np.random.RandomState(0)
+	x = gpuarray.to_gpu(rng.randn(6, 3, 8, 8).astype(np.float32))
+	g = gpuarray.to_gpu(rng.randn(6, 5).astype(np.float32))
+
+	src = build(1)
+	opt = MomentumSGD(learnRate=0.1, momRate=0.9)
+	opt.setupOn(src, useGlobalState=True)
+	for _ in range(3):                       # a few steps: running statistics and momentum state become non-trivial
+		src.zeroGradParams()
+		src(x)
+		src.backward(g)
+		opt.update()
+
+	hdf, ohdf = h5standin.File(), h5standin.File()
+	src.save(hdf=hdf)
+	opt.save(ohdf)
+	assert hdf.closed == 1 and {"params", "links", "attrs"} <= set(hdf.keys())
+
+	dst = build(2)
+	assert not np.allclose(dst["conv"].vars["W"].data.get(), src["conv"].vars["W"].data.get())
+	dst.load(hdf)
+	for mod in ("conv", "bn", "fc"):
+		for vname, var in src[mod].vars.items():
+			assert np.array_equal(var.data.get(), dst[mod].vars[vname].data.get()), (mod, vname)
+	for aname, attr in src["bn"].attrs.items():
+		assert np.array_equal(attr.get(), dst["bn"].attrs[aname].get()), aname
+
+	src.evalMode()
+	dst.evalMode()
+	assert np.array_equal(src(x).get(), dst(x).get())
+
+	opt2 = MomentumSGD(learnRate=0.5, momRate=0.1)
+	opt2.setupOn(dst, useGlobalState=True)
+	opt2.load(ohdf)
+	assert opt2.learnRate == opt.learnRate and opt2.momRate == opt.momRate and opt2.t == opt.t == 3
+	for sname, state in opt.states.items():
+		for ename, entity in state.items():
+			assert np.array_equal(entity.get(), opt2.states[sname][ename].get()), (sname, ename)
