@@ -92,6 +92,35 @@ int pz_graph_begin(void* stream);
 int pz_graph_end(void* stream, void** exec);
 int pz_graph_launch(void* exec, void* stream);
 int pz_graph_destroy(void* exec);
+/* ---- kernel modules next to the hot path (backend.prelumod / padmod / embedmod / upsamplemod) ----
+ * PReLU over [N][C][S] float32 tensors, one slope per channel or (shared != 0) one for all -- Cuda/Kernels/PRelu.py:69-132 */
+int pz_prelu_fwd(const void* x, const void* slopes, void* y, int64_t N, int64_t C, int64_t S, int shared, void* stream);
+int pz_prelu_bwd_data(const void* dy, const void* slopes, const void* x, void* dx, int64_t N, int64_t C, int64_t S, int shared, void* stream);
+/* dslopes[c] (or dslopes[0]) = sum dy * x * (x <= 0); deterministic block reduction */
+int pz_prelu_bwd_params(const void* x, const void* dy, void* dslopes, int64_t N, int64_t C, int64_t S, int shared, void* stream);
+/* reflection padding of `planes` H x W maps (1-d: H = 1) by (up, bottom, left, right); float32 / float16 -- Cuda/Kernels/Pad.py:155-229.
+ * The backward pass gathers (no atomics) and overwrites dx */
+int pz_reflectpad_fwd(int dtype, const void* x, void* y, int64_t planes, int H, int W, int up, int bp, int lp, int rp, void* stream);
+int pz_reflectpad_bwd(int dtype, const void* dy, void* dx, int64_t planes, int H, int W, int up, int bp, int lp, int rp, void* stream);
+/* embedding lookup out[i] = W[idx[i]] (index -1: zero row) and the vocabulary update W[idx[i]] += scale * grad[i] --
+ * Cuda/Kernels/Embedder.py:56-87 */
+int pz_embed_fwd(int dtype, const void* idx, const void* W, void* out, int64_t size, int64_t emb, void* stream);
+int pz_embed_bwd(int dtype, const void* idx, const void* grad, void* W, float scale, int64_t size, int64_t emb, void* stream);
+/* up-sampling of `planes` D x H x W float32 volumes (2-d: D = 1) by integer factors -- Cuda/Kernels/Upsample.py:313-454.
+ * linear: r* = (in - 1) / (out - 1) as float32; the backward pass accumulates into a zeroed dx */
+int pz_upsample_nearest_fwd(const void* x, void* y, int64_t planes, int D, int H, int W, int ds, int hs, int ws, void* stream);
+int pz_upsample_nearest_bwd(const void* dy, void* dx, int64_t planes, int D, int H, int W, int ds, int hs, int ws, void* stream);
+int pz_upsample_linear_fwd(const void* x, void* y, int64_t planes, int D, int H, int W, int oD, int oH, int oW, float rd, float rh, float rw,
+						   int three_d, void* stream);
+int pz_upsample_linear_bwd(const void* dy, void* dx, int64_t planes, int D, int H, int W, int oD, int oH, int oW, float rd, float rh, float rw,
+						   int three_d, void* stream);
+/* mapLRN with a means tensor = divisive normalisation over `planes` H x W maps (cudnnDivisiveNormalization, CuDnnNorm.c:329-510;
+ * the LCN module): y = x * (K + alpha/n^2 * sum_win (x_j - m_i)^2)^-beta; the backward pass returns dx and dmeans and needs
+ * planes*H*W floats of scratch */
+int pz_divnorm_fwd(int dtype, const void* x, const void* means, void* y, int64_t planes, int64_t H, int64_t W, int n, float alpha, float beta, float K,
+				   void* stream);
+int pz_divnorm_bwd(int dtype, const void* x, const void* means, const void* grad, void* dx, void* dmeans, void* tmp, int64_t planes, int64_t H,
+				   int64_t W, int n, float alpha, float beta, float K, void* stream);
 /* diagnosis: the 32 per-role phase clock sums of the tcgen05 engine since the last call (only in builds with -DPZ_TIMELINE,
  * PZ_ERR_UNSUPPORTED otherwise); no reference counterpart */
 int pz_debug_timeline(unsigned long long* out);

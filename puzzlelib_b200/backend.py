@@ -430,14 +430,34 @@ class DnnContext:
 		return self._lrnBackward(0, data, grad, N, alpha, beta, K, out, allocator)
 
 	def mapLRN(self, data, means=None, N=5, alpha=1e-4, beta=0.75, K=2.0, out=None, allocator=None):
-		if means is not None:
-			raise NotImplementedError("mapLRN with a means tensor")
-		return self._lrn(1, data, N, alpha, beta, K, out, allocator)
+		"""reference: CuDnn_Context_pyMapLRN, CuDnnNorm.c:329-420 -- within-map LRN; with `means` the divisive normalisation the
+		LCN module uses (Modules/LCN.py:33-39)"""
+		if means is None:
+			return self._lrn(1, data, N, alpha, beta, K, out, allocator)
+		self._check4d(data, "data")
+		if means.shape != data.shape or means.dtype != data.dtype:
+			raise ValueError("invalid means gpuarray data layout")
+		out = GPUArray(data.shape, data.dtype, allocator=allocator) if out is None else _checkOut(out, data.shape, data.dtype)
+		check(lib.pz_divnorm_fwd(dtypeCode(data.dtype), data.ptr, means.ptr, out.ptr, data.shape[0] * data.shape[1], data.shape[2],
+								 data.shape[3], int(N), float(alpha), float(beta), float(K), None))
+		return out
 
-	def mapLRNBackward(self, data, grad, means=None, N=5, alpha=1e-4, beta=0.75, K=2.0, out=None, allocator=None):
-		if means is not None:
-			raise NotImplementedError("mapLRN with a means tensor")
-		return self._lrnBackward(1, data, grad, N, alpha, beta, K, out, allocator)
+	def mapLRNBackward(self, data, grad, means=None, N=5, alpha=1e-4, beta=0.75, K=2.0, dmeans=None, out=None, allocator=None):
+		"""reference: CuDnn_Context_pyMapLRNBackward, CuDnnNorm.c:456-527 -- returns the input gradient, or (input gradient, means
+		gradient) when a means tensor is given"""
+		if means is None:
+			return self._lrnBackward(1, data, grad, N, alpha, beta, K, out, allocator)
+		self._check4d(data, "data")
+		if grad.shape != data.shape or grad.dtype != data.dtype:
+			raise ValueError("invalid grad gpuarray data layout")
+		if means.shape != data.shape or means.dtype != data.dtype:
+			raise ValueError("invalid means gpuarray data layout")
+		out = GPUArray(data.shape, data.dtype, allocator=allocator) if out is None else _checkOut(out, data.shape, data.dtype)
+		dmeans = GPUArray(data.shape, data.dtype, allocator=allocator) if dmeans is None else _checkOut(dmeans, data.shape, data.dtype)
+		tmp = GPUArray(data.shape, _f32, allocator=allocator)
+		check(lib.pz_divnorm_bwd(dtypeCode(data.dtype), data.ptr, means.ptr, grad.ptr, out.ptr, dmeans.ptr, tmp.ptr,
+								 data.shape[0] * data.shape[1], data.shape[2], data.shape[3], int(N), float(alpha), float(beta), float(K), None))
+		return out, dmeans
 
 	# ------------------------------------------------------------------------------------------ batch norm
 	@staticmethod
@@ -761,6 +781,163 @@ class PoolModule:
 
 # ============================================================================================================ SharedArray
 # ============================================================================================================ costmod
+class PReluModule:
+	"""reference: Cuda/Kernels/PRelu.py:60-132 (float32 only; one slope per map, or one shared by all maps)"""
+	GPUArray = GPUArray
+
+	def __init__(self, backend):
+		self.backend = backend
+
+	@staticmethod
+	def _geometry(data, slopes, sharedMaps):
+		assert slopes.shape == (1, ) if sharedMaps else data.shape[1] == slopes.shape[0]
+		return data.shape[0], data.shape[1], prod(data.shape[2:])
+
+	def prelu(self, data, slopes, inplace=False, sharedMaps=False, allocator=None):
+		assert data.dtype == slopes.dtype and slopes.dtype == _f32
+		N, C, S = self._geometry(data, slopes, sharedMaps)
+		outdata = data if inplace else GPUArray(data.shape, _f32, allocator=allocator)
+		check(lib.pz_prelu_fwd(data.ptr, slopes.ptr, outdata.ptr, N, C, S, 1 if sharedMaps else 0, None))
+		return outdata
+
+	def preluBackwardData(self, grad, slopes, indata, sharedMaps=False, allocator=None):
+		assert grad.dtype == slopes.dtype and slopes.dtype == indata.dtype and indata.dtype == _f32
+		assert grad.shape == indata.shape
+		N, C, S = self._geometry(grad, slopes, sharedMaps)
+		ingrad = GPUArray(grad.shape, _f32, allocator=allocator)
+		check(lib.pz_prelu_bwd_data(grad.ptr, slopes.ptr, indata.ptr, ingrad.ptr, N, C, S, 1 if sharedMaps else 0, None))
+		return ingrad
+
+	def preluBackwardParams(self, indata, outgrad, sharedMaps=False, allocator=None):
+		assert indata.dtype == outgrad.dtype and outgrad.dtype == _f32
+		assert indata.shape == outgrad.shape
+		N, C, S = indata.shape[0], indata.shape[1], prod(indata.shape[2:])
+		slopegrad = GPUArray((1, ) if sharedMaps else (C, ), _f32, allocator=allocator)
+		check(lib.pz_prelu_bwd_params(indata.ptr, outgrad.ptr, slopegrad.ptr, N, C, S, 1 if sharedMaps else 0, None))
+		return slopegrad
+
+
+class PadModule:
+	"""reference: Cuda/Kernels/Pad.py:145-229 (reflection padding of 3-d / 4-d tensors, float32 / float16)"""
+	GPUArray = GPUArray
+
+	def __init__(self, backend):
+		self.backend = backend
+
+	@staticmethod
+	def _geometry(shape, pad, grad):
+		if len(shape) == 3:
+			lpad, rpad = pad
+			upad = bpad = 0
+			batchsize, maps, h, w = shape[0], shape[1], 1, shape[2]
+		elif len(shape) == 4:
+			upad, bpad, lpad, rpad = pad
+			batchsize, maps, h, w = shape
+		else:
+			raise NotImplementedError(len(shape))
+		if grad:
+			h, w = h - upad - bpad, w - lpad - rpad
+		else:
+			assert h >= max(upad, bpad) + 1 and w >= max(lpad, rpad) + 1
+		return batchsize, maps, h, w, upad, bpad, lpad, rpad
+
+	def reflectpad(self, data, pad, allocator=None):
+		batchsize, maps, h, w, upad, bpad, lpad, rpad = self._geometry(data.shape, pad, False)
+		outshape = (batchsize, maps, w + lpad + rpad) if data.ndim == 3 else (batchsize, maps, h + upad + bpad, w + lpad + rpad)
+		outdata = GPUArray(outshape, data.dtype, allocator=allocator)
+		check(lib.pz_reflectpad_fwd(dtypeCode(data.dtype), data.ptr, outdata.ptr, batchsize * maps, h, w, upad, bpad, lpad, rpad, None))
+		return outdata
+
+	def reflectpadBackward(self, grad, pad, allocator=None):
+		batchsize, maps, h, w, upad, bpad, lpad, rpad = self._geometry(grad.shape, pad, True)
+		inshape = (batchsize, maps, w) if grad.ndim == 3 else (batchsize, maps, h, w)
+		ingrad = GPUArray(inshape, grad.dtype, allocator=allocator)
+		check(lib.pz_reflectpad_bwd(dtypeCode(grad.dtype), grad.ptr, ingrad.ptr, batchsize * maps, h, w, upad, bpad, lpad, rpad, None))
+		return ingrad
+
+
+class EmbedModule:
+	"""reference: Cuda/Kernels/Embedder.py:45-87 (int32 word indices, -1 = padding; float32 / float16 vocabulary)"""
+	GPUArray = GPUArray
+
+	def __init__(self, backend):
+		self.backend = backend
+
+	def embed(self, data, W, allocator=None):
+		assert data.dtype == _i32 and (W.dtype == _f32 or W.dtype == np.float16)
+		batchsize, sentlen = data.shape
+		_, embsize = W.shape
+		outdata = GPUArray((batchsize, sentlen, embsize), W.dtype, allocator=allocator)
+		check(lib.pz_embed_fwd(dtypeCode(W.dtype), data.ptr, W.ptr, outdata.ptr, batchsize * sentlen, embsize, None))
+		return outdata
+
+	def embedBackwardParams(self, indata, grad, W, scale):
+		assert indata.shape == grad.shape[:2] and W.shape[1] == grad.shape[2]
+		assert indata.dtype == _i32 and grad.dtype == W.dtype
+		batchsize, sentlen = indata.shape
+		if driver.gradientWriteHook is not None:
+			driver.gradientWriteHook(W)
+		check(lib.pz_embed_bwd(dtypeCode(W.dtype), indata.ptr, grad.ptr, W.ptr, float(scale), batchsize * sentlen, W.shape[1], None))
+
+
+class UpsampleModule:
+	"""reference: Cuda/Kernels/Upsample.py:300-454 (float32; integer scale factors; "nearest" and align-corners "linear")"""
+	GPUArray = GPUArray
+
+	def __init__(self, backend):
+		self.backend = backend
+
+	@staticmethod
+	def _scale(scale, n):
+		return (scale, ) * n if isinstance(scale, int) else tuple(scale)
+
+	def _forward(self, data, dims, scales, mode, allocator):
+		batchsize, maps = data.shape[:2]
+		outdims = tuple(s * d for s, d in zip(scales, dims))
+		outdata = GPUArray((batchsize, maps) + outdims[3 - (data.ndim - 2):], data.dtype, allocator=allocator)
+		if mode == "nearest":
+			check(lib.pz_upsample_nearest_fwd(data.ptr, outdata.ptr, batchsize * maps, *dims, *scales, None))
+		elif mode == "linear":
+			ratios = [(i - 1) / (o - 1) if data.ndim == 5 or k > 0 else 0.0 for k, (i, o) in enumerate(zip(dims, outdims))]
+			check(lib.pz_upsample_linear_fwd(data.ptr, outdata.ptr, batchsize * maps, *dims, *outdims, *ratios, 1 if data.ndim == 5 else 0, None))
+		else:
+			raise NotImplementedError(mode)
+		return outdata
+
+	def _backward(self, grad, outdims, scales, mode, allocator):
+		batchsize, maps = grad.shape[:2]
+		dims = tuple(o // s for s, o in zip(scales, outdims))
+		inshape = (batchsize, maps) + dims[3 - (grad.ndim - 2):]
+		if mode == "nearest":
+			ingrad = GPUArray(inshape, grad.dtype, allocator=allocator)
+			check(lib.pz_upsample_nearest_bwd(grad.ptr, ingrad.ptr, batchsize * maps, *dims, *scales, None))
+		elif mode == "linear":
+			ingrad = GPUArray.zeros(inshape, grad.dtype, allocator=allocator)
+			ratios = [(i - 1) / (o - 1) if grad.ndim == 5 or k > 0 else 0.0 for k, (i, o) in enumerate(zip(dims, outdims))]
+			check(lib.pz_upsample_linear_bwd(grad.ptr, ingrad.ptr, batchsize * maps, *dims, *outdims, *ratios, 1 if grad.ndim == 5 else 0, None))
+		else:
+			raise NotImplementedError(mode)
+		return ingrad
+
+	def upsample2d(self, data, scale, mode="nearest", allocator=None):
+		assert data.dtype == _f32
+		hscale, wscale = self._scale(scale, 2)
+		return self._forward(data, (1, ) + tuple(data.shape[2:]), (1, hscale, wscale), mode, allocator)
+
+	def upsample2dBackward(self, grad, scale, mode="nearest", allocator=None):
+		assert grad.dtype == _f32
+		hscale, wscale = self._scale(scale, 2)
+		return self._backward(grad, (1, ) + tuple(grad.shape[2:]), (1, hscale, wscale), mode, allocator)
+
+	def upsample3d(self, data, scale, mode="nearest", allocator=None):
+		assert data.dtype == _f32
+		return self._forward(data, tuple(data.shape[2:]), self._scale(scale, 3), mode, allocator)
+
+	def upsample3dBackward(self, grad, scale, mode="nearest", allocator=None):
+		assert grad.dtype == _f32
+		return self._backward(grad, tuple(grad.shape[2:]), self._scale(scale, 3), mode, allocator)
+
+
 class CostModule:
 	"""reference: Cuda/Kernels/Costs.py:160-247 (the cross-entropy entry and the accuracy reduction of the training closure)"""
 	GPUArray = GPUArray
@@ -1149,7 +1326,7 @@ class B200Backend:
 		uni = 0
 		bi = 1
 
-	notImplemented = ("ctcmod", "embedmod", "padmod", "prelumod", "upsamplemod", "memmod")
+	notImplemented = ("ctcmod", "memmod")
 
 	def __init__(self, deviceIdx, initmode=0, logger=None):
 		self.deviceIdx = deviceIdx
@@ -1177,6 +1354,7 @@ class B200Backend:
 		self.initmode = 0
 		self.blas, self.dnn = None, None
 		self.matmod, self.poolmod, self.costmod = None, None, None
+		self.prelumod, self.padmod, self.embedmod, self.upsamplemod = None, None, None, None
 
 		# attributes the reference's Backend/Kernels/*.py bind at import time (Cuda/GPUBackend.py:74-131) that sit outside the
 		# hot path and are not implemented: binding works, use raises NotImplementedError
@@ -1191,6 +1369,7 @@ class B200Backend:
 			self.blas, self.dnn = BlasContext(self), DnnContext(self)
 		if initmode >= 2 and self.matmod is None:
 			self.matmod, self.poolmod, self.costmod = MatModule(self), PoolModule(self), CostModule(self)
+			self.prelumod, self.padmod, self.embedmod, self.upsamplemod = PReluModule(self), PadModule(self), EmbedModule(self), UpsampleModule(self)
 		self.initmode = max(self.initmode, initmode)
 
 	# ---- kernel factories (reference attribute names: Cuda/GPUBackend.py:85-131)

@@ -1,0 +1,520 @@
+// pz_shape.cu -- the kernel modules of the reference backend object that sit next to the hot path: PReLU, reflection padding,
+// embedding lookup, nearest / linear up-sampling (reference: Cuda/Kernels/PRelu.py, Pad.py, Embedder.py, Upsample.py -- NVRTC
+// kernels with one thread per element there).  All bandwidth-bound; grid-stride kernels sized from the SM count, plane-major
+// indexing so that the per-element work is a handful of integer instructions, gather-form (atomic-free, deterministic) backward
+// passes wherever the inverse map is closed-form.
+#include "pz_common.h"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+inline unsigned grid_for(int64_t work)
+{
+	const int64_t blocks = pz_cdiv(work, kThreads), cap = (int64_t)pz_num_sms() * 8;
+	return (unsigned)(blocks < 1 ? 1 : (blocks < cap ? blocks : cap));
+}
+
+template <typename T> __device__ __forceinline__ float ldf(const T* p) { return (float)*p; }
+template <> __device__ __forceinline__ float ldf<__half>(const __half* p) { return __half2float(*p); }
+template <typename T> __device__ __forceinline__ void stf(T* p, float v) { *p = (T)v; }
+template <> __device__ __forceinline__ void stf<__half>(__half* p, float v) { *p = __float2half_rn(v); }
+
+// ------------------------------------------------------------------------------------------ PReLU (fp32, PRelu.py:12-57)
+// slope index of element i of an [N][C][S] tensor: channel (i / S) % C, or 0 when one slope is shared by all maps
+__global__ void __launch_bounds__(kThreads) prelu_fwd_kernel(const float* __restrict__ x, const float* __restrict__ slopes, float* __restrict__ y,
+															  int64_t total, int64_t S, int C, int shared)
+{
+	for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += (int64_t)gridDim.x * kThreads) {
+		const int c = shared ? 0 : (int)((i / S) % C);
+		const float v = x[i];
+		y[i] = v * (v > 0.0f ? 1.0f : __ldg(slopes + c));
+	}
+}
+
+__global__ void __launch_bounds__(kThreads) prelu_bwd_data_kernel(const float* __restrict__ dy, const float* __restrict__ slopes,
+																   const float* __restrict__ x, float* __restrict__ dx, int64_t total, int64_t S,
+																   int C, int shared)
+{
+	for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += (int64_t)gridDim.x * kThreads) {
+		const int c = shared ? 0 : (int)((i / S) % C);
+		const float v = x[i];
+		dx[i] = dy[i] * ((v > 0.0f ? 1.0f : 0.0f) + (v <= 0.0f ? 1.0f : 0.0f) * __ldg(slopes + c));
+	}
+}
+
+// dslope[c] = sum over images and positions of dy * x * (x <= 0): one block per channel (all channels for a shared slope), fixed
+// summation tree -- deterministic, unlike an atomic reduction
+__global__ void __launch_bounds__(kThreads) prelu_bwd_params_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ ds,
+																	 int64_t N, int C, int64_t S, int shared)
+{
+	__shared__ float red[kThreads / 32];
+	const int c = blockIdx.x;
+	const int64_t per_image = shared ? (int64_t)C * S : S, count = N * per_image;
+	float acc = 0.0f;
+	for (int64_t j = threadIdx.x; j < count; j += kThreads) {
+		const int64_t n = j / per_image, r = j - n * per_image;
+		const int64_t idx = n * C * S + (shared ? r : (int64_t)c * S + r);
+		const float v = x[idx];
+		acc += dy[idx] * v * (v <= 0.0f ? 1.0f : 0.0f);
+	}
+	for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+	if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		float total = 0.0f;
+		for (int w = 0; w < kThreads / 32; w++) total += red[w];
+		ds[c] = total;
+	}
+}
+
+// ------------------------------------------------------------------------------------------ reflection padding (Pad.py:33-142)
+// numpy "reflect": out[i] = in[mirror(i - pad)] with the edge sample not repeated.  1-d tensors are planes of height 1.
+__device__ __forceinline__ int mirror(int i, int n)
+{
+	if (i < 0) i = -i;
+	if (i >= n) i = 2 * (n - 1) - i;
+	return i;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) reflectpad_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t planes, int H, int W, int up,
+																   int lp, int oH, int oW)
+{
+	const int64_t osize = (int64_t)oH * oW, total = planes * osize;
+	for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += (int64_t)gridDim.x * kThreads) {
+		const int64_t p = i / osize;
+		const int r = (int)(i - p * osize), oy = r / oW, ox = r - oy * oW;
+		y[i] = x[p * H * W + (int64_t)mirror(oy - up, H) * W + mirror(ox - lp, W)];
+	}
+}
+
+// gather form of the adjoint: input position j receives its own output sample plus the mirrored ones -- the left mirror when
+// 1 <= j <= lpad, the right one when n-1-rpad <= j <= n-2 (the reference scatters with atomicAdd, Pad.py:77-139)
+__device__ __forceinline__ int mirror_sources(int j, int n, int before, int after, int (&src)[3])
+{
+	int k = 0;
+	src[k++] = j + before;
+	if (j >= 1 && j <= before) src[k++] = before - j;
+	if (j <= n - 2 && j >= n - 1 - after) src[k++] = before + 2 * (n - 1) - j;
+	return k;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) reflectpad_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, int64_t planes, int H, int W, int up,
+																   int bp, int lp, int rp, int oH, int oW)
+{
+	const int64_t isize = (int64_t)H * W, total = planes * isize;
+	for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += (int64_t)gridDim.x * kThreads) {
+		const int64_t p = i / isize;
+		const int r = (int)(i - p * isize), iy = r / W, ix = r - iy * W;
+		int ys[3], xs[3];
+		const int ny = mirror_sources(iy, H, up, bp, ys), nx = mirror_sources(ix, W, lp, rp, xs);
+		const T* g = dy + p * (int64_t)oH * oW;
+		float acc = 0.0f;
+		for (int a = 0; a < ny; a++)
+			for (int b = 0; b < nx; b++) acc += ldf(g + (int64_t)ys[a] * oW + xs[b]);
+		stf(dx + i, acc);
+	}
+}
+
+// ------------------------------------------------------------------------------------------ embedding lookup (Embedder.py:11-42)
+// index -1 = padding: the output row is zero (the reference zero-fills first and skips the row), no gradient
+template <typename T>
+__global__ void __launch_bounds__(kThreads) embed_fwd_kernel(const int* __restrict__ idx, const T* __restrict__ W, T* __restrict__ out, int64_t size,
+															  int64_t emb)
+{
+	const int64_t total = size * emb;
+	for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += (int64_t)gridDim.x * kThreads) {
+		const int64_t row = i / emb, col = i - row * emb;
+		const int word = __ldg(idx + row);
+		out[i] = word == -1 ? (T)0.0f : W[(int64_t)word * emb + col];
+	}
+}
+
+__device__ __forceinline__ void atomic_add(float* p, float v) { atomicAdd(p, v); }
+__device__ __forceinline__ void atomic_add(__half* p, float v) { atomicAdd(p, __float2half_rn(v)); }
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) embed_bwd_kernel(const int* __restrict__ idx, const T* __restrict__ grad, T* W, float scale, int64_t size,
+															  int64_t emb)
+{
+	const int64_t total = size * emb;
+	for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += (int64_t)gridDim.x * kThreads) {
+		const int64_t row = i / emb, col = i - row * emb;
+		const int word = __ldg(idx + row);
+		if (word == -1) continue;
+		// the vocabulary update W[word] += scale * grad: rows of repeated words collide, hence atomics (as the reference)
+		atomic_add(W + (int64_t)word * emb + col, scale * ldf(grad + i));
+	}
+}
+
+// ------------------------------------------------------------------------------------------ up-sampling (Upsample.py:9-297), fp32
+// nearest: out[z][d*ds+i][y*hs+j][x*ws+k] = in[z][d][y][x]; one thread per OUTPUT element (coalesced stores, the input read hits L1)
+__global__ void __launch_bounds__(kThreads) upsample_nearest_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t planes, int D, int H,
+																		 int W, int ds, int hs, int ws)
+{
+	const int oD = D * ds, oH = H * hs, oW = W * ws;
+	const int64_t osize = (int64_t)oD * oH * oW, total = planes * osize;
+	for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += (int64_t)gridDim.x * kThreads) {
+		const int64_t p = i / osize;
+		int64_t r = i - p * osize;
+		const int od = (int)(r / ((int64_t)oH * oW));
+		r -= (int64_t)od * oH * oW;
+		const int oy = (int)(r / oW), ox = (int)(r - (int64_t)oy * oW);
+		y[i] = x[((p * D + od / ds) * H + oy / hs) * W + ox / ws];
+	}
+}
+
+// the adjoint: every input element sums its ds x hs x ws block of output gradients
+__global__ void __launch_bounds__(kThreads) upsample_nearest_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int64_t planes, int D, int H,
+																		 int W, int ds, int hs, int ws)
+{
+	const int oH = H * hs, oW = W * ws;
+	const int64_t isize = (int64_t)D * H * W, total = planes * isize;
+	for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += (int64_t)gridDim.x * kThreads) {
+		const int64_t p = i / isize;
+		int64_t r = i - p * isize;
+		const int d = (int)(r / ((int64_t)H * W));
+		r -= (int64_t)d * H * W;
+		const int yy = (int)(r / W), xx = (int)(r - (int64_t)yy * W);
+		const float* g = dy + ((p * D * ds + (int64_t)d * ds) * oH + (int64_t)yy * hs) * oW + (int64_t)xx * ws;
+		float acc = 0.0f;
+		for (int a = 0; a < ds; a++)
+			for (int b = 0; b < hs; b++)
+				for (int c = 0; c < ws; c++) acc += g[((int64_t)a * oH + b) * oW + c];
+		dx[i] = acc;
+	}
+}
+
+// linear ("align corners": source coordinate = r * output coordinate, r = (in - 1) / (out - 1) as float32).  The interpolation
+// expressions keep the reference's evaluation order.  Quirk kept on purpose: one of the eight taps of the reference's 3-d FORWARD
+// kernel is addressed with d1 * inw * inw instead of d1 * inh * inw (Upsample.py:241) -- identical whenever inh == inw.
+struct Lerp {
+	int i0, step;
+	float w0, w1;
+};
+__device__ __forceinline__ Lerp lerp_of(float ratio, int o, int n)
+{
+	Lerp l;
+	const float src = ratio * (float)o;
+	l.i0 = (int)src;
+	l.step = l.i0 < n - 1 ? 1 : 0;
+	l.w1 = src - (float)l.i0;
+	l.w0 = 1.0f - l.w1;
+	return l;
+}
+
+__global__ void __launch_bounds__(kThreads) upsample_linear_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t planes, int D, int H,
+																		int W, int oD, int oH, int oW, float rd, float rh, float rw, int three_d)
+{
+	const int64_t osize = (int64_t)oD * oH * oW, total = planes * osize;
+	for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += (int64_t)gridDim.x * kThreads) {
+		const int64_t p = i / osize;
+		int64_t r = i - p * osize;
+		const int od = (int)(r / ((int64_t)oH * oW));
+		r -= (int64_t)od * oH * oW;
+		const int oy = (int)(r / oW), ox = (int)(r - (int64_t)oy * oW);
+		const Lerp lh = lerp_of(rh, oy, H), lw = lerp_of(rw, ox, W);
+		const float* src = x + p * (int64_t)D * H * W;
+		if (!three_d) {
+			const float* a = src + (int64_t)lh.i0 * W + lw.i0;
+			const float* b = src + (int64_t)(lh.i0 + lh.step) * W + lw.i0;
+			y[i] = lh.w0 * (lw.w0 * a[0] + lw.w1 * a[lw.step]) + lh.w1 * (lw.w0 * b[0] + lw.w1 * b[lw.step]);
+		} else {
+			const Lerp ld = lerp_of(rd, od, D);
+			const int64_t hw = (int64_t)H * W, d0 = (int64_t)ld.i0 * hw, d1 = (int64_t)(ld.i0 + ld.step) * hw;
+			const int64_t h0 = (int64_t)lh.i0 * W, h1 = (int64_t)(lh.i0 + lh.step) * W;
+			int64_t quirk = (int64_t)ld.i0 * W * W + h0 + lw.i0 + lw.step;      // Upsample.py:241
+			if (quirk >= (int64_t)D * hw) quirk = d0 + h0 + lw.i0 + lw.step;       // (the reference would read past the volume there)
+			const float near =
+				lh.w0 * (lw.w0 * src[d0 + h0 + lw.i0] + lw.w1 * src[quirk]) +
+				lh.w1 * (lw.w0 * src[d0 + h1 + lw.i0] + lw.w1 * src[d0 + h1 + lw.i0 + lw.step]);
+			const float far =
+				lh.w0 * (lw.w0 * src[d1 + h0 + lw.i0] + lw.w1 * src[d1 + h0 + lw.i0 + lw.step]) +
+				lh.w1 * (lw.w0 * src[d1 + h1 + lw.i0] + lw.w1 * src[d1 + h1 + lw.i0 + lw.step]);
+			y[i] = ld.w0 * near + ld.w1 * far;
+		}
+	}
+}
+
+// the adjoint scatters each output gradient to its 4 / 8 taps (red.add: the taps of neighbouring outputs collide, as in the
+// reference, Upsample.py:141-184, 254-296); dx is zeroed by the caller
+__global__ void __launch_bounds__(kThreads) upsample_linear_bwd_kernel(const float* __restrict__ dy, float* dx, int64_t planes, int D, int H, int W,
+																		int oD, int oH, int oW, float rd, float rh, float rw, int three_d)
+{
+	const int64_t osize = (int64_t)oD * oH * oW, total = planes * osize;
+	for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += (int64_t)gridDim.x * kThreads) {
+		const int64_t p = i / osize;
+		int64_t r = i - p * osize;
+		const int od = (int)(r / ((int64_t)oH * oW));
+		r -= (int64_t)od * oH * oW;
+		const int oy = (int)(r / oW), ox = (int)(r - (int64_t)oy * oW);
+		const Lerp lh = lerp_of(rh, oy, H), lw = lerp_of(rw, ox, W);
+		float* dst = dx + p * (int64_t)D * H * W;
+		const float v = dy[i];
+		const int64_t h0 = (int64_t)lh.i0 * W, h1 = (int64_t)(lh.i0 + lh.step) * W;
+		if (!three_d) {
+			atomicAdd(dst + h0 + lw.i0, lh.w0 * lw.w0 * v);
+			atomicAdd(dst + h0 + lw.i0 + lw.step, lh.w0 * lw.w1 * v);
+			atomicAdd(dst + h1 + lw.i0, lh.w1 * lw.w0 * v);
+			atomicAdd(dst + h1 + lw.i0 + lw.step, lh.w1 * lw.w1 * v);
+		} else {
+			const Lerp ld = lerp_of(rd, od, D);
+			const int64_t hw = (int64_t)H * W, d0 = (int64_t)ld.i0 * hw, d1 = (int64_t)(ld.i0 + ld.step) * hw;
+			atomicAdd(dst + d0 + h0 + lw.i0, ld.w0 * lh.w0 * lw.w0 * v);
+			atomicAdd(dst + d0 + h0 + lw.i0 + lw.step, ld.w0 * lh.w0 * lw.w1 * v);
+			atomicAdd(dst + d0 + h1 + lw.i0, ld.w0 * lh.w1 * lw.w0 * v);
+			atomicAdd(dst + d0 + h1 + lw.i0 + lw.step, ld.w0 * lh.w1 * lw.w1 * v);
+			atomicAdd(dst + d1 + h0 + lw.i0, ld.w1 * lh.w0 * lw.w0 * v);
+			atomicAdd(dst + d1 + h0 + lw.i0 + lw.step, ld.w1 * lh.w0 * lw.w1 * v);
+			atomicAdd(dst + d1 + h1 + lw.i0, ld.w1 * lh.w1 * lw.w0 * v);
+			atomicAdd(dst + d1 + h1 + lw.i0 + lw.step, ld.w1 * lh.w1 * lw.w1 * v);
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------ divisive normalisation (LCN)
+// mapLRN with a means tensor = cudnnDivisiveNormalization (CuDnnNorm.c:329-510; host formulas of Modules/LCN.py:62-143):
+//   norm_i = K + alpha / N^2 * sum_{j in win(i)} (x_j - m_i)^2,   y_i = x_i * norm_i^-beta,   win(i) = [i - lb, i + la) clipped
+//   t_j    = g_j * x_j * norm_j^-(beta + 1)
+//   dx_i   = g_i * norm_i^-beta - (2 alpha beta / N^2) * (x_i * sum_{j in win(i)} t_j - sum_{j in win(i)} t_j * m_j)
+//   dm_i   = (2 alpha beta / N^2) * t_i * sum_{j in win(i)} (x_j - m_i)
+struct DivGeo {
+	int H, W, lb, la;
+	float scale, beta, K;          // scale = alpha / N^2
+};
+
+template <typename T>
+__device__ __forceinline__ float div_norm(const T* __restrict__ xp, float m, const DivGeo& g, int h, int w, float& sumdiff)
+{
+	float s = 0.0f, d = 0.0f;
+	for (int yy = max(0, h - g.lb); yy < min(g.H, h + g.la); yy++)
+		for (int xx = max(0, w - g.lb); xx < min(g.W, w + g.la); xx++) {
+			const float v = ldf(xp + (int64_t)yy * g.W + xx) - m;
+			s = fmaf(v, v, s);
+			d += v;
+		}
+	sumdiff = d;
+	return g.K + g.scale * s;
+}
+
+// PASS 0: y.  PASS 1: t (fp32 scratch) and dm.  PASS 2: dx from g, x, m, t.
+template <typename T, int PASS>
+__global__ void __launch_bounds__(kThreads) divnorm_kernel(const T* __restrict__ x, const T* __restrict__ means, const T* __restrict__ grad,
+															T* __restrict__ out, T* __restrict__ dmeans, float* __restrict__ tmp, DivGeo g, int64_t total)
+{
+	const int64_t plane = (int64_t)g.H * g.W;
+	for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += (int64_t)gridDim.x * kThreads) {
+		const int64_t p = i / plane;
+		const int r = (int)(i - p * plane), h = r / g.W, w = r - h * g.W;
+		const T* xp = x + p * plane;
+		float sumdiff;
+		const float xv = ldf(x + i), norm = div_norm(xp, ldf(means + i), g, h, w, sumdiff);
+		if (PASS == 0) {
+			stf(out + i, xv * powf(norm, -g.beta));
+		} else if (PASS == 1) {
+			const float t = ldf(grad + i) * xv * powf(norm, -(g.beta + 1.0f));
+			tmp[i] = t;
+			stf(dmeans + i, 2.0f * g.beta * g.scale * t * sumdiff);
+		} else {
+			const float* tp = tmp + p * plane;
+			const T* mp = means + p * plane;
+			float s1 = 0.0f, s2 = 0.0f;
+			for (int yy = max(0, h - g.lb); yy < min(g.H, h + g.la); yy++)
+				for (int xx = max(0, w - g.lb); xx < min(g.W, w + g.la); xx++) {
+					const float t = tp[(int64_t)yy * g.W + xx];
+					s1 += t;
+					s2 = fmaf(t, ldf(mp + (int64_t)yy * g.W + xx), s2);
+				}
+			stf(out + i, ldf(grad + i) * powf(norm, -g.beta) - 2.0f * g.beta * g.scale * (xv * s1 - s2));
+		}
+	}
+}
+
+template <typename T>
+int divnorm_launch(int pass, const void* x, const void* means, const void* grad, void* out, void* dmeans, float* tmp, const DivGeo& g, int64_t total,
+				   cudaStream_t s)
+{
+	const unsigned grid = grid_for(total);
+	if (pass == 0) divnorm_kernel<T, 0><<<grid, kThreads, 0, s>>>((const T*)x, (const T*)means, nullptr, (T*)out, nullptr, nullptr, g, total);
+	else {
+		divnorm_kernel<T, 1><<<grid, kThreads, 0, s>>>((const T*)x, (const T*)means, (const T*)grad, nullptr, (T*)dmeans, tmp, g, total);
+		divnorm_kernel<T, 2><<<grid, kThreads, 0, s>>>((const T*)x, (const T*)means, (const T*)grad, (T*)out, nullptr, tmp, g, total);
+		pz_count_launch(1);
+	}
+	pz_count_launch(1);
+	PZ_LAUNCH_CHECK();
+	return PZ_OK;
+}
+
+int div_geo(DivGeo& g, int dtype, int64_t planes, int64_t H, int64_t W, int n, float alpha, float beta, float K)
+{
+	PZ_REQUIRE(dtype == PZ_F32 || dtype == PZ_F16, "divisive normalisation: unsupported dtype %d", dtype);
+	PZ_REQUIRE(planes >= 0 && n >= 1 && H > 0 && W > 0 && H < (1ll << 31) && W < (1ll << 31), "divisive normalisation: bad geometry");
+	g.H = (int)H; g.W = (int)W;
+	g.lb = (n - 1) / 2; g.la = n - g.lb;
+	g.scale = alpha / ((float)n * (float)n);
+	g.beta = beta; g.K = K;
+	return PZ_OK;
+}
+
+}  // namespace
+
+#define PZ_SHAPE_LAUNCH(KERNEL, WORK, ...)                                                   \
+	do {                                                                                     \
+		KERNEL<<<grid_for(WORK), kThreads, 0, pz_stream(stream)>>>(__VA_ARGS__);             \
+		pz_count_launch(1);                                                                  \
+		PZ_LAUNCH_CHECK();                                                                   \
+	} while (0)
+
+extern "C" {
+
+int pz_prelu_fwd(const void* x, const void* slopes, void* y, int64_t N, int64_t C, int64_t S, int shared, void* stream)
+{
+	PZ_REQUIRE(N >= 0 && C > 0 && S > 0 && C < (1ll << 31), "prelu: invalid shape");
+	const int64_t total = N * C * S;
+	if (total == 0) return PZ_OK;
+	PzProfScope prof(PZ_PROF_ELTWISE, pz_stream(stream), 0.0, 8.0 * (double)total);
+	PZ_SHAPE_LAUNCH(prelu_fwd_kernel, total, (const float*)x, (const float*)slopes, (float*)y, total, S, (int)C, shared);
+	return PZ_OK;
+}
+
+int pz_prelu_bwd_data(const void* dy, const void* slopes, const void* x, void* dx, int64_t N, int64_t C, int64_t S, int shared, void* stream)
+{
+	PZ_REQUIRE(N >= 0 && C > 0 && S > 0 && C < (1ll << 31), "prelu: invalid shape");
+	const int64_t total = N * C * S;
+	if (total == 0) return PZ_OK;
+	PzProfScope prof(PZ_PROF_ELTWISE, pz_stream(stream), 0.0, 12.0 * (double)total);
+	PZ_SHAPE_LAUNCH(prelu_bwd_data_kernel, total, (const float*)dy, (const float*)slopes, (const float*)x, (float*)dx, total, S, (int)C, shared);
+	return PZ_OK;
+}
+
+int pz_prelu_bwd_params(const void* x, const void* dy, void* dslopes, int64_t N, int64_t C, int64_t S, int shared, void* stream)
+{
+	PZ_REQUIRE(N >= 0 && C > 0 && S > 0 && C < (1ll << 31), "prelu: invalid shape");
+	PzProfScope prof(PZ_PROF_ELTWISE, pz_stream(stream), 0.0, 8.0 * (double)(N * C * S));
+	prelu_bwd_params_kernel<<<(unsigned)(shared ? 1 : C), kThreads, 0, pz_stream(stream)>>>((const float*)x, (const float*)dy, (float*)dslopes, N, (int)C,
+																						  S, shared);
+	pz_count_launch(1);
+	PZ_LAUNCH_CHECK();
+	return PZ_OK;
+}
+
+static int check_pad(int dtype, int64_t planes, int H, int W, int up, int bp, int lp, int rp)
+{
+	PZ_REQUIRE(dtype == PZ_F32 || dtype == PZ_F16, "reflectpad: unsupported dtype %d", dtype);
+	PZ_REQUIRE(planes >= 0 && H > 0 && W > 0, "reflectpad: invalid shape");
+	PZ_REQUIRE(up >= 0 && bp >= 0 && lp >= 0 && rp >= 0, "reflectpad: negative padding is not supported");
+	PZ_REQUIRE(H >= (up > bp ? up : bp) + 1 || (up == 0 && bp == 0), "reflectpad: padding exceeds the map height");
+	PZ_REQUIRE(W >= (lp > rp ? lp : rp) + 1, "reflectpad: padding exceeds the map width");
+	return PZ_OK;
+}
+
+int pz_reflectpad_fwd(int dtype, const void* x, void* y, int64_t planes, int H, int W, int up, int bp, int lp, int rp, void* stream)
+{
+	int st = check_pad(dtype, planes, H, W, up, bp, lp, rp);
+	if (st != PZ_OK) return st;
+	const int oH = H + up + bp, oW = W + lp + rp;
+	const int64_t total = planes * oH * oW;
+	if (total == 0) return PZ_OK;
+	if (dtype == PZ_F32) PZ_SHAPE_LAUNCH(reflectpad_fwd_kernel<float>, total, (const float*)x, (float*)y, planes, H, W, up, lp, oH, oW);
+	else PZ_SHAPE_LAUNCH(reflectpad_fwd_kernel<__half>, total, (const __half*)x, (__half*)y, planes, H, W, up, lp, oH, oW);
+	return PZ_OK;
+}
+
+int pz_reflectpad_bwd(int dtype, const void* dy, void* dx, int64_t planes, int H, int W, int up, int bp, int lp, int rp, void* stream)
+{
+	int st = check_pad(dtype, planes, H, W, up, bp, lp, rp);
+	if (st != PZ_OK) return st;
+	const int oH = H + up + bp, oW = W + lp + rp;
+	const int64_t total = planes * H * W;
+	if (total == 0) return PZ_OK;
+	if (dtype == PZ_F32) PZ_SHAPE_LAUNCH(reflectpad_bwd_kernel<float>, total, (const float*)dy, (float*)dx, planes, H, W, up, bp, lp, rp, oH, oW);
+	else PZ_SHAPE_LAUNCH(reflectpad_bwd_kernel<__half>, total, (const __half*)dy, (__half*)dx, planes, H, W, up, bp, lp, rp, oH, oW);
+	return PZ_OK;
+}
+
+int pz_embed_fwd(int dtype, const void* idx, const void* W, void* out, int64_t size, int64_t emb, void* stream)
+{
+	PZ_REQUIRE(dtype == PZ_F32 || dtype == PZ_F16, "embed: unsupported dtype %d", dtype);
+	PZ_REQUIRE(size >= 0 && emb > 0, "embed: invalid shape");
+	if (size == 0) return PZ_OK;
+	if (dtype == PZ_F32) PZ_SHAPE_LAUNCH(embed_fwd_kernel<float>, size * emb, (const int*)idx, (const float*)W, (float*)out, size, emb);
+	else PZ_SHAPE_LAUNCH(embed_fwd_kernel<__half>, size * emb, (const int*)idx, (const __half*)W, (__half*)out, size, emb);
+	return PZ_OK;
+}
+
+int pz_embed_bwd(int dtype, const void* idx, const void* grad, void* W, float scale, int64_t size, int64_t emb, void* stream)
+{
+	PZ_REQUIRE(dtype == PZ_F32 || dtype == PZ_F16, "embed: unsupported dtype %d", dtype);
+	PZ_REQUIRE(size >= 0 && emb > 0, "embed: invalid shape");
+	if (size == 0) return PZ_OK;
+	if (dtype == PZ_F32) PZ_SHAPE_LAUNCH(embed_bwd_kernel<float>, size * emb, (const int*)idx, (const float*)grad, (float*)W, scale, size, emb);
+	else PZ_SHAPE_LAUNCH(embed_bwd_kernel<__half>, size * emb, (const int*)idx, (const __half*)grad, (__half*)W, scale, size, emb);
+	return PZ_OK;
+}
+
+int pz_upsample_nearest_fwd(const void* x, void* y, int64_t planes, int D, int H, int W, int ds, int hs, int ws, void* stream)
+{
+	PZ_REQUIRE(planes >= 0 && D > 0 && H > 0 && W > 0 && ds > 0 && hs > 0 && ws > 0, "upsample: invalid shape");
+	const int64_t total = planes * D * ds * H * hs * W * ws;
+	if (total == 0) return PZ_OK;
+	PZ_SHAPE_LAUNCH(upsample_nearest_fwd_kernel, total, (const float*)x, (float*)y, planes, D, H, W, ds, hs, ws);
+	return PZ_OK;
+}
+
+int pz_upsample_nearest_bwd(const void* dy, void* dx, int64_t planes, int D, int H, int W, int ds, int hs, int ws, void* stream)
+{
+	PZ_REQUIRE(planes >= 0 && D > 0 && H > 0 && W > 0 && ds > 0 && hs > 0 && ws > 0, "upsample: invalid shape");
+	const int64_t total = planes * D * H * W;
+	if (total == 0) return PZ_OK;
+	PZ_SHAPE_LAUNCH(upsample_nearest_bwd_kernel, total, (const float*)dy, (float*)dx, planes, D, H, W, ds, hs, ws);
+	return PZ_OK;
+}
+
+int pz_upsample_linear_fwd(const void* x, void* y, int64_t planes, int D, int H, int W, int oD, int oH, int oW, float rd, float rh, float rw,
+						   int three_d, void* stream)
+{
+	PZ_REQUIRE(planes >= 0 && D > 0 && H > 0 && W > 0 && oD > 0 && oH > 0 && oW > 0, "upsample: invalid shape");
+	const int64_t total = planes * oD * oH * oW;
+	if (total == 0) return PZ_OK;
+	PZ_SHAPE_LAUNCH(upsample_linear_fwd_kernel, total, (const float*)x, (float*)y, planes, D, H, W, oD, oH, oW, rd, rh, rw, three_d);
+	return PZ_OK;
+}
+
+int pz_upsample_linear_bwd(const void* dy, void* dx, int64_t planes, int D, int H, int W, int oD, int oH, int oW, float rd, float rh, float rw,
+						   int three_d, void* stream)
+{
+	PZ_REQUIRE(planes >= 0 && D > 0 && H > 0 && W > 0 && oD > 0 && oH > 0 && oW > 0, "upsample: invalid shape");
+	const int64_t total = planes * oD * oH * oW;
+	if (total == 0) return PZ_OK;
+	PZ_SHAPE_LAUNCH(upsample_linear_bwd_kernel, total, (const float*)dy, (float*)dx, planes, D, H, W, oD, oH, oW, rd, rh, rw, three_d);
+	return PZ_OK;
+}
+
+int pz_divnorm_fwd(int dtype, const void* x, const void* means, void* y, int64_t planes, int64_t H, int64_t W, int n, float alpha, float beta, float K,
+				   void* stream)
+{
+	DivGeo g{};
+	int st = div_geo(g, dtype, planes, H, W, n, alpha, beta, K);
+	if (st != PZ_OK) return st;
+	const int64_t total = planes * H * W;
+	if (total == 0) return PZ_OK;
+	return dtype == PZ_F32 ? divnorm_launch<float>(0, x, means, nullptr, y, nullptr, nullptr, g, total, pz_stream(stream))
+						   : divnorm_launch<__half>(0, x, means, nullptr, y, nullptr, nullptr, g, total, pz_stream(stream));
+}
+
+int pz_divnorm_bwd(int dtype, const void* x, const void* means, const void* grad, void* dx, void* dmeans, void* tmp, int64_t planes, int64_t H,
+				   int64_t W, int n, float alpha, float beta, float K, void* stream)
+{
+	DivGeo g{};
+	int st = div_geo(g, dtype, planes, H, W, n, alpha, beta, K);
+	if (st != PZ_OK) return st;
+	const int64_t total = planes * H * W;
+	if (total == 0) return PZ_OK;
+	return dtype == PZ_F32 ? divnorm_launch<float>(1, x, means, grad, dx, dmeans, (float*)tmp, g, total, pz_stream(stream))
+						   : divnorm_launch<__half>(1, x, means, grad, dx, dmeans, (float*)tmp, g, total, pz_stream(stream));
+}
+
+}  // extern "C"

@@ -99,6 +99,19 @@ _SIGNATURES = {
 	"pz_graph_launch": [_P, _P],
 	"pz_graph_destroy": [_P],
 	"pz_debug_timeline": [_P],
+	"pz_divnorm_fwd": [c_int, _P, _P, _P, c_int64, c_int64, c_int64, c_int, c_float, c_float, c_float, _P],
+	"pz_divnorm_bwd": [c_int, _P, _P, _P, _P, _P, _P, c_int64, c_int64, c_int64, c_int, c_float, c_float, c_float, _P],
+	"pz_prelu_fwd": [_P, _P, _P, c_int64, c_int64, c_int64, c_int, _P],
+	"pz_prelu_bwd_data": [_P, _P, _P, _P, c_int64, c_int64, c_int64, c_int, _P],
+	"pz_prelu_bwd_params": [_P, _P, _P, c_int64, c_int64, c_int64, c_int, _P],
+	"pz_reflectpad_fwd": [c_int, _P, _P, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, _P],
+	"pz_reflectpad_bwd": [c_int, _P, _P, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, _P],
+	"pz_embed_fwd": [c_int, _P, _P, _P, c_int64, c_int64, _P],
+	"pz_embed_bwd": [c_int, _P, _P, _P, c_float, c_int64, c_int64, _P],
+	"pz_upsample_nearest_fwd": [_P, _P, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, _P],
+	"pz_upsample_nearest_bwd": [_P, _P, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, _P],
+	"pz_upsample_linear_fwd": [_P, _P, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_float, c_int, _P],
+	"pz_upsample_linear_bwd": [_P, _P, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_float, c_int, _P],
 	"pz_stream_create": [POINTER(_P)],
 	"pz_stream_destroy": [_P],
 	"pz_stream_synchronize": [_P],

@@ -29,7 +29,7 @@ MODULES = [
 	"Modules/MaxPool1D", "Modules/MaxPool2D", "Modules/MaxPool3D", "Modules/MaxUnpool2D", "Modules/MoveAxis", "Modules/Mul",
 	"Modules/MulAddConst", "Modules/NoiseInjector", "Modules/Penalty", "Modules/Replicate", "Modules/Reshape", "Modules/Slice",
 	"Modules/SoftMax", "Modules/Split", "Modules/SubtractMean", "Modules/Sum", "Modules/SwapAxes", "Modules/Tile", "Modules/ToList",
-	"Modules/Transpose",
+	"Modules/Transpose", "Modules/PRelu", "Modules/Pad1D", "Modules/Pad2D", "Modules/Upsample2D", "Modules/Upsample3D", "Modules/LCN",
 	"Containers/Sequential", "Containers/Parallel", "Containers/Graph",
 	"Cost/Abs", "Cost/BCE", "Cost/CrossEntropy", "Cost/Hinge", "Cost/KLDivergence", "Cost/L1Hinge", "Cost/MSE", "Cost/Multi",
 	"Cost/SVM", "Cost/SmoothL1",
@@ -125,3 +125,19 @@ def test_reference_gpuarray_utils_and_kernel_module_tests(refroot, bnd):
 	Pool.unpoolTest(bnd.poolmod)
 	retry(lambda: Costs.crossEntropyTest(bnd.costmod))
 	retry(lambda: Costs.svmTest(bnd.costmod))
+
+
+def test_reference_kernel_module_tests_of_the_side_modules(refroot, bnd):
+	"""Cuda/Kernels/{PRelu,Pad,Embedder,Upsample}.py: the reference's own tests of its NVRTC kernel modules, handed this backend's
+	prelumod / padmod / embedmod / upsamplemod instead"""
+	from PuzzleLib.Cuda.Kernels import PRelu, Pad, Embedder, Upsample
+
+	retry(lambda: PRelu.preluTest(bnd.prelumod))
+	for dtype, atol in bnd.dtypesSupported():
+		retry(lambda: Pad.reflectpad1dTest(bnd.padmod, dtype))
+		retry(lambda: Pad.reflectpad2dTest(bnd.padmod, dtype, atol))
+		retry(lambda: Embedder.embedTest(bnd.embedmod, dtype, atol))
+	retry(lambda: Upsample.upsample2dNearestTest(bnd.upsamplemod))
+	retry(lambda: Upsample.upsample2dLinearTest(bnd.upsamplemod))
+	retry(lambda: Upsample.upsample3dNearestTest(bnd.upsamplemod))
+	retry(lambda: Upsample.upsample3dLinearTest(bnd.upsamplemod))
