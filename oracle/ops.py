@@ -791,3 +791,186 @@ def lrn(x, N, alpha, beta, K, across_maps, grad=None, dtype=np.float64):
 	g = np.asarray(grad, dtype)
 	dx = g / norms ** beta - 2.0 * beta * scale * x * window_sum(g * x / norms ** (beta + 1))
 	return y, dx
+
+
+# ---------------------------------------------------------------------------------------------------------- side modules
+# pinned by tests/golden/ref_cuda_side.npz (the reference's NVRTC kernels / cuDNN on a B200, tests/golden_cases.py SIDE_CASES)
+def prelu(x, slopes, shared=False):
+	"""reference: Cuda/Kernels/PRelu.py:14-24 -- y = x * (x > 0 ? 1 : slope[c]); one slope for all maps when `shared`"""
+	a = slopes.reshape(()) if shared else slopes.reshape((1, -1) + (1, ) * (x.ndim - 2))
+	return x * np.where(x > 0, 1.0, a)
+
+
+def prelu_bwd(x, dy, slopes, shared=False):
+	"""reference: Cuda/Kernels/PRelu.py:26-56 -- (dx, dslopes); dslopes sums dy * x * (x <= 0) over everything but the map axis"""
+	a = slopes.reshape(()) if shared else slopes.reshape((1, -1) + (1, ) * (x.ndim - 2))
+	dx = dy * np.where(x > 0, 1.0, a)
+	contrib = dy.astype(np.float64) * x * (x <= 0)
+	ds = contrib.sum().reshape(1) if shared else contrib.sum(axis=(0, ) + tuple(range(2, x.ndim)))
+	return dx, ds
+
+
+def _pad_widths(ndim, pad):
+	if ndim == 3:
+		return ((0, 0), (0, 0), (pad[0], pad[1]))
+	return ((0, 0), (0, 0), (pad[0], pad[1]), (pad[2], pad[3]))
+
+
+def reflectpad(x, pad):
+	"""reference: Cuda/Kernels/Pad.py:33-74 -- numpy's "reflect" mode; pad = (left, right) or (up, bottom, left, right)"""
+	return np.pad(x, _pad_widths(x.ndim, pad), mode="reflect")
+
+
+def reflectpad_bwd(dy, pad):
+	"""the adjoint of reflectpad (reference: scatter with atomicAdd, Cuda/Kernels/Pad.py:77-139): every padded sample's gradient
+	returns to the input element it was copied from"""
+	inshape = tuple(n - sum(w) for n, w in zip(dy.shape, _pad_widths(dy.ndim, pad)))
+	index = np.arange(int(np.prod(inshape))).reshape(inshape)
+	src = np.pad(index, _pad_widths(dy.ndim, pad), mode="reflect")
+	dx = np.zeros(int(np.prod(inshape)), dtype=np.float64)
+	np.add.at(dx, src.ravel(), dy.astype(np.float64).ravel())
+	return dx.reshape(inshape)
+
+
+def embed(idx, W):
+	"""reference: Cuda/Kernels/Embedder.py:11-22 -- rows of W; index -1 leaves a zero row"""
+	out = W[np.maximum(idx, 0)].copy()
+	out[idx == -1] = 0
+	return out
+
+
+def embed_bwd(idx, dy, W, scale):
+	"""reference: Cuda/Kernels/Embedder.py:24-41 -- W[idx] += scale * dy (repeated words accumulate, -1 skipped)"""
+	out = W.astype(np.float64).copy()
+	keep = idx.ravel() != -1
+	np.add.at(out, idx.ravel()[keep], scale * dy.reshape(-1, dy.shape[-1]).astype(np.float64)[keep])
+	return out
+
+
+def _scales(scale, n):
+	return (scale, ) * n if isinstance(scale, int) else tuple(scale)
+
+
+def upsample_nearest(x, scale):
+	"""reference: Cuda/Kernels/Upsample.py:9-60 -- every input element fills its block of the output"""
+	for axis, s in enumerate(_scales(scale, x.ndim - 2)):
+		x = np.repeat(x, s, axis=2 + axis)
+	return x
+
+
+def upsample_nearest_bwd(dy, scale):
+	"""reference: Cuda/Kernels/Upsample.py:26-43,62-96 -- block sums"""
+	scales = _scales(scale, dy.ndim - 2)
+	shape = list(dy.shape[:2])
+	for n, s in zip(dy.shape[2:], scales):
+		shape += [n // s, s]
+	return dy.astype(np.float64).reshape(shape).sum(axis=tuple(range(3, len(shape), 2)))
+
+
+def _lerp_axis(n_in, n_out):
+	"""float32 source coordinates like the kernels (Upsample.py:108-118): i0, i0 + step, weight of the second tap"""
+	ratio = np.float32((n_in - 1) / (n_out - 1))
+	src = ratio * np.arange(n_out, dtype=np.float32)
+	i0 = src.astype(np.int32)
+	step = (i0 < n_in - 1).astype(np.int32)
+	w1 = (src - i0.astype(np.float32)).astype(np.float32)
+	return i0, step, w1
+
+
+def upsample_linear(x, scale, quirk=True):
+	"""reference: Cuda/Kernels/Upsample.py:100-139 (2-d), 186-252 (3-d) -- align-corners (tri)linear interpolation.  `quirk`: one tap
+	of the reference's 3-d forward kernel is addressed with d1 * inw * inw instead of d1 * inh * inw (Upsample.py:241); it only
+	shows when inh != inw"""
+	scales = _scales(scale, x.ndim - 2)
+	if x.ndim == 4:
+		x = x[:, :, None]
+		scales = (1, ) + scales
+	N, C, D, H, W = x.shape
+	oD, oH, oW = D * scales[0], H * scales[1], W * scales[2]
+	three_d = scales[0] != 1 or D != 1
+	h0, hs, hw1 = _lerp_axis(H, oH)
+	w0, ws, ww1 = _lerp_axis(W, oW)
+	if three_d:
+		d0, dstep, dw1 = _lerp_axis(D, oD)
+	else:
+		d0, dstep, dw1 = np.zeros(1, np.int32), np.zeros(1, np.int32), np.zeros(1, np.float32)
+	f = x.astype(np.float32)
+	flat = f.reshape(N, C, -1)
+	D0, H0, W0 = np.meshgrid(d0, h0, w0, indexing="ij")
+	DS, HS, WS = np.meshgrid(dstep, hs, ws, indexing="ij")
+	Dw, Hw, Ww = np.meshgrid(dw1, hw1, ww1, indexing="ij")
+
+	def tap(d, h, w, quirky=False):
+		if quirky and quirk and three_d:
+			lin = d * W * W + h * W + w
+			lin = np.where(lin >= D * H * W, d * H * W + h * W + w, lin)
+		else:
+			lin = d * H * W + h * W + w
+		return flat[:, :, lin]
+
+	one = np.float32(1)
+	near = (one - Hw) * ((one - Ww) * tap(D0, H0, W0) + Ww * tap(D0, H0, W0 + WS, True)) + \
+		   Hw * ((one - Ww) * tap(D0, H0 + HS, W0) + Ww * tap(D0, H0 + HS, W0 + WS))
+	if not three_d:
+		return near[:, :, 0]
+	far = (one - Hw) * ((one - Ww) * tap(D0 + DS, H0, W0) + Ww * tap(D0 + DS, H0, W0 + WS)) + \
+		  Hw * ((one - Ww) * tap(D0 + DS, H0 + HS, W0) + Ww * tap(D0 + DS, H0 + HS, W0 + WS))
+	return (one - Dw) * near + Dw * far
+
+
+def upsample_linear_bwd(dy, scale):
+	"""reference: Cuda/Kernels/Upsample.py:141-184, 254-296 -- each output gradient goes to its 4 / 8 taps with the forward weights"""
+	scales = _scales(scale, dy.ndim - 2)
+	two_d = dy.ndim == 4
+	if two_d:
+		dy = dy[:, :, None]
+		scales = (1, ) + scales
+	N, C, oD, oH, oW = dy.shape
+	D, H, W = oD // scales[0], oH // scales[1], oW // scales[2]
+	h0, hs, hw1 = _lerp_axis(H, oH)
+	w0, ws, ww1 = _lerp_axis(W, oW)
+	if two_d:
+		d0, dstep, dw1 = np.zeros(1, np.int32), np.zeros(1, np.int32), np.zeros(1, np.float32)
+	else:
+		d0, dstep, dw1 = _lerp_axis(D, oD)
+	D0, H0, W0 = np.meshgrid(d0, h0, w0, indexing="ij")
+	DS, HS, WS = np.meshgrid(dstep, hs, ws, indexing="ij")
+	Dw, Hw, Ww = (a.astype(np.float64) for a in np.meshgrid(dw1, hw1, ww1, indexing="ij"))
+	g = dy.astype(np.float64).reshape(N * C, -1)
+	dx = np.zeros((N * C, D * H * W), dtype=np.float64)
+	for dd, wd in ((D0, 1 - Dw), (D0 + DS, Dw)):
+		for hh, wh in ((H0, 1 - Hw), (H0 + HS, Hw)):
+			for ww, wx in ((W0, 1 - Ww), (W0 + WS, Ww)):
+				lin = (dd * H * W + hh * W + ww).ravel()
+				weight = (wd * wh * wx).ravel()
+				for row in range(N * C):
+					np.add.at(dx[row], lin, weight * g[row])
+	dx = dx.reshape(N, C, D, H, W)
+	return dx[:, :, 0] if two_d else dx
+
+
+def lcn(x, means, N, alpha, beta, K, grad=None):
+	"""mapLRN with a means tensor = cudnnDivisiveNormalization (CuDnnNorm.c:329-527; host formulas of Modules/LCN.py:62-143).
+	-> y, or (dx, dmeans) when `grad` is given.  Window of position i: [i - lb, i + la) clipped, lb = (N - 1) // 2, la = N - lb."""
+	x64, m64 = x.astype(np.float64), means.astype(np.float64)
+	B, C, H, W = x.shape
+	lb = (N - 1) // 2
+	la = N - lb
+	norm = np.empty_like(x64)
+	sumdiff = np.empty_like(x64)
+	for h in range(H):
+		for w in range(W):
+			win = x64[:, :, max(0, h - lb):min(H, h + la), max(0, w - lb):min(W, w + la)] - m64[:, :, h:h + 1, w:w + 1]
+			norm[:, :, h, w] = K + alpha / N ** 2 * (win ** 2).sum(axis=(2, 3))
+			sumdiff[:, :, h, w] = win.sum(axis=(2, 3))
+	if grad is None:
+		return x64 * norm ** -beta
+	g = grad.astype(np.float64)
+	t = g * x64 * norm ** -(beta + 1)
+	k = 2.0 * alpha * beta / N ** 2
+	dx = g * norm ** -beta
+	for h in range(H):
+		for w in range(W):
+			sl = (slice(None), slice(None), slice(max(0, h - lb), min(H, h + la)), slice(max(0, w - lb), min(W, w + la)))
+			dx[:, :, h, w] -= k * (x64[:, :, h, w] * t[sl].sum(axis=(2, 3)) - (t[sl] * m64[sl]).sum(axis=(2, 3)))
+	return dx, k * t * sumdiff

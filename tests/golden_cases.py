@@ -19,9 +19,9 @@ import numpy as np
 def bind():
 	"""The reference's late-bound function table (whatever backend PuzzleLib was configured with)."""
 	from PuzzleLib.Backend import gpuarray, Dnn, Blas, Memory
-	from PuzzleLib.Backend.Kernels import ElementWise, MatVec, Pool, Costs
+	from PuzzleLib.Backend.Kernels import ElementWise, MatVec, Pool, Costs, PRelu, Pad, Embedder, Upsample
 	return types.SimpleNamespace(gpuarray=gpuarray, Dnn=Dnn, Blas=Blas, Memory=Memory, ElementWise=ElementWise, MatVec=MatVec,
-								 Pool=Pool, Costs=Costs)
+								 Pool=Pool, Costs=Costs, PRelu=PRelu, Pad=Pad, Embedder=Embedder, Upsample=Upsample)
 
 
 def _g(B, ary):
@@ -442,13 +442,94 @@ def seedOf(name):
 
 
 def run(B, names=None):
-	"""-> {"case/key": array} for every case in `names` (default: all), each with its own fixed seed"""
+	"""-> {"case/key": array} for every case in `names` (default: all of CASES), each with its own fixed seed"""
 	out = {}
 	for name in (CASES if names is None else names):
 		rng = np.random.RandomState(seedOf(name))
-		for key, val in CASES[name](B, rng).items():
+		fn = CASES[name] if name in CASES else SIDE_CASES[name]
+		for key, val in fn(B, rng).items():
 			out["%s/%s" % (name, key)] = np.asarray(val)
 	return out
+
+
+# ---------------------------------------------------------------------------------------------------------- side modules
+# PReLU, reflection padding, embedding lookup, up-sampling, divisive normalisation: the kernel modules next to the hot path
+# (Backend/Kernels/{PRelu,Pad,Embedder,Upsample}.py, Dnn.mapLRN with a means tensor).  Stored in tests/golden/ref_cuda_side.npz.
+def preluCase(shared):
+	def case(B, rng):
+		x = rng.randn(3, 5, 4, 6).astype(np.float32)
+		slopes = rng.randn(1 if shared else 5).astype(np.float32)
+		dy = rng.randn(*x.shape).astype(np.float32)
+		data, gs, grad = _g(B, x), _g(B, slopes), _g(B, dy)
+		y = B.PRelu.prelu(data, gs, False, shared)
+		dx = B.PRelu.preluBackwardData(grad, gs, data, shared)
+		ds = B.PRelu.preluBackwardParams(data, grad, shared)
+		return {"in_x": x, "in_slopes": slopes, "in_dy": dy, "y": y.get(), "dx": dx.get(), "dslopes": ds.get()}
+	return case
+
+
+def padCase(shape, pad, dtype):
+	def case(B, rng):
+		x = rng.randn(*shape).astype(dtype)
+		fwd, bwd = (B.Pad.reflectpad1d, B.Pad.reflectpad1dBackward) if len(shape) == 3 else (B.Pad.reflectpad2d, B.Pad.reflectpad2dBackward)
+		y = fwd(_g(B, x), pad)
+		dy = rng.randn(*y.shape).astype(dtype)
+		dx = bwd(_g(B, dy), pad)
+		return {"in_x": x, "in_dy": dy, "y": y.get(), "dx": dx.get()}
+	return case
+
+
+def embedCase(dtype):
+	def case(B, rng):
+		vocab, emb = 50, 12
+		idx = rng.randint(-1, vocab, size=(4, 9)).astype(np.int32)
+		idx[0, :3] = 7                                                # repeated words: their gradient rows add up
+		W = rng.randn(vocab, emb).astype(dtype)
+		dy = rng.randn(4, 9, emb).astype(dtype)
+		gW = _g(B, W)
+		y = B.Embedder.embed(_g(B, idx), gW)
+		B.Embedder.embedBackwardParams(_g(B, idx), _g(B, dy), gW, 0.25)
+		return {"in_idx": idx, "in_W": W, "in_dy": dy, "y": y.get(), "W_after": gW.get()}
+	return case
+
+
+def upsampleCase(shape, scale, mode):
+	def case(B, rng):
+		x = rng.randn(*shape).astype(np.float32)
+		fwd, bwd = (B.Upsample.upsample2d, B.Upsample.upsample2dBackward) if len(shape) == 4 else \
+				   (B.Upsample.upsample3d, B.Upsample.upsample3dBackward)
+		y = fwd(_g(B, x), scale, mode)
+		dy = rng.randn(*y.shape).astype(np.float32)
+		dx = bwd(_g(B, dy), scale, mode)
+		return {"in_x": x, "in_dy": dy, "y": y.get(), "dx": dx.get()}
+	return case
+
+
+def lcnCase(shape, N):
+	def case(B, rng):
+		Dnn = B.Dnn
+		x = rng.randn(*shape).astype(np.float32)
+		dy = rng.randn(*shape).astype(np.float32)
+		data, grad = _g(B, x), _g(B, dy)
+		alpha, beta, K = 1e-2, 0.75, 2.0
+		means, _ = Dnn.poolNd(data, (N, N), 1, (N // 2, N // 2), Dnn.PoolMode.avgWithPad, False)
+		y, ws = Dnn.mapLRN(data, means, N, alpha, beta, K, False)
+		dx, dmeans = Dnn.mapLRNBackward(data, y, grad, means, ws, N, alpha, beta, K)
+		return {"in_x": x, "in_dy": dy, "means": means.get(), "y": y.get(), "dx": dx.get(), "dmeans": dmeans.get()}
+	return case
+
+
+SIDE_CASES = {
+	"side_prelu": preluCase(False), "side_prelu_shared": preluCase(True),
+	"side_pad1d_f32": padCase((2, 3, 11), (2, 3), np.float32), "side_pad2d_f32": padCase((2, 3, 7, 9), (2, 1, 3, 0), np.float32),
+	"side_pad2d_f16": padCase((2, 3, 7, 9), (1, 2, 2, 2), np.float16),
+	"side_embed_f32": embedCase(np.float32),
+	"side_up2d_nearest": upsampleCase((2, 3, 5, 7), (2, 3), "nearest"), "side_up2d_linear": upsampleCase((2, 3, 5, 7), (2, 3), "linear"),
+	"side_up3d_nearest": upsampleCase((1, 2, 3, 4, 5), (2, 1, 2), "nearest"),
+	"side_up3d_linear": upsampleCase((1, 2, 3, 4, 4), (2, 2, 3), "linear"),
+	"side_up3d_linear_hw": upsampleCase((1, 2, 3, 5, 4), (2, 2, 2), "linear"),     # inh != inw: the reference's addressing quirk shows
+	"side_lcn": lcnCase((2, 3, 8, 9), 5),
+}
 
 
 # ---------------------------------------------------------------------------------------------------------- whole nets

@@ -68,6 +68,33 @@ def test_case_matches_the_reference_cuda_backend(table, gold, name):
 	assert failures == [], "\n".join(failures)
 
 
+@pytest.fixture(scope="module")
+def goldSide():
+	data = np.load(os.path.join(GOLDEN, "ref_cuda_side.npz"))
+	return {key: data[key] for key in data.files}
+
+
+@pytest.mark.parametrize("name", sorted(gc.SIDE_CASES))
+def test_side_module_case_matches_the_reference_cuda_backend(table, goldSide, name):
+	"""PReLU, reflection padding, embedding lookup, up-sampling, divisive normalisation against the reference's NVRTC kernels /
+	cuDNN (tests/golden/ref_cuda_side.npz): data movement bit-exact, arithmetic within 2e-5 (4e-3 for float16)"""
+	got = gc.run(table, [name])
+	failures = []
+	for key, val in got.items():
+		want = goldSide[key]
+		field = key.split("/")[1]
+		assert val.shape == want.shape and val.dtype == want.dtype, key
+		if field.startswith("in_") or val.dtype.kind in "iu" or (field == "y" and ("pad" in name or "nearest" in name or "embed" in name)):
+			if not np.array_equal(val, want):
+				failures.append("%s: not bit-exact" % key)
+		else:
+			bar = 4e-3 if val.dtype == np.float16 else 2e-5
+			err = rel(val, want)
+			if not err < bar:
+				failures.append("%s: relative error %.3e > %.1e" % (key, err, bar))
+	assert failures == [], "\n".join(failures)
+
+
 def l2(got, want):
 	got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
 	return float(np.linalg.norm(got - want) / (np.linalg.norm(want) + 1e-30))

@@ -22,6 +22,7 @@ def main():
 	ap.add_argument("--out", required=True)
 	ap.add_argument("--nets", default=None)
 	ap.add_argument("--only", default=None)
+	ap.add_argument("--side", action="store_true", help="the side-module table (golden_cases.SIDE_CASES -> ref_cuda_side.npz) instead of CASES")
 	args = ap.parse_args()
 
 	refroot = os.path.join(ROOT, "baseline", "_ref")
@@ -39,7 +40,8 @@ def main():
 	B = golden_cases.bind()
 	print("backend:", type(B.gpuarray.backend).__name__, B.gpuarray.getDeviceName(), flush=True)
 
-	names = [n for n in golden_cases.CASES if args.only is None or any(s in n for s in args.only.split(","))]
+	table = golden_cases.SIDE_CASES if args.side else golden_cases.CASES
+	names = [n for n in table if args.only is None or any(s in n for s in args.only.split(","))]
 	out, errors = {}, {}
 	for name in names:
 		try:
