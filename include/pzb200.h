@@ -121,6 +121,13 @@ int pz_divnorm_fwd(int dtype, const void* x, const void* means, void* y, int64_t
 				   void* stream);
 int pz_divnorm_bwd(int dtype, const void* x, const void* means, const void* grad, void* dx, void* dmeans, void* tmp, int64_t planes, int64_t H,
 				   int64_t W, int n, float alpha, float beta, float K, void* stream);
+/* spatial transformer (cudnnSpatialTfGridGenerator* + cudnnSpatialTfSampler*, CuDnnSpatialTf.c:20-222): theta [B][2][3] -> grid
+ * [B][oH][oW][2] -> out [B][C][oH][oW] by bilinear sampling of data [B][C][H][W]; the backward pass returns dx (zeroed here),
+ * dtheta [B][2][3] and dgrid; float32 / float16 */
+int pz_spatialtf_fwd(int dtype, const void* data, const void* theta, void* grid, void* out, int64_t B, int64_t C, int H, int W, int oH, int oW,
+					 void* stream);
+int pz_spatialtf_bwd(int dtype, const void* grad, const void* data, const void* grid, void* dx, void* dtheta, void* dgrid, int64_t B, int64_t C,
+					 int H, int W, int oH, int oW, void* stream);
 /* diagnosis: the 32 per-role phase clock sums of the tcgen05 engine since the last call (only in builds with -DPZ_TIMELINE,
  * PZ_ERR_UNSUPPORTED otherwise); no reference counterpart */
 int pz_debug_timeline(unsigned long long* out);

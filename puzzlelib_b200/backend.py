@@ -459,6 +459,37 @@ class DnnContext:
 								 data.shape[0] * data.shape[1], data.shape[2], data.shape[3], int(N), float(alpha), float(beta), float(K), None))
 		return out, dmeans
 
+	# ------------------------------------------------------------------------------------------ spatial transformer
+	def spatialTf(self, data, transform, outshape=None, getGrid=False, grid=None, out=None, allocator=None):
+		"""reference: CuDnn_Context_pySpatialTf, CuDnnSpatialTf.c:66-150 -- affine grid + bilinear sampler"""
+		self._check4d(data, "data")
+		outshape = tuple(data.shape) if outshape is None else tuple(int(v) for v in outshape)
+		if len(outshape) != 4 or outshape[:2] != tuple(data.shape[:2]):
+			raise ValueError("invalid outshape")
+		if transform.shape != (data.shape[0], 2, 3) or transform.dtype != data.dtype:
+			raise ValueError("invalid transform gpuarray data layout")
+		gridshape = (data.shape[0], outshape[2], outshape[3], 2)
+		grid = GPUArray(gridshape, data.dtype, allocator=allocator) if grid is None else _checkOut(grid, gridshape, data.dtype)
+		out = GPUArray(outshape, data.dtype, allocator=allocator) if out is None else _checkOut(out, outshape, data.dtype)
+		check(lib.pz_spatialtf_fwd(dtypeCode(data.dtype), data.ptr, transform.ptr, grid.ptr, out.ptr, data.shape[0], data.shape[1],
+								   data.shape[2], data.shape[3], outshape[2], outshape[3], None))
+		return (out, grid) if getGrid else out
+
+	def spatialTfBackward(self, grad, indata, grid, getDGrid=False, dgrid=None, dtransform=None, out=None, allocator=None):
+		"""reference: CuDnn_Context_pySpatialTfBackward, CuDnnSpatialTf.c:229-285 -> (ingrad, dtransform[, dgrid])"""
+		self._check4d(grad, "grad")
+		self._check4d(indata, "indata")
+		B, C, H, W = indata.shape
+		if grad.shape[:2] != (B, C) or grad.dtype != indata.dtype or grid.shape != (B, grad.shape[2], grad.shape[3], 2):
+			raise ValueError("invalid grad / grid gpuarray data layout")
+		out = GPUArray(indata.shape, indata.dtype, allocator=allocator) if out is None else _checkOut(out, indata.shape, indata.dtype)
+		dgrid = GPUArray(grid.shape, indata.dtype, allocator=allocator) if dgrid is None else _checkOut(dgrid, grid.shape, indata.dtype)
+		dtransform = GPUArray((B, 2, 3), indata.dtype, allocator=allocator) if dtransform is None else \
+			_checkOut(dtransform, (B, 2, 3), indata.dtype)
+		check(lib.pz_spatialtf_bwd(dtypeCode(indata.dtype), grad.ptr, indata.ptr, grid.ptr, out.ptr, dtransform.ptr, dgrid.ptr, B, C, H, W,
+								   grad.shape[2], grad.shape[3], None))
+		return (out, dtransform, dgrid) if getDGrid else (out, dtransform)
+
 	# ------------------------------------------------------------------------------------------ batch norm
 	@staticmethod
 	def _bnGeometry(data, mode):

@@ -274,6 +274,118 @@ __global__ void __launch_bounds__(kThreads) upsample_linear_bwd_kernel(const flo
 	}
 }
 
+// ------------------------------------------------------------------------------------------ spatial transformer
+// cudnnSpatialTfGridGenerator* + cudnnSpatialTfSampler* (CuDnnSpatialTf.c:20-222; host formulas of Cuda/Wrappers/CuDnnSpatialTf.py):
+//   grid[b][y][x] = theta[b] (2 x 3) . (xn, yn, 1),  xn = -1 + 2 x / (oW - 1),  yn = -1 + 2 y / (oH - 1)
+//   out[b][c][y][x] = bilinear sample of data[b][c] at ((gx + 1) (W - 1) / 2, (gy + 1) (H - 1) / 2), zero outside the map
+__device__ __forceinline__ float norm_coord(int i, int n) { return -1.0f + (float)i * (2.0f / (float)(n - 1)); }
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) stf_grid_kernel(const T* __restrict__ theta, T* __restrict__ grid, int64_t B, int oH, int oW)
+{
+	const int64_t osize = (int64_t)oH * oW, total = B * osize;
+	for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += (int64_t)gridDim.x * kThreads) {
+		const int64_t b = i / osize;
+		const int r = (int)(i - b * osize), y = r / oW, x = r - y * oW;
+		const T* t = theta + b * 6;
+		const float xn = norm_coord(x, oW), yn = norm_coord(y, oH);
+		stf(grid + 2 * i, ldf(t) * xn + ldf(t + 1) * yn + ldf(t + 2));
+		stf(grid + 2 * i + 1, ldf(t + 3) * xn + ldf(t + 4) * yn + ldf(t + 5));
+	}
+}
+
+struct Taps {
+	int x0, y0;
+	float fx, fy;
+	bool okx0, okx1, oky0, oky1;
+};
+__device__ __forceinline__ Taps taps_of(float gx, float gy, int H, int W)
+{
+	Taps t;
+	const float nx = (gx + 1.0f) * (0.5f * (float)(W - 1)), ny = (gy + 1.0f) * (0.5f * (float)(H - 1));
+	const float flx = floorf(nx), fly = floorf(ny);
+	t.x0 = (int)flx; t.y0 = (int)fly;
+	t.fx = nx - flx; t.fy = ny - fly;
+	t.okx0 = t.x0 >= 0 && t.x0 < W; t.okx1 = t.x0 + 1 >= 0 && t.x0 + 1 < W;
+	t.oky0 = t.y0 >= 0 && t.y0 < H; t.oky1 = t.y0 + 1 >= 0 && t.y0 + 1 < H;
+	return t;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) stf_sample_fwd_kernel(const T* __restrict__ data, const T* __restrict__ grid, T* __restrict__ out, int64_t B,
+																   int C, int H, int W, int oH, int oW)
+{
+	const int64_t osize = (int64_t)oH * oW, total = B * C * osize;
+	for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += (int64_t)gridDim.x * kThreads) {
+		const int64_t bc = i / osize, b = bc / C, pos = i - bc * osize;
+		const T* g = grid + 2 * (b * osize + pos);
+		const Taps t = taps_of(ldf(g), ldf(g + 1), H, W);
+		const T* src = data + bc * (int64_t)H * W + (int64_t)t.y0 * W + t.x0;
+		float v = 0.0f;
+		if (t.oky0 && t.okx0) v += ldf(src) * (1.0f - t.fy) * (1.0f - t.fx);
+		if (t.oky0 && t.okx1) v += ldf(src + 1) * (1.0f - t.fy) * t.fx;
+		if (t.oky1 && t.okx0) v += ldf(src + W) * t.fy * (1.0f - t.fx);
+		if (t.oky1 && t.okx1) v += ldf(src + W + 1) * t.fy * t.fx;
+		stf(out + i, v);
+	}
+}
+
+// one thread per (image, output position): the taps are shared by the channels; the data gradient is scattered (red.add into a
+// zeroed tensor, as taps of neighbouring outputs collide), the grid gradient is summed over the channels in registers
+template <typename T>
+__global__ void __launch_bounds__(kThreads) stf_sample_bwd_kernel(const T* __restrict__ grad, const T* __restrict__ data, const T* __restrict__ grid,
+																   T* dx, T* __restrict__ dgrid, int64_t B, int C, int H, int W, int oH, int oW)
+{
+	const int64_t osize = (int64_t)oH * oW, total = B * osize;
+	const float sx = 0.5f * (float)(W - 1), sy = 0.5f * (float)(H - 1);          // d(nx) / d(gx), d(ny) / d(gy)
+	for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += (int64_t)gridDim.x * kThreads) {
+		const int64_t b = i / osize, pos = i - b * osize;
+		const Taps t = taps_of(ldf(grid + 2 * i), ldf(grid + 2 * i + 1), H, W);
+		float gx = 0.0f, gy = 0.0f;
+		for (int c = 0; c < C; c++) {
+			const int64_t plane = (b * C + c) * (int64_t)H * W + (int64_t)t.y0 * W + t.x0;
+			const float g = ldf(grad + (b * C + c) * osize + pos);
+			float vx = 0.0f, vy = 0.0f;
+			if (t.oky0 && t.okx0) { const float d = ldf(data + plane); atomic_add(dx + plane, g * (1.0f - t.fy) * (1.0f - t.fx)); vx -= d * (1.0f - t.fy); vy -= d * (1.0f - t.fx); }
+			if (t.oky0 && t.okx1) { const float d = ldf(data + plane + 1); atomic_add(dx + plane + 1, g * (1.0f - t.fy) * t.fx); vx += d * (1.0f - t.fy); vy -= d * t.fx; }
+			if (t.oky1 && t.okx0) { const float d = ldf(data + plane + W); atomic_add(dx + plane + W, g * t.fy * (1.0f - t.fx)); vx -= d * t.fy; vy += d * (1.0f - t.fx); }
+			if (t.oky1 && t.okx1) { const float d = ldf(data + plane + W + 1); atomic_add(dx + plane + W + 1, g * t.fy * t.fx); vx += d * t.fy; vy += d * t.fx; }
+			gx = fmaf(g, vx * sx, gx);
+			gy = fmaf(g, vy * sy, gy);
+		}
+		stf(dgrid + 2 * i, gx);
+		stf(dgrid + 2 * i + 1, gy);
+	}
+}
+
+// dtheta[b] = sum over positions of outer(dgrid[b][y][x], (xn, yn, 1)): one block per image, fixed summation tree
+template <typename T>
+__global__ void __launch_bounds__(kThreads) stf_dtheta_kernel(const T* __restrict__ dgrid, T* __restrict__ dtheta, int oH, int oW)
+{
+	__shared__ float red[6][kThreads / 32];
+	const int64_t b = blockIdx.x;
+	const int osize = oH * oW;
+	float acc[6] = {};
+	for (int r = threadIdx.x; r < osize; r += kThreads) {
+		const int y = r / oW, x = r - y * oW;
+		const float xn = norm_coord(x, oW), yn = norm_coord(y, oH);
+		const float gx = ldf(dgrid + 2 * (b * osize + r)), gy = ldf(dgrid + 2 * (b * osize + r) + 1);
+		acc[0] += gx * xn; acc[1] += gx * yn; acc[2] += gx;
+		acc[3] += gy * xn; acc[4] += gy * yn; acc[5] += gy;
+	}
+	for (int k = 0; k < 6; k++) {
+		float v = acc[k];
+		for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+		if ((threadIdx.x & 31) == 0) red[k][threadIdx.x >> 5] = v;
+	}
+	__syncthreads();
+	if (threadIdx.x < 6) {
+		float v = 0.0f;
+		for (int w = 0; w < kThreads / 32; w++) v += red[threadIdx.x][w];
+		stf(dtheta + b * 6 + threadIdx.x, v);
+	}
+}
+
 // ------------------------------------------------------------------------------------------ divisive normalisation (LCN)
 // mapLRN with a means tensor = cudnnDivisiveNormalization (CuDnnNorm.c:329-510; host formulas of Modules/LCN.py:62-143):
 //   norm_i = K + alpha / N^2 * sum_{j in win(i)} (x_j - m_i)^2,   y_i = x_i * norm_i^-beta,   win(i) = [i - lb, i + la) clipped
@@ -515,6 +627,46 @@ int pz_divnorm_bwd(int dtype, const void* x, const void* means, const void* grad
 	if (total == 0) return PZ_OK;
 	return dtype == PZ_F32 ? divnorm_launch<float>(1, x, means, grad, dx, dmeans, (float*)tmp, g, total, pz_stream(stream))
 						   : divnorm_launch<__half>(1, x, means, grad, dx, dmeans, (float*)tmp, g, total, pz_stream(stream));
+}
+
+int pz_spatialtf_fwd(int dtype, const void* data, const void* theta, void* grid, void* out, int64_t B, int64_t C, int H, int W, int oH, int oW,
+					 void* stream)
+{
+	PZ_REQUIRE(dtype == PZ_F32 || dtype == PZ_F16, "spatialTf: unsupported dtype %d", dtype);
+	PZ_REQUIRE(B >= 0 && C > 0 && C < (1ll << 31) && H > 0 && W > 0 && oH > 0 && oW > 0, "spatialTf: invalid shape");
+	if (B == 0) return PZ_OK;
+	const int64_t gtotal = B * oH * oW;
+	if (dtype == PZ_F32) {
+		PZ_SHAPE_LAUNCH(stf_grid_kernel<float>, gtotal, (const float*)theta, (float*)grid, B, oH, oW);
+		PZ_SHAPE_LAUNCH(stf_sample_fwd_kernel<float>, gtotal * C, (const float*)data, (const float*)grid, (float*)out, B, (int)C, H, W, oH, oW);
+	} else {
+		PZ_SHAPE_LAUNCH(stf_grid_kernel<__half>, gtotal, (const __half*)theta, (__half*)grid, B, oH, oW);
+		PZ_SHAPE_LAUNCH(stf_sample_fwd_kernel<__half>, gtotal * C, (const __half*)data, (const __half*)grid, (__half*)out, B, (int)C, H, W, oH, oW);
+	}
+	return PZ_OK;
+}
+
+int pz_spatialtf_bwd(int dtype, const void* grad, const void* data, const void* grid, void* dx, void* dtheta, void* dgrid, int64_t B, int64_t C,
+					 int H, int W, int oH, int oW, void* stream)
+{
+	PZ_REQUIRE(dtype == PZ_F32 || dtype == PZ_F16, "spatialTf: unsupported dtype %d", dtype);
+	PZ_REQUIRE(B >= 0 && C > 0 && C < (1ll << 31) && H > 0 && W > 0 && oH > 0 && oW > 0, "spatialTf: invalid shape");
+	if (B == 0) return PZ_OK;
+	const size_t es = dtype == PZ_F32 ? 4 : 2;
+	PZ_CHECK_CUDA(cudaMemsetAsync(dx, 0, (size_t)(B * C) * H * W * es, pz_stream(stream)));
+	const int64_t gtotal = B * oH * oW;
+	if (dtype == PZ_F32) {
+		PZ_SHAPE_LAUNCH(stf_sample_bwd_kernel<float>, gtotal, (const float*)grad, (const float*)data, (const float*)grid, (float*)dx, (float*)dgrid, B,
+						(int)C, H, W, oH, oW);
+		stf_dtheta_kernel<float><<<(unsigned)B, kThreads, 0, pz_stream(stream)>>>((const float*)dgrid, (float*)dtheta, oH, oW);
+	} else {
+		PZ_SHAPE_LAUNCH(stf_sample_bwd_kernel<__half>, gtotal, (const __half*)grad, (const __half*)data, (const __half*)grid, (__half*)dx,
+						(__half*)dgrid, B, (int)C, H, W, oH, oW);
+		stf_dtheta_kernel<__half><<<(unsigned)B, kThreads, 0, pz_stream(stream)>>>((const __half*)dgrid, (__half*)dtheta, oH, oW);
+	}
+	pz_count_launch(1);
+	PZ_LAUNCH_CHECK();
+	return PZ_OK;
 }
 
 }  // extern "C"

@@ -29,20 +29,23 @@ MODULES = [
 	"Modules/MaxPool1D", "Modules/MaxPool2D", "Modules/MaxPool3D", "Modules/MaxUnpool2D", "Modules/MoveAxis", "Modules/Mul",
 	"Modules/MulAddConst", "Modules/NoiseInjector", "Modules/Penalty", "Modules/Replicate", "Modules/Reshape", "Modules/Slice",
 	"Modules/SoftMax", "Modules/Split", "Modules/SubtractMean", "Modules/Sum", "Modules/SwapAxes", "Modules/Tile", "Modules/ToList",
-	"Modules/Transpose", "Modules/PRelu", "Modules/Pad1D", "Modules/Pad2D", "Modules/Upsample2D", "Modules/Upsample3D", "Modules/LCN",
+	"Modules/Transpose", "Modules/PRelu", "Modules/Pad1D", "Modules/Pad2D", "Modules/Upsample2D", "Modules/Upsample3D", "Modules/LCN", "Modules/SpatialTf",
 	"Containers/Sequential", "Containers/Parallel", "Containers/Graph",
 	"Cost/Abs", "Cost/BCE", "Cost/CrossEntropy", "Cost/Hinge", "Cost/KLDivergence", "Cost/L1Hinge", "Cost/MSE", "Cost/Multi",
 	"Cost/SVM", "Cost/SmoothL1",
 	"Optimizers/AdaDelta", "Optimizers/AdaGrad", "Optimizers/Adam", "Optimizers/MomentumSGD", "Optimizers/NesterovSGD",
 	"Optimizers/RMSProp", "Optimizers/RMSPropGraves", "Optimizers/SGD", "Optimizers/SMORMS3",
-	"Models/Nets/LeNet", "Models/Nets/ResNet", "Models/Nets/VGG", "Models/Nets/NiN", "Models/Nets/Inception",
+	"Models/Nets/LeNet", "Models/Nets/ResNet", "Models/Nets/VGG", "Models/Nets/NiN", "Models/Nets/Inception", "Models/Nets/MiniYolo",
+	"Models/Nets/OpenPoseCOCO", "Models/Nets/OpenPoseMPI", "Models/Nets/SentiNet", "Models/Nets/UNet", "Models/Nets/WaveToLetter",
+	"Modules/Module",
 ]
 
 TENSOR_CORE = [
 	"Modules/Conv1D", "Modules/Conv2D", "Modules/Conv3D", "Modules/Deconv1D", "Modules/Deconv2D", "Modules/Deconv3D", "Modules/RNN",
+	"Passes/ConvertToGraph",
 ]
 
-WRAPPERS = ["CuDnn", "CuDnnNorm", "CuBlas", "CuDnnMemory"]
+WRAPPERS = ["CuDnn", "CuDnnNorm", "CuBlas", "CuDnnMemory", "CuDnnSpatialTf"]
 
 
 def retry(fn, tries=20):      # Unittester.py:13 (threshold=20): unseeded inputs against np.allclose's atol=1e-8
