@@ -128,6 +128,11 @@ int pz_spatialtf_fwd(int dtype, const void* data, const void* theta, void* grid,
 					 void* stream);
 int pz_spatialtf_bwd(int dtype, const void* grad, const void* data, const void* grid, void* dx, void* dtheta, void* dgrid, int64_t B, int64_t C,
 					 int H, int W, int oH, int oW, void* stream);
+/* CTC loss over softmax outputs y [T][B][V] (Cuda/Kernels/CTC.py:232-269): labels = the B label strings concatenated, offsets[B + 1]
+ * their prefix sums, datalen[B] the valid time steps; writes alphas (T * (2 * offsets[B] + B) floats, the reference's layout), nll[B],
+ * adds sum(nll) to *error and writes grad [T][B][V] (zeroed by the caller) = d(sum nll) / d y */
+int pz_ctc_loss(const void* y, const void* datalen, const void* labels, const void* offsets, void* alphas, void* nll, void* error, void* grad, int T,
+				int B, int V, int max_label_len, int blank, void* stream);
 /* diagnosis: the 32 per-role phase clock sums of the tcgen05 engine since the last call (only in builds with -DPZ_TIMELINE,
  * PZ_ERR_UNSUPPORTED otherwise); no reference counterpart */
 int pz_debug_timeline(unsigned long long* out);

@@ -969,6 +969,35 @@ class UpsampleModule:
 		return self._backward(grad, tuple(grad.shape[2:]), self._scale(scale, 3), mode, allocator)
 
 
+class CTCModule:
+	"""reference: Cuda/Kernels/CTC.py:195-269 (connectionist temporal classification loss and its gradient, float32)"""
+	GPUArray = GPUArray
+
+	def __init__(self, backend):
+		self.backend, self.dnn = backend, backend.dnn
+
+	def ctcLoss(self, data, datalen, labels, lengths, blank, error=None, normalized=False, returnAlphas=False, allocator=None):
+		assert data.dtype == _f32 and datalen.dtype == _i32 and labels.dtype == _i32
+		T, batchsize, vocabsize = data.shape
+		lengths = np.asarray(lengths)
+
+		if not normalized:
+			data = self.backend.dnn.softmaxNd(data.reshape(T * batchsize, vocabsize, 1, 1), allocator=allocator).reshape(T, batchsize, vocabsize)
+
+		extOffsets = np.zeros((batchsize + 1, ), dtype=np.int32)
+		extOffsets[1:] = np.cumsum(lengths, dtype=np.int32)
+
+		alphas = GPUArray((T * (2 * int(extOffsets[-1]) + batchsize), ), _f32, allocator=allocator)
+		offsets = GPUArray.toGpu(extOffsets, allocator=allocator)
+		nll = GPUArray((batchsize, ), _f32, allocator=allocator)
+		error = GPUArray.zeros((), _f32, allocator=allocator) if error is None else error
+		grad = GPUArray.zeros(data.shape, _f32, allocator=allocator)
+
+		check(lib.pz_ctc_loss(data.ptr, datalen.ptr, labels.ptr, offsets.ptr, alphas.ptr, nll.ptr, error.ptr, grad.ptr, T, batchsize, vocabsize,
+							  int(lengths.max()) if lengths.size else 0, int(blank), None))
+		return (error, grad) if not returnAlphas else (error, grad, alphas)
+
+
 class CostModule:
 	"""reference: Cuda/Kernels/Costs.py:160-247 (the cross-entropy entry and the accuracy reduction of the training closure)"""
 	GPUArray = GPUArray
@@ -1357,7 +1386,7 @@ class B200Backend:
 		uni = 0
 		bi = 1
 
-	notImplemented = ("ctcmod", "memmod")
+	notImplemented = ("memmod", )
 
 	def __init__(self, deviceIdx, initmode=0, logger=None):
 		self.deviceIdx = deviceIdx
@@ -1385,7 +1414,7 @@ class B200Backend:
 		self.initmode = 0
 		self.blas, self.dnn = None, None
 		self.matmod, self.poolmod, self.costmod = None, None, None
-		self.prelumod, self.padmod, self.embedmod, self.upsamplemod = None, None, None, None
+		self.prelumod, self.padmod, self.embedmod, self.upsamplemod, self.ctcmod = None, None, None, None, None
 
 		# attributes the reference's Backend/Kernels/*.py bind at import time (Cuda/GPUBackend.py:74-131) that sit outside the
 		# hot path and are not implemented: binding works, use raises NotImplementedError
@@ -1401,6 +1430,7 @@ class B200Backend:
 		if initmode >= 2 and self.matmod is None:
 			self.matmod, self.poolmod, self.costmod = MatModule(self), PoolModule(self), CostModule(self)
 			self.prelumod, self.padmod, self.embedmod, self.upsamplemod = PReluModule(self), PadModule(self), EmbedModule(self), UpsampleModule(self)
+			self.ctcmod = CTCModule(self)
 		self.initmode = max(self.initmode, initmode)
 
 	# ---- kernel factories (reference attribute names: Cuda/GPUBackend.py:85-131)

@@ -386,6 +386,121 @@ __global__ void __launch_bounds__(kThreads) stf_dtheta_kernel(const T* __restric
 	}
 }
 
+// ------------------------------------------------------------------------------------------ CTC loss (Cuda/Kernels/CTC.py:9-192)
+// One block per sequence; extended label string l' (blanks interleaved, S = 2 L + 1 states) in shared memory.  alphas [T][S] go to
+// global memory in the reference's layout (sequence b at T * (2 * offset_b + b)), betas are double-buffered in shared memory.
+// The gradient with respect to the SOFTMAX OUTPUT y:  grad[t][v] = -y[t][v] + sum_{s: l'_s = v} exp(alpha + beta - log y + nll).
+// States that share a label are chained in ascending order (`nxt`) instead of the reference's block radix sort: the log-sum over a
+// label visits them in the same order.
+constexpr int kCtcThreads = 128;
+#define PZ_NEG_INF (-__int_as_float(0x7f800000))
+
+__device__ __forceinline__ float log_plus(float a, float b)
+{
+	if (a <= PZ_NEG_INF) return b;
+	if (b <= PZ_NEG_INF) return a;
+	return log1pf(expf(-fabsf(a - b))) + fmaxf(a, b);
+}
+
+__global__ void __launch_bounds__(kCtcThreads) ctc_alpha_kernel(const float* __restrict__ y, const int* __restrict__ datalen, int T, int B, int V,
+																 const int* __restrict__ labels, const int* __restrict__ offsets, float* __restrict__ alphas,
+																 int blank, float* __restrict__ nll, float* error)
+{
+	extern __shared__ int ctc_smem[];
+	int* shl = ctc_smem;
+	const int b = blockIdx.x, offset = offsets[b], S = 2 * (offsets[b + 1] - offset) + 1;
+	y += (int64_t)b * V;
+	labels += offset;
+	float* a = alphas + (int64_t)T * (2 * offset + b);
+
+	for (int i = threadIdx.x; i < S; i += kCtcThreads) {
+		const int label = (i % 2 == 0) ? blank : labels[i / 2];
+		shl[i] = label;
+		a[i] = i < 2 ? logf(y[label]) : PZ_NEG_INF;
+	}
+	__syncthreads();
+	const int Tb = datalen[b];
+	for (int t = 1; t < Tb; t++) {
+		for (int i = threadIdx.x; i < S; i += kCtcThreads) {
+			float prev = a[(int64_t)(t - 1) * S + i];
+			if (i > 0) {
+				prev = log_plus(prev, a[(int64_t)(t - 1) * S + i - 1]);
+				if (i > 1 && shl[i] != blank && shl[i] != shl[i - 2]) prev = log_plus(prev, a[(int64_t)(t - 1) * S + i - 2]);
+			}
+			a[(int64_t)t * S + i] = prev + logf(y[(int64_t)t * B * V + shl[i]]);
+		}
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) {
+		const float tail = S >= 2 ? a[(int64_t)(Tb - 1) * S + S - 2] : PZ_NEG_INF;
+		const float loglike = log_plus(tail, a[(int64_t)(Tb - 1) * S + S - 1]);
+		nll[b] = -loglike;
+		atomicAdd(error, -loglike);
+	}
+}
+
+__global__ void __launch_bounds__(kCtcThreads) ctc_beta_kernel(const float* __restrict__ y, const int* __restrict__ datalen, int T, int B, int V,
+																const int* __restrict__ labels, const int* __restrict__ offsets, const float* __restrict__ alphas,
+																int blank, const float* __restrict__ nll, float* __restrict__ grad, int Smax)
+{
+	extern __shared__ int ctc_smem[];
+	int* shl = ctc_smem;                       // [Smax] extended labels
+	int* nxt = ctc_smem + Smax;                // [Smax] 1 + next state with the same label (0: none) | first occurrence << 30
+	float* betas = reinterpret_cast<float*>(ctc_smem + 2 * Smax);      // [2][Smax]
+	const int b = blockIdx.x, offset = offsets[b], S = 2 * (offsets[b + 1] - offset) + 1;
+	y += (int64_t)b * V;
+	grad += (int64_t)b * V;
+	labels += offset;
+	const float* a = alphas + (int64_t)T * (2 * offset + b);
+	const float loglike = nll[b];
+	if (loglike >= -PZ_NEG_INF) return;       // no valid alignment: the gradient stays zero
+
+	for (int i = threadIdx.x; i < S; i += kCtcThreads) shl[i] = (i % 2 == 0) ? blank : labels[i / 2];
+	__syncthreads();
+	for (int i = threadIdx.x; i < S; i += kCtcThreads) {
+		const int label = shl[i];
+		int next = -1, first = 1;
+		for (int j = i + 1; j < S; j++)
+			if (shl[j] == label) { next = j; break; }
+		for (int j = i - 1; j >= 0; j--)
+			if (shl[j] == label) { first = 0; break; }
+		nxt[i] = (next + 1) | (first << 30);                       // 0 in the low bits: no further state with this label
+	}
+	__syncthreads();
+
+	const int Tb = datalen[b];
+	int src = 0, dst = 1;
+	for (int t = Tb - 1; t >= 0; t--) {
+		if (t < Tb - 1) {
+			for (int i = threadIdx.x; i < S; i += kCtcThreads) {
+				float next = betas[src * Smax + i];
+				if (i < S - 1) {
+					next = log_plus(next, betas[src * Smax + i + 1]);
+					if (i < S - 2 && shl[i] != blank && shl[i] != shl[i + 2]) next = log_plus(next, betas[src * Smax + i + 2]);
+				}
+				betas[dst * Smax + i] = next + logf(y[(int64_t)t * B * V + shl[i]]);
+			}
+			src ^= 1;
+			dst ^= 1;
+		} else {
+			for (int i = threadIdx.x; i < S; i += kCtcThreads)
+				betas[i] = i >= S - 2 ? logf(y[(int64_t)(Tb - 1) * B * V + shl[i]]) : PZ_NEG_INF;
+		}
+		__syncthreads();
+		for (int v = threadIdx.x; v < V; v += kCtcThreads) grad[(int64_t)t * B * V + v] = -y[(int64_t)t * B * V + v];
+		__syncthreads();
+		for (int i = threadIdx.x; i < S; i += kCtcThreads) {
+			if (!(nxt[i] >> 30 & 1)) continue;                          // the first state of a label sums the whole chain
+			float gr = PZ_NEG_INF;
+			for (int j = i; j >= 0; j = (nxt[j] & ~(1 << 30)) - 1) gr = log_plus(gr, a[(int64_t)t * S + j] + betas[src * Smax + j]);
+			const int64_t off = (int64_t)t * B * V + shl[i];
+			const float data = y[off];
+			if (data > 0.0f) grad[off] += expf(gr - logf(data) + loglike);
+		}
+		__syncthreads();
+	}
+}
+
 // ------------------------------------------------------------------------------------------ divisive normalisation (LCN)
 // mapLRN with a means tensor = cudnnDivisiveNormalization (CuDnnNorm.c:329-510; host formulas of Modules/LCN.py:62-143):
 //   norm_i = K + alpha / N^2 * sum_{j in win(i)} (x_j - m_i)^2,   y_i = x_i * norm_i^-beta,   win(i) = [i - lb, i + la) clipped
@@ -665,6 +780,27 @@ int pz_spatialtf_bwd(int dtype, const void* grad, const void* data, const void* 
 		stf_dtheta_kernel<__half><<<(unsigned)B, kThreads, 0, pz_stream(stream)>>>((const __half*)dgrid, (__half*)dtheta, oH, oW);
 	}
 	pz_count_launch(1);
+	PZ_LAUNCH_CHECK();
+	return PZ_OK;
+}
+
+int pz_ctc_loss(const void* y, const void* datalen, const void* labels, const void* offsets, void* alphas, void* nll, void* error, void* grad, int T,
+				int B, int V, int max_label_len, int blank, void* stream)
+{
+	PZ_REQUIRE(T > 0 && B > 0 && V > 0 && max_label_len >= 0 && blank >= 0 && blank < V, "ctcLoss: invalid arguments");
+	const int Smax = 2 * max_label_len + 1;
+	const size_t smem_a = (size_t)Smax * sizeof(int), smem_b = (size_t)Smax * (2 * sizeof(int) + 2 * sizeof(float));
+	PZ_REQUIRE(smem_b <= 200 * 1024, "ctcLoss: label sequences of %d symbols do not fit shared memory", max_label_len);
+	cudaStream_t s = pz_stream(stream);
+	if (smem_b > 48 * 1024) {
+		PZ_CHECK_CUDA(cudaFuncSetAttribute(ctc_alpha_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
+		PZ_CHECK_CUDA(cudaFuncSetAttribute(ctc_beta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+	}
+	ctc_alpha_kernel<<<(unsigned)B, kCtcThreads, smem_a, s>>>((const float*)y, (const int*)datalen, T, B, V, (const int*)labels, (const int*)offsets,
+															  (float*)alphas, blank, (float*)nll, (float*)error);
+	ctc_beta_kernel<<<(unsigned)B, kCtcThreads, smem_b, s>>>((const float*)y, (const int*)datalen, T, B, V, (const int*)labels, (const int*)offsets,
+															 (const float*)alphas, blank, (const float*)nll, (float*)grad, Smax);
+	pz_count_launch(2);
 	PZ_LAUNCH_CHECK();
 	return PZ_OK;
 }

@@ -103,6 +103,7 @@ _SIGNATURES = {
 	"pz_divnorm_bwd": [c_int, _P, _P, _P, _P, _P, _P, c_int64, c_int64, c_int64, c_int, c_float, c_float, c_float, _P],
 	"pz_spatialtf_fwd": [c_int, _P, _P, _P, _P, c_int64, c_int64, c_int, c_int, c_int, c_int, _P],
 	"pz_spatialtf_bwd": [c_int, _P, _P, _P, _P, _P, _P, c_int64, c_int64, c_int, c_int, c_int, c_int, _P],
+	"pz_ctc_loss": [_P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P],
 	"pz_prelu_fwd": [_P, _P, _P, c_int64, c_int64, c_int64, c_int, _P],
 	"pz_prelu_bwd_data": [_P, _P, _P, _P, c_int64, c_int64, c_int64, c_int, _P],
 	"pz_prelu_bwd_params": [_P, _P, _P, c_int64, c_int64, c_int64, c_int, _P],

@@ -32,7 +32,7 @@ MODULES = [
 	"Modules/Transpose", "Modules/PRelu", "Modules/Pad1D", "Modules/Pad2D", "Modules/Upsample2D", "Modules/Upsample3D", "Modules/LCN", "Modules/SpatialTf",
 	"Containers/Sequential", "Containers/Parallel", "Containers/Graph",
 	"Cost/Abs", "Cost/BCE", "Cost/CrossEntropy", "Cost/Hinge", "Cost/KLDivergence", "Cost/L1Hinge", "Cost/MSE", "Cost/Multi",
-	"Cost/SVM", "Cost/SmoothL1",
+	"Cost/SVM", "Cost/SmoothL1", "Cost/CTC",
 	"Optimizers/AdaDelta", "Optimizers/AdaGrad", "Optimizers/Adam", "Optimizers/MomentumSGD", "Optimizers/NesterovSGD",
 	"Optimizers/RMSProp", "Optimizers/RMSPropGraves", "Optimizers/SGD", "Optimizers/SMORMS3",
 	"Models/Nets/LeNet", "Models/Nets/ResNet", "Models/Nets/VGG", "Models/Nets/NiN", "Models/Nets/Inception", "Models/Nets/MiniYolo",
@@ -132,9 +132,10 @@ def test_reference_gpuarray_utils_and_kernel_module_tests(refroot, bnd):
 
 def test_reference_kernel_module_tests_of_the_side_modules(refroot, bnd):
 	"""Cuda/Kernels/{PRelu,Pad,Embedder,Upsample}.py: the reference's own tests of its NVRTC kernel modules, handed this backend's
-	prelumod / padmod / embedmod / upsamplemod instead"""
-	from PuzzleLib.Cuda.Kernels import PRelu, Pad, Embedder, Upsample
+	prelumod / padmod / embedmod / upsamplemod / ctcmod instead"""
+	from PuzzleLib.Cuda.Kernels import PRelu, Pad, Embedder, Upsample, CTC
 
+	retry(lambda: CTC.ctcLossTest(bnd.ctcmod))
 	retry(lambda: PRelu.preluTest(bnd.prelumod))
 	for dtype, atol in bnd.dtypesSupported():
 		retry(lambda: Pad.reflectpad1dTest(bnd.padmod, dtype))
