@@ -1386,7 +1386,7 @@ class B200Backend:
 		uni = 0
 		bi = 1
 
-	notImplemented = ("memmod", )
+	notImplemented = ()
 
 	def __init__(self, deviceIdx, initmode=0, logger=None):
 		self.deviceIdx = deviceIdx
@@ -1427,6 +1427,7 @@ class B200Backend:
 	def updateBackend(self, initmode):
 		if initmode >= 1 and self.dnn is None:
 			self.blas, self.dnn = BlasContext(self), DnnContext(self)
+			self.memmod = self.dnn          # depthConcat / depthSplit / moveaxis / swapaxes / transpose (Cuda/Kernels/Memory.py's surface)
 		if initmode >= 2 and self.matmod is None:
 			self.matmod, self.poolmod, self.costmod = MatModule(self), PoolModule(self), CostModule(self)
 			self.prelumod, self.padmod, self.embedmod, self.upsamplemod = PReluModule(self), PadModule(self), EmbedModule(self), UpsampleModule(self)

@@ -38,6 +38,7 @@ class RnnReserve:
 	def __init__(self):
 		self.cells = []           # per layer direction: dict of saved tensors
 		self.outs = []            # per layer: the (T, B, ndir*H) output
+		self.rands = []           # per layer boundary: the random words of the inter-layer dropout (None without dropout)
 		self.grads = None         # filled by backwardData, consumed by backwardParams
 
 
@@ -50,13 +51,14 @@ class Rnn:
 			raise ValueError("invalid rnn mode %s" % mode)
 		if direction not in (DIR_UNI, DIR_BI):
 			raise ValueError("invalid rnn direction %s" % direction)
-		if dropout != 0.0 and layers > 1:
-			raise NotImplementedError("dropout between recurrent layers is not implemented in the B200 backend yet")
+		if not 0.0 <= dropout < 1.0:
+			raise ValueError("invalid rnn dropout probability %s" % dropout)
 
 		self.backend = backend
 		self.insize, self.hsize, self.layers = int(insize), int(hsize), int(layers)
 		self.dtype, self.algo, self.mode, self.direction = _f32, algo, mode, direction
 		self.dropout, self.seed, self.batchsize = dropout, seed, batchsize
+		self.rng = None
 		self.ngates = len(_GATES[mode])
 		self.ndir = 2 if direction == DIR_BI else 1
 
@@ -221,6 +223,36 @@ class Rnn:
 		else:
 			dbr.set(dbw)
 
+	# ------------------------------------------------------------------------------------------ inter-layer dropout
+	# cudnnSetRNNDescriptor's dropout (CuDnnRnn.c: the dropout descriptor built from `dropout` and `seed`): applied in training to
+	# the output of every layer but the last, same kernel and keep rule as Modules/Dropout.py (keep when the random word is below
+	# (1 - p) * UINT_MAX, scale by 1 / (1 - p)); the masks come from this descriptor's own generator, seeded with `seed`.  cuDNN's
+	# random stream is not reproducible outside cuDNN -- the statistics are, and the backward pass reuses the stored words.
+	def _dropout(self, x, reserve, test, allocator):
+		if self.dropout == 0.0 or test:
+			reserve.rands.append(None)
+			return x
+		if self.rng is None:
+			from .backend import RandomNumberGenerator
+			self.rng = RandomNumberGenerator(seed=int(self.seed))
+		rands = GPUArray(x.shape, np.dtype(np.uint32), allocator=allocator)
+		self.rng.fillInteger(rands)
+		reserve.rands.append(rands)
+		out = GPUArray(x.shape, _f32, allocator=allocator)
+		self.backend.dropoutKer(_f32)(out, x, rands, self._partition(), 1.0 - self.dropout)      # the kernel takes the KEEP probability
+		return out
+
+	def _partition(self):
+		return int((1.0 - self.dropout) * np.iinfo(np.uint32).max)
+
+	def _dropoutBackward(self, dy, layer, reserve, allocator):
+		rands = reserve.rands[layer] if layer < len(reserve.rands) else None
+		if rands is None:
+			return dy
+		out = GPUArray(dy.shape, _f32, allocator=allocator)
+		self.backend.dropoutKer(_f32)(out, dy, rands, self._partition(), 1.0 - self.dropout)
+		return out
+
 	# ------------------------------------------------------------------------------------------ public surface
 	def forward(self, data, W, hidden=None, cells=None, test=False, allocator=None):
 		if data.ndim != 3 or data.shape[2] != self.insize or data.dtype != _f32:
@@ -241,6 +273,8 @@ class Rnn:
 				reserve.cells.append(saved)
 			x = outs[0] if self.ndir == 1 else self.backend.concatenate(outs, 2, None, allocator=allocator)
 			reserve.outs.append(x)
+			if layer < self.layers - 1:
+				x = self._dropout(x, reserve, test, allocator)
 		return x if test else (x, reserve)
 
 	def backwardData(self, grad, outdata, W, reserve, hidden=None, cells=None, allocator=None):
@@ -252,6 +286,8 @@ class Rnn:
 
 		dy = grad
 		for layer in range(self.layers - 1, -1, -1):
+			if layer < self.layers - 1:
+				dy = self._dropoutBackward(dy, layer, reserve, allocator)          # the mask layer `layer`'s output went through
 			parts = [dy] if self.ndir == 1 else self.backend.split(dy, (H, H), 2, allocator=allocator)
 			dx = None
 			for d in range(self.ndir):

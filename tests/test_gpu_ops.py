@@ -1248,3 +1248,49 @@ def test_deferred_fill_fuses_with_accumulation_and_keeps_the_bits(bnd, dtname):
 	assert driver.deferred is None
 	y.fill(1)
 	assert driver.deferred is None and np.array_equal(y.get(), np.ones(n, dt))
+
+
+def test_lstm_dropout_between_layers(bnd):
+	"""cudnnSetRNNDescriptor's dropout: in training the output of every layer but the last passes through a dropout mask (keep rule
+	and scaling of Modules/Dropout.py:33-77); inference ignores it.  Checked against the oracle with the masks the forward pass stored."""
+	T, B, insz, H, p = 6, 8, 24, 32, 0.4
+	rng = np.random.RandomState(77)
+	rnn, W, params = bnd.createRnn(insz, H, np.float32, layers=2, mode=bnd.RNNMode.lstm, dropout=p, seed=1234)
+	W.set((rng.randn(*W.shape) * 0.2).astype(np.float32))
+	host = [_rnn_host_params(q) for q in params]
+	x = rng.randn(T, B, insz).astype(np.float32)
+	dy = rng.randn(T, B, H).astype(np.float32)
+
+	# inference: no dropout
+	plain = rnn.forward(G(bnd, x), W, test=True, allocator=bnd.memoryPool)
+	l1, _ = ops.lstm_forward(x.astype(np.float64), host[0])
+	l2, _ = ops.lstm_forward(l1, host[1])
+	tol = REL_TC * (1 + T / 4.0)
+	assert relerr(plain.get(), l2) < tol
+
+	out, reserve = rnn.forward(G(bnd, x), W, allocator=bnd.memoryPool)
+	assert len(reserve.rands) == 1 and reserve.rands[0].shape == (T, B, H)
+	keep = reserve.rands[0].get().astype(np.uint64) < int((1.0 - p) * np.iinfo(np.uint32).max)
+	assert 0.45 < keep.mean() < 0.75                                   # about 1 - p of the activations survive
+	scale = keep / (1.0 - p)
+
+	o1, c1 = ops.lstm_forward(x.astype(np.float64), host[0])
+	o2, c2 = ops.lstm_forward(o1 * scale, host[1])
+	assert relerr(out.get(), o2) < tol
+	assert relerr(out.get(), l2) > 10 * tol                            # and it is not the inference result
+
+	ingrad, _, _ = rnn.backwardData(G(bnd, dy), out, W, reserve, allocator=bnd.memoryPool)
+	dw = rnn.backwardParams(G(bnd, x), out, reserve, allocator=bnd.memoryPool)
+	dwparams = bnd.acquireRnnParams(rnn, dw)
+	g2, dp2 = ops.lstm_backward(o1 * scale, host[1], c2, dy.astype(np.float64))
+	g1, dp1 = ops.lstm_backward(x.astype(np.float64), host[0], c1, g2 * scale)
+	assert relerr(ingrad.get(), g1) < 2 * tol
+	for layer, dp in ((0, dp1), (1, dp2)):
+		for name, want in dp.items():
+			assert relerr(dwparams[layer][name].get(), want) < 2 * tol, (layer, name)
+
+	# a second descriptor with the same seed draws the same masks
+	rnn2, W2, _ = bnd.createRnn(insz, H, np.float32, layers=2, mode=bnd.RNNMode.lstm, dropout=p, seed=1234)
+	W2.set(W.get())
+	out2, reserve2 = rnn2.forward(G(bnd, x), W2, allocator=bnd.memoryPool)
+	assert np.array_equal(reserve2.rands[0].get(), reserve.rands[0].get()) and np.array_equal(out2.get(), out.get())
