@@ -17,9 +17,12 @@
 // Statistics are accumulated around a per-channel pivot (the channel's first element) so that E[d^2] - E[d]^2 does
 // not cancel when |mean| >> std.
 #include "pz_common.h"
+#pragma nv_diag_suppress 128      // "loop is not reachable": the compile-time BULK branches of the cluster kernels return early
 
 #include <cstdlib>
 #include <initializer_list>
+#include <map>
+#include <utility>
 #include <mutex>
 
 namespace {
@@ -424,6 +427,7 @@ struct ClusterGeo {
 	int SP;                      // vector slots per plane (upper bound)
 	FastDiv32 spdiv;
 	int stash_slots;             // rows_per_cta * SP
+	int bulk_store;              // BULK kernels: results leave by cp.async.bulk too (PZ_BN_BULK_STORE=1; measured no faster, off by default)
 };
 
 constexpr int kSlotUnroll = 8;      // 16-byte loads in flight per thread (the backward kernel reads two tensors: 2 x 4)
@@ -514,6 +518,42 @@ __device__ __forceinline__ void bulk_load_planes(const ClusterGeo& g, uint32_t p
 	if (lane == 0) mbar_arrive1(bar);
 }
 
+// the lanes of a plane's stash region that lie OUTSIDE the plane (before its first element in the head vector, after its last one
+// up to the end of the SP-vector region) are overwritten with `fill`, chosen so that they add nothing to the statistics: the hot
+// loops then run over the stash as a flat array -- no slot decode, no masks (they were issue-bound on both: ~90 instructions per
+// 16-byte vector, profiles/r02_bn_fwd_ncu_keys.txt)
+template <typename T, int VEC>
+__device__ __forceinline__ void stash_fill_outside(uint4* stash, const ClusterGeo& g, uint32_t plane0, uint32_t nrows, T fill, int nthreads)
+{
+	T* lanes = reinterpret_cast<T*>(stash);
+	const uint32_t S = (uint32_t)g.S, width = (uint32_t)g.SP * VEC;
+	for (uint32_t row = threadIdx.x; row < nrows; row += nthreads) {
+		const uint32_t head = (plane0 + row * g.plane_step) & (uint32_t)(VEC - 1);
+		T* rp = lanes + row * width;
+		for (uint32_t e = 0; e < head; e++) rp[e] = fill;
+		for (uint32_t e = head + S; e < width; e++) rp[e] = fill;
+	}
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes)
+{
+	asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+// warp 0: the FULL vectors of every plane leave as one bulk copy per plane (shared -> global); the at most two partial vectors
+// per plane are written lane by lane by `store_partial_vectors`.  The warp waits until the copies have read shared memory.
+template <typename T, int VEC>
+__device__ __forceinline__ void bulk_store_planes(const ClusterGeo& g, uint32_t plane0, uint32_t nrows, T* dst, const uint4* stash)
+{
+	const uint32_t lane = threadIdx.x & 31u, S = (uint32_t)g.S;
+	for (uint32_t row = lane; row < nrows; row += 32u) {
+		const uint32_t lo = plane0 + row * g.plane_step, head = lo & (uint32_t)(VEC - 1);
+		const uint32_t vlo = head ? 1u : 0u, vhi = (head + S) / VEC;
+		if (vhi > vlo) bulk_s2g(dst + (lo - head + vlo * VEC), smem_addr(stash + row * (uint32_t)g.SP + vlo), (vhi - vlo) * 16u);
+	}
+	asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_store_wait() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
 // deterministic block sum of two values; result valid in every thread
 template <int THREADS>
 __device__ __forceinline__ void block_sum2(float& a, float& b, float* red /* [2 * THREADS / 32 + 2] */)
@@ -579,6 +619,19 @@ __device__ __forceinline__ uint32_t partial_vector(const ClusterGeo& g, uint32_t
 	return mask;
 }
 
+template <typename T, int VEC>
+__device__ __forceinline__ void store_partial_vectors(const ClusterGeo& g, uint32_t plane0, uint32_t nrows, T* dst, const uint4* stash, int nthreads)
+{
+	using P = Pack<T, VEC>;
+	for (uint32_t i = threadIdx.x; i < 2u * nrows; i += nthreads) {
+		uint32_t vv, e0;
+		const uint32_t mask = partial_vector<VEC>(g, plane0, i >> 1, (int)(i & 1u), vv, e0);
+		if (!mask) continue;
+		const uint4 raw = stash[(i >> 1) * (uint32_t)g.SP + vv];
+		store_partial<T, VEC>(dst + e0, *reinterpret_cast<const P*>(&raw), mask);
+	}
+}
+
 // the cluster-wide sum of the CTAs' (s1, s2) through distributed shared memory, in rank order
 __device__ __forceinline__ void cluster_sum2(float& s1, float& s2, float* part, int CL)
 {
@@ -622,23 +675,13 @@ __global__ void __launch_bounds__(THREADS) bn_fwd_cluster_kernel(const T* __rest
 			bulk_load_planes<T, VEC>(g, plane0, nrows, src, dst, 1, barp);
 		}
 		mbar_wait0(barp);
+		stash_fill_outside<T, VEC>(stash, g, plane0, nrows, from_f<T>(pivot), THREADS);      // x - pivot = 0 there
+		__syncthreads();
 		for (uint32_t slot = threadIdx.x; slot < (uint32_t)nslots; slot += THREADS) {
-			const SlotGeo<VEC> q = slot_decode<VEC>(g, plane0, slot);
-			if (!q.full(S)) continue;
 			const uint4 raw = stash[slot];
 			const P v = *reinterpret_cast<const P*>(&raw);
 			#pragma unroll
 			for (int e = 0; e < VEC; e++) { const float d = to_f<T>(v.v[e]) - pivot; s1 += d; s2 = fmaf(d, d, s2); }
-		}
-		for (uint32_t i = threadIdx.x; i < 2u * nrows; i += THREADS) {
-			uint32_t vv, e0;
-			const uint32_t mask = partial_vector<VEC>(g, plane0, i >> 1, (int)(i & 1u), vv, e0);
-			if (!mask) continue;
-			const uint4 raw = stash[(i >> 1) * (uint32_t)g.SP + vv];
-			const P pv = *reinterpret_cast<const P*>(&raw);
-			#pragma unroll
-			for (int e = 0; e < VEC; e++)
-				if (mask >> e & 1u) { const float d = to_f<T>(pv.v[e]) - pivot; s1 += d; s2 = fmaf(d, d, s2); }
 		}
 	} else {
 	for (uint32_t base = threadIdx.x; base < (uint32_t)nslots; base += THREADS * kSlotUnroll) {
@@ -691,6 +734,22 @@ __global__ void __launch_bounds__(THREADS) bn_fwd_cluster_kernel(const T* __rest
 
 	// ---- phase 2: shared memory -> y = a * x + b -> HBM
 	__syncthreads();                              // partial vectors were stashed by other threads than the ones that read them
+	if (BULK && g.bulk_store) {
+		// normalise in place, then the planes leave through the copy engine
+		for (uint32_t slot = threadIdx.x; slot < (uint32_t)nslots; slot += THREADS) {
+			const uint4 raw = stash[slot];
+			P v = *reinterpret_cast<const P*>(&raw);
+			#pragma unroll
+			for (int e = 0; e < VEC; e++) v.v[e] = from_f<T>(fmaf(to_f<T>(v.v[e]), a, b));
+			stash[slot] = *reinterpret_cast<const uint4*>(&v);
+		}
+		fence_proxy_async();
+		__syncthreads();
+		if (threadIdx.x < 32) bulk_store_planes<T, VEC>(g, plane0, nrows, y, stash);
+		store_partial_vectors<T, VEC>(g, plane0, nrows, y, stash, THREADS);
+		if (threadIdx.x < 32) bulk_store_wait();
+		return;
+	}
 	for (uint32_t slot = threadIdx.x; slot < (uint32_t)nslots; slot += THREADS) {
 		const SlotGeo<VEC> q = slot_decode<VEC>(g, plane0, slot);
 		if (!q.full(S)) continue;
@@ -710,6 +769,108 @@ __global__ void __launch_bounds__(THREADS) bn_fwd_cluster_kernel(const T* __rest
 		for (int e = 0; e < VEC; e++) v.v[e] = from_f<T>(fmaf(to_f<T>(v.v[e]), a, b));
 		store_partial<T, VEC>(y + e0, v, mask);
 	}
+}
+
+// ---- persistent, double-buffered forward pass.  One cluster of CL CTAs (one CTA per SM, two stash buffers) walks over the channels
+// c = cluster, cluster + nclusters, ...: while the statistics / cluster reduction / normalisation / store of channel i run, the planes
+// of channel i + 1 are already in flight into the other buffer (cp.async.bulk both ways), so an SM always has a channel's worth
+// of loads outstanding and the load -> reduce -> barrier -> store life cycle of the one-shot kernel no longer idles the memory system.
+__device__ __forceinline__ void mbar_wait_parity(uint32_t bar, uint32_t parity)
+{
+	asm volatile(
+		"{\n\t.reg .pred p;\n\t"
+		"WAITP_%=:\n\t"
+		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+		"@!p bra WAITP_%=;\n\t}"
+		::"r"(bar), "r"(parity) : "memory");
+}
+
+template <typename T, int VEC, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) bn_fwd_persistent_kernel(const T* __restrict__ x, T* __restrict__ y, ClusterGeo g, int nclusters,
+																		const float* __restrict__ scale, const float* __restrict__ bias,
+																		float* mean_io, float* var_io, float* save_mean, float* save_invvar,
+																		float eps, float factor)
+{
+	extern __shared__ uint4 stash2[];                // [2][stash_slots]
+	__shared__ float red[2 * THREADS / 32 + 2];
+	__shared__ float part[2];
+	__shared__ uint64_t bars[2];
+	using P = Pack<T, VEC>;
+	const unsigned rank = g.CL > 1 ? cluster_ctarank() : 0u;
+	const int cluster = (int)(blockIdx.x / (unsigned)g.CL);
+	const int n0 = (int)rank * g.rows_per_cta, n1 = min(g.N, n0 + g.rows_per_cta);
+	const uint32_t nrows = (uint32_t)max(0, n1 - n0), S = (uint32_t)g.S;
+	const uint32_t nslots = nrows * (uint32_t)g.SP;
+	const float count = (float)g.N * (float)g.S;
+
+	if (threadIdx.x == 0) { mbar_init1(smem_addr(&bars[0])); mbar_init1(smem_addr(&bars[1])); }
+	__syncthreads();
+
+	auto plane0_of = [&](int c) { return ((uint32_t)n0 * (uint32_t)g.C + (uint32_t)c) * S; };
+	auto issue = [&](int c, int buf) {           // warp 0
+		const T* const src[2] = {x, x};
+		uint4* const dst[2] = {stash2 + (size_t)buf * g.stash_slots, stash2};
+		bulk_load_planes<T, VEC>(g, plane0_of(c), nrows, src, dst, 1, smem_addr(&bars[buf]));
+	};
+
+	int c = cluster;
+	if (c < g.C && threadIdx.x < 32) issue(c, 0);
+	float pivot = c < g.C ? to_f<T>(x[(size_t)c * g.S]) : 0.0f;
+	for (int it = 0; c < g.C; it++, c += nclusters) {
+		const int buf = it & 1, cnext = c + nclusters;
+		uint4* stash = stash2 + (size_t)buf * g.stash_slots;
+		const uint32_t plane0 = plane0_of(c);
+		float pivot_next = 0.0f;
+		if (cnext < g.C) {
+			// the other buffer is free once the bulk stores of the previous channel have read it (warp 0 issued them)
+			if (threadIdx.x < 32) {
+				bulk_store_wait();
+				issue(cnext, buf ^ 1);
+			}
+			pivot_next = to_f<T>(x[(size_t)cnext * g.S]);
+		}
+		mbar_wait_parity(smem_addr(&bars[buf]), (uint32_t)(it >> 1) & 1u);
+
+		stash_fill_outside<T, VEC>(stash, g, plane0, nrows, from_f<T>(pivot), THREADS);
+		__syncthreads();
+		float s1 = 0.0f, s2 = 0.0f;
+		for (uint32_t slot = threadIdx.x; slot < nslots; slot += THREADS) {
+			const uint4 raw = stash[slot];
+			const P v = *reinterpret_cast<const P*>(&raw);
+			#pragma unroll
+			for (int e = 0; e < VEC; e++) { const float d = to_f<T>(v.v[e]) - pivot; s1 += d; s2 = fmaf(d, d, s2); }
+		}
+		block_sum2<THREADS>(s1, s2, red);
+		cluster_sum2(s1, s2, part, g.CL);
+
+		const float dmean = s1 / count;
+		const float mean = pivot + dmean;
+		const float var = fmaxf(s2 / count - dmean * dmean, 0.0f);
+		const float invstd = 1.0f / sqrtf(var + eps);
+		if (rank == 0 && threadIdx.x == 0) {
+			save_mean[c] = mean;
+			save_invvar[c] = invstd;
+			const float uvar = count > 1.0f ? var * (count / (count - 1.0f)) : var;
+			mean_io[c] = (1.0f - factor) * mean_io[c] + factor * mean;
+			var_io[c] = (1.0f - factor) * var_io[c] + factor * uvar;
+		}
+		const float a = scale[c] * invstd, b = bias[c] - mean * a;
+
+		for (uint32_t slot = threadIdx.x; slot < nslots; slot += THREADS) {
+			const uint4 raw = stash[slot];
+			P v = *reinterpret_cast<const P*>(&raw);
+			#pragma unroll
+			for (int e = 0; e < VEC; e++) v.v[e] = from_f<T>(fmaf(to_f<T>(v.v[e]), a, b));
+			stash[slot] = *reinterpret_cast<const uint4*>(&v);
+		}
+		fence_proxy_async();
+		__syncthreads();
+		if (threadIdx.x < 32) bulk_store_planes<T, VEC>(g, plane0, nrows, y, stash);
+		store_partial_vectors<T, VEC>(g, plane0, nrows, y, stash, THREADS);
+		__syncthreads();                    // `red` / the partial-vector reads of this channel are done before the next one starts
+		pivot = pivot_next;
+	}
+	if (threadIdx.x < 32) bulk_store_wait();
 }
 
 template <typename T, int VEC, int THREADS, bool BULK>
@@ -745,9 +906,10 @@ __global__ void __launch_bounds__(THREADS) bn_bwd_cluster_kernel(const T* __rest
 			bulk_load_planes<T, VEC>(g, plane0, nrows, src, dst, 2, barp);
 		}
 		mbar_wait0(barp);
+		stash_fill_outside<T, VEC>(stash_dy, g, plane0, nrows, from_f<T>(0.0f), THREADS);    // no gradient outside the plane ...
+		stash_fill_outside<T, VEC>(stash, g, plane0, nrows, from_f<T>(mean), THREADS);       // ... times a finite (x - mean)
+		__syncthreads();
 		for (uint32_t slot = threadIdx.x; slot < (uint32_t)nslots; slot += THREADS) {
-			const SlotGeo<VEC> q = slot_decode<VEC>(g, plane0, slot);
-			if (!q.full(S)) continue;
 			const uint4 rx = stash[slot], rg = stash_dy[slot];
 			const P v = *reinterpret_cast<const P*>(&rx), w = *reinterpret_cast<const P*>(&rg);
 			#pragma unroll
@@ -756,20 +918,6 @@ __global__ void __launch_bounds__(THREADS) bn_bwd_cluster_kernel(const T* __rest
 				s1 += gv;
 				s2 = fmaf(gv, to_f<T>(v.v[e]) - mean, s2);
 			}
-		}
-		for (uint32_t i = threadIdx.x; i < 2u * nrows; i += THREADS) {
-			uint32_t vv, e0;
-			const uint32_t mask = partial_vector<VEC>(g, plane0, i >> 1, (int)(i & 1u), vv, e0);
-			if (!mask) continue;
-			const uint4 rx = stash[(i >> 1) * (uint32_t)g.SP + vv], rg = stash_dy[(i >> 1) * (uint32_t)g.SP + vv];
-			const P pv = *reinterpret_cast<const P*>(&rx), pw = *reinterpret_cast<const P*>(&rg);
-			#pragma unroll
-			for (int e = 0; e < VEC; e++)
-				if (mask >> e & 1u) {
-					const float gv = to_f<T>(pw.v[e]);
-					s1 += gv;
-					s2 = fmaf(gv, to_f<T>(pv.v[e]) - mean, s2);
-				}
 		}
 	} else {
 	for (uint32_t base = threadIdx.x; base < (uint32_t)nslots; base += THREADS * UNR) {
@@ -824,6 +972,22 @@ __global__ void __launch_bounds__(THREADS) bn_bwd_cluster_kernel(const T* __rest
 
 	// ---- phase 2: shared memory -> dx = c1*dy - c2 - (x - mean)*c3 -> HBM
 	__syncthreads();
+	if (BULK && g.bulk_store) {
+		for (uint32_t slot = threadIdx.x; slot < (uint32_t)nslots; slot += THREADS) {
+			const uint4 rx = stash[slot], rg = stash_dy[slot];
+			const P v = *reinterpret_cast<const P*>(&rx);
+			P w = *reinterpret_cast<const P*>(&rg);
+			#pragma unroll
+			for (int e = 0; e < VEC; e++) w.v[e] = from_f<T>(c1 * to_f<T>(w.v[e]) - c2 - (to_f<T>(v.v[e]) - mean) * c3);
+			stash_dy[slot] = *reinterpret_cast<const uint4*>(&w);
+		}
+		fence_proxy_async();
+		__syncthreads();
+		if (threadIdx.x < 32) bulk_store_planes<T, VEC>(g, plane0, nrows, dx, stash_dy);
+		store_partial_vectors<T, VEC>(g, plane0, nrows, dx, stash_dy, THREADS);
+		if (threadIdx.x < 32) bulk_store_wait();
+		return;
+	}
 	for (uint32_t slot = threadIdx.x; slot < (uint32_t)nslots; slot += THREADS) {
 		const SlotGeo<VEC> q = slot_decode<VEC>(g, plane0, slot);
 		if (!q.full(S)) continue;
@@ -854,6 +1018,7 @@ struct ClusterPlan {
 	size_t smem;             // the stash
 	bool ok;
 	bool bulk;               // planes arrive by cp.async.bulk (the tensor must end on a 16-byte boundary: the last plane's cover is read whole)
+	int grid_override;       // persistent kernels: number of CTAs (0: one cluster per channel)
 };
 
 int env_int(const char* name, int dflt)
@@ -905,16 +1070,49 @@ ClusterPlan make_cluster_plan(std::initializer_list<const void*> ptrs, int64_t N
 	if (p.smem > kStashMax) { p.ok = false; return p; }
 	p.threads = slots >= 2048 ? 512 : 256;
 	if (force_threads == 256 || force_threads == 512) p.threads = force_threads;
-	static const bool bulk_on = env_int("PZ_BN_BULK", 1) != 0;
+	static const bool bulk_on = env_int("PZ_BN_BULK", 1) != 0, bulk_store_on = env_int("PZ_BN_BULK_STORE", 0) != 0;
 	p.bulk = bulk_on && (N * C * S) % vec == 0;
+	g.bulk_store = bulk_store_on ? 1 : 0;
 	return p;
+}
+
+// how many clusters of this shape the device holds at the same time (the GPCs bound it: a cluster lives inside one GPC), cached per
+// (kernel, cluster size, shared memory)
+template <typename K>
+int resident_clusters(K kernel, const ClusterPlan& p)
+{
+	static std::mutex mu;
+	static std::map<std::pair<int, size_t>, int> cache;
+	std::lock_guard<std::mutex> lock(mu);
+	const auto key = std::make_pair(p.g.CL, p.smem);
+	auto it = cache.find(key);
+	if (it != cache.end()) return it->second;
+	int n = 0;
+	cudaLaunchConfig_t cfg{};
+	cfg.gridDim = dim3((unsigned)(pz_num_sms() / p.g.CL * p.g.CL));
+	cfg.blockDim = dim3((unsigned)p.threads);
+	cfg.dynamicSmemBytes = p.smem;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeClusterDimension;
+	attr[0].val.clusterDim.x = (unsigned)p.g.CL;
+	attr[0].val.clusterDim.y = 1;
+	attr[0].val.clusterDim.z = 1;
+	cfg.attrs = attr;
+	cfg.numAttrs = 1;
+	if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kStashMax + 24 * 1024)) != cudaSuccess ||
+		cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess) {
+		cudaGetLastError();
+		n = 0;
+	}
+	cache[key] = n;
+	return n;
 }
 
 template <typename K, typename... Args>
 int launch_cluster(K kernel, const ClusterPlan& p, cudaStream_t s, Args... args)
 {
 	cudaLaunchConfig_t cfg{};
-	cfg.gridDim = dim3((unsigned)(p.g.C * p.g.CL));
+	cfg.gridDim = dim3((unsigned)(p.grid_override > 0 ? p.grid_override : p.g.C * p.g.CL));
 	cfg.blockDim = dim3((unsigned)p.threads);
 	cfg.dynamicSmemBytes = p.smem;
 	cfg.stream = s;
@@ -927,7 +1125,7 @@ int launch_cluster(K kernel, const ClusterPlan& p, cudaStream_t s, Args... args)
 	cfg.numAttrs = 1;
 	if (p.smem > 48 * 1024) {
 		// (idempotent; a per-kernel flag would need one static per instantiation)
-		PZ_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStashMax));
+		PZ_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kStashMax + 24 * 1024)));
 	}
 	if (p.g.CL > 8) PZ_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
 	PZ_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kernel, args...));
@@ -1047,6 +1245,23 @@ int fwd_train(const void* x, void* y, int64_t N, int64_t C, int64_t S, const flo
 		// only rewrites planes it alone reads, and the pivot element is read by every CTA of the cluster before its barrier
 		const ClusterPlan cp = make_cluster_plan({x, y}, N, C, S, sizeof(T), 1);
 		if (cp.ok) {
+			// persistent variant: two stash buffers per CTA, one CTA per SM, as many clusters as the GPU can hold at once
+			// (measured SLOWER than the one-shot kernel on every ResNet-50 shape -- 64 x 256 x 55 x 55: 0.149 vs 0.129 ms, and much slower on
+			// small maps where a cluster's serial chain per channel dominates: profiles/r02_conv_epilogue_gather_experiments.md section 6;
+			// PZ_BN_PERSISTENT=1 enables it for experiments)
+			static const bool persistent_on = env_int("PZ_BN_PERSISTENT", 0) != 0;
+			if (persistent_on && cp.bulk && 2 * cp.smem <= 220 * 1024) {
+				ClusterPlan pp = cp;
+				pp.smem = 2 * cp.smem;
+				pp.threads = 512;
+				const int resident = resident_clusters(bn_fwd_persistent_kernel<T, V, 512>, pp);
+				const int nclusters = resident < (int)C ? resident : (int)C;
+				if (nclusters >= 1 && C >= 2 * nclusters) {
+					pp.grid_override = nclusters * cp.g.CL;
+					return launch_cluster(bn_fwd_persistent_kernel<T, V, 512>, pp, s, (const T*)x, (T*)y, cp.g, nclusters, scale, bias, rm, rv, sm, siv,
+										  (float)eps, (float)factor);
+				}
+			}
 #define PZ_BN_FWD_CLUSTER(TH, BK) launch_cluster(bn_fwd_cluster_kernel<T, V, TH, BK>, cp, s, (const T*)x, (T*)y, cp.g, scale, bias, rm, rv, sm, siv, (float)eps, (float)factor)
 			if (cp.threads == 512) return cp.bulk ? PZ_BN_FWD_CLUSTER(512, true) : PZ_BN_FWD_CLUSTER(512, false);
 			return cp.bulk ? PZ_BN_FWD_CLUSTER(256, true) : PZ_BN_FWD_CLUSTER(256, false);
