@@ -427,6 +427,7 @@ struct ClusterGeo {
 	int SP;                      // vector slots per plane (upper bound)
 	FastDiv32 spdiv;
 	int stash_slots;             // rows_per_cta * SP
+	int stream_stores;           // st.global.cs for the results (PZ_BN_STREAM_STORES)
 	int bulk_store;              // BULK kernels: results leave by cp.async.bulk too (PZ_BN_BULK_STORE=1; measured no faster, off by default)
 };
 
@@ -451,12 +452,15 @@ __device__ __forceinline__ float ld_dsmem(const float* local, unsigned rank)
 	return v;
 }
 
-// write-once results leave with the evict-first hint
+// results go out with plain stores by default: the next kernel (the activation, the next convolution's gather) reads them, and the
+// 126 MB L2 keeps a good part of a layer's output.  PZ_BN_STREAM_STORES=1 restores the evict-first hint (st.global.cs) of the
+// first version for A/B runs.
 template <typename T, int VEC>
-__device__ __forceinline__ void store_streaming(T* dst, const Pack<T, VEC>& v)
+__device__ __forceinline__ void store_streaming(T* dst, const Pack<T, VEC>& v, int streaming)
 {
 	const uint4 u = *reinterpret_cast<const uint4*>(&v);
-	asm volatile("st.global.cs.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w) : "memory");
+	if (streaming) asm volatile("st.global.cs.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w) : "memory");
+	else *reinterpret_cast<uint4*>(dst) = u;
 }
 
 // the first / last vector of an unaligned plane: only the lanes inside the plane are written.  Out of line on purpose -- inlined
@@ -757,7 +761,7 @@ __global__ void __launch_bounds__(THREADS) bn_fwd_cluster_kernel(const T* __rest
 		P v = *reinterpret_cast<const P*>(&raw);
 		#pragma unroll
 		for (int e = 0; e < VEC; e++) v.v[e] = from_f<T>(fmaf(to_f<T>(v.v[e]), a, b));
-		store_streaming<T, VEC>(y + q.e0(), v);
+		store_streaming<T, VEC>(y + q.e0(), v, g.stream_stores);
 	}
 	for (uint32_t i = threadIdx.x; i < 2u * nrows; i += THREADS) {
 		uint32_t vv, e0;
@@ -996,7 +1000,7 @@ __global__ void __launch_bounds__(THREADS) bn_bwd_cluster_kernel(const T* __rest
 		P w = *reinterpret_cast<const P*>(&rg);
 		#pragma unroll
 		for (int e = 0; e < VEC; e++) w.v[e] = from_f<T>(c1 * to_f<T>(w.v[e]) - c2 - (to_f<T>(v.v[e]) - mean) * c3);
-		store_streaming<T, VEC>(dx + q.e0(), w);
+		store_streaming<T, VEC>(dx + q.e0(), w, g.stream_stores);
 	}
 	for (uint32_t i = threadIdx.x; i < 2u * nrows; i += THREADS) {
 		uint32_t vv, e0;
@@ -1073,6 +1077,8 @@ ClusterPlan make_cluster_plan(std::initializer_list<const void*> ptrs, int64_t N
 	static const bool bulk_on = env_int("PZ_BN_BULK", 1) != 0, bulk_store_on = env_int("PZ_BN_BULK_STORE", 0) != 0;
 	p.bulk = bulk_on && (N * C * S) % vec == 0;
 	g.bulk_store = bulk_store_on ? 1 : 0;
+	static const bool stream_on = env_int("PZ_BN_STREAM_STORES", 0) != 0;
+	g.stream_stores = stream_on ? 1 : 0;
 	return p;
 }
 
