@@ -669,9 +669,16 @@ class BlasContext:
 		return out
 
 	def gemmBias(self, A, B, bias, out=None, transpB=False, allocator=None):
-		"""Linear forward with the bias add folded into the GEMM epilogue (Linear.py:36-40 as one kernel)."""
+		"""Linear forward with the bias add folded into the GEMM epilogue (Linear.py:36-40 as one kernel).  An extension: the reference's
+		Linear calls gemm + addVecToMat; the bias must have exactly one entry per output column."""
+		for ary, name in ((A, "A"), (B, "B"), (bias, "bias")):
+			_requireArray(ary, name)
+		if A.ndim != 2 or B.ndim != 2 or B.dtype != A.dtype or bias.dtype != A.dtype:
+			raise ValueError("gemmBias needs 2-d operands and a bias of one dtype")
 		M, K = A.shape
 		N = B.shape[0] if transpB else B.shape[1]
+		if (B.shape[1] if transpB else B.shape[0]) != K or bias.size != N:
+			raise ValueError("gemmBias: shapes %s x %s with a bias of %d entries do not fit" % (A.shape, B.shape, bias.size))
 		out = GPUArray((M, N), A.dtype, allocator=allocator) if out is None else _checkOut(out, (M, N), A.dtype)
 		check(lib.pz_gemm(dtypeCode(A.dtype), A.ptr, B.ptr, out.ptr, M, N, K, A.shape[1], B.shape[1], N, 0, int(transpB),
 						  1.0, 0.0, bias.ptr, None))

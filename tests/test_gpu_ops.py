@@ -272,6 +272,10 @@ def test_gemm_bias_epilogue_and_errors(bnd):
 		bnd.blas.gemm(G(bnd, A), G(bnd, A))
 	with pytest.raises(ValueError):
 		bnd.blas.gemm(G(bnd, A), G(bnd, B), transpA=True, transpB=True)
+	with pytest.raises(ValueError):            # a bias that does not have one entry per output column (Linear(transpose=True)'s quirk)
+		bnd.blas.gemmBias(G(bnd, A), G(bnd, B), G(bnd, b[:800]))
+	with pytest.raises(ValueError):
+		bnd.blas.gemmBias(G(bnd, A), G(bnd, B), G(bnd, b.astype(np.float16)))
 
 
 # ================================================================================================ batch norm
