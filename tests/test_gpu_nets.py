@@ -37,12 +37,15 @@ def record_backward(modules):
 	return orig
 
 
-def check_leaf(M, mod, failures, tol_tc=1e-3, tol=1e-5):
+def check_leaf(M, mod, failures, tol_tc=1e-3, tol=1e-5, floor=0.0):
+	"""`floor`: the rounding of 16-bit storage (every bar is at least this)"""
 	name = "%s(%s)" % (type(mod).__name__, mod.name)
 	g = getattr(mod, "_gradIn", None)
+	tol_tc, tol = max(tol_tc, floor), max(tol, floor)
 
 	def expect(tag, got, want, bar):
 		err = relerr(got, want)
+		bar = max(bar, floor)
 		if not err < bar:
 			failures.append("%s %s relerr %.3e > %.1e" % (name, tag, err, bar))
 
@@ -63,7 +66,7 @@ def check_leaf(M, mod, failures, tol_tc=1e-3, tol=1e-5):
 											   mod.epsilon, 1.0)
 		expect("fwd", mod.data.get(), y, 2e-5)
 		# the mean is accurate relative to the channel's spread (fp32 accumulation), not relative to max |mean| (which is ~0)
-		if not float(np.abs((mod.savemean.get().ravel() - mu) * inv).max()) < 2e-5:
+		if not float(np.abs((mod.savemean.get().ravel() - mu) * inv).max()) < max(2e-5, floor):
 			failures.append("%s savemean off by more than 2e-5 std" % name)
 		expect("saveinvvar", mod.saveinvvar.get().ravel(), inv, tol)
 		if g is not None:
@@ -120,7 +123,7 @@ def check_leaf(M, mod, failures, tol_tc=1e-3, tol=1e-5):
 		failures.append("%s: no checker" % name)
 
 
-def run_and_check(M, net, x, gy):
+def run_and_check(M, net, x, gy, floor=0.0):
 	orig = record_backward(M)
 	try:
 		net.zeroGradParams()
@@ -133,7 +136,7 @@ def run_and_check(M, net, x, gy):
 	import refshim
 	leaves = list(refshim.leaves(net))
 	for mod in leaves:
-		check_leaf(M, mod, failures)
+		check_leaf(M, mod, failures, floor=floor)
 	return out, leaves, failures
 
 
@@ -317,6 +320,30 @@ def test_resnet50_teacher_forced_parity(M):
 	assert sum(isinstance(m, M.Conv2D) for m in leaves) == 53 and sum(isinstance(m, M.BatchNorm2D) for m in leaves) == 53
 	assert net["pool1"].data.shape == (2, 64, 55, 55)          # pool1 is 3x3 s2 p0 -> 55, not 56
 	assert net.grad.shape == x.shape                           # conv1 dgrad IS computed
+	assert failures == [], "\n".join(failures[:20])
+
+
+@pytest.mark.parametrize("dtname,floor", [("float16", 3e-3), ("bfloat16", 2.5e-2)])
+def test_resnet50_teacher_forced_parity_16bit(M, dtname, floor):
+	"""BASELINE.json configs[3] / the reference's float16 path (Containers/Container.py:216-223 calcMode): every layer of ResNet-50
+	in 16-bit storage against the float64 oracle fed with the SAME 16-bit inputs; the bar is the storage rounding (2^-11, 2^-8)"""
+	from PuzzleLib.Models.Nets.ResNet import loadResNet
+	from puzzlelib_b200 import seam, driver
+	if dtname == "bfloat16" and driver.bfloat16 is None:
+		pytest.skip("ml_dtypes.bfloat16 is not available")
+	dt = np.dtype(np.float16) if dtname == "float16" else driver.bfloat16
+	np.random.seed(4321)
+	net = loadResNet(None, "50", initscheme="he")
+	if dtname == "float16":
+		net.calcMode(np.float16)
+	else:
+		seam.calcMode(net, dt)
+	rng = np.random.RandomState(4321)
+	x = rng.randn(2, 3, 224, 224).astype(dt)
+	gy = (rng.randn(2, 1000) * 8.0).astype(dt)               # large enough that the gradients stay out of float16's subnormal range
+	out, leaves, failures = run_and_check(M, net, x, gy, floor=floor)
+	assert out.dtype == dt and out.shape == (2, 1000)
+	assert sum(isinstance(m, M.Conv2D) for m in leaves) == 53
 	assert failures == [], "\n".join(failures[:20])
 
 
