@@ -172,6 +172,9 @@ int pz_add2(int dtype, void* out, const void* a, const void* b, int64_t n, void*
 /* y = (0 + x1*a1) + x2*a2 (x2 may be NULL: y = 0 + x1*a1): the launch sequence fill(0) + toVectorAddVector (+ toVectorAddVector)
  * of Modules/Add.py:15-23 / Replicate.py:18-29 fused into one pass with identical bits (intermediate rounded to the storage type) */
 int pz_axpy2(int dtype, void* y, const void* x1, float a1, const void* x2, float a2, int64_t n, void* stream);
+/* the same fused sum followed by the ReLU the next module applies: y = (0 + a1*x1) + a2*x2, out = max(y, 0); both stored
+ * (Modules/Add.py:15-23 then Modules/Activation.py:69-71 in one pass over the tensors) */
+int pz_axpy2_relu(int dtype, void* y, void* out, const void* x1, float a1, const void* x2, float a2, int64_t n, void* stream);
 /* float32 math mode of pz_conv2d_* and pz_gemm (reference: enableTensorOps, CuDnn.c:61-74 / CuBlas.c:91-106): 0 = TF32
  * tensor-core products with fp32 accumulation (default; within 1e-3 of fp32), 1 = exact fp32 FMAs on the CUDA cores (what
  * cuDNN / cuBLAS give the reference's float32 tensors on this stack; a verification path, not tuned) */

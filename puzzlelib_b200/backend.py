@@ -1216,6 +1216,8 @@ def _actFactory(kind, nscalars):
 			b = float(scalars[1]) if nscalars > 1 else 0.0
 			slc = _slice(kwargs, out.size)
 			if slc is None:
+				if kind == "relu" and driver.deferred is not None and gpuarray.reluAfterSum(out, inp):
+					return          # fused with the pending Add / Replicate sum it reads
 				check(lib.pz_act_fwd(code, dt, out.ptr, inp.ptr, out.size, a, b, None))
 			else:
 				check(lib.pz_act_fwd_slice(code, dt, out.ptr, inp.ptr, out.size, a, b, *slc, None))

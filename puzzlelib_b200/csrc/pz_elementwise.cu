@@ -244,6 +244,19 @@ struct Axpy2 {
 		io[0] = TWO ? fmaf(in[1], a2, first) : first;
 	}
 };
+// the same sum followed by the ReLU the next module applies to it: io[0] = the sum (stored, as the reference's Add module keeps it),
+// io[1] = max(sum, 0) computed from the ROUNDED sum -- bit for bit what the separate relu kernel would read and write
+template <typename T>
+struct Axpy2Relu {
+	float a1, a2;
+	__device__ __forceinline__ void apply(float* io, const float* in) const
+	{
+		const float first = to_f<T>(from_f<T>(fmaf(in[0], a1, 0.0f)));
+		const float sum = to_f<T>(from_f<T>(fmaf(in[1], a2, first)));
+		io[0] = sum;
+		io[1] = sum * (sum > 0.0f);
+	}
+};
 struct Axpy {   // y = y + x * alpha   (ElementWise.py:591)
 	float alpha;
 	__device__ __forceinline__ void apply(float* io, const float* in) const { io[0] = io[0] + in[0] * alpha; }
@@ -399,6 +412,11 @@ int pz_mul_slice(int dtype, void* out, const void* a, const void* b, int64_t n, 
 int pz_axpy(int dtype, void* y, const void* x, float alpha, int64_t n, void* stream)
 {
 	PZ_DISPATCH_FLOAT(dtype, ew_launch<T, 1, 1, true>(y, nullptr, x, nullptr, nullptr, n, Axpy{alpha}, stream));
+}
+
+int pz_axpy2_relu(int dtype, void* y, void* out, const void* x1, float a1, const void* x2, float a2, int64_t n, void* stream)
+{
+	PZ_DISPATCH_FLOAT(dtype, ew_launch<T, 2, 2, false>(y, out, x1, x2, nullptr, n, Axpy2Relu<T>{a1, a2}, stream));
 }
 
 int pz_axpy2(int dtype, void* y, const void* x1, float a1, const void* x2, float a2, int64_t n, void* stream)

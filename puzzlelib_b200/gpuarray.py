@@ -5,6 +5,8 @@ Python-side extension of Cuda/GPUArray.py (fill / astype / min / max / + * += *=
 libpzb200.so.  Views share the Buffer; non-contiguous views (results of slicing) can be read, written and copied
 through pitched 2-D copies exactly like the reference does with memcpy2D/3D (Array.c:560-801).
 """
+import os
+
 import numpy as np
 
 from . import driver
@@ -37,10 +39,10 @@ class DeferredFill:
 	"""The one launch the backend may hold back (see driver.flushDeferred): `y.fill(0)`, which `accumulate` turns into the scaled
 	copy `y = 0 + a * x` and then into the fused `y = (0 + a1 * x1) + a2 * x2`.  Holds references so that neither array's memory
 	can return to the pool while the launch is pending."""
-	__slots__ = ["y", "x", "alpha"]
+	__slots__ = ["y", "x", "alpha", "x2", "alpha2"]
 
 	def __init__(self, y):
-		self.y, self.x, self.alpha = y, None, 0.0
+		self.y, self.x, self.alpha, self.x2, self.alpha2 = y, None, 0.0, None, 0.0
 
 	def matches(self, y, x):
 		return self.y._ptr == y._ptr and self.y.nbytes == y.nbytes and self.y.dtype == y.dtype and x.dtype == y.dtype and \
@@ -50,8 +52,10 @@ class DeferredFill:
 		y = self.y
 		if self.x is None:
 			check(lib.pz_memset8(y._ptr, 0, y.nbytes, None))
-		else:
+		elif self.x2 is None:
 			check(lib.pz_axpy2(dtypeCode(y.dtype), y._ptr, self.x._ptr, self.alpha, None, 0.0, y.size, None))
+		else:
+			check(lib.pz_axpy2(dtypeCode(y.dtype), y._ptr, self.x._ptr, self.alpha, self.x2._ptr, self.alpha2, y.size, None))
 
 
 def accumulate(y, x, alpha):
@@ -63,8 +67,29 @@ def accumulate(y, x, alpha):
 	if op.x is None:
 		op.x, op.alpha = x, float(alpha)                      # y = 0 + alpha * x, still pending
 		return True
+	if op.x2 is None:
+		# y = (0 + a1 * x1) + a2 * x2: complete for a two-input Add / Replicate; kept pending one more call -- if the next
+		# operator is the ReLU of this sum (Add -> Activation in every ResNet block), `reluAfterSum` stores both in one pass
+		op.x2, op.alpha2 = x, float(alpha)
+		return True
+	driver.flushDeferred()                                    # a third term: the two-term sum goes out, this one takes the plain kernel
+	return False
+
+
+_NO_SUM_RELU = bool(int(os.environ.get("PZ_NO_SUM_RELU_FUSION", "0")))      # A/B switch for timing
+
+
+def reluAfterSum(out, inp):
+	"""relu(out, inp) where `inp` is a pending two-term sum: one launch writes the sum and its ReLU; True when it did"""
+	op = driver.deferred
+	if _NO_SUM_RELU or op is None or op.x2 is None or op.y._ptr != inp._ptr or op.y.nbytes != inp.nbytes or out.dtype != inp.dtype or \
+			out.size != inp.size or not out.contiguous or out._ptr == inp._ptr:
+		return False
+	for other in (inp, op.x, op.x2):
+		if not (out._ptr + out.nbytes <= other._ptr or other._ptr + other.nbytes <= out._ptr):
+			return False
 	driver.deferred = None
-	check(lib.pz_axpy2(dtypeCode(y.dtype), y._ptr, op.x._ptr, op.alpha, x._ptr, float(alpha), y.size, None))
+	check(lib.pz_axpy2_relu(dtypeCode(inp.dtype), inp._ptr, out._ptr, op.x._ptr, op.alpha, op.x2._ptr, op.alpha2, inp.size, None))
 	return True
 
 

@@ -1298,3 +1298,50 @@ def test_lstm_dropout_between_layers(bnd):
 	W2.set(W.get())
 	out2, reserve2 = rnn2.forward(G(bnd, x), W2, allocator=bnd.memoryPool)
 	assert np.array_equal(reserve2.rands[0].get(), reserve.rands[0].get()) and np.array_equal(out2.get(), out.get())
+
+
+@pytest.mark.parametrize("dtname", ["float32", "float16"])
+def test_relu_of_a_pending_sum_is_one_launch_with_the_same_bits(bnd, dtname):
+	"""Add -> Activation(relu) of every ResNet block (Modules/Add.py:15-23, Activation.py:69-71): `y.fill(0); y += x1; y += x2;
+	relu(out, y)` is issued as ONE launch that stores both y and out; bits identical to the four launches"""
+	from puzzlelib_b200 import driver
+	dt = np.dtype(dtname)
+	rng = np.random.RandomState(8)
+	n = (1 << 19) + 5
+	x1, x2 = (rng.randn(n).astype(dt) for _ in range(2))
+	g1, g2 = G(bnd, x1), G(bnd, x2)
+	axpy, relu = bnd.toVectorAddVectorKer(dt), bnd.reluKer(dt)
+
+	# the four separate launches, issued directly through the C-ABI (no deferral)
+	code = driver.dtypeCode(dt)
+	yr, outr = bnd.GPUArray.empty((n, ), dt), bnd.GPUArray.empty((n, ), dt)
+	assert driver.lib.pz_memset8(yr.ptr, 0, yr.nbytes, None) == 0
+	assert driver.lib.pz_axpy(code, yr.ptr, g1.ptr, 0.5, n, None) == 0
+	assert driver.lib.pz_axpy(code, yr.ptr, g2.ptr, 1.5, n, None) == 0
+	relu(outr, yr)
+	want_y, want_out = yr.get(), outr.get()
+	assert (want_out >= 0).all() and (want_out > 0).any() and (want_out == 0).any()
+
+	launches = driver.launchCount()
+	y, out = bnd.GPUArray.empty((n, ), dt), bnd.GPUArray.empty((n, ), dt)
+	y.fill(0)
+	axpy(y, g1, 0.5)
+	axpy(y, g2, 1.5)
+	assert driver.deferred is not None and driver.launchCount() == launches      # the complete sum is still pending
+	relu(out, y)
+	assert driver.deferred is None and driver.launchCount() - launches == 1
+	assert np.array_equal(y.get().view(np.uint8), want_y.view(np.uint8))
+	assert np.array_equal(out.get().view(np.uint8), want_out.view(np.uint8))
+
+	# in place, or on another tensor: the sum is flushed first and the plain kernels run
+	y.fill(0)
+	axpy(y, g1, 1.0)
+	axpy(y, g2, 1.0)
+	relu(y, y)
+	s = (x1.astype(np.float32) + x2.astype(np.float32)).astype(dt)
+	assert np.array_equal(y.get(), np.where(s > 0, s, dt.type(0)))
+	y.fill(0)
+	axpy(y, g1, 1.0)
+	axpy(y, g2, 1.0)
+	relu(out, g1)
+	assert np.array_equal(out.get(), np.where(x1 > 0, x1, dt.type(0))) and np.array_equal(y.get(), s)
