@@ -175,6 +175,10 @@ int pz_axpy2(int dtype, void* y, const void* x1, float a1, const void* x2, float
 /* the same fused sum followed by the ReLU the next module applies: y = (0 + a1*x1) + a2*x2, out = max(y, 0); both stored
  * (Modules/Add.py:15-23 then Modules/Activation.py:69-71 in one pass over the tensors) */
 int pz_axpy2_relu(int dtype, void* y, void* out, const void* x1, float a1, const void* x2, float a2, int64_t n, void* stream);
+/* ... or by the ReLU derivative: y = (0 + a1*x1) + a2*x2, ingrad = y * (ref > 0) (Modules/Replicate.py:24-29 then
+ * Modules/Activation.py:74-76) */
+int pz_axpy2_relu_bwd(int dtype, void* y, void* ingrad, const void* x1, float a1, const void* x2, float a2, const void* ref, int64_t n,
+					  void* stream);
 /* float32 math mode of pz_conv2d_* and pz_gemm (reference: enableTensorOps, CuDnn.c:61-74 / CuBlas.c:91-106): 0 = TF32
  * tensor-core products with fp32 accumulation (default; within 1e-3 of fp32), 1 = exact fp32 FMAs on the CUDA cores (what
  * cuDNN / cuBLAS give the reference's float32 tensors on this stack; a verification path, not tuned) */

@@ -1232,6 +1232,8 @@ def _actFactory(kind, nscalars):
 			b = float(scalars[1]) if nscalars > 1 else 0.0
 			slc = _slice(kwargs, ingrad.size)
 			if slc is None:
+				if kind == "relu" and driver.deferred is not None and gpuarray.reluDerAfterSum(ingrad, outgrad, ref):
+					return          # fused with the pending Replicate / Add gradient sum it reads
 				check(lib.pz_act_bwd(code, dt, ingrad.ptr, outgrad.ptr, ref.ptr, ingrad.size, a, b, None))
 			else:
 				check(lib.pz_act_bwd_slice(code, dt, ingrad.ptr, outgrad.ptr, ref.ptr, ingrad.size, a, b, *slc, None))

@@ -257,6 +257,19 @@ struct Axpy2Relu {
 		io[1] = sum * (sum > 0.0f);
 	}
 };
+// ... and followed by the ReLU DERIVATIVE (Replicate.updateGrad's sum of two gradients, then the previous block's Activation.updateGrad):
+// io[0] = the sum, io[1] = sum * (ref > 0) with in[2] = ref, the ReLU's output
+template <typename T>
+struct Axpy2ReluBwd {
+	float a1, a2;
+	__device__ __forceinline__ void apply(float* io, const float* in) const
+	{
+		const float first = to_f<T>(from_f<T>(fmaf(in[0], a1, 0.0f)));
+		const float sum = to_f<T>(from_f<T>(fmaf(in[1], a2, first)));
+		io[0] = sum;
+		io[1] = sum * (in[2] > 0.0f);
+	}
+};
 struct Axpy {   // y = y + x * alpha   (ElementWise.py:591)
 	float alpha;
 	__device__ __forceinline__ void apply(float* io, const float* in) const { io[0] = io[0] + in[0] * alpha; }
@@ -417,6 +430,12 @@ int pz_axpy(int dtype, void* y, const void* x, float alpha, int64_t n, void* str
 int pz_axpy2_relu(int dtype, void* y, void* out, const void* x1, float a1, const void* x2, float a2, int64_t n, void* stream)
 {
 	PZ_DISPATCH_FLOAT(dtype, ew_launch<T, 2, 2, false>(y, out, x1, x2, nullptr, n, Axpy2Relu<T>{a1, a2}, stream));
+}
+
+int pz_axpy2_relu_bwd(int dtype, void* y, void* ingrad, const void* x1, float a1, const void* x2, float a2, const void* ref, int64_t n,
+					  void* stream)
+{
+	PZ_DISPATCH_FLOAT(dtype, ew_launch<T, 2, 3, false>(y, ingrad, x1, x2, ref, n, Axpy2ReluBwd<T>{a1, a2}, stream));
 }
 
 int pz_axpy2(int dtype, void* y, const void* x1, float a1, const void* x2, float a2, int64_t n, void* stream)

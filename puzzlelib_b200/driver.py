@@ -133,6 +133,7 @@ _SIGNATURES = {
 	"pz_axpby": [c_int, _P, _P, c_float, _P, c_float, c_int64, _P],
 	"pz_axpy2": [c_int, _P, _P, c_float, _P, c_float, c_int64, _P],
 	"pz_axpy2_relu": [c_int, _P, _P, _P, c_float, _P, c_float, c_int64, _P],
+	"pz_axpy2_relu_bwd": [c_int, _P, _P, _P, c_float, _P, c_float, _P, c_int64, _P],
 	"pz_scale_shift": [c_int, _P, _P, c_float, c_float, c_int64, _P],
 	"pz_mul": [c_int, _P, _P, _P, c_int64, _P],
 	"pz_add2": [c_int, _P, _P, _P, c_int64, _P],

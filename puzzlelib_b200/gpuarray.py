@@ -79,17 +79,39 @@ def accumulate(y, x, alpha):
 _NO_SUM_RELU = bool(int(os.environ.get("PZ_NO_SUM_RELU_FUSION", "0")))      # A/B switch for timing
 
 
-def reluAfterSum(out, inp):
-	"""relu(out, inp) where `inp` is a pending two-term sum: one launch writes the sum and its ReLU; True when it did"""
+def _pendingSum(inp, out, *others):
+	"""the pending two-term sum that `inp` is, if `out` (a distinct tensor of the same layout) can be written next to it"""
 	op = driver.deferred
 	if _NO_SUM_RELU or op is None or op.x2 is None or op.y._ptr != inp._ptr or op.y.nbytes != inp.nbytes or out.dtype != inp.dtype or \
-			out.size != inp.size or not out.contiguous or out._ptr == inp._ptr:
-		return False
-	for other in (inp, op.x, op.x2):
+			out.size != inp.size or not out.contiguous:
+		return None
+	for other in (inp, op.x, op.x2) + others:
 		if not (out._ptr + out.nbytes <= other._ptr or other._ptr + other.nbytes <= out._ptr):
-			return False
+			return None
+	return op
+
+
+def reluAfterSum(out, inp):
+	"""relu(out, inp) where `inp` is a pending two-term sum: one launch writes the sum and its ReLU; True when it did"""
+	op = _pendingSum(inp, out)
+	if op is None:
+		return False
 	driver.deferred = None
 	check(lib.pz_axpy2_relu(dtypeCode(inp.dtype), inp._ptr, out._ptr, op.x._ptr, op.alpha, op.x2._ptr, op.alpha2, inp.size, None))
+	return True
+
+
+def reluDerAfterSum(ingrad, outgrad, ref):
+	"""reluDer(ingrad, outgrad, ref) where `outgrad` is a pending two-term sum (Replicate's gradient sum feeding the previous block's
+	ReLU): one launch writes the sum and ingrad = sum * (ref > 0); True when it did"""
+	if ref.dtype != outgrad.dtype or ref.size != outgrad.size or not ref.contiguous:
+		return False
+	op = _pendingSum(outgrad, ingrad, ref)
+	if op is None or not (ref._ptr + ref.nbytes <= outgrad._ptr or outgrad._ptr + outgrad.nbytes <= ref._ptr):
+		return False
+	driver.deferred = None
+	check(lib.pz_axpy2_relu_bwd(dtypeCode(outgrad.dtype), outgrad._ptr, ingrad._ptr, op.x._ptr, op.alpha, op.x2._ptr, op.alpha2, ref._ptr,
+								outgrad.size, None))
 	return True
 
 

@@ -1345,3 +1345,42 @@ def test_relu_of_a_pending_sum_is_one_launch_with_the_same_bits(bnd, dtname):
 	axpy(y, g2, 1.0)
 	relu(out, g1)
 	assert np.array_equal(out.get(), np.where(x1 > 0, x1, dt.type(0))) and np.array_equal(y.get(), s)
+
+
+@pytest.mark.parametrize("dtname", ["float32", "float16"])
+def test_relu_derivative_of_a_pending_sum_is_one_launch_with_the_same_bits(bnd, dtname):
+	"""Replicate.updateGrad (sum of two gradients, Modules/Replicate.py:24-29) followed by the previous block's Activation.updateGrad
+	(Modules/Activation.py:74-76): one launch stores the sum and sum * (ref > 0)"""
+	from puzzlelib_b200 import driver
+	dt = np.dtype(dtname)
+	rng = np.random.RandomState(9)
+	n = (1 << 19) + 3
+	x1, x2, r = (rng.randn(n).astype(dt) for _ in range(3))
+	r = np.where(r > 0, r, dt.type(0))                           # a ReLU output
+	g1, g2, gr = G(bnd, x1), G(bnd, x2), G(bnd, r)
+	axpy, reluDer = bnd.toVectorAddVectorKer(dt), bnd.reluDerKer(dt)
+
+	code = driver.dtypeCode(dt)
+	yr, inr = bnd.GPUArray.empty((n, ), dt), bnd.GPUArray.empty((n, ), dt)
+	assert driver.lib.pz_memset8(yr.ptr, 0, yr.nbytes, None) == 0
+	assert driver.lib.pz_axpy(code, yr.ptr, g1.ptr, 1.0, n, None) == 0
+	assert driver.lib.pz_axpy(code, yr.ptr, g2.ptr, 1.0, n, None) == 0
+	reluDer(inr, yr, gr)
+	want_y, want_in = yr.get(), inr.get()
+
+	launches = driver.launchCount()
+	y, ingrad = bnd.GPUArray.empty((n, ), dt), bnd.GPUArray.empty((n, ), dt)
+	y.fill(0)
+	axpy(y, g1, 1.0)
+	axpy(y, g2, 1.0)
+	reluDer(ingrad, y, gr)
+	assert driver.deferred is None and driver.launchCount() - launches == 1
+	assert np.array_equal(y.get().view(np.uint8), want_y.view(np.uint8))
+	assert np.array_equal(ingrad.get().view(np.uint8), want_in.view(np.uint8))
+
+	# in place (inplace=True activations hand the same array as ingrad and outgrad): flushed, then the plain kernel
+	y.fill(0)
+	axpy(y, g1, 1.0)
+	axpy(y, g2, 1.0)
+	reluDer(y, y, gr)
+	assert np.array_equal(y.get().view(np.uint8), want_in.view(np.uint8))
