@@ -250,6 +250,11 @@ int pz_argminmax(int dtype, int32_t* idx, const void* tensor, int64_t z, int64_t
 int pz_bn_fwd_train(int dtype, const void* x, void* y, int64_t N, int64_t C, int64_t S, const float* scale,
 					const float* bias, float* running_mean, float* running_var, float* save_mean,
 					float* save_invvar, double eps, double factor, void* stream);
+/* pz_bn_fwd_train followed by the ReLU the next module applies to y: y AND z = y * (y > 0) are stored; in the cluster kernel by
+ * the same pass (Modules/BatchNormND.py:66-78 then Modules/Activation.py:69-71), otherwise by the plain ReLU kernel */
+int pz_bn_fwd_train_relu(int dtype, const void* x, void* y, void* z, int64_t N, int64_t C, int64_t S, const float* scale, const float* bias,
+						 float* running_mean, float* running_var, float* save_mean, float* save_invvar, double eps, double factor,
+						 void* stream);
 int pz_bn_fwd_infer(int dtype, const void* x, void* y, int64_t N, int64_t C, int64_t S, const float* scale,
 					const float* bias, const float* mean, const float* var, double eps, void* stream);
 int pz_bn_bwd(int dtype, const void* x, const void* dy, void* dx, int64_t N, int64_t C, int64_t S,

@@ -523,6 +523,12 @@ class DnnContext:
 		driver.traceScalar("the batch-norm running-average factor", factor)
 		savemean = GPUArray(scale.shape, _f32, allocator=allocator)
 		saveinvvar = GPUArray(scale.shape, _f32, allocator=allocator)
+		params = (scale, bias, mean, var, savemean, saveinvvar)
+		if data.nbytes >= gpuarray.DEFER_MIN_BYTES and data.contiguous and out.contiguous and all(p.contiguous for p in params):
+			# held back for one call: a ReLU of `out` that follows is folded into the same pass (gpuarray.DeferredBatchNorm)
+			driver.flushDeferred()
+			driver.deferred = gpuarray.DeferredBatchNorm(code, data, out, (N, C, S), params, epsilon, factor)
+			return out, savemean, saveinvvar
 		check(lib.pz_bn_fwd_train(code, data.ptr, out.ptr, N, C, S, scale.ptr, bias.ptr, mean.ptr, var.ptr, savemean.ptr,
 								  saveinvvar.ptr, epsilon, factor, None))
 		return out, savemean, saveinvvar
@@ -1216,8 +1222,8 @@ def _actFactory(kind, nscalars):
 			b = float(scalars[1]) if nscalars > 1 else 0.0
 			slc = _slice(kwargs, out.size)
 			if slc is None:
-				if kind == "relu" and driver.deferred is not None and gpuarray.reluAfterSum(out, inp):
-					return          # fused with the pending Add / Replicate sum it reads
+				if kind == "relu" and driver.deferred is not None and (gpuarray.reluAfterSum(out, inp) or gpuarray.reluAfterBatchNorm(out, inp)):
+					return          # fused with the pending Add / Replicate sum, or the pending batch-norm launch, whose output it reads
 				check(lib.pz_act_fwd(code, dt, out.ptr, inp.ptr, out.size, a, b, None))
 			else:
 				check(lib.pz_act_fwd_slice(code, dt, out.ptr, inp.ptr, out.size, a, b, *slc, None))

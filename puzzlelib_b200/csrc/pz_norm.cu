@@ -649,7 +649,7 @@ __device__ __forceinline__ void cluster_sum2(float& s1, float& s2, float* part, 
 }
 
 template <typename T, int VEC, int THREADS, bool BULK>
-__global__ void __launch_bounds__(THREADS) bn_fwd_cluster_kernel(const T* __restrict__ x, T* __restrict__ y, ClusterGeo g,
+__global__ void __launch_bounds__(THREADS) bn_fwd_cluster_kernel(const T* __restrict__ x, T* __restrict__ y, T* __restrict__ z, ClusterGeo g,
 																  const float* __restrict__ scale, const float* __restrict__ bias,
 																  float* mean_io, float* var_io, float* save_mean, float* save_invvar,
 																  float eps, float factor)
@@ -762,6 +762,12 @@ __global__ void __launch_bounds__(THREADS) bn_fwd_cluster_kernel(const T* __rest
 		#pragma unroll
 		for (int e = 0; e < VEC; e++) v.v[e] = from_f<T>(fmaf(to_f<T>(v.v[e]), a, b));
 		store_streaming<T, VEC>(y + q.e0(), v, g.stream_stores);
+		if (z != nullptr) {
+			// the ReLU the next module applies to y (pz_bn_fwd_train_relu), from the ROUNDED y like the separate kernel: y * (y > 0)
+			#pragma unroll
+			for (int e = 0; e < VEC; e++) { const float f = to_f<T>(v.v[e]); v.v[e] = from_f<T>(f * (f > 0.0f ? 1.0f : 0.0f)); }
+			store_streaming<T, VEC>(z + q.e0(), v, 0);
+		}
 	}
 	for (uint32_t i = threadIdx.x; i < 2u * nrows; i += THREADS) {
 		uint32_t vv, e0;
@@ -772,6 +778,11 @@ __global__ void __launch_bounds__(THREADS) bn_fwd_cluster_kernel(const T* __rest
 		#pragma unroll
 		for (int e = 0; e < VEC; e++) v.v[e] = from_f<T>(fmaf(to_f<T>(v.v[e]), a, b));
 		store_partial<T, VEC>(y + e0, v, mask);
+		if (z != nullptr) {
+			#pragma unroll
+			for (int e = 0; e < VEC; e++) { const float f = to_f<T>(v.v[e]); v.v[e] = from_f<T>(f * (f > 0.0f ? 1.0f : 0.0f)); }
+			store_partial<T, VEC>(z + e0, v, mask);
+		}
 	}
 }
 
@@ -1241,7 +1252,7 @@ Slab make_slab(const Plan& p, int64_t N, int64_t C, int64_t S, int64_t c0, int64
 
 template <typename T>
 int fwd_train(const void* x, void* y, int64_t N, int64_t C, int64_t S, const float* scale, const float* bias, float* rm,
-			  float* rv, float* sm, float* siv, double eps, double factor, void* stream)
+			  float* rv, float* sm, float* siv, double eps, double factor, void* stream, void* z = nullptr, bool* fused = nullptr)
 {
 	constexpr int V = 16 / sizeof(T);
 	cudaStream_t s = pz_stream(stream);
@@ -1256,7 +1267,7 @@ int fwd_train(const void* x, void* y, int64_t N, int64_t C, int64_t S, const flo
 			// small maps where a cluster's serial chain per channel dominates: profiles/r02_conv_epilogue_gather_experiments.md section 6;
 			// PZ_BN_PERSISTENT=1 enables it for experiments)
 			static const bool persistent_on = env_int("PZ_BN_PERSISTENT", 0) != 0;
-			if (persistent_on && cp.bulk && 2 * cp.smem <= 220 * 1024) {
+			if (persistent_on && z == nullptr && cp.bulk && 2 * cp.smem <= 220 * 1024) {
 				ClusterPlan pp = cp;
 				pp.smem = 2 * cp.smem;
 				pp.threads = 512;
@@ -1268,7 +1279,10 @@ int fwd_train(const void* x, void* y, int64_t N, int64_t C, int64_t S, const flo
 										  (float)eps, (float)factor);
 				}
 			}
-#define PZ_BN_FWD_CLUSTER(TH, BK) launch_cluster(bn_fwd_cluster_kernel<T, V, TH, BK>, cp, s, (const T*)x, (T*)y, cp.g, scale, bias, rm, rv, sm, siv, (float)eps, (float)factor)
+			// the fused ReLU output rides on the plain-store phase 2 of the cluster kernel (16-byte aligned like x and y)
+			T* zz = (z != nullptr && !cp.g.bulk_store && (uintptr_t)z % 16 == 0) ? (T*)z : nullptr;
+			if (fused) *fused = zz != nullptr;
+#define PZ_BN_FWD_CLUSTER(TH, BK) launch_cluster(bn_fwd_cluster_kernel<T, V, TH, BK>, cp, s, (const T*)x, (T*)y, zz, cp.g, scale, bias, rm, rv, sm, siv, (float)eps, (float)factor)
 			if (cp.threads == 512) return cp.bulk ? PZ_BN_FWD_CLUSTER(512, true) : PZ_BN_FWD_CLUSTER(512, false);
 			return cp.bulk ? PZ_BN_FWD_CLUSTER(256, true) : PZ_BN_FWD_CLUSTER(256, false);
 #undef PZ_BN_FWD_CLUSTER
@@ -1392,6 +1406,23 @@ int pz_bn_fwd_train(int dtype, const void* x, void* y, int64_t N, int64_t C, int
 	int st = check_dims(N, C, S);
 	if (st != PZ_OK) return st;
 	PZ_DISPATCH_FLOAT(dtype, fwd_train<T>(x, y, N, C, S, scale, bias, running_mean, running_var, save_mean, save_invvar, eps, factor, stream));
+}
+
+int pz_bn_fwd_train_relu(int dtype, const void* x, void* y, void* z, int64_t N, int64_t C, int64_t S, const float* scale, const float* bias,
+						 float* running_mean, float* running_var, float* save_mean, float* save_invvar, double eps, double factor,
+						 void* stream)
+{
+	int st = check_dims(N, C, S);
+	if (st != PZ_OK) return st;
+	bool fused = false;
+	switch (dtype) {
+		case PZ_F32: st = fwd_train<float>(x, y, N, C, S, scale, bias, running_mean, running_var, save_mean, save_invvar, eps, factor, stream, z, &fused); break;
+		case PZ_F16: st = fwd_train<__half>(x, y, N, C, S, scale, bias, running_mean, running_var, save_mean, save_invvar, eps, factor, stream, z, &fused); break;
+		case PZ_BF16: st = fwd_train<__nv_bfloat16>(x, y, N, C, S, scale, bias, running_mean, running_var, save_mean, save_invvar, eps, factor, stream, z, &fused); break;
+		default: pz_set_error(PZ_ERR_UNSUPPORTED, "unsupported dtype %d", dtype); return PZ_ERR_UNSUPPORTED;
+	}
+	if (st != PZ_OK || fused) return st;
+	return pz_act_fwd(PZ_ACT_RELU, dtype, z, y, N * C * S, 0.0f, 0.0f, stream);      // paths without the fused store: the plain ReLU kernel
 }
 
 int pz_bn_fwd_infer(int dtype, const void* x, void* y, int64_t N, int64_t C, int64_t S, const float* scale, const float* bias,

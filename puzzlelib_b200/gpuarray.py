@@ -58,11 +58,45 @@ class DeferredFill:
 			check(lib.pz_axpy2(dtypeCode(y.dtype), y._ptr, self.x._ptr, self.alpha, self.x2._ptr, self.alpha2, y.size, None))
 
 
+class DeferredBatchNorm:
+	"""A train-mode batch-norm forward launch held back for one call: when the next operator is the ReLU of its output (conv -> bn ->
+	relu inside every ResNet block) one pass stores both (`pz_bn_fwd_train_relu`); any other access to device memory launches it as
+	it is.  Holds references to every tensor of the launch."""
+	__slots__ = ["code", "x", "y", "geometry", "params", "eps", "factor"]
+
+	def __init__(self, code, x, y, geometry, params, eps, factor):
+		self.code, self.x, self.y, self.geometry, self.params, self.eps, self.factor = code, x, y, geometry, params, eps, factor
+
+	def launch(self, z=None):
+		ptrs = [p._ptr for p in self.params]          # scale, bias, mean, var, savemean, saveinvvar
+		if z is None:
+			check(lib.pz_bn_fwd_train(self.code, self.x._ptr, self.y._ptr, *self.geometry, *ptrs, self.eps, self.factor, None))
+		else:
+			check(lib.pz_bn_fwd_train_relu(self.code, self.x._ptr, self.y._ptr, z._ptr, *self.geometry, *ptrs, self.eps, self.factor, None))
+
+	def flush(self):
+		self.launch()
+
+
+def reluAfterBatchNorm(out, inp):
+	"""relu(out, inp) where `inp` is the output of a pending batch-norm launch: fused; True when it did"""
+	op = driver.deferred
+	if _NO_SUM_RELU or type(op) is not DeferredBatchNorm or op.y._ptr != inp._ptr or op.y.nbytes != inp.nbytes or out.dtype != inp.dtype or \
+			out.size != inp.size or not out.contiguous:
+		return False
+	for other in (op.x, op.y) + tuple(op.params):
+		if not (out._ptr + out.nbytes <= other._ptr or other._ptr + other.nbytes <= out._ptr):
+			return False
+	driver.deferred = None
+	op.launch(out)
+	return True
+
+
 def accumulate(y, x, alpha):
 	"""y += alpha * x (the reference's toVectorAddVector kernel) with the pending-fill fusion; returns True when the launch was
 	absorbed or issued here"""
 	op = driver.deferred
-	if op is None or not op.matches(y, x):
+	if type(op) is not DeferredFill or not op.matches(y, x):
 		return False
 	if op.x is None:
 		op.x, op.alpha = x, float(alpha)                      # y = 0 + alpha * x, still pending
@@ -82,7 +116,7 @@ _NO_SUM_RELU = bool(int(os.environ.get("PZ_NO_SUM_RELU_FUSION", "0")))      # A/
 def _pendingSum(inp, out, *others):
 	"""the pending two-term sum that `inp` is, if `out` (a distinct tensor of the same layout) can be written next to it"""
 	op = driver.deferred
-	if _NO_SUM_RELU or op is None or op.x2 is None or op.y._ptr != inp._ptr or op.y.nbytes != inp.nbytes or out.dtype != inp.dtype or \
+	if _NO_SUM_RELU or type(op) is not DeferredFill or op.x2 is None or op.y._ptr != inp._ptr or op.y.nbytes != inp.nbytes or out.dtype != inp.dtype or \
 			out.size != inp.size or not out.contiguous:
 		return None
 	for other in (inp, op.x, op.x2) + others:

@@ -1384,3 +1384,45 @@ def test_relu_derivative_of_a_pending_sum_is_one_launch_with_the_same_bits(bnd, 
 	axpy(y, g2, 1.0)
 	reluDer(y, y, gr)
 	assert np.array_equal(y.get().view(np.uint8), want_in.view(np.uint8))
+
+
+@pytest.mark.parametrize("shape", [(16, 32, 55, 55), (8, 16, 112, 112), (64, 48, 14, 14)])
+def test_relu_after_batchnorm_is_folded_into_the_pending_launch(bnd, shape):
+	"""conv -> bn -> relu of every ResNet block: the train-mode batch-norm launch is held back for one call and a ReLU of its output
+	rides on the same pass (cluster kernel) or follows it inside the same C call (other paths).  Every tensor the reference
+	materialises -- y, relu(y), saved and running statistics -- is bit-identical to the two separate launches."""
+	from puzzlelib_b200 import driver
+	N, C, H, W = shape
+	rng = np.random.RandomState(C)
+	x = (rng.randn(*shape) * 2 + 0.5).astype(np.float32)
+	scale, bias = rng.randn(1, C, 1, 1).astype(np.float32), rng.randn(1, C, 1, 1).astype(np.float32)
+	relu = bnd.reluKer(np.float32)
+
+	def run(fused):
+		gx = G(bnd, x)
+		mean, var = bnd.GPUArray.zeros((1, C, 1, 1), np.float32), G(bnd, np.ones((1, C, 1, 1), np.float32))
+		gs, gb = G(bnd, scale), G(bnd, bias)
+		driver.flushDeferred()
+		launches = driver.launchCount()
+		y, sm, siv = bnd.dnn.batchNormNd(gx, mean, var, gs, gb, 1e-5, 0.25, False)
+		if not fused:
+			driver.flushDeferred()                          # the plain launch, then the plain ReLU kernel
+		else:
+			assert driver.deferred is not None and driver.launchCount() == launches
+		z = bnd.GPUArray.empty(shape, np.float32)
+		relu(z, y)
+		assert driver.deferred is None
+		return [a.get() for a in (y, z, sm, siv, mean, var)], driver.launchCount() - launches
+
+	plain, nplain = run(False)
+	fused, nfused = run(True)
+	for name, a, b in zip(("y", "relu", "savemean", "saveinvvar", "mean", "var"), plain, fused):
+		assert np.array_equal(a.view(np.uint8), b.view(np.uint8)), name
+	assert (fused[1] >= 0).all() and (fused[1] == np.where(fused[0] > 0, fused[0], 0)).all()
+	assert nfused <= nplain
+
+	# anything else that touches the output first gets the plain launch
+	gx = G(bnd, x)
+	mean, var = bnd.GPUArray.zeros((1, C, 1, 1), np.float32), G(bnd, np.ones((1, C, 1, 1), np.float32))
+	y, sm, siv = bnd.dnn.batchNormNd(gx, mean, var, G(bnd, scale), G(bnd, bias), 1e-5, 0.25, False)
+	assert np.array_equal(y.get().view(np.uint8), plain[0].view(np.uint8)) and driver.deferred is None
