@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(kThreads) bn_apply_kernel(const T* __restrict_
 	int cur = -1;
 	uint32_t j = 0;
 	bool active = false;
-	float a[VEC], b[VEC];
+	float a[VEC], b[VEC], m[VEC];      // y = (x - m) * a + b
 	for (int it = ir.begin; it < ir.end; it++) {
 		const int cb = it / g.row_groups, rg = it - cb * g.row_groups;
 		if (cb != cur) {
@@ -236,7 +236,8 @@ __global__ void __launch_bounds__(kThreads) bn_apply_kernel(const T* __restrict_
 						invstd = 1.0f / sqrtf(var_io[c] + eps);
 					}
 					a[e] = scale[c] * invstd;
-					b[e] = bias[c] - mean * a[e];
+					b[e] = bias[c];
+					m[e] = mean;
 				}
 			}
 		}
@@ -251,14 +252,14 @@ __global__ void __launch_bounds__(kThreads) bn_apply_kernel(const T* __restrict_
 			#pragma unroll
 			for (int u = 0; u < kRowUnroll; u++) {
 				#pragma unroll
-				for (int e = 0; e < VEC; e++) v[u].v[e] = from_f<T>(fmaf(to_f<T>(v[u].v[e]), a[e], b[e]));
+				for (int e = 0; e < VEC; e++) v[u].v[e] = from_f<T>(fmaf(to_f<T>(v[u].v[e]) - m[e], a[e], b[e]));
 				*reinterpret_cast<Pack<T, VEC>*>(q + (size_t)u * g.row_stride) = v[u];
 			}
 		} else {
 			for (int r = r0; r < r1; r++) {
 				Pack<T, VEC> v = *reinterpret_cast<const Pack<T, VEC>*>(p);
 				#pragma unroll
-				for (int e = 0; e < VEC; e++) v.v[e] = from_f<T>(fmaf(to_f<T>(v.v[e]), a[e], b[e]));
+				for (int e = 0; e < VEC; e++) v.v[e] = from_f<T>(fmaf(to_f<T>(v.v[e]) - m[e], a[e], b[e]));
 				*reinterpret_cast<Pack<T, VEC>*>(q) = v;
 				p += g.row_stride;
 				q += g.row_stride;
@@ -558,6 +559,34 @@ __device__ __forceinline__ void bulk_store_planes(const ClusterGeo& g, uint32_t 
 }
 __device__ __forceinline__ void bulk_store_wait() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
+// The per-thread partial sums (a few dozen float terms each) are combined in DOUBLE: a float tree loses ~1e-7 of the pivot-shifted
+// sums, which is what separates a mean / variance from the correctly rounded one -- and the reference's own unit tests compare
+// batch-norm outputs with numpy at atol 1e-8 (Modules/BatchNorm3D.py:57-59).  Deterministic: fixed trees, partials in rank order.
+__device__ __forceinline__ double warp_sum_d(double v)
+{
+	#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+	return v;
+}
+template <int THREADS>
+__device__ __forceinline__ void block_sum2_d(double& a, double& b, double* red /* [2 * THREADS / 32 + 2] */)
+{
+	a = warp_sum_d(a);
+	b = warp_sum_d(b);
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	if (lane == 0) { red[2 * warp] = a; red[2 * warp + 1] = b; }
+	__syncthreads();
+	if (warp == 0) {
+		double x = lane < THREADS / 32 ? red[2 * lane] : 0.0, y = lane < THREADS / 32 ? red[2 * lane + 1] : 0.0;
+		x = warp_sum_d(x);
+		y = warp_sum_d(y);
+		if (lane == 0) { red[2 * (THREADS / 32)] = x; red[2 * (THREADS / 32) + 1] = y; }
+	}
+	__syncthreads();
+	a = red[2 * (THREADS / 32)];
+	b = red[2 * (THREADS / 32) + 1];
+}
+
 // deterministic block sum of two values; result valid in every thread
 template <int THREADS>
 __device__ __forceinline__ void block_sum2(float& a, float& b, float* red /* [2 * THREADS / 32 + 2] */)
@@ -637,6 +666,24 @@ __device__ __forceinline__ void store_partial_vectors(const ClusterGeo& g, uint3
 }
 
 // the cluster-wide sum of the CTAs' (s1, s2) through distributed shared memory, in rank order
+__device__ __forceinline__ double ld_dsmem_d(const double* local, unsigned rank)
+{
+	unsigned addr = (unsigned)__cvta_generic_to_shared(local), remote;
+	double v;
+	asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(addr), "r"(rank));
+	asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(remote) : "memory");
+	return v;
+}
+__device__ __forceinline__ void cluster_sum2_d(double& s1, double& s2, double* part, int CL)
+{
+	if (CL <= 1) return;
+	if (threadIdx.x == 0) { part[0] = s1; part[1] = s2; }
+	cluster_sync_all();
+	s1 = 0.0;
+	s2 = 0.0;
+	for (int r = 0; r < CL; r++) { s1 += ld_dsmem_d(&part[0], (unsigned)r); s2 += ld_dsmem_d(&part[1], (unsigned)r); }
+	cluster_sync_all();                 // nobody leaves (or overwrites `part`) while a peer still reads it
+}
 __device__ __forceinline__ void cluster_sum2(float& s1, float& s2, float* part, int CL)
 {
 	if (CL <= 1) return;
@@ -655,8 +702,8 @@ __global__ void __launch_bounds__(THREADS) bn_fwd_cluster_kernel(const T* __rest
 																  float eps, float factor)
 {
 	extern __shared__ uint4 stash[];                 // [stash_slots]: this CTA's planes, as the aligned vectors that cover them
-	__shared__ float red[2 * THREADS / 32 + 2];
-	__shared__ float part[2];
+	__shared__ double red[2 * THREADS / 32 + 2];
+	__shared__ double part[2];
 	using P = Pack<T, VEC>;
 	const unsigned rank = g.CL > 1 ? cluster_ctarank() : 0u;
 	const int c = (int)(blockIdx.x / (unsigned)g.CL);
@@ -718,14 +765,15 @@ __global__ void __launch_bounds__(THREADS) bn_fwd_cluster_kernel(const T* __rest
 			if (mask >> e & 1u) { const float d = to_f<T>(pv.v[e]) - pivot; s1 += d; s2 = fmaf(d, d, s2); }
 	}
 	}
-	block_sum2<THREADS>(s1, s2, red);
-	cluster_sum2(s1, s2, part, g.CL);
+	double d1 = s1, d2 = s2;
+	block_sum2_d<THREADS>(d1, d2, red);
+	cluster_sum2_d(d1, d2, part, g.CL);
 
 	const float count = (float)g.N * (float)g.S;
-	const float dmean = s1 / count;
-	const float mean = pivot + dmean;
-	const float var = fmaxf(s2 / count - dmean * dmean, 0.0f);      // biased: used for normalisation
-	const float invstd = 1.0f / sqrtf(var + eps);
+	const double dcount = (double)g.N * (double)g.S, ddmean = d1 / dcount;
+	const float mean = (float)((double)pivot + ddmean);
+	const float var = (float)fmax(d2 / dcount - ddmean * ddmean, 0.0);      // biased: used for normalisation
+	const float invstd = (float)(1.0 / sqrt(fmax(d2 / dcount - ddmean * ddmean, 0.0) + (double)eps));
 	if (rank == 0 && threadIdx.x == 0) {
 		save_mean[c] = mean;
 		save_invvar[c] = invstd;
@@ -734,7 +782,7 @@ __global__ void __launch_bounds__(THREADS) bn_fwd_cluster_kernel(const T* __rest
 		mean_io[c] = (1.0f - factor) * mean_io[c] + factor * mean;
 		var_io[c] = (1.0f - factor) * var_io[c] + factor * uvar;
 	}
-	const float a = scale[c] * invstd, b = bias[c] - mean * a;
+	const float a = scale[c] * invstd, b = bias[c];       // y = (x - mean) * a + b: x - mean is exact where y is small
 
 	// ---- phase 2: shared memory -> y = a * x + b -> HBM
 	__syncthreads();                              // partial vectors were stashed by other threads than the ones that read them
@@ -744,7 +792,7 @@ __global__ void __launch_bounds__(THREADS) bn_fwd_cluster_kernel(const T* __rest
 			const uint4 raw = stash[slot];
 			P v = *reinterpret_cast<const P*>(&raw);
 			#pragma unroll
-			for (int e = 0; e < VEC; e++) v.v[e] = from_f<T>(fmaf(to_f<T>(v.v[e]), a, b));
+			for (int e = 0; e < VEC; e++) v.v[e] = from_f<T>(fmaf(to_f<T>(v.v[e]) - mean, a, b));
 			stash[slot] = *reinterpret_cast<const uint4*>(&v);
 		}
 		fence_proxy_async();
@@ -760,7 +808,7 @@ __global__ void __launch_bounds__(THREADS) bn_fwd_cluster_kernel(const T* __rest
 		const uint4 raw = stash[slot];
 		P v = *reinterpret_cast<const P*>(&raw);
 		#pragma unroll
-		for (int e = 0; e < VEC; e++) v.v[e] = from_f<T>(fmaf(to_f<T>(v.v[e]), a, b));
+		for (int e = 0; e < VEC; e++) v.v[e] = from_f<T>(fmaf(to_f<T>(v.v[e]) - mean, a, b));
 		store_streaming<T, VEC>(y + q.e0(), v, g.stream_stores);
 		if (z != nullptr) {
 			// the ReLU the next module applies to y (pz_bn_fwd_train_relu), from the ROUNDED y like the separate kernel: y * (y > 0)
@@ -776,7 +824,7 @@ __global__ void __launch_bounds__(THREADS) bn_fwd_cluster_kernel(const T* __rest
 		const uint4 raw = stash[(i >> 1) * (uint32_t)g.SP + vv];
 		P v = *reinterpret_cast<const P*>(&raw);
 		#pragma unroll
-		for (int e = 0; e < VEC; e++) v.v[e] = from_f<T>(fmaf(to_f<T>(v.v[e]), a, b));
+		for (int e = 0; e < VEC; e++) v.v[e] = from_f<T>(fmaf(to_f<T>(v.v[e]) - mean, a, b));
 		store_partial<T, VEC>(y + e0, v, mask);
 		if (z != nullptr) {
 			#pragma unroll
@@ -807,8 +855,8 @@ __global__ void __launch_bounds__(THREADS, 1) bn_fwd_persistent_kernel(const T* 
 																		float eps, float factor)
 {
 	extern __shared__ uint4 stash2[];                // [2][stash_slots]
-	__shared__ float red[2 * THREADS / 32 + 2];
-	__shared__ float part[2];
+	__shared__ double red[2 * THREADS / 32 + 2];
+	__shared__ double part[2];
 	__shared__ uint64_t bars[2];
 	using P = Pack<T, VEC>;
 	const unsigned rank = g.CL > 1 ? cluster_ctarank() : 0u;
@@ -855,13 +903,14 @@ __global__ void __launch_bounds__(THREADS, 1) bn_fwd_persistent_kernel(const T* 
 			#pragma unroll
 			for (int e = 0; e < VEC; e++) { const float d = to_f<T>(v.v[e]) - pivot; s1 += d; s2 = fmaf(d, d, s2); }
 		}
-		block_sum2<THREADS>(s1, s2, red);
-		cluster_sum2(s1, s2, part, g.CL);
+		double d1 = s1, d2 = s2;
+		block_sum2_d<THREADS>(d1, d2, red);
+		cluster_sum2_d(d1, d2, part, g.CL);
 
-		const float dmean = s1 / count;
-		const float mean = pivot + dmean;
-		const float var = fmaxf(s2 / count - dmean * dmean, 0.0f);
-		const float invstd = 1.0f / sqrtf(var + eps);
+		const double dcount = (double)g.N * (double)g.S, ddmean = d1 / dcount;
+		const float mean = (float)((double)pivot + ddmean);
+		const float var = (float)fmax(d2 / dcount - ddmean * ddmean, 0.0);
+		const float invstd = (float)(1.0 / sqrt(fmax(d2 / dcount - ddmean * ddmean, 0.0) + (double)eps));
 		if (rank == 0 && threadIdx.x == 0) {
 			save_mean[c] = mean;
 			save_invvar[c] = invstd;
@@ -869,13 +918,13 @@ __global__ void __launch_bounds__(THREADS, 1) bn_fwd_persistent_kernel(const T* 
 			mean_io[c] = (1.0f - factor) * mean_io[c] + factor * mean;
 			var_io[c] = (1.0f - factor) * var_io[c] + factor * uvar;
 		}
-		const float a = scale[c] * invstd, b = bias[c] - mean * a;
+		const float a = scale[c] * invstd, b = bias[c];       // y = (x - mean) * a + b: x - mean is exact where y is small
 
 		for (uint32_t slot = threadIdx.x; slot < nslots; slot += THREADS) {
 			const uint4 raw = stash[slot];
 			P v = *reinterpret_cast<const P*>(&raw);
 			#pragma unroll
-			for (int e = 0; e < VEC; e++) v.v[e] = from_f<T>(fmaf(to_f<T>(v.v[e]), a, b));
+			for (int e = 0; e < VEC; e++) v.v[e] = from_f<T>(fmaf(to_f<T>(v.v[e]) - mean, a, b));
 			stash[slot] = *reinterpret_cast<const uint4*>(&v);
 		}
 		fence_proxy_async();
@@ -895,8 +944,8 @@ __global__ void __launch_bounds__(THREADS) bn_bwd_cluster_kernel(const T* __rest
 																  float* dscale, float* dbias)
 {
 	extern __shared__ uint4 stash[];                 // [2][stash_slots]: x planes, then dy planes
-	__shared__ float red[2 * THREADS / 32 + 2];
-	__shared__ float part[2];
+	__shared__ double red[2 * THREADS / 32 + 2];
+	__shared__ double part[2];
 	using P = Pack<T, VEC>;
 	const unsigned rank = g.CL > 1 ? cluster_ctarank() : 0u;
 	const int c = (int)(blockIdx.x / (unsigned)g.CL);
@@ -977,8 +1026,11 @@ __global__ void __launch_bounds__(THREADS) bn_bwd_cluster_kernel(const T* __rest
 			}
 	}
 	}
-	block_sum2<THREADS>(s1, s2, red);
-	cluster_sum2(s1, s2, part, g.CL);
+	double d1 = s1, d2 = s2;
+	block_sum2_d<THREADS>(d1, d2, red);
+	cluster_sum2_d(d1, d2, part, g.CL);
+	s1 = (float)d1;
+	s2 = (float)d2;
 
 	const float count = (float)g.N * (float)g.S;
 	const float dsc = s2 * invstd;               // sum(dy * xhat)
