@@ -140,7 +140,7 @@ __host__ __device__ inline int bins_per_block(int vec, uint32_t S) { return (int
 // ------------------------------------------------------------------------------------------ forward statistics
 // sums[c] = { sum(x - pivot_c), sum((x - pivot_c)^2) } over the rows of this block
 template <typename T, int VEC>
-__global__ void __launch_bounds__(kThreads) bn_stats_kernel(const T* __restrict__ x, Slab g, float* __restrict__ sums)
+__global__ void __launch_bounds__(kThreads) bn_stats_kernel(const T* __restrict__ x, Slab g, float* __restrict__ sums, float* __restrict__ pivots)
 {
 	extern __shared__ float bins[];
 	const ItemRange ir = my_items(g);
@@ -163,6 +163,8 @@ __global__ void __launch_bounds__(kThreads) bn_stats_kernel(const T* __restrict_
 				pivot[e] = to_f<T>(x[(size_t)ch[e] * g.S]);
 				s1[e] = 0.0f;
 				s2[e] = 0.0f;
+				// the apply kernel takes the pivot from here, not from x: with y == x another CTA may have normalised that element already
+				if (active && rg == 0 && j + e == (uint32_t)ch[e] * g.S) pivots[ch[e]] = pivot[e];
 			}
 		}
 		if (!active) continue;
@@ -194,7 +196,8 @@ __global__ void __launch_bounds__(kThreads) bn_stats_kernel(const T* __restrict_
 // otherwise from the given mean / var (inference).
 template <typename T, int VEC, bool TRAIN>
 __global__ void __launch_bounds__(kThreads) bn_apply_kernel(const T* __restrict__ x, T* __restrict__ y, Slab g,
-															const float* __restrict__ sums, const float* __restrict__ scale,
+															const float* __restrict__ sums, const float* __restrict__ pivots,
+															const float* __restrict__ scale,
 															const float* __restrict__ bias, float* mean_io, float* var_io, float* save_mean,
 															float* save_invvar, float eps, float factor, float count, float* zero_ptr,
 															int zero_n)
@@ -218,7 +221,7 @@ __global__ void __launch_bounds__(kThreads) bn_apply_kernel(const T* __restrict_
 					const int c = (int)fdiv32(j + e, g.sdiv);
 					float mean, invstd;
 					if (TRAIN) {
-						const float pivot = to_f<T>(x[(size_t)c * g.S]);
+						const float pivot = pivots[c];
 						const float dmean = sums[2 * c] / count;
 						mean = pivot + dmean;
 						const float var = fmaxf(sums[2 * c + 1] / count - dmean * dmean, 0.0f);      // biased, used for normalisation
@@ -1206,6 +1209,7 @@ int launch_cluster(K kernel, const ClusterPlan& p, cudaStream_t s, Args... args)
 // Two [C][2] fp32 accumulator buffers, library-owned and used in stream order.  A pass accumulates into one of them and its
 // apply kernel clears what the previous pass left in the other, which the next pass will use.
 struct SumsPair {
+	float* pivots;       // [C] per-channel pivots, written by the statistics kernel (behind the two sums of every channel)
 	float* use;          // all zero over [0, C)
 	float* clear;        // to be cleared by this pass over [0, clear_n)
 	int clear_n;
@@ -1228,14 +1232,15 @@ bool acquire_sums(int64_t C, SumsPair& sp)
 		const int64_t want = C < 65536 ? 65536 : C + C / 2;
 		for (int i = 0; i < 2; i++) {
 			buf[i] = nullptr;
-			if (cudaMalloc((void**)&buf[i], (size_t)want * 2 * sizeof(float)) != cudaSuccess) { cap = 0; cudaGetLastError(); return false; }
-			cudaMemset(buf[i], 0, (size_t)want * 2 * sizeof(float));
+			if (cudaMalloc((void**)&buf[i], (size_t)want * 3 * sizeof(float)) != cudaSuccess) { cap = 0; cudaGetLastError(); return false; }
+			cudaMemset(buf[i], 0, (size_t)want * 3 * sizeof(float));
 			dirty[i] = 0;
 		}
 		cap = want;
 	}
 	const int other = 1 - cur;
 	sp.use = buf[cur];
+	sp.pivots = buf[cur] + 2 * cap;
 	sp.clear = buf[other];
 	sp.clear_n = (int)(dirty[other] * 2);
 	dirty[cur] = C;
@@ -1349,12 +1354,12 @@ int fwd_train(const void* x, void* y, int64_t N, int64_t C, int64_t S, const flo
 		const int64_t c1 = c0 + plan.slab_channels < C ? c0 + plan.slab_channels : C;
 		const Slab g = make_slab(plan, N, C, S, c0, c1);
 		if (plan.vec == V) {
-			PZ_BN_LAUNCH(V, (bn_stats_kernel<T, V>), bins_per_block(V, g.S) * 2 * sizeof(float), (const T*)x, g, sums);
-			PZ_BN_LAUNCH(V, (bn_apply_kernel<T, V, true>), 0, (const T*)x, (T*)y, g, sums, scale, bias, rm, rv, sm, siv, (float)eps,
+			PZ_BN_LAUNCH(V, (bn_stats_kernel<T, V>), bins_per_block(V, g.S) * 2 * sizeof(float), (const T*)x, g, sums, sp.pivots);
+			PZ_BN_LAUNCH(V, (bn_apply_kernel<T, V, true>), 0, (const T*)x, (T*)y, g, sums, sp.pivots, scale, bias, rm, rv, sm, siv, (float)eps,
 						 (float)factor, count, sp.clear, c0 == 0 ? sp.clear_n : 0);
 		} else {
-			PZ_BN_LAUNCH(1, (bn_stats_kernel<T, 1>), bins_per_block(1, g.S) * 2 * sizeof(float), (const T*)x, g, sums);
-			PZ_BN_LAUNCH(1, (bn_apply_kernel<T, 1, true>), 0, (const T*)x, (T*)y, g, sums, scale, bias, rm, rv, sm, siv, (float)eps,
+			PZ_BN_LAUNCH(1, (bn_stats_kernel<T, 1>), bins_per_block(1, g.S) * 2 * sizeof(float), (const T*)x, g, sums, sp.pivots);
+			PZ_BN_LAUNCH(1, (bn_apply_kernel<T, 1, true>), 0, (const T*)x, (T*)y, g, sums, sp.pivots, scale, bias, rm, rv, sm, siv, (float)eps,
 						 (float)factor, count, sp.clear, c0 == 0 ? sp.clear_n : 0);
 		}
 	}
@@ -1373,10 +1378,10 @@ int fwd_infer(const void* x, void* y, int64_t N, int64_t C, int64_t S, const flo
 	const Slab g = make_slab(plan, N, C, S, 0, C);
 	PzProfScope prof(PZ_PROF_BN_FWD, s, 0.0, 2.0 * (double)N * C * S * sizeof(T));
 	if (plan.vec == V)
-		PZ_BN_LAUNCH(V, (bn_apply_kernel<T, V, false>), 0, (const T*)x, (T*)y, g, nullptr, scale, bias, (float*)mean, (float*)var, nullptr,
+		PZ_BN_LAUNCH(V, (bn_apply_kernel<T, V, false>), 0, (const T*)x, (T*)y, g, nullptr, nullptr, scale, bias, (float*)mean, (float*)var, nullptr,
 					 nullptr, (float)eps, 0.0f, 1.0f, nullptr, 0);
 	else
-		PZ_BN_LAUNCH(1, (bn_apply_kernel<T, 1, false>), 0, (const T*)x, (T*)y, g, nullptr, scale, bias, (float*)mean, (float*)var, nullptr,
+		PZ_BN_LAUNCH(1, (bn_apply_kernel<T, 1, false>), 0, (const T*)x, (T*)y, g, nullptr, nullptr, scale, bias, (float*)mean, (float*)var, nullptr,
 					 nullptr, (float)eps, 0.0f, 1.0f, nullptr, 0);
 	PZ_LAUNCH_CHECK();
 	return PZ_OK;

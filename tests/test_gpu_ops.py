@@ -1426,3 +1426,25 @@ def test_relu_after_batchnorm_is_folded_into_the_pending_launch(bnd, shape):
 	mean, var = bnd.GPUArray.zeros((1, C, 1, 1), np.float32), G(bnd, np.ones((1, C, 1, 1), np.float32))
 	y, sm, siv = bnd.dnn.batchNormNd(gx, mean, var, G(bnd, scale), G(bnd, bias), 1e-5, 0.25, False)
 	assert np.array_equal(y.get().view(np.uint8), plain[0].view(np.uint8)) and driver.deferred is None
+
+
+def test_batchnorm_in_place_on_the_two_kernel_path(bnd):
+	"""planes too large for the shared-memory stash take the statistics + apply kernels; with out == data the apply kernel must not
+	rebuild the mean from an element another CTA has already normalised (the pivot travels through a side buffer)"""
+	shape = (64, 4, 112, 112)
+	rng = np.random.RandomState(12)
+	x = (rng.randn(*shape) * 1.5 + 2.0).astype(np.float32)
+	scale, bias = rng.randn(1, 4, 1, 1).astype(np.float32), rng.randn(1, 4, 1, 1).astype(np.float32)
+
+	def run(inplace):
+		gx = G(bnd, x)
+		mean, var = bnd.GPUArray.zeros((1, 4, 1, 1), np.float32), G(bnd, np.ones((1, 4, 1, 1), np.float32))
+		y, sm, siv = bnd.dnn.batchNormNd(gx, mean, var, G(bnd, scale), G(bnd, bias), 1e-5, 1.0, False, out=gx if inplace else None)
+		return y.get(), sm.get(), siv.get(), mean.get()
+
+	# (this path accumulates with atomics: runs agree to rounding, not bit for bit)
+	want, mu, inv, _, _ = ops.batchnorm_train(x, scale.ravel(), bias.ravel(), np.zeros(4), np.ones(4), 1e-5, 1.0)
+	for got in (run(False), run(True)):
+		assert relerr(got[0], want) < 2e-5
+		assert np.allclose(got[1].ravel(), mu, atol=1e-5) and np.allclose(got[2].ravel(), inv, rtol=1e-5)
+		assert np.allclose(got[3].ravel(), mu, atol=1e-5)                # factor 1: the running mean is the batch mean
