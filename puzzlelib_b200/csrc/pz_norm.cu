@@ -1313,7 +1313,7 @@ int fwd_train(const void* x, void* y, int64_t N, int64_t C, int64_t S, const flo
 {
 	constexpr int V = 16 / sizeof(T);
 	cudaStream_t s = pz_stream(stream);
-	PzProfScope prof(PZ_PROF_BN_FWD, s, 0.0, 2.0 * (double)N * C * S * sizeof(T));
+	PzProfScope prof(PZ_PROF_BN_FWD, s, 0.0, (z != nullptr ? 3.0 : 2.0) * (double)N * C * S * sizeof(T));      // + the folded ReLU's output
 	{
 		// one cluster per channel, the tensor crosses HBM once (see "cluster kernels").  In-place (y == x) is safe here: a CTA
 		// only rewrites planes it alone reads, and the pivot element is read by every CTA of the cluster before its barrier
