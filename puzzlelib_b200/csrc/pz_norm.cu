@@ -1313,18 +1313,19 @@ int fwd_train(const void* x, void* y, int64_t N, int64_t C, int64_t S, const flo
 {
 	constexpr int V = 16 / sizeof(T);
 	cudaStream_t s = pz_stream(stream);
-	PzProfScope prof(PZ_PROF_BN_FWD, s, 0.0, (z != nullptr ? 3.0 : 2.0) * (double)N * C * S * sizeof(T));      // + the folded ReLU's output
+	// one cluster per channel, the tensor crosses HBM once (see "cluster kernels").  In-place (y == x) is safe here: a CTA
+	// only rewrites planes it alone reads, and the pivot element is read by every CTA of the cluster before its barrier
+	const ClusterPlan cp = make_cluster_plan({x, y}, N, C, S, sizeof(T), 1);
+	const bool fold = cp.ok && z != nullptr && !cp.g.bulk_store && (uintptr_t)z % 16 == 0;      // the ReLU output rides on the store pass
+	PzProfScope prof(PZ_PROF_BN_FWD, s, 0.0, (fold ? 3.0 : 2.0) * (double)N * C * S * sizeof(T));
 	{
-		// one cluster per channel, the tensor crosses HBM once (see "cluster kernels").  In-place (y == x) is safe here: a CTA
-		// only rewrites planes it alone reads, and the pivot element is read by every CTA of the cluster before its barrier
-		const ClusterPlan cp = make_cluster_plan({x, y}, N, C, S, sizeof(T), 1);
 		if (cp.ok) {
 			// persistent variant: two stash buffers per CTA, one CTA per SM, as many clusters as the GPU can hold at once
 			// (measured SLOWER than the one-shot kernel on every ResNet-50 shape -- 64 x 256 x 55 x 55: 0.149 vs 0.129 ms, and much slower on
 			// small maps where a cluster's serial chain per channel dominates: profiles/r02_conv_epilogue_gather_experiments.md section 6;
 			// PZ_BN_PERSISTENT=1 enables it for experiments)
 			static const bool persistent_on = env_int("PZ_BN_PERSISTENT", 0) != 0;
-			if (persistent_on && z == nullptr && cp.bulk && 2 * cp.smem <= 220 * 1024) {
+			if (persistent_on && !fold && z == nullptr && cp.bulk && 2 * cp.smem <= 220 * 1024) {
 				ClusterPlan pp = cp;
 				pp.smem = 2 * cp.smem;
 				pp.threads = 512;
@@ -1337,7 +1338,7 @@ int fwd_train(const void* x, void* y, int64_t N, int64_t C, int64_t S, const flo
 				}
 			}
 			// the fused ReLU output rides on the plain-store phase 2 of the cluster kernel (16-byte aligned like x and y)
-			T* zz = (z != nullptr && !cp.g.bulk_store && (uintptr_t)z % 16 == 0) ? (T*)z : nullptr;
+			T* zz = fold ? (T*)z : nullptr;
 			if (fused) *fused = zz != nullptr;
 #define PZ_BN_FWD_CLUSTER(TH, BK) launch_cluster(bn_fwd_cluster_kernel<T, V, TH, BK>, cp, s, (const T*)x, (T*)y, zz, cp.g, scale, bias, rm, rv, sm, siv, (float)eps, (float)factor)
 			if (cp.threads == 512) return cp.bulk ? PZ_BN_FWD_CLUSTER(512, true) : PZ_BN_FWD_CLUSTER(512, false);
