@@ -303,6 +303,7 @@ class Device:
 		return Device(n.value)
 
 	def set(self):
+		flushDeferred()               # a pending launch belongs to the device that was current when it was held back
 		check(lib.pz_device_set(self.index))
 		return self
 
