@@ -349,6 +349,25 @@ void set_staged(Epilogue& E, int dtype)
 // operand of wgrad next to a tap-gathered x, and 1x1 wgrad over small planes), 2 = wherever it is legal (experiments).  Four times
 // fewer load instructions do NOT make the fprop / dgrad gather faster (28 x 28, 128 -> 512 channels: 0.043 -> 0.048 ms): the
 // gather is bound behind the LSU, not by issue (profiles/r02_conv_epilogue_gather_experiments.md).
+// PZ_TMA_WGRAD: 0 = producers gather every wgrad operand, 1 = both operands of a 1x1 / stride-1 wgrad over aligned planes come
+// through the copy engine (MODE_K_POS_TMA: 3-d tensor maps, no producer instructions), 2 (default) = also the dy operand next to a
+// tap-gathered x.  Measured (N = 64): 1x1 wgrad over 28 x 28 planes 0.052 -> 0.028 ms (4.6 TB/s), over 14 x 14 planes 0.040 -> 0.031 ms,
+// 3x3 wgrad 0.071 -> 0.060 / 0.080 -> 0.065 ms; ResNet-50 step 16.64 -> 15.99 ms.  The copy engine hands the tensor core raw float
+// bits -- the tf32 MMA ignores the low 13 mantissa bits -- where the producers round to nearest: a copied operand is truncated,
+// which shrinks the result by 3.5e-4 per copied operand on average (max error against a float64 contraction 8.5e-4 / 4.8e-4 of
+// the largest element with two / one copied operands, 3.3e-4 with none; tools/check_tma_wgrad.py).
+int tma_wgrad_level()
+{
+	static const int level = [] { const char* e = getenv("PZ_TMA_WGRAD"); return e ? atoi(e) : 2; }();
+	return level;
+}
+// planes of `chans` channels per image, dense (N, chans, plane): tile rows must not run past the channels
+bool kpos_tma_ok(const Operand& op, const void* ptr, int chans, int rows, int groups, int dtype)
+{
+	return dtype == PZ_F32 && groups == 1 && op.plane % 4 == 0 && op.plane >= 32 && chans % rows == 0 && ((uintptr_t)ptr & 15) == 0 &&
+		   op.rs0 == op.plane && op.ks0 == (long long)chans * op.plane;
+}
+
 int vec_gather_level()
 {
 	static const int level = [] { const char* e = getenv("PZ_VEC_GATHER"); return e ? atoi(e) : 1; }();
@@ -811,7 +830,17 @@ int pz_conv2d_wgrad(int dtype, const pz_conv2d_desc* d, const void* x, const voi
 		const bool vec_x = dense_x && kpos_vec_ok(A, dtype) && (PQ < 512 || vec_gather_level() >= 2);    // 28 x 28 planes: measured slower
 		const int amode = dense_x ? (vec_x && vec_dy ? MODE_K_POS_VEC : MODE_K_POS_DENSE) : MODE_K_POS_TAP;
 		const int bmode = vec_dy && (!dense_x || vec_x) ? MODE_K_POS_VEC : MODE_K_POS_DENSE;
-		st = launch(p, dtype, bn, amode, bmode, !dense_x && RS > 31, g.G, nullptr, pz_stream(stream));
+		// operands over 16-byte aligned planes can come through the copy engine instead (3-d tensor maps, no producer instructions)
+		const int tl = tma_wgrad_level();
+		const bool tma_dy = tl >= 1 && kpos_tma_ok(B, dy, g.K, bn, g.G, dtype);
+		const bool tma_x = tma_dy && dense_x && kpos_tma_ok(A, x, g.C, BM, g.G, dtype);
+		const PlaneTma px{x, PQ, g.C, g.N}, pdy{dy, PQ, g.K, g.N};
+		if (tma_x)
+			st = launch(p, dtype, bn, MODE_K_POS_TMA, MODE_K_POS_TMA, false, g.G, nullptr, pz_stream(stream), &px, &pdy);
+		else if (tma_dy && !dense_x && tl >= 2 && RS <= 31)
+			st = launch(p, dtype, bn, MODE_K_POS_TAP, MODE_K_POS_TMA, false, g.G, nullptr, pz_stream(stream), nullptr, &pdy);
+		else
+			st = launch(p, dtype, bn, amode, bmode, !dense_x && RS > 31, g.G, nullptr, pz_stream(stream));
 	}
 	if (st != PZ_OK || !acc) return st;
 	return finalize16(dtype, dw, wcount, acc, 1, wcount, beta, pz_stream(stream));

@@ -74,7 +74,7 @@ int pick_bn(int n, long long m_rows, int kblocks, int groups, int max_bn)
 float* scratch(size_t bytes) { return (float*)pz_scratch(bytes); }
 
 template <int BN, int AM, int BMODE, bool CDIV, bool H16>
-static int launch_inst(const GemmParams& p, const CUtensorMap& tmap, int grid, cudaStream_t stream)
+static int launch_inst(const GemmParams& p, const CUtensorMap& tmap, const CUtensorMap& tmapA, int grid, cudaStream_t stream)
 {
 	auto kern = umma_gemm_kernel<BN, AM, BMODE, CDIV, H16>;
 	static bool configured = false;
@@ -85,10 +85,47 @@ static int launch_inst(const GemmParams& p, const CUtensorMap& tmap, int grid, c
 	{
 		const bool hbm = p.alg_bytes > 0.0 && p.alg_flops / p.alg_bytes < kPzRidgeFlopPerByte;
 		PzProfScope prof(hbm ? PZ_PROF_GEMM_HBM : PZ_PROF_GEMM, stream, p.alg_flops, p.alg_bytes);
-		kern<<<grid, NTHREADS, Cfg<BN>::SMEM_BYTES, stream>>>(p, tmap);
+		kern<<<grid, NTHREADS, Cfg<BN>::SMEM_BYTES, stream>>>(p, tmap, tmapA);
 	}
 	pz_count_launch(1);
 	PZ_LAUNCH_CHECK();
+	return PZ_OK;
+}
+
+typedef CUresult (*TmapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+								 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+								 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TmapEncodeFn tmap_encoder()
+{
+	// resolved through the runtime so that the library has no link-time dependency on libcuda.so
+	static TmapEncodeFn encode = nullptr;
+	if (!encode) {
+		void* fn = nullptr;
+		cudaDriverEntryPointQueryResult qres;
+		if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+			encode = (TmapEncodeFn)fn;
+	}
+	return encode;
+}
+
+// 3-d tensor map over float planes [images][chans][plane] (MODE_K_POS_TMA): box = 32 positions x `rows` channels of one image,
+// 128-byte swizzle -- the K-major tile the MMA descriptors expect, positions past the plane read as zero
+static int make_plane_tmap(CUtensorMap* tmap, const PlaneTma& t, int rows)
+{
+	PZ_REQUIRE(t.ptr != nullptr && ((uintptr_t)t.ptr & 15) == 0 && t.plane % 4 == 0 && t.chans >= rows && rows <= 256, "bad plane TMA source");
+	TmapEncodeFn encode = tmap_encoder();
+	PZ_REQUIRE(encode != nullptr, "cuTensorMapEncodeTiled is not available in this driver");
+	cuuint64_t dims[3] = {(cuuint64_t)t.plane, (cuuint64_t)t.chans, (cuuint64_t)t.images};
+	cuuint64_t strides[2] = {(cuuint64_t)t.plane * 4, (cuuint64_t)t.plane * (cuuint64_t)t.chans * 4};
+	cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)rows, 1};
+	cuuint32_t estr[3] = {1, 1, 1};
+	memset(tmap, 0, sizeof(*tmap));
+	CUresult r = encode(tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)t.ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+						CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	if (r != CUDA_SUCCESS) {
+		pz_set_error(PZ_ERR_CUDA, "cuTensorMapEncodeTiled (planes) failed (%d)", (int)r);
+		return PZ_ERR_CUDA;
+	}
 	return PZ_OK;
 }
 
@@ -104,19 +141,8 @@ int make_filter_tmap(CUtensorMap* tmap, int dtype, const TmaSource& tma, int bn)
 	cuuint32_t estr[2] = {1, 1};
 	const CUtensorMapDataType dt = dtype == PZ_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
 								   : (dtype == PZ_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
-	// resolved through the runtime so that the library has no link-time dependency on libcuda.so (it must load, and
-	// export its symbols, on a machine without a driver)
-	typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-								 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-								 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-	static EncodeFn encode = nullptr;
-	if (!encode) {
-		void* fn = nullptr;
-		cudaDriverEntryPointQueryResult qres;
-		PZ_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-		PZ_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled is not available in this driver");
-		encode = (EncodeFn)fn;
-	}
+	TmapEncodeFn encode = tmap_encoder();      // (the library must load, and export its symbols, on a machine without a driver)
+	PZ_REQUIRE(encode != nullptr, "cuTensorMapEncodeTiled is not available in this driver");
 	memset(tmap, 0, sizeof(*tmap));
 	CUresult r = encode(tmap, dt, 2, (void*)tma.ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
 						CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -127,7 +153,8 @@ int make_filter_tmap(CUtensorMap* tmap, int dtype, const TmaSource& tma, int bn)
 	return PZ_OK;
 }
 
-int launch(GemmParams& p, int dtype, int bn, int amode, int bmode, bool cdiv, int groups, const TmaSource* tma, cudaStream_t stream)
+int launch(GemmParams& p, int dtype, int bn, int amode, int bmode, bool cdiv, int groups, const TmaSource* tma, cudaStream_t stream,
+		   const PlaneTma* planeA, const PlaneTma* planeB)
 {
 	const int M = p.E.M, N = p.E.N;
 	if (M <= 0 || N <= 0) return PZ_OK;
@@ -157,10 +184,25 @@ int launch(GemmParams& p, int dtype, int bn, int amode, int bmode, bool cdiv, in
 		int st = make_filter_tmap(&tmap, dtype, *tma, bn);
 		if (st != PZ_OK) return st;
 	}
+	alignas(64) CUtensorMap tmapA;
+	memset(&tmapA, 0, sizeof(tmapA));
+	if (amode == MODE_K_POS_TMA || bmode == MODE_K_POS_TMA) {
+		PZ_REQUIRE(dtype == PZ_F32 && groups == 1, "plane TMA operands: float tensors, one group");
+		if (amode == MODE_K_POS_TMA) {
+			PZ_REQUIRE(planeA != nullptr, "bad plane TMA source");
+			int st = make_plane_tmap(&tmapA, *planeA, BM);
+			if (st != PZ_OK) return st;
+		}
+		if (bmode == MODE_K_POS_TMA) {
+			PZ_REQUIRE(planeB != nullptr, "bad plane TMA source");
+			int st = make_plane_tmap(&tmap, *planeB, bn);
+			if (st != PZ_OK) return st;
+		}
+	}
 
 #define PZ_INST(BNV, AMV, BMV, CD, H)                                                  \
 	if (bn == BNV && amode == AMV && bmode == BMV && cdiv == CD && h16 == H)           \
-		return launch_inst<BNV, AMV, BMV, CD, H>(p, tmap, grid, stream);
+		return launch_inst<BNV, AMV, BMV, CD, H>(p, tmap, tmapA, grid, stream);
 #define PZ_INST_BN(AMV, BMV, CD, H) PZ_INST(64, AMV, BMV, CD, H) PZ_INST(128, AMV, BMV, CD, H)
 #define PZ_INST_BN3(AMV, BMV, CD, H) PZ_INST_BN(AMV, BMV, CD, H) PZ_INST(256, AMV, BMV, CD, H)
 	// ---- float32 storage, tf32 products
@@ -181,6 +223,8 @@ int launch(GemmParams& p, int dtype, int bn, int amode, int bmode, bool cdiv, in
 	PZ_INST_BN(MODE_K_POS_VEC, MODE_K_POS_VEC, false, false)   // wgrad of a 1x1 filter over 16-byte aligned planes
 	PZ_INST_BN(MODE_K_POS_TAP, MODE_K_POS_VEC, false, false)   // wgrad: dy planes 16-byte aligned
 	PZ_INST_BN(MODE_K_POS_TAP, MODE_K_POS_VEC, true, false)
+	PZ_INST_BN(MODE_K_POS_TMA, MODE_K_POS_TMA, false, false)   // wgrad of a 1x1 filter: both operands by the copy engine (3-d tensor maps)
+	PZ_INST_BN(MODE_K_POS_TAP, MODE_K_POS_TMA, false, false)   // wgrad: dy by the copy engine next to a tap-gathered x
 	// ---- half / bfloat16 storage
 	PZ_INST_BN3(MODE_MN_CHAN, MODE_TMA, false, true)
 	PZ_INST_BN3(MODE_MN_CHAN, MODE_TMA, true, true)

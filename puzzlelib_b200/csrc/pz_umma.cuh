@@ -116,7 +116,7 @@ __device__ __forceinline__ void split3(uint32_t x, const FastDiv& d12, const Fas
 // computed once, the per-element work is one predicated load + one tf32 rounding.
 enum { MODE_K_GENERAL = 0, MODE_K_SIMPLE = 1, MODE_MN_GENERAL = 2, MODE_MN_SIMPLE = 3, MODE_MN_TAP = 4, MODE_K_TAP = 5,
 	   MODE_K_DENSE = 6, MODE_TMA = 7, MODE_MN_CHAN = 8, MODE_K_POS_TAP = 9, MODE_K_POS_DENSE = 10, MODE_MN_VEC = 11,
-	   MODE_K_POS_VEC = 12 };
+	   MODE_K_POS_VEC = 12, MODE_K_POS_TMA = 13 };
 
 struct Operand {
 	const void* ptr;             // float or 16-bit (half / bfloat16) elements; all strides below are in ELEMENTS
@@ -1274,6 +1274,9 @@ template <int ROWS, bool WIDE> struct ProducerSel<ROWS, MODE_MN_TAP, WIDE, false
 template <int ROWS, bool WIDE> struct ProducerSel<ROWS, MODE_K_TAP, WIDE, false> { using type = KTapProducer<ROWS, WIDE>; };
 template <int ROWS, bool WIDE> struct ProducerSel<ROWS, MODE_K_DENSE, WIDE, false> { using type = KDenseProducer<ROWS>; };
 template <int ROWS, bool WIDE, bool H16> struct ProducerSel<ROWS, MODE_TMA, WIDE, H16> { using type = TmaProducer<ROWS>; };
+// MODE_K_POS_TMA: the KPosDense operand over 16-byte aligned planes, fetched by the copy engine through a 3-d tensor map
+// (positions, channels, images): one box of 32 positions x ROWS channels of one image per k-block, zero-filled past the plane
+template <int ROWS, bool WIDE> struct ProducerSel<ROWS, MODE_K_POS_TMA, WIDE, false> { using type = TmaProducer<ROWS>; };
 template <int ROWS, bool WIDE> struct ProducerSel<ROWS, MODE_MN_CHAN, WIDE, false> { using type = MnChanProducer<ROWS, WIDE>; };
 template <int ROWS, bool WIDE> struct ProducerSel<ROWS, MODE_K_POS_TAP, WIDE, false> { using type = KPosTapProducer<ROWS, WIDE>; };
 template <int ROWS, bool WIDE> struct ProducerSel<ROWS, MODE_K_POS_DENSE, WIDE, false> { using type = KPosDenseProducer<ROWS>; };
@@ -1331,6 +1334,14 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, int 
 	asm volatile(
 		"cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
 		::"r"(dst), "l"((unsigned long long)tmap), "r"(c0), "r"(c1), "r"(bar)
+		: "memory");
+}
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, int c0, int c1, int c2, uint32_t bar)
+{
+	asm volatile(
+		"cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+		::"r"(dst), "l"((unsigned long long)tmap), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
 		: "memory");
 }
 
@@ -1489,12 +1500,15 @@ __device__ __forceinline__ void staged_tile(const Epilogue& E, int row0, int col
 
 // ------------------------------------------------------------------------------------------ the kernel
 template <int BN, int AMODE, int BMODE, bool CDIV, bool H16>
-__global__ void __launch_bounds__(NTHREADS, 1) umma_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ CUtensorMap tmapB)
+__global__ void __launch_bounds__(NTHREADS, 1) umma_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ CUtensorMap tmapB,
+																const __grid_constant__ CUtensorMap tmapA)
 {
 	using C = Cfg<BN>;
 	using EL = typename std::conditional<H16, uint16_t, float>::type;      // operand element as the producers see it
 	constexpr int BKE = H16 ? BK16 : BK;                                   // elements per k-block (one 128-byte row)
 	constexpr bool B_TMA = BMODE == MODE_TMA;
+	constexpr bool A_KPT = AMODE == MODE_K_POS_TMA, B_KPT = BMODE == MODE_K_POS_TMA;   // plane operands through the copy engine
+	static_assert(!(A_KPT || B_KPT) || !H16, "MODE_K_POS_TMA: float tensors only");
 	extern __shared__ uint8_t smem_raw[];
 	const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
 	const uint32_t tables = smem0 + C::STAGES * C::STAGE_BYTES;
@@ -1510,7 +1524,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) umma_gemm_kernel(const __grid_con
 	if (warp == MMA_WARP) {
 		if (lane == 0) {
 			for (int s = 0; s < C::STAGES; s++) {
-				mbar_init(bar_full + 8 * s, NPROD_WARPS + (B_TMA ? 1 : 0));
+				mbar_init(bar_full + 8 * s, NPROD_WARPS + (B_TMA ? 1 : 0) + (A_KPT ? 1 : 0) + (B_KPT ? 1 : 0));
 				mbar_init(bar_empty + 8 * s, 1);
 			}
 			for (int a = 0; a < 2; a++) {
@@ -1600,6 +1614,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) umma_gemm_kernel(const __grid_con
 					else {
 						mbar_arrive_expect_tx(bar_full + 8 * stage, BN * 128);
 						tma_load_2d(tileA + BM * 128, &tmapB, lkb * BKE, lw.group * p.tma_rows_per_group + lw.n_tile * BN, bar_full + 8 * stage);
+					}
+				}
+			}
+			if (A_KPT || B_KPT) {
+				if (gw == 0 && lane == 0) {
+					// k-block -> (image, first position); rows = channels of the (only) group
+					const uint32_t img = fdiv((uint32_t)lkb, p.A.kbdiv);
+					const int pos = (int)((uint32_t)lkb - img * p.A.kbdiv.d) * BKE;
+					if (A_KPT) {
+						mbar_arrive_expect_tx(bar_full + 8 * stage, BM * 128);
+						tma_load_3d(tileA, &tmapA, pos, lw.m_tile * BM, (int)img, bar_full + 8 * stage);
+					}
+					if (B_KPT) {
+						mbar_arrive_expect_tx(bar_full + 8 * stage, BN * 128);
+						tma_load_3d(tileA + BM * 128, &tmapB, pos, lw.n_tile * BN, (int)img, bar_full + 8 * stage);
 					}
 				}
 			}
@@ -1750,7 +1779,13 @@ struct TmaSource {
 	long long rows, kpad;
 };
 // dtype: PZ_F32 (tf32 products), PZ_F16 or PZ_BF16 -- the element type of both operands
-int launch(GemmParams& p, int dtype, int bn, int amode, int bmode, bool cdiv, int groups, const TmaSource* tma, cudaStream_t stream);
+// MODE_K_POS_TMA operand: float planes [images][chans][plane], plane % 4 == 0, 16-byte aligned base, chans % tile rows == 0
+struct PlaneTma {
+	const void* ptr;
+	long long plane, chans, images;
+};
+int launch(GemmParams& p, int dtype, int bn, int amode, int bmode, bool cdiv, int groups, const TmaSource* tma, cudaStream_t stream,
+		   const PlaneTma* planeA = nullptr, const PlaneTma* planeB = nullptr);
 inline int elems_per_kblock(int dtype) { return dtype == PZ_F32 ? BK : BK16; }
 // ---- halo path (pz_halo.cu): stride-1 R x S convolution with the activation operand staged once per channel block
 struct HaloGeometry {
