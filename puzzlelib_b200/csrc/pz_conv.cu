@@ -364,8 +364,32 @@ int tma_wgrad_level()
 // planes of `chans` channels per image, dense (N, chans, plane): tile rows must not run past the channels
 bool kpos_tma_ok(const Operand& op, const void* ptr, int chans, int rows, int groups, int dtype)
 {
-	return dtype == PZ_F32 && groups == 1 && op.plane % 4 == 0 && op.plane >= 32 && chans % rows == 0 && ((uintptr_t)ptr & 15) == 0 &&
+	const int es = dtype == PZ_F32 ? 4 : 2;
+	return groups == 1 && (op.plane * es) % 16 == 0 && op.plane >= elems_per_kblock(dtype) && chans % rows == 0 && ((uintptr_t)ptr & 15) == 0 &&
 		   op.rs0 == op.plane && op.ks0 == (long long)chans * op.plane;
+}
+
+// PZ_TMA_FPROP: the activation operand of 1x1 / stride-1 fprop and dgrad over dense, 16-byte aligned planes comes through the copy
+// engine in its memory order and is multiplied through an MN-major descriptor (MODE_MN_TMA).  0 = off, 1 (default) = planes of at
+// least 512 positions, 2 = every legal plane.  The operand is truncated to tf32 by the tensor core (see PZ_TMA_WGRAD; max error
+// against a float64 contraction 6.6e-4 of the largest element, 3.8e-4 with the rounding producers).  Row tiles are per image
+// there, so 14 x 14 planes fill 196 of 256 rows and lose what the copy engine gains: ResNet-50 step 15.91 (off) / 15.80 (1) /
+// 15.84 ms (2), family of the 1x1 convolutions 5.12 / 5.01 / 5.05 ms (profiles/r02_tma_operands.txt).
+int tma_fprop_level()
+{
+	static const int level = [] { const char* e = getenv("PZ_TMA_FPROP"); return e ? atoi(e) : 1; }();
+	return level;
+}
+bool mn_tma_ok(const Operand& A, const Epilogue& E, int groups, int dtype)
+{
+	const int lvl = tma_fprop_level();
+	const long long plane = A.rd12.d;
+	if (lvl < 1 || (lvl < 2 && plane < 512)) return false;
+	const bool dense_out = E.ms2 == 1 && (E.md2.d == 0 || (long long)E.ms1 == (long long)E.md2.d) && (long long)E.md12.d == plane && !E.c2i &&
+						   E.bias_mode != 2 && E.out_kind == OUT_F32;
+	return dtype == PZ_F32 && groups == 1 && dense_out && A.R == 1 && A.S == 1 && A.ah == 1 && A.aw == 1 && A.ch == 0 && A.cw == 0 && A.cdh == 1 &&
+		   A.cdw == 1 && (long long)A.H * A.W == plane && A.Wd == A.W && (int)A.rd2.d == A.W && plane % 4 == 0 && plane >= 32 &&
+		   A.chans % 32 == 0 && A.ks0 == plane && (long long)A.rs0 == (long long)A.chans * plane && ((uintptr_t)A.ptr & 15) == 0;
 }
 
 int vec_gather_level()
@@ -487,6 +511,10 @@ int pz_conv2d_fprop(int dtype, const pz_conv2d_desc* d, const void* x, const voi
 	}
 	// the table-driven tap producer exists for float only; 16-bit tensors with very few channels take the general gather
 	int amode = chan ? MODE_MN_CHAN : (fast && !h16 ? MODE_MN_TAP : MODE_MN_GENERAL);
+	if (amode == MODE_MN_CHAN && mn_tma_ok(A, E, g.G, dtype)) {
+		const PlaneTma px{x, PQ, g.C, g.N};
+		return launch(p, dtype, bn, MODE_MN_TMA, MODE_TMA, false, g.G, &tsrc, pz_stream(stream), &px);
+	}
 	if (amode == MODE_MN_CHAN && mn_vec_ok(A, dtype)) amode = MODE_MN_VEC;
 	set_staged(E, dtype);
 	return launch(p, dtype, bn, amode, MODE_TMA, amode == MODE_MN_GENERAL ? false : RS > 31, g.G, &tsrc, pz_stream(stream));
@@ -624,6 +652,10 @@ int pz_conv2d_dgrad(int dtype, const pz_conv2d_desc* d, const void* dy, const vo
 		}
 		const bool cdiv = mode == 2 ? strided : Rc * Sc > 31;
 		int amode = mode == 2 ? MODE_MN_GENERAL : (chan ? MODE_MN_CHAN : MODE_MN_TAP);
+		if (amode == MODE_MN_CHAN && a_h == 0 && a_w == 0 && csh == 1 && csw == 1 && mn_tma_ok(QA, q.E, g.G, dtype)) {
+			const PlaneTma pdy{dy, PQ, g.K, g.N};
+			return launch(q, dtype, bn, MODE_MN_TMA, MODE_TMA, false, g.G, &tsrc, pz_stream(stream), &pdy);
+		}
 		if (amode == MODE_MN_CHAN && mn_vec_ok(QA, dtype)) amode = MODE_MN_VEC;
 		set_staged(q.E, dtype);
 		return launch(q, dtype, bn, amode, MODE_TMA, cdiv, g.G, &tsrc, pz_stream(stream));

@@ -110,18 +110,23 @@ static TmapEncodeFn tmap_encoder()
 
 // 3-d tensor map over float planes [images][chans][plane] (MODE_K_POS_TMA): box = 32 positions x `rows` channels of one image,
 // 128-byte swizzle -- the K-major tile the MMA descriptors expect, positions past the plane read as zero
-static int make_plane_tmap(CUtensorMap* tmap, const PlaneTma& t, int rows)
+static int make_plane_tmap(CUtensorMap* tmap, int dtype, const PlaneTma& t, int rows, bool atom32 = false)
 {
-	PZ_REQUIRE(t.ptr != nullptr && ((uintptr_t)t.ptr & 15) == 0 && t.plane % 4 == 0 && t.chans >= rows && rows <= 256, "bad plane TMA source");
+	const size_t es = dtype == PZ_F32 ? 4 : 2;
+	const CUtensorMapDataType dt = dtype == PZ_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+								   : (dtype == PZ_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+	PZ_REQUIRE(t.ptr != nullptr && ((uintptr_t)t.ptr & 15) == 0 && (t.plane * es) % 16 == 0 && t.chans >= rows && rows <= 256, "bad plane TMA source");
 	TmapEncodeFn encode = tmap_encoder();
 	PZ_REQUIRE(encode != nullptr, "cuTensorMapEncodeTiled is not available in this driver");
 	cuuint64_t dims[3] = {(cuuint64_t)t.plane, (cuuint64_t)t.chans, (cuuint64_t)t.images};
-	cuuint64_t strides[2] = {(cuuint64_t)t.plane * 4, (cuuint64_t)t.plane * (cuuint64_t)t.chans * 4};
-	cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)rows, 1};
+	cuuint64_t strides[2] = {(cuuint64_t)t.plane * es, (cuuint64_t)t.plane * (cuuint64_t)t.chans * es};
+	cuuint32_t box[3] = {(cuuint32_t)elems_per_kblock(dtype), (cuuint32_t)rows, 1};
 	cuuint32_t estr[3] = {1, 1, 1};
 	memset(tmap, 0, sizeof(*tmap));
-	CUresult r = encode(tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)t.ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-						CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	// atom32: 32-byte chunks swizzled inside the 128-byte rows (the layout of an MN-major tf32 MMA operand)
+	CUresult r = encode(tmap, dt, 3, (void*)t.ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+						atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+						CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 	if (r != CUDA_SUCCESS) {
 		pz_set_error(PZ_ERR_CUDA, "cuTensorMapEncodeTiled (planes) failed (%d)", (int)r);
 		return PZ_ERR_CUDA;
@@ -168,6 +173,17 @@ int launch(GemmParams& p, int dtype, int bn, int amode, int bmode, bool cdiv, in
 		p.debug_skip = skip;
 	}
 	p.tiles_m = (int)pz_cdiv(M, BM);
+	p.img_tiles = 0;
+	p.fd_img_tiles = make_fastdiv(1);
+	if (amode == MODE_MN_TMA) {
+		// row tiles that do not straddle images (the boxes of the activation tensor map are per image)
+		PZ_REQUIRE(planeA != nullptr && planeA->plane * planeA->images == M && dtype == PZ_F32 && groups == 1 && p.E.md12.d == (uint32_t)planeA->plane,
+				   "bad MN-major TMA operand");
+		p.img_tiles = (int)pz_cdiv(planeA->plane, BM);
+		p.fd_img_tiles = make_fastdiv((uint32_t)p.img_tiles);
+		PZ_REQUIRE(planeA->images * (long long)p.img_tiles < (1ll << 31), "tile grid too large");
+		p.tiles_m = (int)(planeA->images * p.img_tiles);
+	}
 	p.tiles_n = (int)pz_cdiv(N, bn);
 	p.groups = groups;
 	p.fd_tiles_n = make_fastdiv((uint32_t)p.tiles_n);
@@ -186,16 +202,20 @@ int launch(GemmParams& p, int dtype, int bn, int amode, int bmode, bool cdiv, in
 	}
 	alignas(64) CUtensorMap tmapA;
 	memset(&tmapA, 0, sizeof(tmapA));
+	if (amode == MODE_MN_TMA) {
+		int st = make_plane_tmap(&tmapA, dtype, *planeA, BK, true);
+		if (st != PZ_OK) return st;
+	}
 	if (amode == MODE_K_POS_TMA || bmode == MODE_K_POS_TMA) {
-		PZ_REQUIRE(dtype == PZ_F32 && groups == 1, "plane TMA operands: float tensors, one group");
+		PZ_REQUIRE(groups == 1, "plane TMA operands: one group");
 		if (amode == MODE_K_POS_TMA) {
 			PZ_REQUIRE(planeA != nullptr, "bad plane TMA source");
-			int st = make_plane_tmap(&tmapA, *planeA, BM);
+			int st = make_plane_tmap(&tmapA, dtype, *planeA, BM);
 			if (st != PZ_OK) return st;
 		}
 		if (bmode == MODE_K_POS_TMA) {
 			PZ_REQUIRE(planeB != nullptr, "bad plane TMA source");
-			int st = make_plane_tmap(&tmap, *planeB, bn);
+			int st = make_plane_tmap(&tmap, dtype, *planeB, bn);
 			if (st != PZ_OK) return st;
 		}
 	}
@@ -223,6 +243,7 @@ int launch(GemmParams& p, int dtype, int bn, int amode, int bmode, bool cdiv, in
 	PZ_INST_BN(MODE_K_POS_VEC, MODE_K_POS_VEC, false, false)   // wgrad of a 1x1 filter over 16-byte aligned planes
 	PZ_INST_BN(MODE_K_POS_TAP, MODE_K_POS_VEC, false, false)   // wgrad: dy planes 16-byte aligned
 	PZ_INST_BN(MODE_K_POS_TAP, MODE_K_POS_VEC, true, false)
+	PZ_INST_BN3(MODE_MN_TMA, MODE_TMA, false, false)           // 1x1 fprop / dgrad over 16-byte aligned planes: MN-major A by the copy engine
 	PZ_INST_BN(MODE_K_POS_TMA, MODE_K_POS_TMA, false, false)   // wgrad of a 1x1 filter: both operands by the copy engine (3-d tensor maps)
 	PZ_INST_BN(MODE_K_POS_TAP, MODE_K_POS_TMA, false, false)   // wgrad: dy by the copy engine next to a tap-gathered x
 	// ---- half / bfloat16 storage
@@ -236,6 +257,8 @@ int launch(GemmParams& p, int dtype, int bn, int amode, int bmode, bool cdiv, in
 	PZ_INST_BN(MODE_K_POS_TAP, MODE_K_POS_DENSE, false, true)
 	PZ_INST_BN(MODE_K_POS_TAP, MODE_K_POS_DENSE, true, true)
 	PZ_INST_BN(MODE_K_POS_DENSE, MODE_K_POS_DENSE, false, true)
+	PZ_INST_BN(MODE_K_POS_TMA, MODE_K_POS_TMA, false, true)
+	PZ_INST_BN(MODE_K_POS_TAP, MODE_K_POS_TMA, false, true)
 #undef PZ_INST_BN3
 #undef PZ_INST_BN
 #undef PZ_INST

@@ -116,7 +116,7 @@ __device__ __forceinline__ void split3(uint32_t x, const FastDiv& d12, const Fas
 // computed once, the per-element work is one predicated load + one tf32 rounding.
 enum { MODE_K_GENERAL = 0, MODE_K_SIMPLE = 1, MODE_MN_GENERAL = 2, MODE_MN_SIMPLE = 3, MODE_MN_TAP = 4, MODE_K_TAP = 5,
 	   MODE_K_DENSE = 6, MODE_TMA = 7, MODE_MN_CHAN = 8, MODE_K_POS_TAP = 9, MODE_K_POS_DENSE = 10, MODE_MN_VEC = 11,
-	   MODE_K_POS_VEC = 12, MODE_K_POS_TMA = 13 };
+	   MODE_K_POS_VEC = 12, MODE_K_POS_TMA = 13, MODE_MN_TMA = 14 };
 
 struct Operand {
 	const void* ptr;             // float or 16-bit (half / bfloat16) elements; all strides below are in ELEMENTS
@@ -170,6 +170,9 @@ struct GemmParams {
 	FastDiv fd_tiles_n, fd_tiles_m, fd_splits;   // the same counts as magic-number divisors (the decode runs per tile per warp)
 	int tma_rows_per_group;      // MODE_TMA: row offset of group g in the prepared filter = g * tma_rows_per_group
 	int ab_bf16;                 // 16-bit operands: 0 = half, 1 = bfloat16 (selects the tcgen05 input format)
+	// MODE_MN_TMA: row tiles do not straddle images: m_tile = image * img_tiles + block of BM positions of that image
+	int img_tiles;
+	FastDiv fd_img_tiles;
 	int debug_skip;              // PZ_DEBUG_SKIP (timing experiments only, results are wrong): 1 no epilogue stores, 2 no filter TMA, 4 no MMAs
 	double alg_flops, alg_bytes; // host-side bookkeeping for the profiler (algorithmic work of this launch)
 };
@@ -296,7 +299,26 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr)
 	return d;
 }
 
+// MN-major descriptor of the A operand of MODE_MN_TMA.  The only shared-memory layout tcgen05 accepts for MN-major tf32 operands
+// is SWIZZLE_128B_BASE32B (layout type 1; cutlass/gemm/collective/builders/sm100_common.inl): an atom is 32 floats along M
+// (one 128-byte row) x 4 along K (rows 128 bytes apart, 512 bytes in all), the 32-byte chunks of a row XORed with the row
+// index mod 4 (Swizzle<2,5,2> on the byte address) -- what a tensor map with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B writes.
+// LBO = bytes between atoms along M, SBO = bytes between 4-k atoms.  The tile is four TMA boxes of [32 k][32 m] floats:
+// LBO = 4096 (next box), SBO = 512 (next 4 k of the same box); one MMA (8 k) reads two atoms along K.
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t smem_addr, int variant)
+{
+	const uint32_t sbo = (variant & 16) ? 1024 : 512, lbo = 4096;
+	uint64_t d = 0;
+	d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+	d |= (uint64_t)(((variant & 8) ? sbo : lbo) >> 4) << 16;
+	d |= (uint64_t)(((variant & 8) ? lbo : sbo) >> 4) << 32;
+	d |= (uint64_t)1 << 46;
+	d |= (uint64_t)1 << 61;                 // SWIZZLE_128B_BASE32B
+	return d;
+}
+
 // tcgen05 instruction descriptor (cute::UMMA::InstrDescriptor), kind::tf32, fp32 accumulate, both K-major
+// (bit 15 = A is MN-major, bit 16 = B is MN-major)
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int m, int n)
 {
 	return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
@@ -1276,7 +1298,11 @@ template <int ROWS, bool WIDE> struct ProducerSel<ROWS, MODE_K_DENSE, WIDE, fals
 template <int ROWS, bool WIDE, bool H16> struct ProducerSel<ROWS, MODE_TMA, WIDE, H16> { using type = TmaProducer<ROWS>; };
 // MODE_K_POS_TMA: the KPosDense operand over 16-byte aligned planes, fetched by the copy engine through a 3-d tensor map
 // (positions, channels, images): one box of 32 positions x ROWS channels of one image per k-block, zero-filled past the plane
-template <int ROWS, bool WIDE> struct ProducerSel<ROWS, MODE_K_POS_TMA, WIDE, false> { using type = TmaProducer<ROWS>; };
+template <int ROWS, bool WIDE, bool H16> struct ProducerSel<ROWS, MODE_K_POS_TMA, WIDE, H16> { using type = TmaProducer<ROWS>; };
+// MODE_MN_TMA: the activation operand of a 1x1 / stride-1 convolution over 16-byte aligned planes, fetched as it lies in memory
+// (positions contiguous = M-major) by four boxes of 32 positions x 32 channels per k-block; the MMA reads it through an MN-major
+// descriptor, so nobody transposes it
+template <int ROWS, bool WIDE> struct ProducerSel<ROWS, MODE_MN_TMA, WIDE, false> { using type = TmaProducer<ROWS>; };
 template <int ROWS, bool WIDE> struct ProducerSel<ROWS, MODE_MN_CHAN, WIDE, false> { using type = MnChanProducer<ROWS, WIDE>; };
 template <int ROWS, bool WIDE> struct ProducerSel<ROWS, MODE_K_POS_TAP, WIDE, false> { using type = KPosTapProducer<ROWS, WIDE>; };
 template <int ROWS, bool WIDE> struct ProducerSel<ROWS, MODE_K_POS_DENSE, WIDE, false> { using type = KPosDenseProducer<ROWS>; };
@@ -1508,7 +1534,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) umma_gemm_kernel(const __grid_con
 	constexpr int BKE = H16 ? BK16 : BK;                                   // elements per k-block (one 128-byte row)
 	constexpr bool B_TMA = BMODE == MODE_TMA;
 	constexpr bool A_KPT = AMODE == MODE_K_POS_TMA, B_KPT = BMODE == MODE_K_POS_TMA;   // plane operands through the copy engine
-	static_assert(!(A_KPT || B_KPT) || !H16, "MODE_K_POS_TMA: float tensors only");
+	constexpr bool A_MNT = AMODE == MODE_MN_TMA;
+	static_assert(!A_MNT || !H16, "MODE_MN_TMA: float tensors only");
 	extern __shared__ uint8_t smem_raw[];
 	const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
 	const uint32_t tables = smem0 + C::STAGES * C::STAGE_BYTES;
@@ -1524,7 +1551,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) umma_gemm_kernel(const __grid_con
 	if (warp == MMA_WARP) {
 		if (lane == 0) {
 			for (int s = 0; s < C::STAGES; s++) {
-				mbar_init(bar_full + 8 * s, NPROD_WARPS + (B_TMA ? 1 : 0) + (A_KPT ? 1 : 0) + (B_KPT ? 1 : 0));
+				mbar_init(bar_full + 8 * s, NPROD_WARPS + (B_TMA ? 1 : 0) + (A_KPT ? 1 : 0) + (B_KPT ? 1 : 0) + (A_MNT ? 1 : 0));
 				mbar_init(bar_empty + 8 * s, 1);
 			}
 			for (int a = 0; a < 2; a++) {
@@ -1632,6 +1659,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) umma_gemm_kernel(const __grid_con
 					}
 				}
 			}
+			if (A_MNT) {
+				if (gw == 0 && lane == 0) {
+					const uint32_t img = fdiv((uint32_t)lw.m_tile, p.fd_img_tiles);
+					const int pix0 = (int)((uint32_t)lw.m_tile - img * (uint32_t)p.img_tiles) * BM;
+					mbar_arrive_expect_tx(bar_full + 8 * stage, BM * 128);
+					#pragma unroll
+					for (int j = 0; j < BM / 32; j++)
+						tma_load_3d(tileA + j * 4096, &tmapA, pix0 + 32 * j, lkb * BKE, (int)img, bar_full + 8 * stage);
+				}
+			}
 			prodA.store(tileA, va);
 			prodB.store(tileA + BM * 128, vb);
 			PZ_TL(4)
@@ -1647,7 +1684,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) umma_gemm_kernel(const __grid_con
 		// ===================== MMA issuer (one thread of warp 16) =====================
 		setmaxnreg_dec<REGS_MMA>();
 		if (warp == MMA_WARP) {
-			const uint32_t idesc = H16 ? make_idesc_f16(BM, BN, p.ab_bf16) : make_idesc_tf32(BM, BN);
+			const uint32_t idesc = H16 ? make_idesc_f16(BM, BN, p.ab_bf16) : (make_idesc_tf32(BM, BN) | (A_MNT ? 1u << 15 : 0u));
 			int stage = 0;
 			uint32_t phase = 0;
 			int as = 0;
@@ -1667,12 +1704,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) umma_gemm_kernel(const __grid_con
 					PZ_TL(2)
 					if (lane == 0) {
 						const uint32_t tileA = smem0 + stage * C::STAGE_BYTES;
-						const uint64_t da = make_smem_desc(tileA), db = make_smem_desc(tileA + BM * 128);
+						const uint64_t da = A_MNT ? make_smem_desc_mn(tileA, p.debug_skip) : make_smem_desc(tileA);
+						const uint64_t db = make_smem_desc(tileA + BM * 128);
+						constexpr int ASTEP = A_MNT ? 64 : 2;       // MN-major A: the next 8 k are the next 1024 bytes
 						#pragma unroll
 						for (int kk = 0; kk < 4; kk++) {       // 8 tf32 / 16 halves = 32 bytes per MMA: +2 in the (addr >> 4) field
 							if (p.debug_skip & 4) continue;
 							if (H16) umma_f16(tmem_d, da + 2 * kk, db + 2 * kk, idesc, (kb > w.kb_begin || kk > 0) ? 1u : 0u);
-							else umma_tf32(tmem_d, da + 2 * kk, db + 2 * kk, idesc, (kb > w.kb_begin || kk > 0) ? 1u : 0u);
+							else umma_tf32(tmem_d, da + ASTEP * kk, db + 2 * kk, idesc, (kb > w.kb_begin || kk > 0) ? 1u : 0u);
 						}
 						umma_commit(bar_empty + 8 * stage);
 					}
@@ -1719,12 +1758,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) umma_gemm_kernel(const __grid_con
 		for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
 			const Work w = decode_work(p, work);
 			PZ_TL(1)
-			const int m = w.m_tile * BM + lg * 32 + lane;
-			const bool mvalid = m < E.M;
+			int m = w.m_tile * BM + lg * 32 + lane;
+			bool mvalid = m < E.M;
 			int m0, m1, m2;
-			split3((uint32_t)(mvalid ? m : 0), E.md12, E.md2, m0, m1, m2);
+			if (A_MNT) {
+				// image-aligned tiles over dense planes: row = (image, position), positions contiguous in the output too
+				const uint32_t img = fdiv((uint32_t)w.m_tile, p.fd_img_tiles);
+				const int pix = (int)((uint32_t)w.m_tile - img * (uint32_t)p.img_tiles) * BM + lg * 32 + lane;
+				mvalid = pix < (int)E.md12.d;
+				m0 = (int)img; m1 = 0; m2 = mvalid ? pix : 0;
+				m = (int)img * (int)E.md12.d + m2;
+			} else
+				split3((uint32_t)(mvalid ? m : 0), E.md12, E.md2, m0, m1, m2);
 			const int oes = E.out_kind == OUT_F32 ? 4 : 2;       // bytes per output / bias element
-			char* outp = (char*)E.out + ((long long)w.group * E.group_stride + ((long long)m0 * E.ms0 + (long long)m1 * E.ms1 + (long long)m2 * E.ms2)) * oes;
+			char* outp = (char*)E.out + ((long long)w.group * E.group_stride + ((long long)m0 * E.ms0 + (long long)m1 * E.ms1 + (long long)m2 * (A_MNT ? 1 : E.ms2))) * oes;
 			const char* biasp = E.bias ? (const char*)E.bias + (long long)w.group * E.bias_group_stride * oes : nullptr;
 			const bool addbias = !E.atomic || w.split == 0;      // with split-K the bias is contributed once
 			const float bias_m = (E.bias_mode == 2 && mvalid && addbias) ? out_load(biasp, (size_t)m, E.out_kind) : 0.0f;
@@ -1779,7 +1826,7 @@ struct TmaSource {
 	long long rows, kpad;
 };
 // dtype: PZ_F32 (tf32 products), PZ_F16 or PZ_BF16 -- the element type of both operands
-// MODE_K_POS_TMA operand: float planes [images][chans][plane], plane % 4 == 0, 16-byte aligned base, chans % tile rows == 0
+// MODE_K_POS_TMA / MODE_MN_TMA operand: planes [images][chans][plane] of whole 16-byte units on a 16-byte aligned base
 struct PlaneTma {
 	const void* ptr;
 	long long plane, chans, images;
