@@ -116,7 +116,7 @@ __device__ __forceinline__ void split3(uint32_t x, const FastDiv& d12, const Fas
 // computed once, the per-element work is one predicated load + one tf32 rounding.
 enum { MODE_K_GENERAL = 0, MODE_K_SIMPLE = 1, MODE_MN_GENERAL = 2, MODE_MN_SIMPLE = 3, MODE_MN_TAP = 4, MODE_K_TAP = 5,
 	   MODE_K_DENSE = 6, MODE_TMA = 7, MODE_MN_CHAN = 8, MODE_K_POS_TAP = 9, MODE_K_POS_DENSE = 10, MODE_MN_VEC = 11,
-	   MODE_K_POS_VEC = 12, MODE_K_POS_TMA = 13, MODE_MN_TMA = 14 };
+	   MODE_K_POS_VEC = 12, MODE_K_POS_TMA = 13, MODE_MN_TMA = 14, MODE_K_PATCH_TMA = 15 };
 
 struct Operand {
 	const void* ptr;             // float or 16-bit (half / bfloat16) elements; all strides below are in ELEMENTS
@@ -173,6 +173,12 @@ struct GemmParams {
 	// MODE_MN_TMA: row tiles do not straddle images: m_tile = image * img_tiles + block of BM positions of that image
 	int img_tiles;
 	FastDiv fd_img_tiles;
+	// MODE_K_PATCH_TMA (wgrad of a stride-1 filter, both operands through 4-d tensor maps): k-block = image * kbpi + patch, a patch
+	// is a run of one k-block of output columns of one output row (the box must fill its 128-byte swizzle span: a box of 32-byte rows
+	// overran its tile); A rows are ordered (tap, channel), a row tile is 128 / pt_cb boxes of pt_cb channels of one tap, fetched
+	// at the patch origin shifted by the tap (positions outside the image read as zero = padding)
+	int pt_cb, pt_chans, pt_taps, pt_padh, pt_padw;
+	FastDiv pt_fd_pw, pt_fd_chans, pt_fd_s;      // patches per output row, channels, filter width
 	int debug_skip;              // PZ_DEBUG_SKIP (timing experiments only, results are wrong): 1 no epilogue stores, 2 no filter TMA, 4 no MMAs
 	double alg_flops, alg_bytes; // host-side bookkeeping for the profiler (algorithmic work of this launch)
 };
@@ -1299,6 +1305,7 @@ template <int ROWS, bool WIDE, bool H16> struct ProducerSel<ROWS, MODE_TMA, WIDE
 // MODE_K_POS_TMA: the KPosDense operand over 16-byte aligned planes, fetched by the copy engine through a 3-d tensor map
 // (positions, channels, images): one box of 32 positions x ROWS channels of one image per k-block, zero-filled past the plane
 template <int ROWS, bool WIDE, bool H16> struct ProducerSel<ROWS, MODE_K_POS_TMA, WIDE, H16> { using type = TmaProducer<ROWS>; };
+template <int ROWS, bool WIDE, bool H16> struct ProducerSel<ROWS, MODE_K_PATCH_TMA, WIDE, H16> { using type = TmaProducer<ROWS>; };
 // MODE_MN_TMA: the activation operand of a 1x1 / stride-1 convolution over 16-byte aligned planes, fetched as it lies in memory
 // (positions contiguous = M-major) by four boxes of 32 positions x 32 channels per k-block; the MMA reads it through an MN-major
 // descriptor, so nobody transposes it
@@ -1368,6 +1375,14 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, int 
 	asm volatile(
 		"cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
 		::"r"(dst), "l"((unsigned long long)tmap), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+		: "memory");
+}
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, int c0, int c1, int c2, int c3, uint32_t bar)
+{
+	asm volatile(
+		"cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+		::"r"(dst), "l"((unsigned long long)tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
 		: "memory");
 }
 
@@ -1535,6 +1550,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) umma_gemm_kernel(const __grid_con
 	constexpr bool B_TMA = BMODE == MODE_TMA;
 	constexpr bool A_KPT = AMODE == MODE_K_POS_TMA, B_KPT = BMODE == MODE_K_POS_TMA;   // plane operands through the copy engine
 	constexpr bool A_MNT = AMODE == MODE_MN_TMA;
+	constexpr bool AB_PATCH = AMODE == MODE_K_PATCH_TMA;
+	static_assert(AB_PATCH == (BMODE == MODE_K_PATCH_TMA), "MODE_K_PATCH_TMA: both operands");
 	static_assert(!A_MNT || !H16, "MODE_MN_TMA: float tensors only");
 	extern __shared__ uint8_t smem_raw[];
 	const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -1551,7 +1568,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) umma_gemm_kernel(const __grid_con
 	if (warp == MMA_WARP) {
 		if (lane == 0) {
 			for (int s = 0; s < C::STAGES; s++) {
-				mbar_init(bar_full + 8 * s, NPROD_WARPS + (B_TMA ? 1 : 0) + (A_KPT ? 1 : 0) + (B_KPT ? 1 : 0) + (A_MNT ? 1 : 0));
+				mbar_init(bar_full + 8 * s, NPROD_WARPS + (B_TMA ? 1 : 0) + (A_KPT ? 1 : 0) + (B_KPT ? 1 : 0) + (A_MNT ? 1 : 0) + (AB_PATCH ? 1 : 0));
 				mbar_init(bar_empty + 8 * s, 1);
 			}
 			for (int a = 0; a < 2; a++) {
@@ -1657,6 +1674,32 @@ __global__ void __launch_bounds__(NTHREADS, 1) umma_gemm_kernel(const __grid_con
 						mbar_arrive_expect_tx(bar_full + 8 * stage, BN * 128);
 						tma_load_3d(tileA + BM * 128, &tmapB, pos, lw.n_tile * BN, (int)img, bar_full + 8 * stage);
 					}
+				}
+			}
+			if (AB_PATCH) {
+				if (gw == 0 && lane == 0) {
+					// k-block -> (image, output row, run of BKE output columns)
+					const uint32_t img = fdiv((uint32_t)lkb, p.A.kbdiv);
+					const uint32_t pb = (uint32_t)lkb - img * p.A.kbdiv.d;
+					const uint32_t py = fdiv(pb, p.pt_fd_pw);
+					const int w0 = (int)(pb - py * p.pt_fd_pw.d) * BKE, h0 = (int)py;
+					// boxes of this row tile: pt_cb channels of one tap each (the last tile may hold fewer)
+					int nbox = 0;
+					#pragma unroll 1
+					for (int i = 0; i < BM / p.pt_cb; i++)
+						if ((uint32_t)(lw.m_tile * BM + i * p.pt_cb) < (uint32_t)(p.pt_taps * p.pt_chans)) nbox++;
+					mbar_arrive_expect_tx(bar_full + 8 * stage, (uint32_t)(nbox * p.pt_cb + BN) * 128u);
+					#pragma unroll 1
+					for (int i = 0; i < nbox; i++) {
+						const uint32_t mrow = (uint32_t)(lw.m_tile * BM + i * p.pt_cb);
+						const uint32_t tap = fdiv(mrow, p.pt_fd_chans);
+						const int c0 = (int)(mrow - tap * p.pt_fd_chans.d);
+						const uint32_t r = fdiv(tap, p.pt_fd_s);
+						const int sx = (int)(tap - r * p.pt_fd_s.d);
+						tma_load_4d(tileA + (uint32_t)(i * p.pt_cb) * 128u, &tmapA, w0 + sx - p.pt_padw, h0 + (int)r - p.pt_padh, c0, (int)img,
+									bar_full + 8 * stage);
+					}
+					tma_load_4d(tileA + BM * 128, &tmapB, w0, h0, lw.n_tile * BN, (int)img, bar_full + 8 * stage);
 				}
 			}
 			if (A_MNT) {
@@ -1830,6 +1873,7 @@ struct TmaSource {
 struct PlaneTma {
 	const void* ptr;
 	long long plane, chans, images;
+	long long width = 0;         // MODE_K_PATCH_TMA: planes are (plane / width) rows of `width` elements
 };
 int launch(GemmParams& p, int dtype, int bn, int amode, int bmode, bool cdiv, int groups, const TmaSource* tma, cudaStream_t stream,
 		   const PlaneTma* planeA = nullptr, const PlaneTma* planeB = nullptr);
