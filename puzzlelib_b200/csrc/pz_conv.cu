@@ -369,6 +369,10 @@ bool kpos_tma_ok(const Operand& op, const void* ptr, int chans, int rows, int gr
 		   op.rs0 == op.plane && op.ks0 == (long long)chans * op.plane;
 }
 
+// What the copy engine cannot do for these tensors (tools/ubench/tma4d.cu, profiles/r02_tma_operands.txt): a box must start on a
+// 16-byte boundary of global memory, so the tap-shifted windows of a 3x3 filter (one element left / right in a row) cannot be
+// fetched as boxes of an NCHW tensor -- a coordinate of -1 or +1 along the row raises "illegal instruction"; shifts by whole rows
+// would be legal.  That is why only 1x1 filters (and the un-shifted dy operand of any wgrad) take the tensor-map paths.
 // PZ_TMA_FPROP: the activation operand of 1x1 / stride-1 fprop and dgrad over dense, 16-byte aligned planes comes through the copy
 // engine in its memory order and is multiplied through an MN-major descriptor (MODE_MN_TMA).  0 = off, 1 (default) = planes of at
 // least 512 positions, 2 = every legal plane.  The operand is truncated to tf32 by the tensor core (see PZ_TMA_WGRAD; max error
@@ -838,23 +842,6 @@ int pz_conv2d_wgrad(int dtype, const pz_conv2d_desc* d, const void* x, const voi
 	PZ_REQUIRE(fast || !h16, "conv2d wgrad: tensor too large for the 16-bit path");
 	p.kblocks = fast ? g.N * kbpi : (int)pz_cdiv(A.kdim, bke);
 	const int bn = g.Kg > 64 ? 128 : 64;        // the x operand is re-read once per column tile: keep those few
-	// stride-1 filters with several taps over rows of whole 16-byte units: both operands as patches through 4-d tensor maps
-	// (PZ_TMA_WGRAD >= 3).  A k-block is then a run of bke output columns of one output row, the rows are ordered (tap, channel).
-	const int es_ = dtype == PZ_F32 ? 4 : 2;
-	const bool patch = fast && tma_wgrad_level() >= 3 && !dense_x && RS > 1 && g.G == 1 && g.sh == 1 && g.sw == 1 && g.dh == 1 && g.dw == 1 &&
-					   (g.W * es_) % 16 == 0 && (g.Q * es_) % 16 == 0 && g.C % 64 == 0 && g.K % bn == 0 && ((uintptr_t)x & 15) == 0 &&
-					   ((uintptr_t)dy & 15) == 0;
-	if (patch) {
-		const int npw = (int)pz_cdiv(g.Q, bke), nph = g.P;
-		A.kbdiv = B.kbdiv = make_fastdiv((uint32_t)(npw * nph));
-		p.kblocks = g.N * npw * nph;
-		p.pt_cb = g.C % 128 == 0 ? 128 : 64;
-		p.pt_chans = g.C; p.pt_taps = RS; p.pt_padh = g.ph; p.pt_padw = g.pw;
-		p.pt_fd_pw = make_fastdiv((uint32_t)npw); p.pt_fd_chans = make_fastdiv((uint32_t)g.C); p.pt_fd_s = make_fastdiv((uint32_t)g.S);
-		// dw[k][c][tap] = column k * C*RS + c * RS + tap for row tap * C + c
-		E.md12 = make_fastdiv((uint32_t)g.C); E.md2 = make_fastdiv(1);
-		E.ms0 = 1; E.ms1 = RS; E.ms2 = 0;
-	}
 	set_splits(p, pz_cdiv(E.M, BM) * pz_cdiv(E.N, bn) * g.G, 8);
 	E.atomic = p.splits > 1;
 	set_alg(p, g, dtype);
@@ -884,10 +871,6 @@ int pz_conv2d_wgrad(int dtype, const pz_conv2d_desc* d, const void* x, const voi
 		const bool tma_dy = tl >= 1 && kpos_tma_ok(B, dy, g.K, bn, g.G, dtype);
 		const bool tma_x = tma_dy && dense_x && kpos_tma_ok(A, x, g.C, BM, g.G, dtype);
 		const PlaneTma px{x, PQ, g.C, g.N}, pdy{dy, PQ, g.K, g.N};
-		if (patch) {
-			const PlaneTma qx{x, HW, g.C, g.N, g.W}, qdy{dy, PQ, g.K, g.N, g.Q};
-			st = launch(p, dtype, bn, MODE_K_PATCH_TMA, MODE_K_PATCH_TMA, false, g.G, nullptr, pz_stream(stream), &qx, &qdy);
-		} else
 		if (tma_x)
 			st = launch(p, dtype, bn, MODE_K_POS_TMA, MODE_K_POS_TMA, false, g.G, nullptr, pz_stream(stream), &px, &pdy);
 		else if (tma_dy && !dense_x && tl >= 2 && RS <= 31)

@@ -134,32 +134,6 @@ static int make_plane_tmap(CUtensorMap* tmap, int dtype, const PlaneTma& t, int 
 	return PZ_OK;
 }
 
-// 4-d tensor map over planes [images][chans][height][width] (MODE_K_PATCH_TMA): box = a run of one k-block of columns of one row of
-// `rows` channels of one image -- 128 bytes per channel, 128-byte swizzle: the K-major tile again, k running along the row.
-// Coordinates may lie outside the plane (a tap shift into the padding): those elements read as zero.
-static int make_patch_tmap(CUtensorMap* tmap, int dtype, const PlaneTma& t, int rows)
-{
-	const size_t es = dtype == PZ_F32 ? 4 : 2;
-	const CUtensorMapDataType dt = dtype == PZ_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
-								   : (dtype == PZ_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
-	PZ_REQUIRE(t.ptr != nullptr && ((uintptr_t)t.ptr & 15) == 0 && t.width > 0 && t.plane % t.width == 0 && (t.width * es) % 16 == 0 &&
-			   t.chans >= rows && rows <= 256, "bad patch TMA source");
-	TmapEncodeFn encode = tmap_encoder();
-	PZ_REQUIRE(encode != nullptr, "cuTensorMapEncodeTiled is not available in this driver");
-	cuuint64_t dims[4] = {(cuuint64_t)t.width, (cuuint64_t)(t.plane / t.width), (cuuint64_t)t.chans, (cuuint64_t)t.images};
-	cuuint64_t strides[3] = {(cuuint64_t)t.width * es, (cuuint64_t)t.plane * es, (cuuint64_t)t.plane * (cuuint64_t)t.chans * es};
-	cuuint32_t box[4] = {(cuuint32_t)elems_per_kblock(dtype), 1, (cuuint32_t)rows, 1};
-	cuuint32_t estr[4] = {1, 1, 1, 1};
-	memset(tmap, 0, sizeof(*tmap));
-	CUresult r = encode(tmap, dt, 4, (void*)t.ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-						CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-	if (r != CUDA_SUCCESS) {
-		pz_set_error(PZ_ERR_CUDA, "cuTensorMapEncodeTiled (patches) failed (%d)", (int)r);
-		return PZ_ERR_CUDA;
-	}
-	return PZ_OK;
-}
-
 // 2-d tensor map over the prepared filter: rows of kpad elements, box = one k-block x bn rows, 128-byte swizzle
 int make_filter_tmap(CUtensorMap* tmap, int dtype, const TmaSource& tma, int bn)
 {
@@ -199,16 +173,17 @@ int launch(GemmParams& p, int dtype, int bn, int amode, int bmode, bool cdiv, in
 		p.debug_skip = skip;
 	}
 	p.tiles_m = (int)pz_cdiv(M, BM);
-	p.img_tiles = 0;
-	p.fd_img_tiles = make_fastdiv(1);
+	p.img_chunks = p.total_chunks = 0;
+	p.fd_img_chunks = make_fastdiv(1);
 	if (amode == MODE_MN_TMA) {
-		// row tiles that do not straddle images (the boxes of the activation tensor map are per image)
+		// rows in chunks of 32 positions of one image (the boxes of the activation tensor map are per image), 4 chunks per tile
 		PZ_REQUIRE(planeA != nullptr && planeA->plane * planeA->images == M && dtype == PZ_F32 && groups == 1 && p.E.md12.d == (uint32_t)planeA->plane,
 				   "bad MN-major TMA operand");
-		p.img_tiles = (int)pz_cdiv(planeA->plane, BM);
-		p.fd_img_tiles = make_fastdiv((uint32_t)p.img_tiles);
-		PZ_REQUIRE(planeA->images * (long long)p.img_tiles < (1ll << 31), "tile grid too large");
-		p.tiles_m = (int)(planeA->images * p.img_tiles);
+		p.img_chunks = (int)pz_cdiv(planeA->plane, 32);
+		p.fd_img_chunks = make_fastdiv((uint32_t)p.img_chunks);
+		PZ_REQUIRE(planeA->images * (long long)p.img_chunks < (1ll << 31), "tile grid too large");
+		p.total_chunks = (int)(planeA->images * p.img_chunks);
+		p.tiles_m = (int)pz_cdiv(p.total_chunks, BM / 32);
 	}
 	p.tiles_n = (int)pz_cdiv(N, bn);
 	p.groups = groups;
@@ -230,13 +205,6 @@ int launch(GemmParams& p, int dtype, int bn, int amode, int bmode, bool cdiv, in
 	memset(&tmapA, 0, sizeof(tmapA));
 	if (amode == MODE_MN_TMA) {
 		int st = make_plane_tmap(&tmapA, dtype, *planeA, BK, true);
-		if (st != PZ_OK) return st;
-	}
-	if (amode == MODE_K_PATCH_TMA) {
-		PZ_REQUIRE(bmode == MODE_K_PATCH_TMA && planeA != nullptr && planeB != nullptr && groups == 1 && (p.pt_cb == 64 || p.pt_cb == 128),
-				   "bad patch TMA operands");
-		int st = make_patch_tmap(&tmapA, dtype, *planeA, p.pt_cb);
-		if (st == PZ_OK) st = make_patch_tmap(&tmap, dtype, *planeB, bn);
 		if (st != PZ_OK) return st;
 	}
 	if (amode == MODE_K_POS_TMA || bmode == MODE_K_POS_TMA) {
@@ -278,7 +246,6 @@ int launch(GemmParams& p, int dtype, int bn, int amode, int bmode, bool cdiv, in
 	PZ_INST_BN(MODE_K_POS_TAP, MODE_K_POS_VEC, true, false)
 	PZ_INST_BN3(MODE_MN_TMA, MODE_TMA, false, false)           // 1x1 fprop / dgrad over 16-byte aligned planes: MN-major A by the copy engine
 	PZ_INST_BN(MODE_K_POS_TMA, MODE_K_POS_TMA, false, false)   // wgrad of a 1x1 filter: both operands by the copy engine (3-d tensor maps)
-	PZ_INST_BN(MODE_K_PATCH_TMA, MODE_K_PATCH_TMA, false, false)
 	PZ_INST_BN(MODE_K_POS_TAP, MODE_K_POS_TMA, false, false)   // wgrad: dy by the copy engine next to a tap-gathered x
 	// ---- half / bfloat16 storage
 	PZ_INST_BN3(MODE_MN_CHAN, MODE_TMA, false, true)
@@ -292,7 +259,6 @@ int launch(GemmParams& p, int dtype, int bn, int amode, int bmode, bool cdiv, in
 	PZ_INST_BN(MODE_K_POS_TAP, MODE_K_POS_DENSE, true, true)
 	PZ_INST_BN(MODE_K_POS_DENSE, MODE_K_POS_DENSE, false, true)
 	PZ_INST_BN(MODE_K_POS_TMA, MODE_K_POS_TMA, false, true)
-	PZ_INST_BN(MODE_K_PATCH_TMA, MODE_K_PATCH_TMA, false, true)   // wgrad of a stride-1 filter: patches of x (tap-shifted) and dy by 4-d tensor maps
 	PZ_INST_BN(MODE_K_POS_TAP, MODE_K_POS_TMA, false, true)
 #undef PZ_INST_BN3
 #undef PZ_INST_BN

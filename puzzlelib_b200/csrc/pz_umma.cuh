@@ -116,7 +116,7 @@ __device__ __forceinline__ void split3(uint32_t x, const FastDiv& d12, const Fas
 // computed once, the per-element work is one predicated load + one tf32 rounding.
 enum { MODE_K_GENERAL = 0, MODE_K_SIMPLE = 1, MODE_MN_GENERAL = 2, MODE_MN_SIMPLE = 3, MODE_MN_TAP = 4, MODE_K_TAP = 5,
 	   MODE_K_DENSE = 6, MODE_TMA = 7, MODE_MN_CHAN = 8, MODE_K_POS_TAP = 9, MODE_K_POS_DENSE = 10, MODE_MN_VEC = 11,
-	   MODE_K_POS_VEC = 12, MODE_K_POS_TMA = 13, MODE_MN_TMA = 14, MODE_K_PATCH_TMA = 15 };
+	   MODE_K_POS_VEC = 12, MODE_K_POS_TMA = 13, MODE_MN_TMA = 14 };
 
 struct Operand {
 	const void* ptr;             // float or 16-bit (half / bfloat16) elements; all strides below are in ELEMENTS
@@ -170,15 +170,10 @@ struct GemmParams {
 	FastDiv fd_tiles_n, fd_tiles_m, fd_splits;   // the same counts as magic-number divisors (the decode runs per tile per warp)
 	int tma_rows_per_group;      // MODE_TMA: row offset of group g in the prepared filter = g * tma_rows_per_group
 	int ab_bf16;                 // 16-bit operands: 0 = half, 1 = bfloat16 (selects the tcgen05 input format)
-	// MODE_MN_TMA: row tiles do not straddle images: m_tile = image * img_tiles + block of BM positions of that image
-	int img_tiles;
-	FastDiv fd_img_tiles;
-	// MODE_K_PATCH_TMA (wgrad of a stride-1 filter, both operands through 4-d tensor maps): k-block = image * kbpi + patch, a patch
-	// is a run of one k-block of output columns of one output row (the box must fill its 128-byte swizzle span: a box of 32-byte rows
-	// overran its tile); A rows are ordered (tap, channel), a row tile is 128 / pt_cb boxes of pt_cb channels of one tap, fetched
-	// at the patch origin shifted by the tap (positions outside the image read as zero = padding)
-	int pt_cb, pt_chans, pt_taps, pt_padh, pt_padw;
-	FastDiv pt_fd_pw, pt_fd_chans, pt_fd_s;      // patches per output row, channels, filter width
+	// MODE_MN_TMA: rows come in chunks of 32 positions of one image (one TMA box, one epilogue warp each); chunk = image *
+	// img_chunks + block of 32 positions (the last chunk of an image may be partly past the plane); a row tile is 4 consecutive chunks
+	int img_chunks, total_chunks;
+	FastDiv fd_img_chunks;
 	int debug_skip;              // PZ_DEBUG_SKIP (timing experiments only, results are wrong): 1 no epilogue stores, 2 no filter TMA, 4 no MMAs
 	double alg_flops, alg_bytes; // host-side bookkeeping for the profiler (algorithmic work of this launch)
 };
@@ -1305,10 +1300,9 @@ template <int ROWS, bool WIDE, bool H16> struct ProducerSel<ROWS, MODE_TMA, WIDE
 // MODE_K_POS_TMA: the KPosDense operand over 16-byte aligned planes, fetched by the copy engine through a 3-d tensor map
 // (positions, channels, images): one box of 32 positions x ROWS channels of one image per k-block, zero-filled past the plane
 template <int ROWS, bool WIDE, bool H16> struct ProducerSel<ROWS, MODE_K_POS_TMA, WIDE, H16> { using type = TmaProducer<ROWS>; };
-template <int ROWS, bool WIDE, bool H16> struct ProducerSel<ROWS, MODE_K_PATCH_TMA, WIDE, H16> { using type = TmaProducer<ROWS>; };
 // MODE_MN_TMA: the activation operand of a 1x1 / stride-1 convolution over 16-byte aligned planes, fetched as it lies in memory
 // (positions contiguous = M-major) by four boxes of 32 positions x 32 channels per k-block; the MMA reads it through an MN-major
-// descriptor, so nobody transposes it
+// descriptor, so nobody transposes it.  A box never leaves its image, a tile may: rows are chunked per image (GemmParams::img_chunks)
 template <int ROWS, bool WIDE> struct ProducerSel<ROWS, MODE_MN_TMA, WIDE, false> { using type = TmaProducer<ROWS>; };
 template <int ROWS, bool WIDE> struct ProducerSel<ROWS, MODE_MN_CHAN, WIDE, false> { using type = MnChanProducer<ROWS, WIDE>; };
 template <int ROWS, bool WIDE> struct ProducerSel<ROWS, MODE_K_POS_TAP, WIDE, false> { using type = KPosTapProducer<ROWS, WIDE>; };
@@ -1375,14 +1369,6 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, int 
 	asm volatile(
 		"cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
 		::"r"(dst), "l"((unsigned long long)tmap), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
-		: "memory");
-}
-
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, int c0, int c1, int c2, int c3, uint32_t bar)
-{
-	asm volatile(
-		"cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
-		::"r"(dst), "l"((unsigned long long)tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
 		: "memory");
 }
 
@@ -1550,8 +1536,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) umma_gemm_kernel(const __grid_con
 	constexpr bool B_TMA = BMODE == MODE_TMA;
 	constexpr bool A_KPT = AMODE == MODE_K_POS_TMA, B_KPT = BMODE == MODE_K_POS_TMA;   // plane operands through the copy engine
 	constexpr bool A_MNT = AMODE == MODE_MN_TMA;
-	constexpr bool AB_PATCH = AMODE == MODE_K_PATCH_TMA;
-	static_assert(AB_PATCH == (BMODE == MODE_K_PATCH_TMA), "MODE_K_PATCH_TMA: both operands");
 	static_assert(!A_MNT || !H16, "MODE_MN_TMA: float tensors only");
 	extern __shared__ uint8_t smem_raw[];
 	const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -1568,7 +1552,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) umma_gemm_kernel(const __grid_con
 	if (warp == MMA_WARP) {
 		if (lane == 0) {
 			for (int s = 0; s < C::STAGES; s++) {
-				mbar_init(bar_full + 8 * s, NPROD_WARPS + (B_TMA ? 1 : 0) + (A_KPT ? 1 : 0) + (B_KPT ? 1 : 0) + (A_MNT ? 1 : 0) + (AB_PATCH ? 1 : 0));
+				mbar_init(bar_full + 8 * s, NPROD_WARPS + (B_TMA ? 1 : 0) + (A_KPT ? 1 : 0) + (B_KPT ? 1 : 0) + (A_MNT ? 1 : 0));
 				mbar_init(bar_empty + 8 * s, 1);
 			}
 			for (int a = 0; a < 2; a++) {
@@ -1676,40 +1660,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) umma_gemm_kernel(const __grid_con
 					}
 				}
 			}
-			if (AB_PATCH) {
-				if (gw == 0 && lane == 0) {
-					// k-block -> (image, output row, run of BKE output columns)
-					const uint32_t img = fdiv((uint32_t)lkb, p.A.kbdiv);
-					const uint32_t pb = (uint32_t)lkb - img * p.A.kbdiv.d;
-					const uint32_t py = fdiv(pb, p.pt_fd_pw);
-					const int w0 = (int)(pb - py * p.pt_fd_pw.d) * BKE, h0 = (int)py;
-					// boxes of this row tile: pt_cb channels of one tap each (the last tile may hold fewer)
-					int nbox = 0;
-					#pragma unroll 1
-					for (int i = 0; i < BM / p.pt_cb; i++)
-						if ((uint32_t)(lw.m_tile * BM + i * p.pt_cb) < (uint32_t)(p.pt_taps * p.pt_chans)) nbox++;
-					mbar_arrive_expect_tx(bar_full + 8 * stage, (uint32_t)(nbox * p.pt_cb + BN) * 128u);
-					#pragma unroll 1
-					for (int i = 0; i < nbox; i++) {
-						const uint32_t mrow = (uint32_t)(lw.m_tile * BM + i * p.pt_cb);
-						const uint32_t tap = fdiv(mrow, p.pt_fd_chans);
-						const int c0 = (int)(mrow - tap * p.pt_fd_chans.d);
-						const uint32_t r = fdiv(tap, p.pt_fd_s);
-						const int sx = (int)(tap - r * p.pt_fd_s.d);
-						tma_load_4d(tileA + (uint32_t)(i * p.pt_cb) * 128u, &tmapA, w0 + sx - p.pt_padw, h0 + (int)r - p.pt_padh, c0, (int)img,
-									bar_full + 8 * stage);
-					}
-					tma_load_4d(tileA + BM * 128, &tmapB, w0, h0, lw.n_tile * BN, (int)img, bar_full + 8 * stage);
-				}
-			}
 			if (A_MNT) {
 				if (gw == 0 && lane == 0) {
-					const uint32_t img = fdiv((uint32_t)lw.m_tile, p.fd_img_tiles);
-					const int pix0 = (int)((uint32_t)lw.m_tile - img * (uint32_t)p.img_tiles) * BM;
-					mbar_arrive_expect_tx(bar_full + 8 * stage, BM * 128);
+					const int chunk0 = lw.m_tile * (BM / 32);
+					const int nch = min(BM / 32, p.total_chunks - chunk0);       // chunks past the last image are not fetched (nor stored)
+					mbar_arrive_expect_tx(bar_full + 8 * stage, (uint32_t)nch * 4096u);
 					#pragma unroll
-					for (int j = 0; j < BM / 32; j++)
-						tma_load_3d(tileA + j * 4096, &tmapA, pix0 + 32 * j, lkb * BKE, (int)img, bar_full + 8 * stage);
+					for (int j = 0; j < BM / 32; j++) {
+						if (j < nch) {
+							const uint32_t img = fdiv((uint32_t)(chunk0 + j), p.fd_img_chunks);
+							const int pix0 = (int)((uint32_t)(chunk0 + j) - img * (uint32_t)p.img_chunks) * 32;
+							tma_load_3d(tileA + j * 4096, &tmapA, pix0, lkb * BKE, (int)img, bar_full + 8 * stage);
+						}
+					}
 				}
 			}
 			prodA.store(tileA, va);
@@ -1805,10 +1768,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) umma_gemm_kernel(const __grid_con
 			bool mvalid = m < E.M;
 			int m0, m1, m2;
 			if (A_MNT) {
-				// image-aligned tiles over dense planes: row = (image, position), positions contiguous in the output too
-				const uint32_t img = fdiv((uint32_t)w.m_tile, p.fd_img_tiles);
-				const int pix = (int)((uint32_t)w.m_tile - img * (uint32_t)p.img_tiles) * BM + lg * 32 + lane;
-				mvalid = pix < (int)E.md12.d;
+				// chunked rows over dense planes: this warp's 32 rows are one chunk = 32 positions of one image, contiguous in the output too
+				const int chunk = w.m_tile * (BM / 32) + lg;
+				const uint32_t img = fdiv((uint32_t)chunk, p.fd_img_chunks);
+				const int pix = (int)((uint32_t)chunk - img * (uint32_t)p.img_chunks) * 32 + lane;
+				mvalid = chunk < p.total_chunks && pix < (int)E.md12.d;
 				m0 = (int)img; m1 = 0; m2 = mvalid ? pix : 0;
 				m = (int)img * (int)E.md12.d + m2;
 			} else
@@ -1873,7 +1837,6 @@ struct TmaSource {
 struct PlaneTma {
 	const void* ptr;
 	long long plane, chans, images;
-	long long width = 0;         // MODE_K_PATCH_TMA: planes are (plane / width) rows of `width` elements
 };
 int launch(GemmParams& p, int dtype, int bn, int amode, int bmode, bool cdiv, int groups, const TmaSource* tma, cudaStream_t stream,
 		   const PlaneTma* planeA = nullptr, const PlaneTma* planeB = nullptr);
