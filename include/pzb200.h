@@ -260,6 +260,14 @@ int pz_bn_fwd_infer(int dtype, const void* x, void* y, int64_t N, int64_t C, int
 int pz_bn_bwd(int dtype, const void* x, const void* dy, void* dx, int64_t N, int64_t C, int64_t S,
 			  const float* scale, const float* save_mean, const float* save_invvar, float* dscale, float* dbias,
 			  void* stream);
+/* pz_bn_bwd followed by the parameter-gradient accumulation of BatchNormND.accGradParams (Modules/BatchNormND.py:74-83: two
+ * addVectorToVector launches, Backend/Blas.py:43-58 -> ElementWise.py:1030) in the same pass:
+ *   scale_acc = scale_alpha * dscale + scale_beta * scale_acc,  bias_acc = bias_alpha * dbias + bias_beta * bias_acc
+ * (same bits as the two launches; either accumulator may be NULL; they must not overlap another tensor of the call) */
+int pz_bn_bwd_acc(int dtype, const void* x, const void* dy, void* dx, int64_t N, int64_t C, int64_t S,
+				  const float* scale, const float* save_mean, const float* save_invvar, float* dscale, float* dbias,
+				  float* scale_acc, float scale_alpha, float scale_beta, float* bias_acc, float bias_alpha, float bias_beta,
+				  void* stream);
 
 /* ---------------------------------------------------------------- pooling
  * replaces cudnnPoolingForward/Backward (CuDnnPool.c:81,171) -- 2-D; 1-D is H=1 */

@@ -557,6 +557,13 @@ class DnnContext:
 		scalegrad = GPUArray(scale.shape, _f32, allocator=allocator) if scalegrad is None else _checkOut(scalegrad, scale.shape, _f32)
 		bgrad = GPUArray(scale.shape, _f32, allocator=allocator) if bgrad is None else _checkOut(bgrad, scale.shape, _f32)
 
+		tensors = (data, grad, out, scale, savemean, saveinvvar, scalegrad, bgrad)
+		if data.nbytes >= gpuarray.DEFER_MIN_BYTES and all(t.contiguous for t in tensors):
+			# held back: the module's two parameter-gradient accumulations that follow ride on the pass (gpuarray.DeferredBatchNormBackward)
+			driver.flushDeferred()
+			driver.deferred = gpuarray.DeferredBatchNormBackward(dtypeCode(data.dtype), data, grad, out, (N, C, S), (scale, savemean, saveinvvar),
+																 scalegrad, bgrad)
+			return out, scalegrad, bgrad
 		check(lib.pz_bn_bwd(dtypeCode(data.dtype), data.ptr, grad.ptr, out.ptr, N, C, S, scale.ptr, savemean.ptr, saveinvvar.ptr,
 							scalegrad.ptr, bgrad.ptr, None))
 		return out, scalegrad, bgrad
@@ -1484,6 +1491,8 @@ class B200Backend:
 			if driver.gradientWriteHook is not None:
 				driver.gradientWriteHook(out)
 			if slc is None:
+				if driver.deferred is not None and gpuarray.accumulateAfterBatchNormBackward(out, x, alpha, y, beta):
+					return      # rides on the pending batch-norm backward pass (BatchNormND.py:74-83)
 				check(lib.pz_axpby(dt, out.ptr, x.ptr, float(alpha), y.ptr, float(beta), out.size, None))
 			else:
 				check(lib.pz_axpby_slice(dt, out.ptr, x.ptr, float(alpha), y.ptr, float(beta), out.size, *slc, None))

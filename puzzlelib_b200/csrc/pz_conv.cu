@@ -352,10 +352,11 @@ void set_staged(Epilogue& E, int dtype)
 // PZ_TMA_WGRAD: 0 = producers gather every wgrad operand, 1 = both operands of a 1x1 / stride-1 wgrad over aligned planes come
 // through the copy engine (MODE_K_POS_TMA: 3-d tensor maps, no producer instructions), 2 (default) = also the dy operand next to a
 // tap-gathered x.  Measured (N = 64): 1x1 wgrad over 28 x 28 planes 0.052 -> 0.028 ms (4.6 TB/s), over 14 x 14 planes 0.040 -> 0.031 ms,
-// 3x3 wgrad 0.071 -> 0.060 / 0.080 -> 0.065 ms; ResNet-50 step 16.64 -> 15.99 ms.  The copy engine hands the tensor core raw float
-// bits -- the tf32 MMA ignores the low 13 mantissa bits -- where the producers round to nearest: a copied operand is truncated,
-// which shrinks the result by 3.5e-4 per copied operand on average (max error against a float64 contraction 8.5e-4 / 4.8e-4 of
-// the largest element with two / one copied operands, 3.3e-4 with none; tools/check_tma_wgrad.py).
+// 3x3 wgrad 0.071 -> 0.060 / 0.080 -> 0.065 ms; ResNet-50 step 16.64 -> 15.99 ms.  The copy engine hands over raw float bits and the
+// tf32 MMA ignores the low 13 mantissa bits: left alone, a copied operand is truncated, which shrinks the result by 3.5e-4 per
+// copied operand on average (max error against a float64 contraction 8.5e-4 with two copied operands -- one teacher-forced
+// ResNet-50 layer crossed 1e-3).  The producer group therefore rounds the landed tile in place (umma_gemm_kernel, FIXUP) to the
+// value cvt.rna gives the gathering producers: 3.3e-4 again (tools/check_tma_wgrad.py).
 int tma_wgrad_level()
 {
 	static const int level = [] { const char* e = getenv("PZ_TMA_WGRAD"); return e ? atoi(e) : 2; }();
@@ -375,10 +376,10 @@ bool kpos_tma_ok(const Operand& op, const void* ptr, int chans, int rows, int gr
 // would be legal.  That is why only 1x1 filters (and the un-shifted dy operand of any wgrad) take the tensor-map paths.
 // PZ_TMA_FPROP: the activation operand of 1x1 / stride-1 fprop and dgrad over dense, 16-byte aligned planes comes through the copy
 // engine in its memory order and is multiplied through an MN-major descriptor (MODE_MN_TMA).  0 = off, 1 (default) = planes of at
-// least 512 positions, 2 = every legal plane.  The operand is truncated to tf32 by the tensor core (see PZ_TMA_WGRAD; max error
-// against a float64 contraction 6.6e-4 of the largest element, 3.8e-4 with the rounding producers).  Row tiles are per image
-// there, so 14 x 14 planes fill 196 of 256 rows and lose what the copy engine gains: ResNet-50 step 15.91 (off) / 15.80 (1) /
-// 15.84 ms (2), family of the 1x1 convolutions 5.12 / 5.01 / 5.05 ms (profiles/r02_tma_operands.txt).
+// least 512 positions, 2 = every legal plane.  The landed tile is rounded to tf32 in place like the wgrad operands (see
+// PZ_TMA_WGRAD).  Rows come in chunks of 32 positions of one image, so a 14 x 14 plane fills 196 of 224 rows and loses what the
+// copy engine gains: ResNet-50 step 15.91 (off) / 15.80 (1) / 15.84 ms (2), family of the 1x1 convolutions 5.12 / 5.01 / 5.05 ms
+// (profiles/r02_tma_operands.txt).
 int tma_fprop_level()
 {
 	static const int level = [] { const char* e = getenv("PZ_TMA_FPROP"); return e ? atoi(e) : 1; }();

@@ -343,12 +343,35 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_stats_kernel(const T* __restr
 }
 
 // ------------------------------------------------------------------------------------------ backward apply
+// Parameter-gradient accumulation riding on the backward pass (pz_bn_bwd_acc): acc = alpha * grad + beta * acc per channel, with
+// the arithmetic of the elementwise kernel it replaces (Axpby in pz_elementwise.cu, built with --use_fast_math: y * beta rounded
+// and flushed, then one fused multiply-add, flushed) -- the results are the same bits as two `addKer` launches after the pass.
+struct BnAcc {
+	float* scale_acc;
+	float* bias_acc;
+	float scale_alpha, scale_beta, bias_alpha, bias_beta;
+};
+__device__ __forceinline__ float axpby_ftz(float x, float alpha, float y, float beta)
+{
+	float t, r;
+	asm("mul.rn.ftz.f32 %0, %1, %2;" : "=f"(t) : "f"(y), "f"(beta));
+	asm("fma.rn.ftz.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(x), "f"(alpha), "f"(t));
+	return r;
+}
+__device__ __forceinline__ void bn_param_grads(const BnAcc& a, int c, float dsc, float dbi, float* dscale, float* dbias)
+{
+	dscale[c] = dsc;
+	dbias[c] = dbi;
+	if (a.scale_acc) a.scale_acc[c] = axpby_ftz(dsc, a.scale_alpha, a.scale_acc[c], a.scale_beta);
+	if (a.bias_acc) a.bias_acc[c] = axpby_ftz(dbi, a.bias_alpha, a.bias_acc[c], a.bias_beta);
+}
+
 // dx = c1*dy - c2 - (x - mean)*c3 with c1 = scale*invstd, c2 = c1*sum(dy)/m, c3 = c1*invstd^2*sum(dy*(x-mean))/m
 template <typename T, int VEC>
 __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx,
 																Slab g, const float* __restrict__ sums, const float* __restrict__ scale,
 																const float* __restrict__ save_mean, const float* __restrict__ save_invvar,
-																float* dscale, float* dbias, float count, float* zero_ptr, int zero_n)
+																float* dscale, float* dbias, float count, float* zero_ptr, int zero_n, BnAcc acc)
 {
 	constexpr int UNR = kRowUnroll / 2;
 	for (int i = blockIdx.x * kThreads + threadIdx.x; i < zero_n; i += gridDim.x * kThreads) zero_ptr[i] = 0.0f;
@@ -374,7 +397,7 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(const T* __restr
 					c1[e] = scale[c] * invstd;
 					c2[e] = c1[e] * tdy / count;
 					c3[e] = c1[e] * dsc / count * invstd;
-					if (rg == 0 && j + e == (uint32_t)c * g.S) { dscale[c] = dsc; dbias[c] = tdy; }
+					if (rg == 0 && j + e == (uint32_t)c * g.S) bn_param_grads(acc, c, dsc, tdy, dscale, dbias);
 				}
 			}
 		}
@@ -944,7 +967,7 @@ template <typename T, int VEC, int THREADS, bool BULK>
 __global__ void __launch_bounds__(THREADS) bn_bwd_cluster_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx,
 																  ClusterGeo g, const float* __restrict__ scale,
 																  const float* __restrict__ save_mean, const float* __restrict__ save_invvar,
-																  float* dscale, float* dbias)
+																  float* dscale, float* dbias, BnAcc acc)
 {
 	extern __shared__ uint4 stash[];                 // [2][stash_slots]: x planes, then dy planes
 	__shared__ double red[2 * THREADS / 32 + 2];
@@ -1037,7 +1060,7 @@ __global__ void __launch_bounds__(THREADS) bn_bwd_cluster_kernel(const T* __rest
 
 	const float count = (float)g.N * (float)g.S;
 	const float dsc = s2 * invstd;               // sum(dy * xhat)
-	if (rank == 0 && threadIdx.x == 0) { dscale[c] = dsc; dbias[c] = s1; }
+	if (rank == 0 && threadIdx.x == 0) bn_param_grads(acc, c, dsc, s1, dscale, dbias);
 	const float c1 = scale[c] * invstd, c2 = c1 * s1 / count, c3 = c1 * dsc / count * invstd;
 
 	// ---- phase 2: shared memory -> dx = c1*dy - c2 - (x - mean)*c3 -> HBM
@@ -1390,7 +1413,7 @@ int fwd_infer(const void* x, void* y, int64_t N, int64_t C, int64_t S, const flo
 
 template <typename T>
 int bwd(const void* x, const void* dy, void* dx, int64_t N, int64_t C, int64_t S, const float* scale, const float* sm,
-		const float* siv, float* dscale, float* dbias, void* stream)
+		const float* siv, float* dscale, float* dbias, const BnAcc& acc, void* stream)
 {
 	constexpr int V = 16 / sizeof(T);
 	cudaStream_t s = pz_stream(stream);
@@ -1398,7 +1421,7 @@ int bwd(const void* x, const void* dy, void* dx, int64_t N, int64_t C, int64_t S
 	{
 		const ClusterPlan cp = make_cluster_plan({x, dy, dx}, N, C, S, sizeof(T), 2);
 		if (cp.ok) {
-#define PZ_BN_BWD_CLUSTER(TH, BK) launch_cluster(bn_bwd_cluster_kernel<T, V, TH, BK>, cp, s, (const T*)x, (const T*)dy, (T*)dx, cp.g, scale, sm, siv, dscale, dbias)
+#define PZ_BN_BWD_CLUSTER(TH, BK) launch_cluster(bn_bwd_cluster_kernel<T, V, TH, BK>, cp, s, (const T*)x, (const T*)dy, (T*)dx, cp.g, scale, sm, siv, dscale, dbias, acc)
 			if (cp.threads == 512) return cp.bulk ? PZ_BN_BWD_CLUSTER(512, true) : PZ_BN_BWD_CLUSTER(512, false);
 			return cp.bulk ? PZ_BN_BWD_CLUSTER(256, true) : PZ_BN_BWD_CLUSTER(256, false);
 #undef PZ_BN_BWD_CLUSTER
@@ -1414,10 +1437,10 @@ int bwd(const void* x, const void* dy, void* dx, int64_t N, int64_t C, int64_t S
 		const Slab g = make_slab(plan, N, C, S, c0, c1);
 		if (plan.vec == V) {
 			PZ_BN_LAUNCH(V, (bn_bwd_stats_kernel<T, V>), bins_per_block(V, g.S) * 2 * sizeof(float), (const T*)x, (const T*)dy, g, sm, sums);
-			PZ_BN_LAUNCH(V, (bn_bwd_apply_kernel<T, V>), 0, (const T*)x, (const T*)dy, (T*)dx, g, sums, scale, sm, siv, dscale, dbias, count, sp.clear, c0 == 0 ? sp.clear_n : 0);
+			PZ_BN_LAUNCH(V, (bn_bwd_apply_kernel<T, V>), 0, (const T*)x, (const T*)dy, (T*)dx, g, sums, scale, sm, siv, dscale, dbias, count, sp.clear, c0 == 0 ? sp.clear_n : 0, acc);
 		} else {
 			PZ_BN_LAUNCH(1, (bn_bwd_stats_kernel<T, 1>), bins_per_block(1, g.S) * 2 * sizeof(float), (const T*)x, (const T*)dy, g, sm, sums);
-			PZ_BN_LAUNCH(1, (bn_bwd_apply_kernel<T, 1>), 0, (const T*)x, (const T*)dy, (T*)dx, g, sums, scale, sm, siv, dscale, dbias, count, sp.clear, c0 == 0 ? sp.clear_n : 0);
+			PZ_BN_LAUNCH(1, (bn_bwd_apply_kernel<T, 1>), 0, (const T*)x, (const T*)dy, (T*)dx, g, sums, scale, sm, siv, dscale, dbias, count, sp.clear, c0 == 0 ? sp.clear_n : 0, acc);
 		}
 	}
 	PZ_LAUNCH_CHECK();
@@ -1496,7 +1519,21 @@ int pz_bn_bwd(int dtype, const void* x, const void* dy, void* dx, int64_t N, int
 {
 	int st = check_dims(N, C, S);
 	if (st != PZ_OK) return st;
-	PZ_DISPATCH_FLOAT(dtype, bwd<T>(x, dy, dx, N, C, S, scale, save_mean, save_invvar, dscale, dbias, stream));
+	const BnAcc none{nullptr, nullptr, 0.0f, 0.0f, 0.0f, 0.0f};
+	PZ_DISPATCH_FLOAT(dtype, bwd<T>(x, dy, dx, N, C, S, scale, save_mean, save_invvar, dscale, dbias, none, stream));
+}
+
+// pz_bn_bwd followed by  scale_acc = scale_alpha * dscale + scale_beta * scale_acc  and the same for the bias (either may be NULL):
+// what BatchNormND.accGradParams (Modules/BatchNormND.py:74-83) does with two addVectorToVector launches right after the pass.
+// The accumulators must not overlap any other tensor of the call.
+int pz_bn_bwd_acc(int dtype, const void* x, const void* dy, void* dx, int64_t N, int64_t C, int64_t S, const float* scale,
+				  const float* save_mean, const float* save_invvar, float* dscale, float* dbias, float* scale_acc, float scale_alpha,
+				  float scale_beta, float* bias_acc, float bias_alpha, float bias_beta, void* stream)
+{
+	int st = check_dims(N, C, S);
+	if (st != PZ_OK) return st;
+	const BnAcc acc{scale_acc, bias_acc, scale_alpha, scale_beta, bias_alpha, bias_beta};
+	PZ_DISPATCH_FLOAT(dtype, bwd<T>(x, dy, dx, N, C, S, scale, save_mean, save_invvar, dscale, dbias, acc, stream));
 }
 
 }  // extern "C"

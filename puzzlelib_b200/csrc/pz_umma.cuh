@@ -1544,6 +1544,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) umma_gemm_kernel(const __grid_con
 	const uint32_t bar_full = bars, bar_empty = bars + 8 * C::STAGES;
 	const uint32_t bar_accfull = bars + 16 * C::STAGES, bar_accempty = bar_accfull + 16;
 	const uint32_t tmem_slot = bar_accempty + 16;
+	const uint32_t bar_tma = tmem_slot + 16;                  // [STAGES], FIXUP only: the copied activation tiles have landed
+	static_assert(16 * C::STAGES + 48 + 8 * C::STAGES <= C::BAR_BYTES, "barrier area too small");
+	// Float operands that come through the copy engine would reach the tensor core un-rounded (the tf32 MMA ignores the low 13
+	// mantissa bits: truncation, -3.5e-4 per operand on average).  The producer group that owns the k-block therefore rounds the
+	// landed tile in place before it hands the stage to the MMA thread: bits + 0x1000, i.e. round to nearest, ties away from zero,
+	// once the hardware drops the low bits -- the value cvt.rna.tf32.f32 gives the gathering producers, so both routes multiply
+	// the same numbers.  16-bit operands are exact and skip this.
+	constexpr bool FIXUP = !H16 && (A_KPT || B_KPT || A_MNT);
 
 	const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
 	const int lane = threadIdx.x & 31;
@@ -1552,7 +1560,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) umma_gemm_kernel(const __grid_con
 	if (warp == MMA_WARP) {
 		if (lane == 0) {
 			for (int s = 0; s < C::STAGES; s++) {
-				mbar_init(bar_full + 8 * s, NPROD_WARPS + (B_TMA ? 1 : 0) + (A_KPT ? 1 : 0) + (B_KPT ? 1 : 0) + (A_MNT ? 1 : 0));
+				mbar_init(bar_full + 8 * s, NPROD_WARPS + (B_TMA ? 1 : 0) + (FIXUP ? 0 : (A_KPT ? 1 : 0) + (B_KPT ? 1 : 0) + (A_MNT ? 1 : 0)));
+				if (FIXUP) mbar_init(bar_tma + 8 * s, (A_KPT ? 1 : 0) + (B_KPT ? 1 : 0) + (A_MNT ? 1 : 0));
 				mbar_init(bar_empty + 8 * s, 1);
 			}
 			for (int a = 0; a < 2; a++) {
@@ -1650,13 +1659,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) umma_gemm_kernel(const __grid_con
 					// k-block -> (image, first position); rows = channels of the (only) group
 					const uint32_t img = fdiv((uint32_t)lkb, p.A.kbdiv);
 					const int pos = (int)((uint32_t)lkb - img * p.A.kbdiv.d) * BKE;
+					const uint32_t bar_act = (FIXUP ? bar_tma : bar_full) + 8 * stage;
 					if (A_KPT) {
-						mbar_arrive_expect_tx(bar_full + 8 * stage, BM * 128);
-						tma_load_3d(tileA, &tmapA, pos, lw.m_tile * BM, (int)img, bar_full + 8 * stage);
+						mbar_arrive_expect_tx(bar_act, BM * 128);
+						tma_load_3d(tileA, &tmapA, pos, lw.m_tile * BM, (int)img, bar_act);
 					}
 					if (B_KPT) {
-						mbar_arrive_expect_tx(bar_full + 8 * stage, BN * 128);
-						tma_load_3d(tileA + BM * 128, &tmapB, pos, lw.n_tile * BN, (int)img, bar_full + 8 * stage);
+						mbar_arrive_expect_tx(bar_act, BN * 128);
+						tma_load_3d(tileA + BM * 128, &tmapB, pos, lw.n_tile * BN, (int)img, bar_act);
 					}
 				}
 			}
@@ -1664,15 +1674,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) umma_gemm_kernel(const __grid_con
 				if (gw == 0 && lane == 0) {
 					const int chunk0 = lw.m_tile * (BM / 32);
 					const int nch = min(BM / 32, p.total_chunks - chunk0);       // chunks past the last image are not fetched (nor stored)
-					mbar_arrive_expect_tx(bar_full + 8 * stage, (uint32_t)nch * 4096u);
+					const uint32_t bar_act = (FIXUP ? bar_tma : bar_full) + 8 * stage;
+					mbar_arrive_expect_tx(bar_act, (uint32_t)nch * 4096u);
 					#pragma unroll
 					for (int j = 0; j < BM / 32; j++) {
 						if (j < nch) {
 							const uint32_t img = fdiv((uint32_t)(chunk0 + j), p.fd_img_chunks);
 							const int pix0 = (int)((uint32_t)(chunk0 + j) - img * (uint32_t)p.img_chunks) * 32;
-							tma_load_3d(tileA + j * 4096, &tmapA, pix0, lkb * BKE, (int)img, bar_full + 8 * stage);
+							tma_load_3d(tileA + j * 4096, &tmapA, pix0, lkb * BKE, (int)img, bar_act);
 						}
 					}
+				}
+			}
+			if (FIXUP) {
+				// the copied tiles of this stage: wait for them, round them in place (16 bytes per thread per step, conflict-free)
+				mbar_wait(bar_tma + 8 * stage, phase);
+				const uint32_t lo = (A_KPT || A_MNT) ? 0u : (uint32_t)BM * 128u;
+				const uint32_t hi = B_KPT ? (uint32_t)(BM + BN) * 128u : (uint32_t)BM * 128u;
+				#pragma unroll 4
+				for (uint32_t off = lo + (uint32_t)(gw * 32 + lane) * 16u; off < hi; off += NPROD * 16u) {
+					uint32_t a, b, c, d;
+					asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(tileA + off) : "memory");
+					sts128(tileA + off, a + 0x1000u, b + 0x1000u, c + 0x1000u, d + 0x1000u);
 				}
 			}
 			prodA.store(tileA, va);

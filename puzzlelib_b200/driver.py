@@ -169,6 +169,7 @@ _SIGNATURES = {
 	"pz_bn_fwd_train_relu": [c_int, _P, _P, _P, c_int64, c_int64, c_int64, _P, _P, _P, _P, _P, _P, c_double, c_double, _P],
 	"pz_bn_fwd_infer": [c_int, _P, _P, c_int64, c_int64, c_int64, _P, _P, _P, _P, c_double, _P],
 	"pz_bn_bwd": [c_int, _P, _P, _P, c_int64, c_int64, c_int64, _P, _P, _P, _P, _P, _P],
+	"pz_bn_bwd_acc": [c_int, _P, _P, _P, c_int64, c_int64, c_int64, _P, _P, _P, _P, _P, _P, c_float, c_float, _P, c_float, c_float, _P],
 	"pz_pool2d_fwd": [c_int, c_int, _P, _P, c_int64] + [c_int] * 10 + [_P],
 	"pz_pool2d_bwd": [c_int, c_int, _P, _P, _P, _P, c_int64] + [c_int] * 10 + [_P],
 	"pz_maxpool2d_mask_fwd": [_P, _P, _P, c_int64] + [c_int] * 10 + [_P],

@@ -78,6 +78,58 @@ class DeferredBatchNorm:
 		self.launch()
 
 
+class DeferredBatchNormBackward:
+	"""A batch-norm backward launch held back for up to two calls: BatchNormND.accGradParams (Modules/BatchNormND.py:74-83) follows it
+	with `addVectorToVector(scalegrad, acc, out=acc, alpha, beta)` and the same for the bias gradient -- two launches over C floats,
+	106 of them in a ResNet-50 step.  `accumulateAfterBatchNormBackward` absorbs them and the pass writes the accumulators itself
+	(`pz_bn_bwd_acc`, same bits); any other access to device memory launches the pass as it is."""
+	__slots__ = ["code", "x", "dy", "dx", "geometry", "params", "scalegrad", "bgrad", "sacc", "bacc"]
+
+	def __init__(self, code, x, dy, dx, geometry, params, scalegrad, bgrad):
+		self.code, self.x, self.dy, self.dx, self.geometry, self.params = code, x, dy, dx, geometry, params
+		self.scalegrad, self.bgrad, self.sacc, self.bacc = scalegrad, bgrad, None, None
+
+	def tensors(self):
+		return (self.x, self.dy, self.dx, self.scalegrad, self.bgrad) + tuple(self.params) + \
+			tuple(acc[0] for acc in (self.sacc, self.bacc) if acc is not None)
+
+	def flush(self):
+		ptrs = [p._ptr for p in self.params]          # scale, savemean, saveinvvar
+		head = (self.code, self.x._ptr, self.dy._ptr, self.dx._ptr, *self.geometry, *ptrs, self.scalegrad._ptr, self.bgrad._ptr)
+		if self.sacc is None and self.bacc is None:
+			check(lib.pz_bn_bwd(*head, None))
+			return
+		acc = []
+		for a in (self.sacc, self.bacc):
+			acc += [None, 0.0, 0.0] if a is None else [a[0]._ptr, a[1], a[2]]
+		check(lib.pz_bn_bwd_acc(*head, *acc, None))
+
+
+_NO_BN_ACC = bool(int(os.environ.get("PZ_NO_BN_ACC_FUSION", "0")))      # A/B switch for timing and for the bit-identity test
+
+
+def accumulateAfterBatchNormBackward(out, x, alpha, y, beta):
+	"""out = alpha * x + beta * y (the reference's addKer) where x is a parameter gradient of the pending batch-norm backward pass
+	and out is y, a float32 accumulator apart from every tensor of the pass: absorbed; True when it was"""
+	op = driver.deferred
+	if _NO_BN_ACC or type(op) is not DeferredBatchNormBackward or out._ptr != y._ptr or out.nbytes != y.nbytes or out.dtype != np.float32 or \
+			y.dtype != np.float32 or x.dtype != np.float32 or out.size != x.size or not (out.contiguous and x.contiguous and y.contiguous):
+		return False
+	if op.sacc is None and x._ptr == op.scalegrad._ptr and x.nbytes == op.scalegrad.nbytes:
+		slot = "sacc"
+	elif op.bacc is None and x._ptr == op.bgrad._ptr and x.nbytes == op.bgrad.nbytes:
+		slot = "bacc"
+	else:
+		return False
+	for other in op.tensors():
+		if not (out._ptr + out.nbytes <= other._ptr or other._ptr + other.nbytes <= out._ptr):
+			return False
+	setattr(op, slot, (out, float(alpha), float(beta)))
+	if op.sacc is not None and op.bacc is not None:
+		driver.flushDeferred()                        # nothing more to wait for
+	return True
+
+
 def reluAfterBatchNorm(out, inp):
 	"""relu(out, inp) where `inp` is the output of a pending batch-norm launch: fused; True when it did"""
 	op = driver.deferred

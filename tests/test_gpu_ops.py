@@ -1448,3 +1448,48 @@ def test_batchnorm_in_place_on_the_two_kernel_path(bnd):
 		assert relerr(got[0], want) < 2e-5
 		assert np.allclose(got[1].ravel(), mu, atol=1e-5) and np.allclose(got[2].ravel(), inv, rtol=1e-5)
 		assert np.allclose(got[3].ravel(), mu, atol=1e-5)                # factor 1: the running mean is the batch mean
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(64, 64, 28, 28), (32, 16, 55, 55), (8, 24, 112, 112), (64, 256, 7, 7)])
+@pytest.mark.parametrize("terms", ["both", "scale", "bias-first"])
+def test_batchnorm_backward_with_absorbed_parameter_gradient_accumulation(bnd, shape, terms):
+	"""BatchNormND.accGradParams (Modules/BatchNormND.py:74-83) follows the backward pass with two addVectorToVector launches over C
+	floats; the backend holds the pass back and lets them ride on it (pz_bn_bwd_acc).  Same bits as the separate launches -- on the
+	cluster kernels and on the two-kernel path (the 112 x 112 planes), whatever the order and number of accumulations."""
+	from puzzlelib_b200 import driver
+	rng = np.random.RandomState(sum(shape) + len(terms))
+	C = shape[1]
+	x, dy = rng.randn(*shape).astype(np.float32), rng.randn(*shape).astype(np.float32)
+	scale = rng.randn(C).astype(np.float32)
+	mu, inv = x.mean(axis=(0, 2, 3)).astype(np.float32), (1.0 / np.sqrt(x.var(axis=(0, 2, 3)) + 1e-5)).astype(np.float32)
+	acc0 = rng.randn(2, C).astype(np.float32)
+	alpha, beta = 0.75, 0.9
+	add = bnd.addKer(np.float32)
+
+	def run(fused):
+		gx, gdy, gscale, gmu, ginv = (G(bnd, a) for a in (x, dy, scale, mu, inv))
+		sacc, bacc = G(bnd, acc0[0]), G(bnd, acc0[1])
+		before = driver.launchCount()
+		dx, sg, bg = bnd.dnn.batchNormNdBackward(gdy, gx, gscale, gmu, ginv, 1e-5, allocator=bnd.memoryPool)
+		if not fused:
+			driver.flushDeferred()
+		if terms == "both":
+			add(sacc, sg, alpha, sacc, beta)
+			add(bacc, bg, alpha, bacc, beta)
+		elif terms == "scale":
+			add(sacc, sg, alpha, sacc, beta)
+		else:
+			add(bacc, bg, 1.0, bacc, 1.0)
+			add(sacc, sg, alpha, sacc, 0.0)
+		driver.flushDeferred()
+		launches = driver.launchCount() - before
+		return [a.get() for a in (dx, sg, bg, sacc, bacc)], launches
+
+	fused, nf = run(True)
+	plain, npl = run(False)
+	for a, b in zip(fused, plain):
+		assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+	assert nf == npl - (1 if terms == "scale" else 2)            # the accumulations launched nothing of their own
+	want = alpha * plain[1] + (beta if terms != "bias-first" else 0.0) * acc0[0]
+	assert np.allclose(fused[3], want, rtol=1e-5, atol=1e-5)

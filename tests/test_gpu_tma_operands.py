@@ -23,8 +23,9 @@ def run(script, env, *args):
 @pytest.mark.parametrize("level", ["0", "1", "2"])
 def test_wgrad_operands_through_the_copy_engine_float32(level):
 	worst = run("check_tma_wgrad.py", {"PZ_TMA_WGRAD": level}, "f32")
-	# the rounding producers stay near 3e-4; truncated (copied) operands add 3.5e-4 each
-	assert worst < (5e-4 if level == "0" else 1e-3)
+	# copied tiles are rounded in place to the value the gathering producers round to: every level stays near 3e-4
+	# (un-rounded, i.e. truncated by the tensor core, two copied operands reached 8.5e-4)
+	assert worst < 5e-4
 
 
 @pytest.mark.gpu
@@ -37,4 +38,4 @@ def test_wgrad_operands_through_the_copy_engine_float16(level):
 @pytest.mark.parametrize("level", ["0", "1", "2"])
 def test_mn_major_activation_operand_through_the_copy_engine(level):
 	worst = run("check_tma_fprop.py", {"PZ_TMA_FPROP": level})
-	assert worst < (5e-4 if level == "0" else 1e-3)
+	assert worst < 5e-4
