@@ -175,6 +175,7 @@ struct GemmParams {
 	int img_chunks, total_chunks;
 	FastDiv fd_img_chunks;
 	int debug_skip;              // PZ_DEBUG_SKIP (timing experiments only, results are wrong): 1 no epilogue stores, 2 no filter TMA, 4 no MMAs
+								 // 8 / 16: MODE_MN_TMA descriptor with LBO and SBO swapped / SBO 1024 (the variants that were tried)
 	double alg_flops, alg_bytes; // host-side bookkeeping for the profiler (algorithmic work of this launch)
 };
 
