@@ -1,5 +1,6 @@
 """1x1 / stride-1 fprop and dgrad over 16-byte aligned planes: error of the engine's result against a float64 contraction of the
-same inputs, for the PZ_TMA_FPROP level of this process (0 = producer gather, 1 / 2 = MN-major operand through the copy engine)."""
+same inputs, for the PZ_TMA_FPROP level of this process (0 = producer gather, 1 / 2 = MN-major operand through the copy engine,
+rounded to tf32 in place after it lands)."""
 import os, sys
 import numpy as np
 sys.path.insert(0, ".")

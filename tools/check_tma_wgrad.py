@@ -1,6 +1,7 @@
 """wgrad of 1x1 / 3x3 filters over 16-byte aligned planes: error of the engine's result against a float64 contraction of the same
 inputs, for the PZ_TMA_WGRAD level of this process (0 = producer gather with round-to-nearest tf32, 1 / 2 = copy-engine operands,
-raw float bits).  Run on the GPU box once per level."""
+whose landed fp32 tiles the producers round in place to the same values).  `slope-1` is the systematic shrink an un-rounded
+(truncated) operand would show: -3.5e-4 per operand.  Run on the GPU box once per level: check_tma_wgrad.py [f32|f16] [case]."""
 import os, sys
 import numpy as np
 sys.path.insert(0, ".")
